@@ -1,0 +1,219 @@
+/*
+ * pgmp.h -- C ABI of libpgmp.so, the B200-native (sm_100a) post-backbone grouping path of
+ * nibox/Pose-Estimation-with-Message-Passing-Networks.
+ *
+ * The reference has no FFI of its own (it is pure Python over torch / torch_geometric /
+ * torch_scatter / torch_cluster and one missing native module); each entry point below names the
+ * reference Python interface it stands behind (paths relative to the reference root).  The Python
+ * host (pgmp_b200/_native.py, ctypes) is the only caller; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer marked "device" is a CUDA device pointer on the
+ *     current device; the caller (torch) owns every buffer including workspaces (size queries
+ *     below); the library never frees or retains a pointer after the call returns.
+ *   - all work is enqueued on `stream` (a cudaStream_t); no entry point synchronises.
+ *   - return value: 0 = ok, negative = error (PGMP_ERR_*); text via pgmp_last_error()
+ *     (thread-local).  No exception crosses the ABI.  There is no CPU fallback.
+ */
+#ifndef PGMP_H_
+#define PGMP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGMP_VERSION 100
+
+#define PGMP_OK 0
+#define PGMP_ERR_INVALID (-1)     /* bad argument / unsupported combination */
+#define PGMP_ERR_CUDA (-2)        /* a CUDA runtime call failed */
+
+typedef void* pgmp_stream_t;      /* cudaStream_t */
+
+int pgmp_version(void);
+const char* pgmp_last_error(void);
+/* cumulative number of kernels this library has launched in this process (bench.py: gpu_launches) */
+uint64_t pgmp_kernel_launches(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Graph constructor -- replaces NaiveGraphConstructor.construct_graph(), inference branch
+ * (src/graph_constructor/ConstructGraph.py:46-68, 100-103, 206-249) including
+ * joint_det_from_scoremap (:1161-1196), non_maximum_suppression (src/Utils/Utils.py:15-20),
+ * cat_unique (:1199-1209), knn_mpn_graph (:363-368), fully_connected_mpn_graph (:376-381) and
+ * _construct_mpn_graph (:251-325).
+ *
+ * Two calls with ONE host read in between (the reference syncs ~4x per image):
+ *   pgmp_gc_detect : NMS + per-joint top-k / threshold candidates + candidate graph degrees
+ *                    -> device counts; the host reads `counts` to size the exact outputs
+ *   pgmp_gc_emit   : joint_det, scores, batch index, tags, node features, edge index, edge attr
+ * ---------------------------------------------------------------------------------------------- */
+
+#define PGMP_GRAPH_KNN 0
+#define PGMP_GRAPH_FULLY 1
+#define PGMP_EDGE_FEAT_POSITION 1
+#define PGMP_EDGE_FEAT_TYPE 2
+
+/* bits of counts[2 + 2*batch] (see pgmp_gc_detect) */
+#define PGMP_GC_FLAG_CAND_OVERFLOW 1   /* more NMS maxima than cand_capacity for some (image, joint) */
+#define PGMP_GC_FLAG_DET_OVERFLOW 2    /* more detections than max_det_per_type for some (image, joint) */
+#define PGMP_GC_FLAG_NODE_OVERFLOW 4   /* more nodes than max_nodes for some image */
+#define PGMP_GC_FLAG_TOO_FEW 8         /* no-threshold path: fewer than top_k positive maxima (CG.py:1193 assert) */
+
+typedef struct pgmp_gc_params {
+  int32_t batch, num_joints, height, width;  /* scoremaps [B,J,H,W] float32, contiguous */
+  int32_t pool_kernel;                       /* GC.POOL_KERNEL_SIZE, odd, <= 9 */
+  int32_t top_k;                             /* GC.HYBRID_K (threshold path) or 20 (CG.py:1185) */
+  int32_t use_threshold;                     /* 1: DETECT_THRESHOLD <= 1.5 (CG.py:28); 0: no-threshold path */
+  float threshold;                           /* GC.DETECT_THRESHOLD, must be > 0 */
+  int32_t graph_type;                        /* PGMP_GRAPH_* (GC.GRAPH_TYPE) */
+  int32_t knn_k;                             /* 50 (CG.py:365) */
+  int32_t edge_features;                     /* PGMP_EDGE_FEAT_* bit set (GC.EDGE_FEATURES_TO_USE) */
+  float norm_factor;                         /* max(H,W) if GC.NORM_NODE_DISTANCE else 1 (CG.py:311-314) */
+  int32_t cand_capacity;                     /* NMS-maxima list capacity per (image, joint) */
+  int32_t max_det_per_type;                  /* detections kept per (image, joint) */
+  int32_t max_nodes;                         /* nodes per image, multiple of 32 */
+  const float* scoremaps;                    /* device */
+  const float* mask;                         /* device [B,H,W] float32 crowd mask or NULL (GC.MASK_CROWDS) */
+  void* workspace;                           /* device, pgmp_gc_workspace_bytes() bytes, 256-B aligned */
+  uint64_t workspace_bytes;
+} pgmp_gc_params;
+
+uint64_t pgmp_gc_workspace_bytes(const pgmp_gc_params* p);
+
+/* counts: device int64[2 + 2*batch + 1] = { sum N, sum E, N_0..N_{B-1}, E_0..E_{B-1}, flags }. */
+int pgmp_gc_detect(const pgmp_gc_params* p, int64_t* counts, pgmp_stream_t stream);
+
+typedef struct pgmp_gc_outputs {
+  int64_t total_nodes, total_edges;          /* as read back from counts[0..1] */
+  const float* features;                     /* device [B,C,H,W] float32, arbitrary strides (elements) */
+  int64_t feat_stride_b, feat_stride_c, feat_stride_y, feat_stride_x;
+  int32_t channels;
+  const float* tagmaps;                      /* device [B,J,H,W] or [B,J,H,W,T] float32 contiguous */
+  int32_t tag_dim;                           /* T (1 for [B,J,H,W]) */
+  float* x;                                  /* [sum N, C]            CG.py:265,269 */
+  float* edge_attr;                          /* [sum E, F]            CG.py:305-325 */
+  int64_t* edge_index;                       /* [2, sum E] global ids CG.py:222-228 */
+  int64_t* joint_det;                        /* [sum N, 3] (x,y,type) CG.py:1180-1182 */
+  float* joint_scores;                       /* [sum N]               CG.py:1183 */
+  int64_t* batch_index;                      /* [sum N]               CG.py:207 */
+  float* joint_tags;                         /* [sum N, T]            CG.py:103 */
+} pgmp_gc_outputs;
+
+int pgmp_gc_emit(const pgmp_gc_params* p, const pgmp_gc_outputs* o, pgmp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Message-passing network -- replaces NodeClassificationMPNSimple.forward
+ * (src/Models/MessagePassingNetwork/NodeClassificationMPNSimple.py:62-97) with MPLayer
+ * (layers.py:32-86) or TypeAwareMPNLayer (layers.py:157-274), _make_mlp embeddings and heads
+ * (layers.py:8-29), eval-mode BatchNorm folded by the host.
+ * ---------------------------------------------------------------------------------------------- */
+
+#define PGMP_MAX_LAYERS 6
+#define PGMP_AGGR_ADD 0
+#define PGMP_AGGR_MAX 1
+#define PGMP_AGGR_MEAN 2
+#define PGMP_ATTN_NONE 0       /* AGGR_SUB "None" */
+#define PGMP_ATTN_SHARED 1     /* "node_edge_attn" */
+#define PGMP_ATTN_PER_TYPE 2   /* "node_edge_attn_per_type" */
+#define PGMP_PRECISION_FP32 0  /* SIMT fp32 everywhere (parity mode) */
+#define PGMP_PRECISION_TC 1    /* tcgen05 tensor-core message-passing steps, fp32 accumulation */
+
+/* One _make_mlp chain with eval BatchNorm folded into the following Linear. */
+typedef struct pgmp_mlp {
+  int32_t n_layers;
+  int32_t dims[PGMP_MAX_LAYERS + 1];   /* dims[0] = input width, dims[l+1] = output width of layer l */
+  int32_t relu[PGMP_MAX_LAYERS];       /* ReLU after layer l */
+  const float* wt[PGMP_MAX_LAYERS];    /* device [dims[l]][dims[l+1]] = Linear.weight transposed */
+  const float* bias[PGMP_MAX_LAYERS];  /* device [dims[l+1]] */
+  int32_t post_relu;                   /* END_WITH_RELU */
+  const float* post_scale;             /* trailing BatchNorm as scale/shift, or NULL */
+  const float* post_shift;
+} pgmp_mlp;
+
+typedef struct pgmp_mpn_params {
+  int64_t num_nodes, num_edges;
+  const float* x;                      /* device [N, node_in], strides in elements */
+  int64_t x_stride_n, x_stride_c;
+  const float* edge_attr;              /* device [E, edge_in] contiguous */
+  const int64_t* edge_index;           /* device [2, E]; row 0 = source j, row 1 = target i (layers.py:210) */
+  const int64_t* node_types;           /* device [N], already mapped by sum_node_types (utils.py:6-19) */
+
+  int32_t dim;                         /* NODE_FEATURE_DIM = EDGE_FEATURE_DIM = EDGE_FEATURE_HIDDEN, must be 64 */
+  int32_t per_type;                    /* 0: MPLayer, 1: TypeAwareMPNLayer */
+  int32_t num_types;                   /* aggregation slots per node (1 if !per_type) */
+  int32_t num_type_mlps;               /* message weight sets (17 if per_type else 1) */
+  int32_t skip, steps, aux_loss_steps; /* MPN.SKIP / STEPS / AUX_LOSS_STEPS */
+  int32_t aggr;                        /* PGMP_AGGR_* */
+  int32_t attn;                        /* PGMP_ATTN_* */
+  int32_t has_update_mlp;              /* per_type: always 1; agnostic: USE_NODE_UPDATE_MLP */
+  int32_t num_classes;                 /* width of the classification head */
+  int32_t precision;                   /* PGMP_PRECISION_* */
+
+  pgmp_mlp node_emb, edge_emb, edge_head, node_head, class_head;
+  /* message-passing layer, all device float32, input-major ("transposed") matrices.
+   * nd = dim * (skip ? 2 : 1) is the node-feature width seen by the layer. */
+  const float* w1_dst;                 /* [nd][dim]   mlp_edge.0 columns of x_i (target) */
+  const float* w1_src;                 /* [nd][dim]   mlp_edge.0 columns of x_j (source) */
+  const float* w1_e0;                  /* [dim][dim]  mlp_edge.0 columns of the initial edge feature (skip) or NULL */
+  const float* w1_e;                   /* [dim][dim]  mlp_edge.0 columns of the current edge feature */
+  const float* b1;                     /* [dim] */
+  const float* w2;                     /* [dim][dim]  mlp_edge.2 */
+  const float* b2;
+  const float* wm_x;                   /* [num_type_mlps][nd][dim]  mlp_node columns of x_i */
+  const float* wm_e;                   /* [num_type_mlps][dim][dim] mlp_node columns of the updated edge feature */
+  const float* bm;                     /* [num_type_mlps][dim] */
+  const float* wa;                     /* [dim][attn_cols] attn_net.0 (attn_cols = 1 or 17) or NULL */
+  const float* ba;                     /* [attn_cols] */
+  const float* wu;                     /* [num_types*dim][dim] update_mlp.0 or NULL */
+  const float* bu;
+
+  /* outputs: n_out = aux_loss_steps + 1 predictions (NodeClassificationMPNSimple.py:81-84) */
+  float* edge_logits;                  /* [n_out][E] */
+  float* node_logits;                  /* [n_out][N] */
+  float* class_logits;                 /* [n_out][N][num_classes] */
+  void* workspace;                     /* device, pgmp_mpn_workspace_bytes() bytes, 256-B aligned */
+  uint64_t workspace_bytes;
+} pgmp_mpn_params;
+
+uint64_t pgmp_mpn_workspace_bytes(const pgmp_mpn_params* p);
+int pgmp_mpn_forward(const pgmp_mpn_params* p, pgmp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Grouping tail -- replaces sigmoid/softmax (src/valid.py:109-111), the node threshold + subgraph
+ * of pred_to_ann (src/Utils/Utils.py:1448-1451), pred_to_person with CC_METHOD GAEC (:499-514),
+ * cluster_graph / extract_edge_matrix / cluster_andres_graph
+ * (src/Utils/correlation_clustering/correlation_clustering_utils.py:21-64, 99-136, 187-256; the
+ * GAEC solver itself is the reference's missing native andres_graph_wrapper) and the connected
+ * component labelling + per-type winner selection of graph_cluster_to_persons (:672-743).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pgmp_group_params {
+  int32_t batch, num_joints;
+  int64_t num_nodes, num_edges;
+  float node_threshold;                /* MPN.NODE_THRESHOLD */
+  const int64_t* node_offsets;         /* device [B+1] prefix sums of nodes per image */
+  const int64_t* edge_offsets;         /* device [B+1] prefix sums of edges per image (edges grouped by image) */
+  const int64_t* edge_index;           /* device [2,E] global ids */
+  const int64_t* joint_det;            /* device [N,3] */
+  const float* node_logits;            /* device [N] */
+  const float* edge_logits;            /* device [E] */
+  const float* class_logits;           /* device [N, num_joints] or NULL */
+  int64_t* person_labels;              /* out [N]: component id within the image, numbered by smallest node */
+  int32_t* num_components;             /* out [B] */
+  int32_t max_persons;                 /* capacity of `persons` per image */
+  double* persons;                     /* out [B][max_persons][num_joints][3] (x, y, score), Utils.py:709-721 */
+  int32_t* num_persons;                /* out [B] */
+  int32_t* mutants;                    /* out [B] (Utils.py:703-706) */
+  void* workspace;
+  uint64_t workspace_bytes;
+} pgmp_group_params;
+
+uint64_t pgmp_group_workspace_bytes(const pgmp_group_params* p);
+int pgmp_group_persons(const pgmp_group_params* p, pgmp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGMP_H_ */

@@ -1,0 +1,265 @@
+"""Drop-in for ``Models.MessagePassingNetwork`` of the reference
+(``src/Models/MessagePassingNetwork/__init__.py:27-73``): ``get_mpn_model(config)``.
+
+``NAME == "NodeClassificationMPN"`` (81 of the reference's 227 configs, both published
+checkpoints) is served by the CUDA path; the other 18 research variants are out of scope and
+raise ``NotImplementedError`` -- there is no silent PyTorch fallback.
+"""
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from ... import _native as nv
+from .layers import MPLayer, TypeAwareMPNLayer, make_mlp
+
+_NODE_TYPE_MAPS = {  # MessagePassingNetwork/utils.py:6-19
+    "left_right": [0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8],
+    "per_body_part": [0, 0, 0, 0, 0, 1, 1, 2, 3, 2, 3, 4, 5, 4, 5, 4, 5],
+}
+
+
+def sum_node_types(node_summary, node_types):
+    if node_summary == "not":
+        return node_types
+    if node_summary in _NODE_TYPE_MAPS:
+        return torch.tensor(_NODE_TYPE_MAPS[node_summary], device=node_types.device)[node_types]
+    raise NotImplementedError(node_summary)
+
+
+class _Packer:
+    """Lays tensors out in one flat fp32 device buffer (256-byte aligned pieces)."""
+
+    def __init__(self):
+        self.pieces, self.offset = [], 0
+
+    def add(self, t):
+        t = t.detach().to(torch.float32).contiguous().reshape(-1)
+        off = self.offset
+        self.pieces.append((off, t))
+        self.offset = (off + t.numel() + 63) // 64 * 64
+        return off
+
+    def finish(self, device):
+        flat = torch.zeros(max(self.offset, 64), dtype=torch.float32, device=device)
+        for off, t in self.pieces:
+            flat[off:off + t.numel()] = t.to(device)
+        return flat
+
+
+def _fold_mlp(seq, packer):
+    """``make_mlp`` chain -> list of (offset_Wt, offset_b, K, O, relu) with eval-mode BatchNorm folded into
+    the following Linear (BN(v) = s*v + t  =>  W(s*v + t) + b = (W diag s) v + (W t + b))."""
+    layers, pending, post = [], None, None
+    mods = list(seq)
+    for i, m in enumerate(mods):
+        if isinstance(m, nn.Linear):
+            W, b = m.weight.detach().float(), m.bias.detach().float()
+            if pending is not None:
+                s, t = pending
+                b = b + W @ t
+                W = W * s[None, :]
+                pending = None
+            layers.append([W, b, 0])
+        elif isinstance(m, nn.ReLU):
+            layers[-1][2] = 1
+        elif isinstance(m, nn.BatchNorm1d):
+            s = m.weight.detach().float() / torch.sqrt(m.running_var.detach().float() + m.eps)
+            t = m.bias.detach().float() - m.running_mean.detach().float() * s
+            if any(isinstance(n, nn.Linear) for n in mods[i + 1:]):
+                pending = (s, t)
+            else:
+                post = (s, t)
+        else:
+            raise NotImplementedError(type(m))
+    out = [(packer.add(W.t()), packer.add(b), W.shape[1], W.shape[0], r) for W, b, r in layers]
+    post_off = (packer.add(post[0]), packer.add(post[1])) if post is not None else None
+    return out, post_off
+
+
+def _mlp_struct(spec, base):
+    layers, post = spec
+    if len(layers) > nv.MAX_LAYERS:
+        raise NotImplementedError("MLP deeper than %d layers" % nv.MAX_LAYERS)
+    m = nv.Mlp()
+    m.n_layers = len(layers)
+    m.dims[0] = layers[0][2]
+    for l, (ow, ob, K, O, r) in enumerate(layers):
+        m.dims[l + 1], m.relu[l] = O, r
+        m.wt[l], m.bias[l] = base + 4 * ow, base + 4 * ob
+    if post is not None:
+        m.post_scale, m.post_shift = base + 4 * post[0], base + 4 * post[1]
+    return m
+
+
+class NodeClassificationMPNSimple(nn.Module):
+    """Same constructor, parameters (names and shapes) and ``forward`` contract as the reference class
+    (NodeClassificationMPNSimple.py:23-97); inference (``eval()``) runs in ``libpgmp.so``."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.use_skip_connections = config.SKIP
+        self.node_summary = config.NODE_TYPE_SUMMARY
+        if not (config.NODE_FEATURE_DIM == config.EDGE_FEATURE_DIM == config.EDGE_FEATURE_HIDDEN == 64):
+            raise NotImplementedError("NODE_FEATURE_DIM / EDGE_FEATURE_DIM / EDGE_FEATURE_HIDDEN must be 64 "
+                                      "(every NodeClassificationMPN config of the reference)")
+        if config.LATE_FUSION_POS:
+            raise NotImplementedError("LATE_FUSION_POS is out of scope")
+        self.aggr_type = config.AGGR_TYPE
+        if config.AGGR_TYPE == "agnostic":
+            self.mpn_node_cls = MPLayer(config.NODE_FEATURE_DIM, config.EDGE_FEATURE_DIM, config.EDGE_FEATURE_HIDDEN,
+                                        aggr=config.AGGR, skip=config.SKIP,
+                                        use_node_update_mlp=config.USE_NODE_UPDATE_MLP, edge_mlp=config.EDGE_MLP)
+        elif config.AGGR_TYPE == "per_type":
+            num_types = {"per_body_part": 6, "not": config.NUM_JOINTS, "left_right": 9}.get(self.node_summary)
+            self.mpn_node_cls = TypeAwareMPNLayer(config.NODE_FEATURE_DIM, config.EDGE_FEATURE_DIM,
+                                                  config.EDGE_FEATURE_HIDDEN, aggr=config.AGGR, skip=config.SKIP,
+                                                  edge_mlp=config.EDGE_MLP, num_types=num_types,
+                                                  aggr_sub=config.AGGR_SUB, update_type=config.UPDATE_TYPE)
+        else:
+            raise NotImplementedError("AGGR_TYPE=%r" % (config.AGGR_TYPE,))
+        if config.AGGR not in nv.AGGR:
+            raise NotImplementedError("AGGR=%r" % (config.AGGR,))
+        self.edge_embedding = make_mlp(config.EDGE_INPUT_DIM, config.EDGE_EMB.OUTPUT_SIZES, bn=config.EDGE_EMB.BN,
+                                       end_with_relu=config.EDGE_EMB.END_WITH_RELU)
+        self.node_embedding = make_mlp(config.NODE_INPUT_DIM, config.NODE_EMB.OUTPUT_SIZES, bn=config.NODE_EMB.BN,
+                                       end_with_relu=config.NODE_EMB.END_WITH_RELU)
+        self.edge_classification = make_mlp(config.EDGE_FEATURE_DIM, config.EDGE_CLASS.OUTPUT_SIZES, bn=config.BN)
+        self.node_classification = make_mlp(config.NODE_FEATURE_DIM, config.NODE_CLASS.OUTPUT_SIZES, bn=config.BN)
+        self.classification = make_mlp(config.NODE_FEATURE_DIM, config.CLASS.OUTPUT_SIZES, bn=config.BN)
+        self.edge_steps = config.STEPS
+        self.node_steps = config.NODE_STEPS
+        self.aux_loss_steps = config.AUX_LOSS_STEPS
+        self.aggr = config.AGGR
+        self.precision = getattr(config, "B200_PRECISION", "fp32")
+        if self.precision not in nv.PRECISION:
+            raise ValueError("B200_PRECISION must be one of %s" % (sorted(nv.PRECISION),))
+        self._pack_cache = None
+
+    # ------------------------------------------------------------------ weight packing
+    def _pack(self, device):
+        key = (str(device),) + tuple(t._version for t in list(self.parameters()) + list(self.buffers()))
+        if self._pack_cache is not None and self._pack_cache[0] == key:
+            return self._pack_cache[1]
+        pk = _Packer()
+        layer = self.mpn_node_cls
+        skip = bool(self.use_skip_connections)
+        nd = 128 if skip else 64
+        spec = {name: _fold_mlp(getattr(self, name), pk) for name in
+                ("node_embedding", "edge_embedding", "edge_classification", "node_classification", "classification")}
+        W1 = layer.mlp_edge[0].weight.detach().float()            # [64, 2*nd + ed], input = [x_i ; x_j ; e] (layers.py:214)
+        off = {"w1_dst": pk.add(W1[:, :nd].t()), "w1_src": pk.add(W1[:, nd:2 * nd].t())}
+        if skip:                                                   # e = [e_initial ; e_current] (NodeClassificationMPNSimple.py:78)
+            off["w1_e0"] = pk.add(W1[:, 2 * nd:2 * nd + 64].t())
+            off["w1_e"] = pk.add(W1[:, 2 * nd + 64:].t())
+        else:
+            off["w1_e"] = pk.add(W1[:, 2 * nd:].t())
+        off["b1"] = pk.add(layer.mlp_edge[0].bias)
+        off["w2"] = pk.add(layer.mlp_edge[2].weight.detach().float().t())
+        off["b2"] = pk.add(layer.mlp_edge[2].bias)
+        per_type = isinstance(layer, TypeAwareMPNLayer)
+        lins = [m[0] for m in layer.mlp_node.mlp] if per_type else [layer.mlp_node[0]]   # input = [x_i ; e'] (layers.py:223,273)
+        off["wm_x"] = pk.add(torch.stack([l.weight.detach().float()[:, :nd].t() for l in lins]))
+        off["wm_e"] = pk.add(torch.stack([l.weight.detach().float()[:, nd:].t() for l in lins]))
+        off["bm"] = pk.add(torch.stack([l.bias.detach().float() for l in lins]))
+        attn_net = getattr(layer, "attn_net", None)
+        if attn_net is not None:
+            off["wa"] = pk.add(attn_net[0].weight.detach().float().t())
+            off["ba"] = pk.add(attn_net[0].bias)
+        if layer.update_mlp is not None:
+            off["wu"] = pk.add(layer.update_mlp[0].weight.detach().float().t())
+            off["bu"] = pk.add(layer.update_mlp[0].bias)
+        flat = pk.finish(device)
+        packed = dict(flat=flat, spec=spec, off=off, per_type=per_type, skip=skip,
+                      num_types=layer.num_types if per_type else 1,
+                      attn=nv.ATTN[layer.aggr_sub] if per_type else 0,
+                      num_classes=self.classification[-1].out_features)
+        self._pack_cache = (key, packed)
+        return packed
+
+    def num_outputs(self):
+        first = max(self.edge_steps - self.aux_loss_steps - 1, 0)       # NodeClassificationMPNSimple.py:81
+        return self.edge_steps - first
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x, edge_attr, edge_index, **kwargs):
+        if self.training:
+            raise NotImplementedError("training mode (BatchNorm batch statistics + backward kernels) is the next "
+                                      "row of the build (SURVEY.md 8f); call .eval()")
+        if self.node_steps != 0:
+            raise NotImplementedError("NODE_STEPS != 0 (the reference's own loop omits node_types, App. A)")
+        if self.edge_steps < 1:
+            raise NotImplementedError("STEPS must be >= 1")
+        nv.require_cuda(x, "x", torch.float32)
+        nv.require_cuda(edge_attr, "edge_attr", torch.float32)
+        nv.require_cuda(edge_index, "edge_index", torch.int64)
+        node_types = sum_node_types(self.node_summary, kwargs["node_types"])          # :64
+        nv.require_cuda(node_types, "node_types", torch.int64)
+        dev = x.device
+        N, E = x.shape[0], edge_index.shape[1]
+        n_out = self.num_outputs()
+        pk = self._pack(dev)
+        J = pk["num_classes"]
+        if edge_attr.shape[0] != E or (E and edge_attr.shape[1] != self.edge_embedding[0].in_features):
+            raise ValueError("edge_attr must be [E, %d]" % self.edge_embedding[0].in_features)
+        if x.shape[1] != self.node_embedding[0].in_features or node_types.shape[0] != N:
+            raise ValueError("x must be [N, %d] and node_types [N]" % self.node_embedding[0].in_features)
+        edge_logits = torch.empty((n_out, E), dtype=torch.float32, device=dev)
+        node_logits = torch.empty((n_out, N), dtype=torch.float32, device=dev)
+        class_logits = torch.empty((n_out, N, J), dtype=torch.float32, device=dev)
+        if N > 0:
+            lib = nv.lib()
+            x_ = x.detach()
+            ea = edge_attr.detach().contiguous()
+            ei = edge_index.detach().contiguous()
+            nt = node_types.detach().contiguous()
+            base = pk["flat"].data_ptr()
+            p = nv.MpnParams(num_nodes=N, num_edges=E, x=x_.data_ptr(), x_stride_n=x_.stride(0),
+                             x_stride_c=x_.stride(1), edge_attr=ea.data_ptr(), edge_index=ei.data_ptr(),
+                             node_types=nt.data_ptr(), dim=64, per_type=int(pk["per_type"]),
+                             num_types=pk["num_types"], num_type_mlps=17 if pk["per_type"] else 1,
+                             skip=int(pk["skip"]), steps=self.edge_steps, aux_loss_steps=self.aux_loss_steps,
+                             aggr=nv.AGGR[self.aggr], attn=pk["attn"],
+                             has_update_mlp=int(self.mpn_node_cls.update_mlp is not None), num_classes=J,
+                             precision=nv.PRECISION[self.precision])
+            for field, name in (("node_emb", "node_embedding"), ("edge_emb", "edge_embedding"),
+                                ("edge_head", "edge_classification"), ("node_head", "node_classification"),
+                                ("class_head", "classification")):
+                setattr(p, field, _mlp_struct(pk["spec"][name], base))
+            for k, o in pk["off"].items():
+                setattr(p, k, base + 4 * o)
+            p.edge_logits, p.node_logits, p.class_logits = edge_logits.data_ptr(), node_logits.data_ptr(), class_logits.data_ptr()
+            with torch.cuda.device(dev):
+                ws_bytes = int(lib.pgmp_mpn_workspace_bytes(p))
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                p.workspace, p.workspace_bytes = ws.data_ptr(), ws_bytes
+                nv.check(lib.pgmp_mpn_forward(p, nv.current_stream()))
+                ws.record_stream(torch.cuda.current_stream())
+        # lists of independent tensors: the caller mutates entries in place (PoseEstimation.py:95-101);
+        # .squeeze() semantics of :82,:84,:93 (0-d when there is a single edge / node)
+        preds_edge = [edge_logits[i].squeeze() for i in range(n_out)]
+        preds_node = [node_logits[i].squeeze() for i in range(n_out)]
+        preds_class = [class_logits[i] for i in range(n_out)]
+        preds_node.append(preds_node[-1].clone())                      # :93-94 (recomputed on the same features)
+        preds_class.append(preds_class[-1].clone())
+        return preds_edge, preds_node, preds_class, [None]
+
+
+_OUT_OF_SCOPE = (
+    "VanillaMPN", "ClassificationMPN", "ClassificationMPNSimple", "VanillaMPN2", "ClassificationNaive",
+    "NodeClassificationMPNWithBackground", "NodeClassificationMPNTypeBased", "NodeClassificationMPNAttention",
+    "NodeClassificationMPNSelfAttention", "NodeClassificationMPNWithRef", "NodeClassificationMPNFPConstrained",
+    "NodeClassificationMPNTypeConstrained", "NodeClassificationMPNTag", "MPNTag", "LogisticEdgeClassifier",
+    "NodeClassificationMPNGroupBased", "NodeClassificationMPNGroupBasedHierach", "JointTypeClassification",
+    "TagThreshold", "PlainTag")
+
+
+def get_mpn_model(config, **kwargs):
+    """src/Models/MessagePassingNetwork/__init__.py:27-73."""
+    if config.NAME == "NodeClassificationMPN":
+        return NodeClassificationMPNSimple(config)
+    if config.NAME in _OUT_OF_SCOPE:
+        raise NotImplementedError("MPN variant %r is outside the B200 hot path (SURVEY.md 2, row 2); use the "
+                                  "reference implementation for it" % (config.NAME,))
+    raise NotImplementedError(config.NAME)

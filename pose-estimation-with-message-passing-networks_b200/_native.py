@@ -1,0 +1,194 @@
+"""ctypes binding of ``libpgmp.so`` (C ABI declared in ``include/pgmp.h``).
+
+The shared library is built in-tree from ``csrc/*.cu`` with
+``nvcc -gencode arch=compute_100a,code=sm_100a`` (``build()``; ``__graft_entry__.build()``
+calls it).  There is no CPU or PyTorch fallback: if the library cannot be loaded every
+entry point raises.
+"""
+
+import ctypes as C
+import glob
+import os
+import shutil
+import subprocess
+import threading
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG_DIR, "csrc")
+LIB_PATH = os.path.join(PKG_DIR, "libpgmp.so")
+INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+
+MAX_LAYERS = 6
+GRAPH_KNN, GRAPH_FULLY = 0, 1
+EDGE_FEAT_POSITION, EDGE_FEAT_TYPE = 1, 2
+GC_FLAGS = {1: "more NMS maxima than B200_CAND_CAPACITY for some (image, joint)",
+            2: "more detections than B200_MAX_DET_PER_TYPE for some (image, joint)",
+            4: "more nodes than B200_MAX_NODES in some image",
+            8: "no-threshold path: fewer than k positive maxima for some joint (reference asserts, CG.py:1193)"}
+AGGR = {"add": 0, "sum": 0, "max": 1, "mean": 2}
+ATTN = {"None": 0, "node_edge_attn": 1, "node_edge_attn_per_type": 2}
+PRECISION = {"fp32": 0, "tc": 1}
+
+
+class GcParams(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("num_joints", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
+                ("pool_kernel", C.c_int32), ("top_k", C.c_int32), ("use_threshold", C.c_int32),
+                ("threshold", C.c_float), ("graph_type", C.c_int32), ("knn_k", C.c_int32),
+                ("edge_features", C.c_int32), ("norm_factor", C.c_float), ("cand_capacity", C.c_int32),
+                ("max_det_per_type", C.c_int32), ("max_nodes", C.c_int32), ("scoremaps", C.c_void_p),
+                ("mask", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64)]
+
+
+class GcOutputs(C.Structure):
+    _fields_ = [("total_nodes", C.c_int64), ("total_edges", C.c_int64), ("features", C.c_void_p),
+                ("feat_stride_b", C.c_int64), ("feat_stride_c", C.c_int64), ("feat_stride_y", C.c_int64),
+                ("feat_stride_x", C.c_int64), ("channels", C.c_int32), ("tagmaps", C.c_void_p),
+                ("tag_dim", C.c_int32), ("x", C.c_void_p), ("edge_attr", C.c_void_p), ("edge_index", C.c_void_p),
+                ("joint_det", C.c_void_p), ("joint_scores", C.c_void_p), ("batch_index", C.c_void_p),
+                ("joint_tags", C.c_void_p)]
+
+
+class Mlp(C.Structure):
+    _fields_ = [("n_layers", C.c_int32), ("dims", C.c_int32 * (MAX_LAYERS + 1)), ("relu", C.c_int32 * MAX_LAYERS),
+                ("wt", C.c_void_p * MAX_LAYERS), ("bias", C.c_void_p * MAX_LAYERS), ("post_relu", C.c_int32),
+                ("post_scale", C.c_void_p), ("post_shift", C.c_void_p)]
+
+
+class MpnParams(C.Structure):
+    _fields_ = [("num_nodes", C.c_int64), ("num_edges", C.c_int64), ("x", C.c_void_p), ("x_stride_n", C.c_int64),
+                ("x_stride_c", C.c_int64), ("edge_attr", C.c_void_p), ("edge_index", C.c_void_p),
+                ("node_types", C.c_void_p),
+                ("dim", C.c_int32), ("per_type", C.c_int32), ("num_types", C.c_int32), ("num_type_mlps", C.c_int32),
+                ("skip", C.c_int32), ("steps", C.c_int32), ("aux_loss_steps", C.c_int32), ("aggr", C.c_int32),
+                ("attn", C.c_int32), ("has_update_mlp", C.c_int32), ("num_classes", C.c_int32),
+                ("precision", C.c_int32),
+                ("node_emb", Mlp), ("edge_emb", Mlp), ("edge_head", Mlp), ("node_head", Mlp), ("class_head", Mlp),
+                ("w1_dst", C.c_void_p), ("w1_src", C.c_void_p), ("w1_e0", C.c_void_p), ("w1_e", C.c_void_p),
+                ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p), ("wm_x", C.c_void_p),
+                ("wm_e", C.c_void_p), ("bm", C.c_void_p), ("wa", C.c_void_p), ("ba", C.c_void_p),
+                ("wu", C.c_void_p), ("bu", C.c_void_p),
+                ("edge_logits", C.c_void_p), ("node_logits", C.c_void_p), ("class_logits", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64)]
+
+
+class GroupParams(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("num_joints", C.c_int32), ("num_nodes", C.c_int64), ("num_edges", C.c_int64),
+                ("node_threshold", C.c_float), ("node_offsets", C.c_void_p), ("edge_offsets", C.c_void_p),
+                ("edge_index", C.c_void_p), ("joint_det", C.c_void_p), ("node_logits", C.c_void_p),
+                ("edge_logits", C.c_void_p), ("class_logits", C.c_void_p), ("person_labels", C.c_void_p),
+                ("num_components", C.c_void_p), ("max_persons", C.c_int32), ("persons", C.c_void_p),
+                ("num_persons", C.c_void_p), ("mutants", C.c_void_p), ("workspace", C.c_void_p),
+                ("workspace_bytes", C.c_uint64)]
+
+
+# every symbol include/pgmp.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "pgmp_version": (C.c_int, []),
+    "pgmp_last_error": (C.c_char_p, []),
+    "pgmp_kernel_launches": (C.c_uint64, []),
+    "pgmp_gc_workspace_bytes": (C.c_uint64, [C.POINTER(GcParams)]),
+    "pgmp_gc_detect": (C.c_int, [C.POINTER(GcParams), C.c_void_p, C.c_void_p]),
+    "pgmp_gc_emit": (C.c_int, [C.POINTER(GcParams), C.POINTER(GcOutputs), C.c_void_p]),
+    "pgmp_mpn_workspace_bytes": (C.c_uint64, [C.POINTER(MpnParams)]),
+    "pgmp_mpn_forward": (C.c_int, [C.POINTER(MpnParams), C.c_void_p]),
+    "pgmp_group_workspace_bytes": (C.c_uint64, [C.POINTER(GroupParams)]),
+    "pgmp_group_persons": (C.c_int, [C.POINTER(GroupParams), C.c_void_p]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def _stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/*.cu for sm_100a into libpgmp.so (cross-compiles without a GPU)."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: cannot build libpgmp.so")
+    objs = []
+    build_dir = os.path.join(PKG_DIR, "build")
+    os.makedirs(build_dir, exist_ok=True)
+    procs = []
+    for src in sources():
+        obj = os.path.join(build_dir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(
+                os.path.getmtime(p) for p in [src] + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))):
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if verbose and out:
+            print(out)
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed: %s\n%s" % (" ".join(cmd), out))
+    cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed: %s\n%s" % (" ".join(cmd), r.stdout))
+    return LIB_PATH
+
+
+def lib():
+    """The loaded library; raises if it is missing and cannot be built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if _stale() and (shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc")):
+                build()
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError("libpgmp.so is missing; build it with `python -c 'import __graft_entry__ as g; "
+                                   "g.build()'` (needs nvcc). pgmp_b200 has no CPU fallback.")
+            handle = C.CDLL(LIB_PATH)
+            for name, (res, args) in SYMBOLS.items():
+                fn = getattr(handle, name)
+                fn.restype, fn.argtypes = res, args
+            if handle.pgmp_version() != 100:
+                raise RuntimeError("libpgmp.so version mismatch: rebuild")
+            _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError("libpgmp: %s (code %d)" % (lib().pgmp_last_error().decode(), rc))
+
+
+def kernel_launches():
+    return int(lib().pgmp_kernel_launches())
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def current_stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(t, name, dtype=None):
+    import torch
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor: pgmp_b200 has no CPU path" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    return t

@@ -1,0 +1,88 @@
+// Data layout shared by the message-passing kernels (mpn_prep.cu, mpn_simt.cu, mpn_tc.cu).
+//
+// Edge features live in "slot" order, not in the caller's edge order: edges are grouped by
+// (source type, target node) -- type-major -- so that
+//   * a 128-row tile has one source type  -> one message weight matrix per tile (layers.py:264-274)
+//   * the edges of one (target, source type) pair are consecutive -> the per-(node, type) softmax /
+//     sum / max of layers.py:234-251 is a reduction over consecutive rows, no atomics
+// Every type group is padded to a multiple of 128 slots (pad slots have edge = -1).  Within a bin the
+// slots are ordered by the caller's edge id, which makes every floating-point reduction order
+// deterministic.  A bin whose rows straddle a tile boundary is reduced per tile into "parts" that
+// the node update merges (flash-style for the attention softmax).
+#pragma once
+
+#include "common.cuh"
+
+namespace pgmp {
+
+constexpr int kD = 64;          // NODE_FEATURE_DIM = EDGE_FEATURE_DIM = EDGE_FEATURE_HIDDEN
+constexpr int kTile = 128;      // rows (slots / nodes) per CTA tile
+constexpr int kTileP = kTile + 1;  // padded row count of transposed shared-memory tiles
+
+struct MpnWorkspace {
+  // graph bookkeeping
+  int32_t* node_type;     // [N] clamped to [0, T)
+  int32_t* bin_count;     // [T*N] edges per (type, target)
+  int32_t* bin_cursor;    // [T*N] scatter cursors
+  int32_t* bin_lstart;    // [T*N] first slot of the bin relative to its type group
+  int32_t* bin_lpart;     // [T*N] first part row of the bin relative to its type group
+  int32_t* group_total;   // [T] slots used by the group (before padding)
+  int32_t* group_parts;   // [T]
+  int32_t* group_start;   // [T+1] first slot of the group (multiple of 128); [T] = total padded slots
+  int32_t* group_pstart;  // [T+1] first part row of the group; [T] = total parts
+  int32_t* slot_edge;     // [S] caller's edge id or -1
+  int32_t* slot_src;      // [S]
+  int32_t* slot_dst;      // [S]
+  // features
+  float* h0;              // [N][64] node embedding
+  float* h;               // [N][64] current node feature
+  float* g;               // [S][64] current edge feature (slot order), updated in place
+  float* c0;              // [S][64] W1_e0 * g0 + b1 (skip only)
+  float* tab_p;           // [N][64] W1_dst * x_i (+ b1 when !skip)
+  float* tab_q;           // [N][64] W1_src * x_j
+  float* tab_r;           // [T][N][64] Wm_x[t] * x_i + bm[t]
+  float* part_val;        // [P][64] per-part reduced message (weighted sum / sum / max)
+  float* part_mx;         // [P] per-part max attention logit
+  float* part_se;         // [P] per-part sum of exp(logit - max)
+  uint64_t max_slots, max_parts;
+  uint64_t bytes;
+};
+
+inline MpnWorkspace carve_mpn(const pgmp_mpn_params& p) {
+  Carver c(p.workspace);
+  MpnWorkspace w;
+  const uint64_t N = (uint64_t)p.num_nodes, E = (uint64_t)p.num_edges, T = (uint64_t)p.num_types;
+  w.max_slots = round_up<uint64_t>(E, kTile) + T * kTile;       // every group padded to 128
+  const uint64_t bins = T * N;
+  w.max_parts = (E < bins ? E : bins) + w.max_slots / kTile;      // non-empty bins + tile crossings
+  w.node_type = c.take<int32_t>(N);
+  w.bin_count = c.take<int32_t>(bins);
+  w.bin_cursor = c.take<int32_t>(bins);
+  w.bin_lstart = c.take<int32_t>(bins);
+  w.bin_lpart = c.take<int32_t>(bins);
+  w.group_total = c.take<int32_t>(T);
+  w.group_parts = c.take<int32_t>(T);
+  w.group_start = c.take<int32_t>(T + 1);
+  w.group_pstart = c.take<int32_t>(T + 1);
+  w.slot_edge = c.take<int32_t>(w.max_slots);
+  w.slot_src = c.take<int32_t>(w.max_slots);
+  w.slot_dst = c.take<int32_t>(w.max_slots);
+  w.h0 = c.take<float>(N * kD);
+  w.h = c.take<float>(N * kD);
+  w.g = c.take<float>(w.max_slots * kD);
+  w.c0 = c.take<float>(p.skip ? w.max_slots * kD : 0);
+  w.tab_p = c.take<float>(N * kD);
+  w.tab_q = c.take<float>(N * kD);
+  w.tab_r = c.take<float>(T * N * kD);
+  w.part_val = c.take<float>(w.max_parts * kD);
+  w.part_mx = c.take<float>(w.max_parts);
+  w.part_se = c.take<float>(w.max_parts);
+  w.bytes = c.bytes();
+  return w;
+}
+
+// host-side launchers implemented in the .cu files
+int mpn_prepare_graph(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t st);
+int mpn_forward_simt(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t st);
+
+}  // namespace pgmp

@@ -1,0 +1,161 @@
+"""Drop-in for the reference's ``graph_constructor`` package
+(``src/graph_constructor/__init__.py:4-5``, ``ConstructGraph.py:9-249``), inference branch.
+
+``get_graph_constructor(config, **kwargs).construct_graph()`` keeps the reference's
+constructor keywords and its 15-tuple; the work runs in ``libpgmp.so``
+(``csrc/gc.cu``) for the whole batch at once with a single host read (the counts
+that size the outputs) instead of the reference's per-image Python loop.
+"""
+
+import torch
+
+from .. import _native as nv
+
+KNN_K = 50            # ConstructGraph.py:365
+NO_THRESHOLD_K = 20   # ConstructGraph.py:1185
+
+
+class _GatherNodeFeatures(torch.autograd.Function):
+    """x = features[b, :, y, x] with gradients flowing back into ``features``
+    (end-to-end training, train.py:232); forward is the CUDA gather inside ``pgmp_gc_emit``."""
+
+    @staticmethod
+    def forward(ctx, features, x_out, batch_index, joint_det):
+        ctx.save_for_backward(batch_index, joint_det)
+        ctx.feat_shape = features.shape
+        return x_out.view_as(x_out)
+
+    @staticmethod
+    def backward(ctx, grad):
+        batch_index, joint_det = ctx.saved_tensors
+        g = torch.zeros(ctx.feat_shape, dtype=grad.dtype, device=grad.device)
+        g.index_put_((batch_index, slice(None), joint_det[:, 1], joint_det[:, 0]), grad, accumulate=True)
+        return g, None, None, None
+
+
+class NaiveGraphConstructor:
+    """Same constructor signature as the reference class (ConstructGraph.py:11)."""
+
+    def __init__(self, scoremaps, tagmaps, features, joints_gt, factor_list, masks, device, config, testing,
+                 heatmaps, num_joints):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("pgmp_b200 graph constructor needs a CUDA device (no CPU fallback)")
+        self.scoremaps = scoremaps.to(self.device)
+        self.tagmaps = tagmaps.to(self.device) if tagmaps is not None else None
+        self.features = features.to(self.device) if features is not None else None
+        self.joints_gt = joints_gt
+        self.factor_list = factor_list
+        self.masks = masks.to(self.device) if masks is not None else None
+        self.batch_size = scoremaps.shape[0]
+        self.num_joints = num_joints
+        self.testing = testing
+        self.config = config
+
+        if joints_gt is not None or config.USE_GT or config.CHEAT:
+            raise NotImplementedError("ground-truth label construction (ConstructGraph.py:104-143, 475-1158) is "
+                                      "training-only host code outside the inference hot path (SURVEY.md 8f)")
+        self.mask_crowds = config.MASK_CROWDS
+        self.detect_threshold = config.DETECT_THRESHOLD if config.DETECT_THRESHOLD <= 1.5 else None   # CG.py:28
+        self.hybrid_k = config.HYBRID_K
+        self.mpn_graph_type = config.GRAPH_TYPE
+        self.normalize_node_distance = config.NORM_NODE_DISTANCE
+        self.edge_features_to_use = config.EDGE_FEATURES_TO_USE
+        self.pool_kernel_size = config.POOL_KERNEL_SIZE
+        if self.mpn_graph_type not in ("knn", "fully"):
+            raise NotImplementedError("GRAPH_TYPE=%r (knn and fully are in scope)" % (self.mpn_graph_type,))
+        feats = set(self.edge_features_to_use)
+        if not feats or not feats <= {"position", "connection_type"}:
+            raise NotImplementedError("EDGE_FEATURES_TO_USE=%r (position / connection_type are in scope)"
+                                      % (sorted(feats),))
+        self._edge_feat_bits = ((nv.EDGE_FEAT_POSITION if "position" in feats else 0)
+                                | (nv.EDGE_FEAT_TYPE if "connection_type" in feats else 0))
+        if self.mask_crowds and self.masks is None:
+            raise ValueError("MASK_CROWDS needs masks (PoseEstimation.py:73-74)")
+        # capacities of the fixed-size device buffers (build-specific, optional config keys)
+        top_k = self.hybrid_k if self.detect_threshold is not None else NO_THRESHOLD_K
+        self._top_k = top_k
+        self.max_det_per_type = int(getattr(config, "B200_MAX_DET_PER_TYPE", max(256, top_k)))
+        self.cand_capacity = int(getattr(config, "B200_CAND_CAPACITY", max(4096, top_k)))
+        max_nodes = int(getattr(config, "B200_MAX_NODES", min(2048, num_joints * self.max_det_per_type)))
+        self.max_nodes = (max_nodes + 31) // 32 * 32
+        self.num_nodes_per_image = None
+        self.num_edges_per_image = None
+
+    def construct_graph(self):
+        lib = nv.lib()
+        sm = nv.require_cuda(self.scoremaps, "scoremaps")
+        if sm.dim() != 4 or sm.shape[1] != self.num_joints:
+            raise ValueError("scoremaps must be [B, num_joints, H, W], got %s" % (tuple(sm.shape),))
+        sm = sm.detach().float().contiguous()
+        B, J, H, W = sm.shape
+        mask = self.masks.detach().float().contiguous() if self.mask_crowds else None
+        dev = sm.device
+        with torch.cuda.device(dev):
+            stream = nv.current_stream()
+            p = nv.GcParams(
+                batch=B, num_joints=J, height=H, width=W, pool_kernel=self.pool_kernel_size, top_k=self._top_k,
+                use_threshold=int(self.detect_threshold is not None),
+                threshold=float(self.detect_threshold if self.detect_threshold is not None else 0.0),
+                graph_type=nv.GRAPH_FULLY if self.mpn_graph_type == "fully" else nv.GRAPH_KNN, knn_k=KNN_K,
+                edge_features=self._edge_feat_bits,
+                norm_factor=float(max(W, H) if self.normalize_node_distance else 1),     # CG.py:311-314
+                cand_capacity=self.cand_capacity, max_det_per_type=self.max_det_per_type, max_nodes=self.max_nodes,
+                scoremaps=sm.data_ptr(), mask=mask.data_ptr() if mask is not None else None)
+            ws_bytes = int(lib.pgmp_gc_workspace_bytes(p))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            p.workspace, p.workspace_bytes = ws.data_ptr(), ws_bytes
+            counts = torch.empty(2 + 2 * B + 1, dtype=torch.int64, device=dev)
+            nv.check(lib.pgmp_gc_detect(p, counts.data_ptr(), stream))
+            counts_h = counts.cpu()            # the one host read of the graph constructor
+            flags = int(counts_h[-1])
+            if flags:
+                raise RuntimeError("graph constructor capacity exceeded: " +
+                                   "; ".join(msg for bit, msg in nv.GC_FLAGS.items() if flags & bit))
+            N, E = int(counts_h[0]), int(counts_h[1])
+            self.num_nodes_per_image = counts_h[2:2 + B].clone()
+            self.num_edges_per_image = counts_h[2 + B:2 + 2 * B].clone()
+
+            feat = self.features
+            C_ = feat.shape[1] if feat is not None else 0
+            F_ = (2 if self._edge_feat_bits & nv.EDGE_FEAT_POSITION else 0) + \
+                 (J if self._edge_feat_bits & nv.EDGE_FEAT_TYPE else 0)
+            x = torch.empty((N, C_), dtype=torch.float32, device=dev)
+            edge_attr = torch.empty((E, F_), dtype=torch.float32, device=dev)
+            edge_index = torch.empty((2, E), dtype=torch.int64, device=dev)
+            joint_det = torch.empty((N, 3), dtype=torch.int64, device=dev)
+            joint_scores = torch.empty((N,), dtype=torch.float32, device=dev)
+            batch_index = torch.empty((N,), dtype=torch.int64, device=dev)
+            tags = self.tagmaps
+            tag_dim, joint_tags, tags_c = 1, None, None
+            if tags is not None:
+                if tags.dim() not in (4, 5):
+                    raise ValueError("tagmaps must be [B,J,H,W] or [B,J,H,W,T]")
+                tag_dim = tags.shape[4] if tags.dim() == 5 else 1
+                tags_c = tags.detach().float().contiguous()
+                joint_tags = torch.empty((N,) if tags.dim() == 4 else (N, tag_dim), dtype=torch.float32, device=dev)
+            o = nv.GcOutputs(total_nodes=N, total_edges=E)
+            if feat is not None:
+                if feat.dtype != torch.float32:
+                    raise TypeError("features must be float32 (the reference gathers fp32, CG.py:265)")
+                fd = feat.detach()
+                o.features = fd.data_ptr()
+                o.feat_stride_b, o.feat_stride_c, o.feat_stride_y, o.feat_stride_x = fd.stride()
+                o.channels = C_
+                o.x = x.data_ptr()
+            if tags_c is not None:
+                o.tagmaps, o.tag_dim, o.joint_tags = tags_c.data_ptr(), tag_dim, joint_tags.data_ptr()
+            o.edge_attr, o.edge_index = edge_attr.data_ptr(), edge_index.data_ptr()
+            o.joint_det, o.joint_scores, o.batch_index = joint_det.data_ptr(), joint_scores.data_ptr(), batch_index.data_ptr()
+            nv.check(lib.pgmp_gc_emit(p, o, stream))
+            ws.record_stream(torch.cuda.current_stream())
+        if feat is not None and feat.requires_grad and torch.is_grad_enabled():
+            x = _GatherNodeFeatures.apply(feat, x, batch_index, joint_det)
+        # the reference's 15-tuple (ConstructGraph.py:248-249); label slots are None at inference (:243-246)
+        return (x, edge_attr, edge_index, None, None, None, None, joint_det, None, None, None, joint_scores,
+                batch_index, None, joint_tags)
+
+
+def get_graph_constructor(config, **kwargs):
+    """src/graph_constructor/__init__.py:4-5."""
+    return NaiveGraphConstructor(config=config, **kwargs)

@@ -1,0 +1,66 @@
+"""Case tables shared by ``make_golden.py`` (writes fixtures from the reference) and the tests."""
+
+# name -> (synthetic input kwargs, GC config overrides)
+GC_CASES = {
+    # exactly K per joint (bench-style config), kNN-50 and fully connected
+    "knn_small": (dict(batch=2, num_joints=17, size=128, k=10, persons=3), dict(k=10, graph_type="knn")),
+    "fully_small": (dict(batch=2, num_joints=17, size=128, k=10, persons=3), dict(k=10, graph_type="fully")),
+    # threshold extras appended after the top-k block; 3x3 pooling
+    "thr_extras": (dict(batch=2, num_joints=17, size=128, k=10, persons=3),
+                   dict(k=5, graph_type="knn", DETECT_THRESHOLD=0.5, POOL_KERNEL_SIZE=3)),
+    # no-threshold path: top-20, scores + 1e-10
+    "no_threshold": (dict(batch=1, num_joints=17, size=128, k=12, persons=3),
+                     dict(k=5, graph_type="knn", DETECT_THRESHOLD=2.0)),
+    # crowd mask multiplies the NMS map
+    "mask_crowds": (dict(batch=2, num_joints=17, size=128, k=10, persons=3),
+                    dict(k=10, graph_type="knn", MASK_CROWDS=True)),
+    # non-square map, norm = 160 (inexact fp32 division), un-normalised variant too
+    "rect_norm": (dict(batch=1, num_joints=17, size=96, width=160, k=8, persons=2), dict(k=8, graph_type="knn")),
+    "rect_nonorm": (dict(batch=1, num_joints=17, size=96, width=160, k=8, persons=2),
+                    dict(k=8, graph_type="fully", NORM_NODE_DISTANCE=False)),
+    # N <= 51 -> kNN graph is complete
+    "tiny_complete": (dict(batch=2, num_joints=4, size=64, k=5, persons=2), dict(k=5, graph_type="knn")),
+    # CrowdPose-shaped: 14 joints, 60 candidates per joint
+    "crowdpose": (dict(batch=1, num_joints=14, size=256, k=60, persons=20), dict(k=60, graph_type="knn")),
+    # other edge-feature sets
+    "feat_position": (dict(batch=1, num_joints=17, size=128, k=10, persons=3),
+                      dict(k=10, graph_type="knn", EDGE_FEATURES_TO_USE=["position"])),
+    "feat_type": (dict(batch=1, num_joints=17, size=128, k=10, persons=3),
+                  dict(k=10, graph_type="knn", EDGE_FEATURES_TO_USE=["connection_type"])),
+    # BASELINE.json configs[0]: single 512x512 image, 30 per joint, kNN-50 (large arrays stored as digests)
+    "config1_512": (dict(batch=1, num_joints=17, size=512, k=30, persons=8), dict(k=30, graph_type="knn")),
+}
+
+# name -> (GC case providing the graph, MPN config maker name, overrides, weight seed)
+MPN_CASES = {
+    "flagship": ("knn_small", "flagship_mpn_config", dict(), 1),
+    "flagship_aux2": ("knn_small", "flagship_mpn_config", dict(AUX_LOSS_STEPS=2, STEPS=4), 2),
+    "agnostic_max": ("knn_small", "agnostic_mpn_config", dict(), 3),
+    "agnostic_add_noskip_upd": ("knn_small", "agnostic_mpn_config",
+                                dict(AGGR="add", SKIP=False, USE_NODE_UPDATE_MLP=True, STEPS=3), 4),
+    "agnostic_mean": ("tiny_complete", "agnostic_mpn_config", dict(AGGR="mean", STEPS=3, NUM_JOINTS=4,
+                                                                   EDGE_INPUT_DIM=6), 5),
+    "pertype_vanilla_add": ("knn_small", "flagship_mpn_config", dict(AGGR_SUB="None", AGGR="add", STEPS=3), 6),
+    "pertype_vanilla_max": ("knn_small", "flagship_mpn_config", dict(AGGR_SUB="None", AGGR="max", STEPS=3), 7),
+    "pertype_attn_per_type": ("knn_small", "flagship_mpn_config", dict(AGGR_SUB="node_edge_attn_per_type", STEPS=3), 8),
+    "flagship_fully": ("fully_small", "flagship_mpn_config", dict(STEPS=2), 9),
+    "flagship_crowdpose": ("crowdpose", "flagship_mpn_config", dict(STEPS=2, NUM_JOINTS=14, EDGE_INPUT_DIM=16), 10),
+    "flagship_config1": ("config1_512", "flagship_mpn_config", dict(), 11),
+}
+
+# arrays at or above this many bytes are stored as sha256 digests instead of values
+DIGEST_BYTES = 300_000
+
+
+def gc_config_for(pgmp_config, overrides):
+    o = dict(overrides)
+    return pgmp_config.bench_gc_config(k=o.pop("k"), graph_type=o.pop("graph_type"), **o)
+
+
+def mpn_config_for(pgmp_config, maker, overrides):
+    o = dict(overrides)
+    nj = o.get("NUM_JOINTS", 17)
+    cfg = getattr(pgmp_config, maker)(nj, **o)
+    if nj != 17:                                    # CLASS head width follows the dataset's joint count
+        cfg.CLASS.OUTPUT_SIZES = [64, 32, nj]
+    return cfg
