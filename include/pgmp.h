@@ -37,6 +37,12 @@ int pgmp_version(void);
 const char* pgmp_last_error(void);
 /* cumulative number of kernels this library has launched in this process (bench.py: gpu_launches) */
 uint64_t pgmp_kernel_launches(void);
+/* Measurement support (the reference only has unsynchronised time.clock() pairs,
+ * src/Models/PoseEstimation/PoseEstimation.py:206,239): while enabled, every kernel launch is bracketed by
+ * CUDA events on its stream.  pgmp_profile_collect synchronises the device and writes one line per kernel,
+ * "<name> <launches> <total_ms>\n", into `out` (returns bytes written) and clears the records. */
+void pgmp_profile_enable(int on);
+int pgmp_profile_collect(char* out, int size);
 
 /* ------------------------------------------------------------------------------------------------
  * Graph constructor -- replaces NaiveGraphConstructor.construct_graph(), inference branch

@@ -89,6 +89,8 @@ SYMBOLS = {
     "pgmp_version": (C.c_int, []),
     "pgmp_last_error": (C.c_char_p, []),
     "pgmp_kernel_launches": (C.c_uint64, []),
+    "pgmp_profile_enable": (None, [C.c_int]),
+    "pgmp_profile_collect": (C.c_int, [C.c_char_p, C.c_int]),
     "pgmp_gc_workspace_bytes": (C.c_uint64, [C.POINTER(GcParams)]),
     "pgmp_gc_detect": (C.c_int, [C.POINTER(GcParams), C.c_void_p, C.c_void_p]),
     "pgmp_gc_emit": (C.c_int, [C.POINTER(GcParams), C.POINTER(GcOutputs), C.c_void_p]),
@@ -174,6 +176,21 @@ def check(rc):
 
 def kernel_launches():
     return int(lib().pgmp_kernel_launches())
+
+
+def profile(on):
+    lib().pgmp_profile_enable(1 if on else 0)
+
+
+def profile_collect():
+    """{kernel name: (launches, total_ms)} since profiling was enabled / last collected."""
+    buf = C.create_string_buffer(1 << 16)
+    lib().pgmp_profile_collect(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.rsplit(" ", 2)
+        out[name.strip("()")] = (int(cnt), float(ms))
+    return out
 
 
 def ptr(t):

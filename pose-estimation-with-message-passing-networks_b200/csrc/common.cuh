@@ -28,10 +28,18 @@ inline int check_cuda(cudaError_t e, const char* what) {
     if (_rc != PGMP_OK) return _rc;                            \
   } while (0)
 
+// Optional per-kernel timing (pgmp_profile_*): CUDA events recorded on the launching stream around
+// every launch while profiling is enabled.
+extern bool g_profiling;
+void profile_before(const char* name, cudaStream_t st);
+void profile_after(cudaStream_t st);
+
 // every kernel launch goes through this so that pgmp_kernel_launches() is exact
 #define PGMP_LAUNCH(kernel, grid, block, smem, stream, ...)                         \
   do {                                                                              \
+    if (::pgmp::g_profiling) ::pgmp::profile_before(#kernel, (stream));             \
     kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                     \
+    if (::pgmp::g_profiling) ::pgmp::profile_after((stream));                       \
     ::pgmp::g_kernel_launches.fetch_add(1, std::memory_order_relaxed);              \
     int _rc = ::pgmp::check_cuda(cudaGetLastError(), #kernel);                      \
     if (_rc != PGMP_OK) return _rc;                                                 \

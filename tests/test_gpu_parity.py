@@ -1,0 +1,170 @@
+"""GPU parity tests (B200): the CUDA path, called through the reference-shaped host API and the
+C ABI, against the numpy oracle on the same seeded inputs and against the reference's own outputs
+(tests/golden).  Integer / index / gathered quantities are bit-exact; logits within tolerance."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+import pgmp_b200
+import pgmp_b200.synthetic as synthetic
+from helpers import (FP32_TOL, GC_CASES, GC_KEYS, MPN_CASES, assert_close, assert_matches_golden, gc_inputs, golden,
+                     mpn_config_for)
+from pgmp_b200.graph_constructor import get_graph_constructor
+from pgmp_b200.Models.MessagePassingNetwork import get_mpn_model
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+SLOT = dict(x=0, edge_attr=1, edge_index=2, joint_det=7, joint_scores=11, batch_index=12, joint_tags=14)
+
+
+def run_gc(name, **extra):
+    data, cfg, nj = gc_inputs(name)
+    for k, v in extra.items():
+        setattr(cfg, k, v)
+    t = {k: torch.from_numpy(v).to(DEV) for k, v in data.items()}
+    gc = get_graph_constructor(cfg, scoremaps=t["scoremaps"], tagmaps=t["tagmaps"], features=t["features"],
+                               joints_gt=None, factor_list=None, masks=t["masks"] if cfg.MASK_CROWDS else None,
+                               device=DEV, testing=True, heatmaps=None, num_joints=nj)
+    ret = gc.construct_graph()
+    assert len(ret) == 15 and all(ret[i] is None for i in (3, 4, 5, 6, 8, 9, 10, 13))
+    return ret, gc
+
+
+@pytest.mark.parametrize("name", list(GC_CASES))
+def test_graph_constructor_bit_exact(name):
+    ret, gc = run_gc(name)
+    data, cfg, nj = gc_inputs(name)
+    want = oracle.gc.construct_graph(data["scoremaps"], data["tagmaps"], data["features"], cfg, nj, masks=data["masks"])
+    gold = golden("gc_" + name)
+    for k in GC_KEYS:
+        got = ret[SLOT[k]].cpu().numpy()
+        assert got.dtype == want[k].dtype and got.shape == want[k].shape, (k, got.shape, want[k].shape)
+        assert np.array_equal(got, want[k]), f"{k}: {np.sum(got != want[k])} mismatches vs oracle"
+        assert_matches_golden(gold, k, got, exact=True)
+    assert np.array_equal(gc.num_nodes_per_image.numpy(), want["num_nodes"])
+    assert np.array_equal(gc.num_edges_per_image.numpy(), want["num_edges"])
+
+
+def test_graph_constructor_channels_last_and_5d_tags():
+    data, cfg, nj = gc_inputs("knn_small")
+    sm = torch.from_numpy(data["scoremaps"]).to(DEV)
+    feat = torch.from_numpy(data["features"]).to(DEV).contiguous(memory_format=torch.channels_last)
+    tags5 = torch.from_numpy(np.stack([data["tagmaps"], -data["tagmaps"]], -1)).to(DEV)
+    ret = get_graph_constructor(cfg, scoremaps=sm, tagmaps=tags5, features=feat, joints_gt=None, factor_list=None,
+                                masks=None, device=DEV, testing=True, heatmaps=None, num_joints=nj).construct_graph()
+    want = oracle.gc.construct_graph(data["scoremaps"], tags5.cpu().numpy(), data["features"], cfg, nj)
+    assert np.array_equal(ret[0].cpu().numpy(), want["x"])
+    assert np.array_equal(ret[14].cpu().numpy(), want["joint_tags"]) and ret[14].shape[1] == 2
+
+
+def test_graph_constructor_capacity_errors_are_loud():
+    with pytest.raises(RuntimeError, match="B200_MAX_NODES"):
+        run_gc("knn_small", B200_MAX_NODES=64)
+    with pytest.raises(RuntimeError, match="B200_MAX_DET_PER_TYPE"):
+        run_gc("thr_extras", B200_MAX_DET_PER_TYPE=8)
+
+
+def test_nms_hand_made_plateaus_borders():
+    """Equal-valued positive plateaus are all maxima; borders behave like -inf padding."""
+    x = np.zeros((1, 2, 16, 16), dtype=np.float32)
+    x[0, 0, 0, 0] = 0.5
+    x[0, 0, 5, 5] = x[0, 0, 5, 6] = 0.7
+    x[0, 0, 15, 9] = 0.3
+    x[0, 1, 8, 8] = 0.9
+    x[0, 1, 8, 9] = 0.8          # suppressed by its neighbour
+    x[0, 1, 3, 15] = 0.2
+    cfg = pgmp_b200.config.bench_gc_config(k=4, POOL_KERNEL_SIZE=3, DETECT_THRESHOLD=0.6, graph_type="fully")
+    t = torch.from_numpy(x).to(DEV)
+    feat = torch.arange(16 * 16, dtype=torch.float32, device=DEV).reshape(1, 1, 16, 16)
+    ret = get_graph_constructor(cfg, scoremaps=t, tagmaps=t, features=feat, joints_gt=None, factor_list=None,
+                                masks=None, device=DEV, testing=True, heatmaps=None, num_joints=2).construct_graph()
+    want = oracle.gc.construct_graph(x, x, feat.cpu().numpy(), cfg, 2)
+    assert np.array_equal(ret[7].cpu().numpy(), want["joint_det"])
+    assert ret[7].cpu().numpy().tolist() == [[0, 0, 0], [5, 5, 0], [6, 5, 0], [9, 15, 0], [15, 3, 1], [8, 8, 1]]
+    assert np.array_equal(ret[2].cpu().numpy(), want["edge_index"])
+
+
+def mpn_case(name, precision="fp32"):
+    gc_name, maker, over, seed = MPN_CASES[name]
+    cfg = mpn_config_for(pgmp_b200.config, maker, over)
+    cfg.B200_PRECISION = precision
+    data, gcfg, nj = gc_inputs(gc_name)
+    g = oracle.gc.construct_graph(data["scoremaps"], data["tagmaps"], data["features"], gcfg, nj, masks=data["masks"])
+    model = synthetic.synth_mpn_state_dict(get_mpn_model(cfg), seed).eval().to(DEV)
+    return cfg, g, model
+
+
+def run_mpn(model, g):
+    with torch.no_grad():
+        return model(torch.from_numpy(g["x"]).to(DEV), torch.from_numpy(g["edge_attr"]).to(DEV),
+                     torch.from_numpy(g["edge_index"]).to(DEV),
+                     node_types=torch.from_numpy(g["joint_det"][:, 2]).to(DEV))
+
+
+@pytest.mark.parametrize("name", list(MPN_CASES))
+def test_mpn_fp32_matches_oracle_and_reference(name):
+    cfg, g, model = mpn_case(name)
+    pe, pn, pc, tag = run_mpn(model, g)
+    assert tag == [None]
+    sd = {k: v.cpu().numpy() for k, v in model.state_dict().items()}
+    ope, opn, opc = oracle.mpn.node_classification_mpn_forward(sd, cfg, g["x"], g["edge_attr"], g["edge_index"],
+                                                               g["joint_det"][:, 2])
+    gold = golden("mpn_" + name)
+    assert (len(pe), len(pn), len(pc)) == (len(ope), len(opn), len(opc)) == (gold["n_edge"], gold["n_node"], gold["n_class"])
+    for kind, got, want in (("edge", pe, ope), ("node", pn, opn), ("class", pc, opc)):
+        for i, (a, b) in enumerate(zip(got, want)):
+            a = a.cpu().numpy()
+            assert_close(a, b, FP32_TOL, f"{name}:{kind}_{i} vs oracle")
+            assert_close(a, gold[f"{kind}_{i}"], FP32_TOL, f"{name}:{kind}_{i} vs reference")
+
+
+def test_mpn_is_deterministic_and_order_independent():
+    """Same graph with the edge list shuffled gives the same logits per edge (bit-exact: slots are
+    ordered by (type, target, edge id) only inside bins, so compare after un-shuffling within tolerance),
+    and two runs on identical input are bit-identical."""
+    cfg, g, model = mpn_case("flagship")
+    a = run_mpn(model, g)
+    b = run_mpn(model, g)
+    for u, v in zip(a[0] + a[1] + a[2], b[0] + b[1] + b[2]):
+        assert torch.equal(u, v)
+    perm = np.random.default_rng(0).permutation(g["edge_index"].shape[1])
+    g2 = dict(g, edge_index=g["edge_index"][:, perm], edge_attr=g["edge_attr"][perm])
+    c = run_mpn(model, g2)
+    assert_close(c[0][0].cpu().numpy(), a[0][0].cpu().numpy()[perm], FP32_TOL, "shuffled edges")
+    assert_close(c[1][0].cpu().numpy(), a[1][0].cpu().numpy(), FP32_TOL, "shuffled nodes")
+
+
+def test_mpn_tiny_graphs_and_squeeze_semantics():
+    cfg = pgmp_b200.config.flagship_mpn_config(STEPS=2)
+    model = synthetic.synth_mpn_state_dict(get_mpn_model(cfg), 3).eval().to(DEV)
+    rng = np.random.default_rng(0)
+    for n, edges in ((1, []), (2, [(0, 1)]), (2, [(0, 1), (1, 0)]), (3, [(0, 1), (1, 0), (2, 0), (0, 2)])):
+        x = rng.standard_normal((n, 128)).astype(np.float32)
+        ei = np.array(edges, dtype=np.int64).reshape(-1, 2).T.copy()
+        ea = rng.standard_normal((ei.shape[1], 19)).astype(np.float32)
+        nt = rng.integers(0, 17, size=n)
+        pe, pn, pc, _ = model(torch.from_numpy(x).to(DEV), torch.from_numpy(ea).to(DEV), torch.from_numpy(ei).to(DEV),
+                              node_types=torch.from_numpy(nt).to(DEV))
+        sd = {k: v.cpu().numpy() for k, v in model.state_dict().items()}
+        ope, opn, opc = oracle.mpn.node_classification_mpn_forward(sd, cfg, x, ea, ei, nt)
+        assert pe[0].shape == ope[0].shape and pn[0].shape == opn[0].shape and pc[0].shape == opc[0].shape
+        assert_close(pn[0].cpu().numpy(), opn[0], FP32_TOL, f"n={n} node")
+        assert_close(pc[0].cpu().numpy(), opc[0], FP32_TOL, f"n={n} class")
+        if ei.shape[1]:
+            assert_close(pe[0].cpu().numpy(), ope[0], FP32_TOL, f"n={n} edge")
+
+
+def test_end_to_end_graph_constructor_into_mpn():
+    """construct_graph() output feeds forward() directly, as PoseEstimationBaseline.forward does
+    (PoseEstimation.py:82-93)."""
+    ret, _ = run_gc("knn_small")
+    cfg, g, model = mpn_case("flagship")
+    with torch.no_grad():
+        pe, pn, pc, _ = model(ret[0], ret[1], ret[2], node_labels=None, edge_labels=None, batch_index=ret[12],
+                              node_mask=None, node_types=ret[7][:, 2].detach(), joint_tags=ret[14])
+    gold = golden("mpn_flagship")
+    assert_close(pe[-1].cpu().numpy(), gold["edge_0"], FP32_TOL, "edge")
+    assert_close(pn[-1].cpu().numpy(), gold["node_1"], FP32_TOL, "node")
+    assert_close(pc[-1].cpu().numpy(), gold["class_1"], FP32_TOL, "class")
+    pe[-1] = torch.sigmoid(pe[-1])          # the caller mutates list entries (PoseEstimation.py:95-101)
