@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""Benchmark of the post-backbone grouping path (graph constructor + message-passing network).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload = BASELINE.json configs[1]: a COCO-shaped batch of 32 synthetic 512x512 images per GPU
+(17 joints, 128-channel w32 feature map, 30 candidates per joint, symmetric kNN-50 candidate graph,
+flagship per-type / edge-attention MPN with skip connections, 10 steps).  One step = one pass of
+construct_graph() + mpn.forward() over the batch.  Prints ONE JSON line (rank 0).
+
+  value        images/s with the inputs resident in HBM (device-timed with CUDA events, max over ranks)
+  e2e          the same metric through the public API with HOST (pinned) inputs: host->device copy of the
+               step's scoremaps / tagmaps / features and device->host read of the logits inside the timed region
+  roofline     dominant kernel: algorithmic bytes per launch / its mean CUDA-event duration vs measured HBM peak
+  cpu_baseline the numpy oracle (a port of the reference algorithm) timed on this box's host cores
+  --impl reference: the reference's CPU implementation of the path = the oracle port (the reference is pure
+               Python and cannot travel to the GPU box; /root/reference is never read here)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "images/sec and graph edges/sec (grouping path, 512px) at 1/2/4/8 B200"
+J, SIZE, CAND, CHANNELS = 17, 512, 30, 128
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
+    ap.add_argument("--precision", default=os.environ.get("PGMP_PRECISION", "fp32"), choices=["fp32", "tc"])
+    ap.add_argument("--ref-images", type=int, default=2, help="images per step of the CPU reference arm")
+    ap.add_argument("--cpu-sample", type=int, default=8, help="images of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+def workload_config(args, world):
+    return {"workload": "configs[1]: %d synthetic 512x512 images per GPU, 17 joints, 128-ch w32 features, "
+                        "30 candidates/joint, kNN-50 graph, flagship per-type/attention MPN (skip, 10 steps)" % args.batch,
+            "images_per_gpu": args.batch, "global_batch": args.batch * world, "parallelism": "dp%d (images sharded, "
+            "no collective in inference)" % world, "precision_mode": args.precision,
+            "l2": "inputs (5.4 GB per batch) exceed the 126 MB L2; no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------ CPU arms
+def host_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = [i.get("num_threads", 1) for i in threadpool_info()]
+        return max(n) if n else 1
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def oracle_images_per_s(num_images, first_index=0, warm=False):
+    """Time the oracle port (GC + flagship MPN) on `num_images` images of the workload, one at a time
+    like the reference's batch-1 evaluation loop (valid.py:95).  Returns (seconds, edges)."""
+    import numpy as np
+
+    import oracle
+    import pgmp_b200
+    import pgmp_b200.synthetic as synthetic
+    from pgmp_b200.Models.MessagePassingNetwork import get_mpn_model
+
+    gcfg = pgmp_b200.config.bench_gc_config(k=CAND, graph_type="knn")
+    mcfg = pgmp_b200.config.flagship_mpn_config(J)
+    model = synthetic.synth_mpn_state_dict(get_mpn_model(mcfg), 1).eval()
+    sd = {k: v.numpy() for k, v in model.state_dict().items()}
+    total, edges = 0.0, 0
+    for i in range(num_images + (1 if warm else 0)):
+        data = synthetic.synth_batch(1, J, SIZE, CAND, channels=CHANNELS, first_index=first_index + i)
+        t0 = time.perf_counter()
+        g = oracle.gc.construct_graph(data["scoremaps"], data["tagmaps"], data["features"], gcfg, J)
+        oracle.mpn.node_classification_mpn_forward(sd, mcfg, g["x"], g["edge_attr"], g["edge_index"], g["joint_det"][:, 2])
+        dt = time.perf_counter() - t0
+        if warm and i == 0:
+            continue
+        total += dt
+        edges += g["edge_index"].shape[1]
+    return total, edges
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    for _ in range(args.warmup):
+        oracle_images_per_s(1)
+    t, edges = 0.0, 0
+    for s in range(args.steps):
+        dt, e = oracle_images_per_s(args.ref_images, first_index=s * args.ref_images)
+        t += dt
+        edges += e
+    imgs = args.steps * args.ref_images
+    v = imgs / t
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "edges_per_s": edges / t,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, world),
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": host_threads(), "kind": "port",
+                             "sample": "%d images per step x %d steps of the workload, numpy oracle port of the "
+                                       "reference's CPU path (the reference itself is Python + torch_geometric and "
+                                       "cannot run on this box)" % (args.ref_images, args.steps)},
+            "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_b200(args, rank, local_rank, world):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import pgmp_b200
+    import pgmp_b200._native as nv
+    import pgmp_b200.synthetic as synthetic
+    from pgmp_b200.graph_constructor import get_graph_constructor
+    from pgmp_b200.Models.MessagePassingNetwork import get_mpn_model
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    first = rank * B                                           # images are sharded: rank r owns images [rB, rB+B)
+    sm_h = torch.from_numpy(np.stack([synthetic.synth_scoremap(first + b, J, SIZE, CAND) for b in range(B)])).pin_memory()
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    feat = torch.randn(B, CHANNELS, SIZE, SIZE, device=dev, generator=gen)
+    tags = torch.randn(B, J, SIZE, SIZE, device=dev, generator=gen)
+    sm = sm_h.to(dev)
+    gcfg = pgmp_b200.config.bench_gc_config(k=CAND, graph_type="knn")
+    mcfg = pgmp_b200.config.flagship_mpn_config(J, B200_PRECISION=args.precision)
+    model = synthetic.synth_mpn_state_dict(get_mpn_model(mcfg), 1).eval().to(dev)
+
+    def step(scoremaps, tagmaps, features):
+        gc = get_graph_constructor(gcfg, scoremaps=scoremaps, tagmaps=tagmaps, features=features, joints_gt=None,
+                                   factor_list=None, masks=None, device=dev, testing=True, heatmaps=None,
+                                   num_joints=J)
+        ret = gc.construct_graph()
+        with torch.no_grad():
+            pe, pn, pc, _ = model(ret[0], ret[1], ret[2], node_labels=None, edge_labels=None, batch_index=ret[12],
+                                  node_mask=None, node_types=ret[7][:, 2])
+        return ret, pe, pn, pc
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        ret, pe, pn, pc = step(sm, tags, feat)
+    edges_per_step = int(ret[2].shape[1])
+    nodes_per_step = int(ret[0].shape[0])
+
+    # ---- timed region 1: inputs resident in HBM
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    launches0 = nv.kernel_launches()
+    ev0.record()
+    for _ in range(args.steps):
+        step(sm, tags, feat)
+    ev1.record()
+    barrier()
+    launches = nv.kernel_launches() - launches0
+    t_dev = reduce_max(ev0.elapsed_time(ev1) / 1e3)
+    clocks = sampler.summary()
+
+    # ---- per-kernel CUDA-event durations over the same K steps (separate pass; events bracket every launch)
+    nv.profile(True)
+    for _ in range(args.steps):
+        step(sm, tags, feat)
+    prof = nv.profile_collect()
+    nv.profile(False)
+
+    # ---- timed region 2: end to end from pinned host buffers
+    feat_h = torch.empty(feat.shape, dtype=feat.dtype, pin_memory=True).copy_(feat)
+    tags_h = torch.empty(tags.shape, dtype=tags.dtype, pin_memory=True).copy_(tags)
+    out_h = None
+    h2d = sm_h.numel() * 4 + feat_h.numel() * 4 + tags_h.numel() * 4
+
+    def e2e_step():
+        nonlocal out_h
+        s_d = sm_h.to(dev, non_blocking=True)
+        t_d = tags_h.to(dev, non_blocking=True)
+        f_d = feat_h.to(dev, non_blocking=True)
+        ret, pe, pn, pc = step(s_d, t_d, f_d)
+        if out_h is None:
+            out_h = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in (pe[-1], pn[-1], pc[-1])]
+        for h, d in zip(out_h, (pe[-1], pn[-1], pc[-1])):
+            h.copy_(d, non_blocking=True)
+        return sum(h.numel() * 4 for h in out_h)
+
+    d2h = e2e_step()
+    e2e_step()
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    ev1.record()
+    barrier()
+    t_e2e = reduce_max(ev0.elapsed_time(ev1) / 1e3)
+
+    total_images = B * world * args.steps
+    total_edges = reduce_sum(edges_per_step) * args.steps
+    value = total_images / t_dev
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (largest total CUDA-event time)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    top = max(prof.items(), key=lambda kv: kv[1][1])
+    name, (cnt, ms) = top
+    # algorithmic bytes per launch ("Kernels"): SURVEY.md 8(d) per-unit figure x units per launch
+    elem = 4                                                     # storage width of edge features in this mode
+    bytes_per_launch = {
+        "edge_step_kernel": 3 * 64 * elem * edges_per_step,       # read g, read C (skip constant), write g'
+        "edge_step_tc_kernel": 3 * 64 * elem * edges_per_step,
+        "nms_candidates_kernel<R, true>": J * SIZE * SIZE * 4 * B + nodes_per_step * 28,
+    }.get(name)
+    roofline = None
+    if bytes_per_launch:
+        dur = ms / cnt / 1e3
+        ach = bytes_per_launch / dur / 1e9
+        roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "launch_ms": 1e3 * dur, "launches": cnt,
+                    "share_of_kernel_time": ms / sum(v[1] for v in prof.values()),
+                    "algorithmic_bytes_per_launch": bytes_per_launch}
+    kernels = {k: {"launches": c, "ms": round(m, 4)} for k, (c, m) in sorted(prof.items(), key=lambda kv: -kv[1][1])[:8]}
+
+    cpu_t, cpu_edges = (None, None)
+    cpu = None
+    if world == 1:
+        cpu_t, cpu_edges = oracle_images_per_s(args.cpu_sample, warm=True)
+        cpu = {"value": args.cpu_sample / cpu_t, "unit": "images/s", "cores": host_threads(), "kind": "port",
+               "edges_per_s": cpu_edges / cpu_t,
+               "sample": "%d images of the workload, one at a time (numpy oracle port of the reference CPU path)" % args.cpu_sample}
+
+    line = {"metric": METRIC, "value": value, "unit": "images/s", "edges_per_s": total_edges / t_dev,
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_dev / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, world), "clocks": clocks,
+            "e2e": {"value": total_images / t_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * t_e2e / args.steps},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,
+            "graph": {"nodes_per_step_per_gpu": nodes_per_step, "edges_per_step_per_gpu": edges_per_step}}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

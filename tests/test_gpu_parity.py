@@ -1,6 +1,8 @@
 """GPU parity tests (B200): the CUDA path, called through the reference-shaped host API and the
 C ABI, against the numpy oracle on the same seeded inputs and against the reference's own outputs
 (tests/golden).  Integer / index / gathered quantities are bit-exact; logits within tolerance."""
+import copy
+
 import numpy as np
 import pytest
 import torch
@@ -20,6 +22,7 @@ SLOT = dict(x=0, edge_attr=1, edge_index=2, joint_det=7, joint_scores=11, batch_
 
 def run_gc(name, **extra):
     data, cfg, nj = gc_inputs(name)
+    cfg = copy.copy(cfg)
     for k, v in extra.items():
         setattr(cfg, k, v)
     t = {k: torch.from_numpy(v).to(DEV) for k, v in data.items()}
@@ -149,10 +152,11 @@ def test_mpn_tiny_graphs_and_squeeze_semantics():
         sd = {k: v.cpu().numpy() for k, v in model.state_dict().items()}
         ope, opn, opc = oracle.mpn.node_classification_mpn_forward(sd, cfg, x, ea, ei, nt)
         assert pe[0].shape == ope[0].shape and pn[0].shape == opn[0].shape and pc[0].shape == opc[0].shape
-        assert_close(pn[0].cpu().numpy(), opn[0], FP32_TOL, f"n={n} node")
-        assert_close(pc[0].cpu().numpy(), opc[0], FP32_TOL, f"n={n} class")
+        # one- or two-element tensors have no meaningful scale: absolute tolerance on O(1) logits
+        np.testing.assert_allclose(pn[0].cpu().numpy(), opn[0], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(pc[0].cpu().numpy(), opc[0], rtol=1e-4, atol=1e-5)
         if ei.shape[1]:
-            assert_close(pe[0].cpu().numpy(), ope[0], FP32_TOL, f"n={n} edge")
+            np.testing.assert_allclose(pe[0].cpu().numpy(), ope[0], rtol=1e-4, atol=1e-5)
 
 
 def test_end_to_end_graph_constructor_into_mpn():
