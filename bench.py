@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
-    ap.add_argument("--precision", default=os.environ.get("PGMP_PRECISION", "fp32"), choices=["fp32", "tc"])
+    ap.add_argument("--precision", default=os.environ.get("PGMP_PRECISION", "tc"), choices=["fp32", "tc"])
     ap.add_argument("--ref-images", type=int, default=2, help="images per step of the CPU reference arm")
     ap.add_argument("--cpu-sample", type=int, default=8, help="images of the cpu_baseline sample")
     return ap.parse_args()

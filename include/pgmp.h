@@ -175,6 +175,11 @@ typedef struct pgmp_mpn_params {
   const float* ba;                     /* [attn_cols] */
   const float* wu;                     /* [num_types*dim][dim] update_mlp.0 or NULL */
   const float* bu;
+  /* PGMP_PRECISION_TC only: the per-edge weight matrices in Linear.weight layout [out][in] (K contiguous),
+   * split as bf16 hi = bf16(W), lo = bf16(W - hi); device uint16 (bf16 bit patterns). */
+  const void* tc_w1_e;                 /* [2][dim][dim]                 (hi, lo) of mlp_edge.0 current-edge columns */
+  const void* tc_w2;                   /* [2][dim][dim]                 mlp_edge.2 */
+  const void* tc_wm_e;                 /* [num_type_mlps][2][dim][dim]  mlp_node edge columns */
 
   /* outputs: n_out = aux_loss_steps + 1 predictions (NodeClassificationMPNSimple.py:81-84) */
   float* edge_logits;                  /* [n_out][E] */
@@ -183,6 +188,10 @@ typedef struct pgmp_mpn_params {
   void* workspace;                     /* device, pgmp_mpn_workspace_bytes() bytes, 256-B aligned */
   uint64_t workspace_bytes;
 } pgmp_mpn_params;
+
+/* Self-test of the tcgen05 building blocks: D[128,64] = A[128,64] . W[64,64]^T (fp32 device pointers) through
+ * the same bf16x3 split / SWIZZLE_128B tile writers / TMEM epilogue the message-passing kernels use. */
+int pgmp_selftest_umma(const float* a, const float* w, float* d, pgmp_stream_t stream);
 
 uint64_t pgmp_mpn_workspace_bytes(const pgmp_mpn_params* p);
 int pgmp_mpn_forward(const pgmp_mpn_params* p, pgmp_stream_t stream);

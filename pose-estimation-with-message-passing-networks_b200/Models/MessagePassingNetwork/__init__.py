@@ -171,7 +171,17 @@ class NodeClassificationMPNSimple(nn.Module):
             off["wu"] = pk.add(layer.update_mlp[0].weight.detach().float().t())
             off["bu"] = pk.add(layer.update_mlp[0].bias)
         flat = pk.finish(device)
-        packed = dict(flat=flat, spec=spec, off=off, per_type=per_type, skip=skip,
+
+        def split(w):      # bf16x3 operands of the tensor-core path: hi = bf16(W), lo = bf16(W - hi), [out][in]
+            w = w.detach().float().to(device)
+            hi = w.to(torch.bfloat16)
+            lo = (w - hi.float()).to(torch.bfloat16)
+            return torch.stack([hi, lo])
+
+        w1e = W1[:, 2 * nd + 64:] if skip else W1[:, 2 * nd:]
+        tc = dict(tc_w1_e=split(w1e).contiguous(), tc_w2=split(layer.mlp_edge[2].weight).contiguous(),
+                  tc_wm_e=torch.stack([split(l.weight[:, nd:]) for l in lins]).contiguous())
+        packed = dict(flat=flat, tc=tc, spec=spec, off=off, per_type=per_type, skip=skip,
                       num_types=layer.num_types if per_type else 1,
                       attn=nv.ATTN[layer.aggr_sub] if per_type else 0,
                       num_classes=self.classification[-1].out_features)
@@ -229,6 +239,8 @@ class NodeClassificationMPNSimple(nn.Module):
                 setattr(p, field, _mlp_struct(pk["spec"][name], base))
             for k, o in pk["off"].items():
                 setattr(p, k, base + 4 * o)
+            for k, t in pk["tc"].items():
+                setattr(p, k, t.data_ptr())
             p.edge_logits, p.node_logits, p.class_logits = edge_logits.data_ptr(), node_logits.data_ptr(), class_logits.data_ptr()
             with torch.cuda.device(dev):
                 ws_bytes = int(lib.pgmp_mpn_workspace_bytes(p))

@@ -70,6 +70,7 @@ class MpnParams(C.Structure):
                 ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p), ("wm_x", C.c_void_p),
                 ("wm_e", C.c_void_p), ("bm", C.c_void_p), ("wa", C.c_void_p), ("ba", C.c_void_p),
                 ("wu", C.c_void_p), ("bu", C.c_void_p),
+                ("tc_w1_e", C.c_void_p), ("tc_w2", C.c_void_p), ("tc_wm_e", C.c_void_p),
                 ("edge_logits", C.c_void_p), ("node_logits", C.c_void_p), ("class_logits", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64)]
 
@@ -94,6 +95,7 @@ SYMBOLS = {
     "pgmp_gc_workspace_bytes": (C.c_uint64, [C.POINTER(GcParams)]),
     "pgmp_gc_detect": (C.c_int, [C.POINTER(GcParams), C.c_void_p, C.c_void_p]),
     "pgmp_gc_emit": (C.c_int, [C.POINTER(GcParams), C.POINTER(GcOutputs), C.c_void_p]),
+    "pgmp_selftest_umma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pgmp_mpn_workspace_bytes": (C.c_uint64, [C.POINTER(MpnParams)]),
     "pgmp_mpn_forward": (C.c_int, [C.POINTER(MpnParams), C.c_void_p]),
     "pgmp_group_workspace_bytes": (C.c_uint64, [C.POINTER(GroupParams)]),

@@ -438,6 +438,22 @@ __global__ void __launch_bounds__(kTile) edge_step_kernel(const EdgeStepArgs a) 
   if (e >= 0) a.edge_logits[e] = buf[threadIdx.x];
 }
 
+// Edge head (NodeClassificationMPNSimple.py:84) as its own pass over the slot-ordered edge features
+// (used by the tensor-core mode, whose step kernel does not carry the head).
+__global__ void __launch_bounds__(kTile) edge_head_kernel(const float* __restrict__ g, const int32_t* __restrict__ slot_edge,
+                                                          const int32_t* __restrict__ group_start, int T,
+                                                          const pgmp_mlp head, float* __restrict__ edge_logits) {
+  extern __shared__ __align__(16) float smem[];
+  float* buf = smem;
+  float* ws = buf + kD * kTileP;
+  const int64_t slot0 = (int64_t)blockIdx.x * kTile;
+  if (slot0 >= group_start[T]) return;
+  load_tile_rowmajor(buf, g, slot0, slot0 + kTile, kD);
+  run_small_chain(head, buf, buf, ws);
+  const int e = slot_edge[slot0 + threadIdx.x];
+  if (e >= 0) edge_logits[e] = buf[threadIdx.x];
+}
+
 int check_small(const pgmp_mlp& m, const char* name, int in_dim, int out_dim) {
   if (m.n_layers < 1 || m.n_layers > PGMP_MAX_LAYERS) return set_error(PGMP_ERR_INVALID, "%s: %d layers", name, m.n_layers);
   if (m.dims[0] != in_dim) return set_error(PGMP_ERR_INVALID, "%s: input width %d != %d", name, m.dims[0], in_dim);
@@ -513,6 +529,18 @@ int mpn_node_update(const pgmp_mpn_params& p, const MpnWorkspace& w, int out_slo
   float* cl = out_slot >= 0 ? p.class_logits + (size_t)out_slot * N * p.num_classes : nullptr;
   PGMP_LAUNCH(node_update_kernel, (unsigned)ceil_div<int64_t>(N, kTile), kTile, smem, st, av, N, p.num_types,
               p.has_update_mlp, p.wu, p.bu, w.h, out_slot >= 0 ? 1 : 0, p.node_head, p.class_head, nl, cl);
+  return PGMP_OK;
+}
+
+int mpn_edge_head(const pgmp_mpn_params& p, const MpnWorkspace& w, int out_slot, cudaStream_t st) {
+  const size_t smem = sizeof(float) * (kD * kTileP + kWs);
+  static bool attr = false;
+  if (!attr) {
+    PGMP_CUDA(cudaFuncSetAttribute(edge_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  PGMP_LAUNCH(edge_head_kernel, (unsigned)(w.max_slots / kTile), kTile, smem, st, w.g, w.slot_edge, w.group_start,
+              p.num_types, p.edge_head, p.edge_logits + (size_t)out_slot * p.num_edges);
   return PGMP_OK;
 }
 

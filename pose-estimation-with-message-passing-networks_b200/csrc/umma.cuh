@@ -1,0 +1,175 @@
+// Minimal hand-written tcgen05 / TMEM / mbarrier layer for sm_100a (inline PTX; no CUTLASS).
+//
+// Operand tiles live in shared memory in the canonical K-major SWIZZLE_128B layout: rows of 128 bytes
+// (64 bf16), groups of 8 rows = 1024 bytes, the 16-byte chunk c of row r stored at chunk position
+// c ^ (r & 7).  Tile bases are 1024-byte aligned.  Accumulators are fp32 in tensor memory: row i of
+// the 128-row tile is TMEM lane i, output column j is TMEM column j.
+//
+// Precision scheme "bf16x3": an fp32 operand x is split into hi = bf16(x), lo = bf16(x - hi);
+// A.W ~= Ah.Wh + Ah.Wl + Al.Wh with fp32 accumulation (relative error ~2^-16 per product term),
+// which keeps 10 weight-shared recurrent steps within the 1e-3 logit tolerance where plain bf16
+// (measured 4e-3 .. 1e-2) and tf32 (about 1e-3) do not.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace pgmp {
+namespace umma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier ------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  uint32_t spins = 0;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!done && ++spins > (1u << 24)) __trap();   // a lost MMA completion must fail loudly, never hang the GPU
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- tensor memory ---------------------------------------------------------------------------
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst) {   // one full warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {     // the same warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 16 consecutive fp32 columns of this thread's TMEM lane (warp w reads lanes 32*(w%4) .. +31)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// the whole 64-column accumulator row of this thread
+__device__ __forceinline__ void tmem_ld64(uint32_t tmem_base, int col0, float (&v)[64]) {
+  const uint32_t lane_base = ((threadIdx.x >> 5) & 3) * 32;
+  const uint32_t t = tmem_base + (lane_base << 16) + (uint32_t)col0;
+  tmem_ld16(t + 0, v + 0);
+  tmem_ld16(t + 16, v + 16);
+  tmem_ld16(t + 32, v + 32);
+  tmem_ld16(t + 48, v + 48);
+  tmem_ld_wait();
+}
+
+// ---- descriptors ------------------------------------------------------------------------------
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for swizzled K-major, 1),
+//   [32,46) stride byte offset >> 4 (1024 B between 8-row groups), [46,48) version = 1, [61,64) layout = 2
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3fffu) | (1ull << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+// instruction descriptor, kind::f16: D fp32 (bit 4), A = B = bf16 (bits 7, 10), both K-major, N >> 3 at 17, M >> 4 at 24
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the mbarrier once all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// D[128 x N] (+)= A[128 x K] . W[N x K]^T with the bf16x3 split; A and W tiles are [rows][64 bf16] SW128 blocks,
+// K / 64 blocks each, block b of A at a + b * a_block_bytes (same for W).  One thread issues.
+template <int N>
+__device__ __forceinline__ void issue_gemm_x3(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t a_block_bytes,
+                                              uint32_t w_hi, uint32_t w_lo, uint32_t w_block_bytes, int k_blocks,
+                                              bool accumulate) {
+  constexpr uint32_t idesc = idesc_bf16(128, N);
+  uint32_t acc = accumulate ? 1u : 0u;
+  for (int b = 0; b < k_blocks; ++b) {
+    const uint64_t ah = smem_desc_sw128(a_hi + b * a_block_bytes), al = smem_desc_sw128(a_lo + b * a_block_bytes);
+    const uint64_t wh = smem_desc_sw128(w_hi + b * w_block_bytes), wl = smem_desc_sw128(w_lo + b * w_block_bytes);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {   // UMMA_K = 16 bf16 = 32 bytes = 2 descriptor units
+      mma_bf16(tmem_d, ah + 2 * k, wh + 2 * k, idesc, acc);
+      acc = 1u;
+      mma_bf16(tmem_d, ah + 2 * k, wl + 2 * k, idesc, 1u);
+      mma_bf16(tmem_d, al + 2 * k, wh + 2 * k, idesc, 1u);
+    }
+  }
+}
+
+// ---- operand tile writers ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t sw128_offset(int row, int chunk16) {
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk16 ^ (row & 7)) << 4));
+}
+
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+// write 4 consecutive fp32 values (columns col4*4 .. +3 of `row`) into the hi / lo tiles
+__device__ __forceinline__ void store_split4(uint8_t* hi_tile, uint8_t* lo_tile, int row, int col4, float4 v) {
+  __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+  split_bf16(v.x, h0, l0);
+  split_bf16(v.y, h1, l1);
+  split_bf16(v.z, h2, l2);
+  split_bf16(v.w, h3, l3);
+  const uint32_t off = sw128_offset(row, col4 >> 1) + (uint32_t)((col4 & 1) << 3);
+  *reinterpret_cast<uint2*>(hi_tile + off) = make_uint2(pack2(h0, h1), pack2(h2, h3));
+  *reinterpret_cast<uint2*>(lo_tile + off) = make_uint2(pack2(l0, l1), pack2(l2, l3));
+}
+
+// write this thread's whole 64-wide row (values v[0..63]) into the hi / lo tiles (8 x 16-byte chunks each)
+__device__ __forceinline__ void store_split_row(uint8_t* hi_tile, uint8_t* lo_tile, int row, const float (&v)[64]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    __nv_bfloat16 h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split_bf16(v[8 * c + i], h[i], l[i]);
+    const uint32_t off = sw128_offset(row, c);
+    *reinterpret_cast<uint4*>(hi_tile + off) = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
+    *reinterpret_cast<uint4*>(lo_tile + off) = make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
+  }
+}
+
+// copy a [rows][64] bf16 row-major global block (K contiguous) into a SW128 tile, all threads of the CTA
+__device__ __forceinline__ void load_weight_tile(uint8_t* tile, const __nv_bfloat16* __restrict__ src, int rows, int src_ld) {
+  for (int idx = threadIdx.x; idx < rows * 8; idx += blockDim.x) {
+    const int r = idx >> 3, c = idx & 7;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)r * src_ld + c * 8));
+    *reinterpret_cast<uint4*>(tile + sw128_offset(r, c)) = v;
+  }
+}
+
+}  // namespace umma
+}  // namespace pgmp

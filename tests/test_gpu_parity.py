@@ -10,7 +10,7 @@ import torch
 import oracle
 import pgmp_b200
 import pgmp_b200.synthetic as synthetic
-from helpers import (FP32_TOL, GC_CASES, GC_KEYS, MPN_CASES, assert_close, assert_matches_golden, gc_inputs, golden,
+from helpers import (LOGIT_TOL, FP32_TOL, GC_CASES, GC_KEYS, MPN_CASES, assert_close, assert_matches_golden, gc_inputs, golden,
                      mpn_config_for)
 from pgmp_b200.graph_constructor import get_graph_constructor
 from pgmp_b200.Models.MessagePassingNetwork import get_mpn_model
@@ -172,3 +172,37 @@ def test_end_to_end_graph_constructor_into_mpn():
     assert_close(pn[-1].cpu().numpy(), gold["node_1"], FP32_TOL, "node")
     assert_close(pc[-1].cpu().numpy(), gold["class_1"], FP32_TOL, "class")
     pe[-1] = torch.sigmoid(pe[-1])          # the caller mutates list entries (PoseEstimation.py:95-101)
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core mode (tcgen05 / TMEM, bf16x3 split with fp32 accumulation)
+# ------------------------------------------------------------------------------------------------
+def test_umma_selftest_gemm():
+    """The tcgen05 building blocks in isolation: D = A . W^T for one 128x64x64 tile."""
+    import pgmp_b200._native as nv
+    g = torch.Generator().manual_seed(0)
+    A = torch.randn(128, 64, generator=g)
+    W = torch.randn(64, 64, generator=g)
+    D = torch.full((128, 64), float("nan"), device=DEV)
+    A_d, W_d = A.to(DEV), W.to(DEV)          # keep the device copies alive across the launch
+    nv.check(nv.lib().pgmp_selftest_umma(A_d.data_ptr(), W_d.data_ptr(), D.data_ptr(), nv.current_stream()))
+    torch.cuda.synchronize()
+    want = (A.double() @ W.double().t()).numpy()
+    assert_close(D.cpu().numpy(), want, 1e-4, "bf16x3 GEMM")     # ~2^-16 per product term
+
+
+@pytest.mark.parametrize("name", list(MPN_CASES))
+def test_mpn_tensor_core_within_logit_tolerance(name):
+    """north_star: logits within 1e-3 relative error with fp32-accumulated bf16 tensor-core math."""
+    cfg, g, model = mpn_case(name, precision="tc")
+    pe, pn, pc, _ = run_mpn(model, g)
+    sd = {k: v.cpu().numpy() for k, v in model.state_dict().items()}
+    ope, opn, opc = oracle.mpn.node_classification_mpn_forward(sd, cfg, g["x"], g["edge_attr"], g["edge_index"],
+                                                               g["joint_det"][:, 2])
+    gold = golden("mpn_" + name)
+    for kind, got, want in (("edge", pe, ope), ("node", pn, opn), ("class", pc, opc)):
+        assert len(got) == len(want)
+        for i, (a, b) in enumerate(zip(got, want)):
+            a = a.cpu().numpy()
+            assert_close(a, b, LOGIT_TOL, f"{name}:{kind}_{i} vs oracle")
+            assert_close(a, gold[f"{kind}_{i}"], LOGIT_TOL, f"{name}:{kind}_{i} vs reference")
