@@ -180,6 +180,8 @@ typedef struct pgmp_mpn_params {
   const void* tc_w1_e;                 /* [2][dim][dim]                 (hi, lo) of mlp_edge.0 current-edge columns */
   const void* tc_w2;                   /* [2][dim][dim]                 mlp_edge.2 */
   const void* tc_wm_e;                 /* [num_type_mlps][2][dim][dim]  mlp_node edge columns */
+  const void* tc_wtab;                 /* [2 + num_type_mlps][2][dim][nd] node-side columns: mlp_edge.0 target, source, mlp_node[t] */
+  const void* tc_wu;                   /* [num_types][2][dim][dim]      update_mlp.0 columns of type t, or NULL */
 
   /* outputs: n_out = aux_loss_steps + 1 predictions (NodeClassificationMPNSimple.py:81-84) */
   float* edge_logits;                  /* [n_out][E] */

@@ -180,7 +180,12 @@ class NodeClassificationMPNSimple(nn.Module):
 
         w1e = W1[:, 2 * nd + 64:] if skip else W1[:, 2 * nd:]
         tc = dict(tc_w1_e=split(w1e).contiguous(), tc_w2=split(layer.mlp_edge[2].weight).contiguous(),
-                  tc_wm_e=torch.stack([split(l.weight[:, nd:]) for l in lins]).contiguous())
+                  tc_wm_e=torch.stack([split(l.weight[:, nd:]) for l in lins]).contiguous(),
+                  tc_wtab=torch.stack([split(W1[:, :nd]), split(W1[:, nd:2 * nd])] +
+                                      [split(l.weight[:, :nd]) for l in lins]).contiguous())
+        if layer.update_mlp is not None:
+            wu = layer.update_mlp[0].weight.detach().float()
+            tc["tc_wu"] = torch.stack([split(wu[:, t * 64:(t + 1) * 64]) for t in range(wu.shape[1] // 64)]).contiguous()
         packed = dict(flat=flat, tc=tc, spec=spec, off=off, per_type=per_type, skip=skip,
                       num_types=layer.num_types if per_type else 1,
                       attn=nv.ATTN[layer.aggr_sub] if per_type else 0,

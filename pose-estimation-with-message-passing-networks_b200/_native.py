@@ -70,7 +70,8 @@ class MpnParams(C.Structure):
                 ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p), ("wm_x", C.c_void_p),
                 ("wm_e", C.c_void_p), ("bm", C.c_void_p), ("wa", C.c_void_p), ("ba", C.c_void_p),
                 ("wu", C.c_void_p), ("bu", C.c_void_p),
-                ("tc_w1_e", C.c_void_p), ("tc_w2", C.c_void_p), ("tc_wm_e", C.c_void_p),
+                ("tc_w1_e", C.c_void_p), ("tc_w2", C.c_void_p), ("tc_wm_e", C.c_void_p), ("tc_wtab", C.c_void_p),
+                ("tc_wu", C.c_void_p),
                 ("edge_logits", C.c_void_p), ("node_logits", C.c_void_p), ("class_logits", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64)]
 

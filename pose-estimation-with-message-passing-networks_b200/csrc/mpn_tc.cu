@@ -20,6 +20,8 @@ int mpn_embed(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t st);
 int mpn_node_tables(const pgmp_mpn_params& p, const MpnWorkspace& w, const float* h, cudaStream_t st);
 int mpn_node_update(const pgmp_mpn_params& p, const MpnWorkspace& w, int out_slot, cudaStream_t st);
 int mpn_edge_head(const pgmp_mpn_params& p, const MpnWorkspace& w, int out_slot, cudaStream_t st);
+int mpn_node_tables_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, const float* h, cudaStream_t st);
+int mpn_node_update_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, int out_slot, cudaStream_t st);
 
 namespace {
 
@@ -307,7 +309,12 @@ __global__ void __launch_bounds__(kTile) selftest_umma_kernel(const float* __res
 }  // namespace
 
 int mpn_forward_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t st) {
-  if (!p.tc_w1_e || !p.tc_w2 || !p.tc_wm_e) return set_error(PGMP_ERR_INVALID, "PGMP_PRECISION_TC needs the bf16 hi/lo weights");
+  if (!p.tc_w1_e || !p.tc_w2 || !p.tc_wm_e || !p.tc_wtab || (p.has_update_mlp && !p.tc_wu))
+    return set_error(PGMP_ERR_INVALID, "PGMP_PRECISION_TC needs the bf16 hi/lo weights");
+  // the node update runs on the tensor cores when it is a matrix product (update MLP), else it is a plain merge
+  auto node_update = [&](int out_slot) {
+    return p.has_update_mlp ? mpn_node_update_tc(p, w, out_slot, st) : mpn_node_update(p, w, out_slot, st);
+  };
   const int64_t N = p.num_nodes, E = p.num_edges;
   int rc;
   if ((rc = mpn_embed(p, w, st)) != PGMP_OK) return rc;
@@ -332,15 +339,15 @@ int mpn_forward_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t
   for (int s = 0; s < p.steps; ++s) {
     if (s > 0) {
       const int prev_slot = (s - 1) >= first_out ? (s - 1) - first_out : -1;
-      if ((rc = mpn_node_update(p, w, prev_slot, st)) != PGMP_OK) return rc;
+      if ((rc = node_update(prev_slot)) != PGMP_OK) return rc;
     }
-    if ((rc = mpn_node_tables(p, w, w.h, st)) != PGMP_OK) return rc;
+    if ((rc = mpn_node_tables_tc(p, w, w.h, st)) != PGMP_OK) return rc;
     if (E > 0) {
       PGMP_LAUNCH(edge_step_tc_kernel, grid, kTile, kTcSmemBytes, st, a);
       if (s >= first_out && (rc = mpn_edge_head(p, w, s - first_out, st)) != PGMP_OK) return rc;
     }
   }
-  return mpn_node_update(p, w, (p.steps - 1) - first_out, st);
+  return node_update((p.steps - 1) - first_out);
 }
 
 }  // namespace pgmp
