@@ -182,6 +182,8 @@ typedef struct pgmp_mpn_params {
   const void* tc_wm_e;                 /* [num_type_mlps][2][dim][dim]  mlp_node edge columns */
   const void* tc_wtab;                 /* [2 + num_type_mlps][2][dim][nd] node-side columns: mlp_edge.0 target, source, mlp_node[t] */
   const void* tc_wu;                   /* [num_types][2][dim][dim]      update_mlp.0 columns of type t, or NULL */
+  const void* tc_wh1;                  /* [2][64][64] edge head layer 0 (BatchNorm folded), or NULL */
+  const void* tc_wh2;                  /* [2][32][64] edge head layer 1, or NULL */
 
   /* outputs: n_out = aux_loss_steps + 1 predictions (NodeClassificationMPNSimple.py:81-84) */
   float* edge_logits;                  /* [n_out][E] */
@@ -219,7 +221,9 @@ typedef struct pgmp_group_params {
   const float* class_logits;           /* device [N, num_joints] or NULL */
   int64_t* person_labels;              /* out [N]: component id within the image, numbered by smallest node */
   int32_t* num_components;             /* out [B] */
+  int32_t* num_kept_edges;             /* out [B]: edges whose two ends pass the node threshold (0 -> the reference returns None, Utils.py:1452,1457) */
   int32_t max_persons;                 /* capacity of `persons` per image */
+  int32_t max_nodes_per_image;         /* upper bound of nodes in any image (sizes the dense cluster graph) */
   double* persons;                     /* out [B][max_persons][num_joints][3] (x, y, score), Utils.py:709-721 */
   int32_t* num_persons;                /* out [B] */
   int32_t* mutants;                    /* out [B] (Utils.py:703-706) */

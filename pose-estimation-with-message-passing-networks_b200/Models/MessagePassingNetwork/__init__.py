@@ -75,11 +75,11 @@ def _fold_mlp(seq, packer):
             raise NotImplementedError(type(m))
     out = [(packer.add(W.t()), packer.add(b), W.shape[1], W.shape[0], r) for W, b, r in layers]
     post_off = (packer.add(post[0]), packer.add(post[1])) if post is not None else None
-    return out, post_off
+    return out, post_off, [W for W, _, _ in layers]
 
 
 def _mlp_struct(spec, base):
-    layers, post = spec
+    layers, post = spec[0], spec[1]
     if len(layers) > nv.MAX_LAYERS:
         raise NotImplementedError("MLP deeper than %d layers" % nv.MAX_LAYERS)
     m = nv.Mlp()
@@ -183,6 +183,9 @@ class NodeClassificationMPNSimple(nn.Module):
                   tc_wm_e=torch.stack([split(l.weight[:, nd:]) for l in lins]).contiguous(),
                   tc_wtab=torch.stack([split(W1[:, :nd]), split(W1[:, nd:2 * nd])] +
                                       [split(l.weight[:, :nd]) for l in lins]).contiguous())
+        head_w = spec["edge_classification"][2]     # folded Linear weights of the edge head
+        if [tuple(w.shape) for w in head_w] == [(64, 64), (32, 64), (1, 32)]:
+            tc["tc_wh1"], tc["tc_wh2"] = split(head_w[0]).contiguous(), split(head_w[1]).contiguous()
         if layer.update_mlp is not None:
             wu = layer.update_mlp[0].weight.detach().float()
             tc["tc_wu"] = torch.stack([split(wu[:, t * 64:(t + 1) * 64]) for t in range(wu.shape[1] // 64)]).contiguous()

@@ -1,2 +1,89 @@
-"""Grouping tail of the hot path (``src/Utils/Utils.py``: pred_to_ann :1445-1457, pred_to_person :499-514,
-graph_cluster_to_persons :672-743; ``src/Utils/correlation_clustering``)."""
+"""Grouping tail of the hot path: logits -> persons.
+
+Batched CUDA equivalent of ``src/valid.py:109-122`` + ``pred_to_ann`` up to ``pred_to_person``
+(``src/Utils/Utils.py:1445-1457, 499-514``), ``cluster_graph`` with ``CC_METHOD == "GAEC"``
+(``src/Utils/correlation_clustering/correlation_clustering_utils.py``) and
+``graph_cluster_to_persons`` (``Utils.py:672-743``).  The reference does this per image on the host
+with dense N x N numpy matrices and a native solver that is missing from its tree; here one CTA per
+image runs the whole tail on the device (``csrc/group.cu``).
+"""
+
+import numpy as np
+import torch
+
+from .. import _native as nv
+
+
+def group_persons(joint_det, node_logits, edge_index, edge_logits, class_logits, batch_index, num_joints,
+                  node_threshold=0.1, cc_method="GAEC", max_persons=None, detector_scores=None):
+    """Returns one entry per image of the batch: ``None`` where the reference's ``pred_to_ann`` returns
+    ``None`` before grouping (no detector score > 0.1, Utils.py:1448-1449; no edge between kept nodes,
+    :1452,1457) else ``(persons [P, J, 3] float64 ndarray, mutants bool, person_labels [N_b] int64 tensor)``
+    as ``pred_to_person`` does.
+
+    ``node_logits`` / ``edge_logits`` / ``class_logits`` are the MPN's last predictions (logits: the sigmoid /
+    softmax of valid.py:109-111 are applied on the device); ``edge_index`` holds global node ids with the edges of
+    an image contiguous, as ``construct_graph`` returns them.
+    """
+    if cc_method != "GAEC":
+        raise NotImplementedError("CC_METHOD=%r (GAEC, the reference default, is in scope)" % (cc_method,))
+    nv.require_cuda(joint_det, "joint_det", torch.int64)
+    nv.require_cuda(node_logits, "node_logits", torch.float32)
+    nv.require_cuda(edge_index, "edge_index", torch.int64)
+    nv.require_cuda(edge_logits, "edge_logits", torch.float32)
+    nv.require_cuda(batch_index, "batch_index", torch.int64)
+    dev = joint_det.device
+    N, E = joint_det.shape[0], edge_index.shape[1]
+    if N == 0:
+        return []
+    lib = nv.lib()
+    B = int(batch_index[-1].item()) + 1
+    nodes_per = torch.bincount(batch_index, minlength=B)
+    edges_per = torch.bincount(batch_index[edge_index[0]], minlength=B) if E else torch.zeros(B, dtype=torch.int64, device=dev)
+    zero = torch.zeros(1, dtype=torch.int64, device=dev)
+    node_off = torch.cat([zero, nodes_per.cumsum(0)])
+    edge_off = torch.cat([zero, edges_per.cumsum(0)])
+    max_nodes = int(nodes_per.max().item())
+    J = int(num_joints)
+    max_persons = int(max_persons or max(1, max_nodes // 2))
+    labels = torch.empty(N, dtype=torch.int64, device=dev)
+    ncomp = torch.empty(B, dtype=torch.int32, device=dev)
+    nkept = torch.empty(B, dtype=torch.int32, device=dev)
+    npers = torch.empty(B, dtype=torch.int32, device=dev)
+    mutants = torch.empty(B, dtype=torch.int32, device=dev)
+    persons = torch.zeros((B, max_persons, J, 3), dtype=torch.float64, device=dev)
+    jd = joint_det.contiguous()
+    nl = node_logits.detach().reshape(-1).contiguous()
+    el = edge_logits.detach().reshape(-1).contiguous()
+    ei = edge_index.contiguous()
+    cl = class_logits.detach().contiguous() if class_logits is not None else None
+    p = nv.GroupParams(batch=B, num_joints=J, num_nodes=N, num_edges=E, node_threshold=float(node_threshold),
+                       node_offsets=node_off.data_ptr(), edge_offsets=edge_off.data_ptr(), edge_index=ei.data_ptr(),
+                       joint_det=jd.data_ptr(), node_logits=nl.data_ptr(), edge_logits=el.data_ptr(),
+                       class_logits=cl.data_ptr() if cl is not None else None, person_labels=labels.data_ptr(),
+                       num_components=ncomp.data_ptr(), num_kept_edges=nkept.data_ptr(), max_persons=max_persons,
+                       max_nodes_per_image=max_nodes, persons=persons.data_ptr(), num_persons=npers.data_ptr(),
+                       mutants=mutants.data_ptr())
+    with torch.cuda.device(dev):
+        ws_bytes = int(lib.pgmp_group_workspace_bytes(p))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        p.workspace, p.workspace_bytes = ws.data_ptr(), ws_bytes
+        nv.check(lib.pgmp_group_persons(p, nv.current_stream()))
+        ws.record_stream(torch.cuda.current_stream())
+    nkept_h, npers_h, mut_h = nkept.cpu().tolist(), npers.cpu().tolist(), mutants.cpu().tolist()
+    node_off_h = node_off.cpu().tolist()
+    persons_h = persons.cpu().numpy()
+    det_ok = None
+    if detector_scores is not None:                                # Utils.py:1448-1449
+        det_ok = torch.zeros(B, dtype=torch.int64, device=dev).index_add_(
+            0, batch_index, (detector_scores > 0.1).long()).cpu().tolist()
+    out = []
+    for b in range(B):
+        if npers_h[b] > max_persons:
+            raise RuntimeError("more than max_persons=%d persons in image %d" % (max_persons, b))
+        if nkept_h[b] <= 0 or (det_ok is not None and det_ok[b] < 1):
+            out.append(None)
+            continue
+        out.append((persons_h[b, :npers_h[b]].copy() if npers_h[b] else np.array([]), bool(mut_h[b]),
+                    labels[node_off_h[b]:node_off_h[b + 1]]))
+    return out

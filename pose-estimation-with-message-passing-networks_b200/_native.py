@@ -71,7 +71,7 @@ class MpnParams(C.Structure):
                 ("wm_e", C.c_void_p), ("bm", C.c_void_p), ("wa", C.c_void_p), ("ba", C.c_void_p),
                 ("wu", C.c_void_p), ("bu", C.c_void_p),
                 ("tc_w1_e", C.c_void_p), ("tc_w2", C.c_void_p), ("tc_wm_e", C.c_void_p), ("tc_wtab", C.c_void_p),
-                ("tc_wu", C.c_void_p),
+                ("tc_wu", C.c_void_p), ("tc_wh1", C.c_void_p), ("tc_wh2", C.c_void_p),
                 ("edge_logits", C.c_void_p), ("node_logits", C.c_void_p), ("class_logits", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64)]
 
@@ -81,7 +81,8 @@ class GroupParams(C.Structure):
                 ("node_threshold", C.c_float), ("node_offsets", C.c_void_p), ("edge_offsets", C.c_void_p),
                 ("edge_index", C.c_void_p), ("joint_det", C.c_void_p), ("node_logits", C.c_void_p),
                 ("edge_logits", C.c_void_p), ("class_logits", C.c_void_p), ("person_labels", C.c_void_p),
-                ("num_components", C.c_void_p), ("max_persons", C.c_int32), ("persons", C.c_void_p),
+                ("num_components", C.c_void_p), ("num_kept_edges", C.c_void_p), ("max_persons", C.c_int32),
+                ("max_nodes_per_image", C.c_int32), ("persons", C.c_void_p),
                 ("num_persons", C.c_void_p), ("mutants", C.c_void_p), ("workspace", C.c_void_p),
                 ("workspace_bytes", C.c_uint64)]
 

@@ -1,14 +1,283 @@
-// Grouping tail (threshold -> multicut GAEC -> person assembly) -- entry points; kernels follow.
+// Grouping tail: sigmoid / node threshold / subgraph -> multicut weights -> GAEC (greedy additive
+// edge contraction) -> connected-component labels -> per-person keypoint selection.
+//
+// Reference: src/valid.py:109-111, src/Utils/Utils.py:1448-1451 (threshold + subgraph), :499-514
+// (pred_to_person), src/Utils/correlation_clustering/correlation_clustering_utils.py:99-136, 187-256
+// (weights w = (p_ab + p_ba)/2 - 0.5 on kept pairs a < b), Utils.py:672-743 (graph_cluster_to_persons).
+// The GAEC solver itself is the reference's missing native module (andres_graph_wrapper); this
+// kernel follows the same published algorithm and tie rule as oracle/grouping.py: contract the live
+// edge of maximal weight while it is >= 0; ties -> smallest (a, b), a < b, clusters named by their
+// smallest member; weights accumulate in fp64.
+//
+// One CTA per image.  The cluster graph is a dense fp64 matrix in the caller's workspace (absent
+// edges = -inf); every row caches its best upper-triangle entry, a contraction updates O(N) entries
+// in parallel and only rows whose cached best was touched are rescanned (one warp per row).
 #include "common.cuh"
+
+#include <math_constants.h>
+
+namespace pgmp {
+namespace {
+
+constexpr int kThreads = 1024;
+constexpr uint32_t kFull = 0xffffffffu;
+
+struct GroupWs {
+  float* adj32;      // [B][M*M] dense sum of kept edge probabilities (to_dense_adj)
+  double* w;         // [B][M*M] cluster-graph weights, -inf = no edge
+  int* mult;         // [B][M*M] multiplicity of the undirected edge a < b in the kept edge list
+  double* best_val;  // [B][M]
+  int* best_col;     // [B][M]
+  int* rep;          // [B][M]
+  int* flags;        // [B][M] bit0 alive, bit1 dirty, bit2 kept (node threshold)
+  float* p_node;     // [B][M]
+  int* type;         // [B][M] re-assigned joint type (argmax of the class head)
+  int* comp;         // [B][M] component id per node
+  uint64_t bytes;
+};
+
+GroupWs carve(const pgmp_group_params& p, int M) {
+  Carver c(p.workspace);
+  GroupWs w;
+  const uint64_t B = p.batch, mm = (uint64_t)M * M;
+  w.adj32 = c.take<float>(B * mm);
+  w.w = c.take<double>(B * mm);
+  w.mult = c.take<int>(B * mm);
+  w.best_val = c.take<double>(B * M);
+  w.best_col = c.take<int>(B * M);
+  w.rep = c.take<int>(B * M);
+  w.flags = c.take<int>(B * M);
+  w.p_node = c.take<float>(B * M);
+  w.type = c.take<int>(B * M);
+  w.comp = c.take<int>(B * M);
+  w.bytes = c.bytes();
+  return w;
+}
+
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
+
+// better = larger value, then smaller column
+__device__ __forceinline__ bool better(double v, int c, double bv, int bc) { return v > bv || (v == bv && c < bc); }
+
+// one warp rescans row r over alive columns > r
+__device__ void rescan_row(const double* __restrict__ W, const int* __restrict__ flags, int n, int r,
+                           double* __restrict__ best_val, int* __restrict__ best_col) {
+  const int lane = threadIdx.x & 31;
+  double bv = -CUDART_INF;
+  int bc = 0x7fffffff;
+  for (int c = r + 1 + lane; c < n; c += 32) {
+    if (!(flags[c] & 1)) continue;
+    const double v = W[(size_t)r * n + c];
+    if (v != -CUDART_INF && better(v, c, bv, bc)) { bv = v; bc = c; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(kFull, bv, o);
+    const int oc = __shfl_xor_sync(kFull, bc, o);
+    if (better(ov, oc, bv, bc)) { bv = ov; bc = oc; }
+  }
+  if (lane == 0) { best_val[r] = bv; best_col[r] = bc; }
+}
+
+__global__ void __launch_bounds__(kThreads) group_kernel(const pgmp_group_params p, const GroupWs ws, int M) {
+  __shared__ double s_val[32];
+  __shared__ int s_row[32];
+  __shared__ int s_u, s_v, s_any_lower, s_count, s_kept;
+  __shared__ double s_best;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t n0 = p.node_offsets[b], e0 = p.edge_offsets[b], e1 = p.edge_offsets[b + 1];
+  const int n = (int)(p.node_offsets[b + 1] - n0);
+  const int J = p.num_joints;
+  float* __restrict__ A = ws.adj32 + (size_t)b * M * M;
+  double* __restrict__ W = ws.w + (size_t)b * M * M;
+  int* __restrict__ mult = ws.mult + (size_t)b * M * M;
+  double* __restrict__ best_val = ws.best_val + (size_t)b * M;
+  int* __restrict__ best_col = ws.best_col + (size_t)b * M;
+  int* __restrict__ rep = ws.rep + (size_t)b * M;
+  int* __restrict__ flags = ws.flags + (size_t)b * M;
+  float* __restrict__ pn = ws.p_node + (size_t)b * M;
+  int* __restrict__ typ = ws.type + (size_t)b * M;
+  int* __restrict__ comp = ws.comp + (size_t)b * M;
+  if (n <= 0 || n > M) {
+    if (tid == 0) { p.num_components[b] = 0; p.num_persons[b] = 0; p.mutants[b] = 0; p.num_kept_edges[b] = n > M ? -1 : 0; }
+    return;
+  }
+  if (tid == 0) { s_any_lower = 0; s_kept = 0; }
+  // ---- nodes: probability, threshold (Utils.py:1450), class argmax (:699-702)
+  for (int i = tid; i < n; i += kThreads) {
+    const float pr = sigmoidf_(p.node_logits[n0 + i]);
+    pn[i] = pr;
+    flags[i] = 1 | (pr > p.node_threshold ? 4 : 0);
+    rep[i] = i;
+    int t = (int)p.joint_det[(n0 + i) * 3 + 2];
+    if (p.class_logits) {
+      const float* __restrict__ cl = p.class_logits + (n0 + i) * J;
+      float bv = cl[0];
+      t = 0;
+      for (int j = 1; j < J; ++j)
+        if (cl[j] > bv) { bv = cl[j]; t = j; }
+    }
+    typ[i] = t;
+  }
+  for (size_t i = tid; i < (size_t)n * n; i += kThreads) { A[i] = 0.f; W[i] = -CUDART_INF; mult[i] = 0; }
+  __syncthreads();
+  // ---- dense matrix of kept edge probabilities (subgraph + to_dense_adj, correlation_clustering_utils.py:117)
+  for (int64_t e = e0 + tid; e < e1; e += kThreads) {
+    const int s = (int)(p.edge_index[e] - n0), d = (int)(p.edge_index[p.num_edges + e] - n0);
+    if (s < 0 || s >= n || d < 0 || d >= n) continue;
+    if (!((flags[s] & 4) && (flags[d] & 4))) continue;
+    atomicAdd(&s_kept, 1);
+    atomicAdd(&A[(size_t)s * n + d], sigmoidf_(p.edge_logits[e]));
+    if (s < d) atomicAdd(&mult[(size_t)s * n + d], 1); else s_any_lower = 1;
+  }
+  __syncthreads();
+  // ---- multicut weights on pairs a < b present in the kept edge list (:221-227)
+  const int any_lower = s_any_lower;
+  if (tid == 0) p.num_kept_edges[b] = s_kept;
+  for (size_t i = tid; i < (size_t)n * n; i += kThreads) {
+    const int a = (int)(i / n), c = (int)(i - (size_t)a * n);
+    if (a < c && mult[i] > 0) {
+      float v = A[i] + A[(size_t)c * n + a];
+      if (any_lower) v = v / 2.f;                                   // :118-121 (else mirrored, :114-117)
+      const double w = (double)(v - 0.5f) * (double)mult[i];
+      W[i] = w;
+      W[(size_t)c * n + a] = w;
+    }
+  }
+  __syncthreads();
+  for (int r = warp; r < n; r += kThreads / 32) rescan_row(W, flags, n, r, best_val, best_col);
+  __syncthreads();
+  // ---- GAEC
+  for (int it = 0; it < n; ++it) {
+    // global best over rows: larger value, then smaller row (rows cache their smallest best column)
+    double bv = -CUDART_INF;
+    int br = 0x7fffffff;
+    for (int r = tid; r < n; r += kThreads)
+      if ((flags[r] & 1) && better(best_val[r], r, bv, br)) { bv = best_val[r]; br = r; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(kFull, bv, o);
+      const int orow = __shfl_xor_sync(kFull, br, o);
+      if (better(ov, orow, bv, br)) { bv = ov; br = orow; }
+    }
+    if (lane == 0) { s_val[warp] = bv; s_row[warp] = br; }
+    __syncthreads();
+    if (warp == 0) {
+      bv = s_val[lane];
+      br = s_row[lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(kFull, bv, o);
+        const int orow = __shfl_xor_sync(kFull, br, o);
+        if (better(ov, orow, bv, br)) { bv = ov; br = orow; }
+      }
+      if (lane == 0) { s_best = bv; s_u = br; s_v = br < n ? best_col[br] : 0; }
+    }
+    __syncthreads();
+    if (!(s_best >= 0.0)) break;                                    // "there must be negative weights", :213,222
+    const int u = s_u, v = s_v;                                     // u < v: v is contracted into u
+    for (int q = tid; q < n; q += kThreads) {
+      if (rep[q] == v) rep[q] = u;
+      if (q == u || q == v || !(flags[q] & 1)) continue;
+      const double wv = W[(size_t)v * n + q];
+      // entries (q, v) disappear: rows q < v whose best was column v must rescan
+      if (q < v && best_col[q] == v) flags[q] |= 2;
+      if (wv == -CUDART_INF) continue;
+      const double wu = W[(size_t)u * n + q];
+      const double nw = (wu == -CUDART_INF) ? wv : wu + wv;
+      W[(size_t)u * n + q] = nw;
+      W[(size_t)q * n + u] = nw;
+      if (q < u) {                                                  // entry (q, u) lives in row q
+        if (better(nw, u, best_val[q], best_col[q])) { best_val[q] = nw; best_col[q] = u; flags[q] &= ~2; }
+        else if (best_col[q] == u) flags[q] |= 2;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) { flags[v] = 0; flags[u] |= 2; }
+    __syncthreads();
+    for (int r = warp; r < n; r += kThreads / 32) {
+      if ((flags[r] & 3) == 3) {
+        rescan_row(W, flags, n, r, best_val, best_col);
+        if (lane == 0) flags[r] &= ~2;
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  // ---- component labels in order of the smallest member (scipy connected_components, Utils.py:688-691)
+  if (tid == 0) {
+    int c = 0;
+    for (int i = 0; i < n; ++i)
+      if (rep[i] == i) comp[i] = c++;
+    s_count = c;
+    p.num_components[b] = c;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += kThreads) p.person_labels[n0 + i] = comp[rep[i]];
+  __syncthreads();
+  // ---- persons (Utils.py:692-741): components with more than one node, per type the node with the best score
+  if (warp == 0) {
+    int n_person = 0, mutant = 0;
+    double* __restrict__ out = p.persons + (size_t)b * p.max_persons * J * 3;
+    for (int r = 0; r < n; ++r) {
+      if (rep[r] != r) continue;
+      int size = 0;
+      for (int i = r + lane; i < n; i += 32) size += rep[i] == r ? 1 : 0;
+      size = __reduce_add_sync(kFull, size);
+      if (size > J) mutant = 1;                                     // :703-706
+      if (size <= 1) continue;                                      // :708
+      int valid = 0;
+      for (int t = lane; t < J; t += 32) {
+        float best = -1.f;
+        int bi = -1;
+        for (int i = r; i < n; ++i)
+          if (rep[i] == r && typ[i] == t && pn[i] > best) { best = pn[i]; bi = i; }   // first maximum, :718
+        double x = 0, y = 0, sc = 0;
+        if (bi >= 0) {
+          x = (double)p.joint_det[(n0 + bi) * 3 + 0];
+          y = (double)p.joint_det[(n0 + bi) * 3 + 1];
+          sc = (double)best;
+          if (best > 0.f) valid = 1;
+        }
+        if (n_person < p.max_persons) {
+          out[((size_t)n_person * J + t) * 3 + 0] = x;
+          out[((size_t)n_person * J + t) * 3 + 1] = y;
+          out[((size_t)n_person * J + t) * 3 + 2] = sc;
+        }
+      }
+      valid = __any_sync(kFull, valid);
+      if (valid) ++n_person;                                        // :725
+    }
+    if (lane == 0) { p.num_persons[b] = n_person; p.mutants[b] = mutant; }
+  }
+}
+
+int max_nodes_of(const pgmp_group_params& p) { return p.max_nodes_per_image; }
+
+}  // namespace
+}  // namespace pgmp
 
 using namespace pgmp;
 
 extern "C" uint64_t pgmp_group_workspace_bytes(const pgmp_group_params* p) {
-  (void)p;
-  return 0;
+  if (!p || p->batch <= 0 || p->max_nodes_per_image <= 0) return 0;
+  pgmp_group_params q = *p;
+  q.workspace = nullptr;
+  return carve(q, q.max_nodes_per_image).bytes;
 }
 
 extern "C" int pgmp_group_persons(const pgmp_group_params* p, pgmp_stream_t stream) {
-  (void)p; (void)stream;
-  return set_error(PGMP_ERR_INVALID, "pgmp_group_persons: not built yet");
+  if (!p) return set_error(PGMP_ERR_INVALID, "null params");
+  if (p->batch <= 0 || p->num_joints <= 0 || p->num_joints > 64 || p->max_nodes_per_image <= 0 || p->max_persons <= 0)
+    return set_error(PGMP_ERR_INVALID, "bad sizes");
+  if (!p->node_offsets || !p->edge_offsets || !p->joint_det || !p->node_logits || !p->person_labels ||
+      !p->num_components || !p->num_kept_edges || !p->persons || !p->num_persons || !p->mutants || !p->workspace)
+    return set_error(PGMP_ERR_INVALID, "null device pointer");
+  if (p->num_edges > 0 && (!p->edge_index || !p->edge_logits)) return set_error(PGMP_ERR_INVALID, "null edge pointer");
+  const GroupWs w = carve(*p, p->max_nodes_per_image);
+  if (w.bytes > p->workspace_bytes) return set_error(PGMP_ERR_INVALID, "workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PGMP_LAUNCH(group_kernel, p->batch, kThreads, 0, st, *p, w, p->max_nodes_per_image);
+  return PGMP_OK;
 }

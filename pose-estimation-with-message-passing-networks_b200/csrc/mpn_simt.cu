@@ -288,14 +288,24 @@ __global__ void __launch_bounds__(kTile) edge_step_kernel(const EdgeStepArgs a) 
 // Edge head (NodeClassificationMPNSimple.py:84) as its own pass over the slot-ordered edge features
 // (used by the tensor-core mode, whose step kernel does not carry the head).
 __global__ void __launch_bounds__(kTile) edge_head_kernel(const float* __restrict__ g, const int32_t* __restrict__ slot_edge,
-                                                          const int32_t* __restrict__ group_start, int T,
+                                                          const int32_t* __restrict__ group_start, int T, int image,
                                                           const pgmp_mlp head, float* __restrict__ edge_logits) {
   extern __shared__ __align__(16) float smem[];
   float* buf = smem;
   float* ws = buf + kD * kTileP;
   const int64_t slot0 = (int64_t)blockIdx.x * kTile;
   if (slot0 >= group_start[T]) return;
-  load_tile_rowmajor(buf, g, slot0, slot0 + kTile, kD);
+  if (image) {   // tensor-core mode keeps the edge features as bf16 hi/lo SWIZZLE_128B tile images
+    const uint16_t* __restrict__ img = reinterpret_cast<const uint16_t*>(g) + (size_t)blockIdx.x * kTile * kD * 2;
+    for (int idx = threadIdx.x; idx < kTile * kD; idx += blockDim.x) {
+      const int r = idx >> 6, c = idx & 63;
+      const int off = ((r >> 3) * 1024 + (r & 7) * 128 + (((c >> 3) ^ (r & 7)) << 4)) / 2 + (c & 7);
+      const float hi = __uint_as_float((uint32_t)img[off] << 16), lo = __uint_as_float((uint32_t)img[off + kTile * kD] << 16);
+      buf[(size_t)c * kTileP + r] = hi + lo;
+    }
+  } else {
+    load_tile_rowmajor(buf, g, slot0, slot0 + kTile, kD);
+  }
   run_small_chain(head, buf, buf, ws);
   const int e = slot_edge[slot0 + threadIdx.x];
   if (e >= 0) edge_logits[e] = buf[threadIdx.x];
@@ -379,7 +389,7 @@ int mpn_node_update(const pgmp_mpn_params& p, const MpnWorkspace& w, int out_slo
   return PGMP_OK;
 }
 
-int mpn_edge_head(const pgmp_mpn_params& p, const MpnWorkspace& w, int out_slot, cudaStream_t st) {
+int mpn_edge_head(const pgmp_mpn_params& p, const MpnWorkspace& w, int out_slot, bool image, cudaStream_t st) {
   const size_t smem = sizeof(float) * (kD * kTileP + kWs);
   static bool attr = false;
   if (!attr) {
@@ -387,7 +397,7 @@ int mpn_edge_head(const pgmp_mpn_params& p, const MpnWorkspace& w, int out_slot,
     attr = true;
   }
   PGMP_LAUNCH(edge_head_kernel, (unsigned)(w.max_slots / kTile), kTile, smem, st, w.g, w.slot_edge, w.group_start,
-              p.num_types, p.edge_head, p.edge_logits + (size_t)out_slot * p.num_edges);
+              p.num_types, image ? 1 : 0, p.edge_head, p.edge_logits + (size_t)out_slot * p.num_edges);
   return PGMP_OK;
 }
 

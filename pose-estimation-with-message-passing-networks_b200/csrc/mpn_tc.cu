@@ -19,7 +19,7 @@ namespace pgmp {
 int mpn_embed(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t st);
 int mpn_node_tables(const pgmp_mpn_params& p, const MpnWorkspace& w, const float* h, cudaStream_t st);
 int mpn_node_update(const pgmp_mpn_params& p, const MpnWorkspace& w, int out_slot, cudaStream_t st);
-int mpn_edge_head(const pgmp_mpn_params& p, const MpnWorkspace& w, int out_slot, cudaStream_t st);
+int mpn_edge_head(const pgmp_mpn_params& p, const MpnWorkspace& w, int out_slot, bool image, cudaStream_t st);
 int mpn_node_tables_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, const float* h, cudaStream_t st);
 int mpn_node_update_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, int out_slot, cudaStream_t st);
 
@@ -29,7 +29,11 @@ using namespace umma;
 
 constexpr int kATile = kTile * 128;        // bytes of one [128][64] bf16 operand tile
 constexpr int kWTile = kD * 128;           // bytes of one [64][64] bf16 weight tile
-constexpr int kTmemCols = 64;
+constexpr int kAddTile = kTile * kD * 4;   // bytes of one [128][64] fp32 staging tile
+constexpr int kTmemCols = 64;              // selftest kernel
+constexpr int kWgThreads = 128;            // one warpgroup = one tile in flight
+constexpr int kEdgeThreads = 2 * kWgThreads;
+constexpr int kEdgeTmemCols = 256;         // 2 warpgroups x (message / hidden accumulator + head accumulator)
 
 struct EdgeTcArgs {
   const int32_t* slot_edge; const int32_t* slot_src; const int32_t* slot_dst;
@@ -40,198 +44,293 @@ struct EdgeTcArgs {
   float* part_val; float* part_mx; float* part_se;
   int64_t N;
   int T, per_type, aggr, attn, attn_cols;
+  // fused edge head 64 -> 64 -> 32 -> 1 (NodeClassificationMPNSimple.py:84), only when with_head
+  int with_head;
+  const __nv_bfloat16* wh1; const __nv_bfloat16* wh2;   // [2][64][64], [2][32][64]
+  const float* bh1; const float* bh2; const float* wh3; const float* bh3;
+  float* edge_logits;
 };
 
-struct TcSmem {
-  uint8_t* a_hi; uint8_t* a_lo;
-  uint8_t* w1_hi; uint8_t* w1_lo; uint8_t* w2_hi; uint8_t* w2_lo; uint8_t* wm_hi; uint8_t* wm_lo;
-  float* m;          // [128][64] fp32, 16-byte chunks XOR-swizzled by row; aliases a_hi / a_lo
-  float* att; int* dst; float* b2; float* wa;
-  uint64_t* bar; uint32_t* tmem;
-};
-constexpr size_t kTcSmemBytes = 2 * kATile + 6 * kWTile + sizeof(float) * (kTile + kD + kD) + sizeof(int) * kTile + 64 + 1024;
+// ---- shared-memory map of the edge kernel (offsets from the 1024-aligned base) ----------------------
+constexpr int kOffW1 = 0;                              // hi, lo
+constexpr int kOffW2 = kOffW1 + 2 * kWTile;
+constexpr int kOffWh1 = kOffW2 + 2 * kWTile;
+constexpr int kOffWh2 = kOffWh1 + 2 * kWTile;          // [32][64] hi, lo
+constexpr int kOffConst = kOffWh2 + 2 * (kWTile / 2);  // b2[64] bh1[64] bh2[32] wh3[32] (floats)
+constexpr int kOffWg = kOffConst + 1024;               // per-warpgroup regions follow
+constexpr int kWgA = 0;                                // A hi, lo
+constexpr int kWgAdd = kWgA + 2 * kATile;              // fp32 staging: g in, C+P+Q, R, then the messages
+constexpr int kWgWm = kWgAdd + kAddTile;               // message weights hi, lo
+constexpr int kWgMisc = kWgWm + 2 * kWTile;            // dst[128] src[128] att[128] wa[64] bar
+constexpr int kWgBytes = kWgMisc + 2048;
+constexpr size_t kEdgeSmemBytes = kOffWg + 2 * kWgBytes + 64 + 1024;
 
-__device__ __forceinline__ TcSmem carve_smem(uint8_t* raw) {
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
-  TcSmem s;
-  s.a_hi = base; s.a_lo = base + kATile;
-  s.w1_hi = base + 2 * kATile; s.w1_lo = s.w1_hi + kWTile; s.w2_hi = s.w1_lo + kWTile; s.w2_lo = s.w2_hi + kWTile;
-  s.wm_hi = s.w2_lo + kWTile; s.wm_lo = s.wm_hi + kWTile;
-  s.m = reinterpret_cast<float*>(base);
-  uint8_t* misc = s.wm_lo + kWTile;
-  s.att = reinterpret_cast<float*>(misc);
-  s.dst = reinterpret_cast<int*>(s.att + kTile);
-  s.b2 = reinterpret_cast<float*>(s.dst + kTile);
-  s.wa = s.b2 + kD;
-  s.bar = reinterpret_cast<uint64_t*>(s.wa + kD);
-  s.tmem = reinterpret_cast<uint32_t*>(s.bar + 1);
-  return s;
-}
-
-__device__ __forceinline__ int m_index(int row, int col) {   // float index into the swizzled m tile
+__device__ __forceinline__ int stage_index(int row, int col) {   // float index into a swizzled [128][64] fp32 tile
   return row * kD + ((((col >> 2) ^ (row & 15)) << 2) | (col & 3));
 }
 
-// all threads: publish shared-memory operand writes and TMEM reads, then one thread issues the GEMM
-__device__ __forceinline__ void sync_and_issue(const TcSmem& s, uint32_t tmem, uint8_t* w_hi, uint8_t* w_lo) {
+__global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const EdgeTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sbase = smem_u32(base);
+  const int tid = threadIdx.x, wg = tid >> 7, wt = tid & 127, warp = tid >> 5;
+  const uint32_t w1_hi = sbase + kOffW1, w1_lo = w1_hi + kWTile, w2_hi = sbase + kOffW2, w2_lo = w2_hi + kWTile;
+  const uint32_t wh1_hi = sbase + kOffWh1, wh1_lo = wh1_hi + kWTile, wh2_hi = sbase + kOffWh2, wh2_lo = wh2_hi + kWTile / 2;
+  float* s_const = reinterpret_cast<float*>(base + kOffConst);
+  float* s_b2 = s_const; float* s_bh1 = s_const + 64; float* s_bh2 = s_const + 128; float* s_wh3 = s_const + 160;
+  uint8_t* wgb = base + kOffWg + wg * kWgBytes;
+  const uint32_t a_hi = smem_u32(wgb) + kWgA, a_lo = a_hi + kATile;
+  const uint32_t add_a = smem_u32(wgb) + kWgAdd;
+  const uint32_t wm_hi = smem_u32(wgb) + kWgWm, wm_lo = wm_hi + kWTile;
+  int* s_dst = reinterpret_cast<int*>(wgb + kWgMisc);
+  int* s_src = s_dst + kTile;
+  float* s_att = reinterpret_cast<float*>(s_src + kTile);
+  float* s_wa = s_att + kTile;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_wa + kD);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base + kOffWg + 2 * kWgBytes);
+  const float* s_add = reinterpret_cast<const float*>(wgb + kWgAdd);
+
+  if (warp == 0) tmem_alloc<kEdgeTmemCols>(tmem_slot);
+  if (wt == 0) mbar_init(bar, 1);
+  if (tid == 0) fence_barrier_init();
+  load_weight_tile_a(w1_hi, a.w1, kD, kD, tid, kEdgeThreads);
+  load_weight_tile_a(w1_lo, a.w1 + kD * kD, kD, kD, tid, kEdgeThreads);
+  load_weight_tile_a(w2_hi, a.w2, kD, kD, tid, kEdgeThreads);
+  load_weight_tile_a(w2_lo, a.w2 + kD * kD, kD, kD, tid, kEdgeThreads);
+  if (a.with_head) {
+    load_weight_tile_a(wh1_hi, a.wh1, kD, kD, tid, kEdgeThreads);
+    load_weight_tile_a(wh1_lo, a.wh1 + kD * kD, kD, kD, tid, kEdgeThreads);
+    load_weight_tile_a(wh2_hi, a.wh2, 32, kD, tid, kEdgeThreads);
+    load_weight_tile_a(wh2_lo, a.wh2 + 32 * kD, 32, kD, tid, kEdgeThreads);
+    if (tid < kD) s_bh1[tid] = a.bh1[tid];
+    if (tid < 32) { s_bh2[tid] = a.bh2[tid]; s_wh3[tid] = a.wh3[tid]; }
+  }
+  if (tid < kD) s_b2[tid] = a.b2[tid];
+  if (wt < kD) s_wa[wt] = 0.f;
   fence_before_sync();
   fence_async_smem();
   __syncthreads();
-  if (threadIdx.x == 0) {
-    fence_after_sync();
-    issue_gemm_x3<kD>(tmem, smem_u32(s.a_hi), smem_u32(s.a_lo), 0, smem_u32(w_hi), smem_u32(w_lo), 0, 1, false);
-    mma_commit(s.bar);
-  }
-}
-
-__global__ void __launch_bounds__(kTile) edge_step_tc_kernel(const EdgeTcArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  const TcSmem s = carve_smem(smem_raw);
-  const int tid = threadIdx.x, warp = tid >> 5;
-  if (warp == 0) tmem_alloc<kTmemCols>(s.tmem);
-  if (tid == 0) {
-    mbar_init(s.bar, 1);
-    fence_barrier_init();
-  }
-  load_weight_tile(s.w1_hi, a.w1, kD, kD);
-  load_weight_tile(s.w1_lo, a.w1 + kD * kD, kD, kD);
-  load_weight_tile(s.w2_hi, a.w2, kD, kD);
-  load_weight_tile(s.w2_lo, a.w2 + kD * kD, kD, kD);
-  if (tid < kD) {
-    s.b2[tid] = a.b2[tid];
-    s.wa[tid] = 0.f;
-  }
-  fence_before_sync();
-  __syncthreads();
   fence_after_sync();
-  const uint32_t tmem = *s.tmem;
+  const uint32_t tmem = *tmem_slot + (uint32_t)(wg * 128);   // this warpgroup's 128 columns
+  const int bar_id = 1 + wg;
   uint32_t phase = 0;
   int cur_tm = -1, cur_col = -1;
 
   const int total_tiles = a.group_start[a.T] >> 7;
-  const int per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
-  const int tile_begin = blockIdx.x * per_cta;
-  const int tile_end = min(tile_begin + per_cta, total_tiles);
+  const int units = 2 * gridDim.x;
+  const int per_unit = (total_tiles + units - 1) / units;
+  const int tile_begin = (blockIdx.x * 2 + wg) * per_unit;
+  const int tile_end = min(tile_begin + per_unit, total_tiles);
 
+  // per-row indices of the first tile (later tiles are prefetched one tile ahead)
+  int n_e = -1, n_src = -1, n_dst = -1;
+  if (tile_begin < tile_end) {
+    const int64_t sl = (int64_t)tile_begin * kTile + wt;
+    n_e = a.slot_edge[sl]; n_src = a.slot_src[sl]; n_dst = a.slot_dst[sl];
+  }
   for (int tile = tile_begin; tile < tile_end; ++tile) {
     const int64_t slot0 = (int64_t)tile * kTile;
     int t = 0;
     while (t + 1 < a.T && slot0 >= a.group_start[t + 1]) ++t;
     const int tm = a.per_type ? t : 0;
     const int col = a.attn == PGMP_ATTN_PER_TYPE ? t : 0;
-    if (tm != cur_tm) {     // the previous tile's MMAs have completed (we waited on them)
-      load_weight_tile(s.wm_hi, a.wm + (size_t)tm * 2 * kD * kD, kD, kD);
-      load_weight_tile(s.wm_lo, a.wm + (size_t)tm * 2 * kD * kD + kD * kD, kD, kD);
+    // ---- everything this tile needs from global memory is requested up front:
+    //      g (bf16 hi/lo tile image) straight into the operand tiles, C into the staging tile (LDGSTS, no registers)
+    {
+      const uint8_t* __restrict__ gsrc = reinterpret_cast<const uint8_t*>(a.g) + (size_t)tile * (2 * kATile);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int idx = wt + k * kWgThreads;
+        cp_async16(a_hi + idx * 16, gsrc + idx * 16);
+      }
+      if (a.c0) {
+        const float* __restrict__ csrc = a.c0 + slot0 * kD;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int idx = wt + k * kWgThreads;
+          cp_async16(add_a + 4 * stage_index(idx >> 4, (idx & 15) * 4), csrc + idx * 4);
+        }
+      }
+    }
+    const int e = n_e, src = n_src, dst = n_dst;
+    s_dst[wt] = e >= 0 ? dst : -1;
+    s_src[wt] = e >= 0 ? src : -1;
+    if (tile + 1 < tile_end) {   // next tile's indices
+      const int64_t sl = slot0 + kTile + wt;
+      n_e = a.slot_edge[sl]; n_src = a.slot_src[sl]; n_dst = a.slot_dst[sl];
+    }
+    int bin_ls = 0, bin_lp = 0;   // where this row's bin starts (slots / parts), used by the reduction at the end
+    if (e >= 0) {
+      const int64_t bin = (int64_t)t * a.N + dst;
+      bin_ls = a.bin_lstart[bin];
+      bin_lp = a.bin_lpart[bin];
+    }
+    if (tm != cur_tm) {     // all MMAs of the previous tile have completed
+      load_weight_tile_a(wm_hi, a.wm + (size_t)tm * 2 * kD * kD, kD, kD, wt, kWgThreads);
+      load_weight_tile_a(wm_lo, a.wm + (size_t)tm * 2 * kD * kD + kD * kD, kD, kD, wt, kWgThreads);
       cur_tm = tm;
     }
     if (a.attn && col != cur_col) {
-      if (tid < kD) s.wa[tid] = a.wa[tid * a.attn_cols + col];
+      if (wt < kD) s_wa[wt] = a.wa[wt * a.attn_cols + col];
       cur_col = col;
     }
-    // ---- A <- split(g tile), coalesced 16-byte loads
+    named_bar_sync(bar_id, kWgThreads);          // s_dst / s_src visible
+    // ---- P[dst] + Q[src]: half a warp per row (coalesced 256-byte rows), all 32 loads of a thread in flight
+    float4 pq[16];
     {
-      const float4* __restrict__ g4 = reinterpret_cast<const float4*>(a.g + slot0 * kD);
-#pragma unroll 4
+      float4 qq[16];
+#pragma unroll
       for (int k = 0; k < 16; ++k) {
-        const int idx = tid + k * kTile;
-        store_split4(s.a_hi, s.a_lo, idx >> 4, idx & 15, g4[idx]);
+        const int idx = wt + k * kWgThreads;
+        const int r = idx >> 4, c4 = idx & 15;
+        const int rd = s_dst[r], rs = s_src[r];
+        pq[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        qq[k] = pq[k];
+        if (rd >= 0) {
+          pq[k] = __ldg(reinterpret_cast<const float4*>(a.tab_p + (size_t)rd * kD) + c4);
+          qq[k] = __ldg(reinterpret_cast<const float4*>(a.tab_q + (size_t)rs * kD) + c4);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        pq[k].x += qq[k].x; pq[k].y += qq[k].y; pq[k].z += qq[k].z; pq[k].w += qq[k].w;
       }
     }
-    sync_and_issue(s, tmem, s.w1_hi, s.w1_lo);
-
-    const int64_t slot = slot0 + tid;
-    const int e = a.slot_edge[slot];
-    const int src = a.slot_src[slot], dst = a.slot_dst[slot];
-    float add[kD], d[kD];
-    if (e >= 0) {     // per-edge constant + per-node tables, fetched while the MMA runs
-      const float4* __restrict__ p4 = reinterpret_cast<const float4*>(a.tab_p + (size_t)dst * kD);
-      const float4* __restrict__ q4 = reinterpret_cast<const float4*>(a.tab_q + (size_t)src * kD);
-      const float4* __restrict__ c4 = a.c0 ? reinterpret_cast<const float4*>(a.c0 + slot * kD) : nullptr;
-#pragma unroll
-      for (int q = 0; q < kD / 4; ++q) {
-        const float4 p = p4[q], sq = q4[q];
-        float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c4) c = c4[q];
-        add[4 * q + 0] = c.x + p.x + sq.x;
-        add[4 * q + 1] = c.y + p.y + sq.y;
-        add[4 * q + 2] = c.z + p.z + sq.z;
-        add[4 * q + 3] = c.w + p.w + sq.w;
-      }
-    } else {
-#pragma unroll
-      for (int o = 0; o < kD; ++o) add[o] = 0.f;
+    cp_async_wait_all();
+    fence_async_smem();
+    named_bar_sync(bar_id, kWgThreads);          // operand tiles complete
+    if (wt == 0) {
+      fence_after_sync();
+      issue_gemm_x3<kD>(tmem, a_hi, a_lo, 0, w1_hi, w1_lo, 0, 1, false);
+      mma_commit(bar);
     }
-    mbar_wait(s.bar, phase);
+    // ---- staging <- C + P + Q (this thread's own 16-byte items), then R[type][dst] requested into registers
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int idx = wt + k * kWgThreads;
+      const uint32_t ad = add_a + 4 * stage_index(idx >> 4, (idx & 15) * 4);
+      float4 v = pq[k];
+      if (a.c0) {
+        const float4 c = lds128f(ad);
+        v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
+      }
+      sts128f(ad, v);
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int idx = wt + k * kWgThreads;
+      const int rd = s_dst[idx >> 4];
+      pq[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rd >= 0) pq[k] = __ldg(reinterpret_cast<const float4*>(a.tab_r + ((size_t)t * a.N + rd) * kD) + (idx & 15));
+    }
+    named_bar_sync(bar_id, kWgThreads);
+    mbar_wait(bar, phase);
     phase ^= 1;
     fence_after_sync();
+    float d[kD];
     tmem_ld64(tmem, 0, d);
 #pragma unroll
-    for (int o = 0; o < kD; ++o) d[o] = fmaxf(d[o] + add[o], 0.f);
-    store_split_row(s.a_hi, s.a_lo, tid, d);
-    sync_and_issue(s, tmem, s.w2_hi, s.w2_lo);
-
-    if (e >= 0) {     // R[type][dst] for the message, fetched while the MMA runs
-      const float4* __restrict__ r4 = reinterpret_cast<const float4*>(a.tab_r + ((size_t)t * a.N + dst) * kD);
-#pragma unroll
-      for (int q = 0; q < kD / 4; ++q) {
-        const float4 r = r4[q];
-        add[4 * q + 0] = r.x; add[4 * q + 1] = r.y; add[4 * q + 2] = r.z; add[4 * q + 3] = r.w;
-      }
+    for (int q = 0; q < kD / 4; ++q) {
+      const float4 v = lds128f(add_a + 4 * stage_index(wt, 4 * q));
+      d[4 * q + 0] = fmaxf(d[4 * q + 0] + v.x, 0.f);
+      d[4 * q + 1] = fmaxf(d[4 * q + 1] + v.y, 0.f);
+      d[4 * q + 2] = fmaxf(d[4 * q + 2] + v.z, 0.f);
+      d[4 * q + 3] = fmaxf(d[4 * q + 3] + v.w, 0.f);
     }
-    mbar_wait(s.bar, phase);
+    store_split_row_a(a_hi, a_lo, wt, d);
+    fence_before_sync();
+    fence_async_smem();
+    named_bar_sync(bar_id, kWgThreads);
+    if (wt == 0) {
+      fence_after_sync();
+      issue_gemm_x3<kD>(tmem, a_hi, a_lo, 0, w2_hi, w2_lo, 0, 1, false);
+      mma_commit(bar);
+    }
+    // ---- staging <- R (already in registers) while the MMA runs
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int idx = wt + k * kWgThreads;
+      sts128f(add_a + 4 * stage_index(idx >> 4, (idx & 15) * 4), pq[k]);
+    }
+    mbar_wait(bar, phase);
     phase ^= 1;
     fence_after_sync();
     tmem_ld64(tmem, 0, d);
     float att = a.attn ? __ldg(a.ba + col) : 0.f;
 #pragma unroll
     for (int o = 0; o < kD; ++o) {
-      d[o] = fmaxf(d[o] + s.b2[o], 0.f);
-      att = fmaf(d[o], s.wa[o], att);
+      d[o] = fmaxf(d[o] + s_b2[o], 0.f);
+      att = fmaf(d[o], s_wa[o], att);
     }
-    {   // write back g' (row per thread)
-      float4* __restrict__ o4 = reinterpret_cast<float4*>(a.g + slot * kD);
-#pragma unroll
-      for (int q = 0; q < kD / 4; ++q) o4[q] = make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
+    store_split_row_a(a_hi, a_lo, wt, d);
+    s_att[wt] = att;
+    fence_before_sync();
+    fence_async_smem();
+    named_bar_sync(bar_id, kWgThreads);
+    if (wt == 0) {
+      fence_after_sync();
+      issue_gemm_x3<kD>(tmem, a_hi, a_lo, 0, wm_hi, wm_lo, 0, 1, false);
+      if (a.with_head) issue_gemm_x3<kD>(tmem + 64, a_hi, a_lo, 0, wh1_hi, wh1_lo, 0, 1, false);
+      mma_commit(bar);
     }
-    store_split_row(s.a_hi, s.a_lo, tid, d);
-    sync_and_issue(s, tmem, s.wm_hi, s.wm_lo);
-    mbar_wait(s.bar, phase);
+    // ---- write back g' as the bf16 hi/lo tile image (what the next step's MMA consumes), 16-byte coalesced
+    {
+      uint8_t* __restrict__ gdst = reinterpret_cast<uint8_t*>(a.g) + (size_t)tile * (2 * kATile);
+#pragma unroll 4
+      for (int k = 0; k < 16; ++k) {
+        const int idx = wt + k * kWgThreads;
+        const float4 v = lds128f(a_hi + idx * 16);
+        *reinterpret_cast<float4*>(gdst + idx * 16) = v;
+      }
+    }
+    mbar_wait(bar, phase);
     phase ^= 1;
     fence_after_sync();
     tmem_ld64(tmem, 0, d);
-    // ---- message -> shared (aliases the operand tiles: all MMAs reading them are complete)
+    // ---- message m = ReLU(d + R) replaces this thread's own staging row
 #pragma unroll
     for (int q = 0; q < kD / 4; ++q) {
-      float4 v;
-      v.x = fmaxf(d[4 * q + 0] + add[4 * q + 0], 0.f);
-      v.y = fmaxf(d[4 * q + 1] + add[4 * q + 1], 0.f);
-      v.z = fmaxf(d[4 * q + 2] + add[4 * q + 2], 0.f);
-      v.w = fmaxf(d[4 * q + 3] + add[4 * q + 3], 0.f);
-      *reinterpret_cast<float4*>(s.m + m_index(tid, 4 * q)) = v;
+      const uint32_t ad = add_a + 4 * stage_index(wt, 4 * q);
+      const float4 r = lds128f(ad);
+      sts128f(ad, make_float4(fmaxf(d[4 * q + 0] + r.x, 0.f), fmaxf(d[4 * q + 1] + r.y, 0.f),
+                              fmaxf(d[4 * q + 2] + r.z, 0.f), fmaxf(d[4 * q + 3] + r.w, 0.f)));
     }
-    s.att[tid] = att;
-    s.dst[tid] = e >= 0 ? dst : -1;
-    __syncthreads();
+    if (a.with_head) {   // head layer 1 epilogue -> A, layer 2 on the tensor cores
+      tmem_ld64(tmem, 64, d);
+#pragma unroll
+      for (int o = 0; o < kD; ++o) d[o] = fmaxf(d[o] + s_bh1[o], 0.f);
+      named_bar_sync(bar_id, kWgThreads);     // every thread finished reading A for the g' write-back
+      store_split_row_a(a_hi, a_lo, wt, d);
+      fence_before_sync();
+      fence_async_smem();
+      named_bar_sync(bar_id, kWgThreads);
+      if (wt == 0) {
+        fence_after_sync();
+        issue_gemm_x3<32>(tmem + 64, a_hi, a_lo, 0, wh2_hi, wh2_lo, 0, 1, false);
+        mma_commit(bar);
+      }
+    } else {
+      named_bar_sync(bar_id, kWgThreads);
+    }
     // ---- reduce every run of equal targets (a bin, or the part of it inside this tile)
-    if (e >= 0 && (tid == 0 || s.dst[tid - 1] != dst)) {
-      int r1 = tid;
-      while (r1 + 1 < kTile && s.dst[r1 + 1] == dst) ++r1;
-      const int64_t bin = (int64_t)t * a.N + dst;
-      const int first_slot = a.group_start[t] + a.bin_lstart[bin];
-      const int64_t prow = (int64_t)a.group_pstart[t] + a.bin_lpart[bin] + (tile - (first_slot >> 7));
+    if (e >= 0 && (wt == 0 || s_dst[wt - 1] != dst)) {
+      int r1 = wt;
+      while (r1 + 1 < kTile && s_dst[r1 + 1] == dst) ++r1;
+      const int first_slot = a.group_start[t] + bin_ls;
+      const int64_t prow = (int64_t)a.group_pstart[t] + bin_lp + (tile - (first_slot >> 7));
       float u[kD];
       if (a.attn) {
         float mx = -INFINITY;
-        for (int r = tid; r <= r1; ++r) mx = fmaxf(mx, s.att[r]);
+        for (int r = wt; r <= r1; ++r) mx = fmaxf(mx, s_att[r]);
         float se = 0.f;
 #pragma unroll
         for (int o = 0; o < kD; ++o) u[o] = 0.f;
-        for (int r = tid; r <= r1; ++r) {
-          const float wgt = __expf(s.att[r] - mx);
+        for (int r = wt; r <= r1; ++r) {
+          const float wgt = __expf(s_att[r] - mx);
           se += wgt;
 #pragma unroll
           for (int q = 0; q < kD / 4; ++q) {
-            const float4 v = *reinterpret_cast<const float4*>(s.m + m_index(r, 4 * q));
+            const float4 v = lds128f(add_a + 4 * stage_index(r, 4 * q));
             u[4 * q + 0] = fmaf(wgt, v.x, u[4 * q + 0]);
             u[4 * q + 1] = fmaf(wgt, v.y, u[4 * q + 1]);
             u[4 * q + 2] = fmaf(wgt, v.z, u[4 * q + 2]);
@@ -243,13 +342,13 @@ __global__ void __launch_bounds__(kTile) edge_step_tc_kernel(const EdgeTcArgs a)
       } else {
 #pragma unroll
         for (int q = 0; q < kD / 4; ++q) {
-          const float4 v = *reinterpret_cast<const float4*>(s.m + m_index(tid, 4 * q));
+          const float4 v = lds128f(add_a + 4 * stage_index(wt, 4 * q));
           u[4 * q + 0] = v.x; u[4 * q + 1] = v.y; u[4 * q + 2] = v.z; u[4 * q + 3] = v.w;
         }
-        for (int r = tid + 1; r <= r1; ++r) {
+        for (int r = wt + 1; r <= r1; ++r) {
 #pragma unroll
           for (int q = 0; q < kD / 4; ++q) {
-            const float4 v = *reinterpret_cast<const float4*>(s.m + m_index(r, 4 * q));
+            const float4 v = lds128f(add_a + 4 * stage_index(r, 4 * q));
             if (a.aggr == PGMP_AGGR_MAX) {
               u[4 * q + 0] = fmaxf(u[4 * q + 0], v.x); u[4 * q + 1] = fmaxf(u[4 * q + 1], v.y);
               u[4 * q + 2] = fmaxf(u[4 * q + 2], v.z); u[4 * q + 3] = fmaxf(u[4 * q + 3], v.w);
@@ -263,11 +362,69 @@ __global__ void __launch_bounds__(kTile) edge_step_tc_kernel(const EdgeTcArgs a)
 #pragma unroll
       for (int q = 0; q < kD / 4; ++q) o4[q] = make_float4(u[4 * q], u[4 * q + 1], u[4 * q + 2], u[4 * q + 3]);
     }
-    __syncthreads();   // the next tile overwrites the operand / message region
+    if (a.with_head) {   // head layer 2 epilogue and the final 32 -> 1 dot product
+      mbar_wait(bar, phase);
+      phase ^= 1;
+      fence_after_sync();
+      float hv[32];
+      const uint32_t ta = tmem + 64 + ((uint32_t)((warp & 3) * 32) << 16);
+      tmem_ld16(ta, hv);
+      tmem_ld16(ta + 16, hv + 16);
+      tmem_ld_wait();
+      float logit = __ldg(a.bh3);
+#pragma unroll
+      for (int o = 0; o < 32; ++o) logit = fmaf(fmaxf(hv[o] + s_bh2[o], 0.f), s_wh3[o], logit);
+      if (e >= 0) a.edge_logits[e] = logit;
+    }
+    fence_before_sync();
+    named_bar_sync(bar_id, kWgThreads);   // the next tile overwrites the staging / operand tiles
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<kTmemCols>(tmem);
+  if (warp == 0) tmem_dealloc<kEdgeTmemCols>(*tmem_slot);
+}
+
+// fp32 row-major edge features [S][64] -> per-tile bf16 hi/lo operand images (in place, one CTA per tile)
+__global__ void __launch_bounds__(kWgThreads) g_to_image_kernel(float* __restrict__ g, const int32_t* __restrict__ group_start, int T) {
+  const int tile = blockIdx.x;
+  if ((int64_t)tile * kTile >= group_start[T]) return;
+  float4 v[16];
+  const float4* __restrict__ src = reinterpret_cast<const float4*>(g + (size_t)tile * kTile * kD);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = src[threadIdx.x + k * kWgThreads];
+  __syncthreads();   // the whole tile is in registers before any byte of it is overwritten
+  uint8_t* __restrict__ img = reinterpret_cast<uint8_t*>(g) + (size_t)tile * (2 * kATile);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const int idx = threadIdx.x + k * kWgThreads;
+    store_split4(img, img + kATile, idx >> 4, idx & 15, v[k]);
+  }
+}
+
+// ---- selftest ------------------------------------------------------------------------------------------
+struct TcSmem {
+  uint8_t* a_hi; uint8_t* a_lo; uint8_t* w1_hi; uint8_t* w1_lo;
+  uint64_t* bar; uint32_t* tmem;
+};
+constexpr size_t kTcSmemBytes = 2 * kATile + 2 * kWTile + 64 + 1024;
+__device__ __forceinline__ TcSmem carve_smem(uint8_t* raw) {
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  TcSmem s;
+  s.a_hi = base; s.a_lo = base + kATile;
+  s.w1_hi = base + 2 * kATile; s.w1_lo = s.w1_hi + kWTile;
+  s.bar = reinterpret_cast<uint64_t*>(s.w1_lo + kWTile);
+  s.tmem = reinterpret_cast<uint32_t*>(s.bar + 1);
+  return s;
+}
+__device__ __forceinline__ void sync_and_issue(const TcSmem& s, uint32_t tmem, uint8_t* w_hi, uint8_t* w_lo) {
+  fence_before_sync();
+  fence_async_smem();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    fence_after_sync();
+    issue_gemm_x3<kD>(tmem, smem_u32(s.a_hi), smem_u32(s.a_lo), 0, smem_u32(w_hi), smem_u32(w_lo), 0, 1, false);
+    mma_commit(s.bar);
+  }
 }
 
 // D = A . W^T through the same building blocks (pgmp_selftest_umma)
@@ -318,8 +475,9 @@ int mpn_forward_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t
   const int64_t N = p.num_nodes, E = p.num_edges;
   int rc;
   if ((rc = mpn_embed(p, w, st)) != PGMP_OK) return rc;
+  if (E > 0) PGMP_LAUNCH(g_to_image_kernel, (unsigned)(w.max_slots / kTile), kWgThreads, 0, st, w.g, w.group_start, p.num_types);
   PGMP_CUDA(cudaMemcpyAsync(w.h, w.h0, sizeof(float) * N * kD, cudaMemcpyDeviceToDevice, st));
-  PGMP_CUDA(cudaFuncSetAttribute(edge_step_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+  PGMP_CUDA(cudaFuncSetAttribute(edge_step_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdgeSmemBytes));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -333,8 +491,15 @@ int mpn_forward_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t
   a.part_val = w.part_val; a.part_mx = w.part_mx; a.part_se = w.part_se;
   a.N = N; a.T = p.num_types; a.per_type = p.per_type; a.aggr = p.aggr; a.attn = p.attn;
   a.attn_cols = p.attn == PGMP_ATTN_PER_TYPE ? 17 : 1;
-  const unsigned max_tiles = (unsigned)(w.max_slots / kTile);
-  const unsigned grid = max_tiles < (unsigned)(2 * sms) ? max_tiles : (unsigned)(2 * sms);
+  // fused tensor-core edge head when the head is the reference's 64 -> 64 -> 32 -> 1 chain (else a SIMT pass)
+  const pgmp_mlp& eh = p.edge_head;
+  const bool fused_head = p.tc_wh1 && p.tc_wh2 && eh.n_layers == 3 && eh.dims[0] == 64 && eh.dims[1] == 64 &&
+                          eh.dims[2] == 32 && eh.dims[3] == 1 && eh.relu[0] && eh.relu[1] && !eh.relu[2] &&
+                          !eh.post_relu && !eh.post_scale;
+  a.wh1 = static_cast<const __nv_bfloat16*>(p.tc_wh1); a.wh2 = static_cast<const __nv_bfloat16*>(p.tc_wh2);
+  a.bh1 = eh.bias[0]; a.bh2 = eh.bias[1]; a.wh3 = eh.wt[2]; a.bh3 = eh.bias[2];
+  const unsigned max_units = (unsigned)ceil_div<uint64_t>(w.max_slots / kTile, 2);
+  const unsigned grid = max_units < (unsigned)sms ? max_units : (unsigned)sms;
   const int first_out = p.steps - p.aux_loss_steps - 1 > 0 ? p.steps - p.aux_loss_steps - 1 : 0;
   for (int s = 0; s < p.steps; ++s) {
     if (s > 0) {
@@ -343,8 +508,11 @@ int mpn_forward_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t
     }
     if ((rc = mpn_node_tables_tc(p, w, w.h, st)) != PGMP_OK) return rc;
     if (E > 0) {
-      PGMP_LAUNCH(edge_step_tc_kernel, grid, kTile, kTcSmemBytes, st, a);
-      if (s >= first_out && (rc = mpn_edge_head(p, w, s - first_out, st)) != PGMP_OK) return rc;
+      const bool out = s >= first_out;
+      a.with_head = out && fused_head;
+      a.edge_logits = out ? p.edge_logits + (size_t)(s - first_out) * E : nullptr;
+      PGMP_LAUNCH(edge_step_tc_kernel, grid, kEdgeThreads, kEdgeSmemBytes, st, a);
+      if (out && !fused_head && (rc = mpn_edge_head(p, w, s - first_out, true, st)) != PGMP_OK) return rc;
     }
   }
   return node_update((p.steps - 1) - first_out);

@@ -124,6 +124,34 @@ __device__ __forceinline__ void issue_gemm_x3(uint32_t tmem_d, uint32_t a_hi, ui
   }
 }
 
+// ---- explicit shared-state-space accessors (32-bit shared addresses; avoids generic ST/LD) ----------
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void sts128f(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+// 16-byte asynchronous global -> shared copy (LDGSTS), no registers held while in flight
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// sub-CTA barrier: `count` threads meet on hardware barrier `id` (id 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
 // ---- operand tile writers ------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t sw128_offset(int row, int chunk16) {
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk16 ^ (row & 7)) << 4));
@@ -168,6 +196,49 @@ __device__ __forceinline__ void load_weight_tile(uint8_t* tile, const __nv_bfloa
     const int r = idx >> 3, c = idx & 7;
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)r * src_ld + c * 8));
     *reinterpret_cast<uint4*>(tile + sw128_offset(r, c)) = v;
+  }
+}
+
+// address-based variants (shared-space stores)
+__device__ __forceinline__ void store_split4_a(uint32_t hi_tile, uint32_t lo_tile, int row, int col4, float4 v) {
+  __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+  split_bf16(v.x, h0, l0);
+  split_bf16(v.y, h1, l1);
+  split_bf16(v.z, h2, l2);
+  split_bf16(v.w, h3, l3);
+  const uint32_t off = sw128_offset(row, col4 >> 1) + (uint32_t)((col4 & 1) << 3);
+  sts64(hi_tile + off, pack2(h0, h1), pack2(h2, h3));
+  sts64(lo_tile + off, pack2(l0, l1), pack2(l2, l3));
+}
+__device__ __forceinline__ void store_split_row_a(uint32_t hi_tile, uint32_t lo_tile, int row, const float (&v)[64]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    __nv_bfloat16 h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split_bf16(v[8 * c + i], h[i], l[i]);
+    const uint32_t off = sw128_offset(row, c);
+    sts128(hi_tile + off, pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
+    sts128(lo_tile + off, pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
+  }
+}
+// fp32 values of columns col4*4 .. +3 of `row` reconstructed from the hi / lo tiles (hi + lo is exact in fp32)
+__device__ __forceinline__ float4 load_joined4_a(uint32_t hi_tile, uint32_t lo_tile, int row, int col4) {
+  const uint32_t off = sw128_offset(row, col4 >> 1) + (uint32_t)((col4 & 1) << 3);
+  const uint2 h = lds64(hi_tile + off), l = lds64(lo_tile + off);
+  float4 v;
+  v.x = __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
+  v.y = __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u);
+  v.z = __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
+  v.w = __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u);
+  return v;
+}
+// weight tile copy with `n` cooperating threads (thread index `t`)
+__device__ __forceinline__ void load_weight_tile_a(uint32_t tile, const __nv_bfloat16* __restrict__ src, int rows, int src_ld,
+                                                   int t, int n) {
+  for (int idx = t; idx < rows * 8; idx += n) {
+    const int r = idx >> 3, c = idx & 7;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)r * src_ld + c * 8));
+    sts128(tile + sw128_offset(r, c), v.x, v.y, v.z, v.w);
   }
 }
 

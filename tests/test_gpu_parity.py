@@ -206,3 +206,78 @@ def test_mpn_tensor_core_within_logit_tolerance(name):
             a = a.cpu().numpy()
             assert_close(a, b, LOGIT_TOL, f"{name}:{kind}_{i} vs oracle")
             assert_close(a, gold[f"{kind}_{i}"], LOGIT_TOL, f"{name}:{kind}_{i} vs reference")
+
+
+# ------------------------------------------------------------------------------------------------
+# grouping tail: threshold -> GAEC multicut -> persons (bit-exact on identical logits)
+# ------------------------------------------------------------------------------------------------
+def _oracle_graph_for(gc_name):
+    data, gcfg, nj = gc_inputs(gc_name)
+    return oracle.gc.construct_graph(data["scoremaps"], data["tagmaps"], data["features"], gcfg, nj, masks=data["masks"]), nj
+
+
+def _check_grouping(g, nj, logits, th, gold=None):
+    from pgmp_b200.Utils import group_persons
+    res = group_persons(torch.from_numpy(g["joint_det"]).to(DEV), torch.from_numpy(logits["node_logits"]).to(DEV),
+                        torch.from_numpy(g["edge_index"]).to(DEV), torch.from_numpy(logits["edge_logits"]).to(DEV),
+                        torch.from_numpy(logits["class_logits"]).to(DEV), torch.from_numpy(g["batch_index"]).to(DEV),
+                        nj, node_threshold=th)
+    assert len(res) == len(np.unique(g["batch_index"]))
+    for b, got in enumerate(res):
+        sub = synthetic.image_subgraph(g, logits, b)
+        want = oracle.grouping.pred_to_person(sub["joint_det"], sub["node_logits"], sub["edge_index"],
+                                              sub["edge_logits"], sub["class_logits"], th, nj)
+        if want is None:
+            assert got is None
+            continue
+        persons, mutant, labels = got
+        wp, wm, wl = want
+        assert np.array_equal(labels.cpu().numpy(), wl), f"image {b}: person labels differ"
+        assert persons.shape == wp.shape and bool(mutant) == bool(wm)
+        if wp.size:
+            assert np.array_equal(persons[:, :, :2], wp[:, :, :2])
+            np.testing.assert_allclose(persons[:, :, 2], wp[:, :, 2], rtol=1e-6)
+        if gold is not None:
+            assert np.array_equal(labels.cpu().numpy(), gold[f"labels_{b}"])
+            assert np.array_equal(persons[:, :, :2], gold[f"persons_{b}"][:, :, :2])
+
+
+@pytest.mark.parametrize("name,gc_name,seed", [("group_knn_small", "knn_small", 0), ("group_fully_small", "fully_small", 1),
+                                               ("group_crowdpose", "crowdpose", 2)])
+def test_grouping_bit_exact_on_identical_logits(name, gc_name, seed):
+    g, nj = _oracle_graph_for(gc_name)
+    logits = synthetic.synth_group_logits(g["joint_det"], g["batch_index"], g["edge_index"], num_joints=nj, seed=seed)
+    _check_grouping(g, nj, logits, 0.1, golden(name))
+
+
+def test_grouping_edge_cases():
+    g, nj = _oracle_graph_for("knn_small")
+    logits = synthetic.synth_group_logits(g["joint_det"], g["batch_index"], g["edge_index"], num_joints=nj, seed=5)
+    # every node below the threshold in image 1 -> no kept edge -> None (Utils.py:1452,1457)
+    lo = dict(logits, node_logits=logits["node_logits"].copy())
+    lo["node_logits"][g["batch_index"] == 1] = -20.0
+    _check_grouping(g, nj, lo, 0.1)
+    # all edges repulsive -> singletons only -> no persons; all attractive -> one person per image
+    _check_grouping(g, nj, dict(logits, edge_logits=-np.abs(logits["edge_logits"]) - 0.1), 0.1)
+    _check_grouping(g, nj, dict(logits, edge_logits=np.abs(logits["edge_logits"]) + 0.1), 0.5)
+
+
+def test_full_pipeline_heatmaps_to_persons():
+    """construct_graph -> mpn.forward -> group_persons entirely on the device; the grouping must equal the
+    oracle's grouping of the same logits."""
+    from pgmp_b200.Utils import group_persons
+    ret, _ = run_gc("knn_small")
+    cfg, g, model = mpn_case("flagship")
+    with torch.no_grad():
+        pe, pn, pc, _ = model(ret[0], ret[1], ret[2], node_types=ret[7][:, 2])
+    res = group_persons(ret[7], pn[-1], ret[2], pe[-1], pc[-1], ret[12], 17, node_threshold=0.5, detector_scores=ret[11])
+    logits = dict(node_logits=pn[-1].cpu().numpy(), edge_logits=pe[-1].cpu().numpy(), class_logits=pc[-1].cpu().numpy(),
+                  num_joints=17)
+    for b, got in enumerate(res):
+        sub = synthetic.image_subgraph(g, logits, b)
+        want = oracle.grouping.pred_to_person(sub["joint_det"], sub["node_logits"], sub["edge_index"],
+                                              sub["edge_logits"], sub["class_logits"], 0.5, 17)
+        assert (got is None) == (want is None)
+        if want is not None:
+            assert np.array_equal(got[2].cpu().numpy(), want[2])
+            assert got[0].shape == want[0].shape
