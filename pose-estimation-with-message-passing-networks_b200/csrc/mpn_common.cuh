@@ -36,6 +36,9 @@ struct MpnWorkspace {
   // features
   float* h0;              // [N][64] node embedding
   float* h;               // [N][64] current node feature
+  float* h0_img;          // tensor-core mode: bf16 hi/lo operand images of h0 / h, one 32 KB image per 128 nodes
+  float* h_img;
+  float* upd_partial;     // tensor-core mode: [4][ceil128(N)][64] partial node updates (type groups)
   float* g;               // [S][64] current edge feature (slot order), updated in place
   float* c0;              // [S][64] W1_e0 * g0 + b1 (skip only)
   float* tab_p;           // [N][64] W1_dst * x_i (+ b1 when !skip)
@@ -69,6 +72,11 @@ inline MpnWorkspace carve_mpn(const pgmp_mpn_params& p) {
   w.slot_dst = c.take<int32_t>(w.max_slots);
   w.h0 = c.take<float>(N * kD);
   w.h = c.take<float>(N * kD);
+  const uint64_t Np = round_up<uint64_t>(N, kTile);
+  const bool tc = p.precision == PGMP_PRECISION_TC;
+  w.h0_img = c.take<float>(tc ? Np * kD : 0);
+  w.h_img = c.take<float>(tc ? Np * kD : 0);
+  w.upd_partial = c.take<float>(tc ? 4 * Np * kD : 0);
   w.g = c.take<float>(w.max_slots * kD);
   w.c0 = c.take<float>(p.skip ? w.max_slots * kD : 0);
   w.tab_p = c.take<float>(N * kD);

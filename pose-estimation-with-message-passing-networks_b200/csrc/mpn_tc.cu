@@ -20,7 +20,8 @@ int mpn_embed(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t st);
 int mpn_node_tables(const pgmp_mpn_params& p, const MpnWorkspace& w, const float* h, cudaStream_t st);
 int mpn_node_update(const pgmp_mpn_params& p, const MpnWorkspace& w, int out_slot, cudaStream_t st);
 int mpn_edge_head(const pgmp_mpn_params& p, const MpnWorkspace& w, int out_slot, bool image, cudaStream_t st);
-int mpn_node_tables_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, const float* h, cudaStream_t st);
+int mpn_node_tables_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, const float* h_img, cudaStream_t st);
+int mpn_node_image(const MpnWorkspace& w, const float* h, int64_t N, float* img, cudaStream_t st);
 int mpn_node_update_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, int out_slot, cudaStream_t st);
 
 namespace {
@@ -470,13 +471,15 @@ int mpn_forward_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t
     return set_error(PGMP_ERR_INVALID, "PGMP_PRECISION_TC needs the bf16 hi/lo weights");
   // the node update runs on the tensor cores when it is a matrix product (update MLP), else it is a plain merge
   auto node_update = [&](int out_slot) {
-    return p.has_update_mlp ? mpn_node_update_tc(p, w, out_slot, st) : mpn_node_update(p, w, out_slot, st);
+    if (p.has_update_mlp) return mpn_node_update_tc(p, w, out_slot, st);
+    const int r = mpn_node_update(p, w, out_slot, st);          // plain merge (agnostic layer without update MLP)
+    return r != PGMP_OK ? r : mpn_node_image(w, w.h, p.num_nodes, w.h_img, st);
   };
   const int64_t N = p.num_nodes, E = p.num_edges;
   int rc;
   if ((rc = mpn_embed(p, w, st)) != PGMP_OK) return rc;
   if (E > 0) PGMP_LAUNCH(g_to_image_kernel, (unsigned)(w.max_slots / kTile), kWgThreads, 0, st, w.g, w.group_start, p.num_types);
-  PGMP_CUDA(cudaMemcpyAsync(w.h, w.h0, sizeof(float) * N * kD, cudaMemcpyDeviceToDevice, st));
+  if ((rc = mpn_node_image(w, w.h0, N, w.h0_img, st)) != PGMP_OK) return rc;
   PGMP_CUDA(cudaFuncSetAttribute(edge_step_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdgeSmemBytes));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -506,7 +509,7 @@ int mpn_forward_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t
       const int prev_slot = (s - 1) >= first_out ? (s - 1) - first_out : -1;
       if ((rc = node_update(prev_slot)) != PGMP_OK) return rc;
     }
-    if ((rc = mpn_node_tables_tc(p, w, w.h, st)) != PGMP_OK) return rc;
+    if ((rc = mpn_node_tables_tc(p, w, s == 0 ? w.h0_img : w.h_img, st)) != PGMP_OK) return rc;
     if (E > 0) {
       const bool out = s >= first_out;
       a.with_head = out && fused_head;
