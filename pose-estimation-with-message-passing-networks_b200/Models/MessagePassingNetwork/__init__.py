@@ -183,6 +183,14 @@ class NodeClassificationMPNSimple(nn.Module):
                   tc_wm_e=torch.stack([split(l.weight[:, nd:]) for l in lins]).contiguous(),
                   tc_wtab=torch.stack([split(W1[:, :nd]), split(W1[:, nd:2 * nd])] +
                                       [split(l.weight[:, :nd]) for l in lins]).contiguous())
+        emb_w = spec["edge_embedding"][2]           # folded Linear weights of the edge embedding
+        if all(max(w.shape) <= 64 for w in emb_w):
+            pad = torch.zeros(len(emb_w), 2, 64, 64, dtype=torch.bfloat16, device=device)
+            for l, w_ in enumerate(emb_w):
+                pad[l, :, :w_.shape[0], :w_.shape[1]] = split(w_)
+            tc["tc_wemb"] = pad.contiguous()
+        if skip:
+            tc["tc_w1_e0"] = split(W1[:, 2 * nd:2 * nd + 64]).contiguous()
         head_w = spec["edge_classification"][2]     # folded Linear weights of the edge head
         if [tuple(w.shape) for w in head_w] == [(64, 64), (32, 64), (1, 32)]:
             tc["tc_wh1"], tc["tc_wh2"] = split(head_w[0]).contiguous(), split(head_w[1]).contiguous()

@@ -324,10 +324,14 @@ int check_small(const pgmp_mlp& m, const char* name, int in_dim, int out_dim) {
 }  // namespace
 
 int mpn_embed(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t st);
+int mpn_embed_impl(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t st, bool with_edges);
+int mpn_embed_nodes(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t st) { return mpn_embed_impl(p, w, st, false); }
 
 // Embeddings shared by both precision modes: h0 = node_embedding(x); g = edge_embedding(edge_attr) in
 // slot order; C = W1_e0 g + b1.
-int mpn_embed(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t st) {
+int mpn_embed(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t st) { return mpn_embed_impl(p, w, st, true); }
+
+int mpn_embed_impl(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t st, bool with_edges) {
   const int64_t N = p.num_nodes;
   auto maxdim = [](const pgmp_mlp& m) { int d = 0; for (int l = 0; l <= m.n_layers; ++l) d = d > m.dims[l] ? d : m.dims[l]; return d; };
   for (const pgmp_mlp* m : {&p.node_emb, &p.edge_emb}) {
@@ -345,7 +349,7 @@ int mpn_embed(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t st) 
     PGMP_LAUNCH((mlp_chain_kernel<64>), ntiles, kTile, smem64, st, p.node_emb, p.x, p.x_stride_n, p.x_stride_c,
                 (const int32_t*)nullptr, N, w.h0, (const float*)nullptr, (const float*)nullptr, (float*)nullptr);
   }
-  if (p.num_edges > 0) {
+  if (with_edges && p.num_edges > 0) {
     const unsigned etiles = (unsigned)(w.max_slots / kTile);
     const int64_t F = p.edge_emb.dims[0];
     const float* ew = p.skip ? p.w1_e0 : nullptr;

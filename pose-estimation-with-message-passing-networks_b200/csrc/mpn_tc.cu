@@ -22,6 +22,8 @@ int mpn_node_update(const pgmp_mpn_params& p, const MpnWorkspace& w, int out_slo
 int mpn_edge_head(const pgmp_mpn_params& p, const MpnWorkspace& w, int out_slot, bool image, cudaStream_t st);
 int mpn_node_tables_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, const float* h_img, cudaStream_t st);
 int mpn_node_image(const MpnWorkspace& w, const float* h, int64_t N, float* img, cudaStream_t st);
+int mpn_edge_embed_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t st, bool* done);
+int mpn_embed_nodes(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t st);
 int mpn_node_update_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, int out_slot, cudaStream_t st);
 
 namespace {
@@ -65,6 +67,7 @@ constexpr int kWgWm = kWgAdd + kAddTile;               // message weights hi, lo
 constexpr int kWgMisc = kWgWm + 2 * kWTile;            // dst[128] src[128] att[128] wa[64] bar
 constexpr int kWgBytes = kWgMisc + 2048;
 constexpr size_t kEdgeSmemBytes = kOffWg + 2 * kWgBytes + 64 + 1024;
+static_assert(kOffWg % 1024 == 0 && kWgBytes % 1024 == 0 && kWgAdd % 1024 == 0 && kWgWm % 1024 == 0, "operand tiles must be 1024-byte aligned");
 
 __device__ __forceinline__ int stage_index(int row, int col) {   // float index into a swizzled [128][64] fp32 tile
   return row * kD + ((((col >> 2) ^ (row & 15)) << 2) | (col & 3));
@@ -477,8 +480,14 @@ int mpn_forward_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t
   };
   const int64_t N = p.num_nodes, E = p.num_edges;
   int rc;
-  if ((rc = mpn_embed(p, w, st)) != PGMP_OK) return rc;
-  if (E > 0) PGMP_LAUNCH(g_to_image_kernel, (unsigned)(w.max_slots / kTile), kWgThreads, 0, st, w.g, w.group_start, p.num_types);
+  bool emb_tc = false;
+  if (E > 0 && (rc = mpn_edge_embed_tc(p, w, st, &emb_tc)) != PGMP_OK) return rc;
+  if (emb_tc) {
+    if ((rc = mpn_embed_nodes(p, w, st)) != PGMP_OK) return rc;
+  } else {          // unusual embedding shapes: SIMT chain, then convert the edge features to operand images
+    if ((rc = mpn_embed(p, w, st)) != PGMP_OK) return rc;
+    if (E > 0) PGMP_LAUNCH(g_to_image_kernel, (unsigned)(w.max_slots / kTile), kWgThreads, 0, st, w.g, w.group_start, p.num_types);
+  }
   if ((rc = mpn_node_image(w, w.h0, N, w.h0_img, st)) != PGMP_OK) return rc;
   PGMP_CUDA(cudaFuncSetAttribute(edge_step_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdgeSmemBytes));
   int dev = 0, sms = 148;
