@@ -59,7 +59,7 @@ constexpr int kOffW1 = 0;                              // hi, lo
 constexpr int kOffW2 = kOffW1 + 2 * kWTile;
 constexpr int kOffWh1 = kOffW2 + 2 * kWTile;
 constexpr int kOffWh2 = kOffWh1 + 2 * kWTile;          // [32][64] hi, lo
-constexpr int kOffConst = kOffWh2 + 2 * (kWTile / 2);  // b2[64] bh1[64] bh2[32] wh3[32] (floats)
+constexpr int kOffConst = kOffWh2 + 2 * (kWTile / 2);  // b2[64] bh1[64] bh2[32] wh3[32] (floats), group_start[18], group_pstart[18]
 constexpr int kOffWg = kOffConst + 1024;               // per-warpgroup regions follow
 constexpr int kWgA = 0;                                // A hi, lo
 constexpr int kWgAdd = kWgA + 2 * kATile;              // fp32 staging: g in, C+P+Q, R, then the messages
@@ -82,6 +82,8 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
   const uint32_t wh1_hi = sbase + kOffWh1, wh1_lo = wh1_hi + kWTile, wh2_hi = sbase + kOffWh2, wh2_lo = wh2_hi + kWTile / 2;
   float* s_const = reinterpret_cast<float*>(base + kOffConst);
   float* s_b2 = s_const; float* s_bh1 = s_const + 64; float* s_bh2 = s_const + 128; float* s_wh3 = s_const + 160;
+  int* s_gstart = reinterpret_cast<int*>(s_const + 192);     // [T + 1] first slot of each type group
+  int* s_gpstart = s_gstart + 20;                            // [T + 1] first part row of each type group
   uint8_t* wgb = base + kOffWg + wg * kWgBytes;
   const uint32_t a_hi = smem_u32(wgb) + kWgA, a_lo = a_hi + kATile;
   const uint32_t add_a = smem_u32(wgb) + kWgAdd;
@@ -110,6 +112,7 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
     if (tid < 32) { s_bh2[tid] = a.bh2[tid]; s_wh3[tid] = a.wh3[tid]; }
   }
   if (tid < kD) s_b2[tid] = a.b2[tid];
+  if (tid <= a.T) { s_gstart[tid] = a.group_start[tid]; s_gpstart[tid] = a.group_pstart[tid]; }
   if (wt < kD) s_wa[wt] = 0.f;
   fence_before_sync();
   fence_async_smem();
@@ -119,6 +122,12 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
   const int bar_id = 1 + wg;
   uint32_t phase = 0;
   int cur_tm = -1, cur_col = -1;
+  // cooperative passes: item k of this thread is the 16-byte chunk c4 = wt & 15 of row (wt >> 4) + 8k; its
+  // swizzled staging address alternates between two precomputed bases (row & 15 = r0 | (k & 1) << 3)
+  const uint32_t r0 = (uint32_t)(wt >> 4), c4c = (uint32_t)(wt & 15);
+  const uint32_t item_e = add_a + r0 * 256 + ((c4c ^ r0) << 4), item_o = add_a + r0 * 256 + ((c4c ^ r0 ^ 8u) << 4);
+#define ITEM_ADDR(k) ((((k) & 1) ? item_o : item_e) + (uint32_t)(k) * 2048u)
+  bool g_prefetched = false;
 
   const int total_tiles = a.group_start[a.T] >> 7;
   const int units = 2 * gridDim.x;
@@ -135,25 +144,21 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
   for (int tile = tile_begin; tile < tile_end; ++tile) {
     const int64_t slot0 = (int64_t)tile * kTile;
     int t = 0;
-    while (t + 1 < a.T && slot0 >= a.group_start[t + 1]) ++t;
+    while (t + 1 < a.T && slot0 >= s_gstart[t + 1]) ++t;
     const int tm = a.per_type ? t : 0;
     const int col = a.attn == PGMP_ATTN_PER_TYPE ? t : 0;
     // ---- everything this tile needs from global memory is requested up front:
     //      g (bf16 hi/lo tile image) straight into the operand tiles, C into the staging tile (LDGSTS, no registers)
     {
-      const uint8_t* __restrict__ gsrc = reinterpret_cast<const uint8_t*>(a.g) + (size_t)tile * (2 * kATile);
+      if (!g_prefetched) {
+        const uint8_t* __restrict__ gsrc = reinterpret_cast<const uint8_t*>(a.g) + (size_t)tile * (2 * kATile) + wt * 16;
 #pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const int idx = wt + k * kWgThreads;
-        cp_async16(a_hi + idx * 16, gsrc + idx * 16);
+        for (int k = 0; k < 16; ++k) cp_async16(a_hi + wt * 16 + k * 2048, gsrc + k * 2048);
       }
       if (a.c0) {
-        const float* __restrict__ csrc = a.c0 + slot0 * kD;
+        const float* __restrict__ csrc = a.c0 + slot0 * kD + wt * 4;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const int idx = wt + k * kWgThreads;
-          cp_async16(add_a + 4 * stage_index(idx >> 4, (idx & 15) * 4), csrc + idx * 4);
-        }
+        for (int k = 0; k < 16; ++k) cp_async16(ITEM_ADDR(k), csrc + k * 512);
       }
     }
     const int e = n_e, src = n_src, dst = n_dst;
@@ -211,8 +216,7 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
     // ---- staging <- C + P + Q (this thread's own 16-byte items), then R[type][dst] requested into registers
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      const int idx = wt + k * kWgThreads;
-      const uint32_t ad = add_a + 4 * stage_index(idx >> 4, (idx & 15) * 4);
+      const uint32_t ad = ITEM_ADDR(k);
       float4 v = pq[k];
       if (a.c0) {
         const float4 c = lds128f(ad);
@@ -252,10 +256,7 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
     }
     // ---- staging <- R (already in registers) while the MMA runs
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const int idx = wt + k * kWgThreads;
-      sts128f(add_a + 4 * stage_index(idx >> 4, (idx & 15) * 4), pq[k]);
-    }
+    for (int k = 0; k < 16; ++k) sts128f(ITEM_ADDR(k), pq[k]);
     mbar_wait(bar, phase);
     phase ^= 1;
     fence_after_sync();
@@ -279,13 +280,9 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
     }
     // ---- write back g' as the bf16 hi/lo tile image (what the next step's MMA consumes), 16-byte coalesced
     {
-      uint8_t* __restrict__ gdst = reinterpret_cast<uint8_t*>(a.g) + (size_t)tile * (2 * kATile);
-#pragma unroll 4
-      for (int k = 0; k < 16; ++k) {
-        const int idx = wt + k * kWgThreads;
-        const float4 v = lds128f(a_hi + idx * 16);
-        *reinterpret_cast<float4*>(gdst + idx * 16) = v;
-      }
+      uint8_t* __restrict__ gdst = reinterpret_cast<uint8_t*>(a.g) + (size_t)tile * (2 * kATile) + wt * 16;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) *reinterpret_cast<float4*>(gdst + k * 2048) = lds128f(a_hi + wt * 16 + k * 2048);
     }
     mbar_wait(bar, phase);
     phase ^= 1;
@@ -316,12 +313,20 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
     } else {
       named_bar_sync(bar_id, kWgThreads);
     }
+    // the operand tiles are free (no head): start fetching the next tile's edge features behind the reduction
+    g_prefetched = false;
+    if (!a.with_head && tile + 1 < tile_end) {
+      const uint8_t* __restrict__ gsrc = reinterpret_cast<const uint8_t*>(a.g) + (size_t)(tile + 1) * (2 * kATile) + wt * 16;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) cp_async16(a_hi + wt * 16 + k * 2048, gsrc + k * 2048);
+      g_prefetched = true;
+    }
     // ---- reduce every run of equal targets (a bin, or the part of it inside this tile)
     if (e >= 0 && (wt == 0 || s_dst[wt - 1] != dst)) {
       int r1 = wt;
       while (r1 + 1 < kTile && s_dst[r1 + 1] == dst) ++r1;
-      const int first_slot = a.group_start[t] + bin_ls;
-      const int64_t prow = (int64_t)a.group_pstart[t] + bin_lp + (tile - (first_slot >> 7));
+      const int first_slot = s_gstart[t] + bin_ls;
+      const int64_t prow = (int64_t)s_gpstart[t] + bin_lp + (tile - (first_slot >> 7));
       float u[kD];
       if (a.attn) {
         float mx = -INFINITY;
@@ -383,6 +388,7 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
     fence_before_sync();
     named_bar_sync(bar_id, kWgThreads);   // the next tile overwrites the staging / operand tiles
   }
+#undef ITEM_ADDR
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc<kEdgeTmemCols>(*tmem_slot);

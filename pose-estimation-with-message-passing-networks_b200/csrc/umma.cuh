@@ -199,26 +199,33 @@ __device__ __forceinline__ void load_weight_tile(uint8_t* tile, const __nv_bfloa
   }
 }
 
+// two values at a time: one packed conversion for the hi parts, one for the lo parts (same results as split_bf16)
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);          // .x (low half) = a, .y (high half) = b
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 // address-based variants (shared-space stores)
 __device__ __forceinline__ void store_split4_a(uint32_t hi_tile, uint32_t lo_tile, int row, int col4, float4 v) {
-  __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-  split_bf16(v.x, h0, l0);
-  split_bf16(v.y, h1, l1);
-  split_bf16(v.z, h2, l2);
-  split_bf16(v.w, h3, l3);
+  uint32_t h0, l0, h1, l1;
+  split2(v.x, v.y, h0, l0);
+  split2(v.z, v.w, h1, l1);
   const uint32_t off = sw128_offset(row, col4 >> 1) + (uint32_t)((col4 & 1) << 3);
-  sts64(hi_tile + off, pack2(h0, h1), pack2(h2, h3));
-  sts64(lo_tile + off, pack2(l0, l1), pack2(l2, l3));
+  sts64(hi_tile + off, h0, h1);
+  sts64(lo_tile + off, l0, l1);
 }
 __device__ __forceinline__ void store_split_row_a(uint32_t hi_tile, uint32_t lo_tile, int row, const float (&v)[64]) {
+  const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+  const uint32_t x = (uint32_t)(row & 7);
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    __nv_bfloat16 h[8], l[8];
+    uint32_t h[4], l[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) split_bf16(v[8 * c + i], h[i], l[i]);
-    const uint32_t off = sw128_offset(row, c);
-    sts128(hi_tile + off, pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
-    sts128(lo_tile + off, pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
+    for (int i = 0; i < 4; ++i) split2(v[8 * c + 2 * i], v[8 * c + 2 * i + 1], h[i], l[i]);
+    const uint32_t off = row_off + (((uint32_t)c ^ x) << 4);
+    sts128(hi_tile + off, h[0], h[1], h[2], h[3]);
+    sts128(lo_tile + off, l[0], l[1], l[2], l[3]);
   }
 }
 // fp32 values of columns col4*4 .. +3 of `row` reconstructed from the hi / lo tiles (hi + lo is exact in fp32)
