@@ -72,42 +72,222 @@ __device__ __forceinline__ int pt(int v) { return (v >> 24) & 0xff; }
 // can matter globally -- its own top_k scores and everything >= threshold -- and appends those to
 // the (image, joint) list in global memory with one atomic per warp chunk.
 // ------------------------------------------------------------------------------------------------
-template <bool VEC>
-__device__ __forceinline__ float4 load4(const float* __restrict__ row, int t, int W) {
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int c = 4 * t;
-  if (row == nullptr || c < 0 || c >= W) return v;
-  if (VEC) return __ldg(reinterpret_cast<const float4*>(row + c));
-  v.x = __ldg(row + c);
-  if (c + 1 < W) v.y = __ldg(row + c + 1);
-  if (c + 2 < W) v.z = __ldg(row + c + 2);
-  if (c + 3 < W) v.w = __ldg(row + c + 3);
-  return v;
+// Append up to 4 candidate keys per thread to the CTA's shared list with ONE shared atomic per warp and row
+// (four ballots give every candidate its slot; the order inside the list is irrelevant); a full list spills
+// unfiltered to the global list.
+__device__ __forceinline__ void emit_candidates(const uint64_t (&key)[4], uint32_t vmask, uint64_t* s_keys, uint32_t* s_cnt,
+                                                uint64_t* __restrict__ gkeys, uint32_t* __restrict__ gcount, int cand_cap,
+                                                uint32_t* __restrict__ flags) {
+  const uint32_t b0 = __ballot_sync(kFull, vmask & 1u), b1 = __ballot_sync(kFull, vmask & 2u);
+  const uint32_t b2 = __ballot_sync(kFull, vmask & 4u), b3 = __ballot_sync(kFull, vmask & 8u);
+  if ((b0 | b1 | b2 | b3) == 0) return;
+  const int lane = threadIdx.x & 31;
+  const int n0 = __popc(b0), n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3);
+  uint32_t base = 0;
+  if (lane == 0) base = atomicAdd(s_cnt, (uint32_t)(n0 + n1 + n2 + n3));
+  base = __shfl_sync(kFull, base, 0);
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint32_t pos[4] = {base + __popc(b0 & lt), base + n0 + __popc(b1 & lt), base + n0 + n1 + __popc(b2 & lt),
+                           base + n0 + n1 + n2 + __popc(b3 & lt)};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (vmask & (1u << i)) {
+      if (pos[i] < kCtaCandCap) {
+        s_keys[pos[i]] = key[i];
+      } else {
+        const uint32_t g = atomicAdd(gcount, 1u);
+        if (g < (uint32_t)cand_cap) gkeys[g] = key[i]; else atomicOr(flags, (uint32_t)PGMP_GC_FLAG_CAND_OVERFLOW);
+      }
+    }
+  }
+}
+
+// End of a strip: keep only what can matter globally -- the CTA's own top_k scores (32-bit radix select in
+// shared memory, 4 passes of 8 bits) and everything >= threshold -- and append it to the (image, joint) list
+// with one atomic per warp chunk.
+__device__ __forceinline__ void flush_candidates(const uint64_t* s_keys, uint32_t* s_hist, const uint32_t* s_cnt_p,
+                                                 uint32_t* s_prefix_p, uint32_t* s_remaining_p, int top_k, int use_thr,
+                                                 float thr, uint64_t* __restrict__ gkeys, uint32_t* __restrict__ gcount,
+                                                 int cand_cap, uint32_t* __restrict__ flags) {
+  const int t = threadIdx.x, lane = t & 31;
+  __syncthreads();
+  const uint32_t n = min(*s_cnt_p, (uint32_t)kCtaCandCap);
+  if (n == 0) return;
+  uint32_t cut = 0;  // keep entries with score bits >= cut
+  if (n > (uint32_t)top_k) {
+    // the CTA's top_k-th largest score: 32-bit radix select, 4 passes of 8 bits; the 256-bin suffix scan of a
+    // pass is done by one warp (8 bins per lane)
+    if (t == 0) { *s_prefix_p = 0; *s_remaining_p = (uint32_t)top_k; }
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      for (int i = t; i < 256; i += blockDim.x) s_hist[i] = 0;
+      __syncthreads();
+      const uint32_t prefix = *s_prefix_p;
+      const uint32_t himask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+      for (uint32_t i = t; i < n; i += blockDim.x) {
+        const uint32_t sc = (uint32_t)(s_keys[i] >> 32);
+        if ((sc & himask) == prefix) atomicAdd(&s_hist[(sc >> shift) & 0xff], 1u);
+      }
+      __syncthreads();
+      if (t < 32) {
+        const uint32_t rem = *s_remaining_p;
+        uint32_t mine = 0;                     // lane L owns bins [8 (31 - L), 8 (31 - L) + 8): lane 0 = the highest bins
+        const int b0 = 8 * (31 - lane);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) mine += s_hist[b0 + q];
+        uint32_t incl = mine;                  // inclusive scan from the highest bins down
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t v = __shfl_up_sync(kFull, incl, o);
+          if (lane >= o) incl += v;
+        }
+        const uint32_t hit = __ballot_sync(kFull, incl >= rem);   // always non-empty: the matching entries number >= rem
+        const int owner = __ffs(hit) - 1;
+        if (lane == owner) {
+          uint32_t r2 = rem - (incl - mine);
+          int d = b0 + 7;
+          for (; d > b0; --d) {
+            if (s_hist[d] >= r2) break;
+            r2 -= s_hist[d];
+          }
+          *s_prefix_p = prefix | ((uint32_t)d << shift);
+          *s_remaining_p = r2;
+        }
+      }
+      __syncthreads();
+    }
+    cut = *s_prefix_p;
+  }
+  if (use_thr) cut = min(cut, __float_as_uint(thr));   // positive floats order like their bit patterns
+  for (uint32_t base = 0; base < n; base += blockDim.x) {
+    const uint32_t i = base + t;
+    const bool keep = i < n && (uint32_t)(s_keys[i < n ? i : 0] >> 32) >= cut;
+    const uint32_t m = __ballot_sync(kFull, keep);
+    if (m == 0) continue;
+    uint32_t g = 0;
+    if (lane == 0) g = atomicAdd(gcount, (uint32_t)__popc(m));
+    g = __shfl_sync(kFull, g, 0) + __popc(m & ((1u << lane) - 1u));
+    if (keep) {
+      if (g < (uint32_t)cand_cap) gkeys[g] = s_keys[i]; else atomicOr(flags, (uint32_t)PGMP_GC_FLAG_CAND_OVERFLOW);
+    }
+  }
 }
 
 struct RowRegs {
   float4 v, l, r;  // own 4 columns, left / right neighbour's 4 columns (only lanes 0 / 31 load l / r)
 };
 
+// per-thread load plan of a strip: column offsets and which of the three 4-column chunks exist / are needed
+struct LoadPlan {
+  int off_v, off_l, off_r;      // element offsets inside a row
+  bool has_v, has_l, has_r;
+  int n_v, n_l, n_r;            // valid elements of each chunk (scalar path)
+};
+
 template <bool VEC>
-__device__ __forceinline__ RowRegs load_row(const float* __restrict__ map, int yy, int H, int W, int t, int lane) {
+__device__ __forceinline__ float4 load_chunk(const float* __restrict__ p, bool has, int n) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!has) return v;
+  if (VEC) return __ldg(reinterpret_cast<const float4*>(p));
+  v.x = __ldg(p);
+  if (n > 1) v.y = __ldg(p + 1);
+  if (n > 2) v.z = __ldg(p + 2);
+  if (n > 3) v.w = __ldg(p + 3);
+  return v;
+}
+
+template <bool VEC>
+__device__ __forceinline__ RowRegs load_row(const float* __restrict__ map, int yy, int H, int W, const LoadPlan& lp) {
   RowRegs q;
-  const float* row = (yy >= 0 && yy < H) ? map + (size_t)yy * W : nullptr;
-  q.v = load4<VEC>(row, t, W);
-  q.l = make_float4(0.f, 0.f, 0.f, 0.f);
-  q.r = q.l;
-  if (lane == 0) q.l = load4<VEC>(row, t - 1, W);
-  if (lane == 31) q.r = load4<VEC>(row, t + 1, W);
+  const bool ok = yy >= 0 && yy < H;
+  const float* __restrict__ row = map + (size_t)(ok ? yy : 0) * W;
+  q.v = load_chunk<VEC>(row + lp.off_v, ok && lp.has_v, lp.n_v);
+  q.l = load_chunk<VEC>(row + lp.off_l, ok && lp.has_l, lp.n_l);
+  q.r = load_chunk<VEC>(row + lp.off_r, ok && lp.has_r, lp.n_r);
   return q;
 }
 
-__device__ __forceinline__ float4 shfl_up4(float4 v) {
-  return make_float4(__shfl_up_sync(kFull, v.x, 1), __shfl_up_sync(kFull, v.y, 1), __shfl_up_sync(kFull, v.z, 1),
-                     __shfl_up_sync(kFull, v.w, 1));
+// Register state of a strip: rings of the last K = 2R+1 rows (raw values and horizontal maxima).  The ring
+// slot of a row is its phase PH = (row - first row) mod K, a template parameter, so the rings never shift.
+template <int R>
+struct NmsRings {
+  float hm[2 * R + 1][4];
+  float raw[2 * R + 1][4];
+};
+
+struct NmsCtx {
+  LoadPlan lp;
+  const float* map; const float* mk;
+  int H, W, tt, lane, y0, y_end;
+  uint64_t* s_keys; uint32_t* s_cnt; uint64_t* gkeys; uint32_t* gcount; int cand_cap; uint32_t* flags;
+};
+
+template <int R, int PH, bool VEC>
+__device__ __forceinline__ void nms_row_step(NmsRings<R>& rg, const NmsCtx& c, const RowRegs& cur, int yy) {
+  constexpr int K = 2 * R + 1;
+  // only the R columns next to this thread's chunk are needed from each neighbour
+  float4 l = cur.l, r = cur.r;
+  {
+    const float lw = __shfl_up_sync(kFull, cur.v.w, 1), rx = __shfl_down_sync(kFull, cur.v.x, 1);
+    if (c.lane != 0) l.w = lw;
+    if (c.lane != 31) r.x = rx;
+    if (R >= 2) {
+      const float lz = __shfl_up_sync(kFull, cur.v.z, 1), ry = __shfl_down_sync(kFull, cur.v.y, 1);
+      if (c.lane != 0) l.z = lz;
+      if (c.lane != 31) r.y = ry;
+    }
+    if (R >= 3) {
+      const float ly = __shfl_up_sync(kFull, cur.v.y, 1), rz = __shfl_down_sync(kFull, cur.v.z, 1);
+      if (c.lane != 0) l.y = ly;
+      if (c.lane != 31) r.z = rz;
+    }
+    if (R >= 4) {
+      const float lx = __shfl_up_sync(kFull, cur.v.x, 1), rw = __shfl_down_sync(kFull, cur.v.w, 1);
+      if (c.lane != 0) l.x = lx;
+      if (c.lane != 31) r.w = rw;
+    }
+  }
+  const float ext[12] = {l.x, l.y, l.z, l.w, cur.v.x, cur.v.y, cur.v.z, cur.v.w, r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float m = ext[4 + q - R];
+#pragma unroll
+    for (int d = -R + 1; d <= R; ++d) m = fmaxf(m, ext[4 + q + d]);
+    rg.hm[PH][q] = m;
+    rg.raw[PH][q] = ext[4 + q];
+  }
+  const int yc = yy - R;
+  if (yc >= c.y0 && yc < c.y_end) {   // uniform for the CTA
+    constexpr int CS = (PH + K - R) % K;   // ring slot of the centre row
+    uint64_t key[4];
+    uint32_t vmask = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float x = rg.raw[CS][q];
+      const int col = 4 * c.tt + q;
+      float m = rg.hm[0][q];
+#pragma unroll
+      for (int i = 1; i < K; ++i) m = fmaxf(m, rg.hm[i][q]);
+      float s = 0.f;
+      if (x > 0.f && col < c.W && x == m) s = c.mk ? x * __ldg(c.mk + (size_t)yc * c.W + col) : x;   // CG.py:1163-1165
+      key[q] = ((uint64_t)__float_as_uint(s) << 32) | (uint64_t)(~(uint32_t)(yc * c.W + col));
+      if (s > 0.f) vmask |= 1u << q;
+    }
+    emit_candidates(key, vmask, c.s_keys, c.s_cnt, c.gkeys, c.gcount, c.cand_cap, c.flags);
+  }
 }
-__device__ __forceinline__ float4 shfl_down4(float4 v) {
-  return make_float4(__shfl_down_sync(kFull, v.x, 1), __shfl_down_sync(kFull, v.y, 1),
-                     __shfl_down_sync(kFull, v.z, 1), __shfl_down_sync(kFull, v.w, 1));
+
+// K rows per outer iteration, one statically-phased step each
+template <int R, int PH, bool VEC>
+__device__ __forceinline__ void nms_rows(NmsRings<R>& rg, const NmsCtx& c, RowRegs& nxt, int yy, int y_last) {
+  constexpr int K = 2 * R + 1;
+  if constexpr (PH < K) {
+    if (yy < y_last) {
+      const RowRegs cur = nxt;
+      nxt = load_row<VEC>(c.map, yy + 1 < y_last ? yy + 1 : -1, c.H, c.W, c.lp);   // prefetch
+      nms_row_step<R, PH, VEC>(rg, c, cur, yy);
+      nms_rows<R, PH + 1, VEC>(rg, c, nxt, yy + 1, y_last);
+    }
+  }
 }
 
 template <int R, bool VEC>
@@ -122,125 +302,37 @@ __global__ void __launch_bounds__(256) nms_candidates_kernel(
   __shared__ uint32_t s_prefix, s_remaining;
 
   const int b = blockIdx.z, j = blockIdx.y, y0 = (blockIdx.x / xtiles) * kNmsRows;
-  const int t = threadIdx.x, lane = t & 31;
-  const int tt = (blockIdx.x % xtiles) * blockDim.x + t;   // absolute 4-column chunk index
+  const int t = threadIdx.x;
   const int bj = b * J + j;
-  const float* __restrict__ map = scoremaps + (size_t)bj * H * W;
-  const float* __restrict__ mk = mask ? mask + (size_t)b * H * W : nullptr;
-  uint64_t* __restrict__ gkeys = cand_keys + (size_t)bj * cand_cap;
+  NmsCtx c;
+  c.map = scoremaps + (size_t)bj * H * W;
+  c.mk = mask ? mask + (size_t)b * H * W : nullptr;
+  c.H = H; c.W = W; c.lane = t & 31;
+  c.tt = (blockIdx.x % xtiles) * blockDim.x + t;   // absolute 4-column chunk index
+  c.y0 = y0; c.y_end = min(y0 + kNmsRows, H);
+  {
+    const int chunks = (W + 3) >> 2;
+    LoadPlan& lp = c.lp;
+    lp.off_v = 4 * c.tt; lp.off_l = 4 * (c.tt - 1); lp.off_r = 4 * (c.tt + 1);
+    lp.has_v = c.tt < chunks;
+    lp.has_l = c.lane == 0 && c.tt > 0 && c.tt - 1 < chunks;
+    lp.has_r = c.lane == 31 && c.tt + 1 < chunks;
+    lp.n_v = min(4, W - lp.off_v); lp.n_l = min(4, W - lp.off_l); lp.n_r = min(4, W - lp.off_r);
+  }
+  c.s_keys = s_keys; c.s_cnt = &s_cnt;
+  c.gkeys = cand_keys + (size_t)bj * cand_cap; c.gcount = &cand_count[bj]; c.cand_cap = cand_cap; c.flags = flags;
   if (t == 0) s_cnt = 0;
   __syncthreads();
 
-  float hm[K][4];   // ring of horizontal maxima, rows yy-2R .. yy
-  float raw[R + 1][4];  // ring of raw rows yy-R .. yy
+  NmsRings<R> rg;
 #pragma unroll
   for (int i = 0; i < K; ++i)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) hm[i][c] = 0.f;
-#pragma unroll
-  for (int i = 0; i <= R; ++i)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) raw[i][c] = 0.f;
-
-  const int y_end = min(y0 + kNmsRows, H);
-  RowRegs nxt = load_row<VEC>(map, y0 - R, H, W, tt, lane);
-  for (int yy = y0 - R; yy < y_end + R; ++yy) {
-    RowRegs cur = nxt;
-    nxt = load_row<VEC>(map, yy + 1 < y_end + R ? yy + 1 : -1, H, W, tt, lane);  // prefetch
-    float4 l = shfl_up4(cur.v), r = shfl_down4(cur.v);
-    if (lane == 0) l = cur.l;
-    if (lane == 31) r = cur.r;
-    const float ext[12] = {l.x, l.y, l.z, l.w, cur.v.x, cur.v.y, cur.v.z, cur.v.w, r.x, r.y, r.z, r.w};
-#pragma unroll
-    for (int i = 0; i < K - 1; ++i)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) hm[i][c] = hm[i + 1][c];
-#pragma unroll
-    for (int i = 0; i < R; ++i)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) raw[i][c] = raw[i + 1][c];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float m = ext[4 + c - R];
-#pragma unroll
-      for (int d = -R + 1; d <= R; ++d) m = fmaxf(m, ext[4 + c + d]);
-      hm[K - 1][c] = m;
-      raw[R][c] = ext[4 + c];
-    }
-    const int yc = yy - R;
-    if (yc >= y0 && yc < y_end) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float x = raw[0][c];
-        const int col = 4 * tt + c;
-        if (x > 0.f && col < W) {
-          float m = hm[0][c];
-#pragma unroll
-          for (int i = 1; i < K; ++i) m = fmaxf(m, hm[i][c]);
-          if (x == m) {
-            const float s = mk ? x * __ldg(mk + (size_t)yc * W + col) : x;   // CG.py:1163-1165
-            if (s > 0.f) {
-              const uint32_t flat = (uint32_t)(yc * W + col);
-              const uint64_t key = ((uint64_t)__float_as_uint(s) << 32) | (uint64_t)(~flat);
-              const uint32_t pos = atomicAdd(&s_cnt, 1u);
-              if (pos < kCtaCandCap) {
-                s_keys[pos] = key;
-              } else {  // shared list full: unfiltered straight to the global list
-                const uint32_t g = atomicAdd(&cand_count[bj], 1u);
-                if (g < (uint32_t)cand_cap) gkeys[g] = key; else atomicOr(flags, (uint32_t)PGMP_GC_FLAG_CAND_OVERFLOW);
-              }
-            }
-          }
-        }
-      }
-    }
-  }
-  __syncthreads();
-  const uint32_t n = min(s_cnt, (uint32_t)kCtaCandCap);
-  if (n == 0) return;
-
-  // score of the CTA's top_k-th candidate (32-bit radix select, 4 passes of 8 bits)
-  uint32_t cut = 0;  // keep entries with score bits >= cut
-  if (n > (uint32_t)top_k) {
-    if (t == 0) { s_prefix = 0; s_remaining = (uint32_t)top_k; }
-    for (int shift = 24; shift >= 0; shift -= 8) {
-      for (int i = t; i < 256; i += blockDim.x) s_hist[i] = 0;
-      __syncthreads();
-      const uint32_t prefix = s_prefix;
-      const uint32_t himask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
-      for (uint32_t i = t; i < n; i += blockDim.x) {
-        const uint32_t sc = (uint32_t)(s_keys[i] >> 32);
-        if ((sc & himask) == prefix) atomicAdd(&s_hist[(sc >> shift) & 0xff], 1u);
-      }
-      __syncthreads();
-      if (t == 0) {
-        uint32_t rem = s_remaining;
-        int d = 255;
-        for (; d > 0; --d) {
-          if (s_hist[d] >= rem) break;
-          rem -= s_hist[d];
-        }
-        s_prefix = prefix | ((uint32_t)d << shift);
-        s_remaining = rem;
-      }
-      __syncthreads();
-    }
-    cut = s_prefix;
-  }
-  if (use_thr) cut = min(cut, __float_as_uint(thr));   // positive floats order like their bit patterns
-
-  for (uint32_t base = 0; base < n; base += blockDim.x) {
-    const uint32_t i = base + t;
-    const bool keep = i < n && (uint32_t)(s_keys[i < n ? i : 0] >> 32) >= cut;
-    const uint32_t m = __ballot_sync(kFull, keep);
-    if (m == 0) continue;
-    uint32_t g = 0;
-    if (lane == 0) g = atomicAdd(&cand_count[bj], (uint32_t)__popc(m));
-    g = __shfl_sync(kFull, g, 0) + __popc(m & ((1u << lane) - 1u));
-    if (keep) {
-      if (g < (uint32_t)cand_cap) gkeys[g] = s_keys[i]; else atomicOr(flags, (uint32_t)PGMP_GC_FLAG_CAND_OVERFLOW);
-    }
-  }
+    for (int q = 0; q < 4; ++q) { rg.hm[i][q] = 0.f; rg.raw[i][q] = 0.f; }
+  const int y_last = c.y_end + R;
+  RowRegs nxt = load_row<VEC>(c.map, y0 - R, H, W, c.lp);
+  for (int yy = y0 - R; yy < y_last; yy += K) nms_rows<R, 0, VEC>(rg, c, nxt, yy, y_last);
+  flush_candidates(s_keys, s_hist, &s_cnt, &s_prefix, &s_remaining, top_k, use_thr, thr, c.gkeys, c.gcount, cand_cap, flags);
 }
 
 // ------------------------------------------------------------------------------------------------
