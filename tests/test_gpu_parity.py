@@ -281,3 +281,101 @@ def test_full_pipeline_heatmaps_to_persons():
         if want is not None:
             assert np.array_equal(got[2].cpu().numpy(), want[2])
             assert got[0].shape == want[0].shape
+
+
+# ------------------------------------------------------------------------------------------------
+# size-independent properties at the BASELINE workload size (32 images of 17 x 512 x 512, 30 per joint)
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def full_size():
+    B, J, S, K = 32, 17, 512, 30
+    sm = torch.from_numpy(np.stack([synthetic.synth_scoremap(b, J, S, K) for b in range(B)])).to(DEV)
+    gen = torch.Generator(device=DEV).manual_seed(7)
+    feat = torch.randn(B, 128, S, S, device=DEV, generator=gen)
+    tags = torch.randn(B, J, S, S, device=DEV, generator=gen)
+    cfg = pgmp_b200.config.bench_gc_config(k=K, graph_type="knn")
+    ret = get_graph_constructor(cfg, scoremaps=sm, tagmaps=tags, features=feat, joints_gt=None, factor_list=None,
+                                masks=None, device=DEV, testing=True, heatmaps=None, num_joints=J).construct_graph()
+    return dict(B=B, J=J, S=S, K=K, sm=sm, feat=feat, tags=tags, cfg=cfg, ret=ret)
+
+
+def test_full_size_graph_properties(full_size):
+    f = full_size
+    x, ea, ei, jd, js, bi, jt = (f["ret"][i] for i in (0, 1, 2, 7, 11, 12, 14))
+    B, J, K, S = f["B"], f["J"], f["K"], f["S"]
+    N = B * J * K
+    assert jd.shape == (N, 3) and x.shape == (N, 128) and ei.shape[0] == 2
+    # candidates: exactly K per (image, type), (type, y, x)-sorted inside every image, values are gathers of the inputs
+    key = ((bi * J + jd[:, 2]) * S + jd[:, 1]) * S + jd[:, 0]
+    assert bool((key[1:] > key[:-1]).all())
+    assert bool((torch.bincount(bi * J + jd[:, 2], minlength=B * J) == K).all())
+    assert torch.equal(js, f["sm"][bi, jd[:, 2], jd[:, 1], jd[:, 0]])
+    assert torch.equal(x, f["feat"][bi, :, jd[:, 1], jd[:, 0]])
+    assert torch.equal(jt, f["tags"][bi, jd[:, 2], jd[:, 1], jd[:, 0]])
+    # every candidate is a positive 5x5 maximum of its map
+    pooled = torch.nn.functional.max_pool2d(f["sm"], 5, 1, 2)
+    assert bool((pooled[bi, jd[:, 2], jd[:, 1], jd[:, 0]] == js).all()) and bool((js > 0).all())
+    # edge index: (src, dst)-sorted, no self loops, symmetric, inside one image, degree >= 50
+    src, dst = ei
+    ekey = src * N + dst
+    assert bool((ekey[1:] > ekey[:-1]).all()) and bool((src != dst).all())
+    assert bool((bi[src] == bi[dst]).all())
+    rkey, _ = torch.sort(dst * N + src)
+    assert torch.equal(rkey, ekey)
+    assert int(torch.bincount(src, minlength=N).min()) >= 50
+    # edge attributes are the closed form of CG.py:305-325
+    want = torch.zeros_like(ea)
+    want[:, 0] = (jd[dst, 0] - jd[src, 0]).float() / S
+    want[:, 1] = (jd[dst, 1] - jd[src, 1]).float() / S
+    ar = torch.arange(ei.shape[1], device=DEV)
+    want[ar, 2 + jd[src, 2]] = 1
+    want[ar, 2 + jd[dst, 2]] = 1
+    assert torch.equal(ea, want)
+
+
+def test_full_size_batch_independence_and_idempotence(full_size):
+    """Images are independent units: image b's block of the batched graph equals the graph of image b alone
+    (with node ids offset); a second run is bit-identical."""
+    f = full_size
+    J = f["J"]
+    again = get_graph_constructor(f["cfg"], scoremaps=f["sm"], tagmaps=f["tags"], features=f["feat"], joints_gt=None,
+                                  factor_list=None, masks=None, device=DEV, testing=True, heatmaps=None,
+                                  num_joints=J).construct_graph()
+    for i in (0, 1, 2, 7, 11, 12, 14):
+        assert torch.equal(again[i], f["ret"][i])
+    b = 17
+    one = get_graph_constructor(f["cfg"], scoremaps=f["sm"][b:b + 1], tagmaps=f["tags"][b:b + 1], features=f["feat"][b:b + 1],
+                                joints_gt=None, factor_list=None, masks=None, device=DEV, testing=True, heatmaps=None,
+                                num_joints=J).construct_graph()
+    bi = f["ret"][12]
+    nsel = bi == b
+    off = int(torch.nonzero(nsel)[0])
+    esel = nsel[f["ret"][2][0]]
+    assert torch.equal(one[7], f["ret"][7][nsel]) and torch.equal(one[0], f["ret"][0][nsel])
+    assert torch.equal(one[2] + off, f["ret"][2][:, esel]) and torch.equal(one[1], f["ret"][1][esel])
+
+
+@pytest.mark.parametrize("precision", ["tc", "fp32"])
+def test_full_size_mpn_batch_independence(full_size, precision):
+    """The MPN has no cross-image coupling in eval mode: logits of image b inside the 32-image batch equal the
+    logits of image b run alone (same kernels, different tiling) within tolerance; runs are deterministic."""
+    f = full_size
+    J = f["J"]
+    cfg = pgmp_b200.config.flagship_mpn_config(J, B200_PRECISION=precision)
+    model = synthetic.synth_mpn_state_dict(get_mpn_model(cfg), 11).eval().to(DEV)
+    ret = f["ret"]
+    with torch.no_grad():
+        pe, pn, pc, _ = model(ret[0], ret[1], ret[2], node_types=ret[7][:, 2])
+        pe2, pn2, pc2, _ = model(ret[0], ret[1], ret[2], node_types=ret[7][:, 2])
+    assert torch.equal(pe[-1], pe2[-1]) and torch.equal(pn[-1], pn2[-1]) and torch.equal(pc[-1], pc2[-1])
+    assert bool(torch.isfinite(pe[-1]).all()) and bool(torch.isfinite(pc[-1]).all())
+    b = 5
+    nsel = ret[12] == b
+    off = int(torch.nonzero(nsel)[0])
+    esel = nsel[ret[2][0]]
+    with torch.no_grad():
+        qe, qn, qc, _ = model(ret[0][nsel], ret[1][esel], ret[2][:, esel] - off, node_types=ret[7][nsel, 2])
+    tol = LOGIT_TOL if precision == "tc" else FP32_TOL
+    assert_close(qe[-1].cpu().numpy(), pe[-1][esel].cpu().numpy(), tol, "edge logits, image alone vs in batch")
+    assert_close(qn[-1].cpu().numpy(), pn[-1][nsel].cpu().numpy(), tol, "node logits")
+    assert_close(qc[-1].cpu().numpy(), pc[-1][nsel].cpu().numpy(), tol, "class logits")
