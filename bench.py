@@ -159,6 +159,7 @@ def run_b200(args, rank, local_rank, world):
     import pgmp_b200.synthetic as synthetic
     from pgmp_b200.graph_constructor import get_graph_constructor
     from pgmp_b200.Models.MessagePassingNetwork import get_mpn_model
+    from pgmp_b200.Utils import group_persons
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
@@ -261,6 +262,19 @@ def run_b200(args, rank, local_rank, world):
     barrier()
     t_e2e = reduce_max(ev0.elapsed_time(ev1) / 1e3)
 
+    # ---- the grouping tail (sigmoid / threshold / GAEC / persons) on the last logits, reported separately
+    ret, pe, pn, pc = step(sm, tags, feat)
+    group_persons(ret[7], pn[-1], ret[2], pe[-1], pc[-1], ret[12], J, node_threshold=0.1, detector_scores=ret[11])
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        groups = group_persons(ret[7], pn[-1], ret[2], pe[-1], pc[-1], ret[12], J, node_threshold=0.1,
+                               detector_scores=ret[11])
+    ev1.record()
+    barrier()
+    t_group = reduce_max(ev0.elapsed_time(ev1) / 1e3)
+    persons_per_image = sum(0 if g_ is None else len(g_[0]) for g_ in groups) / max(len(groups), 1)
+
     total_images = B * world * args.steps
     total_edges = reduce_sum(edges_per_step) * args.steps
     value = total_images / t_dev
@@ -283,19 +297,34 @@ def run_b200(args, rank, local_rank, world):
     elem = 4                                                     # storage width of edge features in this mode
     bytes_per_launch = {
         "edge_step_kernel": 3 * 64 * elem * edges_per_step,       # read g, read C (skip constant), write g'
-        "edge_step_tc_kernel": 3 * 64 * elem * edges_per_step,
+        "edge_step_tc_kernel": 3 * 64 * elem * edges_per_step,     # g and g' are bf16 hi+lo = 4 bytes per element
         "nms_candidates_kernel<R, true>": J * SIZE * SIZE * 4 * B + nodes_per_step * 28,
     }.get(name)
     roofline = None
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        ent = tj.get(name)
+        if ent and ent.get("edges_per_launch") == edges_per_step:
+            traffic = ent["dram_bytes_per_launch"]
+    except Exception:
+        pass
     if bytes_per_launch:
         dur = ms / cnt / 1e3
         ach = bytes_per_launch / dur / 1e9
         roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                     "launch_ms": 1e3 * dur, "launches": cnt,
                     "share_of_kernel_time": ms / sum(v[1] for v in prof.values()),
                     "algorithmic_bytes_per_launch": bytes_per_launch}
     kernels = {k: {"launches": c, "ms": round(m, 4)} for k, (c, m) in sorted(prof.items(), key=lambda kv: -kv[1][1])[:8]}
+    nms = next(((k, v) for k, v in prof.items() if k.startswith("nms_candidates")), None)
+    roofline_nms = None
+    if nms:
+        nb = J * SIZE * SIZE * 4 * B
+        nd_ = nms[1][1] / nms[1][0] / 1e3
+        roofline_nms = {"bound": "hbm", "kernel": nms[0], "achieved": nb / nd_ / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": nb / nd_ / 1e9 / hbm_peak, "launch_ms": 1e3 * nd_, "algorithmic_bytes_per_launch": nb}
 
     cpu_t, cpu_edges = (None, None)
     cpu = None
@@ -311,7 +340,11 @@ def run_b200(args, rank, local_rank, world):
             "config": workload_config(args, world), "clocks": clocks,
             "e2e": {"value": total_images / t_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * t_e2e / args.steps},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,
+            "gpu_launches": int(launches), "roofline": roofline, "roofline_nms": roofline_nms, "cpu_baseline": cpu,
+            "kernels": kernels,
+            "grouping_tail": {"ms_per_step": 1e3 * t_group / args.steps, "persons_per_image": persons_per_image,
+                              "note": "sigmoid/threshold/GAEC/persons on the step's logits, timed separately "
+                                      "(not part of value: the metric is GC + MPN, SURVEY.md 8d)"},
             "graph": {"nodes_per_step_per_gpu": nodes_per_step, "edges_per_step_per_gpu": edges_per_step}}
     print(json.dumps(line), flush=True)
     if world > 1:
