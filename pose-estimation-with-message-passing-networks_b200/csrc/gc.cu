@@ -12,7 +12,7 @@
 namespace pgmp {
 namespace {
 
-constexpr int kNmsRows = 32;        // output rows per CTA strip
+constexpr int kNmsRows = 64;        // output rows per CTA strip
 constexpr int kCtaCandCap = 2048;   // per-CTA shared-memory candidate list
 constexpr uint32_t kFull = 0xffffffffu;
 
@@ -72,6 +72,13 @@ __device__ __forceinline__ int pt(int v) { return (v >> 24) & 0xff; }
 // can matter globally -- its own top_k scores and everything >= threshold -- and appends those to
 // the (image, joint) list in global memory with one atomic per warp chunk.
 // ------------------------------------------------------------------------------------------------
+// cold path: the CTA's shared list is full -> unfiltered straight to the global list
+__device__ __noinline__ void spill_candidate(uint64_t key, uint64_t* __restrict__ gkeys, uint32_t* __restrict__ gcount,
+                                             int cand_cap, uint32_t* __restrict__ flags) {
+  const uint32_t g = atomicAdd(gcount, 1u);
+  if (g < (uint32_t)cand_cap) gkeys[g] = key; else atomicOr(flags, (uint32_t)PGMP_GC_FLAG_CAND_OVERFLOW);
+}
+
 // Append up to 4 candidate keys per thread to the CTA's shared list with ONE shared atomic per warp and row
 // (four ballots give every candidate its slot; the order inside the list is irrelevant); a full list spills
 // unfiltered to the global list.
@@ -92,12 +99,8 @@ __device__ __forceinline__ void emit_candidates(const uint64_t (&key)[4], uint32
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     if (vmask & (1u << i)) {
-      if (pos[i] < kCtaCandCap) {
-        s_keys[pos[i]] = key[i];
-      } else {
-        const uint32_t g = atomicAdd(gcount, 1u);
-        if (g < (uint32_t)cand_cap) gkeys[g] = key[i]; else atomicOr(flags, (uint32_t)PGMP_GC_FLAG_CAND_OVERFLOW);
-      }
+      if (pos[i] < kCtaCandCap) s_keys[pos[i]] = key[i];
+      else spill_candidate(key[i], gkeys, gcount, cand_cap, flags);
     }
   }
 }
@@ -198,11 +201,11 @@ __device__ __forceinline__ float4 load_chunk(const float* __restrict__ p, bool h
 template <bool VEC>
 __device__ __forceinline__ RowRegs load_row(const float* __restrict__ map, int yy, int H, int W, const LoadPlan& lp) {
   RowRegs q;
-  const bool ok = yy >= 0 && yy < H;
-  const float* __restrict__ row = map + (size_t)(ok ? yy : 0) * W;
-  q.v = load_chunk<VEC>(row + lp.off_v, ok && lp.has_v, lp.n_v);
-  q.l = load_chunk<VEC>(row + lp.off_l, ok && lp.has_l, lp.n_l);
-  q.r = load_chunk<VEC>(row + lp.off_r, ok && lp.has_r, lp.n_r);
+  const bool ok = (unsigned)yy < (unsigned)H;
+  const int base = ok ? yy * W : 0;   // a map has at most 4096 x 4096 elements: 32-bit offsets
+  q.v = load_chunk<VEC>(map + (base + lp.off_v), ok && lp.has_v, lp.n_v);
+  q.l = load_chunk<VEC>(map + (base + lp.off_l), ok && lp.has_l, lp.n_l);
+  q.r = load_chunk<VEC>(map + (base + lp.off_r), ok && lp.has_r, lp.n_r);
   return q;
 }
 
@@ -221,7 +224,7 @@ struct NmsCtx {
   uint64_t* s_keys; uint32_t* s_cnt; uint64_t* gkeys; uint32_t* gcount; int cand_cap; uint32_t* flags;
 };
 
-template <int R, int PH, bool VEC>
+template <int R, int PH, bool VEC, bool MASK>
 __device__ __forceinline__ void nms_row_step(NmsRings<R>& rg, const NmsCtx& c, const RowRegs& cur, int yy) {
   constexpr int K = 2 * R + 1;
   // only the R columns next to this thread's chunk are needed from each neighbour
@@ -268,7 +271,8 @@ __device__ __forceinline__ void nms_row_step(NmsRings<R>& rg, const NmsCtx& c, c
 #pragma unroll
       for (int i = 1; i < K; ++i) m = fmaxf(m, rg.hm[i][q]);
       float s = 0.f;
-      if (x > 0.f && col < c.W && x == m) s = c.mk ? x * __ldg(c.mk + (size_t)yc * c.W + col) : x;   // CG.py:1163-1165
+      // (out-of-image columns hold zeros, so x > 0 already excludes them)
+      if (x > 0.f && x == m) s = MASK ? x * __ldg(c.mk + (yc * c.W + col)) : x;   // CG.py:1163-1165
       key[q] = ((uint64_t)__float_as_uint(s) << 32) | (uint64_t)(~(uint32_t)(yc * c.W + col));
       if (s > 0.f) vmask |= 1u << q;
     }
@@ -277,15 +281,15 @@ __device__ __forceinline__ void nms_row_step(NmsRings<R>& rg, const NmsCtx& c, c
 }
 
 // K rows per outer iteration, one statically-phased step each
-template <int R, int PH, bool VEC>
+template <int R, int PH, bool VEC, bool MASK>
 __device__ __forceinline__ void nms_rows(NmsRings<R>& rg, const NmsCtx& c, RowRegs& nxt, int yy, int y_last) {
   constexpr int K = 2 * R + 1;
   if constexpr (PH < K) {
     if (yy < y_last) {
       const RowRegs cur = nxt;
       nxt = load_row<VEC>(c.map, yy + 1 < y_last ? yy + 1 : -1, c.H, c.W, c.lp);   // prefetch
-      nms_row_step<R, PH, VEC>(rg, c, cur, yy);
-      nms_rows<R, PH + 1, VEC>(rg, c, nxt, yy + 1, y_last);
+      nms_row_step<R, PH, VEC, MASK>(rg, c, cur, yy);
+      nms_rows<R, PH + 1, VEC, MASK>(rg, c, nxt, yy + 1, y_last);
     }
   }
 }
@@ -331,7 +335,11 @@ __global__ void __launch_bounds__(256) nms_candidates_kernel(
     for (int q = 0; q < 4; ++q) { rg.hm[i][q] = 0.f; rg.raw[i][q] = 0.f; }
   const int y_last = c.y_end + R;
   RowRegs nxt = load_row<VEC>(c.map, y0 - R, H, W, c.lp);
-  for (int yy = y0 - R; yy < y_last; yy += K) nms_rows<R, 0, VEC>(rg, c, nxt, yy, y_last);
+  if (mask) {
+    for (int yy = y0 - R; yy < y_last; yy += K) nms_rows<R, 0, VEC, true>(rg, c, nxt, yy, y_last);
+  } else {
+    for (int yy = y0 - R; yy < y_last; yy += K) nms_rows<R, 0, VEC, false>(rg, c, nxt, yy, y_last);
+  }
   flush_candidates(s_keys, s_hist, &s_cnt, &s_prefix, &s_remaining, top_k, use_thr, thr, c.gkeys, c.gcount, cand_cap, flags);
 }
 
