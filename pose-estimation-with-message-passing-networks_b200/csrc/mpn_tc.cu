@@ -75,7 +75,8 @@ __device__ __forceinline__ int stage_index(int row, int col) {   // float index 
 
 __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const EdgeTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // (offset arithmetic on the __shared__ array keeps the shared address space visible to the compiler: LDS / STS, not generic LD / ST)
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(base);
   const int tid = threadIdx.x, wg = tid >> 7, wt = tid & 127, warp = tid >> 5;
   const uint32_t w1_hi = sbase + kOffW1, w1_lo = w1_hi + kWTile, w2_hi = sbase + kOffW2, w2_lo = w2_hi + kWTile;
@@ -418,7 +419,7 @@ struct TcSmem {
 };
 constexpr size_t kTcSmemBytes = 2 * kATile + 2 * kWTile + 64 + 1024;
 __device__ __forceinline__ TcSmem carve_smem(uint8_t* raw) {
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* base = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
   TcSmem s;
   s.a_hi = base; s.a_lo = base + kATile;
   s.w1_hi = base + 2 * kATile; s.w1_lo = s.w1_hi + kWTile;

@@ -37,7 +37,8 @@ __device__ __forceinline__ int stage_index(int row, int col) {
 
 __global__ void __launch_bounds__(2 * kWg, 1) edge_embed_tc_kernel(const EmbArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // (offset arithmetic on the __shared__ array keeps the shared address space visible to the compiler: LDS / STS, not generic LD / ST)
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(base);
   const int tid = threadIdx.x, wg = tid >> 7, wt = tid & 127, warp = tid >> 5;
   float* s_bias = reinterpret_cast<float*>(base + kOffBias);

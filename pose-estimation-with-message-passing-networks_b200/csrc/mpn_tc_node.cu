@@ -34,7 +34,7 @@ struct Setup {
 
 __device__ __forceinline__ Setup setup_cta(uint8_t* raw, size_t payload_bytes) {
   Setup s;
-  s.base_ptr = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  s.base_ptr = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
   s.base = smem_u32(s.base_ptr);
   s.bar = reinterpret_cast<uint64_t*>(s.base_ptr + payload_bytes);
   s.tmem_slot = reinterpret_cast<uint32_t*>(s.bar + 1);
