@@ -263,10 +263,20 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
     fence_after_sync();
     tmem_ld64(tmem, 0, d);
     float att = a.attn ? __ldg(a.ba + col) : 0.f;
+    {
+      float at1 = 0.f, at2 = 0.f, at3 = 0.f;   // four independent chains instead of one 64-deep FFMA dependency
 #pragma unroll
-    for (int o = 0; o < kD; ++o) {
-      d[o] = fmaxf(d[o] + s_b2[o], 0.f);
-      att = fmaf(d[o], s_wa[o], att);
+      for (int o = 0; o < kD; o += 4) {
+        d[o + 0] = fmaxf(d[o + 0] + s_b2[o + 0], 0.f);
+        d[o + 1] = fmaxf(d[o + 1] + s_b2[o + 1], 0.f);
+        d[o + 2] = fmaxf(d[o + 2] + s_b2[o + 2], 0.f);
+        d[o + 3] = fmaxf(d[o + 3] + s_b2[o + 3], 0.f);
+        att = fmaf(d[o + 0], s_wa[o + 0], att);
+        at1 = fmaf(d[o + 1], s_wa[o + 1], at1);
+        at2 = fmaf(d[o + 2], s_wa[o + 2], at2);
+        at3 = fmaf(d[o + 3], s_wa[o + 3], at3);
+      }
+      att = (att + at1) + (at2 + at3);
     }
     store_split_row_a(a_hi, a_lo, wt, d);
     s_att[wt] = att;

@@ -82,52 +82,57 @@ constexpr size_t kTabPayload = 2 * kImage + 4 * kWBlock;   // [h0 image][h image
 constexpr size_t kTabSmem = kTabPayload + 64 + 1024;
 
 __global__ void __launch_bounds__(kTile) node_tables_tc_kernel(
-    const float* __restrict__ h0_img, const float* __restrict__ h_img, int64_t N, int skip, int per_type,
-    const __nv_bfloat16* __restrict__ wtab, const float* __restrict__ b1, const float* __restrict__ bm,
-    float* __restrict__ tab_p, float* __restrict__ tab_q, float* __restrict__ tab_r) {
+    const float* __restrict__ h0_img, const float* __restrict__ h_img, int64_t N, int skip, int per_type, int n_chunks,
+    int chunks_per_cta, const __nv_bfloat16* __restrict__ wtab, const float* __restrict__ b1,
+    const float* __restrict__ bm, float* __restrict__ tab_p, float* __restrict__ tab_q, float* __restrict__ tab_r) {
   extern __shared__ uint8_t smem_raw[];
   Setup s = setup_cta(smem_raw, kTabPayload);
   const int kb = skip ? 2 : 1, nd = kb * kD;
   const uint32_t a0 = s.base;                     // K-block b: hi at a0 + b * kImage, lo at + kHalf
   const uint32_t w_hi = s.base + 2 * kImage;      // K-block b at + b * kWBlock
   const uint32_t w_lo = w_hi + 2 * kWBlock;
-  const int tid = threadIdx.x, c = blockIdx.y;
+  const int tid = threadIdx.x;
   const int64_t row0 = (int64_t)blockIdx.x * kTile;
   for (int b = 0; b < kb; ++b) {                  // [h0 ; h] (NodeClassificationMPNSimple.py:77) or [h]
     const uint8_t* __restrict__ src = reinterpret_cast<const uint8_t*>((skip && b == 0) ? h0_img : h_img) + (size_t)blockIdx.x * kImage;
 #pragma unroll
     for (int k = 0; k < 16; ++k) cp_async16(a0 + b * kImage + (tid + k * kTile) * 16, src + (tid + k * kTile) * 16);
   }
-  // weight chunk c: [chunk][hi/lo][64][nd]; chunk 2 + t uses message MLP t (or the single agnostic one)
-  const int wc = c < 2 ? c : 2 + (per_type ? c - 2 : 0);
-  const __nv_bfloat16* __restrict__ wsrc = wtab + (size_t)wc * 2 * kD * nd;
-  for (int b = 0; b < kb; ++b) {
-    cp_async_weight_tile(w_hi + b * kWBlock, wsrc + b * kD, kD, nd);
-    cp_async_weight_tile(w_lo + b * kWBlock, wsrc + (size_t)kD * nd + b * kD, kD, nd);
-  }
-  const float* bias = c == 0 ? (skip ? nullptr : b1) : (c == 1 ? nullptr : bm + (size_t)(per_type ? c - 2 : 0) * kD);
-  float* dst = c == 0 ? tab_p : (c == 1 ? tab_q : tab_r + (size_t)(c - 2) * N * kD);
-  cp_async_wait_all();
-  fence_async_smem();
-  __syncthreads();
-  if (tid == 0) {
-    fence_after_sync();
-    issue_gemm_x3<kD>(s.tmem, a0, a0 + kHalf, kImage, w_hi, w_lo, kWBlock, kb, false);
-    mma_commit(s.bar);
-  }
-  mbar_wait(s.bar, 0);
-  fence_after_sync();
-  float d[kD];
-  tmem_ld64(s.tmem, 0, d);
-  if (row0 + tid < N) {
-    float4* __restrict__ o4 = reinterpret_cast<float4*>(dst + (row0 + tid) * kD);
+  uint32_t phase = 0;
+  const int c_begin = blockIdx.y * chunks_per_cta, c_end = min(c_begin + chunks_per_cta, n_chunks);
+  for (int c = c_begin; c < c_end; ++c) {
+    // weight chunk c: [chunk][hi/lo][64][nd]; chunk 2 + t uses message MLP t (or the single agnostic one).
+    // The previous chunk's MMA has completed (waited below), so the weight tiles can be overwritten.
+    const int wc = c < 2 ? c : 2 + (per_type ? c - 2 : 0);
+    const __nv_bfloat16* __restrict__ wsrc = wtab + (size_t)wc * 2 * kD * nd;
+    for (int b = 0; b < kb; ++b) {
+      cp_async_weight_tile(w_hi + b * kWBlock, wsrc + b * kD, kD, nd);
+      cp_async_weight_tile(w_lo + b * kWBlock, wsrc + (size_t)kD * nd + b * kD, kD, nd);
+    }
+    const float* bias = c == 0 ? (skip ? nullptr : b1) : (c == 1 ? nullptr : bm + (size_t)(per_type ? c - 2 : 0) * kD);
+    float* dst = c == 0 ? tab_p : (c == 1 ? tab_q : tab_r + (size_t)(c - 2) * N * kD);
+    cp_async_wait_all();
+    fence_before_sync();
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      issue_gemm_x3<kD>(s.tmem, a0, a0 + kHalf, kImage, w_hi, w_lo, kWBlock, kb, false);
+      mma_commit(s.bar);
+    }
+    float bv[kD];
 #pragma unroll
-    for (int q = 0; q < kD / 4; ++q) {
-      float4 v = make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
-      if (bias) {
-        v.x += __ldg(bias + 4 * q); v.y += __ldg(bias + 4 * q + 1); v.z += __ldg(bias + 4 * q + 2); v.w += __ldg(bias + 4 * q + 3);
-      }
-      o4[q] = v;
+    for (int o = 0; o < kD; ++o) bv[o] = bias ? __ldg(bias + o) : 0.f;
+    mbar_wait(s.bar, phase);
+    phase ^= 1;
+    fence_after_sync();
+    float d[kD];
+    tmem_ld64(s.tmem, 0, d);
+    if (row0 + tid < N) {
+      float4* __restrict__ o4 = reinterpret_cast<float4*>(dst + (row0 + tid) * kD);
+#pragma unroll
+      for (int q = 0; q < kD / 4; ++q)
+        o4[q] = make_float4(d[4 * q] + bv[4 * q], d[4 * q + 1] + bv[4 * q + 1], d[4 * q + 2] + bv[4 * q + 2], d[4 * q + 3] + bv[4 * q + 3]);
     }
   }
   teardown_cta(s);
@@ -182,36 +187,53 @@ __global__ void __launch_bounds__(kTile) node_update_tc_kernel(AggrView av, int6
 }
 
 // h' = ReLU(sum of the group partials + bias) -> fp32 rows + operand image; node / class heads when reported
-__global__ void __launch_bounds__(kTile) node_finish_kernel(const float* __restrict__ partial, int64_t N, int64_t Np,
-                                                            int groups, const float* __restrict__ bu,
-                                                            float* __restrict__ h, float* __restrict__ h_img,
-                                                            int with_heads, const pgmp_mlp node_head,
-                                                            const pgmp_mlp class_head, float* __restrict__ node_logits,
-                                                            float* __restrict__ class_logits) {
+constexpr int kFinThreads = 512;
+
+// THREADS = 512 for the plain finish (4 items per thread, one round trip), 128 when the heads run (one thread per node)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) node_finish_kernel(const float* __restrict__ partial, int64_t N, int64_t Np,
+                                                                  int groups, const float* __restrict__ bu,
+                                                                  float* __restrict__ h, float* __restrict__ h_img,
+                                                                  int with_heads, const pgmp_mlp node_head,
+                                                                  const pgmp_mlp class_head, float* __restrict__ node_logits,
+                                                                  float* __restrict__ class_logits) {
   extern __shared__ __align__(16) float smem[];
   float* bufA = smem;                   // [64][kTileP], only for the heads
   float* bufB = bufA + kD * kTileP;
   float* ws = bufB + kD * kTileP;
   const int64_t row0 = (int64_t)blockIdx.x * kTile;
   uint8_t* __restrict__ img = reinterpret_cast<uint8_t*>(h_img) + (size_t)blockIdx.x * kImage;
-#pragma unroll 4
-  for (int k = 0; k < 16; ++k) {
-    const int idx = threadIdx.x + k * kTile;
+  for (int base = 0; base < kTile * 16; base += 4 * THREADS) {
+  float4 v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int idx = base + threadIdx.x + k * THREADS;
+    v[k] = __ldg(reinterpret_cast<const float4*>(partial + (row0 + (idx >> 4)) * kD + 4 * (idx & 15)));
+  }
+  for (int g = 1; g < groups; ++g) {
+    float4 w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int idx = base + threadIdx.x + k * THREADS;
+      w[k] = __ldg(reinterpret_cast<const float4*>(partial + ((size_t)g * Np + row0 + (idx >> 4)) * kD + 4 * (idx & 15)));
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[k].x += w[k].x; v[k].y += w[k].y; v[k].z += w[k].z; v[k].w += w[k].w; }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int idx = base + threadIdx.x + k * THREADS;
     const int r = idx >> 4, c4 = idx & 15;
-    float4 v = *reinterpret_cast<const float4*>(partial + (row0 + r) * kD + 4 * c4);
-    for (int g = 1; g < groups; ++g) {
-      const float4 w = *reinterpret_cast<const float4*>(partial + ((size_t)g * Np + row0 + r) * kD + 4 * c4);
-      v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
-    }
-    const float4 b = *reinterpret_cast<const float4*>(bu + 4 * c4);
-    v = make_float4(fmaxf(v.x + b.x, 0.f), fmaxf(v.y + b.y, 0.f), fmaxf(v.z + b.z, 0.f), fmaxf(v.w + b.w, 0.f));
-    if (row0 + r >= N) v = make_float4(0.f, 0.f, 0.f, 0.f);
-    else *reinterpret_cast<float4*>(h + (row0 + r) * kD + 4 * c4) = v;
-    store_split4(img, img + kHalf, r, c4, v);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bu + 4 * c4));
+    float4 o = make_float4(fmaxf(v[k].x + b.x, 0.f), fmaxf(v[k].y + b.y, 0.f), fmaxf(v[k].z + b.z, 0.f), fmaxf(v[k].w + b.w, 0.f));
+    if (row0 + r >= N) o = make_float4(0.f, 0.f, 0.f, 0.f);
+    else *reinterpret_cast<float4*>(h + (row0 + r) * kD + 4 * c4) = o;
+    store_split4(img, img + kHalf, r, c4, o);
     if (with_heads) {
-      bufA[(size_t)(4 * c4 + 0) * kTileP + r] = v.x; bufA[(size_t)(4 * c4 + 1) * kTileP + r] = v.y;
-      bufA[(size_t)(4 * c4 + 2) * kTileP + r] = v.z; bufA[(size_t)(4 * c4 + 3) * kTileP + r] = v.w;
+      bufA[(size_t)(4 * c4 + 0) * kTileP + r] = o.x; bufA[(size_t)(4 * c4 + 1) * kTileP + r] = o.y;
+      bufA[(size_t)(4 * c4 + 2) * kTileP + r] = o.z; bufA[(size_t)(4 * c4 + 3) * kTileP + r] = o.w;
     }
+  }
   }
   if (!with_heads) return;
   __syncthreads();
@@ -237,9 +259,11 @@ int mpn_node_tables_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, const fl
     PGMP_CUDA(cudaFuncSetAttribute(node_tables_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTabSmem));
     attr = true;
   }
-  PGMP_LAUNCH(node_tables_tc_kernel, dim3((unsigned)ceil_div<int64_t>(p.num_nodes, kTile), 2 + p.num_types), kTile, kTabSmem,
-              st, w.h0_img, h_img, p.num_nodes, p.skip, p.per_type, static_cast<const __nv_bfloat16*>(p.tc_wtab), p.b1, p.bm,
-              w.tab_p, w.tab_q, w.tab_r);
+  const int n_chunks = 2 + p.num_types;
+  const int per = n_chunks >= 8 ? ceil_div(n_chunks, 4) : 1;       // A tile loaded once per ~5 output chunks
+  PGMP_LAUNCH(node_tables_tc_kernel, dim3((unsigned)ceil_div<int64_t>(p.num_nodes, kTile), ceil_div(n_chunks, per)), kTile,
+              kTabSmem, st, w.h0_img, h_img, p.num_nodes, p.skip, p.per_type, n_chunks, per,
+              static_cast<const __nv_bfloat16*>(p.tc_wtab), p.b1, p.bm, w.tab_p, w.tab_q, w.tab_r);
   return PGMP_OK;
 }
 
@@ -248,7 +272,7 @@ int mpn_node_update_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, int out_
   const size_t fin_smem = sizeof(float) * (2 * kD * kTileP + kWs);
   if (!attr) {
     PGMP_CUDA(cudaFuncSetAttribute(node_update_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpdSmem));
-    PGMP_CUDA(cudaFuncSetAttribute(node_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+    PGMP_CUDA(cudaFuncSetAttribute(node_finish_kernel<kTile>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
     attr = true;
   }
   AggrView av{w.bin_count, w.bin_lstart, w.bin_lpart, w.group_pstart, w.part_val, w.part_mx, w.part_se, p.aggr, p.attn};
@@ -259,8 +283,13 @@ int mpn_node_update_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, int out_
               static_cast<const __nv_bfloat16*>(p.tc_wu), w.upd_partial);
   float* nl = out_slot >= 0 ? p.node_logits + (size_t)out_slot * N : nullptr;
   float* cl = out_slot >= 0 ? p.class_logits + (size_t)out_slot * N * p.num_classes : nullptr;
-  PGMP_LAUNCH(node_finish_kernel, tiles, kTile, out_slot >= 0 ? fin_smem : 0, st, w.upd_partial, N, Np, groups, p.bu, w.h,
-              w.h_img, out_slot >= 0 ? 1 : 0, p.node_head, p.class_head, nl, cl);
+  if (out_slot >= 0) {
+    PGMP_LAUNCH((node_finish_kernel<kTile>), tiles, kTile, fin_smem, st, w.upd_partial, N, Np, groups, p.bu, w.h, w.h_img, 1,
+                p.node_head, p.class_head, nl, cl);
+  } else {
+    PGMP_LAUNCH((node_finish_kernel<kFinThreads>), tiles, kFinThreads, 0, st, w.upd_partial, N, Np, groups, p.bu, w.h, w.h_img,
+                0, p.node_head, p.class_head, nl, cl);
+  }
   return PGMP_OK;
 }
 
