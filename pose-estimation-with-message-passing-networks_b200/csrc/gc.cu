@@ -471,11 +471,32 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_adjacency_kernel(
     const int dx = px(v) - qx, dy = py(v) - qy;
     return dx * dx + dy * dy;
   };
+  // squared distances of this lane's candidates (c = lane + 32 i) cached in registers when the image has
+  // at most 32 * kKnnCache nodes; the query itself and out-of-range slots get +inf
+  constexpr int kKnnCache = 32;
+  const bool cached = N <= 32 * kKnnCache;
+  int dc[kKnnCache];
+  int dmax = 0;
+#pragma unroll
+  for (int i = 0; i < kKnnCache; ++i) {
+    const int c = lane + 32 * i;
+    dc[i] = 0x7fffffff;
+    if (cached && c < N && c != q) {
+      dc[i] = dist2(c);
+      dmax = max(dmax, dc[i]);
+    }
+  }
   int lo = 0, hi = 1 << 25;   // 2 * 4095^2 < 2^25
+  if (cached) hi = __reduce_max_sync(kFull, dmax);
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
     int cnt = 0;
-    for (int c = lane; c < N; c += 32) cnt += (c != q && dist2(c) <= mid) ? 1 : 0;
+    if (cached) {
+#pragma unroll
+      for (int i = 0; i < kKnnCache; ++i) cnt += dc[i] <= mid ? 1 : 0;
+    } else {
+      for (int c = lane; c < N; c += 32) cnt += (c != q && dist2(c) <= mid) ? 1 : 0;
+    }
     cnt = __reduce_add_sync(kFull, cnt);
     if (cnt >= kk) hi = mid; else lo = mid + 1;
   }
