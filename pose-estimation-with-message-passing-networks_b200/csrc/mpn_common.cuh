@@ -38,7 +38,7 @@ struct MpnWorkspace {
   float* h;               // [N][64] current node feature
   float* h0_img;          // tensor-core mode: bf16 hi/lo operand images of h0 / h, one 32 KB image per 128 nodes
   float* h_img;
-  float* upd_partial;     // tensor-core mode: [4][ceil128(N)][64] partial node updates (type groups)
+  float* upd_partial;     // tensor-core mode: [groups][ceil128(N)][64] partial node updates (type groups)
   float* g;               // [S][64] current edge feature (slot order), updated in place
   float* c0;              // [S][64] W1_e0 * g0 + b1 (skip only)
   float* tab_p;           // [N][64] W1_dst * x_i (+ b1 when !skip)
@@ -50,6 +50,12 @@ struct MpnWorkspace {
   uint64_t max_slots, max_parts;
   uint64_t bytes;
 };
+
+// type groups of the tensor-core node update: one per type on small graphs (parallelism), 4 on large ones (traffic)
+inline int mpn_update_groups(const pgmp_mpn_params& p) {
+  if (p.num_nodes <= 4096) return p.num_types;
+  return p.num_types < 4 ? p.num_types : 4;
+}
 
 inline MpnWorkspace carve_mpn(const pgmp_mpn_params& p) {
   Carver c(p.workspace);
@@ -76,7 +82,7 @@ inline MpnWorkspace carve_mpn(const pgmp_mpn_params& p) {
   const bool tc = p.precision == PGMP_PRECISION_TC;
   w.h0_img = c.take<float>(tc ? Np * kD : 0);
   w.h_img = c.take<float>(tc ? Np * kD : 0);
-  w.upd_partial = c.take<float>(tc ? 4 * Np * kD : 0);
+  w.upd_partial = c.take<float>(tc ? (uint64_t)mpn_update_groups(p) * Np * kD : 0);
   w.g = c.take<float>(w.max_slots * kD);
   w.c0 = c.take<float>(p.skip ? w.max_slots * kD : 0);
   w.tab_p = c.take<float>(N * kD);

@@ -22,7 +22,7 @@ constexpr int kImage = kTile * kD * 4;   // bytes of one node-tile image: hi til
 constexpr int kHalf = kTile * 128;       // bytes of one [128][64] bf16 tile
 constexpr int kWBlock = kD * 128;        // bytes of one [64][64] bf16 tile
 constexpr int kTmemCols = 64;
-constexpr int kGroups = 4;               // type groups of the node update
+constexpr int kGroups = 4;               // type groups of the node update for large graphs (small graphs: one per type)
 
 struct Setup {
   uint32_t base;      // shared address of the 1024-aligned payload
@@ -142,14 +142,14 @@ __global__ void __launch_bounds__(kTile) node_tables_tc_kernel(
 constexpr size_t kUpdPayload = 2 * kHalf + 2 * kWBlock;   // A hi/lo, W hi/lo
 constexpr size_t kUpdSmem = kUpdPayload + 64 + 1024;
 
-__global__ void __launch_bounds__(kTile) node_update_tc_kernel(AggrView av, int64_t N, int64_t Np, int T,
+__global__ void __launch_bounds__(kTile) node_update_tc_kernel(AggrView av, int64_t N, int64_t Np, int T, int groups,
                                                                const __nv_bfloat16* __restrict__ wu,
                                                                float* __restrict__ partial) {
   extern __shared__ uint8_t smem_raw[];
   Setup s = setup_cta(smem_raw, kUpdPayload);
   const uint32_t a_hi = s.base, a_lo = a_hi + kHalf, w_hi = a_lo + kHalf, w_lo = w_hi + kWBlock;
   const int tid = threadIdx.x, grp = blockIdx.y;
-  const int per = (T + kGroups - 1) / kGroups;
+  const int per = (T + groups - 1) / groups;
   const int t0 = grp * per, t1 = min(t0 + per, T);
   const int64_t row0 = (int64_t)blockIdx.x * kTile;
   const int64_t row = row0 + tid;
@@ -260,7 +260,8 @@ int mpn_node_tables_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, const fl
     attr = true;
   }
   const int n_chunks = 2 + p.num_types;
-  const int per = n_chunks >= 8 ? ceil_div(n_chunks, 4) : 1;       // A tile loaded once per ~5 output chunks
+  // A tile loaded once per ~5 output chunks on large graphs; one chunk per CTA when there are few node tiles
+  const int per = (n_chunks >= 8 && p.num_nodes > 4096) ? ceil_div(n_chunks, 4) : 1;
   PGMP_LAUNCH(node_tables_tc_kernel, dim3((unsigned)ceil_div<int64_t>(p.num_nodes, kTile), ceil_div(n_chunks, per)), kTile,
               kTabSmem, st, w.h0_img, h_img, p.num_nodes, p.skip, p.per_type, n_chunks, per,
               static_cast<const __nv_bfloat16*>(p.tc_wtab), p.b1, p.bm, w.tab_p, w.tab_q, w.tab_r);
@@ -277,9 +278,10 @@ int mpn_node_update_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, int out_
   }
   AggrView av{w.bin_count, w.bin_lstart, w.bin_lpart, w.group_pstart, w.part_val, w.part_mx, w.part_se, p.aggr, p.attn};
   const int64_t N = p.num_nodes, Np = round_up<int64_t>(N, kTile);
-  const int groups = p.num_types < kGroups ? p.num_types : kGroups;
+  // small graphs have too few node tiles to fill the GPU: one CTA per (tile, type); large ones group ~5 types per CTA
+  const int groups = mpn_update_groups(p);
   const unsigned tiles = (unsigned)ceil_div<int64_t>(N, kTile);
-  PGMP_LAUNCH(node_update_tc_kernel, dim3(tiles, groups), kTile, kUpdSmem, st, av, N, Np, p.num_types,
+  PGMP_LAUNCH(node_update_tc_kernel, dim3(tiles, groups), kTile, kUpdSmem, st, av, N, Np, p.num_types, groups,
               static_cast<const __nv_bfloat16*>(p.tc_wu), w.upd_partial);
   float* nl = out_slot >= 0 ? p.node_logits + (size_t)out_slot * N : nullptr;
   float* cl = out_slot >= 0 ? p.class_logits + (size_t)out_slot * N * p.num_classes : nullptr;
