@@ -183,6 +183,9 @@ class NodeClassificationMPNSimple(nn.Module):
                   tc_wm_e=torch.stack([split(l.weight[:, nd:]) for l in lins]).contiguous(),
                   tc_wtab=torch.stack([split(W1[:, :nd]), split(W1[:, nd:2 * nd])] +
                                       [split(l.weight[:, :nd]) for l in lins]).contiguous())
+        nemb_w = spec["node_embedding"][2]          # folded Linear weights of the node embedding
+        if [tuple(w_.shape) for w_ in nemb_w] == [(128, 128), (64, 128), (64, 64)]:
+            tc["tc_wnemb"] = torch.cat([split(w_).reshape(-1) for w_ in nemb_w]).contiguous()
         emb_w = spec["edge_embedding"][2]           # folded Linear weights of the edge embedding
         if all(max(w.shape) <= 64 for w in emb_w):
             pad = torch.zeros(len(emb_w), 2, 64, 64, dtype=torch.bfloat16, device=device)

@@ -24,6 +24,7 @@ int mpn_node_tables_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, const fl
 int mpn_node_image(const MpnWorkspace& w, const float* h, int64_t N, float* img, cudaStream_t st);
 int mpn_edge_embed_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t st, bool* done);
 int mpn_embed_nodes(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t st);
+int mpn_node_embed_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t st, bool* done);
 int mpn_node_update_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, int out_slot, cudaStream_t st);
 
 namespace {
@@ -497,15 +498,16 @@ int mpn_forward_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t
   };
   const int64_t N = p.num_nodes, E = p.num_edges;
   int rc;
-  bool emb_tc = false;
+  bool emb_tc = false, nemb_tc = false;
   if (E > 0 && (rc = mpn_edge_embed_tc(p, w, st, &emb_tc)) != PGMP_OK) return rc;
   if (emb_tc) {
-    if ((rc = mpn_embed_nodes(p, w, st)) != PGMP_OK) return rc;
+    if ((rc = mpn_node_embed_tc(p, w, st, &nemb_tc)) != PGMP_OK) return rc;      // writes h0 and its operand image
+    if (!nemb_tc && (rc = mpn_embed_nodes(p, w, st)) != PGMP_OK) return rc;
   } else {          // unusual embedding shapes: SIMT chain, then convert the edge features to operand images
     if ((rc = mpn_embed(p, w, st)) != PGMP_OK) return rc;
     if (E > 0) PGMP_LAUNCH(g_to_image_kernel, (unsigned)(w.max_slots / kTile), kWgThreads, 0, st, w.g, w.group_start, p.num_types);
   }
-  if ((rc = mpn_node_image(w, w.h0, N, w.h0_img, st)) != PGMP_OK) return rc;
+  if (!nemb_tc && (rc = mpn_node_image(w, w.h0, N, w.h0_img, st)) != PGMP_OK) return rc;
   PGMP_CUDA(cudaFuncSetAttribute(edge_step_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdgeSmemBytes));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

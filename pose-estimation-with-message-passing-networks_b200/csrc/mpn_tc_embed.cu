@@ -186,3 +186,156 @@ int mpn_edge_embed_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStrea
 }
 
 }  // namespace pgmp
+
+// ------------------------------------------------------------------------------------------------
+// Node embedding on the tensor cores for the reference's shape 128 -> 128 -> 64 -> 64 (ReLU, ReLU, none;
+// NodeClassificationMPNSimple.py:65, eval BatchNorm folded): one CTA per 128-node tile, four chained
+// products (layer 1 as two 64-wide halves), h0 written as fp32 rows and as the bf16 hi/lo operand image.
+// ------------------------------------------------------------------------------------------------
+namespace pgmp {
+namespace {
+
+using namespace umma;
+
+constexpr int kNeA = 2 * 2 * kATile;                 // A: 2 K-blocks x (hi, lo)
+constexpr int kNeW1 = 4 * 2 * kWTile;                // W1: 2 output halves x 2 K-blocks x (hi, lo)
+constexpr int kNeW2 = 2 * 2 * kWTile;                // W2: 2 K-blocks x (hi, lo)
+constexpr int kNeW3 = 2 * kWTile;
+constexpr size_t kNeSmem = kNeA + kNeW1 + kNeW2 + kNeW3 + 1024 + 64 + 1024;
+
+__global__ void __launch_bounds__(kWg, 1) node_embed_tc_kernel(
+    const float* __restrict__ x, int64_t sn, int64_t sc, int64_t N, const __nv_bfloat16* __restrict__ w1,
+    const __nv_bfloat16* __restrict__ w2, const __nv_bfloat16* __restrict__ w3, const float* __restrict__ b1,
+    const float* __restrict__ b2, const float* __restrict__ b3, float* __restrict__ h0, float* __restrict__ h0_img) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t sb = smem_u32(base);
+  const uint32_t a0 = sb;                              // K-block k: hi at a0 + k * 2 * kATile, lo at + kATile
+  const uint32_t w1a = sb + kNeA;                      // output half o, K-block k: hi at w1a + (o * 2 + k) * 2 * kWTile
+  const uint32_t w2a = w1a + kNeW1;                    // K-block k: hi at w2a + k * 2 * kWTile
+  const uint32_t w3a = w2a + kNeW2;
+  float* s_bias = reinterpret_cast<float*>(base + kNeA + kNeW1 + kNeW2 + kNeW3);   // b1[128] b2[64] b3[64]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_bias + 256);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x;
+  if (tid < 32) tmem_alloc<128>(tmem_slot);
+  if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  for (int o = 0; o < 2; ++o)
+    for (int k = 0; k < 2; ++k) {
+      load_weight_tile_a(w1a + (o * 2 + k) * 2 * kWTile, w1 + (size_t)o * 64 * 128 + k * 64, kD, 128, tid, kWg);
+      load_weight_tile_a(w1a + (o * 2 + k) * 2 * kWTile + kWTile, w1 + 128 * 128 + (size_t)o * 64 * 128 + k * 64, kD, 128, tid, kWg);
+    }
+  for (int k = 0; k < 2; ++k) {
+    load_weight_tile_a(w2a + k * 2 * kWTile, w2 + k * 64, kD, 128, tid, kWg);
+    load_weight_tile_a(w2a + k * 2 * kWTile + kWTile, w2 + 64 * 128 + k * 64, kD, 128, tid, kWg);
+  }
+  load_weight_tile_a(w3a, w3, kD, kD, tid, kWg);
+  load_weight_tile_a(w3a + kWTile, w3 + kD * kD, kD, kD, tid, kWg);
+  s_bias[tid] = b1[tid];
+  if (tid < kD) { s_bias[128 + tid] = b2[tid]; s_bias[192 + tid] = b3[tid]; }
+  // x tile -> operand blocks (coalesced when the channel stride is 1)
+  const int64_t row0 = (int64_t)blockIdx.x * kTile;
+  for (int k = 0; k < 2; ++k) {
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+      const int idx = tid + i * kWg;
+      const int r = idx >> 4, c4 = idx & 15;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row0 + r < N) {
+        const float* __restrict__ p = x + (row0 + r) * sn + (int64_t)(k * 64 + 4 * c4) * sc;
+        v = sc == 1 ? *reinterpret_cast<const float4*>(p) : make_float4(p[0], p[sc], p[2 * sc], p[3 * sc]);
+      }
+      store_split4_a(a0 + k * 2 * kATile, a0 + k * 2 * kATile + kATile, r, c4, v);
+    }
+  }
+  fence_before_sync();
+  fence_async_smem();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  float d[kD], d2[kD];
+  // layer 1: two 64-wide output halves, K = 128
+  if (tid == 0) {
+    issue_gemm_x3<kD>(tmem, a0, a0 + kATile, 2 * kATile, w1a, w1a + kWTile, 2 * kWTile, 2, false);
+    issue_gemm_x3<kD>(tmem + 64, a0, a0 + kATile, 2 * kATile, w1a + 4 * kWTile, w1a + 5 * kWTile, 2 * kWTile, 2, false);
+    mma_commit(bar);
+  }
+  mbar_wait(bar, 0);
+  fence_after_sync();
+  tmem_ld64(tmem, 0, d);
+  tmem_ld64(tmem, 64, d2);
+#pragma unroll
+  for (int o = 0; o < kD; ++o) { d[o] = fmaxf(d[o] + s_bias[o], 0.f); d2[o] = fmaxf(d2[o] + s_bias[64 + o], 0.f); }
+  store_split_row_a(a0, a0 + kATile, tid, d);
+  store_split_row_a(a0 + 2 * kATile, a0 + 3 * kATile, tid, d2);
+  fence_before_sync();
+  fence_async_smem();
+  __syncthreads();
+  // layer 2: K = 128 -> 64
+  if (tid == 0) {
+    fence_after_sync();
+    issue_gemm_x3<kD>(tmem, a0, a0 + kATile, 2 * kATile, w2a, w2a + kWTile, 2 * kWTile, 2, false);
+    mma_commit(bar);
+  }
+  mbar_wait(bar, 1);
+  fence_after_sync();
+  tmem_ld64(tmem, 0, d);
+#pragma unroll
+  for (int o = 0; o < kD; ++o) d[o] = fmaxf(d[o] + s_bias[128 + o], 0.f);
+  store_split_row_a(a0, a0 + kATile, tid, d);
+  fence_before_sync();
+  fence_async_smem();
+  __syncthreads();
+  // layer 3: 64 -> 64, no activation
+  if (tid == 0) {
+    fence_after_sync();
+    issue_gemm_x3<kD>(tmem, a0, a0 + kATile, 0, w3a, w3a + kWTile, 0, 1, false);
+    mma_commit(bar);
+  }
+  mbar_wait(bar, 0);
+  fence_after_sync();
+  tmem_ld64(tmem, 0, d);
+#pragma unroll
+  for (int o = 0; o < kD; ++o) d[o] += s_bias[192 + o];
+  // h0 image (rows >= N are zero) through the operand tile, then coalesced copies; fp32 rows from registers
+  if (row0 + tid >= N) {
+#pragma unroll
+    for (int o = 0; o < kD; ++o) d[o] = 0.f;
+  }
+  store_split_row_a(a0, a0 + kATile, tid, d);
+  if (row0 + tid < N) {
+    float4* __restrict__ o4 = reinterpret_cast<float4*>(h0 + (row0 + tid) * kD);
+#pragma unroll
+    for (int q = 0; q < kD / 4; ++q) o4[q] = make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
+  }
+  __syncthreads();
+  uint8_t* __restrict__ img = reinterpret_cast<uint8_t*>(h0_img) + (size_t)blockIdx.x * (2 * kATile);
+#pragma unroll 4
+  for (int i = 0; i < 16; ++i) *reinterpret_cast<float4*>(img + (tid + i * kWg) * 16) = lds128f(a0 + (tid + i * kWg) * 16);
+  fence_before_sync();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc<128>(tmem);
+}
+
+}  // namespace
+
+int mpn_node_embed_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t st, bool* done) {
+  *done = false;
+  const pgmp_mlp& m = p.node_emb;
+  if (!p.tc_wnemb || m.n_layers != 3 || m.dims[0] != 128 || m.dims[1] != 128 || m.dims[2] != 64 || m.dims[3] != 64 ||
+      !m.relu[0] || !m.relu[1] || m.relu[2] || m.post_relu || m.post_scale)
+    return PGMP_OK;
+  static bool attr = false;
+  if (!attr) {
+    PGMP_CUDA(cudaFuncSetAttribute(node_embed_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNeSmem));
+    attr = true;
+  }
+  const __nv_bfloat16* wb = static_cast<const __nv_bfloat16*>(p.tc_wnemb);
+  PGMP_LAUNCH(node_embed_tc_kernel, (unsigned)ceil_div<int64_t>(p.num_nodes, kTile), kWg, kNeSmem, st, p.x, p.x_stride_n,
+              p.x_stride_c, p.num_nodes, wb, wb + 2 * 128 * 128, wb + 2 * 128 * 128 + 2 * 64 * 128, m.bias[0], m.bias[1],
+              m.bias[2], w.h0, w.h0_img);
+  *done = true;
+  return PGMP_OK;
+}
+
+}  // namespace pgmp
