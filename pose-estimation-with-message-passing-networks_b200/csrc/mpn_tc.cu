@@ -65,7 +65,7 @@ constexpr int kOffWg = kOffConst + 1024;               // per-warpgroup regions 
 constexpr int kWgA = 0;                                // A hi, lo
 constexpr int kWgAdd = kWgA + 2 * kATile;              // fp32 staging: g in, C+P+Q, R, then the messages
 constexpr int kWgWm = kWgAdd + kAddTile;               // message weights hi, lo
-constexpr int kWgMisc = kWgWm + 2 * kWTile;            // dst[128] src[128] att[128] wa[64] bar
+constexpr int kWgMisc = kWgWm + 2 * kWTile;            // dst[128] src/prow[128] att[128] wa[64] bars[3] split
 constexpr int kWgBytes = kWgMisc + 2048;
 constexpr size_t kEdgeSmemBytes = kOffWg + 2 * kWgBytes + 64 + 1024;
 static_assert(kOffWg % 1024 == 0 && kWgBytes % 1024 == 0 && kWgAdd % 1024 == 0 && kWgWm % 1024 == 0, "operand tiles must be 1024-byte aligned");
@@ -94,13 +94,21 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
   int* s_src = s_dst + kTile;
   float* s_att = reinterpret_cast<float*>(s_src + kTile);
   float* s_wa = s_att + kTile;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(s_wa + kD);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_wa + kD);   // MMA completions
+  uint64_t* g_bar = bar + 1;                                  // bulk load of the edge-feature image
+  uint64_t* c_bar = bar + 2;                                  // bulk load of the C image
+  int* s_split = reinterpret_cast<int*>(bar + 3);             // (unused pad)
+  int* s_prow = s_src;                                        // part row of every head row (s_src is dead by then)
+  float* s_wfirst = reinterpret_cast<float*>(s_split + 2);    // per warp: max logit of its first / last run segment,
+  float* s_wlast = s_wfirst + 4;                              // flags: bit 0 = lane 0 continues the previous warp's run,
+  int* s_wflag = reinterpret_cast<int*>(s_wlast + 4);         //        bit 1 = the whole warp is one segment
+  int* s_seg = s_wflag + 4;                                   // [8] first row of the k-th row segment of the run reduction
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base + kOffWg + 2 * kWgBytes);
   const float* s_add = reinterpret_cast<const float*>(wgb + kWgAdd);
 
   if (warp == 0) tmem_alloc<kEdgeTmemCols>(tmem_slot);
-  if (wt == 0) mbar_init(bar, 1);
-  if (tid == 0) fence_barrier_init();
+  if (wt == 0) { mbar_init(bar, 1); mbar_init(g_bar, 1); mbar_init(c_bar, 1); }
+  fence_barrier_init();
   load_weight_tile_a(w1_hi, a.w1, kD, kD, tid, kEdgeThreads);
   load_weight_tile_a(w1_lo, a.w1 + kD * kD, kD, kD, tid, kEdgeThreads);
   load_weight_tile_a(w2_hi, a.w2, kD, kD, tid, kEdgeThreads);
@@ -122,14 +130,17 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
   fence_after_sync();
   const uint32_t tmem = *tmem_slot + (uint32_t)(wg * 128);   // this warpgroup's 128 columns
   const int bar_id = 1 + wg;
-  uint32_t phase = 0;
+  uint32_t phase = 0, ld_phase = 0;
   int cur_tm = -1, cur_col = -1;
+  float att_bias = 0.f;
   // cooperative passes: item k of this thread is the 16-byte chunk c4 = wt & 15 of row (wt >> 4) + 8k; its
   // swizzled staging address alternates between two precomputed bases (row & 15 = r0 | (k & 1) << 3)
   const uint32_t r0 = (uint32_t)(wt >> 4), c4c = (uint32_t)(wt & 15);
   const uint32_t item_e = add_a + r0 * 256 + ((c4c ^ r0) << 4), item_o = add_a + r0 * 256 + ((c4c ^ r0 ^ 8u) << 4);
 #define ITEM_ADDR(k) ((((k) & 1) ? item_o : item_e) + (uint32_t)(k) * 2048u)
-  bool g_prefetched = false;
+  bool g_issued = false;        // the tile's edge features were requested during the previous tile
+  const bool copier = wt == 32; // the thread that owns the bulk copies (loads of g / C, write-back of g')
+  uint8_t* __restrict__ g_img = reinterpret_cast<uint8_t*>(a.g);
 
   const int total_tiles = a.group_start[a.T] >> 7;
   const int units = 2 * gridDim.x;
@@ -143,31 +154,30 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
     const int64_t sl = (int64_t)tile_begin * kTile + wt;
     n_e = a.slot_edge[sl]; n_src = a.slot_src[sl]; n_dst = a.slot_dst[sl];
   }
+  int t = 0;                    // source type of the tile: monotone over the tiles of a warpgroup
   for (int tile = tile_begin; tile < tile_end; ++tile) {
-    const int64_t slot0 = (int64_t)tile * kTile;
-    int t = 0;
+    const int slot0 = tile * kTile;
     while (t + 1 < a.T && slot0 >= s_gstart[t + 1]) ++t;
     const int tm = a.per_type ? t : 0;
     const int col = a.attn == PGMP_ATTN_PER_TYPE ? t : 0;
-    // ---- everything this tile needs from global memory is requested up front:
-    //      g (bf16 hi/lo tile image) straight into the operand tiles, C into the staging tile (LDGSTS, no registers)
-    {
-      if (!g_prefetched) {
-        const uint8_t* __restrict__ gsrc = reinterpret_cast<const uint8_t*>(a.g) + (size_t)tile * (2 * kATile) + wt * 16;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) cp_async16(a_hi + wt * 16 + k * 2048, gsrc + k * 2048);
+    // ---- bulk requests: g (bf16 hi/lo tile image) straight into the operand tiles, C (swizzled fp32 tile image)
+    //      into the staging tile; both complete on mbarriers, no registers and no per-thread copies
+    if (copier) {
+      if (!g_issued) {
+        mbar_expect_tx(g_bar, 2 * kATile);
+        bulk_load(a_hi, g_img + (size_t)tile * (2 * kATile), 2 * kATile, g_bar);
       }
       if (a.c0) {
-        const float* __restrict__ csrc = a.c0 + slot0 * kD + wt * 4;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) cp_async16(ITEM_ADDR(k), csrc + k * 512);
+        mbar_expect_tx(c_bar, kAddTile);
+        bulk_load(add_a, a.c0 + (size_t)slot0 * kD, kAddTile, c_bar);
       }
     }
     const int e = n_e, src = n_src, dst = n_dst;
     s_dst[wt] = e >= 0 ? dst : -1;
     s_src[wt] = e >= 0 ? src : -1;
+    if (wt < 8) s_seg[wt] = wt == 0 ? 0 : kTile;
     if (tile + 1 < tile_end) {   // next tile's indices
-      const int64_t sl = slot0 + kTile + wt;
+      const int64_t sl = (int64_t)slot0 + kTile + wt;
       n_e = a.slot_edge[sl]; n_src = a.slot_src[sl]; n_dst = a.slot_dst[sl];
     }
     int bin_ls = 0, bin_lp = 0;   // where this row's bin starts (slots / parts), used by the reduction at the end
@@ -179,10 +189,12 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
     if (tm != cur_tm) {     // all MMAs of the previous tile have completed
       load_weight_tile_a(wm_hi, a.wm + (size_t)tm * 2 * kD * kD, kD, kD, wt, kWgThreads);
       load_weight_tile_a(wm_lo, a.wm + (size_t)tm * 2 * kD * kD + kD * kD, kD, kD, wt, kWgThreads);
+      fence_async_smem();
       cur_tm = tm;
     }
     if (a.attn && col != cur_col) {
       if (wt < kD) s_wa[wt] = a.wa[wt * a.attn_cols + col];
+      att_bias = __ldg(a.ba + col);
       cur_col = col;
     }
     named_bar_sync(bar_id, kWgThreads);          // s_dst / s_src visible
@@ -202,30 +214,31 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
           qq[k] = __ldg(reinterpret_cast<const float4*>(a.tab_q + (size_t)rs * kD) + c4);
         }
       }
+      if (wt == 0) {        // the edge features have landed (usually long ago): first product
+        mbar_wait(g_bar, ld_phase);
+        fence_after_sync();
+        issue_gemm_x3<kD>(tmem, a_hi, a_lo, 0, w1_hi, w1_lo, 0, 1, false);
+        mma_commit(bar);
+      }
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
         pq[k].x += qq[k].x; pq[k].y += qq[k].y; pq[k].z += qq[k].z; pq[k].w += qq[k].w;
       }
     }
-    cp_async_wait_all();
-    fence_async_smem();
-    named_bar_sync(bar_id, kWgThreads);          // operand tiles complete
-    if (wt == 0) {
-      fence_after_sync();
-      issue_gemm_x3<kD>(tmem, a_hi, a_lo, 0, w1_hi, w1_lo, 0, 1, false);
-      mma_commit(bar);
-    }
     // ---- staging <- C + P + Q (this thread's own 16-byte items), then R[type][dst] requested into registers
+    if (a.c0) {
+      mbar_wait(c_bar, ld_phase);
+      float4 c[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const uint32_t ad = ITEM_ADDR(k);
-      float4 v = pq[k];
-      if (a.c0) {
-        const float4 c = lds128f(ad);
-        v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
+      for (int k = 0; k < 16; ++k) c[k] = lds128f(ITEM_ADDR(k));
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        pq[k].x += c[k].x; pq[k].y += c[k].y; pq[k].z += c[k].z; pq[k].w += c[k].w;
       }
-      sts128f(ad, v);
     }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) sts128f(ITEM_ADDR(k), pq[k]);
+    ld_phase ^= 1;
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       const int idx = wt + k * kWgThreads;
@@ -263,24 +276,44 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
     phase ^= 1;
     fence_after_sync();
     tmem_ld64(tmem, 0, d);
-    float att = a.attn ? __ldg(a.ba + col) : 0.f;
+    float att;
     {
-      float at1 = 0.f, at2 = 0.f, at3 = 0.f;   // four independent chains instead of one 64-deep FFMA dependency
+      float at0 = 0.f, at1 = 0.f, at2 = 0.f, at3 = 0.f;   // four independent chains instead of one 64-deep FFMA dependency
 #pragma unroll
       for (int o = 0; o < kD; o += 4) {
         d[o + 0] = fmaxf(d[o + 0] + s_b2[o + 0], 0.f);
         d[o + 1] = fmaxf(d[o + 1] + s_b2[o + 1], 0.f);
         d[o + 2] = fmaxf(d[o + 2] + s_b2[o + 2], 0.f);
         d[o + 3] = fmaxf(d[o + 3] + s_b2[o + 3], 0.f);
-        att = fmaf(d[o + 0], s_wa[o + 0], att);
+        at0 = fmaf(d[o + 0], s_wa[o + 0], at0);
         at1 = fmaf(d[o + 1], s_wa[o + 1], at1);
         at2 = fmaf(d[o + 2], s_wa[o + 2], at2);
         at3 = fmaf(d[o + 3], s_wa[o + 3], at3);
       }
-      att = (att + at1) + (at2 + at3);
+      att = att_bias + ((at0 + at1) + (at2 + at3));
     }
     store_split_row_a(a_hi, a_lo, wt, d);
-    s_att[wt] = att;
+    // ---- runs of equal targets (a bin, or the part of it inside this tile): maximum logit of every run, first within
+    //      the warp (segmented shuffle scan), then across the warps of the tile through shared memory
+    const bool is_start = e < 0 || wt == 0 || s_dst[wt - 1] != dst;   // invalid rows are runs of their own
+    const int lane = wt & 31, wq = wt >> 5;
+    float run_max = att;
+    int seg_first = 0, seg_last = 31;
+    if (a.attn) {
+      const unsigned starts = __ballot_sync(0xffffffffu, is_start);
+      const unsigned upto = 0xffffffffu >> (31 - lane);
+      seg_first = 31 - __clz((starts | 1u) & upto);
+      const unsigned above = starts & ~upto;
+      seg_last = above ? __ffs(above) - 2 : 31;
+#pragma unroll
+      for (int dd = 1; dd < 32; dd <<= 1) {
+        const float o = __shfl_down_sync(0xffffffffu, run_max, dd);
+        if (lane + dd <= seg_last) run_max = fmaxf(run_max, o);
+      }
+      run_max = __shfl_sync(0xffffffffu, run_max, seg_first);
+      if (lane == 0) { s_wfirst[wq] = run_max; s_wflag[wq] = (is_start ? 0 : 1) | (seg_last == 31 ? 2 : 0); }
+      if (lane == 31) s_wlast[wq] = run_max;
+    }
     fence_before_sync();
     fence_async_smem();
     named_bar_sync(bar_id, kWgThreads);
@@ -290,29 +323,57 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
       if (a.with_head) issue_gemm_x3<kD>(tmem + 64, a_hi, a_lo, 0, wh1_hi, wh1_lo, 0, 1, false);
       mma_commit(bar);
     }
-    // ---- write back g' as the bf16 hi/lo tile image (what the next step's MMA consumes), 16-byte coalesced
-    {
-      uint8_t* __restrict__ gdst = reinterpret_cast<uint8_t*>(a.g) + (size_t)tile * (2 * kATile) + wt * 16;
-#pragma unroll
-      for (int k = 0; k < 16; ++k) *reinterpret_cast<float4*>(gdst + k * 2048) = lds128f(a_hi + wt * 16 + k * 2048);
+    // ---- write back g' as the bf16 hi/lo tile image (what the next step's MMA consumes): one bulk copy
+    if (copier) bulk_store(g_img + (size_t)tile * (2 * kATile), a_hi, 2 * kATile);
+    // ---- softmax weight of every row relative to its run's maximum; head rows: part row, split point, part maximum
+    if (a.attn) {
+      if (seg_last == 31)        // the run may continue in the following warps
+        for (int k2 = wq + 1; k2 < 4 && (s_wflag[k2] & 1); ++k2) {
+          run_max = fmaxf(run_max, s_wfirst[k2]);
+          if (!(s_wflag[k2] & 2)) break;
+        }
+      if (seg_first == 0 && (s_wflag[wq] & 1))   // ... and may have begun in the preceding ones
+        for (int k2 = wq - 1; k2 >= 0; --k2) {
+          run_max = fmaxf(run_max, s_wlast[k2]);
+          if ((s_wflag[k2] & 3) != 3) break;
+        }
+      s_att[wt] = e >= 0 ? __expf(att - run_max) : 0.f;
+    } else {
+      s_att[wt] = e >= 0 ? 1.f : 0.f;
+    }
+    {   // the last row of a run stores the run's result: its part row (else -1); segment starts of the reduction
+      int ctl = -1;
+      if (e >= 0 && (wt == kTile - 1 || s_dst[wt + 1] != dst)) {
+        const int first_slot = s_gstart[t] + bin_ls;
+        ctl = s_gpstart[t] + bin_lp + (tile - (first_slot >> 7));
+        if (a.attn) a.part_mx[ctl] = run_max;
+      }
+      s_prow[wt] = ctl;
+      if (e >= 0 && is_start)      // segment k of the reduction starts at the first run start >= 16 k
+        for (int k = wt >> 4; k >= 1; --k)
+          if (atomicMin(&s_seg[k], wt) < wt) break;
     }
     mbar_wait(bar, phase);
     phase ^= 1;
     fence_after_sync();
     tmem_ld64(tmem, 0, d);
     // ---- message m = ReLU(d + R) replaces this thread's own staging row
+    {
+      float4 rr[kD / 4];
 #pragma unroll
-    for (int q = 0; q < kD / 4; ++q) {
-      const uint32_t ad = add_a + 4 * stage_index(wt, 4 * q);
-      const float4 r = lds128f(ad);
-      sts128f(ad, make_float4(fmaxf(d[4 * q + 0] + r.x, 0.f), fmaxf(d[4 * q + 1] + r.y, 0.f),
-                              fmaxf(d[4 * q + 2] + r.z, 0.f), fmaxf(d[4 * q + 3] + r.w, 0.f)));
+      for (int q = 0; q < kD / 4; ++q) rr[q] = lds128f(add_a + 4 * stage_index(wt, 4 * q));
+#pragma unroll
+      for (int q = 0; q < kD / 4; ++q)
+        sts128f(add_a + 4 * stage_index(wt, 4 * q),
+                make_float4(fmaxf(d[4 * q + 0] + rr[q].x, 0.f), fmaxf(d[4 * q + 1] + rr[q].y, 0.f),
+                            fmaxf(d[4 * q + 2] + rr[q].z, 0.f), fmaxf(d[4 * q + 3] + rr[q].w, 0.f)));
     }
     if (a.with_head) {   // head layer 1 epilogue -> A, layer 2 on the tensor cores
       tmem_ld64(tmem, 64, d);
 #pragma unroll
       for (int o = 0; o < kD; ++o) d[o] = fmaxf(d[o] + s_bh1[o], 0.f);
-      named_bar_sync(bar_id, kWgThreads);     // every thread finished reading A for the g' write-back
+      if (copier) bulk_wait_read();           // the write-back has finished reading the operand tiles
+      named_bar_sync(bar_id, kWgThreads);
       store_split_row_a(a_hi, a_lo, wt, d);
       fence_before_sync();
       fence_async_smem();
@@ -325,63 +386,58 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
     } else {
       named_bar_sync(bar_id, kWgThreads);
     }
-    // the operand tiles are free (no head): start fetching the next tile's edge features behind the reduction
-    g_prefetched = false;
+    // the operand tiles are free (no head): fetch the next tile's edge features behind the reduction
+    g_issued = false;
     if (!a.with_head && tile + 1 < tile_end) {
-      const uint8_t* __restrict__ gsrc = reinterpret_cast<const uint8_t*>(a.g) + (size_t)(tile + 1) * (2 * kATile) + wt * 16;
-#pragma unroll
-      for (int k = 0; k < 16; ++k) cp_async16(a_hi + wt * 16 + k * 2048, gsrc + k * 2048);
-      g_prefetched = true;
+      if (copier) {
+        bulk_wait_read();
+        mbar_expect_tx(g_bar, 2 * kATile);
+        bulk_load(a_hi, g_img + (size_t)(tile + 1) * (2 * kATile), 2 * kATile, g_bar);
+      }
+      g_issued = true;
     }
-    // ---- reduce every run of equal targets (a bin, or the part of it inside this tile)
-    if (e >= 0 && (wt == 0 || s_dst[wt - 1] != dst)) {
-      int r1 = wt;
-      while (r1 + 1 < kTile && s_dst[r1 + 1] == dst) ++r1;
-      const int first_slot = s_gstart[t] + bin_ls;
-      const int64_t prow = (int64_t)s_gpstart[t] + bin_lp + (tile - (first_slot >> 7));
-      float u[kD];
-      if (a.attn) {
-        float mx = -INFINITY;
-        for (int r = wt; r <= r1; ++r) mx = fmaxf(mx, s_att[r]);
-        float se = 0.f;
+    // ---- reduce every run: thread = (4 columns, one of 8 row segments); the segments meet at run boundaries, so
+    //      every run is reduced by one thread per column quad, rows in order (deterministic), results stored as
+    //      256-byte rows.  Four rows per batch: the shared-memory reads of a batch precede its dependent arithmetic.
+    {
+      const int seg = wt >> 4;
+      const uint32_t c4 = (uint32_t)(wt & 15);
+      const int r_begin = s_seg[seg], r_end = seg == 7 ? kTile : s_seg[seg + 1];
+      const bool use_max = a.aggr == PGMP_AGGR_MAX && !a.attn;
+      const float u0 = use_max ? -INFINITY : 0.f;
+      float se = 0.f;
+      float4 u = make_float4(u0, u0, u0, u0);
+      for (int rb = r_begin; rb < r_end; rb += 4) {
+        int ctl[4];
+        float wv[4];
+        float4 mv[4];
 #pragma unroll
-        for (int o = 0; o < kD; ++o) u[o] = 0.f;
-        for (int r = wt; r <= r1; ++r) {
-          const float wgt = __expf(s_att[r] - mx);
-          se += wgt;
-#pragma unroll
-          for (int q = 0; q < kD / 4; ++q) {
-            const float4 v = lds128f(add_a + 4 * stage_index(r, 4 * q));
-            u[4 * q + 0] = fmaf(wgt, v.x, u[4 * q + 0]);
-            u[4 * q + 1] = fmaf(wgt, v.y, u[4 * q + 1]);
-            u[4 * q + 2] = fmaf(wgt, v.z, u[4 * q + 2]);
-            u[4 * q + 3] = fmaf(wgt, v.w, u[4 * q + 3]);
-          }
+        for (int j = 0; j < 4; ++j) {
+          const int r = min(rb + j, kTile - 1);
+          const bool in = rb + j < r_end;
+          ctl[j] = in ? s_prow[r] : -1;
+          wv[j] = in ? s_att[r] : 0.f;
+          mv[j] = lds128f(add_a + (uint32_t)r * 256u + ((c4 ^ (uint32_t)(r & 15)) << 4));
         }
-        a.part_mx[prow] = mx;
-        a.part_se[prow] = se;
-      } else {
 #pragma unroll
-        for (int q = 0; q < kD / 4; ++q) {
-          const float4 v = lds128f(add_a + 4 * stage_index(wt, 4 * q));
-          u[4 * q + 0] = v.x; u[4 * q + 1] = v.y; u[4 * q + 2] = v.z; u[4 * q + 3] = v.w;
-        }
-        for (int r = wt + 1; r <= r1; ++r) {
-#pragma unroll
-          for (int q = 0; q < kD / 4; ++q) {
-            const float4 v = lds128f(add_a + 4 * stage_index(r, 4 * q));
-            if (a.aggr == PGMP_AGGR_MAX) {
-              u[4 * q + 0] = fmaxf(u[4 * q + 0], v.x); u[4 * q + 1] = fmaxf(u[4 * q + 1], v.y);
-              u[4 * q + 2] = fmaxf(u[4 * q + 2], v.z); u[4 * q + 3] = fmaxf(u[4 * q + 3], v.w);
-            } else {
-              u[4 * q + 0] += v.x; u[4 * q + 1] += v.y; u[4 * q + 2] += v.z; u[4 * q + 3] += v.w;
+        for (int j = 0; j < 4; ++j) {
+          if (use_max) {
+            if (wv[j] > 0.f) {
+              u.x = fmaxf(u.x, mv[j].x); u.y = fmaxf(u.y, mv[j].y); u.z = fmaxf(u.z, mv[j].z); u.w = fmaxf(u.w, mv[j].w);
             }
+          } else {
+            se += wv[j];
+            u.x = fmaf(wv[j], mv[j].x, u.x); u.y = fmaf(wv[j], mv[j].y, u.y);
+            u.z = fmaf(wv[j], mv[j].z, u.z); u.w = fmaf(wv[j], mv[j].w, u.w);
+          }
+          if (ctl[j] >= 0) {
+            *reinterpret_cast<float4*>(a.part_val + (size_t)ctl[j] * kD + 4 * c4) = u;
+            if (a.attn && c4 == 0) a.part_se[ctl[j]] = se;
+            u = make_float4(u0, u0, u0, u0);
+            se = 0.f;
           }
         }
       }
-      float4* __restrict__ o4 = reinterpret_cast<float4*>(a.part_val + prow * kD);
-#pragma unroll
-      for (int q = 0; q < kD / 4; ++q) o4[q] = make_float4(u[4 * q], u[4 * q + 1], u[4 * q + 2], u[4 * q + 3]);
     }
     if (a.with_head) {   // head layer 2 epilogue and the final 32 -> 1 dot product
       mbar_wait(bar, phase);
@@ -400,6 +456,7 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
     fence_before_sync();
     named_bar_sync(bar_id, kWgThreads);   // the next tile overwrites the staging / operand tiles
   }
+  if (copier) bulk_wait_all();
 #undef ITEM_ADDR
   fence_before_sync();
   __syncthreads();
@@ -420,6 +477,23 @@ __global__ void __launch_bounds__(kWgThreads) g_to_image_kernel(float* __restric
   for (int k = 0; k < 16; ++k) {
     const int idx = threadIdx.x + k * kWgThreads;
     store_split4(img, img + kATile, idx >> 4, idx & 15, v[k]);
+  }
+}
+
+// fp32 row-major C rows [S][64] -> per-tile swizzled staging images (in place, one CTA per tile); only after the
+// SIMT embedding fallback, the tensor-core embedding writes the images directly
+__global__ void __launch_bounds__(kWgThreads) c_to_image_kernel(float* __restrict__ c0, const int32_t* __restrict__ group_start, int T) {
+  const int tile = blockIdx.x;
+  if ((int64_t)tile * kTile >= group_start[T]) return;
+  float4 v[16];
+  float4* __restrict__ t4 = reinterpret_cast<float4*>(c0 + (size_t)tile * kTile * kD);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = t4[threadIdx.x + k * kWgThreads];
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const int idx = threadIdx.x + k * kWgThreads;
+    t4[stage_index(idx >> 4, (idx & 15) * 4) >> 2] = v[k];
   }
 }
 
@@ -506,6 +580,7 @@ int mpn_forward_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t
   } else {          // unusual embedding shapes: SIMT chain, then convert the edge features to operand images
     if ((rc = mpn_embed(p, w, st)) != PGMP_OK) return rc;
     if (E > 0) PGMP_LAUNCH(g_to_image_kernel, (unsigned)(w.max_slots / kTile), kWgThreads, 0, st, w.g, w.group_start, p.num_types);
+    if (E > 0 && p.skip) PGMP_LAUNCH(c_to_image_kernel, (unsigned)(w.max_slots / kTile), kWgThreads, 0, st, w.c0, w.group_start, p.num_types);
   }
   if (!nemb_tc && (rc = mpn_node_image(w, w.h0, N, w.h0_img, st)) != PGMP_OK) return rc;
   PGMP_CUDA(cudaFuncSetAttribute(edge_step_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdgeSmemBytes));

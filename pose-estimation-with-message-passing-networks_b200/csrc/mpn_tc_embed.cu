@@ -116,7 +116,8 @@ __global__ void __launch_bounds__(2 * kWg, 1) edge_embed_tc_kernel(const EmbArgs
       }
       if (l < L) {
         store_split_row_a(a_hi, a_lo, wt, d);   // every MMA reading the operand tiles has completed
-      } else {   // C rows: stage as fp32 in the (now free) operand region, then coalesced stores
+      } else {   // C rows: stage as fp32 in the (now free) operand region (the step kernel's swizzled staging
+                 // layout), then copy that image out: the step kernel fetches it with one bulk copy per tile
         named_bar_sync(bar_id, kWg);
 #pragma unroll
         for (int q = 0; q < kD / 4; ++q)
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(2 * kWg, 1) edge_embed_tc_kernel(const EmbArgs
 #pragma unroll 4
         for (int k = 0; k < 16; ++k) {
           const int idx = wt + k * kWg;
-          *reinterpret_cast<float4*>(cdst + idx * 4) = lds128f(a_hi + 4 * stage_index(idx >> 4, (idx & 15) * 4));
+          *reinterpret_cast<float4*>(cdst + idx * 4) = lds128f(a_hi + idx * 16);   // the swizzled tile image itself
         }
       }
     }
