@@ -180,7 +180,7 @@ typedef struct pgmp_mpn_params {
   const void* tc_w1_e;                 /* [2][dim][dim]                 (hi, lo) of mlp_edge.0 current-edge columns */
   const void* tc_w2;                   /* [2][dim][dim]                 mlp_edge.2 */
   const void* tc_wm_e;                 /* [num_type_mlps][2][dim][dim]  mlp_node edge columns */
-  const void* tc_wtab;                 /* [2 + num_type_mlps][2][dim][nd] node-side columns: mlp_edge.0 target, source, mlp_node[t] */
+  const void* tc_wtab;                 /* [2 + num_types][K/64][2][64][64] pre-swizzled (SWIZZLE_128B) tile images of the per-node table weights */
   const void* tc_wu;                   /* [num_types][2][dim][dim]      update_mlp.0 columns of type t, or NULL */
   const void* tc_wnemb;                /* node embedding 128->128->64->64: [2][128][128], [2][64][128], [2][64][64] back to back, or NULL */
   const void* tc_wemb;                 /* [edge_emb.n_layers][2][64][64] edge embedding layers, zero-padded to 64x64, or NULL */

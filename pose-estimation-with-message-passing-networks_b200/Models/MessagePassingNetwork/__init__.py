@@ -178,11 +178,19 @@ class NodeClassificationMPNSimple(nn.Module):
             lo = (w - hi.float()).to(torch.bfloat16)
             return torch.stack([hi, lo])
 
+        def tile_images(w):    # [2][64][K] hi/lo -> [K/64][2][64][64] SWIZZLE_128B tile images (chunk c of row r at c ^ (r & 7))
+            k_blocks = w.shape[2] // 64
+            t = w.reshape(2, 64, k_blocks, 8, 8).permute(2, 0, 1, 3, 4)          # [kb][2][row][chunk][8]
+            r = torch.arange(64, device=w.device)[:, None]
+            src = (torch.arange(8, device=w.device)[None, :] ^ (r & 7))            # position p holds chunk p ^ (r & 7)
+            idx = src[None, None, :, :, None].expand(k_blocks, 2, 64, 8, 8)
+            return torch.gather(t, 3, idx).reshape(k_blocks, 2, 64, 64)
+
         w1e = W1[:, 2 * nd + 64:] if skip else W1[:, 2 * nd:]
         tc = dict(tc_w1_e=split(w1e).contiguous(), tc_w2=split(layer.mlp_edge[2].weight).contiguous(),
                   tc_wm_e=torch.stack([split(l.weight[:, nd:]) for l in lins]).contiguous(),
-                  tc_wtab=torch.stack([split(W1[:, :nd]), split(W1[:, nd:2 * nd])] +
-                                      [split(l.weight[:, :nd]) for l in lins]).contiguous())
+                  tc_wtab=torch.stack([tile_images(split(W1[:, :nd])), tile_images(split(W1[:, nd:2 * nd]))] +
+                                      [tile_images(split(l.weight[:, :nd])) for l in lins]).contiguous())
         nemb_w = spec["node_embedding"][2]          # folded Linear weights of the node embedding
         if [tuple(w_.shape) for w_ in nemb_w] == [(128, 128), (64, 128), (64, 64)]:
             tc["tc_wnemb"] = torch.cat([split(w_).reshape(-1) for w_ in nemb_w]).contiguous()

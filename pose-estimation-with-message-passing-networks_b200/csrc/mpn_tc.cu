@@ -70,10 +70,6 @@ constexpr int kWgBytes = kWgMisc + 2048;
 constexpr size_t kEdgeSmemBytes = kOffWg + 2 * kWgBytes + 64 + 1024;
 static_assert(kOffWg % 1024 == 0 && kWgBytes % 1024 == 0 && kWgAdd % 1024 == 0 && kWgWm % 1024 == 0, "operand tiles must be 1024-byte aligned");
 
-__device__ __forceinline__ int stage_index(int row, int col) {   // float index into a swizzled [128][64] fp32 tile
-  return row * kD + ((((col >> 2) ^ (row & 15)) << 2) | (col & 3));
-}
-
 __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const EdgeTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   // (offset arithmetic on the __shared__ array keeps the shared address space visible to the compiler: LDS / STS, not generic LD / ST)
@@ -210,8 +206,8 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
         pq[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         qq[k] = pq[k];
         if (rd >= 0) {
-          pq[k] = __ldg(reinterpret_cast<const float4*>(a.tab_p + (size_t)rd * kD) + c4);
-          qq[k] = __ldg(reinterpret_cast<const float4*>(a.tab_q + (size_t)rs * kD) + c4);
+          pq[k] = __ldg(reinterpret_cast<const float4*>(a.tab_p + (size_t)rd * kD) + (c4 ^ (rd & 15)));   // table rows are
+          qq[k] = __ldg(reinterpret_cast<const float4*>(a.tab_q + (size_t)rs * kD) + (c4 ^ (rs & 15)));   // swizzled tile images
         }
       }
       if (wt == 0) {        // the edge features have landed (usually long ago): first product
@@ -244,7 +240,7 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
       const int idx = wt + k * kWgThreads;
       const int rd = s_dst[idx >> 4];
       pq[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (rd >= 0) pq[k] = __ldg(reinterpret_cast<const float4*>(a.tab_r + ((size_t)t * a.N + rd) * kD) + (idx & 15));
+      if (rd >= 0) pq[k] = __ldg(reinterpret_cast<const float4*>(a.tab_r + ((size_t)t * a.N + rd) * kD) + ((idx & 15) ^ (rd & 15)));
     }
     named_bar_sync(bar_id, kWgThreads);
     mbar_wait(bar, phase);

@@ -31,10 +31,6 @@ struct EmbArgs {
   float* g_img; float* c0;
 };
 
-__device__ __forceinline__ int stage_index(int row, int col) {
-  return row * kD + ((((col >> 2) ^ (row & 15)) << 2) | (col & 3));
-}
-
 __global__ void __launch_bounds__(2 * kWg, 1) edge_embed_tc_kernel(const EmbArgs a) {
   extern __shared__ uint8_t smem_raw[];
   // (offset arithmetic on the __shared__ array keeps the shared address space visible to the compiler: LDS / STS, not generic LD / ST)

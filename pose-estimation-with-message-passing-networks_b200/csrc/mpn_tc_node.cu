@@ -78,64 +78,122 @@ __global__ void __launch_bounds__(kTile) node_to_image_kernel(const float* __res
 }
 
 // ------------------------------------------------------------------------------------------------
-constexpr size_t kTabPayload = 2 * kImage + 4 * kWBlock;   // [h0 image][h image], W: 2 K-blocks x (hi, lo)
-constexpr size_t kTabSmem = kTabPayload + 64 + 1024;
+// Per-node tables.  Work item = (node tile, output chunk); chunk 0 / 1 are the target / source columns of
+// mlp_edge.0, chunk 2 + t the node columns of message MLP t.  Persistent CTAs (one per SM) walk a contiguous,
+// tile-major range of items.  Warp 4 is the producer: it fetches the A operand ([h0 ; h] tile images) once per tile
+// and the pre-swizzled weight images three items ahead (bulk copies), and issues the products into two alternating
+// TMEM accumulators.  Warps 0-3 are the epilogue: bias, fp32 rows staged as a swizzled tile image, one bulk copy per
+// item into the table (the step kernel gathers 16-byte chunks with the same swizzle).
+constexpr int kTabA = 2 * kImage;                 // [h0 image][h image]
+constexpr int kTabW = 2 * 2 * kWBlock;            // one weight buffer: 2 K-blocks x (hi, lo)
+constexpr int kTabWBufs = 3;
+constexpr int kTabStage = kTile * kD * 4;
+constexpr size_t kTabPayload = kTabA + kTabWBufs * kTabW + 2 * kTabStage;
+constexpr size_t kTabSmem = kTabPayload + 128 + 1024;
+constexpr int kTabThreads = kTile + 32;
 
-__global__ void __launch_bounds__(kTile) node_tables_tc_kernel(
+__global__ void __launch_bounds__(kTabThreads, 1) node_tables_tc_kernel(
     const float* __restrict__ h0_img, const float* __restrict__ h_img, int64_t N, int skip, int per_type, int n_chunks,
-    int chunks_per_cta, const __nv_bfloat16* __restrict__ wtab, const float* __restrict__ b1,
+    int total_items, const __nv_bfloat16* __restrict__ wtab, const float* __restrict__ b1,
     const float* __restrict__ bm, float* __restrict__ tab_p, float* __restrict__ tab_q, float* __restrict__ tab_r) {
   extern __shared__ uint8_t smem_raw[];
-  Setup s = setup_cta(smem_raw, kTabPayload);
-  const int kb = skip ? 2 : 1, nd = kb * kD;
-  const uint32_t a0 = s.base;                     // K-block b: hi at a0 + b * kImage, lo at + kHalf
-  const uint32_t w_hi = s.base + 2 * kImage;      // K-block b at + b * kWBlock
-  const uint32_t w_lo = w_hi + 2 * kWBlock;
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t sb = smem_u32(base);
+  const uint32_t a0 = sb;                               // K-block b: hi at a0 + b * kImage, lo at + kHalf
+  const uint32_t wbuf = sb + kTabA;                     // buffer i at + i * kTabW; K-block b: hi at + b * 2 * kWBlock, lo + kWBlock
+  const uint32_t stage = wbuf + kTabWBufs * kTabW;      // buffer i at + i * kTabStage
+  uint64_t* a_bar = reinterpret_cast<uint64_t*>(base + kTabPayload);   // A operand landed
+  uint64_t* w_full = a_bar + 1;                         // [3] weight image landed
+  uint64_t* w_free = a_bar + 4;                         // [3] the product reading the buffer has completed
+  uint64_t* d_full = a_bar + 7;                         // [2] accumulator complete
+  uint64_t* d_free = a_bar + 9;                         // [2] accumulator drained by the epilogue (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_bar + 11);
   const int tid = threadIdx.x;
-  const int64_t row0 = (int64_t)blockIdx.x * kTile;
-  for (int b = 0; b < kb; ++b) {                  // [h0 ; h] (NodeClassificationMPNSimple.py:77) or [h]
-    const uint8_t* __restrict__ src = reinterpret_cast<const uint8_t*>((skip && b == 0) ? h0_img : h_img) + (size_t)blockIdx.x * kImage;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) cp_async16(a0 + b * kImage + (tid + k * kTile) * 16, src + (tid + k * kTile) * 16);
+  if (tid < 32) tmem_alloc<128>(tmem_slot);
+  if (tid == 0) {
+    for (int i = 0; i < 9; ++i) mbar_init(a_bar + i, 1);
+    mbar_init(d_free, kTile);
+    mbar_init(d_free + 1, kTile);
+    fence_barrier_init();
   }
-  uint32_t phase = 0;
-  const int c_begin = blockIdx.y * chunks_per_cta, c_end = min(c_begin + chunks_per_cta, n_chunks);
-  for (int c = c_begin; c < c_end; ++c) {
-    // weight chunk c: [chunk][hi/lo][64][nd]; chunk 2 + t uses message MLP t (or the single agnostic one).
-    // The previous chunk's MMA has completed (waited below), so the weight tiles can be overwritten.
-    const int wc = c < 2 ? c : 2 + (per_type ? c - 2 : 0);
-    const __nv_bfloat16* __restrict__ wsrc = wtab + (size_t)wc * 2 * kD * nd;
-    for (int b = 0; b < kb; ++b) {
-      cp_async_weight_tile(w_hi + b * kWBlock, wsrc + b * kD, kD, nd);
-      cp_async_weight_tile(w_lo + b * kWBlock, wsrc + (size_t)kD * nd + b * kD, kD, nd);
-    }
-    const float* bias = c == 0 ? (skip ? nullptr : b1) : (c == 1 ? nullptr : bm + (size_t)(per_type ? c - 2 : 0) * kD);
-    float* dst = c == 0 ? tab_p : (c == 1 ? tab_q : tab_r + (size_t)(c - 2) * N * kD);
-    cp_async_wait_all();
-    fence_before_sync();
-    fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const int kb = skip ? 2 : 1;
+  const uint32_t w_bytes = (uint32_t)kb * 2 * kWBlock;
+  const int per = (total_items + gridDim.x - 1) / gridDim.x;
+  const int j0 = blockIdx.x * per, j1 = min(j0 + per, total_items);
+
+  if (tid == kTile) {
+    // ---------------- producer ----------------
+    auto issue_w = [&](int j) {                         // weight image of item j -> buffer (j - j0) % 3
+      const int i = j - j0, buf = i % kTabWBufs;
+      if (i >= kTabWBufs) mbar_wait(w_free + buf, (uint32_t)(i / kTabWBufs - 1) & 1u);
+      const int c = j % n_chunks;
+      const int wc = c < 2 ? c : 2 + (per_type ? c - 2 : 0);
+      mbar_expect_tx(w_full + buf, w_bytes);
+      bulk_load(wbuf + buf * kTabW, wtab + (size_t)wc * kb * 2 * kD * kD, w_bytes, w_full + buf);
+    };
+    int cur_tile = -1;
+    uint32_t a_phase = 0;
+    for (int j = j0; j < j1 && j < j0 + kTabWBufs - 1; ++j) issue_w(j);
+    for (int j = j0; j < j1; ++j) {
+      const int i = j - j0, wb = i % kTabWBufs, db = i & 1;
+      if (j + kTabWBufs - 1 < j1) issue_w(j + kTabWBufs - 1);
+      const int tile = j / n_chunks;
+      if (tile != cur_tile) {                           // [h0 ; h] (NodeClassificationMPNSimple.py:77) or [h]
+        if (i > 0) mbar_wait(d_full + ((i - 1) & 1), (uint32_t)((i - 1) >> 1) & 1u);   // every product on the old tile is done
+        mbar_expect_tx(a_bar, (uint32_t)kb * kImage);
+        for (int b = 0; b < kb; ++b)
+          bulk_load(a0 + b * kImage, reinterpret_cast<const uint8_t*>((skip && b == 0) ? h0_img : h_img) + (size_t)tile * kImage,
+                    kImage, a_bar);
+        mbar_wait(a_bar, a_phase);
+        a_phase ^= 1;
+        cur_tile = tile;
+      }
+      mbar_wait(w_full + wb, (uint32_t)(i / kTabWBufs) & 1u);
+      if (i >= 2) mbar_wait(d_free + db, (uint32_t)((i >> 1) - 1) & 1u);
       fence_after_sync();
-      issue_gemm_x3<kD>(s.tmem, a0, a0 + kHalf, kImage, w_hi, w_lo, kWBlock, kb, false);
-      mma_commit(s.bar);
+      issue_gemm_x3<kD>(tmem + db * 64, a0, a0 + kHalf, kImage, wbuf + wb * kTabW, wbuf + wb * kTabW + kWBlock, 2 * kWBlock, kb, false);
+      mma_commit(d_full + db);
+      mma_commit(w_free + wb);
     }
-    float bv[kD];
+  } else if (tid < kTile) {
+    // ---------------- epilogue ----------------
+    for (int j = j0; j < j1; ++j) {
+      const int i = j - j0, db = i & 1;
+      const int c = j % n_chunks, tile = j / n_chunks;
+      const float* __restrict__ bias = c == 0 ? (skip ? nullptr : b1) : (c == 1 ? nullptr : bm + (size_t)(per_type ? c - 2 : 0) * kD);
+      float* __restrict__ dst = c == 0 ? tab_p : (c == 1 ? tab_q : tab_r + (size_t)(c - 2) * N * kD);
+      float4 bv[kD / 4];
 #pragma unroll
-    for (int o = 0; o < kD; ++o) bv[o] = bias ? __ldg(bias + o) : 0.f;
-    mbar_wait(s.bar, phase);
-    phase ^= 1;
-    fence_after_sync();
-    float d[kD];
-    tmem_ld64(s.tmem, 0, d);
-    if (row0 + tid < N) {
-      float4* __restrict__ o4 = reinterpret_cast<float4*>(dst + (row0 + tid) * kD);
+      for (int q = 0; q < kD / 4; ++q) bv[q] = bias ? __ldg(reinterpret_cast<const float4*>(bias) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      mbar_wait(d_full + db, (uint32_t)(i >> 1) & 1u);
+      fence_after_sync();
+      float d[kD];
+      tmem_ld64(tmem + db * 64, 0, d);
+      fence_before_sync();
+      mbar_arrive(d_free + db);                         // the accumulator may be overwritten
+      const uint32_t st = stage + db * kTabStage;
 #pragma unroll
       for (int q = 0; q < kD / 4; ++q)
-        o4[q] = make_float4(d[4 * q] + bv[4 * q], d[4 * q + 1] + bv[4 * q + 1], d[4 * q + 2] + bv[4 * q + 2], d[4 * q + 3] + bv[4 * q + 3]);
+        sts128f(st + 4 * stage_index(tid, 4 * q),
+                make_float4(d[4 * q] + bv[q].x, d[4 * q + 1] + bv[q].y, d[4 * q + 2] + bv[q].z, d[4 * q + 3] + bv[q].w));
+      fence_async_smem();
+      if (tid == 0) bulk_wait_read();                   // the other staging buffer is free for the next item
+      named_bar_sync(1, kTile);
+      if (tid == 0) {
+        const int64_t row0 = (int64_t)tile * kTile;
+        const int64_t rows = N - row0 < kTile ? N - row0 : kTile;
+        bulk_store(dst + row0 * kD, st, (uint32_t)rows * kD * 4);
+      }
     }
+    if (tid == 0) bulk_wait_all();
   }
-  teardown_cta(s);
+  fence_before_sync();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc<128>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -260,11 +318,13 @@ int mpn_node_tables_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, const fl
     attr = true;
   }
   const int n_chunks = 2 + p.num_types;
-  // A tile loaded once per ~5 output chunks on large graphs; one chunk per CTA when there are few node tiles
-  const int per = (n_chunks >= 8 && p.num_nodes > 4096) ? ceil_div(n_chunks, 4) : 1;
-  PGMP_LAUNCH(node_tables_tc_kernel, dim3((unsigned)ceil_div<int64_t>(p.num_nodes, kTile), ceil_div(n_chunks, per)), kTile,
-              kTabSmem, st, w.h0_img, h_img, p.num_nodes, p.skip, p.per_type, n_chunks, per,
-              static_cast<const __nv_bfloat16*>(p.tc_wtab), p.b1, p.bm, w.tab_p, w.tab_q, w.tab_r);
+  const int total = (int)ceil_div<int64_t>(p.num_nodes, kTile) * n_chunks;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  PGMP_LAUNCH(node_tables_tc_kernel, (unsigned)(total < sms ? total : sms), kTabThreads, kTabSmem, st, w.h0_img, h_img, p.num_nodes,
+              p.skip, p.per_type, n_chunks, total, static_cast<const __nv_bfloat16*>(p.tc_wtab), p.b1, p.bm, w.tab_p, w.tab_q,
+              w.tab_r);
   return PGMP_OK;
 }
 

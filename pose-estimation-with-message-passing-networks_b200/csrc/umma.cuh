@@ -23,6 +23,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done;
@@ -170,6 +173,13 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr)
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // sub-CTA barrier: `count` threads meet on hardware barrier `id` (id 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// float index of (row, col) in a swizzled [128][64] fp32 staging tile: the 16-byte chunk c of row r sits at chunk
+// position c ^ (r & 15), so both row-per-thread and row-per-half-warp accesses are bank-conflict free.  The
+// per-node tables and the C rows are stored in global memory as such tile images (fetched / written by bulk copies).
+__device__ __forceinline__ int stage_index(int row, int col) {
+  return row * 64 + ((((col >> 2) ^ (row & 15)) << 2) | (col & 3));
+}
 
 // ---- operand tile writers ------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t sw128_offset(int row, int chunk16) {
