@@ -208,6 +208,35 @@ def test_mpn_tensor_core_within_logit_tolerance(name):
             assert_close(a, gold[f"{kind}_{i}"], LOGIT_TOL, f"{name}:{kind}_{i} vs reference")
 
 
+@pytest.mark.parametrize("over", [
+    dict(EDGE_EMB=dict(OUTPUT_SIZES=[32, 96, 64])),                      # a layer wider than 64: SIMT edge embedding + image conversion
+    dict(NODE_EMB=dict(OUTPUT_SIZES=[96, 64])),                          # not the 128-128-64-64 chain: SIMT node embedding
+    dict(EDGE_CLASS=dict(OUTPUT_SIZES=[48, 1])),                         # not the 64-64-32-1 head: SIMT edge head on the images
+    dict(SKIP=False, EDGE_EMB=dict(OUTPUT_SIZES=[80, 64])),              # no C rows at all
+], ids=["wide_edge_emb", "short_node_emb", "short_edge_head", "noskip_wide_edge_emb"])
+def test_mpn_tensor_core_fallback_shapes(over):
+    """Layer shapes the tensor-core kernels do not cover run the SIMT stage inside the tensor-core forward; results
+    stay within the logit tolerance of the oracle."""
+    cfg = pgmp_b200.config.flagship_mpn_config(17, STEPS=3, B200_PRECISION="tc")
+    for k, v in over.items():
+        if isinstance(v, dict):
+            for kk, vv in v.items():
+                setattr(getattr(cfg, k), kk, vv)
+        else:
+            setattr(cfg, k, v)
+    data, gcfg, nj = gc_inputs("knn_small")
+    g = oracle.gc.construct_graph(data["scoremaps"], data["tagmaps"], data["features"], gcfg, nj, masks=data["masks"])
+    model = synthetic.synth_mpn_state_dict(get_mpn_model(cfg), 21).eval().to(DEV)
+    pe, pn, pc, _ = run_mpn(model, g)
+    sd = {k: v.cpu().numpy() for k, v in model.state_dict().items()}
+    ope, opn, opc = oracle.mpn.node_classification_mpn_forward(sd, cfg, g["x"], g["edge_attr"], g["edge_index"],
+                                                               g["joint_det"][:, 2])
+    for kind, got, want in (("edge", pe, ope), ("node", pn, opn), ("class", pc, opc)):
+        assert len(got) == len(want)
+        for i, (a, b) in enumerate(zip(got, want)):
+            assert_close(a.cpu().numpy(), b, LOGIT_TOL, f"{kind}_{i} vs oracle")
+
+
 # ------------------------------------------------------------------------------------------------
 # grouping tail: threshold -> GAEC multicut -> persons (bit-exact on identical logits)
 # ------------------------------------------------------------------------------------------------
