@@ -51,10 +51,15 @@ struct MpnWorkspace {
   uint64_t bytes;
 };
 
-// type groups of the tensor-core node update: one per type on small graphs (parallelism), 4 on large ones (traffic)
+// type groups of the tensor-core node update: (node tiles x groups) CTAs should fill the GPU once -- two CTAs per SM
+// are resident -- so small graphs get one group per type (parallelism) and large ones few groups (less traffic)
 inline int mpn_update_groups(const pgmp_mpn_params& p) {
-  if (p.num_nodes <= 4096) return p.num_types;
-  return p.num_types < 4 ? p.num_types : 4;
+  const int64_t tiles = (p.num_nodes + kTile - 1) / kTile;
+  int64_t g = tiles > 0 ? (2 * 148) / tiles : p.num_types;
+  if (g < 1) g = 1;
+  if (g > p.num_types) g = p.num_types;
+  const int64_t per = (p.num_types + g - 1) / g;          // types per group; drop the groups that would be empty
+  return (int)((p.num_types + per - 1) / per);
 }
 
 inline MpnWorkspace carve_mpn(const pgmp_mpn_params& p) {

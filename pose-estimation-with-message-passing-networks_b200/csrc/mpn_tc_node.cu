@@ -197,29 +197,133 @@ __global__ void __launch_bounds__(kTabThreads, 1) node_tables_tc_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------
-constexpr size_t kUpdPayload = 2 * kHalf + 2 * kWBlock;   // A hi/lo, W hi/lo
-constexpr size_t kUpdSmem = kUpdPayload + 64 + 1024;
+// Node update.  CTA = (node tile, type group); thread = node.  Per type t of the group: U[node, t, :] (the merged
+// parts of bin (t, node)) becomes the A operand, Wu_t the B operand, all types accumulate into one TMEM tile.
+// The first part row of every bin is fetched cooperatively -- half a warp per 256-byte row -- into a swizzled
+// shared-memory tile, one type ahead of the merge; the bin bookkeeping is requested two types ahead.  A bin that
+// straddles two tiles of the step kernel (about 3 %) has a second part: its owner thread requests that row and the
+// two (max, sum) pairs into registers together with the prefetch, so no lane pays a dependent chain of loads.
+constexpr int kUpdRows = kTile * kD * 4;                      // one row buffer: [128][64] fp32, swizzled rows
+constexpr size_t kUpdPayload = 2 * kHalf + 2 * kWBlock + 2 * kUpdRows + kTile * 4;   // A, W, 2 row buffers, part ids
+// Two CTAs per SM need 2 x (this + 1 KB system reservation) <= 228 KB, which leaves no room for alignment slack: the
+// kernel relies on the 1024-byte alignment of the dynamic shared-memory window (declared, and checked with a trap).
+constexpr size_t kUpdSmem = kUpdPayload + 64;
+static_assert(2 * (kUpdSmem + 1024) <= 228 * 1024, "node update: two CTAs per SM");
 
 __global__ void __launch_bounds__(kTile) node_update_tc_kernel(AggrView av, int64_t N, int64_t Np, int T, int groups,
                                                                const __nv_bfloat16* __restrict__ wu,
                                                                float* __restrict__ partial) {
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  if (smem_u32(smem_raw) & 1023u) __trap();                   // no slack is allocated for re-aligning (see kUpdSmem)
   Setup s = setup_cta(smem_raw, kUpdPayload);
   const uint32_t a_hi = s.base, a_lo = a_hi + kHalf, w_hi = a_lo + kHalf, w_lo = w_hi + kWBlock;
+  const uint32_t rows = w_lo + kWBlock;                       // buffer i at + i * kUpdRows
+  int* s_part = reinterpret_cast<int*>(s.base_ptr + 2 * kHalf + 2 * kWBlock + 2 * kUpdRows);   // [128] part row or -1
   const int tid = threadIdx.x, grp = blockIdx.y;
   const int per = (T + groups - 1) / groups;
   const int t0 = grp * per, t1 = min(t0 + per, T);
   const int64_t row0 = (int64_t)blockIdx.x * kTile;
   const int64_t row = row0 + tid;
   const int64_t srow = row < N ? row : N - 1;
+  const uint32_t r0 = (uint32_t)(tid >> 4), c4 = (uint32_t)(tid & 15);
   uint32_t phase = 0;
   float u[kD];
+
+  struct Bin { int cnt, ls, lp; };
+  struct Extra { float mx0, se0, mx1, se1; float4 v[kD / 4]; };   // what the owner of a bin holds besides the shared row
+  auto load_bin = [&](int t) {
+    Bin b{0, 0, 0};
+    if (t < t1) {
+      const int64_t bin = (int64_t)t * N + srow;
+      b.cnt = av.bin_count[bin]; b.ls = av.bin_lstart[bin]; b.lp = av.bin_lpart[bin];
+    }
+    return b;
+  };
+  auto parts_of = [](const Bin& b) { return b.cnt ? ((b.ls + b.cnt - 1) >> 7) - (b.ls >> 7) + 1 : 0; };
+  // owner thread: publish the first part row of its bin (-1: empty, or more than two parts), request the scalars
+  // and, for a two-part bin, the second row
+  auto publish = [&](int t, const Bin& b, Extra& x) {
+    int part = -1;
+    const int np = t < t1 ? parts_of(b) : 0;
+    x.mx0 = x.mx1 = 0.f; x.se0 = 1.f; x.se1 = 0.f;
+    if (np == 1 || np == 2) {
+      part = av.group_pstart[t] + b.lp;
+      if (av.attn) x.se0 = __ldg(av.part_se + part);
+      if (np == 2) {
+        if (av.attn) { x.mx0 = __ldg(av.part_mx + part); x.mx1 = __ldg(av.part_mx + part + 1); x.se1 = __ldg(av.part_se + part + 1); }
+        const float4* __restrict__ v4 = reinterpret_cast<const float4*>(av.part_val + (size_t)(part + 1) * kD);
+#pragma unroll
+        for (int q = 0; q < kD / 4; ++q) x.v[q] = __ldg(v4 + q);
+      }
+    }
+    s_part[tid] = part;
+  };
+  // all threads: fetch the published rows of type t, 16 bytes per thread and row, rows r0 + 8k
+  auto fetch = [&](int t) {
+    if (t < t1) {
+      const uint32_t dst = rows + (uint32_t)(t & 1) * kUpdRows;
+#pragma unroll
+      for (uint32_t k = 0; k < 16; ++k) {
+        const uint32_t r = r0 + 8 * k;
+        const int part = s_part[r];
+        if (part >= 0) cp_async16(dst + r * 256u + ((c4 ^ (r & 15u)) << 4), av.part_val + (size_t)part * kD + 4 * c4);
+      }
+    }
+    cp_async_commit();
+  };
+
+  Bin cur = load_bin(t0), nxt = load_bin(t0 + 1);
+  Extra x_cur, x_nxt;
+  publish(t0, cur, x_cur);
+  __syncthreads();
+  fetch(t0);
   for (int t = t0; t < t1; ++t) {
     cp_async_weight_tile(w_hi, wu + (size_t)t * 2 * kD * kD, kD, kD);
     cp_async_weight_tile(w_lo, wu + (size_t)t * 2 * kD * kD + kD * kD, kD, kD);
-    merge_parts(av, t, srow, N, u);               // U[node, t, :] from the per-tile parts
+    cp_async_commit();
+    publish(t + 1, nxt, x_nxt);
+    const Bin after = load_bin(t + 2);
+    __syncthreads();                              // part ids of type t + 1 visible; its row buffer is no longer read
+    fetch(t + 1);
+    cp_async_wait_group<1>();                     // this thread's copies of type t (rows, weights) have landed
+    __syncthreads();                              // ... and everybody else's
+    const int np = parts_of(cur);
+    if (np == 1 || np == 2) {
+      // scale of the shared row (part 0) and of the register row (part 1); layers.py:242-251 per-(target, type) softmax
+      float sc0 = 1.f, sc1 = 1.f, post = 1.f;
+      if (av.attn) {
+        if (np == 2) {
+          const float M = fmaxf(x_cur.mx0, x_cur.mx1);
+          sc0 = __expf(x_cur.mx0 - M); sc1 = __expf(x_cur.mx1 - M);
+        }
+        post = 1.f / (fmaf(x_cur.se1, np == 2 ? sc1 : 0.f, x_cur.se0 * sc0) + 1e-12f);   // torch_scatter softmax eps
+      } else if (av.aggr == PGMP_AGGR_MEAN) {
+        post = 1.f / (float)cur.cnt;
+      }
+      const uint32_t src = rows + (uint32_t)(t & 1) * kUpdRows + (uint32_t)tid * 256u;
+      const uint32_t x = (uint32_t)(tid & 15);
+      const bool use_max = av.aggr == PGMP_AGGR_MAX && !av.attn;
+#pragma unroll
+      for (uint32_t q = 0; q < kD / 4; ++q) {
+        float4 v = lds128f(src + ((q ^ x) << 4));
+        if (np == 2) {
+          const float4 w = x_cur.v[q];
+          if (use_max) {
+            v.x = fmaxf(v.x, w.x); v.y = fmaxf(v.y, w.y); v.z = fmaxf(v.z, w.z); v.w = fmaxf(v.w, w.w);
+          } else {
+            v.x = fmaf(w.x, sc1, v.x * sc0); v.y = fmaf(w.y, sc1, v.y * sc0);
+            v.z = fmaf(w.z, sc1, v.z * sc0); v.w = fmaf(w.w, sc1, v.w * sc0);
+          }
+        }
+        u[4 * q + 0] = v.x * post; u[4 * q + 1] = v.y * post; u[4 * q + 2] = v.z * post; u[4 * q + 3] = v.w * post;
+      }
+    } else if (np == 0) {
+#pragma unroll
+      for (int o = 0; o < kD; ++o) u[o] = 0.f;
+    } else {
+      merge_parts(av, t, srow, N, u);             // a bin of more than 128 edges spread over three or more tiles
+    }
     store_split_row_a(a_hi, a_lo, tid, u);
-    cp_async_wait_all();
     fence_before_sync();
     fence_async_smem();
     __syncthreads();
@@ -228,9 +332,11 @@ __global__ void __launch_bounds__(kTile) node_update_tc_kernel(AggrView av, int6
       issue_gemm_x3<kD>(s.tmem, a_hi, a_lo, 0, w_hi, w_lo, 0, 1, t > t0);
       mma_commit(s.bar);
     }
+    cur = nxt; nxt = after; x_cur = x_nxt;
     mbar_wait(s.bar, phase);                      // operand tiles are reused by the next type
     phase ^= 1;
   }
+  cp_async_wait_all();
   if (t1 > t0) {
     fence_after_sync();
     tmem_ld64(s.tmem, 0, u);
