@@ -408,3 +408,60 @@ def test_full_size_mpn_batch_independence(full_size, precision):
     assert_close(qe[-1].cpu().numpy(), pe[-1][esel].cpu().numpy(), tol, "edge logits, image alone vs in batch")
     assert_close(qn[-1].cpu().numpy(), pn[-1][nsel].cpu().numpy(), tol, "node logits")
     assert_close(qc[-1].cpu().numpy(), pc[-1][nsel].cpu().numpy(), tol, "class logits")
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs[2..3] at full per-image size: w48 / 640 px fully connected, CrowdPose-shaped (14 joints,
+# 60 candidates per joint, kNN and fully connected: 704 760 edges per image)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,J,S,K,graph", [("w48_640_fully", 17, 640, 30, "fully"), ("crowdpose_knn", 14, 512, 60, "knn"),
+                                              ("crowdpose_fully", 14, 512, 60, "fully")])
+def test_other_configs_full_image_size(name, J, S, K, graph):
+    """Graph invariants, tensor-core logits against the fp32 CUDA path (which the small cases pin to the oracle and the
+    reference), and batch independence, at the per-image sizes of the remaining BASELINE configs."""
+    B = 2
+    sm = torch.from_numpy(np.stack([synthetic.synth_scoremap(b, J, S, K, persons=8 if J == 17 else 20) for b in range(B)])).to(DEV)
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    feat = torch.randn(B, 128, S, S, device=DEV, generator=gen)
+    tags = torch.randn(B, J, S, S, device=DEV, generator=gen)
+    gcfg = pgmp_b200.config.bench_gc_config(k=K, graph_type=graph)
+
+    def gc(sl):
+        return get_graph_constructor(gcfg, scoremaps=sm[sl], tagmaps=tags[sl], features=feat[sl], joints_gt=None,
+                                     factor_list=None, masks=None, device=DEV, testing=True, heatmaps=None,
+                                     num_joints=J).construct_graph()
+    ret = gc(slice(0, B))
+    x, ea, ei, jd, bi = ret[0], ret[1], ret[2], ret[7], ret[12]
+    n = J * K
+    N = B * n
+    assert jd.shape == (N, 3) and bool((torch.bincount(bi * J + jd[:, 2], minlength=B * J) == K).all())
+    src, dst = ei
+    ekey = src * N + dst
+    assert bool((ekey[1:] > ekey[:-1]).all()) and bool((src != dst).all()) and bool((bi[src] == bi[dst]).all())
+    if graph == "fully":
+        assert ei.shape[1] == B * n * (n - 1)
+    else:
+        rkey, _ = torch.sort(dst * N + src)
+        assert torch.equal(rkey, ekey) and int(torch.bincount(src, minlength=N).min()) >= 50
+    assert ea.shape == (ei.shape[1], J + 2) and bool((ea[:, 2:].sum(1) >= 1).all())
+
+    over = {} if J == 17 else dict(NUM_JOINTS=J, EDGE_INPUT_DIM=J + 2)
+    logits = {}
+    for prec in ("fp32", "tc"):
+        mcfg = pgmp_b200.config.flagship_mpn_config(J, B200_PRECISION=prec, STEPS=4, **over)
+        if J != 17:
+            mcfg.CLASS.OUTPUT_SIZES = [64, 32, J]
+        model = synthetic.synth_mpn_state_dict(get_mpn_model(mcfg), 5).eval().to(DEV)
+        with torch.no_grad():
+            pe, pn, pc, _ = model(x, ea, ei, node_types=jd[:, 2])
+        logits[prec] = (pe[-1], pn[-1], pc[-1])
+        if prec == "tc":          # image 1 alone == its block of the batch
+            one = gc(slice(1, 2))
+            with torch.no_grad():
+                qe, qn, qc, _ = model(one[0], one[1], one[2], node_types=one[7][:, 2])
+            nsel = bi == 1
+            esel = nsel[src]
+            assert_close(qe[-1].cpu().numpy(), pe[-1][esel].cpu().numpy(), LOGIT_TOL, f"{name}: edge logits alone vs in batch")
+            assert_close(qn[-1].cpu().numpy(), pn[-1][nsel].cpu().numpy(), LOGIT_TOL, f"{name}: node logits alone vs in batch")
+    for kind, a, b in zip(("edge", "node", "class"), logits["tc"], logits["fp32"]):
+        assert_close(a.cpu().numpy(), b.cpu().numpy(), LOGIT_TOL, f"{name}: {kind} logits tc vs fp32")
