@@ -65,10 +65,17 @@ __device__ void rescan_row(const double* __restrict__ W, const int* __restrict__
   const int lane = threadIdx.x & 31;
   double bv = -CUDART_INF;
   int bc = 0x7fffffff;
-  for (int c = r + 1 + lane; c < n; c += 32) {
-    if (!(flags[c] & 1)) continue;
-    const double v = W[(size_t)r * n + c];
-    if (v != -CUDART_INF && better(v, c, bv, bc)) { bv = v; bc = c; }
+  // four independent loads per lane in flight: the row sits in L2, a dependent loop would pay its latency per element
+  for (int c0 = r + 1 + lane; c0 < n; c0 += 128) {
+    double v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = c0 + 32 * k;
+      v[k] = (c < n && (flags[c] & 1)) ? W[(size_t)r * n + c] : -CUDART_INF;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (v[k] != -CUDART_INF && better(v[k], c0 + 32 * k, bv, bc)) { bv = v[k]; bc = c0 + 32 * k; }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -79,7 +86,7 @@ __device__ void rescan_row(const double* __restrict__ W, const int* __restrict__
   if (lane == 0) { best_val[r] = bv; best_col[r] = bc; }
 }
 
-__global__ void __launch_bounds__(kThreads) group_kernel(const pgmp_group_params p, const GroupWs ws, int M) {
+__global__ void __launch_bounds__(kThreads) group_kernel(const pgmp_group_params p, const GroupWs ws, int M, int use_smem) {
   __shared__ double s_val[32];
   __shared__ int s_row[32];
   __shared__ int s_u, s_v, s_any_lower, s_count, s_kept;
@@ -91,10 +98,13 @@ __global__ void __launch_bounds__(kThreads) group_kernel(const pgmp_group_params
   float* __restrict__ A = ws.adj32 + (size_t)b * M * M;
   double* __restrict__ W = ws.w + (size_t)b * M * M;
   int* __restrict__ mult = ws.mult + (size_t)b * M * M;
-  double* __restrict__ best_val = ws.best_val + (size_t)b * M;
-  int* __restrict__ best_col = ws.best_col + (size_t)b * M;
-  int* __restrict__ rep = ws.rep + (size_t)b * M;
-  int* __restrict__ flags = ws.flags + (size_t)b * M;
+  // the per-node bookkeeping of the greedy contraction lives in shared memory when it fits (20 bytes per node): every
+  // contraction step reads it in three dependent phases, an L2 round trip each when it sits in the workspace
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  double* __restrict__ best_val = use_smem ? reinterpret_cast<double*>(s_dyn) : ws.best_val + (size_t)b * M;
+  int* __restrict__ best_col = use_smem ? reinterpret_cast<int*>(s_dyn + (size_t)8 * M) : ws.best_col + (size_t)b * M;
+  int* __restrict__ rep = use_smem ? best_col + M : ws.rep + (size_t)b * M;
+  int* __restrict__ flags = use_smem ? best_col + 2 * M : ws.flags + (size_t)b * M;
   float* __restrict__ pn = ws.p_node + (size_t)b * M;
   int* __restrict__ typ = ws.type + (size_t)b * M;
   int* __restrict__ comp = ws.comp + (size_t)b * M;
@@ -278,6 +288,10 @@ extern "C" int pgmp_group_persons(const pgmp_group_params* p, pgmp_stream_t stre
   const GroupWs w = carve(*p, p->max_nodes_per_image);
   if (w.bytes > p->workspace_bytes) return set_error(PGMP_ERR_INVALID, "workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  PGMP_LAUNCH(group_kernel, p->batch, kThreads, 0, st, *p, w, p->max_nodes_per_image);
+  const size_t book = (size_t)20 * p->max_nodes_per_image;
+  const int use_smem = book <= 160 * 1024;
+  if (use_smem && book > 48 * 1024)
+    PGMP_CUDA(cudaFuncSetAttribute(group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)book));
+  PGMP_LAUNCH(group_kernel, p->batch, kThreads, use_smem ? book : 0, st, *p, w, p->max_nodes_per_image, use_smem);
   return PGMP_OK;
 }

@@ -45,3 +45,18 @@ tot = sum(v[1] for v in prof.values())
 for k, (c, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
     print(f"  {k:40s} x{c:3d} {ms:9.3f} ms  {100*ms/tot:5.1f}%")
 print(f"  kernel total {tot:.3f} ms")
+if len(sys.argv) > 4 and sys.argv[4] == "group":
+    from pgmp_b200.Utils import group_persons
+    args = (ret[7], out[1][-1], ret[2], out[0][-1], out[2][-1], ret[12], J)
+    group_persons(*args, node_threshold=0.1, detector_scores=ret[11])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = group_persons(*args, node_threshold=0.1, detector_scores=ret[11])
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    nv.profile(True)
+    group_persons(*args, node_threshold=0.1, detector_scores=ret[11])
+    prof = nv.profile_collect()
+    nv.profile(False)
+    print(f"  grouping tail: wall {wall*1e3:.3f} ms; kernels {dict((k, round(v[1], 3)) for k, v in prof.items())}; "
+          f"persons/img {np.mean([0 if r is None else len(r[0]) for r in res]):.1f}")
