@@ -33,6 +33,12 @@ class _GatherNodeFeatures(torch.autograd.Function):
         return g, None, None, None
 
 
+def _host_resident(t, need_contiguous=False):
+    """A pinned fp32 host tensor the gather kernels can read in place (no gradient flows into it)."""
+    return (t is not None and t.device.type == "cpu" and t.is_pinned() and t.dtype == torch.float32
+            and not t.requires_grad and (t.is_contiguous() or not need_contiguous))
+
+
 class NaiveGraphConstructor:
     """Same constructor signature as the reference class (ConstructGraph.py:11)."""
 
@@ -42,8 +48,14 @@ class NaiveGraphConstructor:
         if self.device.type != "cuda":
             raise RuntimeError("pgmp_b200 graph constructor needs a CUDA device (no CPU fallback)")
         self.scoremaps = scoremaps.to(self.device)
-        self.tagmaps = tagmaps.to(self.device) if tagmaps is not None else None
-        self.features = features.to(self.device) if features is not None else None
+        # The reference moves every input to the device (ConstructGraph.py:12-18).  Only N pixels of the feature and
+        # tag maps are ever read (N x C x 4 bytes of a 134 MB map per image), so pinned host tensors are left where
+        # they are and the gather kernels read those pixels in place over PCIe (unified addressing); like a
+        # non_blocking copy from pinned memory, the caller must not overwrite them before the stream has caught up.
+        self.tagmaps = tagmaps if _host_resident(tagmaps, need_contiguous=True) else (
+            tagmaps.to(self.device) if tagmaps is not None else None)
+        self.features = features if _host_resident(features) else (
+            features.to(self.device) if features is not None else None)
         self.joints_gt = joints_gt
         self.factor_list = factor_list
         self.masks = masks.to(self.device) if masks is not None else None

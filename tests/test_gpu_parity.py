@@ -61,6 +61,31 @@ def test_graph_constructor_channels_last_and_5d_tags():
     assert np.array_equal(ret[14].cpu().numpy(), want["joint_tags"]) and ret[14].shape[1] == 2
 
 
+def test_graph_constructor_reads_pinned_host_maps_in_place():
+    """Pinned host feature / tag maps are gathered in place over PCIe; results are bit-identical to device-resident
+    inputs, for NCHW and channels-last strides; pageable host tensors are moved to the device as the reference does."""
+    data, gcfg, nj = gc_inputs("knn_small")
+    want, _ = run_gc("knn_small")
+    sm = torch.from_numpy(data["scoremaps"]).to(DEV)
+    for fmt in (torch.contiguous_format, torch.channels_last):
+        feat_h = torch.from_numpy(data["features"]).contiguous(memory_format=fmt).pin_memory()
+        tags_h = torch.from_numpy(data["tagmaps"]).pin_memory()
+        masks = torch.from_numpy(data["masks"]).to(DEV) if gcfg.MASK_CROWDS else None
+        gc = get_graph_constructor(gcfg, scoremaps=sm, tagmaps=tags_h, features=feat_h, joints_gt=None, factor_list=None,
+                                   masks=masks, device=DEV, testing=True, heatmaps=None, num_joints=nj)
+        assert gc.features.device.type == "cpu" and gc.tagmaps.device.type == "cpu"
+        got = gc.construct_graph()
+        torch.cuda.synchronize()
+        for i in (0, 1, 2, 7, 11, 12, 14):
+            assert got[i].device.type == "cuda" and torch.equal(got[i], want[i]), i
+    gc = get_graph_constructor(gcfg, scoremaps=sm, tagmaps=torch.from_numpy(data["tagmaps"]),
+                               features=torch.from_numpy(data["features"]), joints_gt=None, factor_list=None, masks=masks,
+                               device=DEV, testing=True, heatmaps=None, num_joints=nj)
+    assert gc.features.device.type == "cuda"
+    got = gc.construct_graph()
+    assert torch.equal(got[0], want[0]) and torch.equal(got[14], want[14])
+
+
 def test_graph_constructor_capacity_errors_are_loud():
     with pytest.raises(RuntimeError, match="B200_MAX_NODES"):
         run_gc("knn_small", B200_MAX_NODES=64)
