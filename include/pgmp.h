@@ -94,10 +94,10 @@ int pgmp_gc_detect(const pgmp_gc_params* p, int64_t* counts, pgmp_stream_t strea
 
 typedef struct pgmp_gc_outputs {
   int64_t total_nodes, total_edges;          /* as read back from counts[0..1] */
-  const float* features;                     /* device [B,C,H,W] float32, arbitrary strides (elements) */
+  const float* features;                     /* device (or pinned host, read in place) [B,C,H,W] float32, arbitrary strides (elements) */
   int64_t feat_stride_b, feat_stride_c, feat_stride_y, feat_stride_x;
   int32_t channels;
-  const float* tagmaps;                      /* device [B,J,H,W] or [B,J,H,W,T] float32 contiguous */
+  const float* tagmaps;                      /* device (or pinned host) [B,J,H,W] or [B,J,H,W,T] float32 contiguous */
   int32_t tag_dim;                           /* T (1 for [B,J,H,W]) */
   float* x;                                  /* [sum N, C]            CG.py:265,269 */
   float* edge_attr;                          /* [sum E, F]            CG.py:305-325 */
