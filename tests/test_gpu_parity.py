@@ -490,3 +490,34 @@ def test_other_configs_full_image_size(name, J, S, K, graph):
             assert_close(qn[-1].cpu().numpy(), pn[-1][nsel].cpu().numpy(), LOGIT_TOL, f"{name}: node logits alone vs in batch")
     for kind, a, b in zip(("edge", "node", "class"), logits["tc"], logits["fp32"]):
         assert_close(a.cpu().numpy(), b.cpu().numpy(), LOGIT_TOL, f"{name}: {kind} logits tc vs fp32")
+
+
+@pytest.mark.parametrize("precision,aggr_sub", [("tc", "node_edge_attn"), ("tc", "None"), ("fp32", "node_edge_attn")])
+def test_mpn_bins_larger_than_a_tile(precision, aggr_sub):
+    """150 nodes of one type in a complete graph: every (target, type 0) bin holds ~150 edges, i.e. runs that cover
+    whole warps, straddle 128-slot tiles and have three parts -- the slow paths of the run reduction and of the node
+    update -- against the oracle."""
+    rng = np.random.default_rng(5)
+    n = 200
+    types = np.concatenate([np.zeros(150, np.int64), rng.integers(1, 17, size=n - 150)])
+    rng.shuffle(types)
+    xy = rng.integers(0, 512, size=(n, 2))
+    src, dst = np.nonzero(~np.eye(n, dtype=bool))                       # all ordered pairs, (src, dst)-sorted
+    ea = np.zeros((src.size, 19), np.float32)
+    ea[:, 0] = (xy[dst, 0] - xy[src, 0]) / 512.0
+    ea[:, 1] = (xy[dst, 1] - xy[src, 1]) / 512.0
+    ea[np.arange(src.size), 2 + types[src]] = 1
+    ea[np.arange(src.size), 2 + types[dst]] = 1
+    x = rng.standard_normal((n, 128)).astype(np.float32)
+    ei = np.stack([src, dst]).astype(np.int64)
+    cfg = pgmp_b200.config.flagship_mpn_config(17, STEPS=3, AGGR_SUB=aggr_sub, B200_PRECISION=precision)
+    model = synthetic.synth_mpn_state_dict(get_mpn_model(cfg), 31).eval().to(DEV)
+    with torch.no_grad():
+        pe, pn, pc, _ = model(torch.from_numpy(x).to(DEV), torch.from_numpy(ea).to(DEV), torch.from_numpy(ei).to(DEV),
+                              node_types=torch.from_numpy(types).to(DEV))
+    sd = {k: v.cpu().numpy() for k, v in model.state_dict().items()}
+    ope, opn, opc = oracle.mpn.node_classification_mpn_forward(sd, cfg, x, ea, ei, types)
+    tol = LOGIT_TOL if precision == "tc" else FP32_TOL
+    for kind, got, want in (("edge", pe, ope), ("node", pn, opn), ("class", pc, opc)):
+        for i, (a, b) in enumerate(zip(got, want)):
+            assert_close(a.cpu().numpy(), b, tol, f"{kind}_{i} vs oracle")
