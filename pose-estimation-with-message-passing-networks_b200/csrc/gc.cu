@@ -79,28 +79,21 @@ __device__ __noinline__ void spill_candidate(uint64_t key, uint64_t* __restrict_
   if (g < (uint32_t)cand_cap) gkeys[g] = key; else atomicOr(flags, (uint32_t)PGMP_GC_FLAG_CAND_OVERFLOW);
 }
 
-// Append up to 4 candidate keys per thread to the CTA's shared list with ONE shared atomic per warp and row
-// (four ballots give every candidate its slot; the order inside the list is irrelevant); a full list spills
-// unfiltered to the global list.
-__device__ __forceinline__ void emit_candidates(const uint64_t (&key)[4], uint32_t vmask, uint64_t* s_keys, uint32_t* s_cnt,
+// Append this thread's candidates (up to 4, usually none: a warp-row of 128 noisy heatmap pixels holds about five
+// local maxima) to the CTA's shared list: one shared atomic per candidate hands out the slot -- the order inside
+// the list is irrelevant, keys are unique -- and only lanes that own a candidate execute anything.  A full list
+// spills unfiltered to the global list.  Key = score bits << 32 | ~flat index: one 64-bit compare orders by
+// score desc / index asc.
+__device__ __forceinline__ void emit_candidates(const float (&sc)[4], uint32_t flat0, uint64_t* s_keys, uint32_t* s_cnt,
                                                 uint64_t* __restrict__ gkeys, uint32_t* __restrict__ gcount, int cand_cap,
                                                 uint32_t* __restrict__ flags) {
-  const uint32_t b0 = __ballot_sync(kFull, vmask & 1u), b1 = __ballot_sync(kFull, vmask & 2u);
-  const uint32_t b2 = __ballot_sync(kFull, vmask & 4u), b3 = __ballot_sync(kFull, vmask & 8u);
-  if ((b0 | b1 | b2 | b3) == 0) return;
-  const int lane = threadIdx.x & 31;
-  const int n0 = __popc(b0), n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3);
-  uint32_t base = 0;
-  if (lane == 0) base = atomicAdd(s_cnt, (uint32_t)(n0 + n1 + n2 + n3));
-  base = __shfl_sync(kFull, base, 0);
-  const uint32_t lt = (1u << lane) - 1u;
-  const uint32_t pos[4] = {base + __popc(b0 & lt), base + n0 + __popc(b1 & lt), base + n0 + n1 + __popc(b2 & lt),
-                           base + n0 + n1 + n2 + __popc(b3 & lt)};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    if (vmask & (1u << i)) {
-      if (pos[i] < kCtaCandCap) s_keys[pos[i]] = key[i];
-      else spill_candidate(key[i], gkeys, gcount, cand_cap, flags);
+    if (sc[i] > 0.f) {
+      const uint64_t key = ((uint64_t)__float_as_uint(sc[i]) << 32) | (uint64_t)(~(flat0 + (uint32_t)i));
+      const uint32_t pos = atomicAdd(s_cnt, 1u);
+      if (pos < kCtaCandCap) s_keys[pos] = key;
+      else spill_candidate(key, gkeys, gcount, cand_cap, flags);
     }
   }
 }
@@ -261,22 +254,18 @@ __device__ __forceinline__ void nms_row_step(NmsRings<R>& rg, const NmsCtx& c, c
   const int yc = yy - R;
   if (yc >= c.y0 && yc < c.y_end) {   // uniform for the CTA
     constexpr int CS = (PH + K - R) % K;   // ring slot of the centre row
-    uint64_t key[4];
-    uint32_t vmask = 0;
+    float sc[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const float x = rg.raw[CS][q];
-      const int col = 4 * c.tt + q;
       float m = rg.hm[0][q];
 #pragma unroll
       for (int i = 1; i < K; ++i) m = fmaxf(m, rg.hm[i][q]);
-      float s = 0.f;
+      sc[q] = 0.f;
       // (out-of-image columns hold zeros, so x > 0 already excludes them)
-      if (x > 0.f && x == m) s = MASK ? x * __ldg(c.mk + (yc * c.W + col)) : x;   // CG.py:1163-1165
-      key[q] = ((uint64_t)__float_as_uint(s) << 32) | (uint64_t)(~(uint32_t)(yc * c.W + col));
-      if (s > 0.f) vmask |= 1u << q;
+      if (x > 0.f && x == m) sc[q] = MASK ? x * __ldg(c.mk + (yc * c.W + 4 * c.tt + q)) : x;   // CG.py:1163-1165
     }
-    emit_candidates(key, vmask, c.s_keys, c.s_cnt, c.gkeys, c.gcount, c.cand_cap, c.flags);
+    emit_candidates(sc, (uint32_t)(yc * c.W + 4 * c.tt), c.s_keys, c.s_cnt, c.gkeys, c.gcount, c.cand_cap, c.flags);
   }
 }
 
