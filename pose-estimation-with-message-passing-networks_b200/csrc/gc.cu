@@ -87,14 +87,17 @@ __device__ __noinline__ void spill_candidate(uint64_t key, uint64_t* __restrict_
 __device__ __forceinline__ void emit_candidates(const float (&sc)[4], uint32_t flat0, uint64_t* s_keys, uint32_t* s_cnt,
                                                 uint64_t* __restrict__ gkeys, uint32_t* __restrict__ gcount, int cand_cap,
                                                 uint32_t* __restrict__ flags) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    if (sc[i] > 0.f) {
-      const uint64_t key = ((uint64_t)__float_as_uint(sc[i]) << 32) | (uint64_t)(~(flat0 + (uint32_t)i));
-      const uint32_t pos = atomicAdd(s_cnt, 1u);
-      if (pos < kCtaCandCap) s_keys[pos] = key;
-      else spill_candidate(key, gkeys, gcount, cand_cap, flags);
-    }
+  // a loop over the thread's candidates, not four predicated blocks: its trip count across the warp is the largest
+  // number of candidates any lane holds (almost always 0 or 1), and each trip costs one (warp-aggregated) atomic
+  uint32_t vm = (sc[0] > 0.f ? 1u : 0u) | (sc[1] > 0.f ? 2u : 0u) | (sc[2] > 0.f ? 4u : 0u) | (sc[3] > 0.f ? 8u : 0u);
+  while (vm) {
+    const int i = __ffs(vm) - 1;
+    vm &= vm - 1;
+    const float v = i == 0 ? sc[0] : (i == 1 ? sc[1] : (i == 2 ? sc[2] : sc[3]));
+    const uint64_t key = ((uint64_t)__float_as_uint(v) << 32) | (uint64_t)(~(flat0 + (uint32_t)i));
+    const uint32_t pos = atomicAdd(s_cnt, 1u);
+    if (pos < kCtaCandCap) s_keys[pos] = key;
+    else spill_candidate(key, gkeys, gcount, cand_cap, flags);
   }
 }
 
