@@ -129,11 +129,6 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
   uint32_t phase = 0, ld_phase = 0;
   int cur_tm = -1, cur_col = -1;
   float att_bias = 0.f;
-  // cooperative passes: item k of this thread is the 16-byte chunk c4 = wt & 15 of row (wt >> 4) + 8k; its
-  // swizzled staging address alternates between two precomputed bases (row & 15 = r0 | (k & 1) << 3)
-  const uint32_t r0 = (uint32_t)(wt >> 4), c4c = (uint32_t)(wt & 15);
-  const uint32_t item_e = add_a + r0 * 256 + ((c4c ^ r0) << 4), item_o = add_a + r0 * 256 + ((c4c ^ r0 ^ 8u) << 4);
-#define ITEM_ADDR(k) ((((k) & 1) ? item_o : item_e) + (uint32_t)(k) * 2048u)
   bool g_issued = false;        // the tile's edge features were requested during the previous tile
   const bool copier = wt == 32; // the thread that owns the bulk copies (loads of g / C, write-back of g')
   uint8_t* __restrict__ g_img = reinterpret_cast<uint8_t*>(a.g);
@@ -170,7 +165,6 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
     }
     const int e = n_e, src = n_src, dst = n_dst;
     s_dst[wt] = e >= 0 ? dst : -1;
-    s_src[wt] = e >= 0 ? src : -1;
     if (wt < 8) s_seg[wt] = wt == 0 ? 0 : kTile;
     if (tile + 1 < tile_end) {   // next tile's indices
       const int64_t sl = (int64_t)slot0 + kTile + wt;
@@ -193,56 +187,29 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
       att_bias = __ldg(a.ba + col);
       cur_col = col;
     }
-    named_bar_sync(bar_id, kWgThreads);          // s_dst / s_src visible
-    // ---- P[dst] + Q[src]: half a warp per row (coalesced 256-byte rows), all 32 loads of a thread in flight
-    float4 pq[16];
+    // ---- P[dst] and Q[src]: this thread's own two table rows, 16-byte chunks (the tables are swizzled tile images:
+    //      logical chunk q of node n sits at position q ^ (n & 15)); rows of a run share dst, so a warp's P request
+    //      touches about ten lines; all 32 loads of a thread are in flight behind the first product
+    float4 pv[kD / 4], qv[kD / 4];
     {
-      float4 qq[16];
+      const float4* __restrict__ prow = reinterpret_cast<const float4*>(a.tab_p + (size_t)(e >= 0 ? dst : 0) * kD);
+      const float4* __restrict__ qrow = reinterpret_cast<const float4*>(a.tab_q + (size_t)(e >= 0 ? src : 0) * kD);
+      const int xd = dst & 15, xs = src & 15;
 #pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const int idx = wt + k * kWgThreads;
-        const int r = idx >> 4, c4 = idx & 15;
-        const int rd = s_dst[r], rs = s_src[r];
-        pq[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        qq[k] = pq[k];
-        if (rd >= 0) {
-          pq[k] = __ldg(reinterpret_cast<const float4*>(a.tab_p + (size_t)rd * kD) + (c4 ^ (rd & 15)));   // table rows are
-          qq[k] = __ldg(reinterpret_cast<const float4*>(a.tab_q + (size_t)rs * kD) + (c4 ^ (rs & 15)));   // swizzled tile images
-        }
-      }
-      if (wt == 0) {        // the edge features have landed (usually long ago): first product
-        mbar_wait(g_bar, ld_phase);
-        fence_after_sync();
-        issue_gemm_x3<kD>(tmem, a_hi, a_lo, 0, w1_hi, w1_lo, 0, 1, false);
-        mma_commit(bar);
-      }
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        pq[k].x += qq[k].x; pq[k].y += qq[k].y; pq[k].z += qq[k].z; pq[k].w += qq[k].w;
+      for (int q = 0; q < kD / 4; ++q) {
+        pv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        qv[q] = pv[q];
+        if (e >= 0) { pv[q] = __ldg(prow + (q ^ xd)); qv[q] = __ldg(qrow + (q ^ xs)); }
       }
     }
-    // ---- staging <- C + P + Q (this thread's own 16-byte items), then R[type][dst] requested into registers
-    if (a.c0) {
-      mbar_wait(c_bar, ld_phase);
-      float4 c[16];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) c[k] = lds128f(ITEM_ADDR(k));
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        pq[k].x += c[k].x; pq[k].y += c[k].y; pq[k].z += c[k].z; pq[k].w += c[k].w;
-      }
+    if (wt == 0) {        // the edge features have landed (usually long ago): first product
+      mbar_wait(g_bar, ld_phase);
+      fence_after_sync();
+      issue_gemm_x3<kD>(tmem, a_hi, a_lo, 0, w1_hi, w1_lo, 0, 1, false);
+      mma_commit(bar);
     }
-#pragma unroll
-    for (int k = 0; k < 16; ++k) sts128f(ITEM_ADDR(k), pq[k]);
+    if (a.c0) mbar_wait(c_bar, ld_phase);          // the C image sits in the staging tile
     ld_phase ^= 1;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const int idx = wt + k * kWgThreads;
-      const int rd = s_dst[idx >> 4];
-      pq[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (rd >= 0) pq[k] = __ldg(reinterpret_cast<const float4*>(a.tab_r + ((size_t)t * a.N + rd) * kD) + ((idx & 15) ^ (rd & 15)));
-    }
-    named_bar_sync(bar_id, kWgThreads);
     mbar_wait(bar, phase);
     phase ^= 1;
     fence_after_sync();
@@ -250,7 +217,11 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
     tmem_ld64(tmem, 0, d);
 #pragma unroll
     for (int q = 0; q < kD / 4; ++q) {
-      const float4 v = lds128f(add_a + 4 * stage_index(wt, 4 * q));
+      float4 v = make_float4(pv[q].x + qv[q].x, pv[q].y + qv[q].y, pv[q].z + qv[q].z, pv[q].w + qv[q].w);
+      if (a.c0) {
+        const float4 c = lds128f(add_a + 4 * stage_index(wt, 4 * q));
+        v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
+      }
       d[4 * q + 0] = fmaxf(d[4 * q + 0] + v.x, 0.f);
       d[4 * q + 1] = fmaxf(d[4 * q + 1] + v.y, 0.f);
       d[4 * q + 2] = fmaxf(d[4 * q + 2] + v.z, 0.f);
@@ -265,9 +236,17 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
       issue_gemm_x3<kD>(tmem, a_hi, a_lo, 0, w2_hi, w2_lo, 0, 1, false);
       mma_commit(bar);
     }
-    // ---- staging <- R (already in registers) while the MMA runs
+    // ---- R[type][dst]: this thread's own row, requested now, consumed by the third epilogue
+    float4 rv[kD / 4];
+    {
+      const float4* __restrict__ rrow = reinterpret_cast<const float4*>(a.tab_r + ((size_t)t * a.N + (e >= 0 ? dst : 0)) * kD);
+      const int xd = dst & 15;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) sts128f(ITEM_ADDR(k), pq[k]);
+      for (int q = 0; q < kD / 4; ++q) {
+        rv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e >= 0) rv[q] = __ldg(rrow + (q ^ xd));
+      }
+    }
     mbar_wait(bar, phase);
     phase ^= 1;
     fence_after_sync();
@@ -353,17 +332,12 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
     phase ^= 1;
     fence_after_sync();
     tmem_ld64(tmem, 0, d);
-    // ---- message m = ReLU(d + R) replaces this thread's own staging row
-    {
-      float4 rr[kD / 4];
+    // ---- message m = ReLU(d + R) goes to this thread's own staging row (its C row was consumed by the first epilogue)
 #pragma unroll
-      for (int q = 0; q < kD / 4; ++q) rr[q] = lds128f(add_a + 4 * stage_index(wt, 4 * q));
-#pragma unroll
-      for (int q = 0; q < kD / 4; ++q)
-        sts128f(add_a + 4 * stage_index(wt, 4 * q),
-                make_float4(fmaxf(d[4 * q + 0] + rr[q].x, 0.f), fmaxf(d[4 * q + 1] + rr[q].y, 0.f),
-                            fmaxf(d[4 * q + 2] + rr[q].z, 0.f), fmaxf(d[4 * q + 3] + rr[q].w, 0.f)));
-    }
+    for (int q = 0; q < kD / 4; ++q)
+      sts128f(add_a + 4 * stage_index(wt, 4 * q),
+              make_float4(fmaxf(d[4 * q + 0] + rv[q].x, 0.f), fmaxf(d[4 * q + 1] + rv[q].y, 0.f),
+                          fmaxf(d[4 * q + 2] + rv[q].z, 0.f), fmaxf(d[4 * q + 3] + rv[q].w, 0.f)));
     if (a.with_head) {   // head layer 1 epilogue -> A, layer 2 on the tensor cores
       tmem_ld64(tmem, 64, d);
 #pragma unroll
@@ -453,7 +427,6 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
     named_bar_sync(bar_id, kWgThreads);   // the next tile overwrites the staging / operand tiles
   }
   if (copier) bulk_wait_all();
-#undef ITEM_ADDR
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc<kEdgeTmemCols>(*tmem_slot);
