@@ -161,6 +161,9 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
       if (a.c0) {
         mbar_expect_tx(c_bar, kAddTile);
         bulk_load(add_a, a.c0 + (size_t)slot0 * kD, kAddTile, c_bar);
+        // the staging tile is busy until the end of a tile, so the next tile's C cannot be fetched early; pull it
+        // into L2 now, the load above then pays an L2 hit instead of an HBM round trip at the next tile's start
+        if (tile + 1 < tile_end) bulk_prefetch_l2(a.c0 + (size_t)(slot0 + kTile) * kD, kAddTile);
       }
     }
     const int e = n_e, src = n_src, dst = n_dst;

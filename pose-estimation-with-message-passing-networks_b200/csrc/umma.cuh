@@ -56,6 +56,10 @@ __device__ __forceinline__ void bulk_store(void* gdst, uint32_t smem_src, uint32
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+// bring a contiguous global range into L2 ahead of the bulk load that will need it
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(__cvta_generic_to_global(gsrc)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
