@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
         if (e >= 0) { pv[q] = __ldg(prow + (q ^ xd)); qv[q] = __ldg(qrow + (q ^ xs)); }
       }
     }
-    if (wt == 0) {        // the edge features have landed (usually long ago): first product
+    if (wt < 32 && elect_one()) {        // the edge features have landed (usually long ago): first product
       mbar_wait(g_bar, ld_phase);
       fence_after_sync();
       issue_gemm_x3<kD>(tmem, a_hi, a_lo, 0, w1_hi, w1_lo, 0, 1, false);
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
     fence_before_sync();
     fence_async_smem();
     named_bar_sync(bar_id, kWgThreads);
-    if (wt == 0) {
+    if (wt < 32 && elect_one()) {
       fence_after_sync();
       issue_gemm_x3<kD>(tmem, a_hi, a_lo, 0, w2_hi, w2_lo, 0, 1, false);
       mma_commit(bar);
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
     fence_before_sync();
     fence_async_smem();
     named_bar_sync(bar_id, kWgThreads);
-    if (wt == 0) {
+    if (wt < 32 && elect_one()) {
       fence_after_sync();
       issue_gemm_x3<kD>(tmem, a_hi, a_lo, 0, wm_hi, wm_lo, 0, 1, false);
       if (a.with_head) issue_gemm_x3<kD>(tmem + 64, a_hi, a_lo, 0, wh1_hi, wh1_lo, 0, 1, false);
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
       fence_before_sync();
       fence_async_smem();
       named_bar_sync(bar_id, kWgThreads);
-      if (wt == 0) {
+      if (wt < 32 && elect_one()) {
         fence_after_sync();
         issue_gemm_x3<32>(tmem + 64, a_hi, a_lo, 0, wh2_hi, wh2_lo, 0, 1, false);
         mma_commit(bar);

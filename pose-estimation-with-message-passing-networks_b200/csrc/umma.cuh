@@ -66,6 +66,14 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 // generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// one lane of a converged warp (elect.sync): ptxas then knows the guarded code runs in a single thread and moves the
+// MMA / bulk-copy operands to uniform registers directly instead of wrapping every instruction in a waterfall loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- tensor memory ---------------------------------------------------------------------------
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst) {   // one full warp
