@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
   int cur_tm = -1, cur_col = -1;
   float att_bias = 0.f;
   bool g_issued = false;        // the tile's edge features were requested during the previous tile
-  const bool copier = wt == 32; // the thread that owns the bulk copies (loads of g / C, write-back of g')
+  const bool copier_warp = (wt >> 5) == 1;   // one elected lane of this warp owns the bulk copies (loads of g / C, write-back of g')
   uint8_t* __restrict__ g_img = reinterpret_cast<uint8_t*>(a.g);
 
   const int total_tiles = a.group_start[a.T] >> 7;
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
     const int col = a.attn == PGMP_ATTN_PER_TYPE ? t : 0;
     // ---- bulk requests: g (bf16 hi/lo tile image) straight into the operand tiles, C (swizzled fp32 tile image)
     //      into the staging tile; both complete on mbarriers, no registers and no per-thread copies
-    if (copier) {
+    if (copier_warp && elect_one()) {
       if (!g_issued) {
         mbar_expect_tx(g_bar, 2 * kATile);
         bulk_load(a_hi, g_img + (size_t)tile * (2 * kATile), 2 * kATile, g_bar);
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
       mma_commit(bar);
     }
     // ---- write back g' as the bf16 hi/lo tile image (what the next step's MMA consumes): one bulk copy
-    if (copier) bulk_store(g_img + (size_t)tile * (2 * kATile), a_hi, 2 * kATile);
+    if (copier_warp && elect_one()) bulk_store(g_img + (size_t)tile * (2 * kATile), a_hi, 2 * kATile);
     // ---- softmax weight of every row relative to its run's maximum; head rows: part row, split point, part maximum
     if (a.attn) {
       if (seg_last == 31)        // the run may continue in the following warps
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
       tmem_ld64(tmem, 64, d);
 #pragma unroll
       for (int o = 0; o < kD; ++o) d[o] = fmaxf(d[o] + s_bh1[o], 0.f);
-      if (copier) bulk_wait_read();           // the write-back has finished reading the operand tiles
+      if (copier_warp && elect_one()) bulk_wait_read();           // the write-back has finished reading the operand tiles
       named_bar_sync(bar_id, kWgThreads);
       store_split_row_a(a_hi, a_lo, wt, d);
       fence_before_sync();
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
     // the operand tiles are free (no head): fetch the next tile's edge features behind the reduction
     g_issued = false;
     if (!a.with_head && tile + 1 < tile_end) {
-      if (copier) {
+      if (copier_warp && elect_one()) {
         bulk_wait_read();
         mbar_expect_tx(g_bar, 2 * kATile);
         bulk_load(a_hi, g_img + (size_t)(tile + 1) * (2 * kATile), 2 * kATile, g_bar);
@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
     fence_before_sync();
     named_bar_sync(bar_id, kWgThreads);   // the next tile overwrites the staging / operand tiles
   }
-  if (copier) bulk_wait_all();
+  if (copier_warp && elect_one()) bulk_wait_all();
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc<kEdgeTmemCols>(*tmem_slot);

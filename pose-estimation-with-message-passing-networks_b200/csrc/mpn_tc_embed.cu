@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(2 * kWg, 1) edge_embed_tc_kernel(const EmbArgs
       fence_before_sync();
       fence_async_smem();
       named_bar_sync(bar_id, kWg);
-      if (wt == 0) {
+      if (wt < 32 && elect_one()) {
         fence_after_sync();
         issue_gemm_x3<kD>(tmem, a_hi, a_lo, 0, sbase + l * 2 * kWTile, sbase + l * 2 * kWTile + kWTile, 0, 1, false);
         mma_commit(bar);
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(kWg, 1) node_embed_tc_kernel(
   const uint32_t tmem = *tmem_slot;
   float d[kD], d2[kD];
   // layer 1: two 64-wide output halves, K = 128
-  if (tid == 0) {
+  if (tid < 32 && elect_one()) {
     issue_gemm_x3<kD>(tmem, a0, a0 + kATile, 2 * kATile, w1a, w1a + kWTile, 2 * kWTile, 2, false);
     issue_gemm_x3<kD>(tmem + 64, a0, a0 + kATile, 2 * kATile, w1a + 4 * kWTile, w1a + 5 * kWTile, 2 * kWTile, 2, false);
     mma_commit(bar);
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(kWg, 1) node_embed_tc_kernel(
   fence_async_smem();
   __syncthreads();
   // layer 2: K = 128 -> 64
-  if (tid == 0) {
+  if (tid < 32 && elect_one()) {
     fence_after_sync();
     issue_gemm_x3<kD>(tmem, a0, a0 + kATile, 2 * kATile, w2a, w2a + kWTile, 2 * kWTile, 2, false);
     mma_commit(bar);
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(kWg, 1) node_embed_tc_kernel(
   fence_async_smem();
   __syncthreads();
   // layer 3: 64 -> 64, no activation
-  if (tid == 0) {
+  if (tid < 32 && elect_one()) {
     fence_after_sync();
     issue_gemm_x3<kD>(tmem, a0, a0 + kATile, 0, w3a, w3a + kWTile, 0, 1, false);
     mma_commit(bar);

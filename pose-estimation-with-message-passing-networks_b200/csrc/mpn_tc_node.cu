@@ -125,8 +125,8 @@ __global__ void __launch_bounds__(kTabThreads, 1) node_tables_tc_kernel(
   const int per = (total_items + gridDim.x - 1) / gridDim.x;
   const int j0 = blockIdx.x * per, j1 = min(j0 + per, total_items);
 
-  if (tid == kTile) {
-    // ---------------- producer ----------------
+  if (tid >= kTile && elect_one()) {
+    // ---------------- producer (one elected lane of warp 4) ----------------
     auto issue_w = [&](int j) {                         // weight image of item j -> buffer (j - j0) % 3
       const int i = j - j0, buf = i % kTabWBufs;
       if (i >= kTabWBufs) mbar_wait(w_free + buf, (uint32_t)(i / kTabWBufs - 1) & 1u);
@@ -181,15 +181,15 @@ __global__ void __launch_bounds__(kTabThreads, 1) node_tables_tc_kernel(
         sts128f(st + 4 * stage_index(tid, 4 * q),
                 make_float4(d[4 * q] + bv[q].x, d[4 * q + 1] + bv[q].y, d[4 * q + 2] + bv[q].z, d[4 * q + 3] + bv[q].w));
       fence_async_smem();
-      if (tid == 0) bulk_wait_read();                   // the other staging buffer is free for the next item
+      if (tid < 32 && elect_one()) bulk_wait_read();    // the other staging buffer is free for the next item
       named_bar_sync(1, kTile);
-      if (tid == 0) {
+      if (tid < 32 && elect_one()) {
         const int64_t row0 = (int64_t)tile * kTile;
         const int64_t rows = N - row0 < kTile ? N - row0 : kTile;
         bulk_store(dst + row0 * kD, st, (uint32_t)rows * kD * 4);
       }
     }
-    if (tid == 0) bulk_wait_all();
+    if (tid < 32 && elect_one()) bulk_wait_all();
   }
   fence_before_sync();
   __syncthreads();
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(kTile) node_update_tc_kernel(AggrView av, int6
     fence_before_sync();
     fence_async_smem();
     __syncthreads();
-    if (tid == 0) {
+    if (tid < 32 && elect_one()) {
       fence_after_sync();
       issue_gemm_x3<kD>(s.tmem, a_hi, a_lo, 0, w_hi, w_lo, 0, 1, t > t0);
       mma_commit(s.bar);
