@@ -185,6 +185,7 @@ typedef struct pgmp_mpn_params {
   const void* tc_wnemb;                /* node embedding 128->128->64->64: [2][128][128], [2][64][128], [2][64][64] back to back, or NULL */
   const void* tc_wemb;                 /* [edge_emb.n_layers][2][64][64] edge embedding layers, zero-padded to 64x64, or NULL */
   const void* tc_w1_e0;                /* [2][dim][dim] mlp_edge.0 initial-edge columns (skip) or NULL */
+  const void* tc_wheads;               /* node / class heads 64->64->32->{1,J}: node W1 [2][64][64], class W1 [2][64][64], node W2 [2][32][64], class W2 [2][32][64], or NULL */
   const void* tc_wh1;                  /* [2][64][64] edge head layer 0 (BatchNorm folded), or NULL */
   const void* tc_wh2;                  /* [2][32][64] edge head layer 1, or NULL */
 

@@ -205,6 +205,10 @@ class NodeClassificationMPNSimple(nn.Module):
         head_w = spec["edge_classification"][2]     # folded Linear weights of the edge head
         if [tuple(w.shape) for w in head_w] == [(64, 64), (32, 64), (1, 32)]:
             tc["tc_wh1"], tc["tc_wh2"] = split(head_w[0]).contiguous(), split(head_w[1]).contiguous()
+        nh_w, ch_w = spec["node_classification"][2], spec["classification"][2]
+        if ([tuple(w_.shape) for w_ in nh_w[:2]] == [(64, 64), (32, 64)]
+                and [tuple(w_.shape) for w_ in ch_w[:2]] == [(64, 64), (32, 64)]):
+            tc["tc_wheads"] = torch.cat([split(w_).reshape(-1) for w_ in (nh_w[0], ch_w[0], nh_w[1], ch_w[1])]).contiguous()
         if layer.update_mlp is not None:
             wu = layer.update_mlp[0].weight.detach().float()
             tc["tc_wu"] = torch.stack([split(wu[:, t * 64:(t + 1) * 64]) for t in range(wu.shape[1] // 64)]).contiguous()

@@ -71,7 +71,7 @@ class MpnParams(C.Structure):
                 ("wm_e", C.c_void_p), ("bm", C.c_void_p), ("wa", C.c_void_p), ("ba", C.c_void_p),
                 ("wu", C.c_void_p), ("bu", C.c_void_p),
                 ("tc_w1_e", C.c_void_p), ("tc_w2", C.c_void_p), ("tc_wm_e", C.c_void_p), ("tc_wtab", C.c_void_p),
-                ("tc_wu", C.c_void_p), ("tc_wnemb", C.c_void_p), ("tc_wemb", C.c_void_p), ("tc_w1_e0", C.c_void_p), ("tc_wh1", C.c_void_p),
+                ("tc_wu", C.c_void_p), ("tc_wnemb", C.c_void_p), ("tc_wemb", C.c_void_p), ("tc_w1_e0", C.c_void_p), ("tc_wheads", C.c_void_p), ("tc_wh1", C.c_void_p),
                 ("tc_wh2", C.c_void_p),
                 ("edge_logits", C.c_void_p), ("node_logits", C.c_void_p), ("class_logits", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64)]

@@ -336,3 +336,138 @@ int mpn_node_embed_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStrea
 }
 
 }  // namespace pgmp
+
+// ------------------------------------------------------------------------------------------------
+// Node and class heads on the tensor cores for the reference's shapes 64 -> 64 -> 32 -> {1, J}
+// (NodeClassificationMPNSimple.py:81-83, 93-94; ReLU, ReLU, none): one CTA per 128-node tile reads the operand image
+// of h, runs the two first layers as one 128-column product and the two second layers as two 32-column products;
+// the last layers (32 -> 1, 32 -> J) are dot products per thread.
+// ------------------------------------------------------------------------------------------------
+namespace pgmp {
+namespace {
+
+using namespace umma;
+
+constexpr int kNhA = 2 * 2 * kATile;                               // operand blocks 0 / 1, (hi, lo) each
+constexpr int kNhW = 2 * 2 * kWTile + 2 * 2 * (kWTile / 2);        // nh_w1, ch_w1 (64 x 64), nh_w2, ch_w2 (32 x 64), (hi, lo) each
+constexpr int kNhConst = (64 + 64 + 32 + 32 + 32 + 32 * 32 + 32) * 4;   // biases, node w3, class w3 [32][J <= 32], class b3
+constexpr size_t kNhSmem = kNhA + kNhW + kNhConst + 64 + 1024;
+
+__global__ void __launch_bounds__(kWg, 1) node_heads_tc_kernel(
+    const float* __restrict__ h_img, int64_t N, int J, const __nv_bfloat16* __restrict__ w, const float* __restrict__ nb1,
+    const float* __restrict__ cb1, const float* __restrict__ nb2, const float* __restrict__ cb2, const float* __restrict__ nw3,
+    const float* __restrict__ nb3, const float* __restrict__ cw3, const float* __restrict__ cb3,
+    float* __restrict__ node_logits, float* __restrict__ class_logits) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t sb = smem_u32(base);
+  const uint32_t a0 = sb, a1 = sb + 2 * kATile;                    // hi at a, lo at a + kATile
+  const uint32_t nw1 = sb + kNhA, cw1 = nw1 + 2 * kWTile, nw2 = cw1 + 2 * kWTile, cw2 = nw2 + kWTile;   // lo = hi + tile bytes
+  float* s_c = reinterpret_cast<float*>(base + kNhA + kNhW);
+  float* s_nb1 = s_c; float* s_cb1 = s_c + 64; float* s_nb2 = s_c + 128; float* s_cb2 = s_c + 160;
+  float* s_nw3 = s_c + 192; float* s_cw3 = s_c + 224; float* s_cb3 = s_c + 224 + 32 * 32;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_cb3 + 32);
+  uint64_t* a_bar = bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+  const int tid = threadIdx.x;
+  if (tid < 32) tmem_alloc<128>(tmem_slot);
+  if (tid == 0) { mbar_init(bar, 1); mbar_init(a_bar, 1); fence_barrier_init(); }
+  __syncthreads();
+  if (tid < 32 && elect_one()) {
+    mbar_expect_tx(a_bar, 2 * kATile);
+    bulk_load(a0, reinterpret_cast<const uint8_t*>(h_img) + (size_t)blockIdx.x * (2 * kATile), 2 * kATile, a_bar);
+  }
+  load_weight_tile_a(nw1, w, kD, kD, tid, kWg);
+  load_weight_tile_a(nw1 + kWTile, w + kD * kD, kD, kD, tid, kWg);
+  load_weight_tile_a(cw1, w + 2 * kD * kD, kD, kD, tid, kWg);
+  load_weight_tile_a(cw1 + kWTile, w + 3 * kD * kD, kD, kD, tid, kWg);
+  load_weight_tile_a(nw2, w + 4 * kD * kD, 32, kD, tid, kWg);
+  load_weight_tile_a(nw2 + kWTile / 2, w + 4 * kD * kD + 32 * kD, 32, kD, tid, kWg);
+  load_weight_tile_a(cw2, w + 5 * kD * kD, 32, kD, tid, kWg);
+  load_weight_tile_a(cw2 + kWTile / 2, w + 5 * kD * kD + 32 * kD, 32, kD, tid, kWg);
+  if (tid < 64) { s_nb1[tid] = nb1[tid]; s_cb1[tid] = cb1[tid]; }
+  if (tid < 32) { s_nb2[tid] = nb2[tid]; s_cb2[tid] = cb2[tid]; s_nw3[tid] = nw3[tid]; s_cb3[tid] = tid < J ? cb3[tid] : 0.f; }
+  for (int i = tid; i < 32 * J; i += kWg) s_cw3[i] = cw3[i];
+  fence_before_sync();
+  fence_async_smem();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  if (tid < 32 && elect_one()) {
+    mbar_wait(a_bar, 0);
+    issue_gemm_x3<kD>(tmem, a0, a0 + kATile, 0, nw1, nw1 + kWTile, 0, 1, false);
+    issue_gemm_x3<kD>(tmem + 64, a0, a0 + kATile, 0, cw1, cw1 + kWTile, 0, 1, false);
+    mma_commit(bar);
+  }
+  mbar_wait(bar, 0);
+  fence_after_sync();
+  float d[kD];
+  tmem_ld64(tmem, 0, d);
+#pragma unroll
+  for (int o = 0; o < kD; ++o) d[o] = fmaxf(d[o] + s_nb1[o], 0.f);
+  store_split_row_a(a0, a0 + kATile, tid, d);
+  tmem_ld64(tmem, 64, d);
+#pragma unroll
+  for (int o = 0; o < kD; ++o) d[o] = fmaxf(d[o] + s_cb1[o], 0.f);
+  store_split_row_a(a1, a1 + kATile, tid, d);
+  fence_before_sync();
+  fence_async_smem();
+  __syncthreads();
+  if (tid < 32 && elect_one()) {
+    fence_after_sync();
+    issue_gemm_x3<32>(tmem, a0, a0 + kATile, 0, nw2, nw2 + kWTile / 2, 0, 1, false);
+    issue_gemm_x3<32>(tmem + 32, a1, a1 + kATile, 0, cw2, cw2 + kWTile / 2, 0, 1, false);
+    mma_commit(bar);
+  }
+  mbar_wait(bar, 1);
+  fence_after_sync();
+  tmem_ld64(tmem, 0, d);                                           // [0, 32) node hidden, [32, 64) class hidden
+  const int64_t row = (int64_t)blockIdx.x * kTile + tid;
+  float nl = __ldg(nb3);
+#pragma unroll
+  for (int o = 0; o < 32; ++o) {
+    d[o] = fmaxf(d[o] + s_nb2[o], 0.f);
+    nl = fmaf(d[o], s_nw3[o], nl);
+    d[32 + o] = fmaxf(d[32 + o] + s_cb2[o], 0.f);
+  }
+  if (row < N) {
+    node_logits[row] = nl;
+    for (int j = 0; j < J; ++j) {
+      float acc = s_cb3[j];
+#pragma unroll
+      for (int o = 0; o < 32; ++o) acc = fmaf(d[32 + o], s_cw3[o * J + j], acc);
+      class_logits[row * J + j] = acc;
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc<128>(tmem);
+}
+
+bool heads_are_canonical(const pgmp_mlp& m, int out) {
+  return m.n_layers == 3 && m.dims[0] == 64 && m.dims[1] == 64 && m.dims[2] == 32 && m.dims[3] == out && m.relu[0] && m.relu[1] &&
+         !m.relu[2] && !m.post_relu && !m.post_scale;
+}
+
+}  // namespace
+
+// node / class logits of the current h (operand image) when both heads have the reference's shape; *done = false otherwise
+int mpn_node_heads_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, float* node_logits, float* class_logits,
+                      cudaStream_t st, bool* done) {
+  *done = false;
+  if (!p.tc_wheads || p.num_classes > 32 || !heads_are_canonical(p.node_head, 1) || !heads_are_canonical(p.class_head, p.num_classes))
+    return PGMP_OK;
+  static bool attr = false;
+  if (!attr) {
+    PGMP_CUDA(cudaFuncSetAttribute(node_heads_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNhSmem));
+    attr = true;
+  }
+  PGMP_LAUNCH(node_heads_tc_kernel, (unsigned)ceil_div<int64_t>(p.num_nodes, kTile), kWg, kNhSmem, st, w.h_img, p.num_nodes,
+              p.num_classes, static_cast<const __nv_bfloat16*>(p.tc_wheads), p.node_head.bias[0], p.class_head.bias[0],
+              p.node_head.bias[1], p.class_head.bias[1], p.node_head.wt[2], p.node_head.bias[2], p.class_head.wt[2],
+              p.class_head.bias[2], node_logits, class_logits);
+  *done = true;
+  return PGMP_OK;
+}
+
+}  // namespace pgmp

@@ -14,6 +14,10 @@
 #include "umma.cuh"
 
 namespace pgmp {
+
+int mpn_node_heads_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, float* node_logits, float* class_logits,
+                      cudaStream_t st, bool* done);
+
 namespace {
 
 using namespace umma;
@@ -451,6 +455,14 @@ int mpn_node_update_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, int out_
               static_cast<const __nv_bfloat16*>(p.tc_wu), w.upd_partial);
   float* nl = out_slot >= 0 ? p.node_logits + (size_t)out_slot * N : nullptr;
   float* cl = out_slot >= 0 ? p.class_logits + (size_t)out_slot * N * p.num_classes : nullptr;
+  bool tc_heads = out_slot >= 0 && p.tc_wheads != nullptr;
+  if (tc_heads) {      // plain finish, then the heads on the tensor cores (when they have the reference's shape)
+    PGMP_LAUNCH((node_finish_kernel<kFinThreads>), tiles, kFinThreads, 0, st, w.upd_partial, N, Np, groups, p.bu, w.h, w.h_img,
+                0, p.node_head, p.class_head, nl, cl);
+    const int rc = mpn_node_heads_tc(p, w, nl, cl, st, &tc_heads);
+    if (rc != PGMP_OK) return rc;
+    if (tc_heads) return PGMP_OK;
+  }
   if (out_slot >= 0) {
     PGMP_LAUNCH((node_finish_kernel<kTile>), tiles, kTile, fin_smem, st, w.upd_partial, N, Np, groups, p.bu, w.h, w.h_img, 1,
                 p.node_head, p.class_head, nl, cl);
