@@ -238,7 +238,8 @@ def test_mpn_tensor_core_within_logit_tolerance(name):
     dict(NODE_EMB=dict(OUTPUT_SIZES=[96, 64])),                          # not the 128-128-64-64 chain: SIMT node embedding
     dict(EDGE_CLASS=dict(OUTPUT_SIZES=[48, 1])),                         # not the 64-64-32-1 head: SIMT edge head on the images
     dict(SKIP=False, EDGE_EMB=dict(OUTPUT_SIZES=[80, 64])),              # no C rows at all
-], ids=["wide_edge_emb", "short_node_emb", "short_edge_head", "noskip_wide_edge_emb"])
+    dict(NODE_CLASS=dict(OUTPUT_SIZES=[48, 1])),                         # not the 64-64-32-1 head: SIMT node / class heads
+], ids=["wide_edge_emb", "short_node_emb", "short_edge_head", "noskip_wide_edge_emb", "short_node_head"])
 def test_mpn_tensor_core_fallback_shapes(over):
     """Layer shapes the tensor-core kernels do not cover run the SIMT stage inside the tensor-core forward; results
     stay within the logit tolerance of the oracle."""
