@@ -679,22 +679,30 @@ __global__ void __launch_bounds__(256) emit_edges_fully_kernel(
 
 // edge_attr[e] = [ (x_dst - x_src)/norm, (y_dst - y_src)/norm, two_hot(type_src, type_dst) ]  (CG.py:305-325);
 // IEEE division keeps the fp32 result identical to torch's.
+// one warp = 32 consecutive edges: the lanes fetch the endpoint records of their own edge once, then write the
+// 32 x F block element-wise (fully coalesced), taking the records of element i's edge from lane i / F by shuffle
 __global__ void __launch_bounds__(256) edge_attr_kernel(
     int64_t total_edges, int F, int J, int feats, float norm, const int64_t* __restrict__ edge_index,
     const int32_t* __restrict__ gnode_xyt, float* __restrict__ edge_attr) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total_edges * F) return;
-  const int64_t e = idx / F;
-  int f = (int)(idx - e * F);
-  const int s = gnode_xyt[edge_index[e]], d = gnode_xyt[edge_index[total_edges + e]];
-  float v;
-  if (feats & PGMP_EDGE_FEAT_POSITION) {
-    if (f == 0) { edge_attr[idx] = __fdiv_rn((float)(px(d) - px(s)), norm); return; }
-    if (f == 1) { edge_attr[idx] = __fdiv_rn((float)(py(d) - py(s)), norm); return; }
-    f -= 2;
+  const int lane = threadIdx.x & 31;
+  const int64_t e0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+  if (e0 >= total_edges) return;
+  const int64_t e = e0 + lane;
+  int s = 0, d = 0;
+  if (e < total_edges) { s = gnode_xyt[edge_index[e]]; d = gnode_xyt[edge_index[total_edges + e]]; }
+  const int n_el = (int)min((int64_t)32, total_edges - e0) * F;
+  float* __restrict__ out = edge_attr + e0 * F;
+  const int pos = (feats & PGMP_EDGE_FEAT_POSITION) ? 2 : 0;
+  for (int base = 0; base < n_el; base += 32) {
+    const int i = base + lane;
+    const int le = min(i / F, 31);
+    const int f = i - le * F;
+    const int ss = __shfl_sync(kFull, s, le), dd = __shfl_sync(kFull, d, le);
+    float v;
+    if (f < pos) v = __fdiv_rn((float)(f == 0 ? px(dd) - px(ss) : py(dd) - py(ss)), norm);   // CG.py:305-317
+    else v = (f - pos == pt(ss) || f - pos == pt(dd)) ? 1.f : 0.f;                            // two-hot, :323-325
+    if (i < n_el) out[i] = v;
   }
-  v = (f == pt(s) || f == pt(d)) ? 1.f : 0.f;
-  edge_attr[idx] = v;
 }
 
 int validate(const pgmp_gc_params* p) {
@@ -825,7 +833,7 @@ extern "C" int pgmp_gc_emit(const pgmp_gc_params* p, const pgmp_gc_outputs* o, p
   }
   if (o->edge_attr) {
     const int F = ((p->edge_features & PGMP_EDGE_FEAT_POSITION) ? 2 : 0) + ((p->edge_features & PGMP_EDGE_FEAT_TYPE) ? J : 0);
-    PGMP_LAUNCH(edge_attr_kernel, (unsigned)ceil_div<int64_t>(E * F, 256), 256, 0, st, E, F, J, p->edge_features,
+    PGMP_LAUNCH(edge_attr_kernel, (unsigned)ceil_div<int64_t>(E, 256), 256, 0, st, E, F, J, p->edge_features,
                 p->norm_factor, o->edge_index, w.gnode_xyt, o->edge_attr);
   }
   return PGMP_OK;
