@@ -378,15 +378,23 @@ __global__ void __launch_bounds__(THREADS) node_finish_kernel(const float* __res
     const int idx = base + threadIdx.x + k * THREADS;
     v[k] = __ldg(reinterpret_cast<const float4*>(partial + (row0 + (idx >> 4)) * kD + 4 * (idx & 15)));
   }
-  for (int g = 1; g < groups; ++g) {
-    float4 w[4];
+  for (int g0 = 1; g0 < groups; g0 += 4) {       // four groups' loads in flight; the sum keeps the fixed group order
+    float4 w[4][4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int idx = base + threadIdx.x + k * THREADS;
-      w[k] = __ldg(reinterpret_cast<const float4*>(partial + ((size_t)g * Np + row0 + (idx >> 4)) * kD + 4 * (idx & 15)));
-    }
+    for (int gg = 0; gg < 4; ++gg)
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { v[k].x += w[k].x; v[k].y += w[k].y; v[k].z += w[k].z; v[k].w += w[k].w; }
+      for (int k = 0; k < 4; ++k) {
+        const int idx = base + threadIdx.x + k * THREADS;
+        w[gg][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g0 + gg < groups)
+          w[gg][k] = __ldg(reinterpret_cast<const float4*>(partial + ((size_t)(g0 + gg) * Np + row0 + (idx >> 4)) * kD + 4 * (idx & 15)));
+      }
+#pragma unroll
+    for (int gg = 0; gg < 4; ++gg)
+      if (g0 + gg < groups) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { v[k].x += w[gg][k].x; v[k].y += w[gg][k].y; v[k].z += w[gg][k].z; v[k].w += w[gg][k].w; }
+      }
   }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
