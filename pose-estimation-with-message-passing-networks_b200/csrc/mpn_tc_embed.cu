@@ -18,7 +18,8 @@ constexpr int kOffBias = (kMaxL + 1) * 2 * kWTile;         // [(kMaxL + 1)][64] 
 constexpr int kOffWgE = kOffBias + 2048;                   // operand tiles must stay 1024-byte aligned
 constexpr int kWgBytesE = 2 * kATile + 1024;               // A hi/lo (also the fp32 staging of C) + mbarrier
 static_assert((kMaxL + 1) * kD * 4 <= 2048 && kOffWgE % 1024 == 0 && kWgBytesE % 1024 == 0, "alignment");
-constexpr size_t kEmbSmem = kOffWgE + 2 * kWgBytesE + 64 + 1024;
+constexpr int kEmbWgs = 3;                                   // warpgroups (tiles in flight) per CTA: 114 + 3 x 33 KB of shared memory
+constexpr size_t kEmbSmem = kOffWgE + kEmbWgs * kWgBytesE + 64 + 1024;
 
 struct EmbArgs {
   const float* edge_attr; int F;                            // [E][F]
@@ -31,7 +32,7 @@ struct EmbArgs {
   float* g_img; float* c0;
 };
 
-__global__ void __launch_bounds__(2 * kWg, 1) edge_embed_tc_kernel(const EmbArgs a) {
+__global__ void __launch_bounds__(kEmbWgs * kWg, 1) edge_embed_tc_kernel(const EmbArgs a) {
   extern __shared__ uint8_t smem_raw[];
   // (offset arithmetic on the __shared__ array keeps the shared address space visible to the compiler: LDS / STS, not generic LD / ST)
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -41,16 +42,16 @@ __global__ void __launch_bounds__(2 * kWg, 1) edge_embed_tc_kernel(const EmbArgs
   uint8_t* wgb = base + kOffWgE + wg * kWgBytesE;
   const uint32_t a_hi = smem_u32(wgb), a_lo = a_hi + kATile;
   uint64_t* bar = reinterpret_cast<uint64_t*>(wgb + 2 * kATile);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base + kOffWgE + 2 * kWgBytesE);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base + kOffWgE + kEmbWgs * kWgBytesE);
   const int L = a.n_layers, LC = L + (a.w_c ? 1 : 0);
 
-  if (warp == 0) tmem_alloc<128>(tmem_slot);
+  if (warp == 0) tmem_alloc<256>(tmem_slot);
   if (wt == 0) mbar_init(bar, 1);
   if (tid == 0) fence_barrier_init();
   for (int l = 0; l < LC; ++l) {
     const __nv_bfloat16* src = l < L ? a.w + (size_t)l * 2 * kD * kD : a.w_c;
-    load_weight_tile_a(sbase + l * 2 * kWTile, src, kD, kD, tid, 2 * kWg);
-    load_weight_tile_a(sbase + l * 2 * kWTile + kWTile, src + kD * kD, kD, kD, tid, 2 * kWg);
+    load_weight_tile_a(sbase + l * 2 * kWTile, src, kD, kD, tid, kEmbWgs * kWg);
+    load_weight_tile_a(sbase + l * 2 * kWTile + kWTile, src + kD * kD, kD, kD, tid, kEmbWgs * kWg);
     if (tid < kD) {
       const float* b = l < L ? a.bias[l] : a.b_c;
       const int wdt = l < L ? a.width[l] : kD;
@@ -66,9 +67,9 @@ __global__ void __launch_bounds__(2 * kWg, 1) edge_embed_tc_kernel(const EmbArgs
   uint32_t phase = 0;
 
   const int total_tiles = a.group_start[a.T] >> 7;
-  const int units = 2 * gridDim.x;
+  const int units = kEmbWgs * gridDim.x;
   const int per_unit = (total_tiles + units - 1) / units;
-  const int tile_begin = (blockIdx.x * 2 + wg) * per_unit;
+  const int tile_begin = (blockIdx.x * kEmbWgs + wg) * per_unit;
   const int tile_end = min(tile_begin + per_unit, total_tiles);
   for (int tile = tile_begin; tile < tile_end; ++tile) {
     const int64_t slot = (int64_t)tile * kTile + wt;
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(2 * kWg, 1) edge_embed_tc_kernel(const EmbArgs
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<128>(*tmem_slot);
+  if (warp == 0) tmem_dealloc<256>(*tmem_slot);
 }
 
 }  // namespace
@@ -176,8 +177,8 @@ int mpn_edge_embed_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStrea
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const unsigned max_units = (unsigned)ceil_div<uint64_t>(w.max_slots / kTile, 2);
-  PGMP_LAUNCH(edge_embed_tc_kernel, max_units < (unsigned)sms ? max_units : (unsigned)sms, 2 * kWg, kEmbSmem, st, a);
+  const unsigned max_units = (unsigned)ceil_div<uint64_t>(w.max_slots / kTile, kEmbWgs);
+  PGMP_LAUNCH(edge_embed_tc_kernel, max_units < (unsigned)sms ? max_units : (unsigned)sms, kEmbWgs * kWg, kEmbSmem, st, a);
   *done = true;
   return PGMP_OK;
 }
