@@ -194,14 +194,15 @@ __device__ __forceinline__ float4 load_chunk(const float* __restrict__ p, bool h
   return v;
 }
 
+// one address per row and thread: the own chunk at map + off_v + yy * W, the neighbour chunks 4 elements either side
 template <bool VEC>
 __device__ __forceinline__ RowRegs load_row(const float* __restrict__ map, int yy, int H, int W, const LoadPlan& lp) {
   RowRegs q;
   const bool ok = (unsigned)yy < (unsigned)H;
-  const int base = ok ? yy * W : 0;   // a map has at most 4096 x 4096 elements: 32-bit offsets
-  q.v = load_chunk<VEC>(map + (base + lp.off_v), ok && lp.has_v, lp.n_v);
-  q.l = load_chunk<VEC>(map + (base + lp.off_l), ok && lp.has_l, lp.n_l);
-  q.r = load_chunk<VEC>(map + (base + lp.off_r), ok && lp.has_r, lp.n_r);
+  const float* __restrict__ p = map + lp.off_v + (ok ? yy * W : 0);   // a map has at most 4096 x 4096 elements: 32-bit offsets
+  q.v = load_chunk<VEC>(p, ok && lp.has_v, lp.n_v);
+  q.l = load_chunk<VEC>(p - 4, ok && lp.has_l, lp.n_l);
+  q.r = load_chunk<VEC>(p + 4, ok && lp.has_r, lp.n_r);
   return q;
 }
 
