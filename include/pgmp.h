@@ -128,6 +128,25 @@ int pgmp_gc_emit(const pgmp_gc_params* p, const pgmp_gc_outputs* o, pgmp_stream_
 #define PGMP_PRECISION_TC 1    /* tcgen05 tensor-core message-passing steps, fp32 accumulation */
 
 /* One _make_mlp chain with eval BatchNorm folded into the following Linear. */
+/* Node features at the candidates straight from the backbone feature map: replaces
+ * self.feature_gather(feat) (nn.Conv2d(Cin, Cout, 3, 1, 1), PoseEstimation.py:64-66, 79, 341), the bilinear
+ * interpolate(..., size, align_corners=False) of PoseEstimation.py:442-450 and the gather of ConstructGraph.py:265,269 */
+typedef struct pgmp_gather_conv_params {
+  const float* features;                     /* device (or pinned host) [B, Cin, h, w] float32, arbitrary strides (elements) */
+  int64_t feat_stride_b, feat_stride_c, feat_stride_y, feat_stride_x;
+  int32_t cin, height, width;                /* Cin, h, w of the backbone feature map */
+  int32_t cout;                              /* output channels (<= 128) */
+  int32_t out_height, out_width;             /* size the reference interpolates to (the heatmap size) */
+  const float* weight_t;                     /* device [(ky * 3 + kx) * Cin + ci][Cout] = conv weight transposed */
+  const float* bias;                         /* device [Cout] */
+  const int64_t* joint_det;                  /* device [N, 3] (x, y, type) as written by pgmp_gc_emit */
+  const int64_t* batch_index;                /* device [N] */
+  int64_t num_nodes;
+  float* x;                                  /* device [N, Cout] */
+} pgmp_gather_conv_params;
+/* x = interpolate(feature_gather(feat))[:, y, x] at the candidates only; stream-ordered after pgmp_gc_emit */
+int pgmp_gc_gather_conv(const pgmp_gather_conv_params* p, pgmp_stream_t stream);
+
 typedef struct pgmp_mlp {
   int32_t n_layers;
   int32_t dims[PGMP_MAX_LAYERS + 1];   /* dims[0] = input width, dims[l+1] = output width of layer l */

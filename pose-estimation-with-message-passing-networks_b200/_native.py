@@ -51,6 +51,14 @@ class GcOutputs(C.Structure):
                 ("joint_tags", C.c_void_p)]
 
 
+class GatherConvParams(C.Structure):
+    _fields_ = [("features", C.c_void_p), ("feat_stride_b", C.c_int64), ("feat_stride_c", C.c_int64),
+                ("feat_stride_y", C.c_int64), ("feat_stride_x", C.c_int64), ("cin", C.c_int32), ("height", C.c_int32),
+                ("width", C.c_int32), ("cout", C.c_int32), ("out_height", C.c_int32), ("out_width", C.c_int32),
+                ("weight_t", C.c_void_p), ("bias", C.c_void_p), ("joint_det", C.c_void_p), ("batch_index", C.c_void_p),
+                ("num_nodes", C.c_int64), ("x", C.c_void_p)]
+
+
 class Mlp(C.Structure):
     _fields_ = [("n_layers", C.c_int32), ("dims", C.c_int32 * (MAX_LAYERS + 1)), ("relu", C.c_int32 * MAX_LAYERS),
                 ("wt", C.c_void_p * MAX_LAYERS), ("bias", C.c_void_p * MAX_LAYERS), ("post_relu", C.c_int32),
@@ -98,6 +106,7 @@ SYMBOLS = {
     "pgmp_gc_workspace_bytes": (C.c_uint64, [C.POINTER(GcParams)]),
     "pgmp_gc_detect": (C.c_int, [C.POINTER(GcParams), C.c_void_p, C.c_void_p]),
     "pgmp_gc_emit": (C.c_int, [C.POINTER(GcParams), C.POINTER(GcOutputs), C.c_void_p]),
+    "pgmp_gc_gather_conv": (C.c_int, [C.POINTER(GatherConvParams), C.c_void_p]),
     "pgmp_selftest_umma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pgmp_mpn_workspace_bytes": (C.c_uint64, [C.POINTER(MpnParams)]),
     "pgmp_mpn_forward": (C.c_int, [C.POINTER(MpnParams), C.c_void_p]),

@@ -1,0 +1,150 @@
+// Node features at the candidate pixels without materialising the feature maps:
+//   x[n] = interpolate(feature_gather(feat), size = (H, W), bilinear, align_corners = False)[:, y_n, x_n]
+// (PoseEstimation.py:64-66, 79, 341, 442-450; ConstructGraph.py:265, 269).  Convolution and interpolation are
+// linear, so per candidate the 3 x 3 x Cin input patch is interpolated first (4 taps; the zero padding of the
+// convolution is applied per tap) and multiplied once with the [9 Cin, Cout] weight matrix.  The reference writes
+// and re-reads B x 128 x H x W floats (134 MB per 512-pixel image) for what is N x 128 outputs.
+//
+// One persistent CTA of 256 threads = (output channel c = tid & 127, half = tid >> 7) works on 8 candidates at a
+// time: the 4 x 4 x Cin raw neighbourhood of each candidate is fetched once into shared memory (one 32-byte sector
+// per element from NCHW maps -- device memory or pinned host memory), the interpolated patches P[k][8] are built
+// from it, then every thread accumulates 4 candidates: per k one conflict-free weight read, one broadcast 16-byte
+// patch read and 4 FMAs.  The transposed weights stay resident in shared memory (9 Cin Cout floats, 147 KB for
+// 32 -> 128 channels).
+#include "common.cuh"
+
+namespace pgmp {
+namespace {
+
+constexpr int kGcThreads = 256;
+constexpr int kGcCand = 8;              // candidates per pass
+constexpr int kGcMaxCout = 128;         // one thread per output channel and half
+
+struct GatherConvArgs {
+  const float* feat; int64_t sb, sc, sy, sx;
+  int cin, h, w, cout, out_h, out_w;
+  const float* wmat; const float* bias;   // [9 cin][cout], [cout]
+  const int64_t* joint_det; const int64_t* batch_index; int64_t n;
+  float* x;
+  int w_in_smem;
+};
+
+// ATen area_pixel_compute_source_index for align_corners = False, one axis
+__device__ __forceinline__ void bilinear_tap(int dst, int in_size, int out_size, int& i0, int& i1, float& l0, float& l1) {
+  const float scale = __fdiv_rn((float)in_size, (float)out_size);
+  float src = __fsub_rn(__fmul_rn(__fadd_rn((float)dst, 0.5f), scale), 0.5f);
+  src = fmaxf(src, 0.f);
+  i0 = min((int)floorf(src), in_size - 1);
+  i1 = min(i0 + 1, in_size - 1);
+  l1 = __fsub_rn(src, (float)i0);
+  l0 = __fsub_rn(1.f, l1);
+}
+
+__global__ void __launch_bounds__(kGcThreads, 1) gather_conv_kernel(const GatherConvArgs a) {
+  extern __shared__ __align__(16) float s_mem[];
+  const int K = 9 * a.cin;
+  float* s_w = s_mem;                                              // [K][cout] when resident
+  float* s_p = s_mem + (a.w_in_smem ? (size_t)K * a.cout : 0);     // [K][8] interpolated patches
+  float* s_r = s_p + (size_t)K * kGcCand;                          // [8][16][cin] raw 4 x 4 neighbourhoods
+  __shared__ int s_y0[kGcCand], s_x0[kGcCand], s_dy[kGcCand], s_dx[kGcCand], s_b[kGcCand];
+  __shared__ float s_ly[kGcCand][2], s_lx[kGcCand][2];
+  const int tid = threadIdx.x;
+  if (a.w_in_smem)
+    for (int i = tid; i < K * a.cout; i += kGcThreads) s_w[i] = __ldg(a.wmat + i);
+  const float* __restrict__ wsrc = a.w_in_smem ? s_w : a.wmat;
+  const int c = tid & (kGcMaxCout - 1), half = tid >> 7;
+  const float bias = c < a.cout ? __ldg(a.bias + c) : 0.f;
+  const int64_t groups = (a.n + kGcCand - 1) / kGcCand;
+  for (int64_t grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+    const int64_t n0 = grp * kGcCand;
+    __syncthreads();                                               // the previous pass no longer reads s_p / s_r
+    if (tid < kGcCand) {
+      const int64_t n = n0 + tid;
+      int y0 = 0, y1 = 0, x0 = 0, x1 = 0, b = -1;
+      float ly0 = 0.f, ly1 = 0.f, lx0 = 0.f, lx1 = 0.f;
+      if (n < a.n) {
+        b = (int)a.batch_index[n];
+        bilinear_tap((int)a.joint_det[n * 3 + 1], a.h, a.out_h, y0, y1, ly0, ly1);
+        bilinear_tap((int)a.joint_det[n * 3 + 0], a.w, a.out_w, x0, x1, lx0, lx1);
+      }
+      s_b[tid] = b; s_y0[tid] = y0; s_x0[tid] = x0; s_dy[tid] = y1 - y0; s_dx[tid] = x1 - x0;
+      s_ly[tid][0] = ly0; s_ly[tid][1] = ly1; s_lx[tid][0] = lx0; s_lx[tid][1] = lx1;
+    }
+    __syncthreads();
+    // raw neighbourhoods: rows y0 - 1 .. y0 + 2, columns x0 - 1 .. x0 + 2, zero outside the map (conv padding)
+    for (int i = tid; i < kGcCand * 16 * a.cin; i += kGcThreads) {
+      const int ci = i % a.cin, pos = (i / a.cin) & 15, g = i / (16 * a.cin);
+      const int yy = s_y0[g] - 1 + (pos >> 2), xx = s_x0[g] - 1 + (pos & 3);
+      float v = 0.f;
+      if (s_b[g] >= 0 && (unsigned)yy < (unsigned)a.h && (unsigned)xx < (unsigned)a.w)
+        v = __ldg(a.feat + s_b[g] * a.sb + ci * a.sc + yy * a.sy + xx * a.sx);
+      s_r[i] = v;
+    }
+    __syncthreads();
+    // interpolated patches, taps in the order (y0,x0), (y0,x1), (y1,x0), (y1,x1)
+    for (int i = tid; i < K * kGcCand; i += kGcThreads) {
+      const int g = i & (kGcCand - 1), k = i >> 3;
+      const int ci = k % a.cin, kk = k / a.cin, ky = kk / 3, kx = kk - 3 * ky;
+      const float* __restrict__ r = s_r + (size_t)g * 16 * a.cin + ci;
+      float p = 0.f;
+#pragma unroll
+      for (int ty = 0; ty < 2; ++ty)
+#pragma unroll
+        for (int tx = 0; tx < 2; ++tx) {
+          const int py = (ty ? s_dy[g] : 0) + ky, px = (tx ? s_dx[g] : 0) + kx;
+          p = __fadd_rn(p, __fmul_rn(__fmul_rn(s_ly[g][ty], s_lx[g][tx]), r[(py * 4 + px) * a.cin]));
+        }
+      s_p[i] = p;
+    }
+    __syncthreads();
+    if (c < a.cout) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      const float4* __restrict__ p4 = reinterpret_cast<const float4*>(s_p) + half;
+#pragma unroll 4
+      for (int k = 0; k < K; ++k) {
+        const float wv = wsrc[(size_t)k * a.cout + c];
+        const float4 pv = p4[2 * k];
+        acc[0] = fmaf(pv.x, wv, acc[0]); acc[1] = fmaf(pv.y, wv, acc[1]);
+        acc[2] = fmaf(pv.z, wv, acc[2]); acc[3] = fmaf(pv.w, wv, acc[3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t n = n0 + half * 4 + j;
+        if (n < a.n) a.x[n * a.cout + c] = acc[j] + bias;
+      }
+    }
+  }
+}
+
+}  // namespace
+}  // namespace pgmp
+
+extern "C" int pgmp_gc_gather_conv(const pgmp_gather_conv_params* p, pgmp_stream_t stream) {
+  using namespace pgmp;
+  if (!p) return set_error(PGMP_ERR_INVALID, "null params");
+  if (p->num_nodes < 0 || p->cin <= 0 || p->cout <= 0 || p->cout > kGcMaxCout || p->height <= 0 || p->width <= 0 ||
+      p->out_height <= 0 || p->out_width <= 0)
+    return set_error(PGMP_ERR_INVALID, "bad sizes (cout <= %d)", kGcMaxCout);
+  if (p->num_nodes == 0) return PGMP_OK;
+  if (!p->features || !p->weight_t || !p->bias || !p->joint_det || !p->batch_index || !p->x)
+    return set_error(PGMP_ERR_INVALID, "null pointer");
+  GatherConvArgs a;
+  a.feat = p->features; a.sb = p->feat_stride_b; a.sc = p->feat_stride_c; a.sy = p->feat_stride_y; a.sx = p->feat_stride_x;
+  a.cin = p->cin; a.h = p->height; a.w = p->width; a.cout = p->cout; a.out_h = p->out_height; a.out_w = p->out_width;
+  a.wmat = p->weight_t; a.bias = p->bias; a.joint_det = p->joint_det; a.batch_index = p->batch_index; a.n = p->num_nodes;
+  a.x = p->x;
+  const size_t K = (size_t)9 * p->cin;
+  const size_t work = (K * kGcCand + (size_t)kGcCand * 16 * p->cin) * sizeof(float);
+  const size_t wbytes = K * p->cout * sizeof(float);
+  a.w_in_smem = work + wbytes <= 200 * 1024;
+  const size_t smem = work + (a.w_in_smem ? wbytes : 0);
+  if (smem > 200 * 1024) return set_error(PGMP_ERR_INVALID, "cin too large for the patch buffers");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PGMP_CUDA(cudaFuncSetAttribute(gather_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t groups = (p->num_nodes + kGcCand - 1) / kGcCand;
+  PGMP_LAUNCH(gather_conv_kernel, (unsigned)(groups < sms ? groups : sms), kGcThreads, smem, st, a);
+  return PGMP_OK;
+}

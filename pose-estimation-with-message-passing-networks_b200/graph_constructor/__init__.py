@@ -39,6 +39,48 @@ def _host_resident(t, need_contiguous=False):
             and not t.requires_grad and (t.is_contiguous() or not need_contiguous))
 
 
+class ConvUpsampleFeatures:
+    """Lazy ``interpolate(feature_gather(feat), size, mode="bilinear", align_corners=False)``.
+
+    Pass it as ``features=`` instead of the materialised ``[B, 128, H, W]`` tensor: the graph constructor then
+    evaluates the 3x3 convolution and the interpolation only at the candidate pixels, straight from the backbone's
+    feature map (``PoseEstimation.py:64-66, 79, 341, 442-450`` + ``ConstructGraph.py:265, 269``).
+
+    ``feat``: ``[B, Cin, h, w]`` float32, CUDA or pinned host.  ``conv``: the model's ``feature_gather``
+    (``nn.Conv2d(Cin, Cout <= 128, 3, 1, 1)``) or a ``(weight [Cout,Cin,3,3], bias [Cout])`` pair.  ``size``: the
+    ``(H, W)`` the reference interpolates to (the heatmap size; equal to ``(h, w)`` in the training ``forward``).
+    Inference only: no gradient flows to ``feat`` or the convolution.
+    """
+
+    def __init__(self, feat, conv, size):
+        weight, bias = (conv.weight, conv.bias) if hasattr(conv, "weight") else conv
+        if feat.dim() != 4 or feat.dtype != torch.float32:
+            raise TypeError("feat must be a float32 [B, Cin, h, w] tensor")
+        if tuple(weight.shape[1:]) != (feat.shape[1], 3, 3):
+            raise ValueError("feature_gather must be a 3x3 convolution over %d channels (PoseEstimation.py:64)" % feat.shape[1])
+        if hasattr(conv, "padding") and (tuple(conv.padding) != (1, 1) or tuple(conv.stride) != (1, 1)):
+            raise NotImplementedError("FEATURE_GATHER_PADDING / stride other than 1 (default_config.py:26-27)")
+        if weight.shape[0] > 128:
+            raise NotImplementedError("more than 128 output channels")
+        self.feat = feat
+        self.weight, self.bias = weight, bias
+        self.size = (int(size[0]), int(size[1]))
+        self.shape = (feat.shape[0], weight.shape[0]) + self.size
+        self.dtype = torch.float32
+        self.requires_grad = False
+
+    def pack(self, device):
+        """Transposed weights ``[(ky, kx, ci), co]`` and bias on ``device`` (cached per parameter version)."""
+        key = (self.weight.data_ptr(), self.weight._version, str(device))
+        if getattr(self, "_packed_key", None) != key:
+            w = self.weight.detach().to(device=device, dtype=torch.float32)
+            self._wt = w.permute(2, 3, 1, 0).reshape(-1, w.shape[0]).contiguous()
+            b = self.bias if self.bias is not None else torch.zeros(w.shape[0])
+            self._b = b.detach().to(device=device, dtype=torch.float32).contiguous()
+            self._packed_key = key
+        return self._wt, self._b
+
+
 class NaiveGraphConstructor:
     """Same constructor signature as the reference class (ConstructGraph.py:11)."""
 
@@ -54,8 +96,13 @@ class NaiveGraphConstructor:
         # non_blocking copy from pinned memory, the caller must not overwrite them before the stream has caught up.
         self.tagmaps = tagmaps if _host_resident(tagmaps, need_contiguous=True) else (
             tagmaps.to(self.device) if tagmaps is not None else None)
-        self.features = features if _host_resident(features) else (
-            features.to(self.device) if features is not None else None)
+        if isinstance(features, ConvUpsampleFeatures):
+            if not (_host_resident(features.feat) or features.feat.device.type == "cuda"):
+                features.feat = features.feat.to(self.device)
+            self.features = features
+        else:
+            self.features = features if _host_resident(features) else (
+                features.to(self.device) if features is not None else None)
         self.joints_gt = joints_gt
         self.factor_list = factor_list
         self.masks = masks.to(self.device) if masks is not None else None
@@ -147,7 +194,11 @@ class NaiveGraphConstructor:
                 tags_c = tags.detach().float().contiguous()
                 joint_tags = torch.empty((N,) if tags.dim() == 4 else (N, tag_dim), dtype=torch.float32, device=dev)
             o = nv.GcOutputs(total_nodes=N, total_edges=E)
-            if feat is not None:
+            fused = isinstance(feat, ConvUpsampleFeatures)
+            if fused:
+                if feat.size != (H, W):
+                    raise ValueError("ConvUpsampleFeatures size %s != heatmap size %s" % (feat.size, (H, W)))
+            elif feat is not None:
                 if feat.dtype != torch.float32:
                     raise TypeError("features must be float32 (the reference gathers fp32, CG.py:265)")
                 fd = feat.detach()
@@ -160,8 +211,17 @@ class NaiveGraphConstructor:
             o.edge_attr, o.edge_index = edge_attr.data_ptr(), edge_index.data_ptr()
             o.joint_det, o.joint_scores, o.batch_index = joint_det.data_ptr(), joint_scores.data_ptr(), batch_index.data_ptr()
             nv.check(lib.pgmp_gc_emit(p, o, stream))
+            if fused and N > 0:
+                wt, bias = feat.pack(dev)
+                fm = feat.feat.detach()
+                gp = nv.GatherConvParams(
+                    features=fm.data_ptr(), feat_stride_b=fm.stride(0), feat_stride_c=fm.stride(1),
+                    feat_stride_y=fm.stride(2), feat_stride_x=fm.stride(3), cin=fm.shape[1], height=fm.shape[2],
+                    width=fm.shape[3], cout=C_, out_height=H, out_width=W, weight_t=wt.data_ptr(), bias=bias.data_ptr(),
+                    joint_det=joint_det.data_ptr(), batch_index=batch_index.data_ptr(), num_nodes=N, x=x.data_ptr())
+                nv.check(lib.pgmp_gc_gather_conv(gp, stream))
             ws.record_stream(torch.cuda.current_stream())
-        if feat is not None and feat.requires_grad and torch.is_grad_enabled():
+        if feat is not None and not fused and feat.requires_grad and torch.is_grad_enabled():
             x = _GatherNodeFeatures.apply(feat, x, batch_index, joint_det)
         # the reference's 15-tuple (ConstructGraph.py:248-249); label slots are None at inference (:243-246)
         return (x, edge_attr, edge_index, None, None, None, None, joint_det, None, None, None, joint_scores,
