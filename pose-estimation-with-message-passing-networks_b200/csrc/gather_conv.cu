@@ -40,14 +40,18 @@ __device__ __forceinline__ void bilinear_tap(int dst, int in_size, int out_size,
   l0 = __fsub_rn(1.f, l1);
 }
 
+// CIN > 0: compile-time channel count (power of two, 16 raw elements per thread prefetched one pass ahead in
+// registers); CIN == 0: any channel count, no prefetch
+template <int CIN>
 __global__ void __launch_bounds__(kGcThreads, 1) gather_conv_kernel(const GatherConvArgs a) {
   extern __shared__ __align__(16) float s_mem[];
-  const int K = 9 * a.cin;
+  const int cin = CIN > 0 ? CIN : a.cin;
+  const int K = 9 * cin;
   float* s_w = s_mem;                                              // [K][cout] when resident
   float* s_p = s_mem + (a.w_in_smem ? (size_t)K * a.cout : 0);     // [K][8] interpolated patches
   float* s_r = s_p + (size_t)K * kGcCand;                          // [8][16][cin] raw 4 x 4 neighbourhoods
-  __shared__ int s_y0[kGcCand], s_x0[kGcCand], s_dy[kGcCand], s_dx[kGcCand], s_b[kGcCand];
-  __shared__ float s_ly[kGcCand][2], s_lx[kGcCand][2];
+  struct Taps { int y0[kGcCand], x0[kGcCand], dy[kGcCand], dx[kGcCand], b[kGcCand]; float ly[kGcCand][2], lx[kGcCand][2]; };
+  __shared__ Taps s_t[2];
   const int tid = threadIdx.x;
   if (a.w_in_smem)
     for (int i = tid; i < K * a.cout; i += kGcThreads) s_w[i] = __ldg(a.wmat + i);
@@ -55,48 +59,74 @@ __global__ void __launch_bounds__(kGcThreads, 1) gather_conv_kernel(const Gather
   const int c = tid & (kGcMaxCout - 1), half = tid >> 7;
   const float bias = c < a.cout ? __ldg(a.bias + c) : 0.f;
   const int64_t groups = (a.n + kGcCand - 1) / kGcCand;
-  for (int64_t grp = blockIdx.x; grp < groups; grp += gridDim.x) {
-    const int64_t n0 = grp * kGcCand;
-    __syncthreads();                                               // the previous pass no longer reads s_p / s_r
+  constexpr int kRaw = CIN > 0 ? kGcCand * 16 * CIN / kGcThreads : 1;   // raw elements per thread and pass
+
+  auto compute_taps = [&](int64_t grp, Taps& t) {
     if (tid < kGcCand) {
-      const int64_t n = n0 + tid;
+      const int64_t n = grp * kGcCand + tid;
       int y0 = 0, y1 = 0, x0 = 0, x1 = 0, b = -1;
       float ly0 = 0.f, ly1 = 0.f, lx0 = 0.f, lx1 = 0.f;
-      if (n < a.n) {
+      if (grp < groups && n < a.n) {
         b = (int)a.batch_index[n];
         bilinear_tap((int)a.joint_det[n * 3 + 1], a.h, a.out_h, y0, y1, ly0, ly1);
         bilinear_tap((int)a.joint_det[n * 3 + 0], a.w, a.out_w, x0, x1, lx0, lx1);
       }
-      s_b[tid] = b; s_y0[tid] = y0; s_x0[tid] = x0; s_dy[tid] = y1 - y0; s_dx[tid] = x1 - x0;
-      s_ly[tid][0] = ly0; s_ly[tid][1] = ly1; s_lx[tid][0] = lx0; s_lx[tid][1] = lx1;
+      t.b[tid] = b; t.y0[tid] = y0; t.x0[tid] = x0; t.dy[tid] = y1 - y0; t.dx[tid] = x1 - x0;
+      t.ly[tid][0] = ly0; t.ly[tid][1] = ly1; t.lx[tid][0] = lx0; t.lx[tid][1] = lx1;
     }
-    __syncthreads();
-    // raw neighbourhoods: rows y0 - 1 .. y0 + 2, columns x0 - 1 .. x0 + 2, zero outside the map (conv padding)
-    for (int i = tid; i < kGcCand * 16 * a.cin; i += kGcThreads) {
-      const int ci = i % a.cin, pos = (i / a.cin) & 15, g = i / (16 * a.cin);
-      const int yy = s_y0[g] - 1 + (pos >> 2), xx = s_x0[g] - 1 + (pos & 3);
-      float v = 0.f;
-      if (s_b[g] >= 0 && (unsigned)yy < (unsigned)a.h && (unsigned)xx < (unsigned)a.w)
-        v = __ldg(a.feat + s_b[g] * a.sb + ci * a.sc + yy * a.sy + xx * a.sx);
-      s_r[i] = v;
+  };
+  // raw neighbourhood element i of a pass: rows y0 - 1 .. y0 + 2, columns x0 - 1 .. x0 + 2, zero outside the map
+  auto raw = [&](const Taps& t, int i) {
+    const int ci = CIN > 0 ? (i & (CIN - 1)) : i % cin;
+    const int q = CIN > 0 ? i / CIN : i / cin;
+    const int pos = q & 15, g = q >> 4;
+    const int yy = t.y0[g] - 1 + (pos >> 2), xx = t.x0[g] - 1 + (pos & 3);
+    float v = 0.f;
+    if (t.b[g] >= 0 && (unsigned)yy < (unsigned)a.h && (unsigned)xx < (unsigned)a.w)
+      v = __ldg(a.feat + t.b[g] * a.sb + ci * a.sc + yy * a.sy + xx * a.sx);
+    return v;
+  };
+
+  float pre[kRaw];
+  compute_taps(blockIdx.x, s_t[0]);
+  __syncthreads();
+  if (CIN > 0) {
+#pragma unroll
+    for (int j = 0; j < kRaw; ++j) pre[j] = raw(s_t[0], tid + j * kGcThreads);
+  }
+  int cur = 0;
+  for (int64_t grp = blockIdx.x; grp < groups; grp += gridDim.x, cur ^= 1) {
+    const int64_t n0 = grp * kGcCand;
+    const Taps& t = s_t[cur];
+    if (CIN > 0) {
+#pragma unroll
+      for (int j = 0; j < kRaw; ++j) s_r[tid + j * kGcThreads] = pre[j];
+    } else {
+      for (int i = tid; i < kGcCand * 16 * cin; i += kGcThreads) s_r[i] = raw(t, i);
     }
+    compute_taps(grp + gridDim.x, s_t[cur ^ 1]);
     __syncthreads();
     // interpolated patches, taps in the order (y0,x0), (y0,x1), (y1,x0), (y1,x1)
     for (int i = tid; i < K * kGcCand; i += kGcThreads) {
       const int g = i & (kGcCand - 1), k = i >> 3;
-      const int ci = k % a.cin, kk = k / a.cin, ky = kk / 3, kx = kk - 3 * ky;
-      const float* __restrict__ r = s_r + (size_t)g * 16 * a.cin + ci;
+      const int ci = CIN > 0 ? (k & (CIN - 1)) : k % cin;
+      const int kk = CIN > 0 ? k / CIN : k / cin, ky = kk / 3, kx = kk - 3 * ky;
+      const float* __restrict__ r = s_r + (size_t)g * 16 * cin + ci;
       float p = 0.f;
 #pragma unroll
       for (int ty = 0; ty < 2; ++ty)
 #pragma unroll
         for (int tx = 0; tx < 2; ++tx) {
-          const int py = (ty ? s_dy[g] : 0) + ky, px = (tx ? s_dx[g] : 0) + kx;
-          p = __fadd_rn(p, __fmul_rn(__fmul_rn(s_ly[g][ty], s_lx[g][tx]), r[(py * 4 + px) * a.cin]));
+          const int py = (ty ? t.dy[g] : 0) + ky, px = (tx ? t.dx[g] : 0) + kx;
+          p = __fadd_rn(p, __fmul_rn(__fmul_rn(t.ly[g][ty], t.lx[g][tx]), r[(py * 4 + px) * cin]));
         }
       s_p[i] = p;
     }
     __syncthreads();
+    if (CIN > 0 && grp + gridDim.x < groups) {       // the next pass's raw elements fly while this pass multiplies
+#pragma unroll
+      for (int j = 0; j < kRaw; ++j) pre[j] = raw(s_t[cur ^ 1], tid + j * kGcThreads);
+    }
     if (c < a.cout) {
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
       const float4* __restrict__ p4 = reinterpret_cast<const float4*>(s_p) + half;
@@ -113,6 +143,7 @@ __global__ void __launch_bounds__(kGcThreads, 1) gather_conv_kernel(const Gather
         if (n < a.n) a.x[n * a.cout + c] = acc[j] + bias;
       }
     }
+    __syncthreads();                                 // s_p / s_r are rewritten by the next pass
   }
 }
 
@@ -140,11 +171,17 @@ extern "C" int pgmp_gc_gather_conv(const pgmp_gather_conv_params* p, pgmp_stream
   const size_t smem = work + (a.w_in_smem ? wbytes : 0);
   if (smem > 200 * 1024) return set_error(PGMP_ERR_INVALID, "cin too large for the patch buffers");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  PGMP_CUDA(cudaFuncSetAttribute(gather_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t groups = (p->num_nodes + kGcCand - 1) / kGcCand;
-  PGMP_LAUNCH(gather_conv_kernel, (unsigned)(groups < sms ? groups : sms), kGcThreads, smem, st, a);
+  const unsigned grid = (unsigned)(groups < sms ? groups : sms);
+  if (p->cin == 32) {            // the w32 backbone (default_config.py:48)
+    PGMP_CUDA(cudaFuncSetAttribute(gather_conv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PGMP_LAUNCH(gather_conv_kernel<32>, grid, kGcThreads, smem, st, a);
+  } else {
+    PGMP_CUDA(cudaFuncSetAttribute(gather_conv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PGMP_LAUNCH(gather_conv_kernel<0>, grid, kGcThreads, smem, st, a);
+  }
   return PGMP_OK;
 }
