@@ -97,8 +97,10 @@ class NaiveGraphConstructor:
         self.tagmaps = tagmaps if _host_resident(tagmaps, need_contiguous=True) else (
             tagmaps.to(self.device) if tagmaps is not None else None)
         if isinstance(features, ConvUpsampleFeatures):
-            if not (_host_resident(features.feat) or features.feat.device.type == "cuda"):
-                features.feat = features.feat.to(self.device)
+            # every candidate reads a 4 x 4 x Cin neighbourhood of the (small) backbone map: a host-resident map is
+            # copied, reading it in place would cost more PCIe transactions than the copy
+            if features.feat.device.type != "cuda":
+                features.feat = features.feat.to(self.device, non_blocking=True)
             self.features = features
         else:
             self.features = features if _host_resident(features) else (
