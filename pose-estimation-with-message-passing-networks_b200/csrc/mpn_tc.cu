@@ -87,15 +87,14 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
   const uint32_t add_a = smem_u32(wgb) + kWgAdd;
   const uint32_t wm_hi = smem_u32(wgb) + kWgWm, wm_lo = wm_hi + kWTile;
   int* s_dst = reinterpret_cast<int*>(wgb + kWgMisc);
-  int* s_src = s_dst + kTile;
+  int* s_src = s_dst + kTile;                                 // (only its storage is used: s_prow)
   float* s_att = reinterpret_cast<float*>(s_src + kTile);
   float* s_wa = s_att + kTile;
   uint64_t* bar = reinterpret_cast<uint64_t*>(s_wa + kD);   // MMA completions
   uint64_t* g_bar = bar + 1;                                  // bulk load of the edge-feature image
   uint64_t* c_bar = bar + 2;                                  // bulk load of the C image
-  int* s_split = reinterpret_cast<int*>(bar + 3);             // (unused pad)
-  int* s_prow = s_src;                                        // part row of every head row (s_src is dead by then)
-  float* s_wfirst = reinterpret_cast<float*>(s_split + 2);    // per warp: max logit of its first / last run segment,
+  int* s_prow = s_src;                                        // part row stored by the last row of every run, else -1
+  float* s_wfirst = reinterpret_cast<float*>(bar + 4);        // per warp: max logit of its first / last run segment,
   float* s_wlast = s_wfirst + 4;                              // flags: bit 0 = lane 0 continues the previous warp's run,
   int* s_wflag = reinterpret_cast<int*>(s_wlast + 4);         //        bit 1 = the whole warp is one segment
   int* s_seg = s_wflag + 4;                                   // [8] first row of the k-th row segment of the run reduction
