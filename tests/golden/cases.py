@@ -64,3 +64,28 @@ def mpn_config_for(pgmp_config, maker, overrides):
     if nj != 17:                                    # CLASS head width follows the dataset's joint count
         cfg.CLASS.OUTPUT_SIZES = [64, 32, nj]
     return cfg
+
+
+# ---- training-mode cases (round-2 groundwork): name -> (GC case, MPN config maker, overrides, weight seed)
+TRAIN_CASES = {
+    # class_agnostic_end2end/model_57_1_0.yaml shape: agnostic MPLayer, max aggregation, skip
+    "agnostic_max": ("knn_small", "agnostic_mpn_config", dict(STEPS=3, AUX_LOSS_STEPS=1), 41),
+    "flagship": ("knn_small", "flagship_mpn_config", dict(STEPS=2), 42),
+}
+
+
+def train_loss_weights(shapes, seed):
+    """Fixed random coefficients of the scalar test loss L = sum_k <c_k, pred_k>."""
+    import numpy as np
+    rng = np.random.default_rng(1000 + seed)
+    return [rng.standard_normal(s).astype(np.float32) for s in shapes]
+
+
+def sample_indices(n, name):
+    """64 fixed positions of a flattened parameter gradient (all of it when smaller)."""
+    import hashlib
+    import numpy as np
+    if n <= 64:
+        return np.arange(n)
+    rng = np.random.default_rng(int.from_bytes(hashlib.sha256(name.encode()).digest()[:4], "little"))
+    return np.sort(rng.choice(n, 64, replace=False))
