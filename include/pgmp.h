@@ -219,6 +219,8 @@ typedef struct pgmp_mpn_params {
 /* Self-test of the tcgen05 building blocks: D[128,64] = A[128,64] . W[64,64]^T (fp32 device pointers) through
  * the same bf16x3 split / SWIZZLE_128B tile writers / TMEM epilogue the message-passing kernels use. */
 int pgmp_selftest_umma(const float* a, const float* w, float* d, pgmp_stream_t stream);
+/* the same product with the A operand in tensor memory (tcgen05.st + the TS form of tcgen05.mma) */
+int pgmp_selftest_umma_ts(const float* a, const float* w, float* d, pgmp_stream_t stream);
 
 uint64_t pgmp_mpn_workspace_bytes(const pgmp_mpn_params* p);
 int pgmp_mpn_forward(const pgmp_mpn_params* p, pgmp_stream_t stream);

@@ -108,6 +108,7 @@ SYMBOLS = {
     "pgmp_gc_emit": (C.c_int, [C.POINTER(GcParams), C.POINTER(GcOutputs), C.c_void_p]),
     "pgmp_gc_gather_conv": (C.c_int, [C.POINTER(GatherConvParams), C.c_void_p]),
     "pgmp_selftest_umma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pgmp_selftest_umma_ts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pgmp_mpn_workspace_bytes": (C.c_uint64, [C.POINTER(MpnParams)]),
     "pgmp_mpn_forward": (C.c_int, [C.POINTER(MpnParams), C.c_void_p]),
     "pgmp_group_workspace_bytes": (C.c_uint64, [C.POINTER(GroupParams)]),

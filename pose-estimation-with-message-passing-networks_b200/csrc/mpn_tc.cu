@@ -530,6 +530,63 @@ __global__ void __launch_bounds__(kTile) selftest_umma_kernel(const float* __res
   if (warp == 0) tmem_dealloc<kTmemCols>(tmem);
 }
 
+// D = A . W^T with the A operand in tensor memory (pgmp_selftest_umma_ts): the threads split their row of A into
+// bf16 hi / lo pairs and store them with tcgen05.st (hi in columns [64, 96), lo in [96, 128)); B stays in shared memory
+__global__ void __launch_bounds__(kTile) selftest_umma_ts_kernel(const float* __restrict__ A, const float* __restrict__ W,
+                                                                  float* __restrict__ D) {
+  extern __shared__ uint8_t smem_raw[];
+  const TcSmem s = carve_smem(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tmem_alloc<128>(s.tmem);
+  if (tid == 0) {
+    mbar_init(s.bar, 1);
+    fence_barrier_init();
+  }
+  const float4* __restrict__ w4 = reinterpret_cast<const float4*>(W);
+  for (int k = 0; k < 8; ++k) {
+    const int idx = tid + k * kTile;
+    store_split4(s.w1_hi, s.w1_lo, idx >> 4, idx & 15, w4[idx]);
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *s.tmem;
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  uint32_t hi[32], lo[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) split2(A[tid * kD + 2 * k], A[tid * kD + 2 * k + 1], hi[k], lo[k]);
+  tmem_st16(tmem + lane_base + 64, hi);
+  tmem_st16(tmem + lane_base + 80, hi + 16);
+  tmem_st16(tmem + lane_base + 96, lo);
+  tmem_st16(tmem + lane_base + 112, lo + 16);
+  tmem_st_wait();
+  fence_before_sync();
+  fence_async_smem();
+  __syncthreads();
+  if (tid < 32 && elect_one()) {
+    fence_after_sync();
+    constexpr uint32_t idesc = idesc_bf16(128, kD);
+    const uint64_t wh = smem_desc_sw128(smem_u32(s.w1_hi)), wl = smem_desc_sw128(smem_u32(s.w1_lo));
+    uint32_t acc = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {        // K = 16 per instruction = 8 columns of the A operand
+      mma_bf16_ts(tmem, tmem + 64 + 8 * k, wh + 2 * k, idesc, acc);
+      acc = 1;
+      mma_bf16_ts(tmem, tmem + 64 + 8 * k, wl + 2 * k, idesc, 1u);
+      mma_bf16_ts(tmem, tmem + 96 + 8 * k, wh + 2 * k, idesc, 1u);
+    }
+    mma_commit(s.bar);
+  }
+  mbar_wait(s.bar, 0);
+  fence_after_sync();
+  float d[kD];
+  tmem_ld64(tmem, 0, d);
+  for (int o = 0; o < kD; ++o) D[tid * kD + o] = d[o];
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<128>(tmem);
+}
+
 }  // namespace
 
 int mpn_forward_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t st) {
@@ -603,5 +660,14 @@ extern "C" int pgmp_selftest_umma(const float* a, const float* w, float* d, pgmp
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   PGMP_CUDA(cudaFuncSetAttribute(selftest_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
   PGMP_LAUNCH(selftest_umma_kernel, 1, kTile, kTcSmemBytes, st, a, w, d);
+  return PGMP_OK;
+}
+
+extern "C" int pgmp_selftest_umma_ts(const float* a, const float* w, float* d, pgmp_stream_t stream) {
+  using namespace pgmp;
+  if (!a || !w || !d) return set_error(PGMP_ERR_INVALID, "null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PGMP_CUDA(cudaFuncSetAttribute(selftest_umma_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+  PGMP_LAUNCH(selftest_umma_ts_kernel, 1, kTile, kTcSmemBytes, st, a, w, d);
   return PGMP_OK;
 }
