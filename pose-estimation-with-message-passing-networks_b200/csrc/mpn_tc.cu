@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = *tmem_slot + (uint32_t)(wg * 128);   // this warpgroup's 128 columns
+  const uint32_t tmem_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // ... at this warp's lanes
   const int bar_id = 1 + wg;
   uint32_t phase = 0, ld_phase = 0;
   int cur_tm = -1, cur_col = -1;
@@ -229,13 +230,14 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
       d[4 * q + 2] = fmaxf(d[4 * q + 2] + v.z, 0.f);
       d[4 * q + 3] = fmaxf(d[4 * q + 3] + v.w, 0.f);
     }
-    store_split_row_a(a_hi, a_lo, wt, d);
+    // hidden goes to tensor memory (columns 64..127 of this warpgroup, free until the head product of a reported
+    // step): the second product takes its A operand from there, no swizzled shared-memory stores or operand reads
+    store_split_row_tmem(tmem_row + 64, tmem_row + 96, d);
     fence_before_sync();
-    fence_async_smem();
     named_bar_sync(bar_id, kWgThreads);
     if (wt < 32 && elect_one()) {
       fence_after_sync();
-      issue_gemm_x3<kD>(tmem, a_hi, a_lo, 0, w2_hi, w2_lo, 0, 1, false);
+      issue_gemm_x3_ts<kD>(tmem, tmem + 64, tmem + 96, w2_hi, w2_lo, false);
       mma_commit(bar);
     }
     // ---- R[type][dst]: this thread's own row, requested now, consumed by the third epilogue

@@ -174,6 +174,23 @@ __device__ __forceinline__ void issue_gemm_x3(uint32_t tmem_d, uint32_t a_hi, ui
   }
 }
 
+// The same product with the A operand in tensor memory (TS form): a_hi / a_lo are TMEM addresses of [128 x 64] bf16
+// operands (32 columns each, element k of a row in the 16-bit half k & 1 of column k / 2).  K = 64 only.
+template <int N>
+__device__ __forceinline__ void issue_gemm_x3_ts(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t w_hi, uint32_t w_lo,
+                                                 bool accumulate) {
+  constexpr uint32_t idesc = idesc_bf16(128, N);
+  uint32_t acc = accumulate ? 1u : 0u;
+  const uint64_t wh = smem_desc_sw128(w_hi), wl = smem_desc_sw128(w_lo);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {   // UMMA_K = 16 bf16 = 8 TMEM columns of A = 2 descriptor units of W
+    mma_bf16_ts(tmem_d, a_hi + 8 * k, wh + 2 * k, idesc, acc);
+    acc = 1u;
+    mma_bf16_ts(tmem_d, a_hi + 8 * k, wl + 2 * k, idesc, 1u);
+    mma_bf16_ts(tmem_d, a_lo + 8 * k, wh + 2 * k, idesc, 1u);
+  }
+}
+
 // ---- explicit shared-state-space accessors (32-bit shared addresses; avoids generic ST/LD) ----------
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -265,6 +282,19 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
   hi = *reinterpret_cast<const uint32_t*>(&h);
   const __nv_bfloat162 l = __floats2bfloat162_rn(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
   lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// this thread's 64-wide row as a TS-form A operand: hi pairs -> 32 columns at t_hi, lo pairs -> 32 columns at t_lo
+// (t_* already carry the lane base of the warp)
+__device__ __forceinline__ void store_split_row_tmem(uint32_t t_hi, uint32_t t_lo, const float (&v)[64]) {
+#pragma unroll
+  for (int part = 0; part < 2; ++part) {
+    uint32_t h[16], l[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) split2(v[32 * part + 2 * i], v[32 * part + 2 * i + 1], h[i], l[i]);
+    tmem_st16(t_hi + 16 * part, h);
+    tmem_st16(t_lo + 16 * part, l);
+  }
+  tmem_st_wait();
 }
 // address-based variants (shared-space stores)
 __device__ __forceinline__ void store_split4_a(uint32_t hi_tile, uint32_t lo_tile, int row, int col4, float4 v) {
