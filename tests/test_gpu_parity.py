@@ -216,6 +216,20 @@ def test_umma_selftest_gemm():
     assert_close(D.cpu().numpy(), want, 1e-4, "bf16x3 GEMM")     # ~2^-16 per product term
 
 
+def test_umma_selftest_gemm_a_operand_in_tensor_memory():
+    """The TS form of tcgen05.mma: A written to tensor memory with tcgen05.st (row = lane, element k in half k & 1 of
+    column k / 2), B in shared memory."""
+    import pgmp_b200._native as nv
+    g = torch.Generator().manual_seed(4)
+    A = torch.randn(128, 64, generator=g)
+    W = torch.randn(64, 64, generator=g)
+    D = torch.full((128, 64), float("nan"), device=DEV)
+    A_d, W_d = A.to(DEV), W.to(DEV)
+    nv.check(nv.lib().pgmp_selftest_umma_ts(A_d.data_ptr(), W_d.data_ptr(), D.data_ptr(), nv.current_stream()))
+    torch.cuda.synchronize()
+    assert_close(D.cpu().numpy(), (A.double() @ W.double().t()).numpy(), 1e-4, "bf16x3 GEMM, TS form")
+
+
 @pytest.mark.parametrize("name", list(MPN_CASES))
 def test_mpn_tensor_core_within_logit_tolerance(name):
     """north_star: logits within 1e-3 relative error with fp32-accumulated bf16 tensor-core math."""
