@@ -233,10 +233,15 @@ int pgmp_mpn_forward(const pgmp_mpn_params* p, pgmp_stream_t stream);
  * GAEC solver itself is the reference's missing native andres_graph_wrapper) and the connected
  * component labelling + per-type winner selection of graph_cluster_to_persons (:672-743).
  * ---------------------------------------------------------------------------------------------- */
+#define PGMP_CC_GAEC 0
+#define PGMP_CC_THRESHOLD 1
+
 typedef struct pgmp_group_params {
   int32_t batch, num_joints;
   int64_t num_nodes, num_edges;
   float node_threshold;                /* MPN.NODE_THRESHOLD */
+  int32_t cc_method;                   /* PGMP_CC_GAEC (greedy additive edge contraction) or PGMP_CC_THRESHOLD (Utils.py:508-509) */
+  float edge_threshold;                /* PGMP_CC_THRESHOLD: edges with probability > this join their ends (0.8 in the reference) */
   const int64_t* node_offsets;         /* device [B+1] prefix sums of nodes per image */
   const int64_t* edge_offsets;         /* device [B+1] prefix sums of edges per image (edges grouped by image) */
   const int64_t* edge_index;           /* device [2,E] global ids */

@@ -140,8 +140,26 @@ def graph_cluster_to_persons(joint_det, node_prob, person_labels, class_prob, nu
     return np.array(persons), mutant
 
 
-def pred_to_person(joint_det, node_logits, edge_index, edge_logits, class_logits, node_threshold, num_joints):
-    """valid.py:109-111 + Utils.py:1448-1457 + :499-514 for ``CC_METHOD == "GAEC"``.
+def threshold_clusters(edge_index, edge_prob, n, edge_threshold=0.8):
+    """``CC_METHOD == "threshold"`` (Utils.py:508-509): the kept edges with probability > 0.8 are the solution; their
+    connected components are the persons.  Returns each node's representative = smallest node of its component."""
+    rep = np.arange(n, dtype=np.int64)
+
+    def find(i):
+        while rep[i] != i:
+            rep[i] = rep[rep[i]]
+            i = rep[i]
+        return i
+    for s, d in edge_index[:, edge_prob > np.float32(edge_threshold)].T.tolist():
+        a, b = find(s), find(d)
+        if a != b:
+            rep[max(a, b)] = min(a, b)
+    return np.array([find(i) for i in range(n)], dtype=np.int64)
+
+
+def pred_to_person(joint_det, node_logits, edge_index, edge_logits, class_logits, node_threshold, num_joints,
+                   cc_method="GAEC"):
+    """valid.py:109-111 + Utils.py:1448-1457 + :499-514 for ``CC_METHOD in ("GAEC", "threshold")``.
 
     Returns (persons, mutants, person_labels) or None when the reference's
     ``pred_to_ann`` returns None before grouping (no edge survives)."""
@@ -152,8 +170,11 @@ def pred_to_person(joint_det, node_logits, edge_index, edge_logits, class_logits
     if ei.shape[1] == 0:
         return None                                               # Utils.py:1452,1457
     n = len(joint_det)
-    a, b, w = multicut_weights(ei, pe)
-    rep = gaec(a, b, w, n)
+    if cc_method == "threshold":
+        rep = threshold_clusters(ei, pe, n)
+    else:
+        a, b, w = multicut_weights(ei, pe)
+        rep = gaec(a, b, w, n)
     labels = connected_component_labels(rep)
     persons, mutant = graph_cluster_to_persons(np.asarray(joint_det), p_node, labels, p_cls, num_joints)
     return persons, mutant, labels

@@ -25,8 +25,8 @@ def group_persons(joint_det, node_logits, edge_index, edge_logits, class_logits,
     softmax of valid.py:109-111 are applied on the device); ``edge_index`` holds global node ids with the edges of
     an image contiguous, as ``construct_graph`` returns them.
     """
-    if cc_method != "GAEC":
-        raise NotImplementedError("CC_METHOD=%r (GAEC, the reference default, is in scope)" % (cc_method,))
+    if cc_method not in nv.CC_METHODS:
+        raise NotImplementedError("CC_METHOD=%r (GAEC, the reference default, and threshold are in scope)" % (cc_method,))
     nv.require_cuda(joint_det, "joint_det", torch.int64)
     nv.require_cuda(node_logits, "node_logits", torch.float32)
     nv.require_cuda(edge_index, "edge_index", torch.int64)
@@ -58,6 +58,7 @@ def group_persons(joint_det, node_logits, edge_index, edge_logits, class_logits,
     ei = edge_index.contiguous()
     cl = class_logits.detach().contiguous() if class_logits is not None else None
     p = nv.GroupParams(batch=B, num_joints=J, num_nodes=N, num_edges=E, node_threshold=float(node_threshold),
+                       cc_method=nv.CC_METHODS[cc_method], edge_threshold=0.8,
                        node_offsets=node_off.data_ptr(), edge_offsets=edge_off.data_ptr(), edge_index=ei.data_ptr(),
                        joint_det=jd.data_ptr(), node_logits=nl.data_ptr(), edge_logits=el.data_ptr(),
                        class_logits=cl.data_ptr() if cl is not None else None, person_labels=labels.data_ptr(),

@@ -85,9 +85,13 @@ class MpnParams(C.Structure):
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64)]
 
 
+CC_METHODS = {"GAEC": 0, "threshold": 1}
+
+
 class GroupParams(C.Structure):
     _fields_ = [("batch", C.c_int32), ("num_joints", C.c_int32), ("num_nodes", C.c_int64), ("num_edges", C.c_int64),
-                ("node_threshold", C.c_float), ("node_offsets", C.c_void_p), ("edge_offsets", C.c_void_p),
+                ("node_threshold", C.c_float), ("cc_method", C.c_int32), ("edge_threshold", C.c_float),
+                ("node_offsets", C.c_void_p), ("edge_offsets", C.c_void_p),
                 ("edge_index", C.c_void_p), ("joint_det", C.c_void_p), ("node_logits", C.c_void_p),
                 ("edge_logits", C.c_void_p), ("class_logits", C.c_void_p), ("person_labels", C.c_void_p),
                 ("num_components", C.c_void_p), ("num_kept_edges", C.c_void_p), ("max_persons", C.c_int32),

@@ -157,8 +157,40 @@ __global__ void __launch_bounds__(kThreads) group_kernel(const pgmp_group_params
   __syncthreads();
   for (int r = warp; r < n; r += kThreads / 32) rescan_row(W, flags, n, r, best_val, best_col);
   __syncthreads();
+  // ---- CC_METHOD "threshold" (Utils.py:508-509): the kept edges with probability above the edge threshold are the
+  //      solution; min-label propagation over the image's edge list + pointer jumping gives every node the smallest
+  //      node of its component as representative (the invariant the greedy contraction below also keeps)
+  if (p.cc_method == PGMP_CC_THRESHOLD) {
+    __shared__ int s_changed;
+    for (;;) {
+      __syncthreads();
+      if (tid == 0) s_changed = 0;
+      __syncthreads();
+      for (int64_t e = e0 + tid; e < e1; e += kThreads) {
+        const int s = (int)(p.edge_index[e] - n0), d = (int)(p.edge_index[p.num_edges + e] - n0);
+        if (s < 0 || s >= n || d < 0 || d >= n) continue;
+        if (!((flags[s] & 4) && (flags[d] & 4))) continue;
+        if (!(sigmoidf_(p.edge_logits[e]) > p.edge_threshold)) continue;
+        const int ls = rep[s], ld = rep[d];
+        if (ls != ld) {
+          const int m = min(ls, ld);
+          atomicMin(&rep[s], m);
+          atomicMin(&rep[d], m);
+          s_changed = 1;
+        }
+      }
+      __syncthreads();
+      for (int i = tid; i < n; i += kThreads) {       // pointer jumping
+        int r = rep[i];
+        while (rep[r] != r) r = rep[r];
+        rep[i] = r;
+      }
+      __syncthreads();
+      if (!s_changed) break;
+    }
+  }
   // ---- GAEC
-  for (int it = 0; it < n; ++it) {
+  for (int it = 0; it < n && p.cc_method == PGMP_CC_GAEC; ++it) {
     // global best over rows: larger value, then smaller row (rows cache their smallest best column)
     double bv = -CUDART_INF;
     int br = 0x7fffffff;

@@ -285,17 +285,17 @@ def _oracle_graph_for(gc_name):
     return oracle.gc.construct_graph(data["scoremaps"], data["tagmaps"], data["features"], gcfg, nj, masks=data["masks"]), nj
 
 
-def _check_grouping(g, nj, logits, th, gold=None):
+def _check_grouping(g, nj, logits, th, gold=None, cc_method="GAEC"):
     from pgmp_b200.Utils import group_persons
     res = group_persons(torch.from_numpy(g["joint_det"]).to(DEV), torch.from_numpy(logits["node_logits"]).to(DEV),
                         torch.from_numpy(g["edge_index"]).to(DEV), torch.from_numpy(logits["edge_logits"]).to(DEV),
                         torch.from_numpy(logits["class_logits"]).to(DEV), torch.from_numpy(g["batch_index"]).to(DEV),
-                        nj, node_threshold=th)
+                        nj, node_threshold=th, cc_method=cc_method)
     assert len(res) == len(np.unique(g["batch_index"]))
     for b, got in enumerate(res):
         sub = synthetic.image_subgraph(g, logits, b)
         want = oracle.grouping.pred_to_person(sub["joint_det"], sub["node_logits"], sub["edge_index"],
-                                              sub["edge_logits"], sub["class_logits"], th, nj)
+                                              sub["edge_logits"], sub["class_logits"], th, nj, cc_method=cc_method)
         if want is None:
             assert got is None
             continue
@@ -309,6 +309,16 @@ def _check_grouping(g, nj, logits, th, gold=None):
         if gold is not None:
             assert np.array_equal(labels.cpu().numpy(), gold[f"labels_{b}"])
             assert np.array_equal(persons[:, :, :2], gold[f"persons_{b}"][:, :, :2])
+
+
+@pytest.mark.parametrize("name,gc_name,seed", [("group_threshold_knn_small", "knn_small", 0),
+                                               ("group_threshold_crowdpose", "crowdpose", 2)])
+def test_grouping_threshold_method_matches_reference(name, gc_name, seed):
+    """CC_METHOD = "threshold" (Utils.py:508-509): fixtures come from the reference's own code (no stand-in)."""
+    g, nj = _oracle_graph_for(gc_name)
+    logits = synthetic.synth_group_logits(g["joint_det"], g["batch_index"], g["edge_index"], num_joints=nj, seed=seed)
+    _check_grouping(g, nj, logits, 0.1, gold=golden(name), cc_method="threshold")
+    _check_grouping(g, nj, dict(logits, edge_logits=logits["edge_logits"] * 0.3), 0.1, cc_method="threshold")   # few joins
 
 
 @pytest.mark.parametrize("name,gc_name,seed", [("group_knn_small", "knn_small", 0), ("group_fully_small", "fully_small", 1),
