@@ -174,6 +174,7 @@ typedef struct pgmp_mpn_params {
   int32_t aggr;                        /* PGMP_AGGR_* */
   int32_t attn;                        /* PGMP_ATTN_* */
   int32_t has_update_mlp;              /* per_type: always 1; agnostic: USE_NODE_UPDATE_MLP */
+  int32_t update_hier;                 /* 1: UPDATE_TYPE hierarch_mlp (layers.py:89-128): `hier` replaces wu / bu; num_types 17 or 14 */
   int32_t num_classes;                 /* width of the classification head */
   int32_t precision;                   /* PGMP_PRECISION_* */
 
@@ -193,6 +194,7 @@ typedef struct pgmp_mpn_params {
   const float* wa;                     /* [dim][attn_cols] attn_net.0 (attn_cols = 1 or 17) or NULL */
   const float* ba;                     /* [attn_cols] */
   const float* wu;                     /* [num_types*dim][dim] update_mlp.0 or NULL */
+  const float* hier;                   /* hierarch_mlp: 7 first-layer, 6 second-layer and the final Linear as [out][in] weight + bias, back to back */
   const float* bu;
   /* PGMP_PRECISION_TC only: the per-edge weight matrices in Linear.weight layout [out][in] (K contiguous),
    * split as bf16 hi = bf16(W), lo = bf16(W - hi); device uint16 (bf16 bit patterns). */

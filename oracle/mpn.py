@@ -136,7 +136,7 @@ def mp_layer(sd, p, x, e, edge_index, aggr, use_node_update_mlp):
     return out, e_new
 
 
-def type_aware_layer(sd, p, x, e, edge_index, node_types, aggr, aggr_sub, num_types):
+def type_aware_layer(sd, p, x, e, edge_index, node_types, aggr, aggr_sub, num_types, update_type="mlp"):
     """``TypeAwareMPNLayer.forward`` (agnostic edge MLP, ``update_type == "mlp"``), layers.py:207-258."""
     src, dst = edge_index
     n = x.shape[0]
@@ -162,8 +162,23 @@ def type_aware_layer(sd, p, x, e, edge_index, node_types, aggr, aggr_sub, num_ty
             upd[:, t] = scatter(m[sel] * a[:, None], dst[sel], n, "add")
     else:
         raise NotImplementedError(aggr_sub)
+    if update_type == "hierarch_mlp":
+        return hierarch_update_mlp(sd, p + ".update_mlp", upd, num_types), e_new
     out = relu(linear(sd, p + ".update_mlp.0", upd.reshape(n, -1)))   # layers.py:253-258
     return out, e_new
+
+
+def hierarch_update_mlp(sd, p, upd, num_joints):
+    """``HierarchUpdateMlp.forward`` (layers.py:109-128): body-part tree over the per-type aggregates [N, T, D]."""
+    n = upd.shape[0]
+    if num_joints == 17:                                             # layers.py:114-116
+        order_1 = [(0, 1, 2, 3, 4), (5, 6), (7, 9), (8, 10), (11, 12), (13, 15), (14, 16)]
+    else:                                                            # layers.py:117-119
+        order_1 = [(0, 1), (2, 3), (4, 6), (5, 7), (8, 9), (10, 12), (11, 13)]
+    order_2 = [(0, 1), (1, 2), (1, 3), (1, 4), (4, 5), (4, 6)]
+    out_1 = np.stack([relu(linear(sd, f"{p}.first_layer.{i}", upd[:, list(t)].reshape(n, -1))) for i, t in enumerate(order_1)], 1)
+    out_2 = np.stack([relu(linear(sd, f"{p}.second_layer.{i}", out_1[:, list(t)].reshape(n, -1))) for i, t in enumerate(order_2)], 1)
+    return relu(linear(sd, p + ".final", out_2.reshape(n, -1)))
 
 
 # ---------------------------------------------------------------- the model
@@ -196,7 +211,7 @@ def node_classification_mpn_forward(sd, cfg, x, edge_attr, edge_index, node_type
             h, g = mp_layer(sd, "mpn_node_cls", h, g, edge_index, cfg.AGGR, cfg.USE_NODE_UPDATE_MLP)
         else:
             h, g = type_aware_layer(sd, "mpn_node_cls", h, g, edge_index, node_types, cfg.AGGR,
-                                    cfg.AGGR_SUB, num_types)
+                                    cfg.AGGR_SUB, num_types, getattr(cfg, "UPDATE_TYPE", "mlp"))
         if i >= cfg.STEPS - cfg.AUX_LOSS_STEPS - 1:               # :81-84
             pn, pc = heads_node(h)
             preds_node.append(pn)

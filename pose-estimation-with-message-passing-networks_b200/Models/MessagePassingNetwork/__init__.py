@@ -167,7 +167,13 @@ class NodeClassificationMPNSimple(nn.Module):
         if attn_net is not None:
             off["wa"] = pk.add(attn_net[0].weight.detach().float().t())
             off["ba"] = pk.add(attn_net[0].bias)
-        if layer.update_mlp is not None:
+        hier = per_type and getattr(layer, "update_type", "mlp") == "hierarch_mlp"
+        if hier:      # layers.py:89-128: [out][in] weights and biases back to back: 7 first, 6 second, final
+            um = layer.update_mlp
+            off["hier"] = pk.add(torch.cat([t.detach().float().reshape(-1) for lin in
+                                            (list(um.first_layer) + list(um.second_layer) + [um.final])
+                                            for t in (lin.weight, lin.bias)]))
+        elif layer.update_mlp is not None:
             off["wu"] = pk.add(layer.update_mlp[0].weight.detach().float().t())
             off["bu"] = pk.add(layer.update_mlp[0].bias)
         flat = pk.finish(device)
@@ -209,10 +215,10 @@ class NodeClassificationMPNSimple(nn.Module):
         if ([tuple(w_.shape) for w_ in nh_w[:2]] == [(64, 64), (32, 64)]
                 and [tuple(w_.shape) for w_ in ch_w[:2]] == [(64, 64), (32, 64)]):
             tc["tc_wheads"] = torch.cat([split(w_).reshape(-1) for w_ in (nh_w[0], ch_w[0], nh_w[1], ch_w[1])]).contiguous()
-        if layer.update_mlp is not None:
+        if layer.update_mlp is not None and not hier:
             wu = layer.update_mlp[0].weight.detach().float()
             tc["tc_wu"] = torch.stack([split(wu[:, t * 64:(t + 1) * 64]) for t in range(wu.shape[1] // 64)]).contiguous()
-        packed = dict(flat=flat, tc=tc, spec=spec, off=off, per_type=per_type, skip=skip,
+        packed = dict(flat=flat, tc=tc, spec=spec, off=off, per_type=per_type, skip=skip, hier=hier,
                       num_types=layer.num_types if per_type else 1,
                       attn=nv.ATTN[layer.aggr_sub] if per_type else 0,
                       num_classes=self.classification[-1].out_features)
@@ -262,7 +268,8 @@ class NodeClassificationMPNSimple(nn.Module):
                              num_types=pk["num_types"], num_type_mlps=17 if pk["per_type"] else 1,
                              skip=int(pk["skip"]), steps=self.edge_steps, aux_loss_steps=self.aux_loss_steps,
                              aggr=nv.AGGR[self.aggr], attn=pk["attn"],
-                             has_update_mlp=int(self.mpn_node_cls.update_mlp is not None), num_classes=J,
+                             has_update_mlp=int(self.mpn_node_cls.update_mlp is not None), update_hier=int(pk["hier"]),
+                             num_classes=J,
                              precision=nv.PRECISION[self.precision])
             for field, name in (("node_emb", "node_embedding"), ("edge_emb", "edge_embedding"),
                                 ("edge_head", "edge_classification"), ("node_head", "node_classification"),

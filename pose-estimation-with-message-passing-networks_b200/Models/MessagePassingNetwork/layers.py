@@ -63,6 +63,21 @@ class TypeAwareNodeUpdate(nn.Module):
         self.output_dim = output_dim
 
 
+class HierarchUpdateMlp(nn.Module):
+    """Body-part tree over the per-type aggregates (layers.py:89-128): parameter container, reference names."""
+
+    def __init__(self, node_dim, num_joints):
+        super().__init__()
+        if num_joints not in (17, 14):
+            raise NotImplementedError("hierarch_mlp is defined for 17 or 14 joint types (layers.py:96)")
+        first_in = 5 if num_joints == 17 else 2
+        self.node_dim, self.num_joints = node_dim, num_joints
+        self.first_layer = nn.ModuleList([nn.Linear(node_dim * first_in, node_dim // 2)] +
+                                         [nn.Linear(node_dim * 2, node_dim // 2) for _ in range(6)])
+        self.second_layer = nn.ModuleList([nn.Linear(2 * node_dim // 2, node_dim // 2) for _ in range(6)])
+        self.final = nn.Linear(6 * node_dim // 2, node_dim)
+
+
 class TypeAwareMPNLayer(nn.Module):
     """Per-type layer (layers.py:157-258)."""
 
@@ -71,8 +86,8 @@ class TypeAwareMPNLayer(nn.Module):
         super().__init__()
         if edge_mlp != "agnostic":
             raise NotImplementedError("EDGE_MLP=%r is out of scope" % (edge_mlp,))
-        if update_type != "mlp":
-            raise NotImplementedError("UPDATE_TYPE=%r is out of scope (hierarch_* are research ablations)" % (update_type,))
+        if update_type not in ("mlp", "hierarch_mlp"):
+            raise NotImplementedError("UPDATE_TYPE=%r is out of scope (hierarch_cnn is a research ablation)" % (update_type,))
         if aggr_sub not in ("None", "node_edge_attn", "node_edge_attn_per_type"):
             # the reference returns None from aggregate() for anything else (layers.py:228-231)
             raise NotImplementedError("AGGR_SUB=%r" % (aggr_sub,))
@@ -85,7 +100,10 @@ class TypeAwareMPNLayer(nn.Module):
         f = 2 if skip else 1
         self.mlp_edge = _edge_mlp(node_dim, edge_dim, edge_hidden, skip)
         self.mlp_node = TypeAwareNodeUpdate(node_dim * f + edge_dim, node_dim)
-        self.update_mlp = nn.Sequential(nn.Linear(node_dim * num_types, node_dim), nn.ReLU(inplace=True))
+        if update_type == "mlp":
+            self.update_mlp = nn.Sequential(nn.Linear(node_dim * num_types, node_dim), nn.ReLU(inplace=True))
+        else:
+            self.update_mlp = HierarchUpdateMlp(node_dim, num_types)                 # layers.py:189-190
         if aggr_sub == "node_edge_attn":
             self.attn_net = nn.Sequential(nn.Linear(edge_dim, 1))
         elif aggr_sub == "node_edge_attn_per_type":

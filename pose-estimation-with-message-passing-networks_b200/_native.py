@@ -71,13 +71,13 @@ class MpnParams(C.Structure):
                 ("node_types", C.c_void_p),
                 ("dim", C.c_int32), ("per_type", C.c_int32), ("num_types", C.c_int32), ("num_type_mlps", C.c_int32),
                 ("skip", C.c_int32), ("steps", C.c_int32), ("aux_loss_steps", C.c_int32), ("aggr", C.c_int32),
-                ("attn", C.c_int32), ("has_update_mlp", C.c_int32), ("num_classes", C.c_int32),
+                ("attn", C.c_int32), ("has_update_mlp", C.c_int32), ("update_hier", C.c_int32), ("num_classes", C.c_int32),
                 ("precision", C.c_int32),
                 ("node_emb", Mlp), ("edge_emb", Mlp), ("edge_head", Mlp), ("node_head", Mlp), ("class_head", Mlp),
                 ("w1_dst", C.c_void_p), ("w1_src", C.c_void_p), ("w1_e0", C.c_void_p), ("w1_e", C.c_void_p),
                 ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p), ("wm_x", C.c_void_p),
                 ("wm_e", C.c_void_p), ("bm", C.c_void_p), ("wa", C.c_void_p), ("ba", C.c_void_p),
-                ("wu", C.c_void_p), ("bu", C.c_void_p),
+                ("wu", C.c_void_p), ("hier", C.c_void_p), ("bu", C.c_void_p),
                 ("tc_w1_e", C.c_void_p), ("tc_w2", C.c_void_p), ("tc_wm_e", C.c_void_p), ("tc_wtab", C.c_void_p),
                 ("tc_wu", C.c_void_p), ("tc_wnemb", C.c_void_p), ("tc_wemb", C.c_void_p), ("tc_w1_e0", C.c_void_p), ("tc_wheads", C.c_void_p), ("tc_wh1", C.c_void_p),
                 ("tc_wh2", C.c_void_p),

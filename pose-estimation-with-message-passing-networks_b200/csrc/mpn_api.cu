@@ -14,14 +14,20 @@ static int validate_mpn(const pgmp_mpn_params* p) {
   if (p->aux_loss_steps < 0) return set_error(PGMP_ERR_INVALID, "AUX_LOSS_STEPS < 0");
   if (p->per_type) {
     if (p->num_types < 1 || p->num_types > 17 || p->num_type_mlps != 17) return set_error(PGMP_ERR_INVALID, "per_type: num_types %d, mlps %d", p->num_types, p->num_type_mlps);
-    if (!p->has_update_mlp || !p->wu) return set_error(PGMP_ERR_INVALID, "per_type needs update_mlp");
+    if (p->update_hier) {
+      if (!p->hier || (p->num_types != 17 && p->num_types != 14))
+        return set_error(PGMP_ERR_INVALID, "hierarch_mlp needs its weights and 17 or 14 joint types (layers.py:96)");
+    } else if (!p->has_update_mlp || !p->wu) {
+      return set_error(PGMP_ERR_INVALID, "per_type needs update_mlp");
+    }
   } else {
     if (p->num_types != 1 || p->num_type_mlps != 1) return set_error(PGMP_ERR_INVALID, "agnostic: num_types must be 1");
     if (p->attn != PGMP_ATTN_NONE) return set_error(PGMP_ERR_INVALID, "attention aggregation needs per_type");
   }
   if (p->aggr < 0 || p->aggr > 2 || p->attn < 0 || p->attn > 2) return set_error(PGMP_ERR_INVALID, "aggr %d attn %d", p->aggr, p->attn);
   if (p->attn && (!p->wa || !p->ba)) return set_error(PGMP_ERR_INVALID, "attention without attn_net weights");
-  if (p->has_update_mlp && (!p->wu || !p->bu)) return set_error(PGMP_ERR_INVALID, "update_mlp weights missing");
+  if (p->update_hier && !p->per_type) return set_error(PGMP_ERR_INVALID, "hierarch_mlp needs per_type");
+  if (p->has_update_mlp && !p->update_hier && (!p->wu || !p->bu)) return set_error(PGMP_ERR_INVALID, "update_mlp weights missing");
   if (p->skip && !p->w1_e0) return set_error(PGMP_ERR_INVALID, "skip without w1_e0");
   if (!p->x || !p->node_types || !p->w1_dst || !p->w1_src || !p->w1_e || !p->b1 || !p->w2 || !p->b2 || !p->wm_x ||
       !p->wm_e || !p->bm || !p->node_logits || !p->class_logits || !p->workspace)

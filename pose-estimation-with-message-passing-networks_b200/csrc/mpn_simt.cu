@@ -14,6 +14,9 @@
 #include "simt_mlp.cuh"
 
 namespace pgmp {
+
+int mpn_node_update_hier(const pgmp_mpn_params& p, const MpnWorkspace& w, int out_slot, cudaStream_t st);
+
 namespace {
 
 // ------------------------------------------------------------------------------------------------
@@ -364,6 +367,15 @@ int mpn_embed_impl(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t
   return PGMP_OK;
 }
 
+// out[M][dims[-1]] = mlp(in[M][dims[0]]) for a 64-wide-or-narrower chain (heads)
+int mpn_run_mlp_rows(const pgmp_mlp& mlp, const float* in, int64_t M, float* out, cudaStream_t st) {
+  const size_t smem64 = sizeof(float) * (2 * kD * kTileP + kWs);
+  PGMP_CUDA(cudaFuncSetAttribute(mlp_chain_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
+  PGMP_LAUNCH((mlp_chain_kernel<64>), (unsigned)ceil_div<int64_t>(M, kTile), kTile, smem64, st, mlp, in, (int64_t)mlp.dims[0],
+              (int64_t)1, (const int32_t*)nullptr, M, out, (const float*)nullptr, (const float*)nullptr, (float*)nullptr);
+  return PGMP_OK;
+}
+
 int mpn_node_tables(const pgmp_mpn_params& p, const MpnWorkspace& w, const float* h, cudaStream_t st) {
   const size_t smem = sizeof(float) * (3 * kD * kTileP + kWs);
   static bool attr = false;
@@ -433,7 +445,7 @@ int mpn_forward_simt(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream
   for (int s = 0; s < p.steps; ++s) {
     if (s > 0) {
       const int prev_slot = (s - 1) >= first_out ? (s - 1) - first_out : -1;
-      if ((rc = mpn_node_update(p, w, prev_slot, st)) != PGMP_OK) return rc;
+      if ((rc = (p.update_hier ? mpn_node_update_hier(p, w, prev_slot, st) : mpn_node_update(p, w, prev_slot, st))) != PGMP_OK) return rc;
     }
     if ((rc = mpn_node_tables(p, w, w.h, st)) != PGMP_OK) return rc;
     const int slot = s >= first_out ? s - first_out : -1;
@@ -441,7 +453,8 @@ int mpn_forward_simt(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream
     a.edge_logits = slot >= 0 ? p.edge_logits + (size_t)slot * E : nullptr;
     if (E > 0) PGMP_LAUNCH(edge_step_kernel, (unsigned)(w.max_slots / kTile), kTile, smem_edge, st, a);
   }
-  return mpn_node_update(p, w, (p.steps - 1) - first_out, st);
+  return p.update_hier ? mpn_node_update_hier(p, w, (p.steps - 1) - first_out, st)
+                       : mpn_node_update(p, w, (p.steps - 1) - first_out, st);
 }
 
 }  // namespace pgmp

@@ -26,6 +26,7 @@ int mpn_edge_embed_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStrea
 int mpn_embed_nodes(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t st);
 int mpn_node_embed_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t st, bool* done);
 int mpn_node_update_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, int out_slot, cudaStream_t st);
+int mpn_node_update_hier(const pgmp_mpn_params& p, const MpnWorkspace& w, int out_slot, cudaStream_t st);
 
 namespace {
 
@@ -592,10 +593,14 @@ __global__ void __launch_bounds__(kTile) selftest_umma_ts_kernel(const float* __
 }  // namespace
 
 int mpn_forward_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t st) {
-  if (!p.tc_w1_e || !p.tc_w2 || !p.tc_wm_e || !p.tc_wtab || (p.has_update_mlp && !p.tc_wu))
+  if (!p.tc_w1_e || !p.tc_w2 || !p.tc_wm_e || !p.tc_wtab || (p.has_update_mlp && !p.update_hier && !p.tc_wu))
     return set_error(PGMP_ERR_INVALID, "PGMP_PRECISION_TC needs the bf16 hi/lo weights");
   // the node update runs on the tensor cores when it is a matrix product (update MLP), else it is a plain merge
   auto node_update = [&](int out_slot) {
+    if (p.update_hier) {            // hierarch_mlp update: fp32 SIMT kernel, then the operand image of h
+      const int r = mpn_node_update_hier(p, w, out_slot, st);
+      return r != PGMP_OK ? r : mpn_node_image(w, w.h, p.num_nodes, w.h_img, st);
+    }
     if (p.has_update_mlp) return mpn_node_update_tc(p, w, out_slot, st);
     const int r = mpn_node_update(p, w, out_slot, st);          // plain merge (agnostic layer without update MLP)
     return r != PGMP_OK ? r : mpn_node_image(w, w.h, p.num_nodes, w.h_img, st);

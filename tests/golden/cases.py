@@ -46,6 +46,7 @@ MPN_CASES = {
     "flagship_fully": ("fully_small", "flagship_mpn_config", dict(STEPS=2), 9),
     "flagship_crowdpose": ("crowdpose", "flagship_mpn_config", dict(STEPS=2, NUM_JOINTS=14, EDGE_INPUT_DIM=16), 10),
     "flagship_config1": ("config1_512", "flagship_mpn_config", dict(), 11),
+    "pertype_hierarch_mlp": ("knn_small", "flagship_mpn_config", dict(UPDATE_TYPE="hierarch_mlp", STEPS=3), 12),
 }
 
 # arrays at or above this many bytes are stored as sha256 digests instead of values

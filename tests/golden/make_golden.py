@@ -58,11 +58,16 @@ def run_reference_gc(cg, name):
 
 
 def main():
+    only = set(sys.argv[1:])          # optional: (re)generate just these fixtures, e.g. `mpn_pertype_hierarch_mlp`
     cg, mpn = ref_shims.load_reference()
     gc_out = {}
     for name in GC_CASES:
+        if only and f"gc_{name}" not in only and not any(o.startswith("mpn_") and MPN_CASES[o[4:]][0] == name for o in only):
+            continue
         res = run_reference_gc(cg, name)
         gc_out[name] = res
+        if only and f"gc_{name}" not in only:
+            continue
         out = {}
         for k, v in res.items():
             pack(out, k, v)
@@ -70,6 +75,8 @@ def main():
         print(f"gc_{name}: N={len(res['joint_det'])} E={res['edge_index'].shape[1]}")
 
     for name, (gc_name, maker, over, seed) in MPN_CASES.items():
+        if only and f"mpn_{name}" not in only:
+            continue
         cfg = mpn_config_for(pgmp_b200.config, maker, over)
         model = mpn.NodeClassificationMPNSimple(cfg).eval()
         synthetic.synth_mpn_state_dict(model, seed)
@@ -92,6 +99,8 @@ def main():
         np.savez_compressed(os.path.join(HERE, f"mpn_{name}.npz"), **out)
         print(f"mpn_{name}: edge |max| {np.abs(pe[-1].numpy()).max():.3f} node |max| {np.abs(pn[-1].numpy()).max():.3f}")
 
+    if only:
+        return
     # grouping tail: the reference's own weight plumbing + person assembly around OUR GAEC restatement
     pred_to_person, subgraph = ref_shims.load_reference_grouping(oracle.grouping.gaec)
     for name, gc_name, seed in [("group_knn_small", "knn_small", 0), ("group_fully_small", "fully_small", 1),
