@@ -228,6 +228,68 @@ uint64_t pgmp_mpn_workspace_bytes(const pgmp_mpn_params* p);
 int pgmp_mpn_forward(const pgmp_mpn_params* p, pgmp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Training step of the message-passing network: forward of
+ * NodeClassificationMPNSimple (NodeClassificationMPNSimple.py:62-97) in train() mode -- BatchNorm1d
+ * with batch statistics (layers.py:13-14, 22-23), running statistics updated in place -- with the
+ * type-agnostic MPLayer (layers.py:32-86; AGGR max / add / mean, SKIP, USE_NODE_UPDATE_MLP), and the
+ * reverse pass torch autograd runs for the reference (train.py:232-236): gradients of every
+ * parameter and of the node input x.  fp32 throughout.
+ *
+ * Parameters and their gradients are two flat fp32 device buffers with the same element offsets;
+ * every matrix keeps the layout of its nn.Linear.weight, [out][in].
+ * Two calls sharing one workspace (the forward leaves the activations the backward needs):
+ *   pgmp_mpn_train_forward  -> logits, BatchNorm running statistics
+ *   pgmp_mpn_train_backward -> grads (ACCUMULATED into `grads`: zero it first), grad_x (overwritten)
+ * Reductions run in a fixed order (no floating-point atomics): results are reproducible run to run.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pgmp_mlp_train {
+  int32_t n_layers;
+  int32_t dims[PGMP_MAX_LAYERS + 1];       /* dims[0] = input width, dims[l+1] = output width of Linear l */
+  int32_t relu[PGMP_MAX_LAYERS];           /* ReLU after Linear l */
+  int32_t bn[PGMP_MAX_LAYERS];             /* BatchNorm1d after that ReLU (ReLU comes BEFORE BatchNorm, layers.py:11-14) */
+  int64_t w[PGMP_MAX_LAYERS];              /* element offset of Linear.weight [dims[l+1]][dims[l]] in params / grads */
+  int64_t b[PGMP_MAX_LAYERS];              /* Linear.bias */
+  int64_t gamma[PGMP_MAX_LAYERS];          /* BatchNorm weight / bias (unused when bn[l] == 0) */
+  int64_t beta[PGMP_MAX_LAYERS];
+  float* running_mean[PGMP_MAX_LAYERS];    /* device [dims[l+1]], updated in place with momentum 0.1, or NULL */
+  float* running_var[PGMP_MAX_LAYERS];     /* (unbiased batch variance goes into the running estimate) */
+} pgmp_mlp_train;
+
+typedef struct pgmp_mpn_train_params {
+  int64_t num_nodes, num_edges;
+  const float* x;                          /* device [N, node_emb.dims[0]] contiguous */
+  const float* edge_attr;                  /* device [E, edge_emb.dims[0]] contiguous */
+  const int64_t* edge_index;               /* device [2, E]; row 0 = source j, row 1 = target i */
+  int32_t dim;                             /* 64 */
+  int32_t skip, steps, aux_loss_steps;
+  int32_t aggr;                            /* PGMP_AGGR_* */
+  int32_t has_update_mlp;
+  int32_t num_classes;
+  const float* params;                     /* device, flat */
+  float* grads;                            /* device, flat, same offsets (backward only) */
+  pgmp_mlp_train node_emb, edge_emb, edge_head, node_head, class_head;
+  int64_t w1, b1;                          /* mlp_edge.0 [64][2*nd + ed], nd = 64 * (skip ? 2 : 1), ed likewise; columns [x_i ; x_j ; e] (layers.py:66) */
+  int64_t w2, b2;                          /* mlp_edge.2 [64][64] */
+  int64_t wm, bm;                          /* mlp_node.0 [64][nd + 64]; columns [x_i ; e'] (layers.py:76) */
+  int64_t wu, bu;                          /* update_mlp.0 [64][64] (has_update_mlp) */
+  /* n_out = min(steps, aux_loss_steps + 1) reported steps */
+  float* edge_logits;                      /* out [n_out][E] */
+  float* node_logits;                      /* out [n_out][N] */
+  float* class_logits;                     /* out [n_out][N][num_classes] */
+  /* backward only */
+  const float* d_edge_logits;              /* [n_out][E]   dL/d edge_logits */
+  const float* d_node_logits;              /* [n_out][N] */
+  const float* d_class_logits;             /* [n_out][N][num_classes] */
+  float* grad_x;                           /* out [N, node_emb.dims[0]] or NULL */
+  void* workspace;                         /* device, pgmp_mpn_train_workspace_bytes() bytes, 256-B aligned; must survive from forward to backward */
+  uint64_t workspace_bytes;
+} pgmp_mpn_train_params;
+
+uint64_t pgmp_mpn_train_workspace_bytes(const pgmp_mpn_train_params* p);
+int pgmp_mpn_train_forward(const pgmp_mpn_train_params* p, pgmp_stream_t stream);
+int pgmp_mpn_train_backward(const pgmp_mpn_train_params* p, pgmp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Grouping tail -- replaces sigmoid/softmax (src/valid.py:109-111), the node threshold + subgraph
  * of pred_to_ann (src/Utils/Utils.py:1448-1451), pred_to_person with CC_METHOD GAEC (:499-514),
  * cluster_graph / extract_edge_matrix / cluster_andres_graph

@@ -93,6 +93,108 @@ def _mlp_struct(spec, base):
     return m
 
 
+def _mlp_train_struct(seq, prefix, offsets):
+    """``make_mlp`` chain -> ``pgmp_mlp_train`` (training mode: BatchNorm stays a separate stage, nothing is folded)."""
+    m = nv.MlpTrain()
+    l = -1
+    for i, mod in enumerate(seq):
+        name = "%s.%d" % (prefix, i)
+        if isinstance(mod, nn.Linear):
+            l += 1
+            if l >= nv.MAX_LAYERS:
+                raise NotImplementedError("MLP deeper than %d layers" % nv.MAX_LAYERS)
+            m.dims[l], m.dims[l + 1] = mod.in_features, mod.out_features
+            m.w[l], m.b[l] = offsets[name + ".weight"], offsets[name + ".bias"]
+        elif isinstance(mod, nn.ReLU):
+            m.relu[l] = 1
+        elif isinstance(mod, nn.BatchNorm1d):
+            if mod.momentum != 0.1 or mod.eps != 1e-5 or not mod.affine or not mod.track_running_stats:
+                raise NotImplementedError("BatchNorm1d with non-default settings")
+            m.bn[l] = 1
+            m.gamma[l], m.beta[l] = offsets[name + ".weight"], offsets[name + ".bias"]
+            m.running_mean[l], m.running_var[l] = mod.running_mean.data_ptr(), mod.running_var.data_ptr()
+        else:
+            raise NotImplementedError(type(mod))
+    m.n_layers = l + 1
+    return m
+
+
+class _MpnTrainFunction(torch.autograd.Function):
+    """One training step of the MPN in ``libpgmp.so``: ``pgmp_mpn_train_forward`` / ``pgmp_mpn_train_backward``
+    stand where torch autograd runs the reference's Python forward (train.py:232-236)."""
+
+    @staticmethod
+    def forward(ctx, model, x, edge_attr, edge_index, *params):
+        names = [n for n, _ in model.named_parameters()]
+        dev = x.device
+        lib = nv.lib()
+        sizes = [p.numel() for p in params]
+        offsets, off = {}, 0
+        for n, k in zip(names, sizes):
+            offsets[n] = off
+            off += k
+        flat = torch.cat([p.detach().reshape(-1) for p in params]).contiguous()
+        x_ = x.detach().contiguous()
+        ea = edge_attr.detach().contiguous()
+        ei = edge_index.detach().contiguous()
+        N, E = x_.shape[0], ei.shape[1]
+        n_out = model.num_outputs()
+        J = model.classification[-1].out_features
+        edge_logits = torch.empty((n_out, E), dtype=torch.float32, device=dev)
+        node_logits = torch.empty((n_out, N), dtype=torch.float32, device=dev)
+        class_logits = torch.empty((n_out, N, J), dtype=torch.float32, device=dev)
+        layer = model.mpn_node_cls
+        p = nv.MpnTrainParams(num_nodes=N, num_edges=E, x=x_.data_ptr(), edge_attr=ea.data_ptr(), edge_index=ei.data_ptr(),
+                              dim=64, skip=int(bool(model.use_skip_connections)), steps=model.edge_steps,
+                              aux_loss_steps=model.aux_loss_steps, aggr=nv.AGGR[model.aggr],
+                              has_update_mlp=int(layer.update_mlp is not None), num_classes=J, params=flat.data_ptr(),
+                              edge_logits=edge_logits.data_ptr(), node_logits=node_logits.data_ptr(),
+                              class_logits=class_logits.data_ptr())
+        for field, name in (("node_emb", "node_embedding"), ("edge_emb", "edge_embedding"),
+                            ("edge_head", "edge_classification"), ("node_head", "node_classification"),
+                            ("class_head", "classification")):
+            setattr(p, field, _mlp_train_struct(getattr(model, name), name, offsets))
+        p.w1, p.b1 = offsets["mpn_node_cls.mlp_edge.0.weight"], offsets["mpn_node_cls.mlp_edge.0.bias"]
+        p.w2, p.b2 = offsets["mpn_node_cls.mlp_edge.2.weight"], offsets["mpn_node_cls.mlp_edge.2.bias"]
+        p.wm, p.bm = offsets["mpn_node_cls.mlp_node.0.weight"], offsets["mpn_node_cls.mlp_node.0.bias"]
+        if layer.update_mlp is not None:
+            p.wu, p.bu = offsets["mpn_node_cls.update_mlp.0.weight"], offsets["mpn_node_cls.update_mlp.0.bias"]
+        with torch.cuda.device(dev):
+            ws_bytes = int(lib.pgmp_mpn_train_workspace_bytes(p))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            p.workspace, p.workspace_bytes = ws.data_ptr(), ws_bytes
+            nv.check(lib.pgmp_mpn_train_forward(p, nv.current_stream()))
+        for mod in model.modules():            # the kernels updated the running statistics in place
+            if isinstance(mod, nn.BatchNorm1d):
+                torch.autograd.graph.increment_version((mod.running_mean, mod.running_var))
+                mod.num_batches_tracked += 1
+        ctx.p, ctx.sizes, ctx.shapes = p, sizes, [tuple(q.shape) for q in params]
+        ctx.keep = (flat, x_, ea, ei, ws, edge_logits, node_logits, class_logits)   # the forward's activations live in ws
+        ctx.need_x = x.requires_grad
+        return edge_logits, node_logits, class_logits
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_edge, d_node, d_class):
+        p = ctx.p
+        flat, x_ = ctx.keep[0], ctx.keep[1]
+        dev = flat.device
+        grads = torch.zeros_like(flat)
+        grad_x = torch.empty_like(x_) if ctx.need_x else None
+        de, dn, dc = d_edge.contiguous().float(), d_node.contiguous().float(), d_class.contiguous().float()
+        p.grads, p.grad_x = grads.data_ptr(), (grad_x.data_ptr() if grad_x is not None else None)
+        p.d_edge_logits, p.d_node_logits, p.d_class_logits = de.data_ptr(), dn.data_ptr(), dc.data_ptr()
+        with torch.cuda.device(dev):
+            nv.check(nv.lib().pgmp_mpn_train_backward(p, nv.current_stream()))
+            for t in ctx.keep + (de, dn, dc):
+                t.record_stream(torch.cuda.current_stream())
+        out, off = [], 0
+        for k, shape in zip(ctx.sizes, ctx.shapes):
+            out.append(grads[off:off + k].view(shape))
+            off += k
+        return (None, grad_x, None, None) + tuple(out)
+
+
 class NodeClassificationMPNSimple(nn.Module):
     """Same constructor, parameters (names and shapes) and ``forward`` contract as the reference class
     (NodeClassificationMPNSimple.py:23-97); inference (``eval()``) runs in ``libpgmp.so``."""
@@ -232,8 +334,7 @@ class NodeClassificationMPNSimple(nn.Module):
     # ------------------------------------------------------------------ forward
     def forward(self, x, edge_attr, edge_index, **kwargs):
         if self.training:
-            raise NotImplementedError("training mode (BatchNorm batch statistics + backward kernels) is the next "
-                                      "row of the build (SURVEY.md 8f); call .eval()")
+            return self._forward_train(x, edge_attr, edge_index, **kwargs)
         if self.node_steps != 0:
             raise NotImplementedError("NODE_STEPS != 0 (the reference's own loop omits node_types, App. A)")
         if self.edge_steps < 1:
@@ -294,6 +395,39 @@ class NodeClassificationMPNSimple(nn.Module):
         preds_node.append(preds_node[-1].clone())                      # :93-94 (recomputed on the same features)
         preds_class.append(preds_class[-1].clone())
         return preds_edge, preds_node, preds_class, [None]
+
+
+def _forward_train(self, x, edge_attr, edge_index, **kwargs):
+    """``train()`` mode: BatchNorm batch statistics, activations kept for the reverse pass."""
+    if self.aggr_type != "agnostic":
+        raise NotImplementedError("training kernels cover the type-agnostic MPLayer (class_agnostic_end2end configs); "
+                                  "AGGR_TYPE=%r trains with the reference for now" % (self.aggr_type,))
+    if self.node_steps != 0 or self.edge_steps < 1:
+        raise NotImplementedError("NODE_STEPS != 0 / STEPS < 1")
+    nv.require_cuda(x, "x", torch.float32)
+    nv.require_cuda(edge_attr, "edge_attr", torch.float32)
+    nv.require_cuda(edge_index, "edge_index", torch.int64)
+    N, E = x.shape[0], edge_index.shape[1]
+    if N == 0:
+        raise ValueError("empty graph")
+    if edge_attr.shape[0] != E or (E and edge_attr.shape[1] != self.edge_embedding[0].in_features):
+        raise ValueError("edge_attr must be [E, %d]" % self.edge_embedding[0].in_features)
+    if x.shape[1] != self.node_embedding[0].in_features:
+        raise ValueError("x must be [N, %d]" % self.node_embedding[0].in_features)
+    params = [p for _, p in self.named_parameters()]
+    for p in params:
+        nv.require_cuda(p, "parameter", torch.float32)
+    edge_logits, node_logits, class_logits = _MpnTrainFunction.apply(self, x, edge_attr, edge_index, *params)
+    n_out = self.num_outputs()
+    preds_edge = [edge_logits[i].squeeze() for i in range(n_out)]
+    preds_node = [node_logits[i].squeeze() for i in range(n_out)]
+    preds_class = [class_logits[i] for i in range(n_out)]
+    preds_node.append(preds_node[-1].clone())                          # :93-94
+    preds_class.append(preds_class[-1].clone())
+    return preds_edge, preds_node, preds_class, [None]
+
+
+NodeClassificationMPNSimple._forward_train = _forward_train
 
 
 _OUT_OF_SCOPE = (

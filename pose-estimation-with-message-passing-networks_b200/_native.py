@@ -85,6 +85,27 @@ class MpnParams(C.Structure):
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64)]
 
 
+class MlpTrain(C.Structure):
+    _fields_ = [("n_layers", C.c_int32), ("dims", C.c_int32 * (MAX_LAYERS + 1)), ("relu", C.c_int32 * MAX_LAYERS),
+                ("bn", C.c_int32 * MAX_LAYERS), ("w", C.c_int64 * MAX_LAYERS), ("b", C.c_int64 * MAX_LAYERS),
+                ("gamma", C.c_int64 * MAX_LAYERS), ("beta", C.c_int64 * MAX_LAYERS),
+                ("running_mean", C.c_void_p * MAX_LAYERS), ("running_var", C.c_void_p * MAX_LAYERS)]
+
+
+class MpnTrainParams(C.Structure):
+    _fields_ = [("num_nodes", C.c_int64), ("num_edges", C.c_int64), ("x", C.c_void_p), ("edge_attr", C.c_void_p),
+                ("edge_index", C.c_void_p), ("dim", C.c_int32), ("skip", C.c_int32), ("steps", C.c_int32),
+                ("aux_loss_steps", C.c_int32), ("aggr", C.c_int32), ("has_update_mlp", C.c_int32),
+                ("num_classes", C.c_int32), ("params", C.c_void_p), ("grads", C.c_void_p),
+                ("node_emb", MlpTrain), ("edge_emb", MlpTrain), ("edge_head", MlpTrain), ("node_head", MlpTrain),
+                ("class_head", MlpTrain),
+                ("w1", C.c_int64), ("b1", C.c_int64), ("w2", C.c_int64), ("b2", C.c_int64), ("wm", C.c_int64),
+                ("bm", C.c_int64), ("wu", C.c_int64), ("bu", C.c_int64),
+                ("edge_logits", C.c_void_p), ("node_logits", C.c_void_p), ("class_logits", C.c_void_p),
+                ("d_edge_logits", C.c_void_p), ("d_node_logits", C.c_void_p), ("d_class_logits", C.c_void_p),
+                ("grad_x", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64)]
+
+
 CC_METHODS = {"GAEC": 0, "threshold": 1}
 
 
@@ -115,6 +136,9 @@ SYMBOLS = {
     "pgmp_selftest_umma_ts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pgmp_mpn_workspace_bytes": (C.c_uint64, [C.POINTER(MpnParams)]),
     "pgmp_mpn_forward": (C.c_int, [C.POINTER(MpnParams), C.c_void_p]),
+    "pgmp_mpn_train_workspace_bytes": (C.c_uint64, [C.POINTER(MpnTrainParams)]),
+    "pgmp_mpn_train_forward": (C.c_int, [C.POINTER(MpnTrainParams), C.c_void_p]),
+    "pgmp_mpn_train_backward": (C.c_int, [C.POINTER(MpnTrainParams), C.c_void_p]),
     "pgmp_group_workspace_bytes": (C.c_uint64, [C.POINTER(GroupParams)]),
     "pgmp_group_persons": (C.c_int, [C.POINTER(GroupParams), C.c_void_p]),
 }

@@ -1,0 +1,913 @@
+// Training step of the message-passing network with the type-agnostic MPLayer (include/pgmp.h,
+// pgmp_mpn_train_*): forward in train() mode and the reverse pass.
+//
+// Reference: NodeClassificationMPNSimple.forward (NodeClassificationMPNSimple.py:62-97), MPLayer
+// (layers.py:32-86), _make_mlp (layers.py:8-29; ReLU BEFORE BatchNorm1d), torch autograd for the gradients
+// (train.py:232-236).  Checked against oracle/mpn_train.py, which is pinned to the reference under float64 autograd.
+//
+// Structure.  The same column split of mlp_edge.0 / mlp_node.0 the inference path uses keeps the per-edge work at
+// 64-wide products: with x = [h0 ; h] and e = [g0 ; g]
+//     hidden = ReLU(W1_e e + b1 + P[dst] + Q[src]),  P = W1_dst x, Q = W1_src x        (per node)
+//     m      = ReLU(Wm_e g' + R[dst]),               R = Wm_x x + bm                   (per node)
+// and in the reverse pass the gradients that flow to x through the gathers are summed per node FIRST
+// (S_dst = sum over edges into n of d hidden, ...) and multiplied by the weights once per node:
+//     dx = S_dst W1_dst + S_src W1_src + T_dst Wm_x,    dW1_dst = S_dst^T x, ...
+// The per-node sums run over CSR bins ordered by edge id, weight gradients are reduced from per-CTA partial
+// tiles in a fixed order: no floating-point atomics anywhere, results are reproducible.
+// All arithmetic is fp32 SIMT (BatchNorm statistics accumulate in fp64); this is the first correct training path,
+// the tensor-core version of the three E-level products is the next step.
+#include "common.cuh"
+
+namespace pgmp {
+namespace {
+
+constexpr int kD = 64;
+constexpr int BM = 64, BN = 64, BK = 16;
+constexpr int kMaxSplits = 256;
+constexpr int kMaxWidth = 128;
+constexpr int kMaxSteps = 64, kMaxOut = 32;
+constexpr float kBnEps = 1e-5f;
+constexpr float kBnMomentum = 0.1f;
+constexpr uint32_t kFull = 0xffffffffu;
+
+// ------------------------------------------------------------------ operand descriptors
+struct ASeg {
+  const float* p;
+  int ld, w;
+};
+struct ASrc {   // up to two column blocks side by side (torch.cat(..., dim=1) without materialising it)
+  int n;
+  ASeg s[2];
+};
+inline ASrc src1(const float* p, int w) { return ASrc{1, {{p, w, w}, {nullptr, 0, 0}}}; }
+inline ASrc src2(const float* p, const float* q, int w) { return ASrc{2, {{p, w, w}, {q, w, w}}}; }
+inline int src_width(const ASrc& a) { return a.s[0].w + (a.n > 1 ? a.s[1].w : 0); }
+
+__device__ __forceinline__ float a_load(const ASrc& a, int64_t r, int k) {
+  if (k < a.s[0].w) return a.s[0].p[r * a.s[0].ld + k];
+  k -= a.s[0].w;
+  if (a.n > 1 && k < a.s[1].w) return a.s[1].p[r * a.s[1].ld + k];
+  return 0.f;
+}
+
+// ------------------------------------------------------------------ Y = act(A W^T + b + add1[idx1] + add2[idx2])
+struct FwdArgs {
+  ASrc a;
+  int64_t M;
+  int K, O;
+  const float* W;   // element (o, k) at W[o * ldw + coloff + k]
+  int ldw, coloff;
+  const float* bias;
+  const float* add1;   // [.][64] rows gathered by idx1 (O == 64), or null
+  const int64_t* idx1;
+  const float* add2;
+  const int64_t* idx2;
+  int relu;
+  float* Y;
+  int ldy;
+};
+
+__global__ void __launch_bounds__(256) lin_fwd_kernel(const FwdArgs g) {
+  __shared__ float As[BM][BK + 1];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  const int64_t r0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < g.K; k0 += BK) {
+    const int k = k0 + (t & 15);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = (t >> 4) + 16 * i;
+      const int64_t gr = r0 + r;
+      As[r][t & 15] = (gr < g.M && k < g.K) ? a_load(g.a, gr, k) : 0.f;
+      const int o = n0 + r;
+      Bs[t & 15][r] = (o < g.O && k < g.K) ? g.W[(int64_t)o * g.ldw + g.coloff + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float a = As[ty * 4 + i][kk];
+        acc[i][0] = fmaf(a, b.x, acc[i][0]);
+        acc[i][1] = fmaf(a, b.y, acc[i][1]);
+        acc[i][2] = fmaf(a, b.z, acc[i][2]);
+        acc[i][3] = fmaf(a, b.w, acc[i][3]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t gr = r0 + ty * 4 + i;
+    if (gr >= g.M) continue;
+    const float* e1 = g.add1 ? g.add1 + g.idx1[gr] * kD : nullptr;
+    const float* e2 = g.add2 ? g.add2 + g.idx2[gr] * kD : nullptr;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int o = n0 + tx * 4 + j;
+      if (o >= g.O) continue;
+      float v = acc[i][j];
+      if (g.bias) v += g.bias[o];
+      if (e1) v += e1[o];
+      if (e2) v += e2[o];
+      if (g.relu) v = fmaxf(v, 0.f);
+      g.Y[gr * g.ldy + o] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ dA = dY W, columns routed to their owners
+struct Target {
+  float* p;
+  int ld, k0, w, add;   // columns [k0, k0 + w) of dA go to p[r * ld + (k - k0)], overwriting or adding
+};
+struct BwdInArgs {
+  const float* dY;
+  int ldd;
+  int64_t M;
+  int O, K;
+  const float* W;
+  int ldw, coloff;
+  int nt;
+  Target t[2];
+};
+
+__global__ void __launch_bounds__(256) lin_bwd_in_kernel(const BwdInArgs g) {
+  __shared__ float As[BM][BK + 1];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  const int64_t r0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  float acc[4][4] = {};
+  for (int o0 = 0; o0 < g.O; o0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = (t >> 4) + 16 * i;
+      const int64_t gr = r0 + r;
+      const int o = o0 + (t & 15);
+      As[r][t & 15] = (gr < g.M && o < g.O) ? g.dY[gr * g.ldd + o] : 0.f;
+      const int ob = o0 + (t >> 6) + 4 * i;
+      const int k = n0 + (t & 63);
+      Bs[(t >> 6) + 4 * i][t & 63] = (ob < g.O && k < g.K) ? g.W[(int64_t)ob * g.ldw + g.coloff + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float a = As[ty * 4 + i][kk];
+        acc[i][0] = fmaf(a, b.x, acc[i][0]);
+        acc[i][1] = fmaf(a, b.y, acc[i][1]);
+        acc[i][2] = fmaf(a, b.z, acc[i][2]);
+        acc[i][3] = fmaf(a, b.w, acc[i][3]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int k = n0 + tx * 4 + j;
+    if (k >= g.K) continue;
+    const Target* tg = nullptr;
+    if (k >= g.t[0].k0 && k < g.t[0].k0 + g.t[0].w) tg = &g.t[0];
+    else if (g.nt > 1 && k >= g.t[1].k0 && k < g.t[1].k0 + g.t[1].w) tg = &g.t[1];
+    if (!tg) continue;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t gr = r0 + ty * 4 + i;
+      if (gr >= g.M) continue;
+      float* q = tg->p + gr * tg->ld + (k - tg->k0);
+      *q = tg->add ? *q + acc[i][j] : acc[i][j];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ dW partial tiles: part[s] = dY[rows_s]^T A[rows_s]
+struct BwdWArgs {
+  const float* dY;
+  int ldd, O;
+  ASrc a;
+  int K;
+  int64_t M, rows_per_split;
+  float* part;    // [splits][O][K]
+  float* partb;   // [splits][O] column sums of dY, or null
+};
+
+__global__ void __launch_bounds__(256) lin_bwd_w_kernel(const BwdWArgs g) {
+  __shared__ __align__(16) float Ds[BK][BN + 4];
+  __shared__ __align__(16) float As[BK][BN + 4];
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  const int k0 = blockIdx.x * BN, o0 = blockIdx.y * BN, split = blockIdx.z;
+  const int64_t rb = (int64_t)split * g.rows_per_split;
+  const int64_t re = min(rb + g.rows_per_split, g.M);
+  float acc[4][4] = {};
+  float bsum[4] = {};
+  for (int64_t r0 = rb; r0 < re; r0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = (t >> 6) + 4 * i;
+      const int c = t & 63;
+      const int64_t gr = r0 + r;
+      const bool in = gr < re;
+      Ds[r][c] = (in && o0 + c < g.O) ? g.dY[gr * g.ldd + o0 + c] : 0.f;
+      As[r][c] = (in && k0 + c < g.K) ? a_load(g.a, gr, k0 + c) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < BK; ++rr) {
+      const float4 d = *reinterpret_cast<const float4*>(&Ds[rr][ty * 4]);
+      const float4 a = *reinterpret_cast<const float4*>(&As[rr][tx * 4]);
+      const float dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[i][0] = fmaf(dv[i], a.x, acc[i][0]);
+        acc[i][1] = fmaf(dv[i], a.y, acc[i][1]);
+        acc[i][2] = fmaf(dv[i], a.z, acc[i][2]);
+        acc[i][3] = fmaf(dv[i], a.w, acc[i][3]);
+        bsum[i] += dv[i];
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int o = o0 + ty * 4 + i;
+    if (o >= g.O) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tx * 4 + j;
+      if (k < g.K) g.part[((int64_t)split * g.O + o) * g.K + k] = acc[i][j];
+    }
+    if (g.partb && blockIdx.x == 0 && tx == 0) g.partb[(int64_t)split * g.O + o] = bsum[i];
+  }
+}
+
+// dW[o][coloff + k] += sum_s part[s][o][k] (s ascending), db[o] += sum_s partb[s][o]
+__global__ void __launch_bounds__(256) reduce_parts_kernel(const float* __restrict__ part, const float* __restrict__ partb,
+                                                            int splits, int O, int K, float* __restrict__ dW, int ldw,
+                                                            int coloff, float* __restrict__ db) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = O * K;
+  if (idx < total) {
+    float s = 0.f;
+    for (int i = 0; i < splits; ++i) s += part[(int64_t)i * total + idx];
+    dW[(int64_t)(idx / K) * ldw + coloff + idx % K] += s;
+  }
+  if (db && partb && idx < O) {
+    float s = 0.f;
+    for (int i = 0; i < splits; ++i) s += partb[(int64_t)i * O + idx];
+    db[idx] += s;
+  }
+}
+
+// ------------------------------------------------------------------ elementwise
+__global__ void __launch_bounds__(256) relu_mask_kernel(const float* gin, const float* __restrict__ y, float* gout, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) gout[i] = y[i] > 0.f ? gin[i] : 0.f;
+}
+
+__global__ void __launch_bounds__(256) add_into_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
+}
+
+// ------------------------------------------------------------------ CSR of the edges by one endpoint, bins ordered by edge id
+__global__ void __launch_bounds__(256) csr_count_kernel(const int64_t* __restrict__ key, int64_t E, int64_t N,
+                                                         int32_t* __restrict__ cnt, int32_t* __restrict__ bad) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int64_t k = key[e];
+  if (k < 0 || k >= N) { *bad = 1; return; }
+  atomicAdd(&cnt[k], 1);
+}
+
+__global__ void __launch_bounds__(1024) csr_scan_kernel(const int32_t* __restrict__ cnt, int64_t N, int32_t* __restrict__ ptr) {
+  __shared__ int s_warp[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t chunk = ceil_div<int64_t>(N, blockDim.x);
+  const int64_t b0 = min((int64_t)threadIdx.x * chunk, N), b1 = min(b0 + chunk, N);
+  int sum = 0;
+  for (int64_t b = b0; b < b1; ++b) sum += cnt[b];
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl += u;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const int w = s_warp[lane];
+    int wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(kFull, wi, o);
+      if (lane >= o) wi += u;
+    }
+    s_warp[lane] = wi - w;
+  }
+  __syncthreads();
+  int run = s_warp[warp] + incl - sum;
+  for (int64_t b = b0; b < b1; ++b) {
+    ptr[b] = run;
+    run += cnt[b];
+  }
+  if (threadIdx.x == blockDim.x - 1) ptr[N] = run;   // exclusive prefix + own chunk = total
+}
+
+__global__ void __launch_bounds__(256) csr_fill_kernel(const int64_t* __restrict__ key, int64_t E, int64_t N,
+                                                        const int32_t* __restrict__ ptr, int32_t* __restrict__ cursor,
+                                                        int32_t* __restrict__ perm) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int64_t k = key[e];
+  if (k < 0 || k >= N) return;
+  perm[ptr[k] + atomicAdd(&cursor[k], 1)] = (int32_t)e;
+}
+
+__global__ void __launch_bounds__(256) csr_sort_kernel(const int32_t* __restrict__ ptr, int64_t N, int32_t* __restrict__ perm) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  int32_t* s = perm + ptr[n];
+  const int c = ptr[n + 1] - ptr[n];
+  for (int i = 1; i < c; ++i) {
+    const int32_t v = s[i];
+    int j = i - 1;
+    while (j >= 0 && s[j] > v) { s[j + 1] = s[j]; --j; }
+    s[j + 1] = v;
+  }
+}
+
+// ------------------------------------------------------------------ per-node reductions over the CSR bins (64 columns)
+// S[n] = sum of V[e] over the bin of n, in edge order
+__global__ void __launch_bounds__(256) seg_sum_kernel(const float* __restrict__ V, const int32_t* __restrict__ ptr,
+                                                       const int32_t* __restrict__ perm, int64_t N, float* __restrict__ S) {
+  const int64_t n = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 6);
+  const int c = threadIdx.x & 63;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int i = ptr[n]; i < ptr[n + 1]; ++i) s += V[(int64_t)perm[i] * kD + c];
+  S[n * kD + c] = s;
+}
+
+// scatter(m, dst, reduce = aggr) with empty bins = 0 (torch_scatter; layers.py:32-34 aggr of MessagePassing)
+__global__ void __launch_bounds__(256) aggregate_fwd_kernel(const float* __restrict__ m, const int32_t* __restrict__ ptr,
+                                                             const int32_t* __restrict__ perm, int64_t N, int aggr,
+                                                             float* __restrict__ out) {
+  const int64_t n = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 6);
+  const int c = threadIdx.x & 63;
+  if (n >= N) return;
+  const int b = ptr[n], e = ptr[n + 1];
+  float v = 0.f;
+  if (e > b) {
+    if (aggr == PGMP_AGGR_MAX) {
+      v = m[(int64_t)perm[b] * kD + c];
+      for (int i = b + 1; i < e; ++i) v = fmaxf(v, m[(int64_t)perm[i] * kD + c]);
+    } else {
+      for (int i = b; i < e; ++i) v += m[(int64_t)perm[i] * kD + c];
+      if (aggr == PGMP_AGGR_MEAN) v /= (float)(e - b);
+    }
+  }
+  out[n * kD + c] = v;
+}
+
+// gradient of the aggregation: max routes to the maxima of the bin, evenly among ties (oracle/mpn_train.py scatter)
+__global__ void __launch_bounds__(256) aggregate_bwd_kernel(const float* __restrict__ dagg, const float* __restrict__ m,
+                                                             const float* __restrict__ agg, const int32_t* __restrict__ ptr,
+                                                             const int32_t* __restrict__ perm, int64_t N, int aggr,
+                                                             float* __restrict__ dm) {
+  const int64_t n = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 6);
+  const int c = threadIdx.x & 63;
+  if (n >= N) return;
+  const int b = ptr[n], e = ptr[n + 1];
+  if (e <= b) return;
+  const float g = dagg[n * kD + c];
+  if (aggr == PGMP_AGGR_MAX) {
+    const float mx = agg[n * kD + c];
+    int ties = 0;
+    for (int i = b; i < e; ++i) ties += m[(int64_t)perm[i] * kD + c] == mx;
+    const float share = g / (float)max(ties, 1);
+    for (int i = b; i < e; ++i) {
+      const int64_t o = (int64_t)perm[i] * kD + c;
+      dm[o] = m[o] == mx ? share : 0.f;
+    }
+  } else {
+    const float share = aggr == PGMP_AGGR_MEAN ? g / (float)(e - b) : g;
+    for (int i = b; i < e; ++i) dm[(int64_t)perm[i] * kD + c] = share;
+  }
+}
+
+// ------------------------------------------------------------------ BatchNorm1d, training mode
+// column sums in fp64 over a row range: mode 0 (sum y, sum y^2); mode 1 (sum g, sum g * xhat)
+__global__ void __launch_bounds__(256) bn_partial_kernel(const float* __restrict__ Y, const float* __restrict__ G,
+                                                          const float* __restrict__ mean, const float* __restrict__ inv,
+                                                          int64_t M, int C, int Cp, int64_t rows_per_cta,
+                                                          double* __restrict__ part) {
+  __shared__ double sh[2][256];
+  const int c = threadIdx.x % Cp, lane = threadIdx.x / Cp, lanes = 256 / Cp;
+  const int64_t rb = (int64_t)blockIdx.x * rows_per_cta, re = min(rb + rows_per_cta, M);
+  double s1 = 0.0, s2 = 0.0;
+  if (c < C) {
+    if (G == nullptr) {
+      for (int64_t r = rb + lane; r < re; r += lanes) {
+        const double y = Y[r * C + c];
+        s1 += y;
+        s2 += y * y;
+      }
+    } else {
+      const float mu = mean[c], iv = inv[c];
+      for (int64_t r = rb + lane; r < re; r += lanes) {
+        const float gg = G[r * C + c];
+        s1 += gg;
+        s2 += (double)gg * (double)((Y[r * C + c] - mu) * iv);
+      }
+    }
+  }
+  sh[0][threadIdx.x] = s1;
+  sh[1][threadIdx.x] = s2;
+  __syncthreads();
+  if (lane == 0 && c < C) {
+    for (int l = 1; l < lanes; ++l) {
+      s1 += sh[0][l * Cp + c];
+      s2 += sh[1][l * Cp + c];
+    }
+    part[((int64_t)blockIdx.x * 2 + 0) * C + c] = s1;
+    part[((int64_t)blockIdx.x * 2 + 1) * C + c] = s2;
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ part, int nparts, int C, int64_t M, float* __restrict__ mean,
+                                   float* __restrict__ inv, float* __restrict__ rm, float* __restrict__ rv) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int i = 0; i < nparts; ++i) {
+    s += part[((int64_t)i * 2 + 0) * C + c];
+    q += part[((int64_t)i * 2 + 1) * C + c];
+  }
+  const double mu = s / (double)M;
+  double var = q / (double)M - mu * mu;
+  if (var < 0.0) var = 0.0;
+  mean[c] = (float)mu;
+  inv[c] = (float)(1.0 / sqrt(var + (double)kBnEps));
+  if (rm) rm[c] = (1.f - kBnMomentum) * rm[c] + kBnMomentum * (float)mu;
+  if (rv) rv[c] = (1.f - kBnMomentum) * rv[c] + kBnMomentum * (float)(var * (double)M / (double)(M > 1 ? M - 1 : 1));
+}
+
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ part, int nparts, int C, int64_t M, float* __restrict__ m1,
+                                       float* __restrict__ m2, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int i = 0; i < nparts; ++i) {
+    s += part[((int64_t)i * 2 + 0) * C + c];
+    q += part[((int64_t)i * 2 + 1) * C + c];
+  }
+  dbeta[c] += (float)s;
+  dgamma[c] += (float)q;
+  m1[c] = (float)(s / (double)M);
+  m2[c] = (float)(q / (double)M);
+}
+
+__global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ Y, const float* __restrict__ mean,
+                                                        const float* __restrict__ inv, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, int64_t total, int C,
+                                                        float* __restrict__ Z) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  Z[i] = (Y[i] - mean[c]) * inv[c] * gamma[c] + beta[c];
+}
+
+// dY = inv * gamma * (g - mean(g) - xhat * mean(g * xhat)), then the ReLU in front of the BatchNorm
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ G, const float* __restrict__ Y,
+                                                            const float* __restrict__ mean, const float* __restrict__ inv,
+                                                            const float* __restrict__ gamma, const float* __restrict__ m1,
+                                                            const float* __restrict__ m2, int64_t total, int C, int relu,
+                                                            float* __restrict__ dY) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const float y = Y[i];
+  const float xh = (y - mean[c]) * inv[c];
+  const float d = inv[c] * gamma[c] * (G[i] - m1[c] - xh * m2[c]);
+  dY[i] = (relu && !(y > 0.f)) ? 0.f : d;
+}
+
+// ------------------------------------------------------------------ workspace
+struct MlpInst {
+  float* y[PGMP_MAX_LAYERS];      // output of Linear (+ ReLU) l
+  float* z[PGMP_MAX_LAYERS];      // BatchNorm output (bn[l])
+  float* mean[PGMP_MAX_LAYERS];
+  float* inv[PGMP_MAX_LAYERS];
+  const float* out(const pgmp_mlp_train& m) const { return m.bn[m.n_layers - 1] ? z[m.n_layers - 1] : y[m.n_layers - 1]; }
+  const float* act(const pgmp_mlp_train& m, int l) const { return m.bn[l] ? z[l] : y[l]; }
+};
+
+struct TrainWs {
+  int32_t *dst_ptr, *dst_perm, *src_ptr, *src_perm, *cnt, *bad;
+  MlpInst node_emb, edge_emb;
+  MlpInst edge_head[kMaxOut], node_head[kMaxOut], class_head[kMaxOut];
+  float *hid[kMaxSteps], *g[kMaxSteps], *m[kMaxSteps], *agg[kMaxSteps], *h[kMaxSteps];
+  float *tab_p, *tab_q, *tab_r;
+  float *dh, *dhp, *dh0, *tn1, *tn2, *tn3, *dg, *dg0, *be1, *be2, *ga, *gb;
+  double* bn_part;
+  float *bn_m1, *bn_m2, *part, *partb;
+  uint64_t bytes;
+};
+
+inline int n_out_of(const pgmp_mpn_train_params& p) {
+  const int first = p.steps - p.aux_loss_steps - 1 > 0 ? p.steps - p.aux_loss_steps - 1 : 0;   // NodeClassificationMPNSimple.py:81
+  return p.steps - first;
+}
+
+MlpInst carve_mlp(Carver& c, const pgmp_mlp_train& m, uint64_t M, float* final_out) {
+  MlpInst inst{};
+  for (int l = 0; l < m.n_layers; ++l) {
+    const uint64_t O = (uint64_t)m.dims[l + 1];
+    const bool last = l == m.n_layers - 1;
+    inst.y[l] = (last && final_out && !m.bn[l]) ? final_out : c.take<float>(M * O);
+    if (m.bn[l]) {
+      inst.z[l] = (last && final_out) ? final_out : c.take<float>(M * O);
+      inst.mean[l] = c.take<float>(O);
+      inst.inv[l] = c.take<float>(O);
+    }
+  }
+  return inst;
+}
+
+TrainWs carve_train(const pgmp_mpn_train_params& p) {
+  Carver c(p.workspace);
+  TrainWs w{};
+  const uint64_t N = (uint64_t)p.num_nodes, E = (uint64_t)p.num_edges;
+  w.dst_ptr = c.take<int32_t>(N + 1);
+  w.src_ptr = c.take<int32_t>(N + 1);
+  w.dst_perm = c.take<int32_t>(E);
+  w.src_perm = c.take<int32_t>(E);
+  w.cnt = c.take<int32_t>(N);
+  w.bad = c.take<int32_t>(1);
+  w.node_emb = carve_mlp(c, p.node_emb, N, nullptr);
+  w.edge_emb = carve_mlp(c, p.edge_emb, E, nullptr);
+  const int n_out = n_out_of(p);
+  for (int s = 0; s < p.steps && s < kMaxSteps; ++s) {
+    w.hid[s] = c.take<float>(E * kD);
+    w.g[s] = c.take<float>(E * kD);
+    w.m[s] = c.take<float>(E * kD);
+    w.agg[s] = c.take<float>(N * kD);
+    w.h[s] = p.has_update_mlp ? c.take<float>(N * kD) : w.agg[s];
+  }
+  for (int k = 0; k < n_out && k < kMaxOut; ++k) {
+    w.edge_head[k] = carve_mlp(c, p.edge_head, E, p.edge_logits ? p.edge_logits + (uint64_t)k * E : nullptr);
+    w.node_head[k] = carve_mlp(c, p.node_head, N, p.node_logits ? p.node_logits + (uint64_t)k * N : nullptr);
+    w.class_head[k] = carve_mlp(c, p.class_head, N, p.class_logits ? p.class_logits + (uint64_t)k * N * p.num_classes : nullptr);
+  }
+  w.tab_p = c.take<float>(N * kD);
+  w.tab_q = c.take<float>(N * kD);
+  w.tab_r = c.take<float>(N * kD);
+  w.dh = c.take<float>(N * kD);
+  w.dhp = c.take<float>(N * kD);
+  w.dh0 = c.take<float>(N * kD);
+  w.tn1 = c.take<float>(N * kD);
+  w.tn2 = c.take<float>(N * kD);
+  w.tn3 = c.take<float>(N * kD);
+  w.dg = c.take<float>(E * kD);
+  w.dg0 = c.take<float>(E * kD);
+  w.be1 = c.take<float>(E * kD);
+  w.be2 = c.take<float>(E * kD);
+  const uint64_t rows = N > E ? N : E;
+  w.ga = c.take<float>(rows * kMaxWidth);
+  w.gb = c.take<float>(rows * kMaxWidth);
+  w.bn_part = c.take<double>((uint64_t)kMaxSplits * 2 * kMaxWidth);
+  w.bn_m1 = c.take<float>(kMaxWidth);
+  w.bn_m2 = c.take<float>(kMaxWidth);
+  w.part = c.take<float>((uint64_t)kMaxSplits * kMaxWidth * kMaxWidth);
+  w.partb = c.take<float>((uint64_t)kMaxSplits * kMaxWidth);
+  w.bytes = c.bytes();
+  return w;
+}
+
+// ------------------------------------------------------------------ launch helpers
+inline unsigned blocks_for(int64_t n, int per = 256) { return (unsigned)ceil_div<int64_t>(n > 0 ? n : 1, per); }
+
+int launch_fwd(cudaStream_t st, const ASrc& a, int64_t M, const float* W, int ldw, int coloff, const float* bias, int O,
+               int relu, float* Y, const float* add1 = nullptr, const int64_t* idx1 = nullptr, const float* add2 = nullptr,
+               const int64_t* idx2 = nullptr) {
+  if (M <= 0) return PGMP_OK;
+  FwdArgs g{a, M, src_width(a), O, W, ldw, coloff, bias, add1, idx1, add2, idx2, relu, Y, O};
+  PGMP_LAUNCH(lin_fwd_kernel, dim3(blocks_for(M, BM), (unsigned)ceil_div(O, BN)), 256, 0, st, g);
+  return PGMP_OK;
+}
+
+int launch_bwd_in(cudaStream_t st, const float* dY, int O, int64_t M, const float* W, int ldw, int coloff, int K, Target t0,
+                  const Target* t1 = nullptr) {
+  if (M <= 0) return PGMP_OK;
+  BwdInArgs g{dY, O, M, O, K, W, ldw, coloff, t1 ? 2 : 1, {t0, t1 ? *t1 : Target{nullptr, 0, 0, 0, 0}}};
+  PGMP_LAUNCH(lin_bwd_in_kernel, dim3(blocks_for(M, BM), (unsigned)ceil_div(K, BN)), 256, 0, st, g);
+  return PGMP_OK;
+}
+
+// dW[:, coloff : coloff + K] += dY^T A (and db += column sums of dY when db != null)
+int launch_bwd_w(cudaStream_t st, const TrainWs& w, const float* dY, int O, const ASrc& a, int64_t M, float* dW, int ldw,
+                 int coloff, float* db) {
+  if (M <= 0) return PGMP_OK;
+  const int K = src_width(a);
+  int splits = (int)ceil_div<int64_t>(M, 512);
+  if (splits > kMaxSplits) splits = kMaxSplits;
+  const int64_t rows = round_up<int64_t>(ceil_div<int64_t>(M, splits), BK);
+  splits = (int)ceil_div<int64_t>(M, rows);
+  BwdWArgs g{dY, O, O, a, K, M, rows, w.part, db ? w.partb : nullptr};
+  PGMP_LAUNCH(lin_bwd_w_kernel, dim3((unsigned)ceil_div(K, BN), (unsigned)ceil_div(O, BN), (unsigned)splits), 256, 0, st, g);
+  PGMP_LAUNCH(reduce_parts_kernel, blocks_for((int64_t)O * K), 256, 0, st, w.part, db ? w.partb : nullptr, splits, O, K, dW,
+              ldw, coloff, db);
+  return PGMP_OK;
+}
+
+int bn_partials(cudaStream_t st, const TrainWs& w, const float* Y, const float* G, const float* mean, const float* inv,
+                int64_t M, int C, int* nparts) {
+  int Cp = 32;
+  while (Cp < C) Cp <<= 1;
+  int n = (int)ceil_div<int64_t>(M, 256);
+  if (n > kMaxSplits) n = kMaxSplits;
+  if (n < 1) n = 1;
+  const int64_t rows = ceil_div<int64_t>(M, n);
+  n = (int)ceil_div<int64_t>(M, rows);
+  PGMP_LAUNCH(bn_partial_kernel, (unsigned)n, 256, 0, st, Y, G, mean, inv, M, C, Cp, rows, w.bn_part);
+  *nparts = n;
+  return PGMP_OK;
+}
+
+#define PGMP_TRY(expr)                  \
+  do {                                  \
+    int _r = (expr);                    \
+    if (_r != PGMP_OK) return _r;       \
+  } while (0)
+
+int mlp_forward(cudaStream_t st, const TrainWs& w, const pgmp_mlp_train& m, const MlpInst& inst, ASrc input, int64_t M,
+                const float* params) {
+  if (M <= 0) return PGMP_OK;
+  ASrc cur = input;
+  for (int l = 0; l < m.n_layers; ++l) {
+    const int K = m.dims[l], O = m.dims[l + 1];
+    PGMP_TRY(launch_fwd(st, cur, M, params + m.w[l], K, 0, params + m.b[l], O, m.relu[l], inst.y[l]));
+    if (m.bn[l]) {
+      int nparts = 0;
+      PGMP_TRY(bn_partials(st, w, inst.y[l], nullptr, nullptr, nullptr, M, O, &nparts));
+      PGMP_LAUNCH(bn_finalize_kernel, 1, kMaxWidth, 0, st, w.bn_part, nparts, O, M, inst.mean[l], inst.inv[l],
+                  m.running_mean[l], m.running_var[l]);
+      PGMP_LAUNCH(bn_apply_kernel, blocks_for(M * O), 256, 0, st, inst.y[l], inst.mean[l], inst.inv[l], params + m.gamma[l],
+                  params + m.beta[l], M * O, O, inst.z[l]);
+    }
+    cur = src1(inst.act(m, l), O);
+  }
+  return PGMP_OK;
+}
+
+// reverse pass of one _make_mlp chain; the gradient of the input goes to `t0` / `t1` (nt = 0: not needed)
+int mlp_backward(cudaStream_t st, const TrainWs& w, const pgmp_mlp_train& m, const MlpInst& inst, ASrc input, int64_t M,
+                 const float* params, float* grads, const float* d_out, int nt, Target t0, Target t1) {
+  if (M <= 0) return PGMP_OK;
+  const float* g = d_out;
+  float* bufs[2] = {w.ga, w.gb};
+  int which = 0;
+  for (int l = m.n_layers - 1; l >= 0; --l) {
+    const int K = m.dims[l], O = m.dims[l + 1];
+    if (m.bn[l]) {
+      int nparts = 0;
+      PGMP_TRY(bn_partials(st, w, inst.y[l], g, inst.mean[l], inst.inv[l], M, O, &nparts));
+      PGMP_LAUNCH(bn_bwd_finalize_kernel, 1, kMaxWidth, 0, st, w.bn_part, nparts, O, M, w.bn_m1, w.bn_m2,
+                  grads + m.gamma[l], grads + m.beta[l]);
+      PGMP_LAUNCH(bn_bwd_apply_kernel, blocks_for(M * O), 256, 0, st, g, inst.y[l], inst.mean[l], inst.inv[l],
+                  params + m.gamma[l], w.bn_m1, w.bn_m2, M * O, O, m.relu[l], bufs[which]);
+      g = bufs[which];
+      which ^= 1;
+    } else if (m.relu[l]) {
+      PGMP_LAUNCH(relu_mask_kernel, blocks_for(M * O), 256, 0, st, g, inst.y[l], bufs[which], M * O);
+      g = bufs[which];
+      which ^= 1;
+    }
+    const ASrc in = l == 0 ? input : src1(inst.act(m, l - 1), K);
+    PGMP_TRY(launch_bwd_w(st, w, g, O, in, M, grads + m.w[l], K, 0, grads + m.b[l]));
+    if (l > 0) {
+      PGMP_TRY(launch_bwd_in(st, g, O, M, params + m.w[l], K, 0, K, Target{bufs[which], K, 0, K, 0}));
+      g = bufs[which];
+      which ^= 1;
+    } else if (nt > 0) {
+      PGMP_TRY(launch_bwd_in(st, g, O, M, params + m.w[l], K, 0, K, t0, nt > 1 ? &t1 : nullptr));
+    }
+  }
+  return PGMP_OK;
+}
+
+int build_csr(cudaStream_t st, const TrainWs& w, const int64_t* key, int64_t E, int64_t N, int32_t* ptr, int32_t* perm) {
+  PGMP_CUDA(cudaMemsetAsync(w.cnt, 0, sizeof(int32_t) * N, st));
+  if (E > 0) PGMP_LAUNCH(csr_count_kernel, blocks_for(E), 256, 0, st, key, E, N, w.cnt, w.bad);
+  PGMP_LAUNCH(csr_scan_kernel, 1, 1024, 0, st, w.cnt, N, ptr);
+  PGMP_CUDA(cudaMemsetAsync(w.cnt, 0, sizeof(int32_t) * N, st));
+  if (E > 0) {
+    PGMP_LAUNCH(csr_fill_kernel, blocks_for(E), 256, 0, st, key, E, N, ptr, w.cnt, perm);
+    PGMP_LAUNCH(csr_sort_kernel, blocks_for(N), 256, 0, st, ptr, N, perm);
+  }
+  return PGMP_OK;
+}
+
+int validate_mlp(const pgmp_mlp_train& m, const char* name, int in_dim, int out_dim) {
+  if (m.n_layers < 1 || m.n_layers > PGMP_MAX_LAYERS) return set_error(PGMP_ERR_INVALID, "%s: %d layers", name, m.n_layers);
+  for (int l = 0; l <= m.n_layers; ++l)
+    if (m.dims[l] < 1 || m.dims[l] > kMaxWidth) return set_error(PGMP_ERR_INVALID, "%s: width %d outside [1, %d]", name, m.dims[l], kMaxWidth);
+  if (in_dim > 0 && m.dims[0] != in_dim) return set_error(PGMP_ERR_INVALID, "%s: input width %d, expected %d", name, m.dims[0], in_dim);
+  if (m.dims[m.n_layers] != out_dim) return set_error(PGMP_ERR_INVALID, "%s: output width %d, expected %d", name, m.dims[m.n_layers], out_dim);
+  return PGMP_OK;
+}
+
+int validate_train(const pgmp_mpn_train_params* p, bool backward) {
+  if (!p) return set_error(PGMP_ERR_INVALID, "null params");
+  if (p->num_nodes <= 0 || p->num_edges < 0) return set_error(PGMP_ERR_INVALID, "bad graph size N=%lld E=%lld", (long long)p->num_nodes, (long long)p->num_edges);
+  if (p->num_nodes > (1ll << 30) || p->num_edges > (1ll << 30)) return set_error(PGMP_ERR_INVALID, "graph too large for 32-bit bins");
+  if (p->dim != kD) return set_error(PGMP_ERR_INVALID, "NODE/EDGE_FEATURE_DIM must be 64, got %d", p->dim);
+  if (p->steps < 1 || p->steps > kMaxSteps) return set_error(PGMP_ERR_INVALID, "STEPS %d outside [1, %d]", p->steps, kMaxSteps);
+  if (p->aux_loss_steps < 0 || n_out_of(*p) > kMaxOut) return set_error(PGMP_ERR_INVALID, "AUX_LOSS_STEPS %d", p->aux_loss_steps);
+  if (p->aggr < 0 || p->aggr > 2) return set_error(PGMP_ERR_INVALID, "aggr %d", p->aggr);
+  if (p->num_classes < 1 || p->num_classes > kMaxWidth) return set_error(PGMP_ERR_INVALID, "num_classes %d", p->num_classes);
+  PGMP_TRY(validate_mlp(p->node_emb, "node_embedding", 0, kD));
+  PGMP_TRY(validate_mlp(p->edge_emb, "edge_embedding", 0, kD));
+  PGMP_TRY(validate_mlp(p->edge_head, "edge_classification", kD, 1));
+  PGMP_TRY(validate_mlp(p->node_head, "node_classification", kD, 1));
+  PGMP_TRY(validate_mlp(p->class_head, "classification", kD, p->num_classes));
+  if (!p->x || !p->params || !p->node_logits || !p->class_logits || !p->workspace) return set_error(PGMP_ERR_INVALID, "null device pointer");
+  if (p->num_edges > 0 && (!p->edge_attr || !p->edge_index || !p->edge_logits)) return set_error(PGMP_ERR_INVALID, "null edge pointer");
+  if (backward) {
+    if (!p->grads || !p->d_node_logits || !p->d_class_logits || (p->num_edges > 0 && !p->d_edge_logits))
+      return set_error(PGMP_ERR_INVALID, "backward: null gradient pointer");
+  }
+  return PGMP_OK;
+}
+
+}  // namespace
+
+// ================================================================== forward
+int mpn_train_forward(const pgmp_mpn_train_params& p, cudaStream_t st) {
+  const TrainWs w = carve_train(p);
+  if (w.bytes > p.workspace_bytes)
+    return set_error(PGMP_ERR_INVALID, "workspace too small: %llu < %llu", (unsigned long long)p.workspace_bytes, (unsigned long long)w.bytes);
+  const int64_t N = p.num_nodes, E = p.num_edges;
+  const float* P = p.params;
+  const int64_t* src = p.edge_index;
+  const int64_t* dst = p.edge_index + E;
+  const int nd = p.skip ? 2 * kD : kD, ed = nd;
+  const int ld1 = 2 * nd + ed, ldm = nd + kD;
+
+  PGMP_CUDA(cudaMemsetAsync(w.bad, 0, sizeof(int32_t), st));
+  PGMP_TRY(build_csr(st, w, dst, E, N, w.dst_ptr, w.dst_perm));
+  PGMP_TRY(build_csr(st, w, src, E, N, w.src_ptr, w.src_perm));
+
+  PGMP_TRY(mlp_forward(st, w, p.node_emb, w.node_emb, src1(p.x, p.node_emb.dims[0]), N, P));          // :65
+  PGMP_TRY(mlp_forward(st, w, p.edge_emb, w.edge_emb, src1(p.edge_attr, p.edge_emb.dims[0]), E, P));   // :66
+  const float* h0 = w.node_emb.out(p.node_emb);
+  const float* g0 = w.edge_emb.out(p.edge_emb);
+  const int first = p.steps - n_out_of(p);
+  for (int s = 0; s < p.steps; ++s) {
+    const float* hp = s ? w.h[s - 1] : h0;
+    const float* gp = s ? w.g[s - 1] : g0;
+    const ASrc xs = p.skip ? src2(h0, hp, kD) : src1(hp, kD);      // :76-78
+    const ASrc es = p.skip ? src2(g0, gp, kD) : src1(gp, kD);
+    // mlp_edge (layers.py:66): hidden = ReLU(W1 [x_i ; x_j ; e] + b1), g' = ReLU(W2 hidden + b2)
+    PGMP_TRY(launch_fwd(st, xs, N, P + p.w1, ld1, 0, nullptr, kD, 0, w.tab_p));
+    PGMP_TRY(launch_fwd(st, xs, N, P + p.w1, ld1, nd, nullptr, kD, 0, w.tab_q));
+    PGMP_TRY(launch_fwd(st, es, E, P + p.w1, ld1, 2 * nd, P + p.b1, kD, 1, w.hid[s], w.tab_p, dst, w.tab_q, src));
+    PGMP_TRY(launch_fwd(st, src1(w.hid[s], kD), E, P + p.w2, kD, 0, P + p.b2, kD, 1, w.g[s]));
+    // message (layers.py:74-77): m = ReLU(Wm [x_i ; g'] + bm); aggregate over the target
+    PGMP_TRY(launch_fwd(st, xs, N, P + p.wm, ldm, 0, P + p.bm, kD, 0, w.tab_r));
+    PGMP_TRY(launch_fwd(st, src1(w.g[s], kD), E, P + p.wm, ldm, nd, nullptr, kD, 1, w.m[s], w.tab_r, dst));
+    PGMP_LAUNCH(aggregate_fwd_kernel, blocks_for(N, 4), 256, 0, st, w.m[s], w.dst_ptr, w.dst_perm, N, p.aggr, w.agg[s]);
+    if (p.has_update_mlp)                                            // layers.py:79-82
+      PGMP_TRY(launch_fwd(st, src1(w.agg[s], kD), N, P + p.wu, kD, 0, P + p.bu, kD, 1, w.h[s]));
+    if (s >= first) {                                                // :81-84
+      const int k = s - first;
+      PGMP_TRY(mlp_forward(st, w, p.node_head, w.node_head[k], src1(w.h[s], kD), N, P));
+      PGMP_TRY(mlp_forward(st, w, p.class_head, w.class_head[k], src1(w.h[s], kD), N, P));
+      PGMP_TRY(mlp_forward(st, w, p.edge_head, w.edge_head[k], src1(w.g[s], kD), E, P));
+    }
+  }
+  return PGMP_OK;
+}
+
+// ================================================================== backward
+int mpn_train_backward(const pgmp_mpn_train_params& p, cudaStream_t st) {
+  const TrainWs w = carve_train(p);
+  if (w.bytes > p.workspace_bytes)
+    return set_error(PGMP_ERR_INVALID, "workspace too small: %llu < %llu", (unsigned long long)p.workspace_bytes, (unsigned long long)w.bytes);
+  const int64_t N = p.num_nodes, E = p.num_edges;
+  const float* P = p.params;
+  float* G = p.grads;
+  const int nd = p.skip ? 2 * kD : kD, ed = nd;
+  const int ld1 = 2 * nd + ed, ldm = nd + kD;
+  const int J = p.num_classes;
+  const float* h0 = w.node_emb.out(p.node_emb);
+  const float* g0 = w.edge_emb.out(p.edge_emb);
+  const int first = p.steps - n_out_of(p);
+  const int64_t nN = N * kD, nE = E * kD;
+
+  float* dh = w.dh;     // gradient of h_s (complete once the heads of step s have been added)
+  float* dhp = w.dhp;   // gradient of h_{s-1} collected during step s
+  PGMP_CUDA(cudaMemsetAsync(dh, 0, sizeof(float) * nN, st));
+  PGMP_CUDA(cudaMemsetAsync(w.dh0, 0, sizeof(float) * nN, st));
+  if (E > 0) {
+    PGMP_CUDA(cudaMemsetAsync(w.dg, 0, sizeof(float) * nE, st));
+    PGMP_CUDA(cudaMemsetAsync(w.dg0, 0, sizeof(float) * nE, st));
+  }
+  const Target none{nullptr, 0, 0, 0, 0};
+  for (int s = p.steps - 1; s >= 0; --s) {
+    const float* hp = s ? w.h[s - 1] : h0;
+    const float* gp = s ? w.g[s - 1] : g0;
+    const ASrc xs = p.skip ? src2(h0, hp, kD) : src1(hp, kD);
+    const ASrc es = p.skip ? src2(g0, gp, kD) : src1(gp, kD);
+    if (s >= first) {
+      const int k = s - first;
+      PGMP_TRY(mlp_backward(st, w, p.edge_head, w.edge_head[k], src1(w.g[s], kD), E, P, G, p.d_edge_logits + (int64_t)k * E, 1,
+                            Target{w.dg, kD, 0, kD, 1}, none));
+      PGMP_TRY(mlp_backward(st, w, p.node_head, w.node_head[k], src1(w.h[s], kD), N, P, G, p.d_node_logits + (int64_t)k * N, 1,
+                            Target{dh, kD, 0, kD, 1}, none));
+      PGMP_TRY(mlp_backward(st, w, p.class_head, w.class_head[k], src1(w.h[s], kD), N, P, G,
+                            p.d_class_logits + (int64_t)k * N * J, 1, Target{dh, kD, 0, kD, 1}, none));
+    }
+    // update_mlp
+    const float* dagg = dh;
+    if (p.has_update_mlp) {
+      PGMP_LAUNCH(relu_mask_kernel, blocks_for(nN), 256, 0, st, dh, w.h[s], w.tn1, nN);
+      PGMP_TRY(launch_bwd_w(st, w, w.tn1, kD, src1(w.agg[s], kD), N, G + p.wu, kD, 0, G + p.bu));
+      PGMP_TRY(launch_bwd_in(st, w.tn1, kD, N, P + p.wu, kD, 0, kD, Target{w.tn2, kD, 0, kD, 0}));
+      dagg = w.tn2;
+    }
+    PGMP_CUDA(cudaMemsetAsync(dhp, 0, sizeof(float) * nN, st));
+    const Target tx0{p.skip ? w.dh0 : dhp, kD, 0, kD, 1};        // columns of x = [h0 ; h_{s-1}] (or just h_{s-1})
+    const Target tx1{dhp, kD, kD, kD, 1};
+    if (E > 0) {
+      // aggregation and the ReLU of the message
+      float* dm = w.be1;
+      PGMP_LAUNCH(aggregate_bwd_kernel, blocks_for(N, 4), 256, 0, st, dagg, w.m[s], w.agg[s], w.dst_ptr, w.dst_perm, N, p.aggr, dm);
+      PGMP_LAUNCH(relu_mask_kernel, blocks_for(nE), 256, 0, st, dm, w.m[s], dm, nE);
+      // mlp_node: edge columns per edge, node columns through the per-target sums
+      PGMP_LAUNCH(seg_sum_kernel, blocks_for(N, 4), 256, 0, st, dm, w.dst_ptr, w.dst_perm, N, w.tn3);
+      PGMP_TRY(launch_bwd_w(st, w, dm, kD, src1(w.g[s], kD), E, G + p.wm, ldm, nd, nullptr));
+      PGMP_TRY(launch_bwd_w(st, w, w.tn3, kD, xs, N, G + p.wm, ldm, 0, G + p.bm));
+      PGMP_TRY(launch_bwd_in(st, w.tn3, kD, N, P + p.wm, ldm, 0, nd, tx0, p.skip ? &tx1 : nullptr));
+      PGMP_TRY(launch_bwd_in(st, dm, kD, E, P + p.wm, ldm, nd, kD, Target{w.dg, kD, 0, kD, 1}));
+      // mlp_edge.2
+      PGMP_LAUNCH(relu_mask_kernel, blocks_for(nE), 256, 0, st, w.dg, w.g[s], w.dg, nE);
+      PGMP_TRY(launch_bwd_w(st, w, w.dg, kD, src1(w.hid[s], kD), E, G + p.w2, kD, 0, G + p.b2));
+      float* dhid = w.be2;
+      PGMP_TRY(launch_bwd_in(st, w.dg, kD, E, P + p.w2, kD, 0, kD, Target{dhid, kD, 0, kD, 0}));
+      PGMP_LAUNCH(relu_mask_kernel, blocks_for(nE), 256, 0, st, dhid, w.hid[s], dhid, nE);
+      // mlp_edge.0
+      PGMP_LAUNCH(seg_sum_kernel, blocks_for(N, 4), 256, 0, st, dhid, w.dst_ptr, w.dst_perm, N, w.tn1);
+      PGMP_LAUNCH(seg_sum_kernel, blocks_for(N, 4), 256, 0, st, dhid, w.src_ptr, w.src_perm, N, w.tn2);
+      PGMP_TRY(launch_bwd_w(st, w, dhid, kD, es, E, G + p.w1, ld1, 2 * nd, nullptr));
+      PGMP_TRY(launch_bwd_w(st, w, w.tn1, kD, xs, N, G + p.w1, ld1, 0, G + p.b1));
+      PGMP_TRY(launch_bwd_w(st, w, w.tn2, kD, xs, N, G + p.w1, ld1, nd, nullptr));
+      PGMP_TRY(launch_bwd_in(st, w.tn1, kD, N, P + p.w1, ld1, 0, nd, tx0, p.skip ? &tx1 : nullptr));
+      PGMP_TRY(launch_bwd_in(st, w.tn2, kD, N, P + p.w1, ld1, nd, nd, tx0, p.skip ? &tx1 : nullptr));
+      // e = [g0 ; g_{s-1}]: the gradient of g_{s-1} replaces dg (dg of step s is consumed)
+      const Target te0{p.skip ? w.dg0 : w.dg, kD, 0, kD, p.skip ? 1 : 0};
+      const Target te1{w.dg, kD, kD, kD, 0};
+      PGMP_TRY(launch_bwd_in(st, dhid, kD, E, P + p.w1, ld1, 2 * nd, ed, te0, p.skip ? &te1 : nullptr));
+    }
+    float* tmp = dh;
+    dh = dhp;
+    dhp = tmp;
+  }
+  // h_{-1} = h0, g_{-1} = g0
+  PGMP_LAUNCH(add_into_kernel, blocks_for(nN), 256, 0, st, w.dh0, dh, nN);
+  if (E > 0) PGMP_LAUNCH(add_into_kernel, blocks_for(nE), 256, 0, st, w.dg0, w.dg, nE);
+  const int xin = p.node_emb.dims[0];
+  PGMP_TRY(mlp_backward(st, w, p.node_emb, w.node_emb, src1(p.x, xin), N, P, G, w.dh0, p.grad_x ? 1 : 0,
+                        Target{p.grad_x, xin, 0, xin, 0}, none));
+  PGMP_TRY(mlp_backward(st, w, p.edge_emb, w.edge_emb, src1(p.edge_attr, p.edge_emb.dims[0]), E, P, G, w.dg0, 0, none, none));
+  return PGMP_OK;
+}
+
+}  // namespace pgmp
+
+using namespace pgmp;
+
+extern "C" uint64_t pgmp_mpn_train_workspace_bytes(const pgmp_mpn_train_params* p) {
+  if (!p || p->num_nodes <= 0 || p->num_edges < 0 || p->steps < 1 || p->steps > kMaxSteps) return 0;
+  pgmp_mpn_train_params q = *p;
+  q.workspace = nullptr;
+  return carve_train(q).bytes;
+}
+
+extern "C" int pgmp_mpn_train_forward(const pgmp_mpn_train_params* p, pgmp_stream_t stream) {
+  const int rc = validate_train(p, false);
+  if (rc != PGMP_OK) return rc;
+  return mpn_train_forward(*p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int pgmp_mpn_train_backward(const pgmp_mpn_train_params* p, pgmp_stream_t stream) {
+  const int rc = validate_train(p, true);
+  if (rc != PGMP_OK) return rc;
+  return mpn_train_backward(*p, static_cast<cudaStream_t>(stream));
+}

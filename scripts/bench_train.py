@@ -1,0 +1,115 @@
+"""Training-step measurement (BASELINE.json configs[4]): class_agnostic_end2end shape --
+agnostic MPLayer, max aggregation, skip, 10 steps -- on 8 synthetic 256x256 images per GPU (the train-time
+``forward`` path works on the half-resolution maps), 30 candidates per joint, kNN-50 graph.
+
+One step = graph construction (CUDA) -> MPN forward in train() mode (CUDA, BatchNorm batch statistics) -> a focal-free
+stand-in loss (BCE-with-logits / cross-entropy on random labels: the reference's losses and label construction are
+outside the hot path) -> reverse pass (CUDA) -> ONE all-reduce of the 101 203-parameter gradient bucket (NCCL) -> Adam.
+Timed on the device with CUDA events, max over ranks; rank 0 prints one JSON line.
+
+    python scripts/bench_train.py [--steps 10 --warmup 3 --batch 8]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 scripts/bench_train.py
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+import pgmp_b200  # noqa: E402
+import pgmp_b200._native as nv  # noqa: E402
+import pgmp_b200.parallel as par  # noqa: E402
+import pgmp_b200.synthetic as synthetic  # noqa: E402
+from pgmp_b200.graph_constructor import get_graph_constructor  # noqa: E402
+from pgmp_b200.Models.MessagePassingNetwork import get_mpn_model  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--mpn-steps", type=int, default=10)
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    J, K = 17, 30
+    data = synthetic.synth_batch(args.batch, J, args.size, K, persons=8, first_index=rank * args.batch)
+    t = {k: torch.from_numpy(v).to(dev) for k, v in data.items()}
+    gcfg = pgmp_b200.config.bench_gc_config(k=K, graph_type="knn")
+    mcfg = pgmp_b200.config.agnostic_mpn_config(J, STEPS=args.mpn_steps)
+    model = synthetic.synth_mpn_state_dict(get_mpn_model(mcfg), 0).to(dev).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    gen = torch.Generator(device=dev).manual_seed(rank)
+    ev = {k: [torch.cuda.Event(enable_timing=True) for _ in range(2)] for k in ("gc", "fwd", "bwd", "ar", "step")}
+    acc = {k: 0.0 for k in ev}
+    info = {}
+
+    def step(timed):
+        ev["step"][0].record()
+        ev["gc"][0].record()
+        ret = get_graph_constructor(gcfg, scoremaps=t["scoremaps"], tagmaps=t["tagmaps"], features=t["features"], joints_gt=None,
+                                    factor_list=None, masks=None, device=dev, testing=False, heatmaps=None,
+                                    num_joints=J).construct_graph()
+        x, edge_attr, edge_index, joint_det = ret[0], ret[1], ret[2], ret[7]
+        ev["gc"][1].record()
+        N, E = x.shape[0], edge_index.shape[1]
+        info.update(nodes=N, edges=E)
+        ev["fwd"][0].record()
+        pe, pn, pc, _ = model(x, edge_attr, edge_index, node_types=joint_det[:, 2])
+        ev["fwd"][1].record()
+        loss = (F.binary_cross_entropy_with_logits(pe[-1], (torch.rand(E, device=dev, generator=gen) < 0.1).float())
+                + F.binary_cross_entropy_with_logits(pn[-1], (torch.rand(N, device=dev, generator=gen) < 0.5).float())
+                + F.cross_entropy(pc[-1], joint_det[:, 2]))
+        opt.zero_grad(set_to_none=True)
+        ev["bwd"][0].record()
+        loss.backward()
+        ev["bwd"][1].record()
+        ev["ar"][0].record()
+        info["allreduce_bytes"] = par.allreduce_gradients(model.parameters())
+        ev["ar"][1].record()
+        opt.step()
+        ev["step"][1].record()
+        torch.cuda.synchronize()
+        if timed:
+            for k in ev:
+                acc[k] += ev[k][0].elapsed_time(ev[k][1])
+        return float(loss)
+
+    for _ in range(args.warmup):
+        step(False)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = nv.kernel_launches()
+    losses = [step(True) for _ in range(args.steps)]
+    launches = nv.kernel_launches() - launches0
+    ms = {k: par.max_over_ranks(v / args.steps, dev) for k, v in acc.items()}
+    if rank == 0:
+        imgs = args.batch * world
+        print(json.dumps({
+            "metric": "training step: images/sec (GC + MPN forward + backward + gradient all-reduce + Adam)",
+            "value": imgs / (ms["step"] * 1e-3), "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms["step"], "ms": ms, "edges_per_s": info["edges"] * world / (ms["step"] * 1e-3),
+            "config": {"workload": "configs[4]: %d synthetic %dx%d images per GPU, agnostic MPLayer (max, skip, %d steps), "
+                                   "kNN-50 graph" % (args.batch, args.size, args.size, args.mpn_steps),
+                       "nodes_per_gpu": info["nodes"], "edges_per_gpu": info["edges"]},
+            "dtype": "f32", "data": "synthetic", "scaling": "weak", "allreduce_bytes": info["allreduce_bytes"],
+            "gpu_launches": launches, "loss_first_last": [losses[0], losses[-1]]}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
