@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--mpn-steps", type=int, default=10)
+    ap.add_argument("--profile", action="store_true", help="after the timed steps: one more step with per-kernel CUDA events")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -85,7 +86,7 @@ def main():
         if timed:
             for k in ev:
                 acc[k] += ev[k][0].elapsed_time(ev[k][1])
-        return float(loss)
+        return float(loss.detach())
 
     for _ in range(args.warmup):
         step(False)
@@ -107,6 +108,13 @@ def main():
                        "nodes_per_gpu": info["nodes"], "edges_per_gpu": info["edges"]},
             "dtype": "f32", "data": "synthetic", "scaling": "weak", "allreduce_bytes": info["allreduce_bytes"],
             "gpu_launches": launches, "loss_first_last": [losses[0], losses[-1]]}))
+    if args.profile and rank == 0:
+        nv.profile(True)
+        step(False)
+        prof = nv.profile_collect()
+        nv.profile(False)
+        for name, (cnt, tot) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+            print("%-28s %5d launches %9.3f ms" % (name, cnt, tot))
     if world > 1:
         dist.destroy_process_group()
 

@@ -8,7 +8,7 @@ import oracle.mpn_train as T
 import pgmp_b200
 from cases import mpn_config_for
 for name in sys.argv[1:]:
-    gc_name, over, seed = m.VARIANTS[name]
+    gc_name, over, seed, _ = m.VARIANTS[name]
     g = m.graph_for(gc_name)
     cfg = mpn_config_for(pgmp_b200.config, "agnostic_mpn_config", over)
     model, sd0, x, pe, pn, pc, coeffs, loss = m.run_cuda(cfg, seed, g)
