@@ -129,11 +129,15 @@ class _MpnTrainFunction(torch.autograd.Function):
         dev = x.device
         lib = nv.lib()
         sizes = [p.numel() for p in params]
-        offsets, off = {}, 0
-        for n, k in zip(names, sizes):
+        offsets, off, pieces = {}, 0, []
+        pad = torch.zeros(3, dtype=torch.float32, device=dev)
+        for n, k, q in zip(names, sizes, params):      # every tensor starts on a 16-byte boundary (vectorised loads)
             offsets[n] = off
-            off += k
-        flat = torch.cat([p.detach().reshape(-1) for p in params]).contiguous()
+            pieces.append(q.detach().reshape(-1))
+            if k % 4:
+                pieces.append(pad[:4 - k % 4])
+            off += (k + 3) // 4 * 4
+        flat = torch.cat(pieces).contiguous()
         x_ = x.detach().contiguous()
         ea = edge_attr.detach().contiguous()
         ei = edge_index.detach().contiguous()
@@ -169,6 +173,7 @@ class _MpnTrainFunction(torch.autograd.Function):
                 torch.autograd.graph.increment_version((mod.running_mean, mod.running_var))
                 mod.num_batches_tracked += 1
         ctx.p, ctx.sizes, ctx.shapes = p, sizes, [tuple(q.shape) for q in params]
+        ctx.offsets = [offsets[n] for n in names]
         ctx.keep = (flat, x_, ea, ei, ws, edge_logits, node_logits, class_logits)   # the forward's activations live in ws
         ctx.need_x = x.requires_grad
         return edge_logits, node_logits, class_logits
@@ -188,10 +193,7 @@ class _MpnTrainFunction(torch.autograd.Function):
             nv.check(nv.lib().pgmp_mpn_train_backward(p, nv.current_stream()))
             for t in ctx.keep + (de, dn, dc):
                 t.record_stream(torch.cuda.current_stream())
-        out, off = [], 0
-        for k, shape in zip(ctx.sizes, ctx.shapes):
-            out.append(grads[off:off + k].view(shape))
-            off += k
+        out = [grads[off:off + k].view(shape) for off, k, shape in zip(ctx.offsets, ctx.sizes, ctx.shapes)]
         return (None, grad_x, None, None) + tuple(out)
 
 

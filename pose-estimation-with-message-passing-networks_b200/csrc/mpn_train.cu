@@ -23,7 +23,7 @@ namespace {
 
 constexpr int kD = 64;
 constexpr int BM = 64, BN = 64, BK = 16;
-constexpr int kMaxSplits = 256;
+constexpr int kMaxSplits = 512;
 constexpr int kMaxWidth = 128;
 constexpr int kMaxSteps = 64, kMaxOut = 32;
 constexpr float kBnEps = 1e-5f;
@@ -67,6 +67,42 @@ struct FwdArgs {
   int ldy;
 };
 
+// A / dY tile loader shared by the forward and input-gradient kernels: 64 rows x 16 columns starting at column c0.
+// VEC: every row start is 16-byte aligned and the widths are multiples of 4 -> one float4 per thread.
+template <bool VEC>
+__device__ __forceinline__ void load_a_tile(const ASrc& a, int64_t r0, int64_t M, int c0, int K, int t, float (&v)[4]) {
+  if (VEC) {
+    const int64_t gr = r0 + (t >> 2);
+    const int c = c0 + (t & 3) * 4;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gr < M && c < K) {
+      int cc = c;
+      const ASeg* s = &a.s[0];
+      if (cc >= s->w) { cc -= s->w; s = &a.s[1]; }
+      x = *reinterpret_cast<const float4*>(s->p + gr * s->ld + cc);
+    }
+    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+  } else {
+    const int c = c0 + (t & 15);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t gr = r0 + (t >> 4) + 16 * i;
+      v[i] = (gr < M && c < K) ? a_load(a, gr, c) : 0.f;
+    }
+  }
+}
+template <bool VEC>
+__device__ __forceinline__ void store_a_tile(float (*As)[BK + 1], int t, const float (&v)[4]) {
+  if (VEC) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) As[t >> 2][(t & 3) * 4 + i] = v[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) As[(t >> 4) + 16 * i][t & 15] = v[i];
+  }
+}
+
+template <bool VEC>
 __global__ void __launch_bounds__(256) lin_fwd_kernel(const FwdArgs g) {
   __shared__ float As[BM][BK + 1];
   __shared__ __align__(16) float Bs[BK][BN + 4];
@@ -74,17 +110,39 @@ __global__ void __launch_bounds__(256) lin_fwd_kernel(const FwdArgs g) {
   const int64_t r0 = (int64_t)blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
   float acc[4][4] = {};
-  for (int k0 = 0; k0 < g.K; k0 += BK) {
-    const int k = k0 + (t & 15);
+  float va[4], vb[4];
+  // W tile: rows = outputs o, 16 consecutive k (the reduction index is contiguous in Linear.weight)
+  auto load_b = [&](int k0) {
+    if (VEC) {
+      const int o = n0 + (t >> 2), k = k0 + (t & 3) * 4;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (o < g.O && k < g.K) x = *reinterpret_cast<const float4*>(g.W + (int64_t)o * g.ldw + g.coloff + k);
+      vb[0] = x.x; vb[1] = x.y; vb[2] = x.z; vb[3] = x.w;
+    } else {
+      const int k = k0 + (t & 15);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = (t >> 4) + 16 * i;
-      const int64_t gr = r0 + r;
-      As[r][t & 15] = (gr < g.M && k < g.K) ? a_load(g.a, gr, k) : 0.f;
-      const int o = n0 + r;
-      Bs[t & 15][r] = (o < g.O && k < g.K) ? g.W[(int64_t)o * g.ldw + g.coloff + k] : 0.f;
+      for (int i = 0; i < 4; ++i) {
+        const int o = n0 + (t >> 4) + 16 * i;
+        vb[i] = (o < g.O && k < g.K) ? g.W[(int64_t)o * g.ldw + g.coloff + k] : 0.f;
+      }
+    }
+  };
+  load_a_tile<VEC>(g.a, r0, g.M, 0, g.K, t, va);
+  load_b(0);
+  for (int k0 = 0; k0 < g.K; k0 += BK) {
+    store_a_tile<VEC>(As, t, va);
+    if (VEC) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) Bs[(t & 3) * 4 + i][t >> 2] = vb[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) Bs[t & 15][(t >> 4) + 16 * i] = vb[i];
     }
     __syncthreads();
+    if (k0 + BK < g.K) {      // next tile in flight while this one is multiplied
+      load_a_tile<VEC>(g.a, r0, g.M, k0 + BK, g.K, t, va);
+      load_b(k0 + BK);
+    }
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
@@ -123,6 +181,7 @@ __global__ void __launch_bounds__(256) lin_fwd_kernel(const FwdArgs g) {
 struct Target {
   float* p;
   int ld, k0, w, add;   // columns [k0, k0 + w) of dA go to p[r * ld + (k - k0)], overwriting or adding
+  const float* mask;    // same layout as p, or null: the result is zeroed where mask <= 0 (the ReLU in front of p)
 };
 struct BwdInArgs {
   const float* dY;
@@ -135,6 +194,7 @@ struct BwdInArgs {
   Target t[2];
 };
 
+template <bool VEC>
 __global__ void __launch_bounds__(256) lin_bwd_in_kernel(const BwdInArgs g) {
   __shared__ float As[BM][BK + 1];
   __shared__ __align__(16) float Bs[BK][BN + 4];
@@ -142,18 +202,39 @@ __global__ void __launch_bounds__(256) lin_bwd_in_kernel(const BwdInArgs g) {
   const int64_t r0 = (int64_t)blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
   float acc[4][4] = {};
-  for (int o0 = 0; o0 < g.O; o0 += BK) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = (t >> 4) + 16 * i;
-      const int64_t gr = r0 + r;
-      const int o = o0 + (t & 15);
-      As[r][t & 15] = (gr < g.M && o < g.O) ? g.dY[gr * g.ldd + o] : 0.f;
-      const int ob = o0 + (t >> 6) + 4 * i;
+  float va[4], vb[4];
+  const ASrc dy = ASrc{1, {{g.dY, g.ldd, g.O}, {nullptr, 0, 0}}};
+  // W tile: 16 rows (outputs o) x 64 consecutive input columns
+  auto load_b = [&](int o0) {
+    if (VEC) {
+      const int ob = o0 + (t >> 4), k = n0 + (t & 15) * 4;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ob < g.O && k < g.K) x = *reinterpret_cast<const float4*>(g.W + (int64_t)ob * g.ldw + g.coloff + k);
+      vb[0] = x.x; vb[1] = x.y; vb[2] = x.z; vb[3] = x.w;
+    } else {
       const int k = n0 + (t & 63);
-      Bs[(t >> 6) + 4 * i][t & 63] = (ob < g.O && k < g.K) ? g.W[(int64_t)ob * g.ldw + g.coloff + k] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ob = o0 + (t >> 6) + 4 * i;
+        vb[i] = (ob < g.O && k < g.K) ? g.W[(int64_t)ob * g.ldw + g.coloff + k] : 0.f;
+      }
+    }
+  };
+  load_a_tile<VEC>(dy, r0, g.M, 0, g.O, t, va);
+  load_b(0);
+  for (int o0 = 0; o0 < g.O; o0 += BK) {
+    store_a_tile<VEC>(As, t, va);
+    if (VEC) {
+      *reinterpret_cast<float4*>(&Bs[t >> 4][(t & 15) * 4]) = make_float4(vb[0], vb[1], vb[2], vb[3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) Bs[(t >> 6) + 4 * i][t & 63] = vb[i];
     }
     __syncthreads();
+    if (o0 + BK < g.O) {
+      load_a_tile<VEC>(dy, r0, g.M, o0 + BK, g.O, t, va);
+      load_b(o0 + BK);
+    }
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
@@ -172,16 +253,19 @@ __global__ void __launch_bounds__(256) lin_bwd_in_kernel(const BwdInArgs g) {
   for (int j = 0; j < 4; ++j) {
     const int k = n0 + tx * 4 + j;
     if (k >= g.K) continue;
-    const Target* tg = nullptr;
-    if (k >= g.t[0].k0 && k < g.t[0].k0 + g.t[0].w) tg = &g.t[0];
-    else if (g.nt > 1 && k >= g.t[1].k0 && k < g.t[1].k0 + g.t[1].w) tg = &g.t[1];
-    if (!tg) continue;
+    const int which = (k >= g.t[0].k0 && k < g.t[0].k0 + g.t[0].w) ? 0 : ((g.nt > 1 && k >= g.t[1].k0 && k < g.t[1].k0 + g.t[1].w) ? 1 : -1);
+    if (which < 0) continue;
+    float* const tp = which ? g.t[1].p : g.t[0].p;
+    const float* const tm = which ? g.t[1].mask : g.t[0].mask;
+    const int tld = which ? g.t[1].ld : g.t[0].ld, tk0 = which ? g.t[1].k0 : g.t[0].k0, tadd = which ? g.t[1].add : g.t[0].add;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int64_t gr = r0 + ty * 4 + i;
       if (gr >= g.M) continue;
-      float* q = tg->p + gr * tg->ld + (k - tg->k0);
-      *q = tg->add ? *q + acc[i][j] : acc[i][j];
+      const int64_t off = gr * tld + (k - tk0);
+      float v = tadd ? tp[off] + acc[i][j] : acc[i][j];
+      if (tm && !(tm[off] > 0.f)) v = 0.f;
+      tp[off] = v;
     }
   }
 }
@@ -197,6 +281,7 @@ struct BwdWArgs {
   float* partb;   // [splits][O] column sums of dY, or null
 };
 
+template <bool VEC>
 __global__ void __launch_bounds__(256) lin_bwd_w_kernel(const BwdWArgs g) {
   __shared__ __align__(16) float Ds[BK][BN + 4];
   __shared__ __align__(16) float As[BK][BN + 4];
@@ -204,19 +289,52 @@ __global__ void __launch_bounds__(256) lin_bwd_w_kernel(const BwdWArgs g) {
   const int k0 = blockIdx.x * BN, o0 = blockIdx.y * BN, split = blockIdx.z;
   const int64_t rb = (int64_t)split * g.rows_per_split;
   const int64_t re = min(rb + g.rows_per_split, g.M);
+  const bool want_bias = g.partb && blockIdx.x == 0 && tx == 0;
   float acc[4][4] = {};
   float bsum[4] = {};
-  for (int64_t r0 = rb; r0 < re; r0 += BK) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = (t >> 6) + 4 * i;
+  float vd[4], va[4];
+  // 16 rows x 64 columns of dY (columns o0..) and of A (columns k0..)
+  auto load = [&](int64_t r0) {
+    if (VEC) {
+      const int64_t gr = r0 + (t >> 4);
+      const int c = (t & 15) * 4;
+      float4 d = make_float4(0.f, 0.f, 0.f, 0.f), a = d;
+      if (gr < re) {
+        if (o0 + c < g.O) d = *reinterpret_cast<const float4*>(g.dY + gr * g.ldd + o0 + c);
+        int cc = k0 + c;
+        if (cc < g.K) {
+          const ASeg* s = &g.a.s[0];
+          if (cc >= s->w) { cc -= s->w; s = &g.a.s[1]; }
+          a = *reinterpret_cast<const float4*>(s->p + gr * s->ld + cc);
+        }
+      }
+      vd[0] = d.x; vd[1] = d.y; vd[2] = d.z; vd[3] = d.w;
+      va[0] = a.x; va[1] = a.y; va[2] = a.z; va[3] = a.w;
+    } else {
       const int c = t & 63;
-      const int64_t gr = r0 + r;
-      const bool in = gr < re;
-      Ds[r][c] = (in && o0 + c < g.O) ? g.dY[gr * g.ldd + o0 + c] : 0.f;
-      As[r][c] = (in && k0 + c < g.K) ? a_load(g.a, gr, k0 + c) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t gr = r0 + (t >> 6) + 4 * i;
+        const bool in = gr < re;
+        vd[i] = (in && o0 + c < g.O) ? g.dY[gr * g.ldd + o0 + c] : 0.f;
+        va[i] = (in && k0 + c < g.K) ? a_load(g.a, gr, k0 + c) : 0.f;
+      }
+    }
+  };
+  load(rb);
+  for (int64_t r0 = rb; r0 < re; r0 += BK) {
+    if (VEC) {
+      *reinterpret_cast<float4*>(&Ds[t >> 4][(t & 15) * 4]) = make_float4(vd[0], vd[1], vd[2], vd[3]);
+      *reinterpret_cast<float4*>(&As[t >> 4][(t & 15) * 4]) = make_float4(va[0], va[1], va[2], va[3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        Ds[(t >> 6) + 4 * i][t & 63] = vd[i];
+        As[(t >> 6) + 4 * i][t & 63] = va[i];
+      }
     }
     __syncthreads();
+    if (r0 + BK < re) load(r0 + BK);
 #pragma unroll
     for (int rr = 0; rr < BK; ++rr) {
       const float4 d = *reinterpret_cast<const float4*>(&Ds[rr][ty * 4]);
@@ -228,7 +346,10 @@ __global__ void __launch_bounds__(256) lin_bwd_w_kernel(const BwdWArgs g) {
         acc[i][1] = fmaf(dv[i], a.y, acc[i][1]);
         acc[i][2] = fmaf(dv[i], a.z, acc[i][2]);
         acc[i][3] = fmaf(dv[i], a.w, acc[i][3]);
-        bsum[i] += dv[i];
+      }
+      if (want_bias) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bsum[i] += dv[i];
       }
     }
     __syncthreads();
@@ -242,7 +363,7 @@ __global__ void __launch_bounds__(256) lin_bwd_w_kernel(const BwdWArgs g) {
       const int k = k0 + tx * 4 + j;
       if (k < g.K) g.part[((int64_t)split * g.O + o) * g.K + k] = acc[i][j];
     }
-    if (g.partb && blockIdx.x == 0 && tx == 0) g.partb[(int64_t)split * g.O + o] = bsum[i];
+    if (want_bias) g.partb[(int64_t)split * g.O + o] = bsum[i];
   }
 }
 
@@ -375,7 +496,8 @@ __global__ void __launch_bounds__(256) aggregate_fwd_kernel(const float* __restr
   out[n * kD + c] = v;
 }
 
-// gradient of the aggregation: max routes to the maxima of the bin, evenly among ties (oracle/mpn_train.py scatter)
+// gradient of the aggregation (max routes to the maxima of the bin, evenly among ties; oracle/mpn_train.py scatter)
+// followed by the ReLU of the message MLP: dm is the gradient of its pre-activation
 __global__ void __launch_bounds__(256) aggregate_bwd_kernel(const float* __restrict__ dagg, const float* __restrict__ m,
                                                              const float* __restrict__ agg, const int32_t* __restrict__ ptr,
                                                              const int32_t* __restrict__ perm, int64_t N, int aggr,
@@ -393,11 +515,15 @@ __global__ void __launch_bounds__(256) aggregate_bwd_kernel(const float* __restr
     const float share = g / (float)max(ties, 1);
     for (int i = b; i < e; ++i) {
       const int64_t o = (int64_t)perm[i] * kD + c;
-      dm[o] = m[o] == mx ? share : 0.f;
+      const float v = m[o];
+      dm[o] = (v == mx && v > 0.f) ? share : 0.f;      // ... and through the ReLU of the message
     }
   } else {
     const float share = aggr == PGMP_AGGR_MEAN ? g / (float)(e - b) : g;
-    for (int i = b; i < e; ++i) dm[(int64_t)perm[i] * kD + c] = share;
+    for (int i = b; i < e; ++i) {
+      const int64_t o = (int64_t)perm[i] * kD + c;
+      dm[o] = m[o] > 0.f ? share : 0.f;
+    }
   }
 }
 
@@ -593,20 +719,36 @@ TrainWs carve_train(const pgmp_mpn_train_params& p) {
 // ------------------------------------------------------------------ launch helpers
 inline unsigned blocks_for(int64_t n, int per = 256) { return (unsigned)ceil_div<int64_t>(n > 0 ? n : 1, per); }
 
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+inline bool vec_src(const ASrc& a) {
+  for (int i = 0; i < a.n; ++i)
+    if (!al16(a.s[i].p) || (a.s[i].ld & 3) || (a.s[i].w & 3)) return false;
+  return true;
+}
+inline bool vec_w(const float* W, int ldw, int coloff, int K) { return al16(W) && !(ldw & 3) && !(coloff & 3) && !(K & 3); }
+
 int launch_fwd(cudaStream_t st, const ASrc& a, int64_t M, const float* W, int ldw, int coloff, const float* bias, int O,
                int relu, float* Y, const float* add1 = nullptr, const int64_t* idx1 = nullptr, const float* add2 = nullptr,
                const int64_t* idx2 = nullptr) {
   if (M <= 0) return PGMP_OK;
   FwdArgs g{a, M, src_width(a), O, W, ldw, coloff, bias, add1, idx1, add2, idx2, relu, Y, O};
-  PGMP_LAUNCH(lin_fwd_kernel, dim3(blocks_for(M, BM), (unsigned)ceil_div(O, BN)), 256, 0, st, g);
+  const dim3 grid(blocks_for(M, BM), (unsigned)ceil_div(O, BN));
+  if (vec_src(a) && vec_w(W, ldw, coloff, g.K))
+    PGMP_LAUNCH(lin_fwd_kernel<true>, grid, 256, 0, st, g);
+  else
+    PGMP_LAUNCH(lin_fwd_kernel<false>, grid, 256, 0, st, g);
   return PGMP_OK;
 }
 
 int launch_bwd_in(cudaStream_t st, const float* dY, int O, int64_t M, const float* W, int ldw, int coloff, int K, Target t0,
                   const Target* t1 = nullptr) {
   if (M <= 0) return PGMP_OK;
-  BwdInArgs g{dY, O, M, O, K, W, ldw, coloff, t1 ? 2 : 1, {t0, t1 ? *t1 : Target{nullptr, 0, 0, 0, 0}}};
-  PGMP_LAUNCH(lin_bwd_in_kernel, dim3(blocks_for(M, BM), (unsigned)ceil_div(K, BN)), 256, 0, st, g);
+  BwdInArgs g{dY, O, M, O, K, W, ldw, coloff, t1 ? 2 : 1, {t0, t1 ? *t1 : Target{nullptr, 0, 0, 0, 0, nullptr}}};
+  const dim3 grid(blocks_for(M, BM), (unsigned)ceil_div(K, BN));
+  if (al16(dY) && !(O & 3) && vec_w(W, ldw, coloff, K))
+    PGMP_LAUNCH(lin_bwd_in_kernel<true>, grid, 256, 0, st, g);
+  else
+    PGMP_LAUNCH(lin_bwd_in_kernel<false>, grid, 256, 0, st, g);
   return PGMP_OK;
 }
 
@@ -615,12 +757,16 @@ int launch_bwd_w(cudaStream_t st, const TrainWs& w, const float* dY, int O, cons
                  int coloff, float* db) {
   if (M <= 0) return PGMP_OK;
   const int K = src_width(a);
-  int splits = (int)ceil_div<int64_t>(M, 512);
+  int splits = (int)ceil_div<int64_t>(M, 256);
   if (splits > kMaxSplits) splits = kMaxSplits;
   const int64_t rows = round_up<int64_t>(ceil_div<int64_t>(M, splits), BK);
   splits = (int)ceil_div<int64_t>(M, rows);
   BwdWArgs g{dY, O, O, a, K, M, rows, w.part, db ? w.partb : nullptr};
-  PGMP_LAUNCH(lin_bwd_w_kernel, dim3((unsigned)ceil_div(K, BN), (unsigned)ceil_div(O, BN), (unsigned)splits), 256, 0, st, g);
+  const dim3 grid((unsigned)ceil_div(K, BN), (unsigned)ceil_div(O, BN), (unsigned)splits);
+  if (al16(dY) && !(O & 3) && vec_src(a) && !(K & 3))
+    PGMP_LAUNCH(lin_bwd_w_kernel<true>, grid, 256, 0, st, g);
+  else
+    PGMP_LAUNCH(lin_bwd_w_kernel<false>, grid, 256, 0, st, g);
   PGMP_LAUNCH(reduce_parts_kernel, blocks_for((int64_t)O * K), 256, 0, st, w.part, db ? w.partb : nullptr, splits, O, K, dW,
               ldw, coloff, db);
   return PGMP_OK;
@@ -819,7 +965,7 @@ int mpn_train_backward(const pgmp_mpn_train_params& p, cudaStream_t st) {
     PGMP_CUDA(cudaMemsetAsync(w.dg, 0, sizeof(float) * nE, st));
     PGMP_CUDA(cudaMemsetAsync(w.dg0, 0, sizeof(float) * nE, st));
   }
-  const Target none{nullptr, 0, 0, 0, 0};
+  const Target none{nullptr, 0, 0, 0, 0, nullptr};
   for (int s = p.steps - 1; s >= 0; --s) {
     const float* hp = s ? w.h[s - 1] : h0;
     const float* gp = s ? w.g[s - 1] : g0;
@@ -849,19 +995,17 @@ int mpn_train_backward(const pgmp_mpn_train_params& p, cudaStream_t st) {
       // aggregation and the ReLU of the message
       float* dm = w.be1;
       PGMP_LAUNCH(aggregate_bwd_kernel, blocks_for(N, 4), 256, 0, st, dagg, w.m[s], w.agg[s], w.dst_ptr, w.dst_perm, N, p.aggr, dm);
-      PGMP_LAUNCH(relu_mask_kernel, blocks_for(nE), 256, 0, st, dm, w.m[s], dm, nE);
       // mlp_node: edge columns per edge, node columns through the per-target sums
       PGMP_LAUNCH(seg_sum_kernel, blocks_for(N, 4), 256, 0, st, dm, w.dst_ptr, w.dst_perm, N, w.tn3);
       PGMP_TRY(launch_bwd_w(st, w, dm, kD, src1(w.g[s], kD), E, G + p.wm, ldm, nd, nullptr));
       PGMP_TRY(launch_bwd_w(st, w, w.tn3, kD, xs, N, G + p.wm, ldm, 0, G + p.bm));
       PGMP_TRY(launch_bwd_in(st, w.tn3, kD, N, P + p.wm, ldm, 0, nd, tx0, p.skip ? &tx1 : nullptr));
-      PGMP_TRY(launch_bwd_in(st, dm, kD, E, P + p.wm, ldm, nd, kD, Target{w.dg, kD, 0, kD, 1}));
+      // ... the gradient of g_s is complete with this term: the epilogue also applies the ReLU of mlp_edge.2
+      PGMP_TRY(launch_bwd_in(st, dm, kD, E, P + p.wm, ldm, nd, kD, Target{w.dg, kD, 0, kD, 1, w.g[s]}));
       // mlp_edge.2
-      PGMP_LAUNCH(relu_mask_kernel, blocks_for(nE), 256, 0, st, w.dg, w.g[s], w.dg, nE);
       PGMP_TRY(launch_bwd_w(st, w, w.dg, kD, src1(w.hid[s], kD), E, G + p.w2, kD, 0, G + p.b2));
       float* dhid = w.be2;
-      PGMP_TRY(launch_bwd_in(st, w.dg, kD, E, P + p.w2, kD, 0, kD, Target{dhid, kD, 0, kD, 0}));
-      PGMP_LAUNCH(relu_mask_kernel, blocks_for(nE), 256, 0, st, dhid, w.hid[s], dhid, nE);
+      PGMP_TRY(launch_bwd_in(st, w.dg, kD, E, P + p.w2, kD, 0, kD, Target{dhid, kD, 0, kD, 0, w.hid[s]}));   // + ReLU of mlp_edge.0
       // mlp_edge.0
       PGMP_LAUNCH(seg_sum_kernel, blocks_for(N, 4), 256, 0, st, dhid, w.dst_ptr, w.dst_perm, N, w.tn1);
       PGMP_LAUNCH(seg_sum_kernel, blocks_for(N, 4), 256, 0, st, dhid, w.src_ptr, w.src_perm, N, w.tn2);

@@ -30,7 +30,7 @@ from pgmp_b200.graph_constructor import get_graph_constructor  # noqa: E402
 from pgmp_b200.Models.MessagePassingNetwork import get_mpn_model  # noqa: E402
 
 
-def main():
+def parse(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
@@ -38,13 +38,11 @@ def main():
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--mpn-steps", type=int, default=10)
     ap.add_argument("--profile", action="store_true", help="after the timed steps: one more step with per-kernel CUDA events")
-    args = ap.parse_args()
-    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    return ap.parse_args(argv)
+
+
+def run_training(args, rank, world, dev):
+    """The measurement itself; the caller owns the process group.  Returns the result dict on rank 0 (None elsewhere)."""
     J, K = 17, 30
     data = synthetic.synth_batch(args.batch, J, args.size, K, persons=8, first_index=rank * args.batch)
     t = {k: torch.from_numpy(v).to(dev) for k, v in data.items()}
@@ -97,9 +95,10 @@ def main():
     losses = [step(True) for _ in range(args.steps)]
     launches = nv.kernel_launches() - launches0
     ms = {k: par.max_over_ranks(v / args.steps, dev) for k, v in acc.items()}
+    result = None
     if rank == 0:
         imgs = args.batch * world
-        print(json.dumps({
+        result = ({
             "metric": "training step: images/sec (GC + MPN forward + backward + gradient all-reduce + Adam)",
             "value": imgs / (ms["step"] * 1e-3), "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms["step"], "ms": ms, "edges_per_s": info["edges"] * world / (ms["step"] * 1e-3),
@@ -107,14 +106,50 @@ def main():
                                    "kNN-50 graph" % (args.batch, args.size, args.size, args.mpn_steps),
                        "nodes_per_gpu": info["nodes"], "edges_per_gpu": info["edges"]},
             "dtype": "f32", "data": "synthetic", "scaling": "weak", "allreduce_bytes": info["allreduce_bytes"],
-            "gpu_launches": launches, "loss_first_last": [losses[0], losses[-1]]}))
+            "gpu_launches": launches, "loss_first_last": [losses[0], losses[-1]]})
     if args.profile and rank == 0:
+        import time
+        marks = []
+
+        def mark(name):
+            torch.cuda.synchronize()
+            marks.append((name, time.perf_counter()))
+        mark("start")
+        gc = get_graph_constructor(gcfg, scoremaps=t["scoremaps"], tagmaps=t["tagmaps"], features=t["features"], joints_gt=None,
+                                   factor_list=None, masks=None, device=dev, testing=False, heatmaps=None, num_joints=J)
+        mark("gc ctor")
+        ret = gc.construct_graph()
+        mark("construct_graph")
+        pe, pn, pc, _ = model(ret[0], ret[1], ret[2], node_types=ret[7][:, 2])
+        mark("mpn forward")
+        loss = pe[-1].sum() + pn[-1].sum() + pc[-1].sum()
+        mark("loss")
+        loss.backward()
+        mark("backward")
+        del pe, pn, pc, loss, ret, gc
+        mark("free")
+        print("host wall time per phase (synchronised): " + ", ".join(
+            "%s %.2f ms" % (b[0], (b[1] - a[1]) * 1e3) for a, b in zip(marks[:-1], marks[1:])))
         nv.profile(True)
         step(False)
         prof = nv.profile_collect()
         nv.profile(False)
         for name, (cnt, tot) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
             print("%-28s %5d launches %9.3f ms" % (name, cnt, tot))
+    return result
+
+
+def main():
+    args = parse()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    result = run_training(args, rank, world, dev)
+    if rank == 0:
+        print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()
 
