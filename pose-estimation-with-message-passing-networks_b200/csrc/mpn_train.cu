@@ -50,6 +50,113 @@ __device__ __forceinline__ float a_load(const ASrc& a, int64_t r, int k) {
   return 0.f;
 }
 
+// ------------------------------------------------------------------ tensor-core inner product, fp32-accurate
+// The three GEMM kernels keep a 64 x 64 output tile per CTA and multiply 16-deep slices out of shared memory with
+// mma.sync.m16n8k8 (tf32 operands, fp32 accumulation).  Every fp32 operand is split on the fly into
+// hi = tf32(x), lo = tf32(x - hi) and a.b ~= a_lo.b_hi + a_hi.b_lo + a_hi.b_hi ("3xTF32"): the dropped lo.lo term is
+// 2^-22 relative, so the result matches an fp32 FMA chain to rounding (the TIGHT tolerance of tests/test_gpu_train.py).
+// Warp w of the 8 owns rows (w & 3) * 16 .. +16 and columns (w >> 2) * 32 .. +32 of the tile (4 n-blocks of 8).
+constexpr int AS_LD = BK + 4;    // row-major A slice [64][16]: 20-float rows -> conflict-free fragment loads
+constexpr int BS_LD = BN + 8;    // k-major slices [16][64]: 72-float rows
+
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// acc += A_slice . B_slice.  A_KMAJOR = false: A element (row, k) at Ar[row * AS_LD + k]; true: at Ak[k * BS_LD + row].
+// B element (k, col) at Bk[k * BS_LD + col].
+// acc += A_slice . B_slice.
+// A_KMAJOR = false: A element (row, k) at Aop[row * AS_LD + k]; true: at Aop[k * BS_LD + row].
+// B_NMAJOR = false: B element (k, col) at Bop[k * BS_LD + col]; true: at Bop[col * AS_LD + k].
+template <bool A_KMAJOR, bool B_NMAJOR>
+__device__ __forceinline__ void tile_mma(const float* __restrict__ Aop, const float* __restrict__ Bop, int wr, int wc, int g,
+                                         int t4, float (&acc)[4][4]) {
+#pragma unroll
+  for (int k8 = 0; k8 < BK; k8 += 8) {
+    uint32_t ah[4], al[4];
+    if (A_KMAJOR) {
+      split_tf32(Aop[(k8 + t4) * BS_LD + wr + g], ah[0], al[0]);
+      split_tf32(Aop[(k8 + t4) * BS_LD + wr + g + 8], ah[1], al[1]);
+      split_tf32(Aop[(k8 + t4 + 4) * BS_LD + wr + g], ah[2], al[2]);
+      split_tf32(Aop[(k8 + t4 + 4) * BS_LD + wr + g + 8], ah[3], al[3]);
+    } else {
+      split_tf32(Aop[(wr + g) * AS_LD + k8 + t4], ah[0], al[0]);
+      split_tf32(Aop[(wr + g + 8) * AS_LD + k8 + t4], ah[1], al[1]);
+      split_tf32(Aop[(wr + g) * AS_LD + k8 + t4 + 4], ah[2], al[2]);
+      split_tf32(Aop[(wr + g + 8) * AS_LD + k8 + t4 + 4], ah[3], al[3]);
+    }
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) {
+      uint32_t bh[2], bl[2];
+      if (B_NMAJOR) {
+        split_tf32(Bop[(wc + nb * 8 + g) * AS_LD + k8 + t4], bh[0], bl[0]);
+        split_tf32(Bop[(wc + nb * 8 + g) * AS_LD + k8 + t4 + 4], bh[1], bl[1]);
+      } else {
+        split_tf32(Bop[(k8 + t4) * BS_LD + wc + nb * 8 + g], bh[0], bl[0]);
+        split_tf32(Bop[(k8 + t4 + 4) * BS_LD + wc + nb * 8 + g], bh[1], bl[1]);
+      }
+      mma_tf32(acc[nb], al, bh);      // small terms first
+      mma_tf32(acc[nb], ah, bl);
+      mma_tf32(acc[nb], ah, bh);
+    }
+  }
+}
+// accumulator element e of n-block nb: row = wr + g + 8 * (e >> 1), column = wc + nb * 8 + 2 * t4 + (e & 1)
+
+// ------------------------------------------------------------------ operand slices into shared memory
+// VEC (every row start 16-byte aligned, widths multiples of 4): 16-byte cp.async copies straight into a kStages-deep
+// ring of slices, two slices in flight while one is multiplied.  Otherwise (19-wide edge attributes, 1 / 17-wide head
+// outputs): scalar loads, one slice at a time.
+constexpr int kStages = 3;
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 16 : 0;      // 0 source bytes: the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// address of element (r, c) of a column-concatenated source; c is a multiple of 4 and the widths are too
+__device__ __forceinline__ const float* src_ptr(const ASrc& a, int64_t r, int c) {
+  const ASeg* s = &a.s[0];
+  if (c >= s->w) { c -= s->w; s = &a.s[1]; }
+  return s->p + r * s->ld + c;
+}
+
+template <bool VEC, class Issue, class Fill, class Compute>
+__device__ __forceinline__ void run_slices(int n_iter, Issue issue, Fill fill, Compute compute) {
+  if (VEC) {
+#pragma unroll
+    for (int s = 0; s < kStages - 1; ++s) {
+      if (s < n_iter) issue(s, s);
+      cp_commit();
+    }
+    for (int i = 0; i < n_iter; ++i) {
+      cp_wait<kStages - 2>();
+      __syncthreads();                      // slice i has landed for every thread; slice i - 1 is no longer read
+      const int nx = i + kStages - 1;
+      if (nx < n_iter) issue(nx, nx % kStages);
+      cp_commit();
+      compute(i % kStages);
+    }
+  } else {
+    for (int i = 0; i < n_iter; ++i) {
+      __syncthreads();
+      fill(i);
+      __syncthreads();
+      compute(0);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ Y = act(A W^T + b + add1[idx1] + add2[idx2])
 struct FwdArgs {
   ASrc a;
@@ -67,113 +174,56 @@ struct FwdArgs {
   int ldy;
 };
 
-// A / dY tile loader shared by the forward and input-gradient kernels: 64 rows x 16 columns starting at column c0.
-// VEC: every row start is 16-byte aligned and the widths are multiples of 4 -> one float4 per thread.
 template <bool VEC>
-__device__ __forceinline__ void load_a_tile(const ASrc& a, int64_t r0, int64_t M, int c0, int K, int t, float (&v)[4]) {
-  if (VEC) {
-    const int64_t gr = r0 + (t >> 2);
-    const int c = c0 + (t & 3) * 4;
-    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (gr < M && c < K) {
-      int cc = c;
-      const ASeg* s = &a.s[0];
-      if (cc >= s->w) { cc -= s->w; s = &a.s[1]; }
-      x = *reinterpret_cast<const float4*>(s->p + gr * s->ld + cc);
-    }
-    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
-  } else {
-    const int c = c0 + (t & 15);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int64_t gr = r0 + (t >> 4) + 16 * i;
-      v[i] = (gr < M && c < K) ? a_load(a, gr, c) : 0.f;
-    }
-  }
-}
-template <bool VEC>
-__device__ __forceinline__ void store_a_tile(float (*As)[BK + 1], int t, const float (&v)[4]) {
-  if (VEC) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) As[t >> 2][(t & 3) * 4 + i] = v[i];
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) As[(t >> 4) + 16 * i][t & 15] = v[i];
-  }
-}
-
-template <bool VEC>
-__global__ void __launch_bounds__(256) lin_fwd_kernel(const FwdArgs g) {
-  __shared__ float As[BM][BK + 1];
-  __shared__ __align__(16) float Bs[BK][BN + 4];
-  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+__global__ void __launch_bounds__(256) lin_fwd_kernel(const FwdArgs q) {
+  constexpr int ST = VEC ? kStages : 1;
+  __shared__ __align__(16) float As[ST][BM * AS_LD];     // rows of A, 16 reduction columns
+  __shared__ __align__(16) float Bt[ST][BN * AS_LD];     // rows of W (outputs o), the same 16 reduction columns
+  const int t = threadIdx.x;
+  const int warp = t >> 5, g = (t & 31) >> 2, t4 = t & 3, wr = (warp & 3) * 16, wc = (warp >> 2) * 32;
   const int64_t r0 = (int64_t)blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
   float acc[4][4] = {};
-  float va[4], vb[4];
-  // W tile: rows = outputs o, 16 consecutive k (the reduction index is contiguous in Linear.weight)
-  auto load_b = [&](int k0) {
-    if (VEC) {
-      const int o = n0 + (t >> 2), k = k0 + (t & 3) * 4;
-      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (o < g.O && k < g.K) x = *reinterpret_cast<const float4*>(g.W + (int64_t)o * g.ldw + g.coloff + k);
-      vb[0] = x.x; vb[1] = x.y; vb[2] = x.z; vb[3] = x.w;
-    } else {
-      const int k = k0 + (t & 15);
+  auto issue = [&](int it, int st) {
+    const int row = t >> 2, c = it * BK + (t & 3) * 4;
+    const int64_t gr = r0 + row;
+    const bool va = gr < q.M && c < q.K;
+    cp_async16(&As[st][row * AS_LD + (t & 3) * 4], va ? src_ptr(q.a, gr, c) : q.W, va);
+    const int o = n0 + row;
+    const bool vb = o < q.O && c < q.K;
+    cp_async16(&Bt[st][row * AS_LD + (t & 3) * 4], vb ? q.W + (int64_t)o * q.ldw + q.coloff + c : q.W, vb);
+  };
+  auto fill = [&](int it) {
+    const int k = it * BK + (t & 15);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int o = n0 + (t >> 4) + 16 * i;
-        vb[i] = (o < g.O && k < g.K) ? g.W[(int64_t)o * g.ldw + g.coloff + k] : 0.f;
-      }
+    for (int i = 0; i < 4; ++i) {
+      const int row = (t >> 4) + 16 * i;
+      const int64_t gr = r0 + row;
+      As[0][row * AS_LD + (t & 15)] = (gr < q.M && k < q.K) ? a_load(q.a, gr, k) : 0.f;
+      const int o = n0 + row;
+      Bt[0][row * AS_LD + (t & 15)] = (o < q.O && k < q.K) ? q.W[(int64_t)o * q.ldw + q.coloff + k] : 0.f;
     }
   };
-  load_a_tile<VEC>(g.a, r0, g.M, 0, g.K, t, va);
-  load_b(0);
-  for (int k0 = 0; k0 < g.K; k0 += BK) {
-    store_a_tile<VEC>(As, t, va);
-    if (VEC) {
+  run_slices<VEC>(ceil_div(q.K, BK), issue, fill, [&](int st) { tile_mma<false, true>(As[st], Bt[st], wr, wc, g, t4, acc); });
 #pragma unroll
-      for (int i = 0; i < 4; ++i) Bs[(t & 3) * 4 + i][t >> 2] = vb[i];
-    } else {
+  for (int h = 0; h < 2; ++h) {
+    const int64_t gr = r0 + wr + g + 8 * h;
+    if (gr >= q.M) continue;
+    const float* e1 = q.add1 ? q.add1 + q.idx1[gr] * kD : nullptr;
+    const float* e2 = q.add2 ? q.add2 + q.idx2[gr] * kD : nullptr;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) Bs[t & 15][(t >> 4) + 16 * i] = vb[i];
-    }
-    __syncthreads();
-    if (k0 + BK < g.K) {      // next tile in flight while this one is multiplied
-      load_a_tile<VEC>(g.a, r0, g.M, k0 + BK, g.K, t, va);
-      load_b(k0 + BK);
-    }
+    for (int nb = 0; nb < 4; ++nb)
 #pragma unroll
-    for (int kk = 0; kk < BK; ++kk) {
-      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float a = As[ty * 4 + i][kk];
-        acc[i][0] = fmaf(a, b.x, acc[i][0]);
-        acc[i][1] = fmaf(a, b.y, acc[i][1]);
-        acc[i][2] = fmaf(a, b.z, acc[i][2]);
-        acc[i][3] = fmaf(a, b.w, acc[i][3]);
+      for (int j = 0; j < 2; ++j) {
+        const int o = n0 + wc + nb * 8 + 2 * t4 + j;
+        if (o >= q.O) continue;
+        float v = acc[nb][2 * h + j];
+        if (q.bias) v += q.bias[o];
+        if (e1) v += e1[o];
+        if (e2) v += e2[o];
+        if (q.relu) v = fmaxf(v, 0.f);
+        q.Y[gr * q.ldy + o] = v;
       }
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int64_t gr = r0 + ty * 4 + i;
-    if (gr >= g.M) continue;
-    const float* e1 = g.add1 ? g.add1 + g.idx1[gr] * kD : nullptr;
-    const float* e2 = g.add2 ? g.add2 + g.idx2[gr] * kD : nullptr;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int o = n0 + tx * 4 + j;
-      if (o >= g.O) continue;
-      float v = acc[i][j];
-      if (g.bias) v += g.bias[o];
-      if (e1) v += e1[o];
-      if (e2) v += e2[o];
-      if (g.relu) v = fmaxf(v, 0.f);
-      g.Y[gr * g.ldy + o] = v;
-    }
   }
 }
 
@@ -195,79 +245,57 @@ struct BwdInArgs {
 };
 
 template <bool VEC>
-__global__ void __launch_bounds__(256) lin_bwd_in_kernel(const BwdInArgs g) {
-  __shared__ float As[BM][BK + 1];
-  __shared__ __align__(16) float Bs[BK][BN + 4];
-  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+__global__ void __launch_bounds__(256) lin_bwd_in_kernel(const BwdInArgs q) {
+  constexpr int ST = VEC ? kStages : 1;
+  __shared__ __align__(16) float As[ST][BM * AS_LD];     // rows of dY, 16 output columns o (the reduction index)
+  __shared__ __align__(16) float Bs[ST][BK * BS_LD];     // the same 16 rows o of W, 64 input columns
+  const int t = threadIdx.x;
+  const int warp = t >> 5, g = (t & 31) >> 2, t4 = t & 3, wr = (warp & 3) * 16, wc = (warp >> 2) * 32;
   const int64_t r0 = (int64_t)blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
   float acc[4][4] = {};
-  float va[4], vb[4];
-  const ASrc dy = ASrc{1, {{g.dY, g.ldd, g.O}, {nullptr, 0, 0}}};
-  // W tile: 16 rows (outputs o) x 64 consecutive input columns
-  auto load_b = [&](int o0) {
-    if (VEC) {
-      const int ob = o0 + (t >> 4), k = n0 + (t & 15) * 4;
-      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ob < g.O && k < g.K) x = *reinterpret_cast<const float4*>(g.W + (int64_t)ob * g.ldw + g.coloff + k);
-      vb[0] = x.x; vb[1] = x.y; vb[2] = x.z; vb[3] = x.w;
-    } else {
-      const int k = n0 + (t & 63);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int ob = o0 + (t >> 6) + 4 * i;
-        vb[i] = (ob < g.O && k < g.K) ? g.W[(int64_t)ob * g.ldw + g.coloff + k] : 0.f;
-      }
-    }
+  auto issue = [&](int it, int st) {
+    const int row = t >> 2, c = it * BK + (t & 3) * 4;
+    const int64_t gr = r0 + row;
+    const bool va = gr < q.M && c < q.O;
+    cp_async16(&As[st][row * AS_LD + (t & 3) * 4], va ? q.dY + gr * q.ldd + c : q.W, va);
+    const int ob = it * BK + (t >> 4), k = n0 + (t & 15) * 4;
+    const bool vb = ob < q.O && k < q.K;
+    cp_async16(&Bs[st][(t >> 4) * BS_LD + (t & 15) * 4], vb ? q.W + (int64_t)ob * q.ldw + q.coloff + k : q.W, vb);
   };
-  load_a_tile<VEC>(dy, r0, g.M, 0, g.O, t, va);
-  load_b(0);
-  for (int o0 = 0; o0 < g.O; o0 += BK) {
-    store_a_tile<VEC>(As, t, va);
-    if (VEC) {
-      *reinterpret_cast<float4*>(&Bs[t >> 4][(t & 15) * 4]) = make_float4(vb[0], vb[1], vb[2], vb[3]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) Bs[(t >> 6) + 4 * i][t & 63] = vb[i];
-    }
-    __syncthreads();
-    if (o0 + BK < g.O) {
-      load_a_tile<VEC>(dy, r0, g.M, o0 + BK, g.O, t, va);
-      load_b(o0 + BK);
-    }
-#pragma unroll
-    for (int kk = 0; kk < BK; ++kk) {
-      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float a = As[ty * 4 + i][kk];
-        acc[i][0] = fmaf(a, b.x, acc[i][0]);
-        acc[i][1] = fmaf(a, b.y, acc[i][1]);
-        acc[i][2] = fmaf(a, b.z, acc[i][2]);
-        acc[i][3] = fmaf(a, b.w, acc[i][3]);
-      }
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int k = n0 + tx * 4 + j;
-    if (k >= g.K) continue;
-    const int which = (k >= g.t[0].k0 && k < g.t[0].k0 + g.t[0].w) ? 0 : ((g.nt > 1 && k >= g.t[1].k0 && k < g.t[1].k0 + g.t[1].w) ? 1 : -1);
-    if (which < 0) continue;
-    float* const tp = which ? g.t[1].p : g.t[0].p;
-    const float* const tm = which ? g.t[1].mask : g.t[0].mask;
-    const int tld = which ? g.t[1].ld : g.t[0].ld, tk0 = which ? g.t[1].k0 : g.t[0].k0, tadd = which ? g.t[1].add : g.t[0].add;
+  auto fill = [&](int it) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int64_t gr = r0 + ty * 4 + i;
-      if (gr >= g.M) continue;
-      const int64_t off = gr * tld + (k - tk0);
-      float v = tadd ? tp[off] + acc[i][j] : acc[i][j];
-      if (tm && !(tm[off] > 0.f)) v = 0.f;
-      tp[off] = v;
+      const int row = (t >> 4) + 16 * i;
+      const int64_t gr = r0 + row;
+      const int o = it * BK + (t & 15);
+      As[0][row * AS_LD + (t & 15)] = (gr < q.M && o < q.O) ? q.dY[gr * q.ldd + o] : 0.f;
+      const int ob = it * BK + (t >> 6) + 4 * i, k = n0 + (t & 63);
+      Bs[0][((t >> 6) + 4 * i) * BS_LD + (t & 63)] = (ob < q.O && k < q.K) ? q.W[(int64_t)ob * q.ldw + q.coloff + k] : 0.f;
     }
-  }
+  };
+  run_slices<VEC>(ceil_div(q.O, BK), issue, fill, [&](int st) { tile_mma<false, false>(As[st], Bs[st], wr, wc, g, t4, acc); });
+#pragma unroll
+  for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int k = n0 + wc + nb * 8 + 2 * t4 + j;
+      if (k >= q.K) continue;
+      const int which = (k >= q.t[0].k0 && k < q.t[0].k0 + q.t[0].w) ? 0 : ((q.nt > 1 && k >= q.t[1].k0 && k < q.t[1].k0 + q.t[1].w) ? 1 : -1);
+      if (which < 0) continue;
+      float* const tp = which ? q.t[1].p : q.t[0].p;
+      const float* const tm = which ? q.t[1].mask : q.t[0].mask;
+      const int tld = which ? q.t[1].ld : q.t[0].ld, tk0 = which ? q.t[1].k0 : q.t[0].k0, tadd = which ? q.t[1].add : q.t[0].add;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int64_t gr = r0 + wr + g + 8 * h;
+        if (gr >= q.M) continue;
+        const int64_t off = gr * tld + (k - tk0);
+        float v = tadd ? tp[off] + acc[nb][2 * h + j] : acc[nb][2 * h + j];
+        if (tm && !(tm[off] > 0.f)) v = 0.f;
+        tp[off] = v;
+      }
+    }
 }
 
 // ------------------------------------------------------------------ dW partial tiles: part[s] = dY[rows_s]^T A[rows_s]
@@ -282,106 +310,89 @@ struct BwdWArgs {
 };
 
 template <bool VEC>
-__global__ void __launch_bounds__(256) lin_bwd_w_kernel(const BwdWArgs g) {
-  __shared__ __align__(16) float Ds[BK][BN + 4];
-  __shared__ __align__(16) float As[BK][BN + 4];
-  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+__global__ void __launch_bounds__(256) lin_bwd_w_kernel(const BwdWArgs q) {
+  constexpr int ST = VEC ? kStages : 1;
+  __shared__ __align__(16) float Ds[ST][BK * BS_LD];     // 16 rows (the reduction index) of dY, 64 output columns
+  __shared__ __align__(16) float As[ST][BK * BS_LD];     // the same 16 rows of A, 64 input columns
+  const int t = threadIdx.x;
+  const int warp = t >> 5, g = (t & 31) >> 2, t4 = t & 3, wr = (warp & 3) * 16, wc = (warp >> 2) * 32;
   const int k0 = blockIdx.x * BN, o0 = blockIdx.y * BN, split = blockIdx.z;
-  const int64_t rb = (int64_t)split * g.rows_per_split;
-  const int64_t re = min(rb + g.rows_per_split, g.M);
-  const bool want_bias = g.partb && blockIdx.x == 0 && tx == 0;
+  const int64_t rb = (int64_t)split * q.rows_per_split;
+  const int64_t re = min(rb + q.rows_per_split, q.M);
+  const bool want_bias = q.partb && blockIdx.x == 0 && t < BN;   // thread t sums column o0 + t of dY
   float acc[4][4] = {};
-  float bsum[4] = {};
-  float vd[4], va[4];
-  // 16 rows x 64 columns of dY (columns o0..) and of A (columns k0..)
-  auto load = [&](int64_t r0) {
-    if (VEC) {
-      const int64_t gr = r0 + (t >> 4);
-      const int c = (t & 15) * 4;
-      float4 d = make_float4(0.f, 0.f, 0.f, 0.f), a = d;
-      if (gr < re) {
-        if (o0 + c < g.O) d = *reinterpret_cast<const float4*>(g.dY + gr * g.ldd + o0 + c);
-        int cc = k0 + c;
-        if (cc < g.K) {
-          const ASeg* s = &g.a.s[0];
-          if (cc >= s->w) { cc -= s->w; s = &g.a.s[1]; }
-          a = *reinterpret_cast<const float4*>(s->p + gr * s->ld + cc);
-        }
-      }
-      vd[0] = d.x; vd[1] = d.y; vd[2] = d.z; vd[3] = d.w;
-      va[0] = a.x; va[1] = a.y; va[2] = a.z; va[3] = a.w;
-    } else {
-      const int c = t & 63;
+  float bsum = 0.f;
+  auto issue = [&](int it, int st) {
+    const int64_t gr = rb + (int64_t)it * BK + (t >> 4);
+    const int c = (t & 15) * 4;
+    const bool vd = gr < re && o0 + c < q.O;
+    cp_async16(&Ds[st][(t >> 4) * BS_LD + c], vd ? q.dY + gr * q.ldd + o0 + c : q.dY, vd);
+    const bool va = gr < re && k0 + c < q.K;
+    cp_async16(&As[st][(t >> 4) * BS_LD + c], va ? src_ptr(q.a, gr, k0 + c) : q.dY, va);
+  };
+  auto fill = [&](int it) {
+    const int c = t & 63;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int64_t gr = r0 + (t >> 6) + 4 * i;
-        const bool in = gr < re;
-        vd[i] = (in && o0 + c < g.O) ? g.dY[gr * g.ldd + o0 + c] : 0.f;
-        va[i] = (in && k0 + c < g.K) ? a_load(g.a, gr, k0 + c) : 0.f;
-      }
+    for (int i = 0; i < 4; ++i) {
+      const int r = (t >> 6) + 4 * i;
+      const int64_t gr = rb + (int64_t)it * BK + r;
+      const bool in = gr < re;
+      Ds[0][r * BS_LD + c] = (in && o0 + c < q.O) ? q.dY[gr * q.ldd + o0 + c] : 0.f;
+      As[0][r * BS_LD + c] = (in && k0 + c < q.K) ? a_load(q.a, gr, k0 + c) : 0.f;
     }
   };
-  load(rb);
-  for (int64_t r0 = rb; r0 < re; r0 += BK) {
-    if (VEC) {
-      *reinterpret_cast<float4*>(&Ds[t >> 4][(t & 15) * 4]) = make_float4(vd[0], vd[1], vd[2], vd[3]);
-      *reinterpret_cast<float4*>(&As[t >> 4][(t & 15) * 4]) = make_float4(va[0], va[1], va[2], va[3]);
-    } else {
+  run_slices<VEC>((int)ceil_div<int64_t>(re - rb, BK), issue, fill, [&](int st) {
+    tile_mma<true, false>(Ds[st], As[st], wr, wc, g, t4, acc);      // rows of the tile = outputs o, columns = inputs k
+    if (want_bias) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        Ds[(t >> 6) + 4 * i][t & 63] = vd[i];
-        As[(t >> 6) + 4 * i][t & 63] = va[i];
-      }
+      for (int rr = 0; rr < BK; ++rr) bsum += Ds[st][rr * BS_LD + t];
     }
-    __syncthreads();
-    if (r0 + BK < re) load(r0 + BK);
+  });
 #pragma unroll
-    for (int rr = 0; rr < BK; ++rr) {
-      const float4 d = *reinterpret_cast<const float4*>(&Ds[rr][ty * 4]);
-      const float4 a = *reinterpret_cast<const float4*>(&As[rr][tx * 4]);
-      const float dv[4] = {d.x, d.y, d.z, d.w};
+  for (int h = 0; h < 2; ++h) {
+    const int o = o0 + wr + g + 8 * h;
+    if (o >= q.O) continue;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        acc[i][0] = fmaf(dv[i], a.x, acc[i][0]);
-        acc[i][1] = fmaf(dv[i], a.y, acc[i][1]);
-        acc[i][2] = fmaf(dv[i], a.z, acc[i][2]);
-        acc[i][3] = fmaf(dv[i], a.w, acc[i][3]);
+    for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int k = k0 + wc + nb * 8 + 2 * t4 + j;
+        if (k < q.K) q.part[((int64_t)split * q.O + o) * q.K + k] = acc[nb][2 * h + j];
       }
-      if (want_bias) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) bsum[i] += dv[i];
-      }
-    }
-    __syncthreads();
   }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int o = o0 + ty * 4 + i;
-    if (o >= g.O) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int k = k0 + tx * 4 + j;
-      if (k < g.K) g.part[((int64_t)split * g.O + o) * g.K + k] = acc[i][j];
-    }
-    if (want_bias) g.partb[(int64_t)split * g.O + o] = bsum[i];
-  }
+  if (want_bias && o0 + t < q.O) q.partb[(int64_t)split * q.O + o0 + t] = bsum;
 }
 
-// dW[o][coloff + k] += sum_s part[s][o][k] (s ascending), db[o] += sum_s partb[s][o]
+// dW[o][coloff + k] += sum_s part[s][o][k], db[o] += sum_s partb[s][o].  Fixed association (reproducible): a CTA owns
+// 32 consecutive outputs; thread group q = 0..7 sums the splits s = q, q + 8, ... in order, the groups are added in order.
 __global__ void __launch_bounds__(256) reduce_parts_kernel(const float* __restrict__ part, const float* __restrict__ partb,
                                                             int splits, int O, int K, float* __restrict__ dW, int ldw,
                                                             int coloff, float* __restrict__ db) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float sh[8][33];
+  const int e = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int total = O * K;
-  if (idx < total) {
-    float s = 0.f;
-    for (int i = 0; i < splits; ++i) s += part[(int64_t)i * total + idx];
-    dW[(int64_t)(idx / K) * ldw + coloff + idx % K] += s;
+  const int nw = ceil_div(total, 32);              // CTAs [0, nw) reduce dW, the rest db
+  const bool bias = (int)blockIdx.x >= nw;
+  const int idx = (bias ? (int)blockIdx.x - nw : (int)blockIdx.x) * 32 + e;
+  const int n = bias ? O : total;
+  const float* __restrict__ src = bias ? partb : part;
+  float c0 = 0.f, c1 = 0.f;
+  if (idx < n) {
+    int i = grp;
+    for (; i + 8 < splits; i += 16) {
+      c0 += src[(int64_t)i * n + idx];
+      c1 += src[(int64_t)(i + 8) * n + idx];
+    }
+    if (i < splits) c0 += src[(int64_t)i * n + idx];
   }
-  if (db && partb && idx < O) {
-    float s = 0.f;
-    for (int i = 0; i < splits; ++i) s += partb[(int64_t)i * O + idx];
-    db[idx] += s;
+  sh[grp][e] = c0 + c1;
+  __syncthreads();
+  if (grp == 0 && idx < n) {
+    float s = sh[0][e];
+#pragma unroll
+    for (int u = 1; u < 8; ++u) s += sh[u][e];
+    if (bias) db[idx] += s;
+    else dW[(int64_t)(idx / K) * ldw + coloff + idx % K] += s;
   }
 }
 
@@ -767,8 +778,8 @@ int launch_bwd_w(cudaStream_t st, const TrainWs& w, const float* dY, int O, cons
     PGMP_LAUNCH(lin_bwd_w_kernel<true>, grid, 256, 0, st, g);
   else
     PGMP_LAUNCH(lin_bwd_w_kernel<false>, grid, 256, 0, st, g);
-  PGMP_LAUNCH(reduce_parts_kernel, blocks_for((int64_t)O * K), 256, 0, st, w.part, db ? w.partb : nullptr, splits, O, K, dW,
-              ldw, coloff, db);
+  PGMP_LAUNCH(reduce_parts_kernel, (unsigned)(ceil_div(O * K, 32) + (db ? ceil_div(O, 32) : 0)), 256, 0, st, w.part,
+              db ? w.partb : nullptr, splits, O, K, dW, ldw, coloff, db);
   return PGMP_OK;
 }
 

@@ -35,7 +35,7 @@ VARIANTS = {   # name -> (graph, MPN config overrides, weight seed, gradient tol
     "tiny_max_skip_aux": ("tiny_complete", dict(STEPS=3, AUX_LOSS_STEPS=1, **TINY), 46, TIGHT),
     "tiny_add_noskip_update_mlp": ("tiny_complete", dict(AGGR="add", SKIP=False, USE_NODE_UPDATE_MLP=True, STEPS=2, **TINY), 47, TIGHT),
     "tiny_mean_all_steps": ("tiny_complete", dict(AGGR="mean", STEPS=2, AUX_LOSS_STEPS=5, **TINY), 44, TIGHT),
-    "tiny_max_update_mlp": ("tiny_complete", dict(STEPS=4, USE_NODE_UPDATE_MLP=True, **TINY), 48, TIGHT),
+    "tiny_max_update_mlp": ("tiny_complete", dict(STEPS=4, USE_NODE_UPDATE_MLP=True, **TINY), 49, TIGHT),
     # the fixture case: class_agnostic_end2end shape (max aggregation, skip), one auxiliary step; N = 340, E = 20 048
     "agnostic_max": ("knn_small", dict(STEPS=3, AUX_LOSS_STEPS=1), 41, LOOSE),
     "add_noskip_update_mlp": ("knn_small", dict(AGGR="add", SKIP=False, USE_NODE_UPDATE_MLP=True, STEPS=2), 43, LOOSE),
