@@ -165,8 +165,18 @@ class _MpnTrainFunction(torch.autograd.Function):
             p.wu, p.bu = offsets["mpn_node_cls.update_mlp.0.weight"], offsets["mpn_node_cls.update_mlp.0.bias"]
         with torch.cuda.device(dev):
             ws_bytes = int(lib.pgmp_mpn_train_workspace_bytes(p))
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            p.workspace, p.workspace_bytes = ws.data_ptr(), ws_bytes
+            # The activations of all steps live in this workspace until the reverse pass (2.6 GB at 8 images): it is
+            # handed back to a per-module pool after backward() instead of going through the allocator every step.
+            pool = model.__dict__.setdefault("_train_ws_pool", [])
+            stream = torch.cuda.current_stream().cuda_stream       # a pooled workspace is only reused on the stream it was last used on
+            hit = next((e for e in pool if e[0] == stream and e[1].device == dev and e[1].numel() >= ws_bytes), None)
+            if hit is not None:
+                pool.remove(hit)
+                ws = hit[1]
+            else:
+                pool.clear()
+                ws = torch.empty(ws_bytes + ws_bytes // 8, dtype=torch.uint8, device=dev)
+            p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
             nv.check(lib.pgmp_mpn_train_forward(p, nv.current_stream()))
         for mod in model.modules():            # the kernels updated the running statistics in place
             if isinstance(mod, nn.BatchNorm1d):
@@ -175,6 +185,7 @@ class _MpnTrainFunction(torch.autograd.Function):
         ctx.p, ctx.sizes, ctx.shapes = p, sizes, [tuple(q.shape) for q in params]
         ctx.offsets = [offsets[n] for n in names]
         ctx.keep = (flat, x_, ea, ei, ws, edge_logits, node_logits, class_logits)   # the forward's activations live in ws
+        ctx.pool = pool
         ctx.need_x = x.requires_grad
         return edge_logits, node_logits, class_logits
 
@@ -194,6 +205,8 @@ class _MpnTrainFunction(torch.autograd.Function):
             for t in ctx.keep + (de, dn, dc):
                 t.record_stream(torch.cuda.current_stream())
         out = [grads[off:off + k].view(shape) for off, k, shape in zip(ctx.offsets, ctx.sizes, ctx.shapes)]
+        if len(ctx.pool) < 2:
+            ctx.pool.append((torch.cuda.current_stream().cuda_stream, ctx.keep[4]))   # stream-ordered reuse
         return (None, grad_x, None, None) + tuple(out)
 
 
