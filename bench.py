@@ -325,6 +325,21 @@ def run_b200(args, rank, local_rank, world):
     total_images = B * world * args.steps
     total_edges = reduce_sum(edges_per_step) * args.steps
     value = total_images / t_dev
+    # BASELINE.json configs[4] (SURVEY.md 8d config 5) beside the headline: one training step of the agnostic MPN
+    # (GC + forward + reverse pass + gradient all-reduce + Adam), same ranks; scripts/bench_train.py is the stand-alone form
+    train = None
+    try:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("pgmp_bench_train", os.path.join(ROOT, "scripts", "bench_train.py"))
+        bt = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(bt)
+        del feat, tags, sm
+        torch.cuda.empty_cache()
+        r = bt.run_training(bt.parse(["--steps", "5", "--warmup", "3"]), rank, world, dev)
+        if rank == 0:
+            train = {k: r[k] for k in ("value", "unit", "ms_per_step", "ms", "edges_per_s", "config", "allreduce_bytes", "gpu_launches")}
+    except Exception as exc:      # the headline line must not depend on the training row
+        train = {"error": "%s: %s" % (type(exc).__name__, exc)}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -398,24 +413,8 @@ def run_b200(args, rank, local_rank, world):
                               "note": "sigmoid/threshold/GAEC/persons on the step's logits, timed separately "
                                       "(not part of value: the metric is GC + MPN, SURVEY.md 8d)"},
             "graph": {"nodes_per_step_per_gpu": nodes_per_step, "edges_per_step_per_gpu": edges_per_step}}
-    # BASELINE.json configs[4] (SURVEY.md 8d config 5) beside the headline: one training step of the agnostic MPN
-    # (GC + forward + reverse pass + gradient all-reduce + Adam), same ranks; scripts/bench_train.py is the stand-alone form
-    train = None
-    try:
-        import importlib.util
-        spec = importlib.util.spec_from_file_location("pgmp_bench_train", os.path.join(ROOT, "scripts", "bench_train.py"))
-        bt = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(bt)
-        del feat, tags, sm
-        torch.cuda.empty_cache()
-        r = bt.run_training(bt.parse(["--steps", "5", "--warmup", "3"]), rank, world, dev)
-        if rank == 0:
-            train = {k: r[k] for k in ("value", "unit", "ms_per_step", "ms", "edges_per_s", "config", "allreduce_bytes", "gpu_launches")}
-    except Exception as exc:      # the headline line must not depend on the training row
-        train = {"error": "%s: %s" % (type(exc).__name__, exc)}
-    if rank == 0:
-        line["train_step"] = train
-        print(json.dumps(line), flush=True)
+    line["train_step"] = train
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
