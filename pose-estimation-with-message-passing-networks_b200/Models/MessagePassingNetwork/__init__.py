@@ -177,6 +177,9 @@ class _MpnTrainFunction(torch.autograd.Function):
                 pool.clear()
                 ws = torch.empty(ws_bytes + ws_bytes // 8, dtype=torch.uint8, device=dev)
             p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
+            ctx.token = object()                                    # this forward owns the workspace until another forward takes it
+            owners = model.__dict__.setdefault("_train_ws_owner", {})
+            owners[ws.data_ptr()] = ctx.token
             nv.check(lib.pgmp_mpn_train_forward(p, nv.current_stream()))
         for mod in model.modules():            # the kernels updated the running statistics in place
             if isinstance(mod, nn.BatchNorm1d):
@@ -185,7 +188,7 @@ class _MpnTrainFunction(torch.autograd.Function):
         ctx.p, ctx.sizes, ctx.shapes = p, sizes, [tuple(q.shape) for q in params]
         ctx.offsets = [offsets[n] for n in names]
         ctx.keep = (flat, x_, ea, ei, ws, edge_logits, node_logits, class_logits)   # the forward's activations live in ws
-        ctx.pool = pool
+        ctx.pool, ctx.owners = pool, owners
         ctx.need_x = x.requires_grad
         return edge_logits, node_logits, class_logits
 
@@ -194,6 +197,9 @@ class _MpnTrainFunction(torch.autograd.Function):
     def backward(ctx, d_edge, d_node, d_class):
         p = ctx.p
         flat, x_ = ctx.keep[0], ctx.keep[1]
+        if ctx.owners.get(ctx.keep[4].data_ptr()) is not ctx.token:
+            raise RuntimeError("the activations of this forward pass are gone: its workspace went back to the module's pool "
+                               "after the first backward() and a later forward() has reused it")
         dev = flat.device
         grads = torch.zeros_like(flat)
         grad_x = torch.empty_like(x_) if ctx.need_x else None
@@ -205,7 +211,7 @@ class _MpnTrainFunction(torch.autograd.Function):
             for t in ctx.keep + (de, dn, dc):
                 t.record_stream(torch.cuda.current_stream())
         out = [grads[off:off + k].view(shape) for off, k, shape in zip(ctx.offsets, ctx.sizes, ctx.shapes)]
-        if len(ctx.pool) < 2:
+        if len(ctx.pool) < 2 and not any(e[1] is ctx.keep[4] for e in ctx.pool):
             ctx.pool.append((torch.cuda.current_stream().cuda_stream, ctx.keep[4]))   # stream-ordered reuse
         return (None, grad_x, None, None) + tuple(out)
 

@@ -170,3 +170,41 @@ def test_training_per_type_raises():
     with pytest.raises(NotImplementedError):
         model(torch.from_numpy(g["x"]).to(DEV), torch.from_numpy(g["edge_attr"]).to(DEV), torch.from_numpy(g["edge_index"]).to(DEV),
               node_types=torch.from_numpy(g["joint_det"][:, 2]).to(DEV))
+
+
+def test_training_full_size_properties():
+    """BASELINE configs[4] size (8 images of 256 x 256, ~231 k edges, 10 steps), where the oracle is too slow:
+    size-independent properties of the reverse pass.  It is linear in dL/d(logits) -- grads(d1 + d2) = grads(d1) + grads(d2),
+    grads(0) = 0 -- and running it twice on the same forward gives identical bits."""
+    from pgmp_b200.graph_constructor import get_graph_constructor
+    J, K, B = 17, 30, 8
+    data = synthetic.synth_batch(B, J, 256, K, persons=8)
+    t = {k: torch.from_numpy(v).to(DEV) for k, v in data.items()}
+    ret = get_graph_constructor(pgmp_b200.config.bench_gc_config(k=K, graph_type="knn"), scoremaps=t["scoremaps"], tagmaps=t["tagmaps"],
+                                features=t["features"], joints_gt=None, factor_list=None, masks=None, device=DEV, testing=False,
+                                heatmaps=None, num_joints=J).construct_graph()
+    x, edge_attr, edge_index, joint_det = ret[0].clone().requires_grad_(True), ret[1], ret[2], ret[7]
+    assert x.shape[0] == B * J * K and edge_index.shape[1] > 200_000
+    model = synthetic.synth_mpn_state_dict(get_mpn_model(pgmp_b200.config.agnostic_mpn_config(J, AUX_LOSS_STEPS=1)), 7).to(DEV).train()
+    pe, pn, pc, _ = model(x, edge_attr, edge_index, node_types=joint_det[:, 2])
+    outs = [pe[0], pe[1], pn[0], pn[1], pc[0], pc[1]]
+    assert all(bool(torch.isfinite(o).all()) for o in outs)
+    params = [x] + list(model.parameters())
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    d1 = [torch.randn(o.shape, device=DEV, generator=gen) for o in outs]
+    d2 = [torch.randn(o.shape, device=DEV, generator=gen) for o in outs]
+
+    def grads(d):
+        return torch.autograd.grad(outs, params, grad_outputs=d, retain_graph=True)
+
+    g1, g2, g12, g1b = grads(d1), grads(d2), grads([a + b for a, b in zip(d1, d2)]), grads(d1)
+    g0 = grads([torch.zeros_like(o) for o in outs])
+    for a, b, c, a2, z, p in zip(g1, g2, g12, g1b, g0, params):
+        assert torch.equal(a, a2)                                   # reproducible
+        assert float(z.abs().max()) == 0.0                          # zero in, zero out
+        scale = float(c.abs().max()) + 1e-30
+        assert float((a + b - c).abs().max()) <= 2e-4 * scale, (tuple(p.shape), float((a + b - c).abs().max()) / scale)
+    # the activations are gone once another forward has taken the pooled workspace
+    model(x, edge_attr, edge_index, node_types=joint_det[:, 2])
+    with pytest.raises(RuntimeError):
+        grads(d1)
