@@ -14,8 +14,9 @@
 //     dx = S_dst W1_dst + S_src W1_src + T_dst Wm_x,    dW1_dst = S_dst^T x, ...
 // The per-node sums run over CSR bins ordered by edge id, weight gradients are reduced from per-CTA partial
 // tiles in a fixed order: no floating-point atomics anywhere, results are reproducible.
-// All arithmetic is fp32 SIMT (BatchNorm statistics accumulate in fp64); this is the first correct training path,
-// the tensor-core version of the three E-level products is the next step.
+// Arithmetic: the products run on the tensor cores with fp32-accurate 3xTF32 operands (see tile_mma), everything else is
+// fp32 SIMT; BatchNorm statistics accumulate in fp64.  Moving the E-level products to tcgen05 (bf16x3 operand images as in
+// mpn_tc.cu) is the next step.
 #include "common.cuh"
 
 namespace pgmp {
