@@ -84,20 +84,24 @@ __device__ __noinline__ void spill_candidate(uint64_t key, uint64_t* __restrict_
 // the list is irrelevant, keys are unique -- and only lanes that own a candidate execute anything.  A full list
 // spills unfiltered to the global list.  Key = score bits << 32 | ~flat index: one 64-bit compare orders by
 // score desc / index asc.
-__device__ __forceinline__ void emit_candidates(const float (&sc)[4], uint32_t flat0, uint64_t* s_keys, uint32_t* s_cnt,
+__device__ __forceinline__ void emit_candidates(const float (&sc)[4], uint32_t flat0, uint32_t s_keys_a, uint32_t s_cnt_a,
                                                 uint64_t* __restrict__ gkeys, uint32_t* __restrict__ gcount, int cand_cap,
                                                 uint32_t* __restrict__ flags) {
   // a loop over the thread's candidates, not four predicated blocks: its trip count across the warp is the largest
-  // number of candidates any lane holds (almost always 0 or 1), and each trip costs one (warp-aggregated) atomic
+  // number of candidates any lane holds (almost always 0 or 1).  The list is addressed in the shared state space
+  // (32-bit addresses formed once per kernel) and the slot comes from a plain per-lane shared atomic: the
+  // compiler's warp-aggregated form (vote + leader election + two popcounts + shuffle) costs more instructions
+  // than the handful of same-address conflicts it saves.
   uint32_t vm = (sc[0] > 0.f ? 1u : 0u) | (sc[1] > 0.f ? 2u : 0u) | (sc[2] > 0.f ? 4u : 0u) | (sc[3] > 0.f ? 8u : 0u);
   while (vm) {
     const int i = __ffs(vm) - 1;
     vm &= vm - 1;
     const float v = i == 0 ? sc[0] : (i == 1 ? sc[1] : (i == 2 ? sc[2] : sc[3]));
-    const uint64_t key = ((uint64_t)__float_as_uint(v) << 32) | (uint64_t)(~(flat0 + (uint32_t)i));
-    const uint32_t pos = atomicAdd(s_cnt, 1u);
-    if (pos < kCtaCandCap) s_keys[pos] = key;
-    else spill_candidate(key, gkeys, gcount, cand_cap, flags);
+    const uint32_t hi = __float_as_uint(v), lo = ~(flat0 + (uint32_t)i);
+    uint32_t pos;
+    asm volatile("atom.shared.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(pos) : "r"(s_cnt_a) : "memory");   // inc with a bound never reached: ptxas warp-aggregates add (and inc 0xffffffff)
+    if (pos < kCtaCandCap) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(s_keys_a + pos * 8u), "r"(lo), "r"(hi) : "memory");
+    else spill_candidate(((uint64_t)hi << 32) | (uint64_t)lo, gkeys, gcount, cand_cap, flags);
   }
 }
 
@@ -218,7 +222,8 @@ struct NmsCtx {
   LoadPlan lp;
   const float* map; const float* mk;
   int H, W, tt, lane, y0, y_end;
-  uint64_t* s_keys; uint32_t* s_cnt; uint64_t* gkeys; uint32_t* gcount; int cand_cap; uint32_t* flags;
+  uint32_t s_keys_a, s_cnt_a;   // shared-state-space addresses of the CTA's candidate list and its counter
+  uint64_t* gkeys; uint32_t* gcount; int cand_cap; uint32_t* flags;
 };
 
 template <int R, int PH, bool VEC, bool MASK>
@@ -269,7 +274,7 @@ __device__ __forceinline__ void nms_row_step(NmsRings<R>& rg, const NmsCtx& c, c
       // (out-of-image columns hold zeros, so x > 0 already excludes them)
       if (x > 0.f && x == m) sc[q] = MASK ? x * __ldg(c.mk + (yc * c.W + 4 * c.tt + q)) : x;   // CG.py:1163-1165
     }
-    emit_candidates(sc, (uint32_t)(yc * c.W + 4 * c.tt), c.s_keys, c.s_cnt, c.gkeys, c.gcount, c.cand_cap, c.flags);
+    emit_candidates(sc, (uint32_t)(yc * c.W + 4 * c.tt), c.s_keys_a, c.s_cnt_a, c.gkeys, c.gcount, c.cand_cap, c.flags);
   }
 }
 
@@ -316,7 +321,7 @@ __global__ void __launch_bounds__(256) nms_candidates_kernel(
     lp.has_r = c.lane == 31 && c.tt + 1 < chunks;
     lp.n_v = min(4, W - lp.off_v); lp.n_l = min(4, W - lp.off_l); lp.n_r = min(4, W - lp.off_r);
   }
-  c.s_keys = s_keys; c.s_cnt = &s_cnt;
+  c.s_keys_a = (uint32_t)__cvta_generic_to_shared(s_keys); c.s_cnt_a = (uint32_t)__cvta_generic_to_shared(&s_cnt);
   c.gkeys = cand_keys + (size_t)bj * cand_cap; c.gcount = &cand_count[bj]; c.cand_cap = cand_cap; c.flags = flags;
   if (t == 0) s_cnt = 0;
   __syncthreads();
