@@ -87,3 +87,46 @@ def test_factories_follow_the_reference_contract():
     assert sum(p.numel() for p in a.parameters()) == 101203
     with pytest.raises(NotImplementedError):
         m.train()(torch.zeros(1), torch.zeros(1), torch.zeros(1), node_types=None)
+
+
+def test_training_mlp_descriptor_follows_make_mlp():
+    """Host logic of the training path (no GPU): a ``make_mlp`` chain maps onto ``pgmp_mlp_train`` layer by layer --
+    ReLU before BatchNorm (layers.py:11-14), last Linear bare unless END_WITH_RELU, offsets from the flat layout."""
+    import torch
+
+    import pgmp_b200
+    from pgmp_b200.Models.MessagePassingNetwork import _mlp_train_struct, get_mpn_model
+
+    model = get_mpn_model(pgmp_b200.config.agnostic_mpn_config(17, STEPS=2))
+    offsets, off = {}, 0
+    for n, p in model.named_parameters():
+        offsets[n] = off
+        off += (p.numel() + 3) // 4 * 4
+    m = _mlp_train_struct(model.edge_embedding, "edge_embedding", offsets)
+    assert m.n_layers == 4 and list(m.dims)[:5] == [19, 32, 64, 64, 64]
+    assert list(m.relu)[:4] == [1, 1, 1, 0] and list(m.bn)[:4] == [1, 1, 1, 0]
+    assert m.w[1] == offsets["edge_embedding.3.weight"] and m.gamma[1] == offsets["edge_embedding.5.weight"]
+    assert m.running_mean[0] == model.edge_embedding[2].running_mean.data_ptr()
+    h = _mlp_train_struct(model.classification, "classification", offsets)
+    assert h.n_layers == 3 and list(h.dims)[:4] == [64, 64, 32, 17] and list(h.relu)[:3] == [1, 1, 0] and not any(h.bn)
+    assert all(o % 4 == 0 for o in offsets.values())            # 16-byte aligned pieces (vectorised loads)
+    cfg = pgmp_b200.config.agnostic_mpn_config(17, STEPS=2)
+    cfg.NODE_EMB.END_WITH_RELU = True
+    e = _mlp_train_struct(get_mpn_model(cfg).node_embedding, "node_embedding",
+                          {n: 0 for n, _ in get_mpn_model(cfg).named_parameters()})
+    assert list(e.relu)[:3] == [1, 1, 1] and list(e.bn)[:3] == [1, 1, 1]
+
+
+def test_training_mode_rejects_cpu_tensors():
+    import pytest
+    import torch
+
+    import pgmp_b200
+    from pgmp_b200.Models.MessagePassingNetwork import get_mpn_model
+
+    model = get_mpn_model(pgmp_b200.config.agnostic_mpn_config(17, STEPS=2)).train()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        model(torch.zeros(4, 128), torch.zeros(2, 19), torch.zeros(2, 2, dtype=torch.int64), node_types=torch.zeros(4, dtype=torch.int64))
+    flagship = get_mpn_model(pgmp_b200.config.flagship_mpn_config(17, STEPS=2)).train()
+    with pytest.raises(NotImplementedError):
+        flagship(torch.zeros(4, 128), torch.zeros(2, 19), torch.zeros(2, 2, dtype=torch.int64), node_types=torch.zeros(4, dtype=torch.int64))
