@@ -147,6 +147,14 @@ typedef struct pgmp_gather_conv_params {
 /* x = interpolate(feature_gather(feat))[:, y, x] at the candidates only; stream-ordered after pgmp_gc_emit */
 int pgmp_gc_gather_conv(const pgmp_gather_conv_params* p, pgmp_stream_t stream);
 
+/* Reverse of the node-feature gather of pgmp_gc_emit (x[n, :] = features[b, :, y, x], ConstructGraph.py:265, 269) under
+ * autograd -- end-to-end training, train.py:232: d_features[b, :, y, x] = sum of grad_x[n, :] over the nodes at that pixel
+ * (candidates of different joint types can share one), summed in node order without atomics.  d_features ([B, C, H, W],
+ * strides in elements) must be zero-filled by the caller; pixels without a node are not touched. */
+int pgmp_gc_gather_backward(const float* grad_x, const int64_t* joint_det, const int64_t* batch_index, int64_t num_nodes,
+                            int32_t channels, float* d_features, int64_t stride_b, int64_t stride_c, int64_t stride_y,
+                            int64_t stride_x, pgmp_stream_t stream);
+
 typedef struct pgmp_mlp {
   int32_t n_layers;
   int32_t dims[PGMP_MAX_LAYERS + 1];   /* dims[0] = input width, dims[l+1] = output width of layer l */

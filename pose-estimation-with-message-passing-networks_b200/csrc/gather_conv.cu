@@ -185,3 +185,73 @@ extern "C" int pgmp_gc_gather_conv(const pgmp_gather_conv_params* p, pgmp_stream
   }
   return PGMP_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Reverse of the plain node-feature gather x[n, :] = features[b, :, y, x] (ConstructGraph.py:265, 269) under autograd
+// (end-to-end training, train.py:232): d_features[b, :, y, x] = sum of grad_x[n, :] over the nodes at that pixel.
+// Candidates of different joint types can share a pixel; the first node of a pixel (in node order) sums its
+// duplicates in node order and stores the result, so there is no floating-point atomic and the sum order is fixed.
+// ------------------------------------------------------------------------------------------------
+namespace pgmp {
+namespace {
+
+constexpr int kGbMaxChunks = 8;   // channels <= 256
+
+__global__ void __launch_bounds__(256) gather_backward_kernel(const float* __restrict__ grad_x, const int64_t* __restrict__ joint_det,
+                                                               const int64_t* __restrict__ batch_index, int64_t N, int C,
+                                                               float* __restrict__ df, int64_t sb, int64_t sc, int64_t sy, int64_t sx) {
+  const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (n >= N) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t b = batch_index[n], x = joint_det[n * 3], y = joint_det[n * 3 + 1];
+  // the image's nodes are contiguous (batch_index ascends): [lo, hi)
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {       // first index with batch_index == b
+    const int64_t mid = (lo + hi) >> 1;
+    if (batch_index[mid] < b) lo = mid + 1; else hi = mid;
+  }
+  const int64_t first = lo;
+  lo = n; hi = N;
+  while (lo < hi) {       // first index with batch_index > b
+    const int64_t mid = (lo + hi) >> 1;
+    if (batch_index[mid] <= b) lo = mid + 1; else hi = mid;
+  }
+  const int64_t last = lo;
+  float acc[kGbMaxChunks];
+#pragma unroll
+  for (int i = 0; i < kGbMaxChunks; ++i) acc[i] = (lane + 32 * i < C) ? grad_x[n * C + lane + 32 * i] : 0.f;
+  for (int64_t base = first; base < last; base += 32) {
+    const int64_t m = base + lane;
+    const bool same = m < last && m != n && joint_det[m * 3] == x && joint_det[m * 3 + 1] == y;
+    uint32_t hits = __ballot_sync(0xffffffffu, same);
+    if (base < n && (hits & (n - base >= 32 ? 0xffffffffu : ((1u << (n - base)) - 1u)))) return;   // an earlier node owns the pixel
+    while (hits) {          // later nodes at the same pixel, ascending
+      const int64_t d = base + (__ffs(hits) - 1);
+      hits &= hits - 1;
+#pragma unroll
+      for (int i = 0; i < kGbMaxChunks; ++i)
+        if (lane + 32 * i < C) acc[i] += grad_x[d * C + lane + 32 * i];
+    }
+  }
+  float* __restrict__ dst = df + b * sb + y * sy + x * sx;
+#pragma unroll
+  for (int i = 0; i < kGbMaxChunks; ++i)
+    if (lane + 32 * i < C) dst[(int64_t)(lane + 32 * i) * sc] = acc[i];
+}
+
+}  // namespace
+}  // namespace pgmp
+
+extern "C" int pgmp_gc_gather_backward(const float* grad_x, const int64_t* joint_det, const int64_t* batch_index,
+                                       int64_t num_nodes, int32_t channels, float* d_features, int64_t stride_b,
+                                       int64_t stride_c, int64_t stride_y, int64_t stride_x, pgmp_stream_t stream) {
+  using namespace pgmp;
+  if (num_nodes < 0 || channels <= 0 || channels > 32 * kGbMaxChunks)
+    return set_error(PGMP_ERR_INVALID, "bad sizes (channels <= %d)", 32 * kGbMaxChunks);
+  if (num_nodes == 0) return PGMP_OK;
+  if (!grad_x || !joint_det || !batch_index || !d_features) return set_error(PGMP_ERR_INVALID, "null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PGMP_LAUNCH(gather_backward_kernel, (unsigned)ceil_div<int64_t>(num_nodes * 32, 256), 256, 0, st, grad_x, joint_det,
+              batch_index, num_nodes, (int)channels, d_features, stride_b, stride_c, stride_y, stride_x);
+  return PGMP_OK;
+}

@@ -28,8 +28,12 @@ class _GatherNodeFeatures(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad):
         batch_index, joint_det = ctx.saved_tensors
-        g = torch.zeros(ctx.feat_shape, dtype=grad.dtype, device=grad.device)
-        g.index_put_((batch_index, slice(None), joint_det[:, 1], joint_det[:, 0]), grad, accumulate=True)
+        g = torch.zeros(ctx.feat_shape, dtype=torch.float32, device=grad.device)     # the dense gradient the backbone expects
+        gx = grad.contiguous().float()
+        with torch.cuda.device(grad.device):
+            nv.check(nv.lib().pgmp_gc_gather_backward(gx.data_ptr(), joint_det.data_ptr(), batch_index.data_ptr(), gx.shape[0],
+                                                      gx.shape[1], g.data_ptr(), g.stride(0), g.stride(1), g.stride(2),
+                                                      g.stride(3), nv.current_stream()))
         return g, None, None, None
 
 

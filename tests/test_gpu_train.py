@@ -208,3 +208,35 @@ def test_training_full_size_properties():
     model(x, edge_attr, edge_index, node_types=joint_det[:, 2])
     with pytest.raises(RuntimeError):
         grads(d1)
+
+
+def test_gather_gradient_reaches_the_feature_maps():
+    """End-to-end training (train.py:232): dL/dx flows back into the feature maps through pgmp_gc_gather_backward.
+    Three joint types share their heatmap here, so their candidates share pixels and the kernel has to sum duplicates;
+    the result is bit-identical to the sequential numpy scatter-add (same order of additions)."""
+    from pgmp_b200.graph_constructor import get_graph_constructor
+    J, K = 6, 8
+    data = synthetic.synth_batch(3, J, 96, K, channels=40, persons=2, width=128)
+    data["scoremaps"][:, 1] = data["scoremaps"][:, 0]
+    data["scoremaps"][:, 2] = data["scoremaps"][:, 0]
+    feat = torch.from_numpy(data["features"]).to(DEV).requires_grad_(True)
+    ret = get_graph_constructor(pgmp_b200.config.bench_gc_config(k=K, graph_type="knn"), scoremaps=torch.from_numpy(data["scoremaps"]).to(DEV),
+                                tagmaps=torch.from_numpy(data["tagmaps"]).to(DEV), features=feat, joints_gt=None, factor_list=None,
+                                masks=None, device=DEV, testing=False, heatmaps=None, num_joints=J).construct_graph()
+    x, joint_det, batch_index = ret[0], ret[7].cpu().numpy(), ret[12].cpu().numpy()
+    assert x.requires_grad
+    pix = {(b, y, xx) for b, (xx, y, _) in zip(batch_index, joint_det)}
+    assert len(pix) < len(joint_det)                                   # duplicates are present
+    coeff = np.random.default_rng(5).standard_normal(tuple(x.shape)).astype(np.float32)
+    (x * torch.from_numpy(coeff).to(DEV)).sum().backward()
+    want = np.zeros(data["features"].shape, np.float32)
+    for n in range(len(joint_det)):                                    # sequential, node order
+        want[batch_index[n], :, joint_det[n, 1], joint_det[n, 0]] += coeff[n]
+    assert np.array_equal(feat.grad.cpu().numpy(), want)
+    # channels-last feature maps (the strides are honoured)
+    feat2 = torch.from_numpy(data["features"]).to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    ret2 = get_graph_constructor(pgmp_b200.config.bench_gc_config(k=K, graph_type="knn"), scoremaps=torch.from_numpy(data["scoremaps"]).to(DEV),
+                                 tagmaps=torch.from_numpy(data["tagmaps"]).to(DEV), features=feat2, joints_gt=None, factor_list=None,
+                                 masks=None, device=DEV, testing=False, heatmaps=None, num_joints=J).construct_graph()
+    (ret2[0] * torch.from_numpy(coeff).to(DEV)).sum().backward()
+    assert np.array_equal(feat2.grad.cpu().numpy(), want)
