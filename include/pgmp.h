@@ -147,6 +147,17 @@ typedef struct pgmp_gather_conv_params {
 /* x = interpolate(feature_gather(feat))[:, y, x] at the candidates only; stream-ordered after pgmp_gc_emit */
 int pgmp_gc_gather_conv(const pgmp_gather_conv_params* p, pgmp_stream_t stream);
 
+/* Scoremap assembly in front of the NMS -- hr_process_output (src/Models/HigherHRNet/hrnet.py:587-611):
+ *   up = interpolate(stage1 [B, C1, h, w], size = (H, W), bilinear, align_corners = False)
+ *   scoremaps [B, J, H, W] = (stage2 + up[:, :J]) / 2 (PGMP_ASSEMBLE_AVG) or up[:, :J] (PGMP_ASSEMBLE_SMALL)
+ *   tags [B, C1 - J, H, W] = up[:, J:]                (skipped when tags == NULL)
+ * in one pass over the outputs.  All pointers device, contiguous float32. */
+#define PGMP_ASSEMBLE_AVG 0
+#define PGMP_ASSEMBLE_SMALL 1
+int pgmp_gc_assemble_scoremaps(const float* stage1, const float* stage2, int32_t batch, int32_t channels1, int32_t num_joints,
+                               int32_t h, int32_t w, int32_t H, int32_t W, int32_t mode, float* scoremaps, float* tags,
+                               pgmp_stream_t stream);
+
 /* Reverse of the node-feature gather of pgmp_gc_emit (x[n, :] = features[b, :, y, x], ConstructGraph.py:265, 269) under
  * autograd -- end-to-end training, train.py:232: d_features[b, :, y, x] = sum of grad_x[n, :] over the nodes at that pixel
  * (candidates of different joint types can share one), summed in node order without atomics.  d_features ([B, C, H, W],

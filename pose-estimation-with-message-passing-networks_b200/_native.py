@@ -132,6 +132,8 @@ SYMBOLS = {
     "pgmp_gc_detect": (C.c_int, [C.POINTER(GcParams), C.c_void_p, C.c_void_p]),
     "pgmp_gc_emit": (C.c_int, [C.POINTER(GcParams), C.POINTER(GcOutputs), C.c_void_p]),
     "pgmp_gc_gather_conv": (C.c_int, [C.POINTER(GatherConvParams), C.c_void_p]),
+    "pgmp_gc_assemble_scoremaps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                             C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pgmp_gc_gather_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64,
                                           C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
     "pgmp_selftest_umma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

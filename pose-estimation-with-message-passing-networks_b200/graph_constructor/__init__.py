@@ -234,6 +234,32 @@ class NaiveGraphConstructor:
                 batch_index, None, joint_tags)
 
 
+def hr_process_output(output, mode, num_joints):
+    """Drop-in for the closure ``create_process_func_hr(config)`` returns (src/Models/HigherHRNet/hrnet.py:587-611):
+    ``output = ((scoremap_1, scoremap_2), features)`` -> ``(scoremaps, features, tags)``.  The bilinear up-sampling of the
+    half-resolution stage, the average with the full-resolution stage and the tag maps come out of ONE CUDA kernel
+    (``pgmp_gc_assemble_scoremaps``) instead of interpolate + add + divide over the full maps."""
+    (s1, s2), features = output
+    if mode == "large":
+        return s2, features, s1[:, num_joints:]
+    if mode not in ("avg", "small"):
+        raise NotImplementedError(mode)
+    nv.require_cuda(s1, "scoremap_1", torch.float32)
+    nv.require_cuda(s2, "scoremap_2", torch.float32)
+    s1c, s2c = s1.detach().contiguous(), s2.detach().contiguous()
+    B, C1, h, w = s1c.shape
+    H, W = s2c.shape[2], s2c.shape[3]
+    if C1 < num_joints or s2c.shape[0] != B or (mode == "avg" and s2c.shape[1] != num_joints):
+        raise ValueError("scoremap_1 must be [B, >= J, h, w] and scoremap_2 [B, J, H, W]")
+    scoremaps = torch.empty((B, num_joints, H, W), dtype=torch.float32, device=s1.device)
+    tags = torch.empty((B, C1 - num_joints, H, W), dtype=torch.float32, device=s1.device)
+    with torch.cuda.device(s1.device):
+        nv.check(nv.lib().pgmp_gc_assemble_scoremaps(s1c.data_ptr(), s2c.data_ptr(), B, C1, num_joints, h, w, H, W,
+                                                     0 if mode == "avg" else 1, scoremaps.data_ptr(),
+                                                     tags.data_ptr() if C1 > num_joints else None, nv.current_stream()))
+    return scoremaps, features, tags
+
+
 def get_graph_constructor(config, **kwargs):
     """src/graph_constructor/__init__.py:4-5."""
     return NaiveGraphConstructor(config=config, **kwargs)
