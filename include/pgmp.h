@@ -347,6 +347,27 @@ typedef struct pgmp_group_params {
 uint64_t pgmp_group_workspace_bytes(const pgmp_group_params* p);
 int pgmp_group_persons(const pgmp_group_params* p, pgmp_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Pose-assembly tail of pred_to_ann (src/Utils/Utils.py:1472-1477): refine (:1026-1104) -- joints a person is missing
+ * are looked up in the heatmaps where the tag is closest to the person's mean tag -- and adjust (:917-936), batched
+ * over images and persons; `persons` is updated in place.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pgmp_refine_params {
+  int32_t batch, num_joints, height, width;
+  int32_t tag_dim;                     /* T of tags [B, J, H, W, T] (1 for [B, J, H, W]) */
+  int32_t max_persons;
+  int32_t do_refine, do_adjust;        /* with_refine / adjustment of pred_to_ann */
+  const float* scoremaps;              /* device [B, J, H, W] */
+  const float* tags;                   /* device [B, J, H, W, T] */
+  double* persons;                     /* device [B][max_persons][J][3] (x, y, score), as pgmp_group_persons writes them */
+  const int32_t* num_persons;          /* device [B] */
+  void* workspace;
+  uint64_t workspace_bytes;
+} pgmp_refine_params;
+
+uint64_t pgmp_refine_workspace_bytes(const pgmp_refine_params* p);
+int pgmp_refine_persons(const pgmp_refine_params* p, pgmp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

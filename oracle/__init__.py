@@ -28,4 +28,4 @@ Parity status ("Oracle"):
   with the tie rule written down in the function docstrings.
 """
 
-from . import assemble, gc, mpn, grouping  # noqa: F401
+from . import assemble, gc, mpn, grouping, refine  # noqa: F401

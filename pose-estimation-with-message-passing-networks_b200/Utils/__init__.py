@@ -88,3 +88,39 @@ def group_persons(joint_det, node_logits, edge_index, edge_logits, class_logits,
         out.append((persons_h[b, :npers_h[b]].copy() if npers_h[b] else np.array([]), bool(mut_h[b]),
                     labels[node_off_h[b]:node_off_h[b + 1]]))
     return out
+
+
+def refine_persons(scoremaps, tags, persons, with_refine=True, adjustment=True):
+    """The pose-assembly tail of ``pred_to_ann`` (``src/Utils/Utils.py:1472-1477``) for a whole batch: ``refine``
+    (:1026-1104) places the joints a person is missing where the heatmap is high and the tag is close to the person's
+    mean tag, ``adjust`` (:917-936) adds the quarter-pixel offsets.  ``scoremaps [B, J, H, W]`` and ``tags [B, J, H, W]``
+    (or ``[B, J, H, W, T]``) are CUDA float32 tensors, ``persons`` is a list with one ``[P, J, 3]`` float64 array
+    (x, y, score; e.g. ``group_persons(...)[b][0]`` after ``fill_mean``) or ``None`` per image.  Returns the updated list.
+    """
+    nv.require_cuda(scoremaps, "scoremaps", torch.float32)
+    nv.require_cuda(tags, "tags", torch.float32)
+    B, J, H, W = scoremaps.shape
+    if len(persons) != B or tags.shape[:4] != scoremaps.shape:
+        raise ValueError("one persons entry per image; tags must be [B, J, H, W(, T)]")
+    T = tags.shape[4] if tags.dim() == 5 else 1
+    counts = [0 if q is None or len(q) == 0 else int(q.shape[0]) for q in persons]
+    pmax = max(counts + [1])
+    host = np.zeros((B, pmax, J, 3), dtype=np.float64)
+    for b, q in enumerate(persons):
+        if counts[b]:
+            host[b, :counts[b]] = q
+    dev = scoremaps.device
+    kp = torch.from_numpy(host).to(dev)
+    npers = torch.tensor(counts, dtype=torch.int32, device=dev)
+    sm, tg = scoremaps.contiguous(), tags.contiguous()
+    p = nv.RefineParams(batch=B, num_joints=J, height=H, width=W, tag_dim=T, max_persons=pmax, do_refine=int(bool(with_refine)),
+                        do_adjust=int(bool(adjustment)), scoremaps=sm.data_ptr(), tags=tg.data_ptr(), persons=kp.data_ptr(),
+                        num_persons=npers.data_ptr())
+    lib = nv.lib()
+    with torch.cuda.device(dev):
+        ws_bytes = int(lib.pgmp_refine_workspace_bytes(p))
+        ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+        p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
+        nv.check(lib.pgmp_refine_persons(p, nv.current_stream()))
+    out_h = kp.cpu().numpy()
+    return [None if q is None else (out_h[b, :counts[b]].copy() if counts[b] else q) for b, q in enumerate(persons)]

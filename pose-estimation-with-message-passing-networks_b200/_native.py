@@ -121,6 +121,13 @@ class GroupParams(C.Structure):
                 ("workspace_bytes", C.c_uint64)]
 
 
+class RefineParams(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("num_joints", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
+                ("tag_dim", C.c_int32), ("max_persons", C.c_int32), ("do_refine", C.c_int32), ("do_adjust", C.c_int32),
+                ("scoremaps", C.c_void_p), ("tags", C.c_void_p), ("persons", C.c_void_p), ("num_persons", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64)]
+
+
 # every symbol include/pgmp.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "pgmp_version": (C.c_int, []),
@@ -145,6 +152,8 @@ SYMBOLS = {
     "pgmp_mpn_train_backward": (C.c_int, [C.POINTER(MpnTrainParams), C.c_void_p]),
     "pgmp_group_workspace_bytes": (C.c_uint64, [C.POINTER(GroupParams)]),
     "pgmp_group_persons": (C.c_int, [C.POINTER(GroupParams), C.c_void_p]),
+    "pgmp_refine_workspace_bytes": (C.c_uint64, [C.POINTER(RefineParams)]),
+    "pgmp_refine_persons": (C.c_int, [C.POINTER(RefineParams), C.c_void_p]),
 }
 
 _lib = None

@@ -90,3 +90,40 @@ def sample_indices(n, name):
         return np.arange(n)
     rng = np.random.default_rng(int.from_bytes(hashlib.sha256(name.encode()).digest()[:4], "little"))
     return np.sort(rng.choice(n, 64, replace=False))
+
+
+# ---- pose-assembly tail (refine / adjust): name -> (batch, joints, height, width, tag dim or None, persons per image, seed)
+REFINE_CASES = {
+    "coco_t1": (2, 17, 64, 80, None, (5, 3), 1),
+    "tags2": (1, 17, 48, 48, 2, (4,), 2),
+    "crowd14": (1, 14, 40, 56, None, (9,), 3),
+}
+
+
+def refine_inputs(name):
+    """Seeded inputs of a REFINE case: scoremaps [B,J,H,W] f32, tags [B,J,H,W(,T)] f32, keypoints: list of [P,J,3] f64
+    (x, y, score) with about a third of the joints missing (score 0, position = the mean of the detected ones as
+    ``fill_mean`` leaves them, Utils.py:1469-1471)."""
+    import numpy as np
+    B, J, H, W, T, persons, seed = REFINE_CASES[name]
+    rng = np.random.default_rng(7000 + seed)
+    sm = rng.uniform(0, 0.05, (B, J, H, W)).astype(np.float32)
+    for b in range(B):
+        for j in range(J):
+            for _ in range(6):
+                y, x = int(rng.integers(1, H - 1)), int(rng.integers(1, W - 1))
+                sm[b, j, y - 1:y + 2, x - 1:x + 2] += rng.uniform(0.1, 0.9, (3, 3)).astype(np.float32)
+    shape = (B, J, H, W) if T is None else (B, J, H, W, T)
+    tags = (rng.standard_normal(shape) * 2.0).astype(np.float32)
+    kps = []
+    for b in range(B):
+        k = np.zeros((persons[b], J, 3), np.float64)
+        for p in range(persons[b]):
+            det = rng.uniform(size=J) > 0.35
+            det[int(rng.integers(0, J))] = True
+            k[p, :, 0] = rng.integers(0, W, J) + rng.choice([0.0, 0.25, 0.5], J)
+            k[p, :, 1] = rng.integers(0, H, J) + rng.choice([0.0, 0.25, 0.5], J)
+            k[p, :, 2] = np.where(det, rng.uniform(0.1, 1.0, J), 0.0)
+            k[p, ~det, :2] = k[p, det, :2].mean(axis=0)
+        kps.append(k)
+    return sm, tags, kps
