@@ -124,3 +124,35 @@ def refine_persons(scoremaps, tags, persons, with_refine=True, adjustment=True):
         nv.check(lib.pgmp_refine_persons(p, nv.current_stream()))
     out_h = kp.cpu().numpy()
     return [None if q is None else (out_h[b, :counts[b]].copy() if counts[b] else q) for b, q in enumerate(persons)]
+
+
+def filter_and_fill(persons, with_filter=False, fill_mean=True):
+    """The host steps of ``pred_to_ann`` between the grouping and ``refine`` (``src/Utils/Utils.py:1463-1471``) for one
+    image: ``with_filter`` keeps the persons whose best joint score exceeds 0.25 (returns ``None`` when none is left, as
+    the reference returns no annotation), ``fill_mean`` moves every missing joint (score 0) to the mean position of the
+    person's detected joints.  ``persons`` is a ``[P, J, 3]`` float64 array (x, y, score); a copy is returned."""
+    p = np.array(persons, dtype=np.float64, copy=True)
+    if p.ndim != 3:                                    # Utils.py:1458-1460: no person
+        return None
+    if with_filter:
+        p = p[p[:, :, 2].max(axis=1) > 0.25]
+        if p.shape[0] == 0:
+            return None
+    if fill_mean:
+        for i in range(len(p)):
+            missing = p[i, :, 2] == 0
+            p[i, missing, :2] = p[i, ~missing, :2].mean(axis=0)
+    return p
+
+
+def persons_from_groups(scoremaps, tags, groups, with_refine=True, adjustment=True, with_filter=False, fill_mean=True):
+    """``pred_to_ann`` from the grouping to the final keypoints (``Utils.py:1458-1477``) for a whole batch:
+    ``groups`` is what ``group_persons`` returns; per image ``filter_and_fill`` on the host (a few dozen floats), then
+    ``refine`` / ``adjust`` for all images in one device call.  Returns one ``[P, J, 3]`` float64 array or ``None`` per image
+    (the input of ``reverse_affine_map``, :1478)."""
+    persons = []
+    for g in groups:
+        persons.append(None if g is None else filter_and_fill(g[0], with_filter, fill_mean))
+    if not (with_refine or adjustment) or all(q is None for q in persons):
+        return persons
+    return refine_persons(scoremaps, tags, persons, with_refine=with_refine, adjustment=adjustment)

@@ -69,3 +69,44 @@ def test_cuda_refine_ragged_batch_and_full_size():
     out = refine_persons(torch.from_numpy(sm).cuda(), torch.from_numpy(tags).cuda(), kps)
     assert out[0] is None and out[2].shape == (0, J, 3)
     assert np.array_equal(out[1], R.adjust(R.refine(sm[1], tags[1], k), sm[1]))
+
+
+def test_filter_and_fill_follows_pred_to_ann():
+    """Host steps of pred_to_ann (Utils.py:1463-1471), stated directly."""
+    from pgmp_b200.Utils import filter_and_fill
+    rng = np.random.default_rng(2)
+    p = np.zeros((4, 17, 3))
+    p[:, :, :2] = rng.uniform(0, 100, (4, 17, 2))
+    p[:, :, 2] = np.where(rng.uniform(size=(4, 17)) > 0.4, rng.uniform(0.05, 1.0, (4, 17)), 0.0)
+    p[2, :, 2] = np.where(p[2, :, 2] > 0, 0.2, 0.0)                  # best score 0.2: filtered
+    p[:, 3, 2] = np.maximum(p[:, 3, 2], 0.1)
+    want = p.copy()
+    keep = want[:, :, 2].max(axis=1) > 0.25
+    want = want[keep]
+    for i in range(len(want)):
+        want[i, want[i, :, 2] == 0, :2] = want[i, want[i, :, 2] != 0, :2].mean(axis=0)
+    got = filter_and_fill(p, with_filter=True, fill_mean=True)
+    assert got.shape[0] == 3 and np.array_equal(got, want)
+    assert np.array_equal(filter_and_fill(p, with_filter=False, fill_mean=False), p)
+    assert filter_and_fill(np.array([]), True, True) is None
+    low = p.copy()
+    low[:, :, 2] *= 0.1
+    assert filter_and_fill(low, with_filter=True) is None
+
+
+@pytest.mark.gpu
+def test_persons_from_groups_chain():
+    """group_persons output -> filter / fill (host) -> refine + adjust (device) against the oracle chain."""
+    from pgmp_b200.Utils import filter_and_fill, persons_from_groups
+    sm, tags, kps = refine_inputs("coco_t1")
+    raw = []
+    for k in kps:                                                    # undo the fixture's fill: arbitrary positions at missing joints
+        r = k.copy()
+        r[r[:, :, 2] == 0, :2] = 0.0
+        raw.append(r)
+    groups = [(raw[0], False, None), None]
+    got = persons_from_groups(torch.from_numpy(sm).cuda(), torch.from_numpy(tags).cuda(), groups, with_filter=True)
+    assert got[1] is None
+    want = filter_and_fill(raw[0], True, True)
+    want = R.adjust(R.refine(sm[0], tags[0], want), sm[0])
+    assert np.array_equal(got[0], want)
