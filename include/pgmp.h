@@ -252,7 +252,7 @@ int pgmp_mpn_forward(const pgmp_mpn_params* p, pgmp_stream_t stream);
  * with batch statistics (layers.py:13-14, 22-23), running statistics updated in place -- with the
  * type-agnostic MPLayer (layers.py:32-86; AGGR max / add / mean, SKIP, USE_NODE_UPDATE_MLP), and the
  * reverse pass torch autograd runs for the reference (train.py:232-236): gradients of every
- * parameter and of the node input x.  fp32 throughout.
+ * parameter and of the node input x.  fp32-accurate throughout (products: tensor cores with the 3xTF32 operand split; statistics in fp64).
  *
  * Parameters and their gradients are two flat fp32 device buffers with the same element offsets;
  * every matrix keeps the layout of its nn.Linear.weight, [out][in].
