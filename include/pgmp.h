@@ -161,7 +161,8 @@ int pgmp_gc_assemble_scoremaps(const float* stage1, const float* stage2, int32_t
 /* Reverse of the node-feature gather of pgmp_gc_emit (x[n, :] = features[b, :, y, x], ConstructGraph.py:265, 269) under
  * autograd -- end-to-end training, train.py:232: d_features[b, :, y, x] = sum of grad_x[n, :] over the nodes at that pixel
  * (candidates of different joint types can share one), summed in node order without atomics.  d_features ([B, C, H, W],
- * strides in elements) must be zero-filled by the caller; pixels without a node are not touched. */
+ * strides in elements) must be zero-filled by the caller; pixels without a node are not touched.  joint_det / batch_index are
+ * the arrays pgmp_gc_emit wrote (batch_index ascending: the nodes of an image are contiguous). */
 int pgmp_gc_gather_backward(const float* grad_x, const int64_t* joint_det, const int64_t* batch_index, int64_t num_nodes,
                             int32_t channels, float* d_features, int64_t stride_b, int64_t stride_c, int64_t stride_y,
                             int64_t stride_x, pgmp_stream_t stream);
