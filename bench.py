@@ -15,9 +15,10 @@ construct_graph() + mpn.forward() over the batch.  Prints ONE JSON line (rank 0)
                only (the constructor leaves pinned maps on the host), the logits are read back; the sub-key
                all_inputs_copied is the same call after copying every input to the device as the reference does
   roofline     dominant kernel: algorithmic bytes per launch / its mean CUDA-event duration vs measured HBM peak
-  cpu_baseline the numpy oracle (a port of the reference algorithm) timed on this box's host cores
-  --impl reference: the reference's CPU implementation of the path = the oracle port (the reference is pure
-               Python and cannot travel to the GPU box; /root/reference is never read here)
+  cpu_baseline the UNMODIFIED reference files (baseline/_ref, a verbatim git-ignored copy made by oracle/make_ref.py;
+               kind "reference") timed on this box's host cores; the numpy oracle port (kind "port") only when no
+               copy of the reference is reachable
+  --impl reference: the same CPU arm as its own bench line, a bounded sample of images per step
 """
 import argparse
 import json
@@ -43,7 +44,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     ap.add_argument("--precision", default=os.environ.get("PGMP_PRECISION", "tc"), choices=["fp32", "tc"])
     ap.add_argument("--ref-images", type=int, default=2, help="images per step of the CPU reference arm")
-    ap.add_argument("--cpu-sample", type=int, default=8, help="images of the cpu_baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=12, help="images of the cpu_baseline sample")
     return ap.parse_args()
 
 
@@ -65,54 +66,103 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def oracle_images_per_s(num_images, first_index=0, warm=False):
-    """Time the oracle port (GC + flagship MPN) on `num_images` images of the workload, one at a time
-    like the reference's batch-1 evaluation loop (valid.py:95).  Returns (seconds, edges)."""
-    import numpy as np
+_CPU_ARM = {}
 
-    import oracle
+
+def cpu_arm():
+    """The CPU implementation the baseline legs time: the UNMODIFIED reference files (graph constructor + MPN, loaded
+    byte for byte by oracle/ref_shims.py from /root/reference or from the verbatim copy oracle/make_ref.py leaves in
+    baseline/_ref) when they are reachable -- kind "reference" -- else the numpy oracle port -- kind "port"."""
+    if _CPU_ARM:
+        return _CPU_ARM
+    import torch
+
     import pgmp_b200
     import pgmp_b200.synthetic as synthetic
+    from oracle import ref_shims
     from pgmp_b200.Models.MessagePassingNetwork import get_mpn_model
 
     gcfg = pgmp_b200.config.bench_gc_config(k=CAND, graph_type="knn")
     mcfg = pgmp_b200.config.flagship_mpn_config(J)
-    model = synthetic.synth_mpn_state_dict(get_mpn_model(mcfg), 1).eval()
-    sd = {k: v.numpy() for k, v in model.state_dict().items()}
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    src = ref_shims.ref_src()
+    if src is not None:
+        cg, mpn = ref_shims.load_reference()
+        model = synthetic.synth_mpn_state_dict(mpn.NodeClassificationMPNSimple(mcfg), 1).eval()
+
+        def run(data):
+            t = {k: torch.from_numpy(v) for k, v in data.items()}
+            with torch.no_grad():
+                ret = cg.NaiveGraphConstructor(
+                    scoremaps=t["scoremaps"], tagmaps=t["tagmaps"], features=t["features"], joints_gt=None, factor_list=None,
+                    masks=None, device=torch.device("cpu"), config=gcfg, testing=True, heatmaps=None,
+                    num_joints=J).construct_graph()
+                model(ret[0], ret[1], ret[2], node_labels=None, edge_labels=None, batch_index=ret[12], node_mask=None,
+                      node_types=ret[7][:, 2])
+            return int(ret[2].shape[1])
+        _CPU_ARM.update(kind="reference", run=run, cores=threads,
+                        what="the unmodified reference files (ConstructGraph.py + NodeClassificationMPNSimple.py) from %s; "
+                             "torch_geometric / torch_scatter / torch_cluster are the pure-torch stand-ins of "
+                             "oracle/ref_shims.py" % ("baseline/_ref" if "baseline" in src else src))
+    else:
+        import oracle
+        model = synthetic.synth_mpn_state_dict(get_mpn_model(mcfg), 1).eval()
+        sd = {k: v.numpy() for k, v in model.state_dict().items()}
+
+        def run(data):
+            g = oracle.gc.construct_graph(data["scoremaps"], data["tagmaps"], data["features"], gcfg, J)
+            oracle.mpn.node_classification_mpn_forward(sd, mcfg, g["x"], g["edge_attr"], g["edge_index"], g["joint_det"][:, 2])
+            return int(g["edge_index"].shape[1])
+        _CPU_ARM.update(kind="port", run=run, cores=host_threads(),
+                        what="numpy oracle port of the reference's CPU path (no copy of the reference is reachable: "
+                             "run oracle/make_ref.py where /root/reference exists)")
+    return _CPU_ARM
+
+
+def cpu_images_per_s(num_images, first_index=0, warm=False):
+    """Time the CPU arm (GC + flagship MPN) on `num_images` images of the workload, one at a time like the
+    reference's batch-1 evaluation loop (valid.py:95); input synthesis is outside the clock.  Returns (seconds, edges)."""
+    import pgmp_b200.synthetic as synthetic
+
+    arm = cpu_arm()
     total, edges = 0.0, 0
     for i in range(num_images + (1 if warm else 0)):
         data = synthetic.synth_batch(1, J, SIZE, CAND, channels=CHANNELS, first_index=first_index + i)
         t0 = time.perf_counter()
-        g = oracle.gc.construct_graph(data["scoremaps"], data["tagmaps"], data["features"], gcfg, J)
-        oracle.mpn.node_classification_mpn_forward(sd, mcfg, g["x"], g["edge_attr"], g["edge_index"], g["joint_det"][:, 2])
+        e = arm["run"](data)
         dt = time.perf_counter() - t0
         if warm and i == 0:
             continue
         total += dt
-        edges += g["edge_index"].shape[1]
+        edges += e
     return total, edges
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    arm = cpu_arm()
     for _ in range(args.warmup):
-        oracle_images_per_s(1)
+        cpu_images_per_s(1)
     t, edges = 0.0, 0
     for s in range(args.steps):
-        dt, e = oracle_images_per_s(args.ref_images, first_index=s * args.ref_images)
+        dt, e = cpu_images_per_s(args.ref_images, first_index=s * args.ref_images)
         t += dt
         edges += e
     imgs = args.steps * args.ref_images
     v = imgs / t
+    cfg = workload_config(args, world)
+    cfg["reference_sample"] = ("each step times %d images of the workload (a bounded sample of the %d-image batch, so that the "
+                               "run ends within minutes); images/s does not depend on the sample size: the reference "
+                               "loops over images (ConstructGraph.py:58)" % (args.ref_images, args.batch))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "edges_per_s": edges / t,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, world),
-            "cpu_baseline": {"value": v, "unit": "images/s", "cores": host_threads(), "kind": "port",
-                             "sample": "%d images per step x %d steps of the workload, numpy oracle port of the "
-                                       "reference's CPU path (the reference itself is Python + torch_geometric and "
-                                       "cannot run on this box)" % (args.ref_images, args.steps)},
+            "config": cfg,
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": arm["cores"], "kind": arm["kind"],
+                             "sample": "%d images per step x %d steps of the workload, one image at a time; %s"
+                                       % (args.ref_images, args.steps, arm["what"])},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -391,10 +441,11 @@ def run_b200(args, rank, local_rank, world):
     cpu_t, cpu_edges = (None, None)
     cpu = None
     if world == 1:
-        cpu_t, cpu_edges = oracle_images_per_s(args.cpu_sample, warm=True)
-        cpu = {"value": args.cpu_sample / cpu_t, "unit": "images/s", "cores": host_threads(), "kind": "port",
+        cpu_t, cpu_edges = cpu_images_per_s(args.cpu_sample, warm=True)
+        arm = cpu_arm()
+        cpu = {"value": args.cpu_sample / cpu_t, "unit": "images/s", "cores": arm["cores"], "kind": arm["kind"],
                "edges_per_s": cpu_edges / cpu_t,
-               "sample": "%d images of the workload, one at a time (numpy oracle port of the reference CPU path)" % args.cpu_sample}
+               "sample": "%d images of the workload, one at a time; %s" % (args.cpu_sample, arm["what"])}
 
     line = {"metric": METRIC, "value": value, "unit": "images/s", "edges_per_s": total_edges / t_dev,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_dev / args.steps,

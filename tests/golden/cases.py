@@ -127,3 +127,25 @@ def refine_inputs(name):
             k[p, ~det, :2] = k[p, det, :2].mean(axis=0)
         kps.append(k)
     return sm, tags, kps
+
+
+# ---- BASELINE.json configs[2..3] at full per-image size, 10 steps:
+#      name -> (synthetic input kwargs, GC config overrides, flagship MPN overrides, weight seed)
+FULL_CASES = {
+    "w48_640_fully": (dict(batch=1, num_joints=17, size=640, k=30, persons=8), dict(k=30, graph_type="fully"), dict(), 21),
+    "crowdpose_knn": (dict(batch=1, num_joints=14, size=512, k=60, persons=20), dict(k=60, graph_type="knn"),
+                      dict(NUM_JOINTS=14, EDGE_INPUT_DIM=16), 22),
+    "crowdpose_fully": (dict(batch=1, num_joints=14, size=512, k=60, persons=20), dict(k=60, graph_type="fully"),
+                        dict(NUM_JOINTS=14, EDGE_INPUT_DIM=16), 23),
+}
+FULL_EDGE_SAMPLE = 8192
+
+
+def full_edge_sample(n, name):
+    """The fixed edge positions whose logits a full-size fixture stores."""
+    import hashlib
+    import numpy as np
+    if n <= FULL_EDGE_SAMPLE:
+        return np.arange(n)
+    rng = np.random.default_rng(int.from_bytes(hashlib.sha256(("full_" + name).encode()).digest()[:4], "little"))
+    return np.sort(rng.choice(n, FULL_EDGE_SAMPLE, replace=False))

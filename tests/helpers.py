@@ -16,6 +16,7 @@ GC_KEYS = ["x", "edge_attr", "edge_index", "joint_det", "joint_scores", "batch_i
 # north_star tolerance: logits within 1e-3 relative error.  "Relative" is measured against the
 # tensor's scale: max|a - b| <= tol * max|b| and ||a - b||_2 <= tol * ||b||_2.
 FP32_TOL = 2e-5      # fp32 mode: only the summation order differs from the reference
+FP32_TOL_FULL = 5e-5 # fp32 mode on the full-size configs (sums over up to 839 edges per target, 10 steps)
 LOGIT_TOL = 1e-3     # tensor-core mode (north_star)
 
 
