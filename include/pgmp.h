@@ -66,7 +66,7 @@ int pgmp_profile_collect(char* out, int size);
 #define PGMP_GC_FLAG_CAND_OVERFLOW 1   /* more NMS maxima than cand_capacity for some (image, joint) */
 #define PGMP_GC_FLAG_DET_OVERFLOW 2    /* more detections than max_det_per_type for some (image, joint) */
 #define PGMP_GC_FLAG_NODE_OVERFLOW 4   /* more nodes than max_nodes for some image */
-#define PGMP_GC_FLAG_TOO_FEW 8         /* no-threshold path: fewer than top_k positive maxima (CG.py:1193 assert) */
+#define PGMP_GC_FLAG_TOO_FEW 8         /* no-threshold path: the map has fewer than top_k pixels (CG.py:1193 assert); fewer than top_k positive maxima is NOT an error: the block is padded with zero-score pixels like torch.topk, CG.py:1187-1189 */
 
 typedef struct pgmp_gc_params {
   int32_t batch, num_joints, height, width;  /* scoremaps [B,J,H,W] float32, contiguous */

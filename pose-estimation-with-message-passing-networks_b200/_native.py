@@ -27,7 +27,7 @@ EDGE_FEAT_POSITION, EDGE_FEAT_TYPE = 1, 2
 GC_FLAGS = {1: "more NMS maxima than B200_CAND_CAPACITY for some (image, joint)",
             2: "more detections than B200_MAX_DET_PER_TYPE for some (image, joint)",
             4: "more nodes than B200_MAX_NODES in some image",
-            8: "no-threshold path: fewer than k positive maxima for some joint (reference asserts, CG.py:1193)"}
+            8: "no-threshold path: a map has fewer than k pixels (the reference's assert, CG.py:1193)"}
 AGGR = {"add": 0, "sum": 0, "max": 1, "mean": 2}
 ATTN = {"None": 0, "node_edge_attn": 1, "node_edge_attn_per_type": 2}
 PRECISION = {"fp32": 0, "tc": 1}

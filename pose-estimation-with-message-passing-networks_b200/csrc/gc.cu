@@ -7,13 +7,13 @@
 //   detect: nms_candidates -> select_detections -> layout_nodes -> [knn_adjacency] -> row_degrees
 //           -> totals           (host reads the counts once)
 //   emit:   emit_nodes, gather_features, emit_edges_{knn,fully}, edge_attr
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pgmp {
 namespace {
 
-constexpr int kNmsRows = 64;        // output rows per CTA strip
-constexpr int kCtaCandCap = 2048;   // per-CTA shared-memory candidate list
 constexpr uint32_t kFull = 0xffffffffu;
 
 struct GcWorkspace {
@@ -62,106 +62,99 @@ __device__ __forceinline__ int py(int v) { return (v >> 12) & 0xfff; }
 __device__ __forceinline__ int pt(int v) { return (v >> 24) & 0xff; }
 
 // ------------------------------------------------------------------------------------------------
-// K1: max-pool NMS (Utils.py:15-20) fused with candidate extraction.
-// One CTA = one (image, joint, 32-row strip, <=1024-column tile), 4 columns per thread.  Rows stream
-// top to bottom through registers: the horizontal (2R+1)-max is taken across lanes with warp
-// shuffles, the vertical one over a register ring of row maxima, so every heatmap element is
-// loaded once per strip (+ R halo rows above and below).  A pixel is a candidate iff it is
-// positive and equals its window maximum; zero padding is then equivalent to the reference's -inf
-// padding.  Candidates go to a shared-memory list; at the end of the strip the CTA keeps only what
-// can matter globally -- its own top_k scores and everything >= threshold -- and appends those to
-// the (image, joint) list in global memory with one atomic per warp chunk.
+// K1: max-pool NMS (Utils.py:15-20) fused with candidate extraction -- shared-memory row ring fed by the
+// bulk-copy (TMA) engine, threshold-first.
+//
+// One CTA = one (image, joint, strip of rows, <= 1024-column tile).  Rows stream through a ring of 4 stages x
+// 8 rows in shared memory: one elected thread issues `cp.async.bulk` copies (a whole stage is ONE contiguous copy
+// when the tile spans the map's width) three stages ahead, completion on an mbarrier per stage; no thread ever
+// touches a global load or an address computation for the heatmap.
+// A pixel matters only if it is a positive window maximum AND can end up in the result: score >= the strip's running
+// cut = min(DETECT_THRESHOLD, k-th largest candidate found so far).  So the common path of a warp-row (128 pixels) is:
+// one LDS.128, the max of the four values, one compare -- and a single warp-wide REDUX over the 8 rows of a stage.
+// Only warp-rows that hold a pixel >= cut run the (2R+1)^2 window maximum, straight from the ring (vertical maxima
+// of 4 + 2R columns, then the horizontal one): no register ring, no shuffles, ~70 instructions instead of ~160,
+// and only where it matters.  Candidates go to a shared-memory list; whenever it has grown by >= k entries the CTA
+// re-selects its k-th largest score (32-bit radix select), raises the cut and compacts the list.
+// Zero padding is equivalent to the reference's -inf padding because candidates are positive.
 // ------------------------------------------------------------------------------------------------
-// cold path: the CTA's shared list is full -> unfiltered straight to the global list
+constexpr int kNmsStageRows = 8;     // >= 2 R for every supported R (pool kernel <= 9)
+constexpr int kNmsStages = 4;
+constexpr int kNmsRingRows = kNmsStageRows * kNmsStages;
+constexpr int kNmsListCap = 512;     // per-CTA shared-memory candidate queue (consumer warps -> producer warp), a ring
+constexpr int kNmsKeepCap = 256;     // the producer warp's list of survivors (>= the running cut)
+constexpr int kNmsClaimMargin = 256; // a consumer thread claims a queue slot only while this many are free (<= 256 consumer threads race)
+
+struct NmsArgs {
+  const float* scoremaps; const float* mask;
+  int J, H, W, xtiles, rows_per_cta, pitch, top_k, use_thr;
+  float thr;
+  uint64_t* cand_keys; uint32_t* cand_count; int cand_cap; uint32_t* flags;
+};
+
+__device__ __forceinline__ uint32_t nms_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 nms_lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void nms_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void nms_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void nms_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done, spins = 0;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (!done && ++spins > (1u << 24)) __trap();   // a lost copy must fail loudly, never hang the GPU
+  } while (!done);
+}
+__device__ __forceinline__ void nms_bulk_load(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+               "l"(__cvta_generic_to_global(gsrc)), "r"(bytes), "r"(bar) : "memory");
+}
+
+// cold path: the CTA's shared list is full -> straight to the global list (already filtered by the running cut)
 __device__ __noinline__ void spill_candidate(uint64_t key, uint64_t* __restrict__ gkeys, uint32_t* __restrict__ gcount,
                                              int cand_cap, uint32_t* __restrict__ flags) {
   const uint32_t g = atomicAdd(gcount, 1u);
   if (g < (uint32_t)cand_cap) gkeys[g] = key; else atomicOr(flags, (uint32_t)PGMP_GC_FLAG_CAND_OVERFLOW);
 }
 
-// Append this thread's candidates (up to 4, usually none: a warp-row of 128 noisy heatmap pixels holds about five
-// local maxima) to the CTA's shared list: one shared atomic per candidate hands out the slot -- the order inside
-// the list is irrelevant, keys are unique -- and only lanes that own a candidate execute anything.  A full list
-// spills unfiltered to the global list.  Key = score bits << 32 | ~flat index: one 64-bit compare orders by
-// score desc / index asc.
+// Hand this thread's candidates (up to 4, usually none) to the producer warp through the CTA's shared queue: a slot is
+// claimed with one shared atomic while the ring has room (claimed - consumed stays below the capacity, so a claimed
+// slot has always been consumed and zeroed), else the candidate goes straight to the global list.  Key = score bits
+// << 32 | ~flat index: one 64-bit compare orders by score desc / index asc; a zero key means "empty slot".
 __device__ __forceinline__ void emit_candidates(const float (&sc)[4], uint32_t flat0, uint32_t s_keys_a, uint32_t s_cnt_a,
                                                 uint64_t* __restrict__ gkeys, uint32_t* __restrict__ gcount, int cand_cap,
                                                 uint32_t* __restrict__ flags) {
-  // a loop over the thread's candidates, not four predicated blocks: its trip count across the warp is the largest
-  // number of candidates any lane holds (almost always 0 or 1).  The list is addressed in the shared state space
-  // (32-bit addresses formed once per kernel) and the slot comes from a plain per-lane shared atomic: the
-  // compiler's warp-aggregated form (vote + leader election + two popcounts + shuffle) costs more instructions
-  // than the handful of same-address conflicts it saves.
   uint32_t vm = (sc[0] > 0.f ? 1u : 0u) | (sc[1] > 0.f ? 2u : 0u) | (sc[2] > 0.f ? 4u : 0u) | (sc[3] > 0.f ? 8u : 0u);
   while (vm) {
     const int i = __ffs(vm) - 1;
     vm &= vm - 1;
     const float v = i == 0 ? sc[0] : (i == 1 ? sc[1] : (i == 2 ? sc[2] : sc[3]));
     const uint32_t hi = __float_as_uint(v), lo = ~(flat0 + (uint32_t)i);
-    uint32_t pos;
-    asm volatile("atom.shared.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(pos) : "r"(s_cnt_a) : "memory");   // inc with a bound never reached: ptxas warp-aggregates add (and inc 0xffffffff)
-    if (pos < kCtaCandCap) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(s_keys_a + pos * 8u), "r"(lo), "r"(hi) : "memory");
-    else spill_candidate(((uint64_t)hi << 32) | (uint64_t)lo, gkeys, gcount, cand_cap, flags);
+    uint32_t claimed, consumed;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(claimed) : "r"(s_cnt_a) : "memory");
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(consumed) : "r"(s_cnt_a + 16u) : "memory");   // s_misc[4]
+    if (claimed - consumed < (uint32_t)(kNmsListCap - kNmsClaimMargin)) {
+      uint32_t pos;
+      asm volatile("atom.shared.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(pos) : "r"(s_cnt_a) : "memory");   // (a bound never reached: ptxas warp-aggregates add and inc 0xffffffff)
+      asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(s_keys_a + (pos & (uint32_t)(kNmsListCap - 1)) * 8u), "r"(lo), "r"(hi) : "memory");
+    } else {
+      spill_candidate(((uint64_t)hi << 32) | (uint64_t)lo, gkeys, gcount, cand_cap, flags);
+    }
   }
 }
 
-// End of a strip: keep only what can matter globally -- the CTA's own top_k scores (32-bit radix select in
-// shared memory, 4 passes of 8 bits) and everything >= threshold -- and append it to the (image, joint) list
-// with one atomic per warp chunk.
-__device__ __forceinline__ void flush_candidates(const uint64_t* s_keys, uint32_t* s_hist, const uint32_t* s_cnt_p,
-                                                 uint32_t* s_prefix_p, uint32_t* s_remaining_p, int top_k, int use_thr,
-                                                 float thr, uint64_t* __restrict__ gkeys, uint32_t* __restrict__ gcount,
-                                                 int cand_cap, uint32_t* __restrict__ flags) {
-  const int t = threadIdx.x, lane = t & 31;
-  __syncthreads();
-  const uint32_t n = min(*s_cnt_p, (uint32_t)kCtaCandCap);
-  if (n == 0) return;
-  uint32_t cut = 0;  // keep entries with score bits >= cut
-  if (n > (uint32_t)top_k) {
-    // the CTA's top_k-th largest score: 32-bit radix select, 4 passes of 8 bits; the 256-bin suffix scan of a
-    // pass is done by one warp (8 bins per lane)
-    if (t == 0) { *s_prefix_p = 0; *s_remaining_p = (uint32_t)top_k; }
-    for (int shift = 24; shift >= 0; shift -= 8) {
-      for (int i = t; i < 256; i += blockDim.x) s_hist[i] = 0;
-      __syncthreads();
-      const uint32_t prefix = *s_prefix_p;
-      const uint32_t himask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
-      for (uint32_t i = t; i < n; i += blockDim.x) {
-        const uint32_t sc = (uint32_t)(s_keys[i] >> 32);
-        if ((sc & himask) == prefix) atomicAdd(&s_hist[(sc >> shift) & 0xff], 1u);
-      }
-      __syncthreads();
-      if (t < 32) {
-        const uint32_t rem = *s_remaining_p;
-        uint32_t mine = 0;                     // lane L owns bins [8 (31 - L), 8 (31 - L) + 8): lane 0 = the highest bins
-        const int b0 = 8 * (31 - lane);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) mine += s_hist[b0 + q];
-        uint32_t incl = mine;                  // inclusive scan from the highest bins down
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t v = __shfl_up_sync(kFull, incl, o);
-          if (lane >= o) incl += v;
-        }
-        const uint32_t hit = __ballot_sync(kFull, incl >= rem);   // always non-empty: the matching entries number >= rem
-        const int owner = __ffs(hit) - 1;
-        if (lane == owner) {
-          uint32_t r2 = rem - (incl - mine);
-          int d = b0 + 7;
-          for (; d > b0; --d) {
-            if (s_hist[d] >= r2) break;
-            r2 -= s_hist[d];
-          }
-          *s_prefix_p = prefix | ((uint32_t)d << shift);
-          *s_remaining_p = r2;
-        }
-      }
-      __syncthreads();
-    }
-    cut = *s_prefix_p;
-  }
-  if (use_thr) cut = min(cut, __float_as_uint(thr));   // positive floats order like their bit patterns
-  for (uint32_t base = 0; base < n; base += blockDim.x) {
+// Append the list entries with score bits >= cut to the (image, joint) list in global memory, one atomic per warp chunk.
+__device__ __forceinline__ void nms_write_global(const uint64_t* s_keys, uint32_t n, uint32_t cut, uint64_t* __restrict__ gkeys,
+                                                 uint32_t* __restrict__ gcount, int cand_cap, uint32_t* __restrict__ flags) {
+  const int t = threadIdx.y * blockDim.x + threadIdx.x, lane = t & 31, nt = blockDim.x * blockDim.y;
+  for (uint32_t base = 0; base < n; base += nt) {
     const uint32_t i = base + t;
     const bool keep = i < n && (uint32_t)(s_keys[i < n ? i : 0] >> 32) >= cut;
     const uint32_t m = __ballot_sync(kFull, keep);
@@ -175,170 +168,354 @@ __device__ __forceinline__ void flush_candidates(const uint64_t* s_keys, uint32_
   }
 }
 
-struct RowRegs {
-  float4 v, l, r;  // own 4 columns, left / right neighbour's 4 columns (only lanes 0 / 31 load l / r)
-};
-
-// per-thread load plan of a strip: column offsets and which of the three 4-column chunks exist / are needed
-struct LoadPlan {
-  int off_v, off_l, off_r;      // element offsets inside a row
-  bool has_v, has_l, has_r;
-  int n_v, n_l, n_r;            // valid elements of each chunk (scalar path)
-};
-
 template <bool VEC>
-__device__ __forceinline__ float4 load_chunk(const float* __restrict__ p, bool has, int n) {
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (!has) return v;
+__device__ __forceinline__ float4 nms_ldg4(const float* __restrict__ p, int n) {   // n = valid elements (scalar path)
   if (VEC) return __ldg(reinterpret_cast<const float4*>(p));
-  v.x = __ldg(p);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (n > 0) v.x = __ldg(p);
   if (n > 1) v.y = __ldg(p + 1);
   if (n > 2) v.z = __ldg(p + 2);
   if (n > 3) v.w = __ldg(p + 3);
   return v;
 }
 
-// one address per row and thread: the own chunk at map + off_v + yy * W, the neighbour chunks 4 elements either side
-template <bool VEC>
-__device__ __forceinline__ RowRegs load_row(const float* __restrict__ map, int yy, int H, int W, const LoadPlan& lp) {
-  RowRegs q;
-  const bool ok = (unsigned)yy < (unsigned)H;
-  const float* __restrict__ p = map + lp.off_v + (ok ? yy * W : 0);   // a map has at most 4096 x 4096 elements: 32-bit offsets
-  q.v = load_chunk<VEC>(p, ok && lp.has_v, lp.n_v);
-  q.l = load_chunk<VEC>(p - 4, ok && lp.has_l, lp.n_l);
-  q.r = load_chunk<VEC>(p + 4, ok && lp.has_r, lp.n_r);
-  return q;
+__device__ __forceinline__ float2 nms_lds64(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
 }
 
-// Register state of a strip: rings of the last K = 2R+1 rows (raw values and horizontal maxima).  The ring
-// slot of a row is its phase PH = (row - first row) mod K, a template parameter, so the rings never shift.
-template <int R>
-struct NmsRings {
-  float hm[2 * R + 1][4];
-  float raw[2 * R + 1][4];
-};
-
-struct NmsCtx {
-  LoadPlan lp;
-  const float* map; const float* mk;
-  int H, W, tt, lane, y0, y_end;
-  uint32_t s_keys_a, s_cnt_a;   // shared-state-space addresses of the CTA's candidate list and its counter
-  uint64_t* gkeys; uint32_t* gcount; int cand_cap; uint32_t* flags;
-};
-
-template <int R, int PH, bool VEC, bool MASK>
-__device__ __forceinline__ void nms_row_step(NmsRings<R>& rg, const NmsCtx& c, const RowRegs& cur, int yy) {
-  constexpr int K = 2 * R + 1;
-  // only the R columns next to this thread's chunk are needed from each neighbour
-  float4 l = cur.l, r = cur.r;
-  {
-    const float lw = __shfl_up_sync(kFull, cur.v.w, 1), rx = __shfl_down_sync(kFull, cur.v.x, 1);
-    if (c.lane != 0) l.w = lw;
-    if (c.lane != 31) r.x = rx;
-    if (R >= 2) {
-      const float lz = __shfl_up_sync(kFull, cur.v.z, 1), ry = __shfl_down_sync(kFull, cur.v.y, 1);
-      if (c.lane != 0) l.z = lz;
-      if (c.lane != 31) r.y = ry;
+__device__ __forceinline__ void nms_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// One warp: the k-th largest score (bit pattern) among the first n list entries, n >= k (entries whose 8-byte store
+// has not landed yet read as 0 and only lower the result).  Same radix select as nms_kth_largest, warp-synchronous.
+__device__ __forceinline__ uint32_t nms_kth_largest_warp(const volatile uint64_t* s_keys, uint32_t n, int k, uint32_t* s_hist) {
+  const int lane = threadIdx.x & 31;
+  uint32_t prefix = 0, rem = (uint32_t)k;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s_hist[lane * 8 + q] = 0;
+    __syncwarp();
+    const uint32_t himask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+    for (uint32_t i = lane; i < n; i += 32) {
+      const uint32_t sc = (uint32_t)(s_keys[i] >> 32);
+      if ((sc & himask) == prefix) atomicAdd(&s_hist[(sc >> shift) & 0xff], 1u);
     }
-    if (R >= 3) {
-      const float ly = __shfl_up_sync(kFull, cur.v.y, 1), rz = __shfl_down_sync(kFull, cur.v.z, 1);
-      if (c.lane != 0) l.y = ly;
-      if (c.lane != 31) r.z = rz;
+    __syncwarp();
+    uint32_t mine = 0;                     // lane L owns bins [8 (31 - L), 8 (31 - L) + 8): lane 0 = the highest bins
+    const int b0 = 8 * (31 - lane);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) mine += s_hist[b0 + q];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(kFull, incl, o);
+      if (lane >= o) incl += v;
     }
-    if (R >= 4) {
-      const float lx = __shfl_up_sync(kFull, cur.v.x, 1), rw = __shfl_down_sync(kFull, cur.v.w, 1);
-      if (c.lane != 0) l.x = lx;
-      if (c.lane != 31) r.w = rw;
+    const uint32_t hit = __ballot_sync(kFull, incl >= rem);
+    if (hit == 0) return 0;                // (cannot happen for n >= k; never return an unproven bound)
+    const int owner = __ffs(hit) - 1;
+    uint32_t r2 = rem - (incl - mine);
+    int d = b0 + 7;
+    if (lane == owner) {
+      for (; d > b0; --d) {
+        if (s_hist[d] >= r2) break;
+        r2 -= s_hist[d];
+      }
     }
+    prefix |= (uint32_t)__shfl_sync(kFull, d, owner) << shift;
+    rem = __shfl_sync(kFull, r2, owner);
+    __syncwarp();
   }
-  const float ext[12] = {l.x, l.y, l.z, l.w, cur.v.x, cur.v.y, cur.v.z, cur.v.w, r.x, r.y, r.z, r.w};
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    float m = ext[4 + q - R];
-#pragma unroll
-    for (int d = -R + 1; d <= R; ++d) m = fmaxf(m, ext[4 + q + d]);
-    rg.hm[PH][q] = m;
-    rg.raw[PH][q] = ext[4 + q];
-  }
-  const int yc = yy - R;
-  if (yc >= c.y0 && yc < c.y_end) {   // uniform for the CTA
-    constexpr int CS = (PH + K - R) % K;   // ring slot of the centre row
-    float sc[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float x = rg.raw[CS][q];
-      float m = rg.hm[0][q];
-#pragma unroll
-      for (int i = 1; i < K; ++i) m = fmaxf(m, rg.hm[i][q]);
-      sc[q] = 0.f;
-      // (out-of-image columns hold zeros, so x > 0 already excludes them)
-      if (x > 0.f && x == m) sc[q] = MASK ? x * __ldg(c.mk + (yc * c.W + 4 * c.tt + q)) : x;   // CG.py:1163-1165
-    }
-    emit_candidates(sc, (uint32_t)(yc * c.W + 4 * c.tt), c.s_keys_a, c.s_cnt_a, c.gkeys, c.gcount, c.cand_cap, c.flags);
-  }
+  return prefix;
 }
 
-// K rows per outer iteration, one statically-phased step each
-template <int R, int PH, bool VEC, bool MASK>
-__device__ __forceinline__ void nms_rows(NmsRings<R>& rg, const NmsCtx& c, RowRegs& nxt, int yy, int y_last) {
-  constexpr int K = 2 * R + 1;
-  if constexpr (PH < K) {
-    if (yy < y_last) {
-      const RowRegs cur = nxt;
-      nxt = load_row<VEC>(c.map, yy + 1 < y_last ? yy + 1 : -1, c.H, c.W, c.lp);   // prefetch
-      nms_row_step<R, PH, VEC, MASK>(rg, c, cur, yy);
-      nms_rows<R, PH + 1, VEC, MASK>(rg, c, nxt, yy + 1, y_last);
-    }
-  }
+__device__ __forceinline__ float nms_max3(float a, float b, float c) {   // FMNMX3
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
 }
 
-template <int R, bool VEC>
-__global__ void __launch_bounds__(256) nms_candidates_kernel(
-    const float* __restrict__ scoremaps, const float* __restrict__ mask, int J, int H, int W, int xtiles, int top_k,
-    int use_thr, float thr, uint64_t* __restrict__ cand_keys, uint32_t* __restrict__ cand_count, int cand_cap,
-    uint32_t* __restrict__ flags) {
-  constexpr int K = 2 * R + 1;
-  __shared__ uint64_t s_keys[kCtaCandCap];
-  __shared__ uint32_t s_hist[256];
-  __shared__ uint32_t s_cnt;
-  __shared__ uint32_t s_prefix, s_remaining;
+// blockDim = 32 x (column bands of the tile x RW row groups + 2).  Consumer warp (band, row group) owns 128 columns
+// and RPW = 8 / RW consecutive rows of every stage.  The last two warps serve them:
+//   LOADER    issues the bulk copies as ring stages are released (one `empty` mbarrier per stage, one arrival per
+//             consumer warp) and zero-fills the ring rows that lie outside the image, so consumers never test a row;
+//   SELECTOR  drains the candidate queue, keeps the survivors and re-selects the running cut.
+// Consumer warps never meet at a CTA-wide barrier until the strip ends: a warp that runs into a blob does not hold
+// up the others, and neither the copies nor the cut wait for each other.
+template <int R, int RPW, bool VEC, bool MASK>
+__global__ void __launch_bounds__(576) nms_candidates_kernel(const NmsArgs a) {
+  constexpr int S = kNmsStageRows, RW = S / RPW, HALO = R > 0 ? 1 : 0;
+  extern __shared__ __align__(128) uint8_t nms_smem[];
+  const int P = a.pitch, H = a.H, W = a.W;
+  uint64_t* s_keys = reinterpret_cast<uint64_t*>(nms_smem + (size_t)kNmsRingRows * P * 4);   // the queue (ring)
+  uint64_t* s_keep = s_keys + kNmsListCap;                               // the selector's survivors
+  uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_keep + kNmsKeepCap);
+  uint64_t* s_bars = reinterpret_cast<uint64_t*>(s_hist + 256);          // full[4], empty[4]
+  // [0] queue entries claimed [1] effective cut (score bits) [4] queue entries consumed [5] survivors [6] consumer warps done
+  // [7] next work item
+  uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_bars + 2 * kNmsStages);
+  const uint32_t ring_a = nms_smem_u32(nms_smem), keys_a = nms_smem_u32(s_keys), cnt_a = nms_smem_u32(s_misc);
+  const uint32_t full_a = nms_smem_u32(s_bars), empty_a = full_a + 8u * kNmsStages;
 
-  const int b = blockIdx.z, j = blockIdx.y, y0 = (blockIdx.x / xtiles) * kNmsRows;
-  const int t = threadIdx.x;
-  const int bj = b * J + j;
-  NmsCtx c;
-  c.map = scoremaps + (size_t)bj * H * W;
-  c.mk = mask ? mask + (size_t)b * H * W : nullptr;
-  c.H = H; c.W = W; c.lane = t & 31;
-  c.tt = (blockIdx.x % xtiles) * blockDim.x + t;   // absolute 4-column chunk index
-  c.y0 = y0; c.y_end = min(y0 + kNmsRows, H);
-  {
-    const int chunks = (W + 3) >> 2;
-    LoadPlan& lp = c.lp;
-    lp.off_v = 4 * c.tt; lp.off_l = 4 * (c.tt - 1); lp.off_r = 4 * (c.tt + 1);
-    lp.has_v = c.tt < chunks;
-    lp.has_l = c.lane == 0 && c.tt > 0 && c.tt - 1 < chunks;
-    lp.has_r = c.lane == 31 && c.tt + 1 < chunks;
-    lp.n_v = min(4, W - lp.off_v); lp.n_l = min(4, W - lp.off_l); lp.n_r = min(4, W - lp.off_r);
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int n_cons = (int)(blockDim.x >> 5) - 2;                         // consumer warps
+  const int bands = n_cons / RW;
+  const int b = blockIdx.z, j = blockIdx.y;
+  const int strip = blockIdx.x / a.xtiles, xt = blockIdx.x - strip * a.xtiles;
+  const int bj = b * a.J + j;
+  const float* __restrict__ map = a.scoremaps + (size_t)bj * H * W;
+  const float* __restrict__ mk = MASK ? a.mask + (size_t)b * H * W : nullptr;
+  uint64_t* __restrict__ gkeys = a.cand_keys + (size_t)bj * a.cand_cap;
+  uint32_t* __restrict__ gcount = &a.cand_count[bj];
+  const int y0 = strip * a.rows_per_cta, y_end = min(y0 + a.rows_per_cta, H);
+  const int tile_cols = 128 * bands;
+  const int x0 = xt * tile_cols;
+  const int gx0 = x0 > 0 ? x0 - 4 : 0;                                   // first map column held in a ring row
+  const int gcount_cols = min(W, x0 + tile_cols + 4) - gx0;               // columns per ring row
+  const uint32_t rowb = (uint32_t)P * 4u;
+  const int ybase = y0 - R;                                              // map row of ring row 0 (may be negative)
+  const int y_need = min(H, y_end + R);                                  // in-image rows [max(0, ybase), y_need) are read ...
+  const int n_iter = (y_end - y0 + S - 1) / S;
+  const int n_stage = (y_end + R - ybase + S - 1) / S;                    // ... out-of-image rows up to y_end + R as zeros
+  const uint32_t thr_bits = __float_as_uint(a.thr);
+
+  for (int i = t; i < kNmsListCap; i += blockDim.x) s_keys[i] = 0ull;     // 0 = "empty slot"
+  if (t == 0) {
+    for (int i = 0; i < kNmsStages; ++i) { nms_mbar_init(full_a + 8u * i, 1); nms_mbar_init(empty_a + 8u * i, (uint32_t)n_cons); }
+    s_misc[0] = 0; s_misc[4] = 0; s_misc[5] = 0; s_misc[6] = 0; s_misc[7] = 0;
+    s_misc[1] = 1u;      // smallest positive float: "x >= cut" == "x > 0" until a real cut exists
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  c.s_keys_a = (uint32_t)__cvta_generic_to_shared(s_keys); c.s_cnt_a = (uint32_t)__cvta_generic_to_shared(&s_cnt);
-  c.gkeys = cand_keys + (size_t)bj * cand_cap; c.gcount = &cand_count[bj]; c.cand_cap = cand_cap; c.flags = flags;
-  if (t == 0) s_cnt = 0;
   __syncthreads();
 
-  NmsRings<R> rg;
-#pragma unroll
-  for (int i = 0; i < K; ++i)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) { rg.hm[i][q] = 0.f; rg.raw[i][q] = 0.f; }
-  const int y_last = c.y_end + R;
-  RowRegs nxt = load_row<VEC>(c.map, y0 - R, H, W, c.lp);
-  if (mask) {
-    for (int yy = y0 - R; yy < y_last; yy += K) nms_rows<R, 0, VEC, true>(rg, c, nxt, yy, y_last);
+  if (warp == n_cons) {
+    // ---- LOADER: stage L = map rows [ybase + L S, ybase + (L + 1) S) -> ring rows (L mod 4) S ...
+    for (int L = 0; L < n_stage; ++L) {
+      if (L >= kNmsStages) nms_mbar_wait(empty_a + 8u * (L & (kNmsStages - 1)), (uint32_t)(L / kNmsStages + 1) & 1u);
+      const int ys = ybase + L * S;
+      const int r_lo = max(ys, 0);
+      const int nrows = min(ys + S, y_need) - r_lo;
+      const uint32_t bar = full_a + 8u * (L & (kNmsStages - 1));
+      float* slot = reinterpret_cast<float*>(nms_smem) + (size_t)((L & (kNmsStages - 1)) * S) * P;
+      if (ys < 0 || ys + S > H) {                   // rows above / below the image read as zeros (= the -inf padding, scores > 0)
+        for (int r = 0; r < S; ++r)
+          if ((unsigned)(ys + r) >= (unsigned)H)
+            for (int i = lane; i < P; i += 32) slot[(size_t)r * P + i] = 0.f;
+        __syncwarp();
+      }
+      if (nrows <= 0) {
+        if (lane == 0) nms_mbar_arrive(bar);
+      } else if (VEC) {
+        if (lane == 0) {
+          const uint32_t dst = ring_a + (uint32_t)((r_lo - ybase) & (kNmsRingRows - 1)) * rowb;
+          if (a.xtiles == 1) {                      // the tile spans the width: rows are contiguous in memory and in the ring
+            const uint32_t bytes = (uint32_t)nrows * rowb;
+            nms_mbar_expect_tx(bar, bytes);
+            nms_bulk_load(dst, map + (size_t)r_lo * W, bytes, bar);
+          } else {
+            const uint32_t bytes = (uint32_t)gcount_cols * 4u;
+            nms_mbar_expect_tx(bar, bytes * (uint32_t)nrows);
+            for (int r = 0; r < nrows; ++r) nms_bulk_load(dst + (uint32_t)r * rowb, map + (size_t)(r_lo + r) * W + gx0, bytes, bar);
+          }
+        }
+      } else {                                      // unaligned maps: the warp copies, zero-filling up to the pitch
+        float* ring = slot + (size_t)(r_lo - ys) * P;
+        for (int i = lane; i < nrows * P; i += 32) {
+          const int r = i / P, x = i - r * P;
+          ring[i] = x < gcount_cols ? __ldg(map + (size_t)(r_lo + r) * W + gx0 + x) : 0.f;
+        }
+        __syncwarp();
+        if (lane == 0) nms_mbar_arrive(bar);
+      }
+      __syncwarp();
+    }
+  } else if (warp == n_cons + 1) {
+    // ---- SELECTOR: drain the candidate queue.  Entries are taken in claim order up to the first one whose 8-byte store
+    //      has not landed yet; survivors (>= cut) join the keep list, the slots are zeroed and released.
+    const uint32_t trigger = (uint32_t)min(kNmsKeepCap - 64, max(3 * a.top_k, 96));   // survivors that start a re-selection
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    volatile uint64_t* q = s_keys;
+    uint32_t rd = 0, kc = 0, cut = 1u;
+    for (;;) {
+      const uint32_t done = *reinterpret_cast<volatile uint32_t*>(&s_misc[6]);     // (read before the queue: nothing is lost)
+      const uint32_t claimed = *reinterpret_cast<volatile uint32_t*>(&s_misc[0]);
+      if (claimed == rd) {
+        if (done == (uint32_t)n_cons) break;
+        __nanosleep(64);
+        continue;
+      }
+      const uint32_t i = rd + (uint32_t)lane;
+      const uint64_t key = (int32_t)(claimed - i) > 0 ? q[i & (kNmsListCap - 1)] : 0ull;
+      const uint32_t landed = __ballot_sync(kFull, key != 0ull);
+      const int len = landed == kFull ? 32 : __ffs(~landed) - 1;                   // leading run of landed entries
+      const bool mine = lane < len;
+      const bool keep = mine && (uint32_t)(key >> 32) >= cut;
+      const uint32_t km = __ballot_sync(kFull, keep);
+      if (keep) s_keep[kc + __popc(km & lt_mask)] = key;
+      if (mine) q[i & (kNmsListCap - 1)] = 0ull;
+      kc += __popc(km);
+      rd += (uint32_t)len;
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&s_misc[4]) = rd;
+      if (kc >= trigger) {
+        if (kc > (uint32_t)a.top_k) {          // the k-th largest survivor is a proven lower bound of the strip's k-th largest
+          const uint32_t kth = nms_kth_largest_warp(s_keep, kc, a.top_k, s_hist);
+          uint32_t eff = max(kth, cut);                                            // cuts only rise
+          if (a.use_thr) eff = min(eff, max(thr_bits, 1u));                        // scores >= DETECT_THRESHOLD always matter
+          cut = eff;
+          if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&s_misc[1]) = cut;
+          uint32_t w = 0;                                                          // in-place compaction, 32 entries at a time
+          for (uint32_t base = 0; base < kc; base += 32) {
+            const uint32_t e = base + (uint32_t)lane;
+            const uint64_t k2 = e < kc ? s_keep[e] : 0ull;
+            const bool kp = e < kc && (uint32_t)(k2 >> 32) >= cut;
+            const uint32_t m2 = __ballot_sync(kFull, kp);
+            if (kp) s_keep[w + __popc(m2 & lt_mask)] = k2;
+            w += __popc(m2);
+            __syncwarp();
+          }
+          kc = w;
+        }
+        if (kc >= trigger) {                   // ties / many scores above the threshold: hand the survivors over, keep the cut
+          for (uint32_t base = 0; base < kc; base += 32) {
+            const uint32_t e = base + (uint32_t)lane;
+            const uint32_t m2 = __ballot_sync(kFull, e < kc);
+            uint32_t g = 0;
+            if (lane == 0) g = atomicAdd(gcount, (uint32_t)__popc(m2));
+            g = __shfl_sync(kFull, g, 0) + (uint32_t)lane;
+            if (e < kc) {
+              if (g < (uint32_t)a.cand_cap) gkeys[g] = s_keep[e]; else atomicOr(a.flags, (uint32_t)PGMP_GC_FLAG_CAND_OVERFLOW);
+            }
+          }
+          kc = 0;
+        }
+      }
+    }
+    if (lane == 0) s_misc[5] = kc;
   } else {
-    for (int yy = y0 - R; yy < y_last; yy += K) nms_rows<R, 0, VEC, false>(rg, c, nxt, yy, y_last);
+    // ---- CONSUMERS
+    // Work items (stage, column band, row group) are handed out in order by one shared counter: a warp that runs into
+    // blobs takes fewer items, so no warp waits for a slower one (the only coupling is the ring's depth).
+    const int n_items = n_iter * n_cons;
+    const uint32_t inv_cons = 0xffffffffu / (uint32_t)n_cons + 1u, inv_bands = 0xffffffffu / (uint32_t)bands + 1u;
+    for (;;) {
+      int item = 0;
+      if (lane == 0) item = (int)atomicAdd(&s_misc[7], 1u);
+      item = __shfl_sync(kFull, item, 0);
+      if (item >= n_items) break;
+      const int s = (int)__umulhi((uint32_t)item, inv_cons), unit = item - s * n_cons;   // item / n_cons (item < 2^16)
+      const int wr = bands == 1 ? unit : (int)__umulhi((uint32_t)unit, inv_bands);        // unit / bands
+      const int tx = (unit - wr * bands) * 32 + lane;                                     // row group wr, column thread tx
+      const int c = x0 + 4 * tx;                                           // this thread's first column
+      const bool has_v = c < W, has_l = has_v && c >= 4, has_r = c + 4 < W;
+      // (threads beyond the map's width read column gx0 instead and never report anything: no zero-filled registers)
+      const uint32_t col_a = ring_a + (uint32_t)(has_v ? c - gx0 : 0) * 4u;  // + ring row * P * 4
+      nms_mbar_wait(full_a + 8u * (s & (kNmsStages - 1)), (uint32_t)(s / kNmsStages) & 1u);
+      if (s + 1 < n_stage) nms_mbar_wait(full_a + 8u * ((s + 1) & (kNmsStages - 1)), (uint32_t)((s + 1) / kNmsStages) & 1u);
+      const float cutf = __uint_as_float(*reinterpret_cast<volatile uint32_t*>(&s_misc[1]));
+      const int yr = y0 + s * S + wr * RPW;         // the item's first row
+      const int rr0 = (yr - HALO - ybase) & (kNmsRingRows - 1);   // ring row of its first (halo) row
+      // ---- common path: which of the warp's rows hold a pixel that can matter -- score >= cut and, cheaply, not below
+      //      the pixel above / below it (rows of a blob other than its ridge fail here); one REDUX for the rows
+      uint32_t pm = 0;
+      {
+        float4 v[RPW + 2 * HALO];
+#pragma unroll
+        for (int i = 0; i < RPW + 2 * HALO; ++i) {
+          v[i] = nms_lds128(col_a + (uint32_t)((rr0 + i) & (kNmsRingRows - 1)) * rowb);
+        }
+#pragma unroll
+        for (int i = 0; i < RPW; ++i) {
+          const float4 x = v[i + HALO];
+          bool p;
+          if (MASK) {
+            float4 sc = x;
+            if (has_v && yr + i < y_end) {
+              const float4 m4 = nms_ldg4<VEC>(mk + (size_t)(yr + i) * W + c, W - c);
+              sc.x *= m4.x; sc.y *= m4.y; sc.z *= m4.z; sc.w *= m4.w;
+            }
+            if (R > 0) {
+              const float4 u = v[i], d = v[i + 2 * HALO];
+              p = (sc.x >= cutf && x.x >= fmaxf(u.x, d.x)) || (sc.y >= cutf && x.y >= fmaxf(u.y, d.y)) ||
+                  (sc.z >= cutf && x.z >= fmaxf(u.z, d.z)) || (sc.w >= cutf && x.w >= fmaxf(u.w, d.w));
+            } else {
+              p = fmaxf(fmaxf(sc.x, sc.y), fmaxf(sc.z, sc.w)) >= cutf;
+            }
+          } else if (R > 0) {
+            const float4 u = v[i], d = v[i + 2 * HALO];
+            // ... nor below its neighbours inside this thread's four columns
+            p = (int)(x.x >= fmaxf(nms_max3(u.x, d.x, cutf), x.y)) | (int)(x.y >= nms_max3(nms_max3(u.y, d.y, cutf), x.x, x.z)) |
+                (int)(x.z >= nms_max3(nms_max3(u.z, d.z, cutf), x.y, x.w)) | (int)(x.w >= fmaxf(nms_max3(u.w, d.w, cutf), x.z));
+          } else {
+            p = nms_max3(x.x, x.y, fmaxf(x.z, x.w)) >= cutf;
+          }
+          pm |= (p ? 1u : 0u) << i;
+        }
+      }
+      uint32_t rows = __reduce_or_sync(kFull, has_v ? pm : 0u);
+      if (yr + RPW > y_end) rows &= (1u << max(y_end - yr, 0)) - 1u;        // the strip ends inside this stage
+      // ---- rows with such a pixel in this warp's 128 columns: window maxima straight from the ring
+      while (rows) {
+        const int r = __ffs(rows) - 1;
+        rows &= rows - 1;
+        const int y = yr + r;
+        const int rr1 = rr0 + HALO + r - R;          // ring row of the window's first row (+ 32: positive)
+        // column maxima over the 2R+1 rows, two rows per 3-input max; the centre row's own 4 values are kept
+        float cm[12], xc[4] = {0.f, 0.f, 0.f, 0.f};
+        auto load_row = [&](int dy, float (&e)[12]) {
+          const uint32_t ra = col_a + (uint32_t)((rr1 + dy + kNmsRingRows) & (kNmsRingRows - 1)) * rowb;
+          float4 l = make_float4(0.f, 0.f, 0.f, 0.f), rr = l;
+          const float4 v = nms_lds128(ra);
+          if (R > 2) {
+            if (has_l) l = nms_lds128(ra - 16u);
+            if (has_r) rr = nms_lds128(ra + 16u);
+          } else if (R > 0) {
+            if (has_l) { const float2 q = nms_lds64(ra - 8u); l.z = q.x; l.w = q.y; }
+            if (has_r) { const float2 q = nms_lds64(ra + 16u); rr.x = q.x; rr.y = q.y; }
+          }
+          e[0] = l.x; e[1] = l.y; e[2] = l.z; e[3] = l.w; e[4] = v.x; e[5] = v.y; e[6] = v.z; e[7] = v.w;
+          e[8] = rr.x; e[9] = rr.y; e[10] = rr.z; e[11] = rr.w;
+          if (dy == R) { xc[0] = v.x; xc[1] = v.y; xc[2] = v.z; xc[3] = v.w; }
+        };
+        load_row(0, cm);
+#pragma unroll
+        for (int dy = 1; dy + 1 <= 2 * R; dy += 2) {
+          float ea[12], eb[12];
+          load_row(dy, ea);
+          load_row(dy + 1, eb);
+#pragma unroll
+          for (int i = 4 - R; i < 8 + R; ++i) cm[i] = nms_max3(cm[i], ea[i], eb[i]);
+        }
+        float sc[4];
+        float4 m4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (MASK) { if (has_v) m4 = nms_ldg4<VEC>(mk + (size_t)y * W + c, W - c); }   // CG.py:1163-1165
+        const float mq[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float m = cm[4 + q - R];
+#pragma unroll
+          for (int d = -R + 1; d + 1 <= R; d += 2) m = nms_max3(m, cm[4 + q + d], cm[4 + q + d + 1]);
+          const float x = xc[q];
+          // (out-of-image rows / columns hold zeros or are not loaded, so x > 0 already excludes them)
+          float v = (x > 0.f && x == m) ? (MASK ? x * mq[q] : x) : 0.f;
+          sc[q] = (has_v && v >= cutf) ? v : 0.f;
+        }
+        emit_candidates(sc, (uint32_t)(y * W + c), keys_a, cnt_a, gkeys, gcount, a.cand_cap, a.flags);
+      }
+      __syncwarp();
+      if (lane == 0) nms_mbar_arrive(empty_a + 8u * (s & (kNmsStages - 1)));   // one of the n_cons items of stage s is done
+    }
+    if (lane == 0) atomicAdd(&s_misc[6], 1u);
   }
-  flush_candidates(s_keys, s_hist, &s_cnt, &s_prefix, &s_remaining, top_k, use_thr, thr, c.gkeys, c.gcount, cand_cap, flags);
+  // ---- end of the strip: what can matter globally -- the survivors and whatever still sits in the queue, >= the cut
+  //      (a proven lower bound of the strip's k-th largest score, already capped by the threshold)
+  __syncthreads();
+  const uint32_t cut = s_misc[1];
+  nms_write_global(s_keys, (uint32_t)kNmsListCap, cut, gkeys, gcount, a.cand_cap, a.flags);   // empty slots are zero < cut
+  nms_write_global(s_keep, s_misc[5], cut, gkeys, gcount, a.cand_cap, a.flags);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -363,46 +540,88 @@ __device__ void bitonic_sort_asc(uint64_t* s, int P) {
   }
 }
 
+// No-threshold path with fewer than k positive maxima (clean or crowd-masked maps): torch.topk fills the block with
+// zero-score pixels (CG.py:1187; `+ 1e-10` makes them nonzero, :1189) -- by this build's tie rule the zero-score
+// pixels with the lowest flat indices.  A pixel's score x * nms * mask is zero unless it is a window maximum
+// (-inf padding, Utils.py:17) with x != 0 and mask != 0.  One warp scans the map from index 0.
+template <int DUMMY = 0>
+__device__ void pad_with_zero_pixels(const float* __restrict__ map, const float* __restrict__ mask, int H, int W, int R,
+                                     int need, int* s_pad, int* s_npad) {
+  const int lane = threadIdx.x & 31;
+  int found = 0;
+  for (int base = 0; base < H * W && found < need; base += 32) {
+    const int i = base + lane;
+    bool zero = false;
+    if (i < H * W) {
+      const int y = i / W, x = i - y * W;
+      const float v = map[i];
+      bool is_max = true;
+      for (int dy = -R; dy <= R && is_max; ++dy)
+        for (int dx = -R; dx <= R; ++dx) {
+          const int yy = y + dy, xx = x + dx;
+          if ((unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W && map[yy * W + xx] > v) { is_max = false; break; }
+        }
+      const float sc = is_max ? (mask ? v * mask[i] : v) : 0.f;
+      zero = sc == 0.f;
+    }
+    const uint32_t m = __ballot_sync(kFull, zero);
+    const int pos = found + __popc(m & ((1u << lane) - 1u));
+    if (zero && pos < need) s_pad[pos] = i;
+    found += __popc(m);
+  }
+  if (lane == 0) *s_npad = min(found, need);
+}
+
 __global__ void __launch_bounds__(256) select_detections_kernel(
     const uint64_t* __restrict__ cand_keys, const uint32_t* __restrict__ cand_count, int cand_cap, int top_k,
-    int use_thr, float thr, int max_det, int32_t* __restrict__ det_idx, int32_t* __restrict__ det_n1,
-    int32_t* __restrict__ det_n2, uint32_t* __restrict__ flags) {
+    int use_thr, float thr, int max_det, const float* __restrict__ scoremaps, const float* __restrict__ mask, int J, int H,
+    int W, int R, int32_t* __restrict__ det_idx, int32_t* __restrict__ det_n1, int32_t* __restrict__ det_n2,
+    uint32_t* __restrict__ flags) {
   extern __shared__ uint64_t s[];
-  __shared__ int s_n2;
+  __shared__ int s_n2, s_npad;
+  __shared__ int s_pad[256];                 // top_k <= max_det_per_type; the no-threshold k is 20
   const int bj = blockIdx.x;
   const int n = (int)min(cand_count[bj], (uint32_t)cand_cap);
   int P = 1;
-  while (P < n) P <<= 1;
+  while (P < n || P < top_k) P <<= 1;
   const uint64_t* __restrict__ g = cand_keys + (size_t)bj * cand_cap;
   for (int i = threadIdx.x; i < P; i += blockDim.x) s[i] = i < n ? ~g[i] : ~0ull;   // ~key ascending = key descending
-  if (threadIdx.x == 0) s_n2 = 0;
+  if (threadIdx.x == 0) { s_n2 = 0; s_npad = 0; }
   __syncthreads();
   bitonic_sort_asc(s, P);
-  const int n1 = min(top_k, n);
+  int n1 = min(top_k, n);
   if (use_thr) {
     const uint32_t tb = __float_as_uint(thr);
     int c = 0;
     for (int i = n1 + threadIdx.x; i < n; i += blockDim.x) c += ((uint32_t)((~s[i]) >> 32) >= tb) ? 1 : 0;
     if (c) atomicAdd(&s_n2, c);
-  } else if (n1 < top_k && threadIdx.x == 0) {
-    atomicOr(flags, (uint32_t)PGMP_GC_FLAG_TOO_FEW);
+  } else if (n1 < top_k && threadIdx.x < 32) {
+    pad_with_zero_pixels(scoremaps + (size_t)bj * H * W, mask ? mask + (size_t)(bj / J) * H * W : nullptr, H, W, R,
+                         min(top_k - n1, 256), s_pad, &s_npad);
   }
   __syncthreads();
+  const int npad = s_npad;
+  if (!use_thr && n1 + npad < top_k && threadIdx.x == 0) atomicOr(flags, (uint32_t)PGMP_GC_FLAG_TOO_FEW);   // map smaller than k
   int n2 = s_n2;
-  if (n1 + n2 > max_det) {
+  if (n1 + npad + n2 > max_det) {
     if (threadIdx.x == 0) atomicOr(flags, (uint32_t)PGMP_GC_FLAG_DET_OVERFLOW);
-    n2 = max_det - n1;
+    n2 = max(max_det - n1 - npad, 0);
   }
-  const int total = n1 + n2;
+  const int total = min(n1 + npad + n2, max_det);
   __syncthreads();
+  // second key: block << 33 | flat << 1 | zero-score pad; the pads belong to block 1 and sort among it by flat index
   for (int i = threadIdx.x; i < P; i += blockDim.x) {
-    const uint32_t flat = ~(uint32_t)(~s[i]);   // low 32 bits of the key hold ~flat
-    s[i] = i < total ? (((uint64_t)(i >= n1 ? 1u : 0u) << 32) | flat) : ~0ull;
+    uint64_t key = ~0ull;
+    if (i < n1) key = (uint64_t)(~(uint32_t)(~s[i])) << 1;                  // low 32 bits of the candidate key hold ~flat
+    else if (i < n1 + npad) key = ((uint64_t)(uint32_t)s_pad[i - n1] << 1) | 1ull;
+    else if (i < total) key = (1ull << 33) | ((uint64_t)(~(uint32_t)(~s[i - npad])) << 1);
+    s[i] = key;
   }
   __syncthreads();
   bitonic_sort_asc(s, P);
-  for (int i = threadIdx.x; i < total; i += blockDim.x) det_idx[(size_t)bj * max_det + i] = (int32_t)(uint32_t)s[i];
-  if (threadIdx.x == 0) { det_n1[bj] = n1; det_n2[bj] = n2; }
+  for (int i = threadIdx.x; i < total; i += blockDim.x)
+    det_idx[(size_t)bj * max_det + i] = (int32_t)(((uint32_t)(s[i] >> 1) & 0x7fffffffu) | ((uint32_t)(s[i] & 1ull) << 31));
+  if (threadIdx.x == 0) { det_n1[bj] = min(n1 + npad, total); det_n2[bj] = total - min(n1 + npad, total); }
 }
 
 // K3: per-image node order: top-k blocks of types 0..J-1, then the extras blocks of types 0..J-1
@@ -430,11 +649,12 @@ __global__ void __launch_bounds__(256) layout_nodes_kernel(
     const int n1 = det_n1[bj], n2 = det_n2[bj];
     const float* __restrict__ map = scoremaps + (size_t)bj * H * W;
     for (int i = threadIdx.x; i < n1 + n2; i += blockDim.x) {
-      const int flat = det_idx[(size_t)bj * max_det + i];
+      const int packed = det_idx[(size_t)bj * max_det + i];
+      const int flat = packed & 0x7fffffff;                 // bit 31: a zero-score pixel that pads the top-k block
       const int y = flat / W, x = flat - y * W;
       const int node = i < n1 ? s_start[j] + i : s_start[J + j] + (i - n1);
-      float s = map[flat];
-      if (mask) s = s * mask[(size_t)b * H * W + flat];
+      float s = packed < 0 ? 0.f : map[flat];
+      if (mask && packed >= 0) s = s * mask[(size_t)b * H * W + flat];
       if (!use_thr) s = __fadd_rn(s, 1e-10f);   // CG.py:1189
       node_xyt[(size_t)b * max_nodes + node] = pack_xyt(x, y, j);
       node_score[(size_t)b * max_nodes + node] = s;
@@ -733,20 +953,62 @@ int validate(const pgmp_gc_params* p) {
   return PGMP_OK;
 }
 
+int nms_strip_rows(const pgmp_gc_params& p, int xtiles) {
+  // rows per CTA: whole maps give the sharpest running cut (measured: 0.175 ms against 0.198 ms with half maps at
+  // 32 x 17 x 512 x 512); split maps into strips only as far as it takes to fill the 3 CTA slots of every SM
+  const char* env = getenv("PGMP_NMS_STRIP_ROWS");   // tuning / test hook
+  const int forced = env ? atoi(env) : 0;
+  int rows;
+  if (forced > 0) {
+    rows = forced;
+  } else {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t maps = (int64_t)p.batch * p.num_joints * xtiles;
+    int64_t strips = (3 * sms + maps - 1) / maps;
+    if (strips > ceil_div(p.height, 32)) strips = ceil_div(p.height, 32);
+    if (strips < 1) strips = 1;
+    rows = ceil_div(p.height, (int)strips);
+  }
+  rows = round_up(rows, kNmsStageRows);
+  return rows < kNmsStageRows ? kNmsStageRows : rows;
+}
+
 template <int R>
 int launch_nms(const pgmp_gc_params& p, const GcWorkspace& w, cudaStream_t st) {
-  const bool vec = (p.width % 4 == 0) && (reinterpret_cast<uintptr_t>(p.scoremaps) % 16 == 0);
+  const bool vec = (p.width % 4 == 0) && (reinterpret_cast<uintptr_t>(p.scoremaps) % 16 == 0) &&
+                   (reinterpret_cast<uintptr_t>(p.mask) % 16 == 0);
   const int chunks = ceil_div(p.width, 4);
-  const int threads = min(round_up(chunks, 32), 256);
-  const int xtiles = ceil_div(chunks, threads);
-  const dim3 grid(ceil_div(p.height, kNmsRows) * xtiles, p.num_joints, p.batch);
-  if (vec) {
-    PGMP_LAUNCH((nms_candidates_kernel<R, true>), grid, threads, 0, st, p.scoremaps, p.mask, p.num_joints, p.height,
-                p.width, xtiles, p.top_k, p.use_threshold, p.threshold, w.cand_keys, w.cand_count, p.cand_capacity, w.flags);
-  } else {
-    PGMP_LAUNCH((nms_candidates_kernel<R, false>), grid, threads, 0, st, p.scoremaps, p.mask, p.num_joints, p.height,
-                p.width, xtiles, p.top_k, p.use_threshold, p.threshold, w.cand_keys, w.cand_count, p.cand_capacity, w.flags);
-  }
+  const int xtiles = ceil_div(chunks, 256);
+  const int threads = round_up(ceil_div(chunks, xtiles), 32);     // column threads of a tile (32 per 128-column band)
+  const int bands = threads / 32;
+  const int rw = bands <= 4 ? 2 : 1;                              // row groups: consumer warps = bands x rw <= 8 (+ loader and selector warps)
+  NmsArgs a;
+  a.scoremaps = p.scoremaps; a.mask = p.mask; a.J = p.num_joints; a.H = p.height; a.W = p.width; a.xtiles = xtiles;
+  a.rows_per_cta = nms_strip_rows(p, xtiles);
+  // ring row pitch (floats): the map's width when one tile spans it (a stage is one contiguous bulk copy), else the
+  // tile's columns + 4 either side; unaligned maps: rounded up and zero-filled by the copying warp
+  const int cols = xtiles == 1 ? p.width : 4 * threads + 8;
+  a.pitch = vec ? cols : round_up(cols, 4) + 4;
+  a.top_k = p.top_k; a.use_thr = p.use_threshold; a.thr = p.threshold;
+  a.cand_keys = w.cand_keys; a.cand_count = w.cand_count; a.cand_cap = p.cand_capacity; a.flags = w.flags;
+  const size_t smem = (size_t)kNmsRingRows * a.pitch * 4 + (size_t)(kNmsListCap + kNmsKeepCap) * 8 + 256 * 4 + 2 * kNmsStages * 8 + 64;
+  const dim3 grid(ceil_div(p.height, a.rows_per_cta) * xtiles, p.num_joints, p.batch);
+  const int block = 32 * (bands * rw + 2);
+#define PGMP_NMS_LAUNCH2(RPW, V, M)                                                                                             \
+  do {                                                                                                                          \
+    PGMP_CUDA(cudaFuncSetAttribute(nms_candidates_kernel<R, RPW, V, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    PGMP_LAUNCH((nms_candidates_kernel<R, RPW, V, M>), grid, block, smem, st, a);                                               \
+  } while (0)
+#define PGMP_NMS_LAUNCH(V, M)                                             \
+  do {                                                                    \
+    if (rw == 2) PGMP_NMS_LAUNCH2(4, V, M); else PGMP_NMS_LAUNCH2(8, V, M); \
+  } while (0)
+  if (vec) { if (p.mask) PGMP_NMS_LAUNCH(true, true); else PGMP_NMS_LAUNCH(true, false); }
+  else { if (p.mask) PGMP_NMS_LAUNCH(false, true); else PGMP_NMS_LAUNCH(false, false); }
+#undef PGMP_NMS_LAUNCH
+#undef PGMP_NMS_LAUNCH2
   return PGMP_OK;
 }
 
@@ -783,12 +1045,13 @@ extern "C" int pgmp_gc_detect(const pgmp_gc_params* p, int64_t* counts, pgmp_str
   }
   if (rc != PGMP_OK) return rc;
   int P = 1;
-  while (P < p->cand_capacity) P <<= 1;
+  while (P < p->cand_capacity || P < p->top_k) P <<= 1;
   const size_t sel_smem = sizeof(uint64_t) * P;
   if (sel_smem > 48 * 1024)
     PGMP_CUDA(cudaFuncSetAttribute(select_detections_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
   PGMP_LAUNCH(select_detections_kernel, B * J, 256, sel_smem, st, w.cand_keys, w.cand_count, p->cand_capacity, p->top_k,
-              p->use_threshold, p->threshold, p->max_det_per_type, w.det_idx, w.det_n1, w.det_n2, w.flags);
+              p->use_threshold, p->threshold, p->max_det_per_type, p->scoremaps, p->mask, J, p->height, p->width,
+              p->pool_kernel / 2, w.det_idx, w.det_n1, w.det_n2, w.flags);
   PGMP_LAUNCH(layout_nodes_kernel, B, 256, sizeof(int32_t) * 2 * J, st, p->scoremaps, p->mask, J, p->height, p->width,
               p->use_threshold, p->max_det_per_type, p->max_nodes, w.det_idx, w.det_n1, w.det_n2, w.node_xyt,
               w.node_score, w.node_count, w.flags);

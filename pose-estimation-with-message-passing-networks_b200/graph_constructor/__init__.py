@@ -144,8 +144,27 @@ class NaiveGraphConstructor:
         self.cand_capacity = int(getattr(config, "B200_CAND_CAPACITY", max(4096, top_k)))
         max_nodes = int(getattr(config, "B200_MAX_NODES", min(2048, num_joints * self.max_det_per_type)))
         self.max_nodes = (max_nodes + 31) // 32 * 32
+        # capacities the caller set explicitly are hard limits; the defaults grow on overflow (construct_graph)
+        self._fixed_caps = {k for k in ("B200_MAX_DET_PER_TYPE", "B200_CAND_CAPACITY", "B200_MAX_NODES") if hasattr(config, k)}
         self.num_nodes_per_image = None
         self.num_edges_per_image = None
+
+    def _grow(self, flags):
+        """The fixed-size device buffers were too small for this input (the reference has no such limit): grow the ones
+        that overflowed and tell the caller to run the detection again.  False when nothing can grow any further."""
+        if flags & 8:
+            return False
+        ok = True
+        if flags & 1:
+            ok &= "B200_CAND_CAPACITY" not in self._fixed_caps and self.cand_capacity < 16384
+            self.cand_capacity = min(16384, 4 * self.cand_capacity)
+        if flags & 2:
+            ok &= "B200_MAX_DET_PER_TYPE" not in self._fixed_caps and self.max_det_per_type < 4096
+            self.max_det_per_type = min(4096, 4 * self.max_det_per_type)
+        if flags & 4 or (flags & 2 and "B200_MAX_NODES" not in self._fixed_caps):
+            ok &= "B200_MAX_NODES" not in self._fixed_caps and self.max_nodes < 16384
+            self.max_nodes = min(16384, 2 * self.max_nodes)
+        return bool(ok)
 
     def construct_graph(self):
         lib = nv.lib()
@@ -158,22 +177,25 @@ class NaiveGraphConstructor:
         dev = sm.device
         with torch.cuda.device(dev):
             stream = nv.current_stream()
-            p = nv.GcParams(
-                batch=B, num_joints=J, height=H, width=W, pool_kernel=self.pool_kernel_size, top_k=self._top_k,
-                use_threshold=int(self.detect_threshold is not None),
-                threshold=float(self.detect_threshold if self.detect_threshold is not None else 0.0),
-                graph_type=nv.GRAPH_FULLY if self.mpn_graph_type == "fully" else nv.GRAPH_KNN, knn_k=KNN_K,
-                edge_features=self._edge_feat_bits,
-                norm_factor=float(max(W, H) if self.normalize_node_distance else 1),     # CG.py:311-314
-                cand_capacity=self.cand_capacity, max_det_per_type=self.max_det_per_type, max_nodes=self.max_nodes,
-                scoremaps=sm.data_ptr(), mask=mask.data_ptr() if mask is not None else None)
-            ws_bytes = int(lib.pgmp_gc_workspace_bytes(p))
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            p.workspace, p.workspace_bytes = ws.data_ptr(), ws_bytes
-            counts = torch.empty(2 + 2 * B + 1, dtype=torch.int64, device=dev)
-            nv.check(lib.pgmp_gc_detect(p, counts.data_ptr(), stream))
-            counts_h = counts.cpu()            # the one host read of the graph constructor
-            flags = int(counts_h[-1])
+            for attempt in range(6):
+                p = nv.GcParams(
+                    batch=B, num_joints=J, height=H, width=W, pool_kernel=self.pool_kernel_size, top_k=self._top_k,
+                    use_threshold=int(self.detect_threshold is not None),
+                    threshold=float(self.detect_threshold if self.detect_threshold is not None else 0.0),
+                    graph_type=nv.GRAPH_FULLY if self.mpn_graph_type == "fully" else nv.GRAPH_KNN, knn_k=KNN_K,
+                    edge_features=self._edge_feat_bits,
+                    norm_factor=float(max(W, H) if self.normalize_node_distance else 1),     # CG.py:311-314
+                    cand_capacity=self.cand_capacity, max_det_per_type=self.max_det_per_type, max_nodes=self.max_nodes,
+                    scoremaps=sm.data_ptr(), mask=mask.data_ptr() if mask is not None else None)
+                ws_bytes = int(lib.pgmp_gc_workspace_bytes(p))
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                p.workspace, p.workspace_bytes = ws.data_ptr(), ws_bytes
+                counts = torch.empty(2 + 2 * B + 1, dtype=torch.int64, device=dev)
+                nv.check(lib.pgmp_gc_detect(p, counts.data_ptr(), stream))
+                counts_h = counts.cpu()            # the one host read of the graph constructor
+                flags = int(counts_h[-1])
+                if not flags or not self._grow(flags):
+                    break
             if flags:
                 raise RuntimeError("graph constructor capacity exceeded: " +
                                    "; ".join(msg for bit, msg in nv.GC_FLAGS.items() if flags & bit))

@@ -94,6 +94,87 @@ def test_graph_constructor_capacity_errors_are_loud():
         run_gc("thr_extras", B200_MAX_DET_PER_TYPE=8)
 
 
+def _gc_vs_oracle(x, cfg, nj, masks=None, feat_c=2):
+    """construct_graph() of the CUDA path on scoremaps ``x`` [B,J,H,W] against the oracle, every output bit-exact."""
+    rng = np.random.default_rng(int(x.size) % 9973)
+    feat = rng.standard_normal((x.shape[0], feat_c) + x.shape[2:]).astype(np.float32)
+    tags = rng.standard_normal(x.shape).astype(np.float32)
+    t = lambda a: torch.from_numpy(a).to(DEV)
+    ret = get_graph_constructor(cfg, scoremaps=t(x), tagmaps=t(tags), features=t(feat), joints_gt=None, factor_list=None,
+                                masks=t(masks) if masks is not None else None, device=DEV, testing=True, heatmaps=None,
+                                num_joints=nj).construct_graph()
+    want = oracle.gc.construct_graph(x, tags, feat, cfg, nj, masks=masks)
+    for k in GC_KEYS:
+        got = ret[SLOT[k]].cpu().numpy()
+        assert got.shape == want[k].shape, (k, got.shape, want[k].shape)
+        assert np.array_equal(got, want[k]), f"{k}: {np.sum(got != want[k])} mismatches vs oracle"
+    return ret
+
+
+@pytest.mark.parametrize("H,W,pool,strip", [(64, 512, 5, 0), (200, 640, 5, 32), (77, 333, 3, 16), (40, 1100, 5, 0),
+                                            (96, 2052, 7, 40), (33, 50, 9, 8), (130, 130, 1, 64), (512, 512, 5, 512)])
+def test_nms_shapes_strips_and_tiles(H, W, pool, strip, monkeypatch):
+    """The shared-memory row-ring NMS over map shapes that exercise every loader: one contiguous bulk copy per stage
+    (W % 4 == 0, one tile), per-row bulk copies (W > 1024: several column tiles with halos), thread copies (W % 4 != 0),
+    all pool kernels, strips that end inside a stage, and the running cut with several strips per map."""
+    if strip:
+        monkeypatch.setenv("PGMP_NMS_STRIP_ROWS", str(strip))
+    rng = np.random.default_rng(H * 7 + W)
+    J = 3
+    x = rng.uniform(0, 0.02, (2, J, H, W)).astype(np.float32)
+    for b in range(2):
+        for j in range(J):
+            for _ in range(40):       # distinct peaks incl. the borders and corners
+                y, xx = int(rng.integers(0, H)), int(rng.integers(0, W))
+                x[b, j, y, xx] = rng.uniform(0.1, 1.0)
+    x[0, 0, 0, 0] = x[0, 0, H - 1, W - 1] = x[0, 0, 0, W - 1] = x[0, 0, H - 1, 0] = 0.97
+    x[1, 1, H // 2, :7] = 0.5         # a plateau: every pixel of it is a maximum
+    cfg = pgmp_b200.config.bench_gc_config(k=12, POOL_KERNEL_SIZE=pool, DETECT_THRESHOLD=0.9, graph_type="knn")
+    if pool == 1:                     # every positive pixel is a maximum
+        cfg = pgmp_b200.config.bench_gc_config(k=12, POOL_KERNEL_SIZE=1, DETECT_THRESHOLD=0.99, graph_type="knn")
+    _gc_vs_oracle(x, cfg, J)
+
+
+def test_nms_crowd_mask_with_fractional_and_large_values():
+    """score = x * mask (CG.py:1163-1165) with mask values other than 0 / 1: the running cut compares the masked score."""
+    rng = np.random.default_rng(11)
+    x = rng.uniform(0, 0.3, (1, 4, 96, 128)).astype(np.float32)
+    masks = rng.choice(np.array([0.0, 0.5, 1.0, 3.0], np.float32), size=(1, 96, 128))
+    cfg = pgmp_b200.config.bench_gc_config(k=9, POOL_KERNEL_SIZE=3, DETECT_THRESHOLD=0.6, MASK_CROWDS=True, graph_type="knn")
+    _gc_vs_oracle(x, cfg, 4, masks=masks)
+
+
+def test_no_threshold_path_pads_with_zero_score_pixels():
+    """Fewer than 20 positive maxima for a joint (clean or crowd-masked maps): torch.topk pads the block with zero-score
+    pixels and `+ 1e-10` keeps them (CG.py:1184-1195) -- no error, exactly 20 J rows."""
+    rng = np.random.default_rng(3)
+    J, H, W = 4, 48, 64
+    x = np.zeros((2, J, H, W), np.float32)
+    for j, n in enumerate((25, 4, 0, 19)):
+        for _ in range(n):
+            x[0, j, int(rng.integers(0, H)), int(rng.integers(0, W))] = rng.uniform(0.1, 1.0)
+    x[0, 1, 0, 0] = 0.4                                   # the first pixels are maxima themselves: not padding
+    x[0, 1, 0, 2] = 0.3
+    x[1] = rng.uniform(0, 1, (J, H, W)).astype(np.float32)
+    masks = np.ones((2, H, W), np.float32)
+    masks[1, :, 5:] = 0                                   # image 1: only 5 columns survive the crowd mask
+    for mc in (False, True):
+        cfg = pgmp_b200.config.bench_gc_config(k=5, DETECT_THRESHOLD=2.0, MASK_CROWDS=mc, graph_type="knn")
+        ret = _gc_vs_oracle(x, cfg, J, masks=masks if mc else None)
+        assert ret[7].shape[0] == 2 * J * 20
+        assert float(ret[11].min()) == np.float32(1e-10) or not mc
+
+
+def test_default_capacities_grow_on_overflow():
+    """A noisy map with 3 x 3 pooling and a low threshold has ~1 000 detections per joint: the default device capacities
+    (256 per type, 1 024 nodes) grow and the detection is repeated instead of raising."""
+    rng = np.random.default_rng(5)
+    x = rng.uniform(0.1, 1.0, (1, 4, 96, 96)).astype(np.float32)
+    cfg = pgmp_b200.config.bench_gc_config(k=5, POOL_KERNEL_SIZE=3, DETECT_THRESHOLD=0.2, graph_type="knn")
+    ret = _gc_vs_oracle(x, cfg, 4)
+    assert ret[7].shape[0] > 2048
+
+
 def test_nms_hand_made_plateaus_borders():
     """Equal-valued positive plateaus are all maxima; borders behave like -inf padding."""
     x = np.zeros((1, 2, 16, 16), dtype=np.float32)
