@@ -79,7 +79,7 @@ __device__ __forceinline__ int pt(int v) { return (v >> 24) & 0xff; }
 // Zero padding is equivalent to the reference's -inf padding because candidates are positive.
 // ------------------------------------------------------------------------------------------------
 constexpr int kNmsStageRows = 8;     // >= 2 R for every supported R (pool kernel <= 9)
-constexpr int kNmsStages = 4;
+constexpr int kNmsStages = 4;       // stages s, s + 1 are read while s + 2, s + 3 load (3 stages / 4 CTAs per SM measured slower: 0.184 vs 0.175 ms)
 constexpr int kNmsRingRows = kNmsStageRows * kNmsStages;
 constexpr int kNmsListCap = 512;     // per-CTA shared-memory candidate queue (consumer warps -> producer warp), a ring
 constexpr int kNmsKeepCap = 256;     // the producer warp's list of survivors (>= the running cut)
@@ -237,6 +237,15 @@ __device__ __forceinline__ float nms_max3(float a, float b, float c) {   // FMNM
   return d;
 }
 
+// a.x >= b.x || a.y >= b.y || ... as one predicate chain (no SEL / LOP per comparison, no branches)
+__device__ __forceinline__ bool nms_any_ge(float4 a, float4 b) {
+  uint32_t r;
+  asm("{\n .reg .pred p;\n setp.ge.f32 p, %1, %5;\n setp.ge.or.f32 p, %2, %6, p;\n setp.ge.or.f32 p, %3, %7, p;\n"
+      " setp.ge.or.f32 p, %4, %8, p;\n selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(r) : "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w));
+  return r != 0;
+}
+
 // blockDim = 32 x (column bands of the tile x RW row groups + 2).  Consumer warp (band, row group) owns 128 columns
 // and RPW = 8 / RW consecutive rows of every stage.  The last two warps serve them:
 //   LOADER    issues the bulk copies as ring stages are released (one `empty` mbarrier per stage, one arrival per
@@ -245,7 +254,7 @@ __device__ __forceinline__ float nms_max3(float a, float b, float c) {   // FMNM
 // Consumer warps never meet at a CTA-wide barrier until the strip ends: a warp that runs into a blob does not hold
 // up the others, and neither the copies nor the cut wait for each other.
 template <int R, int RPW, bool VEC, bool MASK>
-__global__ void __launch_bounds__(576) nms_candidates_kernel(const NmsArgs a) {
+__global__ void __launch_bounds__(320, 3) nms_candidates_kernel(const NmsArgs a) {
   constexpr int S = kNmsStageRows, RW = S / RPW, HALO = R > 0 ? 1 : 0;
   extern __shared__ __align__(128) uint8_t nms_smem[];
   const int P = a.pitch, H = a.H, W = a.W;
@@ -293,12 +302,12 @@ __global__ void __launch_bounds__(576) nms_candidates_kernel(const NmsArgs a) {
   if (warp == n_cons) {
     // ---- LOADER: stage L = map rows [ybase + L S, ybase + (L + 1) S) -> ring rows (L mod 4) S ...
     for (int L = 0; L < n_stage; ++L) {
-      if (L >= kNmsStages) nms_mbar_wait(empty_a + 8u * (L & (kNmsStages - 1)), (uint32_t)(L / kNmsStages + 1) & 1u);
+      if (L >= kNmsStages) nms_mbar_wait(empty_a + 8u * ((unsigned)L % kNmsStages), (uint32_t)(L / kNmsStages + 1) & 1u);
       const int ys = ybase + L * S;
       const int r_lo = max(ys, 0);
       const int nrows = min(ys + S, y_need) - r_lo;
-      const uint32_t bar = full_a + 8u * (L & (kNmsStages - 1));
-      float* slot = reinterpret_cast<float*>(nms_smem) + (size_t)((L & (kNmsStages - 1)) * S) * P;
+      const uint32_t bar = full_a + 8u * ((unsigned)L % kNmsStages);
+      float* slot = reinterpret_cast<float*>(nms_smem) + (size_t)(((unsigned)L % kNmsStages) * S) * P;
       if (ys < 0 || ys + S > H) {                   // rows above / below the image read as zeros (= the -inf padding, scores > 0)
         for (int r = 0; r < S; ++r)
           if ((unsigned)(ys + r) >= (unsigned)H)
@@ -309,7 +318,7 @@ __global__ void __launch_bounds__(576) nms_candidates_kernel(const NmsArgs a) {
         if (lane == 0) nms_mbar_arrive(bar);
       } else if (VEC) {
         if (lane == 0) {
-          const uint32_t dst = ring_a + (uint32_t)((r_lo - ybase) & (kNmsRingRows - 1)) * rowb;
+          const uint32_t dst = ring_a + (uint32_t)((unsigned)(r_lo - ybase) % kNmsRingRows) * rowb;
           if (a.xtiles == 1) {                      // the tile spans the width: rows are contiguous in memory and in the ring
             const uint32_t bytes = (uint32_t)nrows * rowb;
             nms_mbar_expect_tx(bar, bytes);
@@ -343,7 +352,7 @@ __global__ void __launch_bounds__(576) nms_candidates_kernel(const NmsArgs a) {
       const uint32_t claimed = *reinterpret_cast<volatile uint32_t*>(&s_misc[0]);
       if (claimed == rd) {
         if (done == (uint32_t)n_cons) break;
-        __nanosleep(64);
+        __nanosleep(256);
         continue;
       }
       const uint32_t i = rd + (uint32_t)lane;
@@ -413,11 +422,11 @@ __global__ void __launch_bounds__(576) nms_candidates_kernel(const NmsArgs a) {
       const bool has_v = c < W, has_l = has_v && c >= 4, has_r = c + 4 < W;
       // (threads beyond the map's width read column gx0 instead and never report anything: no zero-filled registers)
       const uint32_t col_a = ring_a + (uint32_t)(has_v ? c - gx0 : 0) * 4u;  // + ring row * P * 4
-      nms_mbar_wait(full_a + 8u * (s & (kNmsStages - 1)), (uint32_t)(s / kNmsStages) & 1u);
-      if (s + 1 < n_stage) nms_mbar_wait(full_a + 8u * ((s + 1) & (kNmsStages - 1)), (uint32_t)((s + 1) / kNmsStages) & 1u);
+      nms_mbar_wait(full_a + 8u * ((unsigned)s % kNmsStages), (uint32_t)(s / kNmsStages) & 1u);
+      if (s + 1 < n_stage) nms_mbar_wait(full_a + 8u * ((unsigned)(s + 1) % kNmsStages), (uint32_t)((s + 1) / kNmsStages) & 1u);
       const float cutf = __uint_as_float(*reinterpret_cast<volatile uint32_t*>(&s_misc[1]));
       const int yr = y0 + s * S + wr * RPW;         // the item's first row
-      const int rr0 = (yr - HALO - ybase) & (kNmsRingRows - 1);   // ring row of its first (halo) row
+      const int rr0 = (int)((unsigned)(yr - HALO - ybase) % kNmsRingRows);   // ring row of its first (halo) row
       // ---- common path: which of the warp's rows hold a pixel that can matter -- score >= cut and, cheaply, not below
       //      the pixel above / below it (rows of a blob other than its ridge fail here); one REDUX for the rows
       uint32_t pm = 0;
@@ -425,7 +434,7 @@ __global__ void __launch_bounds__(576) nms_candidates_kernel(const NmsArgs a) {
         float4 v[RPW + 2 * HALO];
 #pragma unroll
         for (int i = 0; i < RPW + 2 * HALO; ++i) {
-          v[i] = nms_lds128(col_a + (uint32_t)((rr0 + i) & (kNmsRingRows - 1)) * rowb);
+          v[i] = nms_lds128(col_a + (uint32_t)(rr0 + i - (rr0 + i >= kNmsRingRows ? kNmsRingRows : 0)) * rowb);
         }
 #pragma unroll
         for (int i = 0; i < RPW; ++i) {
@@ -447,8 +456,8 @@ __global__ void __launch_bounds__(576) nms_candidates_kernel(const NmsArgs a) {
           } else if (R > 0) {
             const float4 u = v[i], d = v[i + 2 * HALO];
             // ... nor below its neighbours inside this thread's four columns
-            p = (int)(x.x >= fmaxf(nms_max3(u.x, d.x, cutf), x.y)) | (int)(x.y >= nms_max3(nms_max3(u.y, d.y, cutf), x.x, x.z)) |
-                (int)(x.z >= nms_max3(nms_max3(u.z, d.z, cutf), x.y, x.w)) | (int)(x.w >= fmaxf(nms_max3(u.w, d.w, cutf), x.z));
+            p = nms_any_ge(x, make_float4(fmaxf(nms_max3(u.x, d.x, cutf), x.y), nms_max3(nms_max3(u.y, d.y, cutf), x.x, x.z),
+                                          nms_max3(nms_max3(u.z, d.z, cutf), x.y, x.w), fmaxf(nms_max3(u.w, d.w, cutf), x.z)));
           } else {
             p = nms_max3(x.x, x.y, fmaxf(x.z, x.w)) >= cutf;
           }
@@ -466,7 +475,7 @@ __global__ void __launch_bounds__(576) nms_candidates_kernel(const NmsArgs a) {
         // column maxima over the 2R+1 rows, two rows per 3-input max; the centre row's own 4 values are kept
         float cm[12], xc[4] = {0.f, 0.f, 0.f, 0.f};
         auto load_row = [&](int dy, float (&e)[12]) {
-          const uint32_t ra = col_a + (uint32_t)((rr1 + dy + kNmsRingRows) & (kNmsRingRows - 1)) * rowb;
+          const uint32_t ra = col_a + (uint32_t)((unsigned)(rr1 + dy + kNmsRingRows) % kNmsRingRows) * rowb;
           float4 l = make_float4(0.f, 0.f, 0.f, 0.f), rr = l;
           const float4 v = nms_lds128(ra);
           if (R > 2) {
@@ -506,7 +515,7 @@ __global__ void __launch_bounds__(576) nms_candidates_kernel(const NmsArgs a) {
         emit_candidates(sc, (uint32_t)(y * W + c), keys_a, cnt_a, gkeys, gcount, a.cand_cap, a.flags);
       }
       __syncwarp();
-      if (lane == 0) nms_mbar_arrive(empty_a + 8u * (s & (kNmsStages - 1)));   // one of the n_cons items of stage s is done
+      if (lane == 0) nms_mbar_arrive(empty_a + 8u * ((unsigned)s % kNmsStages));   // one of the n_cons items of stage s is done
     }
     if (lane == 0) atomicAdd(&s_misc[6], 1u);
   }
