@@ -9,11 +9,14 @@ Workload = BASELINE.json configs[1]: a COCO-shaped batch of 32 synthetic 512x512
 flagship per-type / edge-attention MPN with skip connections, 10 steps).  One step = one pass of
 construct_graph() + mpn.forward() over the batch.  Prints ONE JSON line (rank 0).
 
-  value        images/s with the inputs resident in HBM (device-timed with CUDA events, max over ranks)
-  e2e          the same metric through the public API called with HOST (pinned) tensors, every step: the heatmaps
-               are copied to the device, the feature / tag maps are read in place over PCIe at the candidate pixels
-               only (the constructor leaves pinned maps on the host), the logits are read back; the sub-key
-               all_inputs_copied is the same call after copying every input to the device as the reference does
+  value        images/s with the inputs resident in HBM (device-timed with CUDA events, max over ranks), K batches
+               through pgmp_b200.pipeline.GroupingPipeline (construct_graph + forward per batch; the next batch's
+               detection half runs on a side stream so the host read of the counts never drains the GPU);
+               serial_calls = the same batches as plain back-to-back calls
+  e2e          the same metric through the same API called with HOST (pinned) tensors, every step: the heatmaps
+               are copied to the device (side stream), the feature / tag maps are read in place over PCIe at the
+               candidate pixels only (the constructor leaves pinned maps on the host), the logits are read back;
+               stage_ms times the stages alone; all_inputs_copied copies every input first as the reference does
   roofline     dominant kernel: algorithmic bytes per launch / its mean CUDA-event duration vs measured HBM peak
   cpu_baseline the UNMODIFIED reference files (baseline/_ref, a verbatim git-ignored copy made by oracle/make_ref.py;
                kind "reference") timed on this box's host cores; the numpy oracle port (kind "port") only when no
@@ -259,102 +262,117 @@ def run_b200(args, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    from pgmp_b200.pipeline import GroupingPipeline
+    pipe = GroupingPipeline(gcfg, model, J, dev)
+    resident = dict(scoremaps=sm, tagmaps=tags, features=feat)
+
+    def run_pipelined(batch, steps, after=None):
+        """`steps` batches through the public pipelined API (construct_graph + forward per batch, the detection half of
+        the next batch in flight on a side stream); every batch does the full work."""
+        out = None
+        for out in pipe.run(batch for _ in range(steps)):
+            if after is not None:
+                after(out)
+        return out
+
     for _ in range(max(args.warmup, 3)):
         ret, pe, pn, pc = step(sm, tags, feat)
+    run_pipelined(resident, 2)
     edges_per_step = int(ret[2].shape[1])
     nodes_per_step = int(ret[0].shape[0])
 
-    # ---- timed region 1: inputs resident in HBM
+    # ---- timed region 1: inputs resident in HBM, K batches through the pipelined API
     sampler = ClockSampler(local_rank)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     launches0 = nv.kernel_launches()
     ev0.record()
-    for _ in range(args.steps):
-        step(sm, tags, feat)
+    run_pipelined(resident, args.steps)
     ev1.record()
     barrier()
     launches = nv.kernel_launches() - launches0
     t_dev = reduce_max(ev0.elapsed_time(ev1) / 1e3)
     clocks = sampler.summary()
+    # the same K steps as plain back-to-back calls (one host wait per batch), for comparison
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step(sm, tags, feat)
+    ev1.record()
+    barrier()
+    t_serial = reduce_max(ev0.elapsed_time(ev1) / 1e3)
 
-    # ---- per-kernel CUDA-event durations over the same K steps (separate pass; events bracket every launch)
+    # ---- per-kernel CUDA-event durations over K steps (separate pass; events bracket every launch)
     nv.profile(True)
     for _ in range(args.steps):
         step(sm, tags, feat)
     prof = nv.profile_collect()
     nv.profile(False)
 
-    # ---- timed region 2: end to end from pinned host buffers
-    feat_h = torch.empty(feat.shape, dtype=feat.dtype, pin_memory=True).copy_(feat)
+    # ---- timed region 2: end to end from pinned host buffers through the same API.  The heatmaps are copied to the
+    # device (every pixel is read by the NMS); of the feature / tag maps only the candidate pixels are read, in place
+    # over PCIe (graph_constructor/__init__.py); the logits are read back into pinned host memory every step.
+    # The feature maps sit in pinned host memory in channels_last memory format ([B, C, H, W] tensor, C innermost): a
+    # node's 128 channels are one 512-byte read over PCIe.  With the reference's NCHW strides the same gather is 2.1 M
+    # separate 4-byte reads (measured: 7.1 ms per step, features_nchw below); both layouts give bit-identical outputs.
+    feat_h = torch.empty(feat.shape, dtype=feat.dtype, pin_memory=True, memory_format=torch.channels_last).copy_(feat)
+    feat_h_nchw = torch.empty(feat.shape, dtype=feat.dtype, pin_memory=True).copy_(feat)
     tags_h = torch.empty(tags.shape, dtype=tags.dtype, pin_memory=True).copy_(tags)
-    out_h = None
+    host = dict(scoremaps=sm_h, tagmaps=tags_h, features=feat_h)
+    out_h = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in (pe[-1], pn[-1], pc[-1])]
+    d2h = sum(h.numel() * 4 for h in out_h)
+    n_nodes = nodes_per_step
 
-    # The public API is handed the pinned HOST tensors.  Heatmaps are copied to the device (every pixel is read by
-    # the NMS); of the feature / tag maps only the candidate pixels are read, in place over PCIe
-    # (graph_constructor/__init__.py), unless copy_all forces the reference's behaviour of moving every input.
-    def e2e_step(copy_all=False):
-        nonlocal out_h
-        s_d = sm_h.to(dev, non_blocking=True)
-        t_in = tags_h.to(dev, non_blocking=True) if copy_all else tags_h
-        f_in = feat_h.to(dev, non_blocking=True) if copy_all else feat_h
-        ret, pe, pn, pc = step(s_d, t_in, f_in)
-        if out_h is None:
-            out_h = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in (pe[-1], pn[-1], pc[-1])]
-        for h, d in zip(out_h, (pe[-1], pn[-1], pc[-1])):
+    def read_back(out):
+        for h, d in zip(out_h, (out[1][0][-1], out[1][1][-1], out[1][2][-1])):
             h.copy_(d, non_blocking=True)
-        return sum(h.numel() * 4 for h in out_h), ret[0].shape[0]
 
-    def time_e2e(copy_all):
-        e2e_step(copy_all)
-        e2e_step(copy_all)
+    def time_e2e(fn):
+        fn(2)
         barrier()
         ev0.record()
-        for _ in range(args.steps):
-            e2e_step(copy_all)
+        fn(args.steps)
         ev1.record()
         barrier()
         return reduce_max(ev0.elapsed_time(ev1) / 1e3)
 
-    d2h, n_nodes = e2e_step()
-    t_e2e = time_e2e(False)
-    t_e2e_copy = time_e2e(True)
+    def e2e_serial(steps, copy_all=False):          # plain calls: copy, compute and read-back strictly one after another
+        for _ in range(steps):
+            b = dict(host)
+            if copy_all:                            # the reference's behaviour: every input moved first (CG.py:12-18)
+                b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            gc = get_graph_constructor(gcfg, scoremaps=b["scoremaps"], tagmaps=b["tagmaps"], features=b["features"],
+                                       joints_gt=None, factor_list=None, masks=None, device=dev, testing=True, heatmaps=None,
+                                       num_joints=J)
+            ret_ = gc.construct_graph()
+            with torch.no_grad():
+                o = model(ret_[0], ret_[1], ret_[2], node_types=ret_[7][:, 2])
+            read_back((ret_, o))
 
-    # informational: the same steps with the next step's heatmap copy issued on a second stream while the current
-    # step computes (what a prefetching data loader does); every step's copy and read-back stay inside the timed region
-    copy_stream = torch.cuda.Stream(device=dev)
-    bufs = [torch.empty(sm_h.shape, dtype=sm_h.dtype, device=dev) for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
-    freed = [torch.cuda.Event() for _ in range(2)]
-
-    def prefetch(i):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(freed[i & 1])
-            bufs[i & 1].copy_(sm_h, non_blocking=True)
-            ready[i & 1].record(copy_stream)
-
-    def pipelined(steps):
-        cur = torch.cuda.current_stream()
-        for ev in freed:
-            ev.record(cur)
-        prefetch(0)
-        for i in range(steps):
-            if i + 1 < steps:
-                prefetch(i + 1)
-            cur.wait_event(ready[i & 1])
-            ret, pe, pn, pc = step(bufs[i & 1], tags_h, feat_h)
-            freed[i & 1].record(cur)
-            for h, d in zip(out_h, (pe[-1], pn[-1], pc[-1])):
-                h.copy_(d, non_blocking=True)
-
-    pipelined(2)
+    t_e2e = time_e2e(lambda k: run_pipelined(host, k, after=read_back))
+    t_e2e_serial = time_e2e(e2e_serial)
+    host_nchw = dict(host, features=feat_h_nchw)
+    t_e2e_nchw = time_e2e(lambda k: run_pipelined(host_nchw, k, after=read_back))
+    t_e2e_copy = time_e2e(lambda k: e2e_serial(k, copy_all=True))
+    # stages of one end-to-end step, each timed alone: the heatmap copy, and the kernels with the maps on the host
+    sm_d = torch.empty(sm_h.shape, dtype=sm_h.dtype, device=dev)
+    sm_d.copy_(sm_h, non_blocking=True)
     barrier()
     ev0.record()
-    pipelined(args.steps)
+    for _ in range(3):
+        sm_d.copy_(sm_h, non_blocking=True)
     ev1.record()
     barrier()
-    t_e2e_pipe = reduce_max(ev0.elapsed_time(ev1) / 1e3)
+    t_copy = ev0.elapsed_time(ev1) / 3
+    nv.profile(True)
+    e2e_serial(2)
+    prof_h = nv.profile_collect()
+    nv.profile(False)
+    stage_ms = {"heatmap_h2d": t_copy,
+                "gather_from_host": sum(prof_h[k][1] / prof_h[k][0] for k in ("gather_features_kernel", "emit_nodes_kernel") if k in prof_h),
+                "kernels_total": sum(v[1] for v in prof_h.values()) / 2}
+    del sm_d
     h2d_copy_all = sm_h.numel() * 4 + feat_h.numel() * 4 + tags_h.numel() * 4
     # bytes that cross PCIe towards the device per step: the heatmap copy + the gathered feature / tag elements
     h2d = sm_h.numel() * 4 + n_nodes * feat_h.shape[1] * 4 + n_nodes * 4
@@ -449,15 +467,25 @@ def run_b200(args, rank, local_rank, world):
 
     line = {"metric": METRIC, "value": value, "unit": "images/s", "edges_per_s": total_edges / t_dev,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_dev / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, world), "clocks": clocks,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16x3 (bf16 hi/lo operand pairs on tcgen05, fp32 accumulate, fp32-equivalent storage)" if args.precision == "tc" else "f32",
+            "data": "synthetic", "config": workload_config(args, world), "clocks": clocks,
+            "serial_calls": {"value": total_images / t_serial, "ms_per_step": 1e3 * t_serial / args.steps,
+                             "note": "the same batches as plain back-to-back construct_graph() + forward() calls (one host "
+                                     "wait per batch); value uses pgmp_b200.pipeline.GroupingPipeline, which starts the "
+                                     "next batch's detection half on a side stream"},
             "e2e": {"value": total_images / t_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * t_e2e / args.steps,
-                    "inputs": "pinned host tensors passed to the public API: heatmaps copied, feature / tag maps "
-                              "gathered in place over PCIe (only the candidate pixels)",
+                    "inputs": "pinned host tensors passed to the public API (GroupingPipeline): heatmaps copied on the side "
+                              "stream while the previous batch computes, feature / tag maps gathered in place over PCIe "
+                              "(only the candidate pixels), logits read back every step",
+                    "stage_ms": stage_ms,
+                    "pcie_gbs_heatmap_copy": sm_h.numel() * 4 / (t_copy * 1e-3) / 1e9,
+                    "serial_calls": {"value": total_images / t_e2e_serial, "ms_per_step": 1e3 * t_e2e_serial / args.steps},
+                    "features_nchw": {"value": total_images / t_e2e_nchw, "ms_per_step": 1e3 * t_e2e_nchw / args.steps,
+                                      "note": "the same pipelined calls with the host feature maps in NCHW strides"},
                     "all_inputs_copied": {"value": total_images / t_e2e_copy, "ms_per_step": 1e3 * t_e2e_copy / args.steps,
-                                          "h2d_bytes_per_step": h2d_copy_all},
-                    "next_copy_prefetched": {"value": total_images / t_e2e_pipe, "ms_per_step": 1e3 * t_e2e_pipe / args.steps}},
+                                          "h2d_bytes_per_step": h2d_copy_all}},
             "gpu_launches": int(launches), "roofline": roofline, "roofline_nms": roofline_nms, "cpu_baseline": cpu,
             "kernels": kernels,
             "grouping_tail": {"ms_per_step": 1e3 * t_group / args.steps, "persons_per_image": persons_per_image,

@@ -11,6 +11,8 @@
 // accumulator lives in tensor memory and is read back one row per thread for the fused epilogue:
 // bias / gathered per-node terms, ReLU, the attention logit, the in-tile per-(target, type)
 // softmax / sum / max reduction (no atomics) and the write-back of g'.
+#include <cstdlib>
+
 #include "mpn_common.cuh"
 #include "umma.cuh"
 
@@ -71,89 +73,110 @@ constexpr int kWgBytes = kWgMisc + 2048;
 constexpr size_t kEdgeSmemBytes = kOffWg + 2 * kWgBytes + 64 + 1024;
 static_assert(kOffWg % 1024 == 0 && kWgBytes % 1024 == 0 && kWgAdd % 1024 == 0 && kWgWm % 1024 == 0, "operand tiles must be 1024-byte aligned");
 
-__global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const EdgeTcArgs a) {
+// ---- the step kernel: TWO threads per edge slot (column halves), 2 tiles in flight = 512 threads = 16 warps per SM ------
+// Thread (row, half) owns columns [32 half, 32 half + 32) of its row -- warps w and w + 4 of a tile group share the TMEM
+// lane quarter w & 3, so both may read it.  Against one thread per row (round 1: a 64-wide accumulator row per thread,
+// 255 registers, 8 warps per SM) this halves the registers and the instruction stream per thread and doubles the warps
+// the schedulers can switch between (ncu warps active 12.5 % -> 25 %, issue slots 36 % -> 43 % busy).  Row-wise quantities
+// that need the whole row (attention logit) are summed through shared memory.
+// Measured with in-kernel phase timers (17 000 cycles per tile, round 2): ~3 100 issuing the P / Q gathers (16-byte
+// chunks of 32 different rows per request: the L1 data pipe is the busiest unit, 55 %), ~1 100 per product between its
+// operands being ready and its result being visible (x 3), ~3 900 in the three epilogues, ~2 000 in the run scan,
+// ~2 400 in the run reduction.  Tried and rejected, with numbers, in DESIGN.md: cooperative (line-wide) table gathers
+// through the staging tile, requesting the next tile's features a whole tile early, L2 prefetch of the next tile's rows.
+constexpr int kTgThreads = 256;                 // one tile group = one tile in flight
+constexpr int kEdge2Threads = 2 * kTgThreads;
+constexpr int kWg2Misc = kWgMisc;               // dst[128] prow[128] att[128] wa[64] bars[4] scan[12] seg[16] att1[128]
+constexpr int kWg2Bytes = kWgMisc + 3072;
+constexpr size_t kEdge2SmemBytes = kOffWg + 2 * kWg2Bytes + 64 + 1024;
+static_assert(kWg2Bytes % 1024 == 0, "operand tiles must be 1024-byte aligned");
+static_assert(kEdge2SmemBytes <= 227 * 1024, "edge step: shared memory");
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  tmem_ld16(taddr, v);
+  tmem_ld16(taddr + 16, v + 16);
+  tmem_ld_wait();
+}
+
+__global__ void __launch_bounds__(kEdge2Threads, 1) edge_step_tc_kernel(const EdgeTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  // (offset arithmetic on the __shared__ array keeps the shared address space visible to the compiler: LDS / STS, not generic LD / ST)
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(base);
-  const int tid = threadIdx.x, wg = tid >> 7, wt = tid & 127, warp = tid >> 5;
+  const int tid = threadIdx.x, tg = tid >> 8, tt = tid & 255, warp = tid >> 5;
+  const int row = tt & 127, half = tt >> 7, c0col = 32 * half;      // this thread: row of the tile, columns [c0col, c0col + 32)
   const uint32_t w1_hi = sbase + kOffW1, w1_lo = w1_hi + kWTile, w2_hi = sbase + kOffW2, w2_lo = w2_hi + kWTile;
   const uint32_t wh1_hi = sbase + kOffWh1, wh1_lo = wh1_hi + kWTile, wh2_hi = sbase + kOffWh2, wh2_lo = wh2_hi + kWTile / 2;
   float* s_const = reinterpret_cast<float*>(base + kOffConst);
   float* s_b2 = s_const; float* s_bh1 = s_const + 64; float* s_bh2 = s_const + 128; float* s_wh3 = s_const + 160;
   int* s_gstart = reinterpret_cast<int*>(s_const + 192);     // [T + 1] first slot of each type group
   int* s_gpstart = s_gstart + 20;                            // [T + 1] first part row of each type group
-  uint8_t* wgb = base + kOffWg + wg * kWgBytes;
+  uint8_t* wgb = base + kOffWg + tg * kWg2Bytes;
   const uint32_t a_hi = smem_u32(wgb) + kWgA, a_lo = a_hi + kATile;
   const uint32_t add_a = smem_u32(wgb) + kWgAdd;
   const uint32_t wm_hi = smem_u32(wgb) + kWgWm, wm_lo = wm_hi + kWTile;
-  int* s_dst = reinterpret_cast<int*>(wgb + kWgMisc);
-  int* s_src = s_dst + kTile;                                 // (only its storage is used: s_prow)
-  float* s_att = reinterpret_cast<float*>(s_src + kTile);
+  int* s_dst = reinterpret_cast<int*>(wgb + kWg2Misc);
+  int* s_prow = s_dst + kTile;                                // part row stored by the last row of every run, else -1
+  float* s_att = reinterpret_cast<float*>(s_prow + kTile);    // first: half 0's share of the logit, then the softmax weight
   float* s_wa = s_att + kTile;
   uint64_t* bar = reinterpret_cast<uint64_t*>(s_wa + kD);   // MMA completions
   uint64_t* g_bar = bar + 1;                                  // bulk load of the edge-feature image
   uint64_t* c_bar = bar + 2;                                  // bulk load of the C image
-  int* s_prow = s_src;                                        // part row stored by the last row of every run, else -1
   float* s_wfirst = reinterpret_cast<float*>(bar + 4);        // per warp: max logit of its first / last run segment,
   float* s_wlast = s_wfirst + 4;                              // flags: bit 0 = lane 0 continues the previous warp's run,
   int* s_wflag = reinterpret_cast<int*>(s_wlast + 4);         //        bit 1 = the whole warp is one segment
-  int* s_seg = s_wflag + 4;                                   // [8] first row of the k-th row segment of the run reduction
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base + kOffWg + 2 * kWgBytes);
-  const float* s_add = reinterpret_cast<const float*>(wgb + kWgAdd);
+  int* s_seg = s_wflag + 4;                                   // [16] first row of the k-th row segment of the run reduction
+  float* s_att1 = reinterpret_cast<float*>(s_seg + 16);       // half 1's share of the attention logit
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base + kOffWg + 2 * kWg2Bytes);
 
   if (warp == 0) tmem_alloc<kEdgeTmemCols>(tmem_slot);
-  if (wt == 0) { mbar_init(bar, 1); mbar_init(g_bar, 1); mbar_init(c_bar, 1); }
+  if (tt == 0) { mbar_init(bar, 1); mbar_init(g_bar, 1); mbar_init(c_bar, 1); }
   fence_barrier_init();
-  load_weight_tile_a(w1_hi, a.w1, kD, kD, tid, kEdgeThreads);
-  load_weight_tile_a(w1_lo, a.w1 + kD * kD, kD, kD, tid, kEdgeThreads);
-  load_weight_tile_a(w2_hi, a.w2, kD, kD, tid, kEdgeThreads);
-  load_weight_tile_a(w2_lo, a.w2 + kD * kD, kD, kD, tid, kEdgeThreads);
+  load_weight_tile_a(w1_hi, a.w1, kD, kD, tid, kEdge2Threads);
+  load_weight_tile_a(w1_lo, a.w1 + kD * kD, kD, kD, tid, kEdge2Threads);
+  load_weight_tile_a(w2_hi, a.w2, kD, kD, tid, kEdge2Threads);
+  load_weight_tile_a(w2_lo, a.w2 + kD * kD, kD, kD, tid, kEdge2Threads);
   if (a.with_head) {
-    load_weight_tile_a(wh1_hi, a.wh1, kD, kD, tid, kEdgeThreads);
-    load_weight_tile_a(wh1_lo, a.wh1 + kD * kD, kD, kD, tid, kEdgeThreads);
-    load_weight_tile_a(wh2_hi, a.wh2, 32, kD, tid, kEdgeThreads);
-    load_weight_tile_a(wh2_lo, a.wh2 + 32 * kD, 32, kD, tid, kEdgeThreads);
+    load_weight_tile_a(wh1_hi, a.wh1, kD, kD, tid, kEdge2Threads);
+    load_weight_tile_a(wh1_lo, a.wh1 + kD * kD, kD, kD, tid, kEdge2Threads);
+    load_weight_tile_a(wh2_hi, a.wh2, 32, kD, tid, kEdge2Threads);
+    load_weight_tile_a(wh2_lo, a.wh2 + 32 * kD, 32, kD, tid, kEdge2Threads);
     if (tid < kD) s_bh1[tid] = a.bh1[tid];
     if (tid < 32) { s_bh2[tid] = a.bh2[tid]; s_wh3[tid] = a.wh3[tid]; }
   }
   if (tid < kD) s_b2[tid] = a.b2[tid];
   if (tid <= a.T) { s_gstart[tid] = a.group_start[tid]; s_gpstart[tid] = a.group_pstart[tid]; }
-  if (wt < kD) s_wa[wt] = 0.f;
+  if (tt < kD) s_wa[tt] = 0.f;
   fence_before_sync();
   fence_async_smem();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tmem = *tmem_slot + (uint32_t)(wg * 128);   // this warpgroup's 128 columns
+  const uint32_t tmem = *tmem_slot + (uint32_t)(tg * 128);   // this tile group's 128 columns
   const uint32_t tmem_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // ... at this warp's lanes
-  const int bar_id = 1 + wg;
+  const int bar_id = 1 + tg, scan_bar_id = 3 + tg;
   uint32_t phase = 0, ld_phase = 0;
   int cur_tm = -1, cur_col = -1;
   float att_bias = 0.f;
   bool g_issued = false;        // the tile's edge features were requested during the previous tile
-  const bool copier_warp = (wt >> 5) == 1;   // one elected lane of this warp owns the bulk copies (loads of g / C, write-back of g')
+  const bool copier_warp = (tt >> 5) == 1;   // one elected lane of this warp owns the bulk copies (loads of g / C, write-back of g')
   uint8_t* __restrict__ g_img = reinterpret_cast<uint8_t*>(a.g);
 
   const int total_tiles = a.group_start[a.T] >> 7;
   const int units = 2 * gridDim.x;
   const int per_unit = (total_tiles + units - 1) / units;
-  const int tile_begin = (blockIdx.x * 2 + wg) * per_unit;
+  const int tile_begin = (blockIdx.x * 2 + tg) * per_unit;
   const int tile_end = min(tile_begin + per_unit, total_tiles);
 
-  // per-row indices of the first tile (later tiles are prefetched one tile ahead)
-  int n_e = -1, n_src = -1, n_dst = -1;
+  int n_e = -1, n_src = -1, n_dst = -1;      // per-row indices, prefetched one tile ahead (both halves of a row hold them)
   if (tile_begin < tile_end) {
-    const int64_t sl = (int64_t)tile_begin * kTile + wt;
+    const int64_t sl = (int64_t)tile_begin * kTile + row;
     n_e = a.slot_edge[sl]; n_src = a.slot_src[sl]; n_dst = a.slot_dst[sl];
   }
-  int t = 0;                    // source type of the tile: monotone over the tiles of a warpgroup
+  int t = 0;                    // source type of the tile: monotone over the tiles of a tile group
   for (int tile = tile_begin; tile < tile_end; ++tile) {
     const int slot0 = tile * kTile;
     while (t + 1 < a.T && slot0 >= s_gstart[t + 1]) ++t;
     const int tm = a.per_type ? t : 0;
     const int col = a.attn == PGMP_ATTN_PER_TYPE ? t : 0;
-    // ---- bulk requests: g (bf16 hi/lo tile image) straight into the operand tiles, C (swizzled fp32 tile image)
-    //      into the staging tile; both complete on mbarriers, no registers and no per-thread copies
     if (copier_warp && elect_one()) {
       if (!g_issued) {
         mbar_expect_tx(g_bar, 2 * kATile);
@@ -162,68 +185,71 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
       if (a.c0) {
         mbar_expect_tx(c_bar, kAddTile);
         bulk_load(add_a, a.c0 + (size_t)slot0 * kD, kAddTile, c_bar);
-        // the staging tile is busy until the end of a tile, so the next tile's C cannot be fetched early; pull it
-        // into L2 now, the load above then pays an L2 hit instead of an HBM round trip at the next tile's start
         if (tile + 1 < tile_end) bulk_prefetch_l2(a.c0 + (size_t)(slot0 + kTile) * kD, kAddTile);
       }
     }
     const int e = n_e, src = n_src, dst = n_dst;
-    s_dst[wt] = e >= 0 ? dst : -1;
-    if (wt < 8) s_seg[wt] = wt == 0 ? 0 : kTile;
+    if (half == 0) s_dst[row] = e >= 0 ? dst : -1;
+    if (tt < 16) s_seg[tt] = tt == 0 ? 0 : kTile;
     if (tile + 1 < tile_end) {   // next tile's indices
-      const int64_t sl = (int64_t)slot0 + kTile + wt;
+      const int64_t sl = (int64_t)slot0 + kTile + row;
       n_e = a.slot_edge[sl]; n_src = a.slot_src[sl]; n_dst = a.slot_dst[sl];
     }
-    int bin_ls = 0, bin_lp = 0;   // where this row's bin starts (slots / parts), used by the reduction at the end
-    if (e >= 0) {
+    int bin_ls = 0, bin_lp = 0;   // where this row's bin starts (slots / parts), used by the last row of a run
+    if (half == 0 && e >= 0) {
       const int64_t bin = (int64_t)t * a.N + dst;
       bin_ls = a.bin_lstart[bin];
       bin_lp = a.bin_lpart[bin];
     }
     if (tm != cur_tm) {     // all MMAs of the previous tile have completed
-      load_weight_tile_a(wm_hi, a.wm + (size_t)tm * 2 * kD * kD, kD, kD, wt, kWgThreads);
-      load_weight_tile_a(wm_lo, a.wm + (size_t)tm * 2 * kD * kD + kD * kD, kD, kD, wt, kWgThreads);
+      load_weight_tile_a(wm_hi, a.wm + (size_t)tm * 2 * kD * kD, kD, kD, tt, kTgThreads);
+      load_weight_tile_a(wm_lo, a.wm + (size_t)tm * 2 * kD * kD + kD * kD, kD, kD, tt, kTgThreads);
       fence_async_smem();
       cur_tm = tm;
     }
     if (a.attn && col != cur_col) {
-      if (wt < kD) s_wa[wt] = a.wa[wt * a.attn_cols + col];
+      if (tt < kD) s_wa[tt] = a.wa[tt * a.attn_cols + col];
       att_bias = __ldg(a.ba + col);
       cur_col = col;
     }
-    // ---- P[dst] and Q[src]: this thread's own two table rows, 16-byte chunks (the tables are swizzled tile images:
-    //      logical chunk q of node n sits at position q ^ (n & 15)); rows of a run share dst, so a warp's P request
-    //      touches about ten lines; all 32 loads of a thread are in flight behind the first product
-    float4 pv[kD / 4], qv[kD / 4];
+    // ---- P[dst] and Q[src]: this thread's half of its two table rows (swizzled tile images: logical 16-byte chunk q
+    //      of node n sits at position q ^ (n & 15)), requested before the first product is waited for, summed on arrival.
+    //      (Gathering the rows cooperatively -- 16 threads per 256-byte row through the staging tile -- was measured:
+    //      the L1 requests drop 8x but the gather latency lands on the tile's critical path, 3.28 ms instead of 2.26 ms
+    //      per 10 steps.)
+    float4 pq[8];
     {
       const float4* __restrict__ prow = reinterpret_cast<const float4*>(a.tab_p + (size_t)(e >= 0 ? dst : 0) * kD);
       const float4* __restrict__ qrow = reinterpret_cast<const float4*>(a.tab_q + (size_t)(e >= 0 ? src : 0) * kD);
       const int xd = dst & 15, xs = src & 15;
+      float4 qv[8];
 #pragma unroll
-      for (int q = 0; q < kD / 4; ++q) {
-        pv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        qv[q] = pv[q];
-        if (e >= 0) { pv[q] = __ldg(prow + (q ^ xd)); qv[q] = __ldg(qrow + (q ^ xs)); }
+      for (int q = 0; q < 8; ++q) {
+        pq[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        qv[q] = pq[q];
+        if (e >= 0) { pq[q] = __ldg(prow + ((8 * half + q) ^ xd)); qv[q] = __ldg(qrow + ((8 * half + q) ^ xs)); }
       }
-    }
-    if (wt < 32 && elect_one()) {        // the edge features have landed (usually long ago): first product
-      mbar_wait(g_bar, ld_phase);
-      fence_after_sync();
-      issue_gemm_x3<kD>(tmem, a_hi, a_lo, 0, w1_hi, w1_lo, 0, 1, false);
-      mma_commit(bar);
+      if (tt < 32 && elect_one()) {        // the edge features have landed: first product
+        mbar_wait(g_bar, ld_phase);
+        fence_after_sync();
+        issue_gemm_x3<kD>(tmem, a_hi, a_lo, 0, w1_hi, w1_lo, 0, 1, false);
+        mma_commit(bar);
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { pq[q].x += qv[q].x; pq[q].y += qv[q].y; pq[q].z += qv[q].z; pq[q].w += qv[q].w; }
     }
     if (a.c0) mbar_wait(c_bar, ld_phase);          // the C image sits in the staging tile
     ld_phase ^= 1;
     mbar_wait(bar, phase);
     phase ^= 1;
     fence_after_sync();
-    float d[kD];
-    tmem_ld64(tmem, 0, d);
+    float d[32];
+    tmem_ld32(tmem_row + (uint32_t)c0col, d);
 #pragma unroll
-    for (int q = 0; q < kD / 4; ++q) {
-      float4 v = make_float4(pv[q].x + qv[q].x, pv[q].y + qv[q].y, pv[q].z + qv[q].z, pv[q].w + qv[q].w);
+    for (int q = 0; q < 8; ++q) {
+      float4 v = pq[q];
       if (a.c0) {
-        const float4 c = lds128f(add_a + 4 * stage_index(wt, 4 * q));
+        const float4 c = lds128f(add_a + 4 * stage_index(row, c0col + 4 * q));
         v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
       }
       d[4 * q + 0] = fmaxf(d[4 * q + 0] + v.x, 0.f);
@@ -231,73 +257,69 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
       d[4 * q + 2] = fmaxf(d[4 * q + 2] + v.z, 0.f);
       d[4 * q + 3] = fmaxf(d[4 * q + 3] + v.w, 0.f);
     }
-    // hidden goes to tensor memory (columns 64..127 of this warpgroup, free until the head product of a reported
-    // step): the second product takes its A operand from there, no swizzled shared-memory stores or operand reads
-    store_split_row_tmem(tmem_row + 64, tmem_row + 96, d);
+    {   // hidden -> tensor memory (TS-form A operand: element k of a row in half k & 1 of column k / 2): this thread's
+        // 32 elements are 16 columns of the hi block (64 ..) and 16 of the lo block (96 ..)
+      uint32_t h[16], l[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) split2(d[2 * i], d[2 * i + 1], h[i], l[i]);
+      tmem_st16(tmem_row + 64 + 16 * half, h);
+      tmem_st16(tmem_row + 96 + 16 * half, l);
+      tmem_st_wait();
+    }
     fence_before_sync();
-    named_bar_sync(bar_id, kWgThreads);
-    if (wt < 32 && elect_one()) {
+    named_bar_sync(bar_id, kTgThreads);
+    if (tt < 32 && elect_one()) {
       fence_after_sync();
       issue_gemm_x3_ts<kD>(tmem, tmem + 64, tmem + 96, w2_hi, w2_lo, false);
       mma_commit(bar);
     }
-    // ---- R[type][dst]: this thread's own row, requested now, consumed by the third epilogue
-    float4 rv[kD / 4];
+    // ---- R[type][dst]: this thread's half row, requested now, consumed by the third epilogue
+    float4 rv[8];
     {
       const float4* __restrict__ rrow = reinterpret_cast<const float4*>(a.tab_r + ((size_t)t * a.N + (e >= 0 ? dst : 0)) * kD);
       const int xd = dst & 15;
 #pragma unroll
-      for (int q = 0; q < kD / 4; ++q) {
+      for (int q = 0; q < 8; ++q) {
         rv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e >= 0) rv[q] = __ldg(rrow + (q ^ xd));
+        if (e >= 0) rv[q] = __ldg(rrow + ((8 * half + q) ^ xd));
       }
     }
     mbar_wait(bar, phase);
     phase ^= 1;
     fence_after_sync();
-    tmem_ld64(tmem, 0, d);
-    float att;
+    tmem_ld32(tmem_row + (uint32_t)c0col, d);
     {
-      float at0 = 0.f, at1 = 0.f, at2 = 0.f, at3 = 0.f;   // four independent chains instead of one 64-deep FFMA dependency
+      float at0 = 0.f, at1 = 0.f, at2 = 0.f, at3 = 0.f;   // four independent chains
 #pragma unroll
-      for (int o = 0; o < kD; o += 4) {
-        d[o + 0] = fmaxf(d[o + 0] + s_b2[o + 0], 0.f);
-        d[o + 1] = fmaxf(d[o + 1] + s_b2[o + 1], 0.f);
-        d[o + 2] = fmaxf(d[o + 2] + s_b2[o + 2], 0.f);
-        d[o + 3] = fmaxf(d[o + 3] + s_b2[o + 3], 0.f);
-        at0 = fmaf(d[o + 0], s_wa[o + 0], at0);
-        at1 = fmaf(d[o + 1], s_wa[o + 1], at1);
-        at2 = fmaf(d[o + 2], s_wa[o + 2], at2);
-        at3 = fmaf(d[o + 3], s_wa[o + 3], at3);
+      for (int o = 0; o < 32; o += 4) {
+        d[o + 0] = fmaxf(d[o + 0] + s_b2[c0col + o + 0], 0.f);
+        d[o + 1] = fmaxf(d[o + 1] + s_b2[c0col + o + 1], 0.f);
+        d[o + 2] = fmaxf(d[o + 2] + s_b2[c0col + o + 2], 0.f);
+        d[o + 3] = fmaxf(d[o + 3] + s_b2[c0col + o + 3], 0.f);
+        at0 = fmaf(d[o + 0], s_wa[c0col + o + 0], at0);
+        at1 = fmaf(d[o + 1], s_wa[c0col + o + 1], at1);
+        at2 = fmaf(d[o + 2], s_wa[c0col + o + 2], at2);
+        at3 = fmaf(d[o + 3], s_wa[c0col + o + 3], at3);
       }
-      att = att_bias + ((at0 + at1) + (at2 + at3));
+      (half ? s_att1 : s_att)[row] = (at0 + at1) + (at2 + at3);
     }
-    store_split_row_a(a_hi, a_lo, wt, d);
-    // ---- runs of equal targets (a bin, or the part of it inside this tile): maximum logit of every run, first within
-    //      the warp (segmented shuffle scan), then across the warps of the tile through shared memory
-    const bool is_start = e < 0 || wt == 0 || s_dst[wt - 1] != dst;   // invalid rows are runs of their own
-    const int lane = wt & 31, wq = wt >> 5;
-    float run_max = att;
-    int seg_first = 0, seg_last = 31;
-    if (a.attn) {
-      const unsigned starts = __ballot_sync(0xffffffffu, is_start);
-      const unsigned upto = 0xffffffffu >> (31 - lane);
-      seg_first = 31 - __clz((starts | 1u) & upto);
-      const unsigned above = starts & ~upto;
-      seg_last = above ? __ffs(above) - 2 : 31;
+    {   // g' -> the operand tile (4 of the row's 8 sixteen-byte chunks per thread)
+      const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+      const uint32_t x = (uint32_t)(row & 7);
 #pragma unroll
-      for (int dd = 1; dd < 32; dd <<= 1) {
-        const float o = __shfl_down_sync(0xffffffffu, run_max, dd);
-        if (lane + dd <= seg_last) run_max = fmaxf(run_max, o);
+      for (int c = 0; c < 4; ++c) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split2(d[8 * c + 2 * i], d[8 * c + 2 * i + 1], h[i], l[i]);
+        const uint32_t off = row_off + (((uint32_t)(4 * half + c) ^ x) << 4);
+        sts128(a_hi + off, h[0], h[1], h[2], h[3]);
+        sts128(a_lo + off, l[0], l[1], l[2], l[3]);
       }
-      run_max = __shfl_sync(0xffffffffu, run_max, seg_first);
-      if (lane == 0) { s_wfirst[wq] = run_max; s_wflag[wq] = (is_start ? 0 : 1) | (seg_last == 31 ? 2 : 0); }
-      if (lane == 31) s_wlast[wq] = run_max;
     }
     fence_before_sync();
     fence_async_smem();
-    named_bar_sync(bar_id, kWgThreads);
-    if (wt < 32 && elect_one()) {
+    named_bar_sync(bar_id, kTgThreads);
+    if (tt < 32 && elect_one()) {
       fence_after_sync();
       issue_gemm_x3<kD>(tmem, a_hi, a_lo, 0, wm_hi, wm_lo, 0, 1, false);
       if (a.with_head) issue_gemm_x3<kD>(tmem + 64, a_hi, a_lo, 0, wh1_hi, wh1_lo, 0, 1, false);
@@ -305,61 +327,94 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
     }
     // ---- write back g' as the bf16 hi/lo tile image (what the next step's MMA consumes): one bulk copy
     if (copier_warp && elect_one()) bulk_store(g_img + (size_t)tile * (2 * kATile), a_hi, 2 * kATile);
-    // ---- softmax weight of every row relative to its run's maximum; head rows: part row, split point, part maximum
-    if (a.attn) {
-      if (seg_last == 31)        // the run may continue in the following warps
-        for (int k2 = wq + 1; k2 < 4 && (s_wflag[k2] & 1); ++k2) {
-          run_max = fmaxf(run_max, s_wfirst[k2]);
-          if (!(s_wflag[k2] & 2)) break;
+    // ---- runs of equal targets (a bin, or the part of it inside this tile), handled by the half-0 thread of every row:
+    //      maximum logit of every run -- first within the warp (segmented shuffle scan), then across the four warps
+    //      through shared memory -- the softmax weight of every row, and for the last row of a run its part row
+    if (half == 0) {
+      const float att = att_bias + (s_att[row] + s_att1[row]);
+      const bool is_start = e < 0 || row == 0 || s_dst[row - 1] != dst;   // invalid rows are runs of their own
+      const int lane = row & 31, wq = row >> 5;
+      float run_max = att;
+      int seg_first = 0, seg_last = 31;
+      if (a.attn) {
+        const unsigned starts = __ballot_sync(0xffffffffu, is_start);
+        const unsigned upto = 0xffffffffu >> (31 - lane);
+        seg_first = 31 - __clz((starts | 1u) & upto);
+        const unsigned above = starts & ~upto;
+        seg_last = above ? __ffs(above) - 2 : 31;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+          const float o = __shfl_down_sync(0xffffffffu, run_max, dd);
+          if (lane + dd <= seg_last) run_max = fmaxf(run_max, o);
         }
-      if (seg_first == 0 && (s_wflag[wq] & 1))   // ... and may have begun in the preceding ones
-        for (int k2 = wq - 1; k2 >= 0; --k2) {
-          run_max = fmaxf(run_max, s_wlast[k2]);
-          if ((s_wflag[k2] & 3) != 3) break;
-        }
-      s_att[wt] = e >= 0 ? __expf(att - run_max) : 0.f;
-    } else {
-      s_att[wt] = e >= 0 ? 1.f : 0.f;
-    }
-    {   // the last row of a run stores the run's result: its part row (else -1); segment starts of the reduction
+        run_max = __shfl_sync(0xffffffffu, run_max, seg_first);
+        if (lane == 0) { s_wfirst[wq] = run_max; s_wflag[wq] = (is_start ? 0 : 1) | (seg_last == 31 ? 2 : 0); }
+        if (lane == 31) s_wlast[wq] = run_max;
+        named_bar_sync(scan_bar_id, kTile);
+        if (seg_last == 31)        // the run may continue in the following warps
+          for (int k2 = wq + 1; k2 < 4 && (s_wflag[k2] & 1); ++k2) {
+            run_max = fmaxf(run_max, s_wfirst[k2]);
+            if (!(s_wflag[k2] & 2)) break;
+          }
+        if (seg_first == 0 && (s_wflag[wq] & 1))   // ... and may have begun in the preceding ones
+          for (int k2 = wq - 1; k2 >= 0; --k2) {
+            run_max = fmaxf(run_max, s_wlast[k2]);
+            if ((s_wflag[k2] & 3) != 3) break;
+          }
+        s_att[row] = e >= 0 ? __expf(att - run_max) : 0.f;
+      } else {
+        s_att[row] = e >= 0 ? 1.f : 0.f;
+      }
       int ctl = -1;
-      if (e >= 0 && (wt == kTile - 1 || s_dst[wt + 1] != dst)) {
+      if (e >= 0 && (row == kTile - 1 || s_dst[row + 1] != dst)) {
         const int first_slot = s_gstart[t] + bin_ls;
         ctl = s_gpstart[t] + bin_lp + (tile - (first_slot >> 7));
         if (a.attn) a.part_mx[ctl] = run_max;
       }
-      s_prow[wt] = ctl;
-      if (e >= 0 && is_start)      // segment k of the reduction starts at the first run start >= 16 k
-        for (int k = wt >> 4; k >= 1; --k)
-          if (atomicMin(&s_seg[k], wt) < wt) break;
+      s_prow[row] = ctl;
+      if (e >= 0 && is_start)      // segment k of the reduction starts at the first run start >= 8 k
+        for (int k = row >> 3; k >= 1; --k)
+          if (atomicMin(&s_seg[k], row) < row) break;
     }
     mbar_wait(bar, phase);
     phase ^= 1;
     fence_after_sync();
-    tmem_ld64(tmem, 0, d);
-    // ---- message m = ReLU(d + R) goes to this thread's own staging row (its C row was consumed by the first epilogue)
+    tmem_ld32(tmem_row + (uint32_t)c0col, d);
+    // ---- message m = ReLU(d + R) goes to this thread's half of its staging row (the C row was consumed by the first epilogue)
 #pragma unroll
-    for (int q = 0; q < kD / 4; ++q)
-      sts128f(add_a + 4 * stage_index(wt, 4 * q),
+    for (int q = 0; q < 8; ++q)
+      sts128f(add_a + 4 * stage_index(row, c0col + 4 * q),
               make_float4(fmaxf(d[4 * q + 0] + rv[q].x, 0.f), fmaxf(d[4 * q + 1] + rv[q].y, 0.f),
                           fmaxf(d[4 * q + 2] + rv[q].z, 0.f), fmaxf(d[4 * q + 3] + rv[q].w, 0.f)));
     if (a.with_head) {   // head layer 1 epilogue -> A, layer 2 on the tensor cores
-      tmem_ld64(tmem, 64, d);
+      tmem_ld32(tmem_row + 64 + (uint32_t)c0col, d);
 #pragma unroll
-      for (int o = 0; o < kD; ++o) d[o] = fmaxf(d[o] + s_bh1[o], 0.f);
+      for (int o = 0; o < 32; ++o) d[o] = fmaxf(d[o] + s_bh1[c0col + o], 0.f);
       if (copier_warp && elect_one()) bulk_wait_read();           // the write-back has finished reading the operand tiles
-      named_bar_sync(bar_id, kWgThreads);
-      store_split_row_a(a_hi, a_lo, wt, d);
+      named_bar_sync(bar_id, kTgThreads);
+      {
+        const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+        const uint32_t x = (uint32_t)(row & 7);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) split2(d[8 * c + 2 * i], d[8 * c + 2 * i + 1], h[i], l[i]);
+          const uint32_t off = row_off + (((uint32_t)(4 * half + c) ^ x) << 4);
+          sts128(a_hi + off, h[0], h[1], h[2], h[3]);
+          sts128(a_lo + off, l[0], l[1], l[2], l[3]);
+        }
+      }
       fence_before_sync();
       fence_async_smem();
-      named_bar_sync(bar_id, kWgThreads);
-      if (wt < 32 && elect_one()) {
+      named_bar_sync(bar_id, kTgThreads);
+      if (tt < 32 && elect_one()) {
         fence_after_sync();
         issue_gemm_x3<32>(tmem + 64, a_hi, a_lo, 0, wh2_hi, wh2_lo, 0, 1, false);
         mma_commit(bar);
       }
     } else {
-      named_bar_sync(bar_id, kWgThreads);
+      named_bar_sync(bar_id, kTgThreads);
     }
     // the operand tiles are free (no head): fetch the next tile's edge features behind the reduction
     g_issued = false;
@@ -371,13 +426,13 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
       }
       g_issued = true;
     }
-    // ---- reduce every run: thread = (4 columns, one of 8 row segments); the segments meet at run boundaries, so
+    // ---- reduce every run: thread = (4 columns, one of 16 row segments); the segments meet at run boundaries, so
     //      every run is reduced by one thread per column quad, rows in order (deterministic), results stored as
     //      256-byte rows.  Four rows per batch: the shared-memory reads of a batch precede its dependent arithmetic.
     {
-      const int seg = wt >> 4;
-      const uint32_t c4 = (uint32_t)(wt & 15);
-      const int r_begin = s_seg[seg], r_end = seg == 7 ? kTile : s_seg[seg + 1];
+      const int seg = tt >> 4;
+      const uint32_t c4 = (uint32_t)(tt & 15);
+      const int r_begin = s_seg[seg], r_end = seg == 15 ? kTile : s_seg[seg + 1];
       const bool use_max = a.aggr == PGMP_AGGR_MAX && !a.attn;
       const float u0 = use_max ? -INFINITY : 0.f;
       float se = 0.f;
@@ -414,22 +469,21 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) edge_step_tc_kernel(const Edg
         }
       }
     }
-    if (a.with_head) {   // head layer 2 epilogue and the final 32 -> 1 dot product
+    if (a.with_head) {   // head layer 2 epilogue and the final 32 -> 1 dot product (the half-0 thread of every row)
       mbar_wait(bar, phase);
       phase ^= 1;
       fence_after_sync();
-      float hv[32];
-      const uint32_t ta = tmem + 64 + ((uint32_t)((warp & 3) * 32) << 16);
-      tmem_ld16(ta, hv);
-      tmem_ld16(ta + 16, hv + 16);
-      tmem_ld_wait();
-      float logit = __ldg(a.bh3);
+      if (half == 0) {
+        float hv[32];
+        tmem_ld32(tmem_row + 64, hv);
+        float logit = __ldg(a.bh3);
 #pragma unroll
-      for (int o = 0; o < 32; ++o) logit = fmaf(fmaxf(hv[o] + s_bh2[o], 0.f), s_wh3[o], logit);
-      if (e >= 0) a.edge_logits[e] = logit;
+        for (int o = 0; o < 32; ++o) logit = fmaf(fmaxf(hv[o] + s_bh2[o], 0.f), s_wh3[o], logit);
+        if (e >= 0) a.edge_logits[e] = logit;
+      }
     }
     fence_before_sync();
-    named_bar_sync(bar_id, kWgThreads);   // the next tile overwrites the staging / operand tiles
+    named_bar_sync(bar_id, kTgThreads);   // the next tile overwrites the staging / operand tiles
   }
   if (copier_warp && elect_one()) bulk_wait_all();
   fence_before_sync();
@@ -618,7 +672,7 @@ int mpn_forward_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t
     if (E > 0 && p.skip) PGMP_LAUNCH(c_to_image_kernel, (unsigned)(w.max_slots / kTile), kWgThreads, 0, st, w.c0, w.group_start, p.num_types);
   }
   if (!nemb_tc && (rc = mpn_node_image(w, w.h0, N, w.h0_img, st)) != PGMP_OK) return rc;
-  PGMP_CUDA(cudaFuncSetAttribute(edge_step_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdgeSmemBytes));
+  PGMP_CUDA(cudaFuncSetAttribute(edge_step_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdge2SmemBytes));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -652,7 +706,7 @@ int mpn_forward_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t
       const bool out = s >= first_out;
       a.with_head = out && fused_head;
       a.edge_logits = out ? p.edge_logits + (size_t)(s - first_out) * E : nullptr;
-      PGMP_LAUNCH(edge_step_tc_kernel, grid, kEdgeThreads, kEdgeSmemBytes, st, a);
+      PGMP_LAUNCH(edge_step_tc_kernel, grid, kEdge2Threads, kEdge2SmemBytes, st, a);
       if (out && !fused_head && (rc = mpn_edge_head(p, w, s - first_out, true, st)) != PGMP_OK) return rc;
     }
   }

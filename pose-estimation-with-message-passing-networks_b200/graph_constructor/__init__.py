@@ -93,7 +93,10 @@ class NaiveGraphConstructor:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("pgmp_b200 graph constructor needs a CUDA device (no CPU fallback)")
-        self.scoremaps = scoremaps.to(self.device)
+        # pinned host heatmaps are copied by the detection launch itself (on its stream, non-blocking): with
+        # detect_async() the copy of the next batch overlaps the current batch's kernels
+        self.scoremaps = scoremaps if _host_resident(scoremaps, need_contiguous=True) else scoremaps.to(self.device)
+        self._pending = None
         # The reference moves every input to the device (ConstructGraph.py:12-18).  Only N pixels of the feature and
         # tag maps are ever read (N x C x 4 bytes of a 134 MB map per image), so pinned host tensors are left where
         # they are and the gather kernels read those pixels in place over PCIe (unified addressing); like a
@@ -166,39 +169,76 @@ class NaiveGraphConstructor:
             self.max_nodes = min(16384, 2 * self.max_nodes)
         return bool(ok)
 
+    def _launch_detect(self, stream=None):
+        """Detection half (NMS -> candidates -> node layout -> kNN adjacency -> counts) on ``stream`` (default: the
+        current one); the counts that size the outputs go to pinned host memory behind an event."""
+        lib = nv.lib()
+        dev = self.device
+        sm_in = self.scoremaps
+        if sm_in.dim() != 4 or sm_in.shape[1] != self.num_joints:
+            raise ValueError("scoremaps must be [B, num_joints, H, W], got %s" % (tuple(sm_in.shape),))
+        B, J, H, W = sm_in.shape
+        with torch.cuda.device(dev), torch.cuda.stream(stream if stream is not None else torch.cuda.current_stream(dev)):
+            if sm_in.device.type == "cpu":
+                sm = torch.empty(sm_in.shape, dtype=torch.float32, device=dev)
+                sm.copy_(sm_in, non_blocking=True)
+            else:
+                sm = nv.require_cuda(sm_in, "scoremaps").detach().float().contiguous()
+                if stream is not None:
+                    sm.record_stream(stream)        # allocated on the caller's stream, read on this one
+            mask = self.masks.detach().float().contiguous() if self.mask_crowds else None
+            p = nv.GcParams(
+                batch=B, num_joints=J, height=H, width=W, pool_kernel=self.pool_kernel_size, top_k=self._top_k,
+                use_threshold=int(self.detect_threshold is not None),
+                threshold=float(self.detect_threshold if self.detect_threshold is not None else 0.0),
+                graph_type=nv.GRAPH_FULLY if self.mpn_graph_type == "fully" else nv.GRAPH_KNN, knn_k=KNN_K,
+                edge_features=self._edge_feat_bits,
+                norm_factor=float(max(W, H) if self.normalize_node_distance else 1),     # CG.py:311-314
+                cand_capacity=self.cand_capacity, max_det_per_type=self.max_det_per_type, max_nodes=self.max_nodes,
+                scoremaps=sm.data_ptr(), mask=mask.data_ptr() if mask is not None else None)
+            ws_bytes = int(lib.pgmp_gc_workspace_bytes(p))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            p.workspace, p.workspace_bytes = ws.data_ptr(), ws_bytes
+            counts = torch.empty(2 + 2 * B + 1, dtype=torch.int64, device=dev)
+            nv.check(lib.pgmp_gc_detect(p, counts.data_ptr(), nv.current_stream()))
+            counts_h = torch.empty(counts.shape, dtype=torch.int64, pin_memory=True)
+            counts_h.copy_(counts, non_blocking=True)
+            event = torch.cuda.Event()
+            event.record()
+            used = torch.cuda.current_stream(dev)
+        return dict(p=p, ws=ws, sm=sm, mask=mask, counts=counts, counts_h=counts_h, event=event, stream=used)
+
+    def detect_async(self, stream=None):
+        """Optional: start the detection half now, on ``stream`` (a side stream lets it -- and the host-to-device copy of
+        pinned heatmaps -- overlap the previous batch's kernels).  ``construct_graph()`` then only waits for the counts,
+        which have usually arrived long before, instead of draining the stream.  See ``pgmp_b200.pipeline``."""
+        if self._pending is None:
+            self._pending = self._launch_detect(stream)
+        return self
+
     def construct_graph(self):
         lib = nv.lib()
-        sm = nv.require_cuda(self.scoremaps, "scoremaps")
-        if sm.dim() != 4 or sm.shape[1] != self.num_joints:
-            raise ValueError("scoremaps must be [B, num_joints, H, W], got %s" % (tuple(sm.shape),))
-        sm = sm.detach().float().contiguous()
+        dev = self.device
+        for attempt in range(6):
+            d = self._pending or self._launch_detect(None)
+            self._pending = None
+            d["event"].synchronize()               # the one host wait of the graph constructor: the counts
+            counts_h = d["counts_h"]
+            flags = int(counts_h[-1])
+            if not flags or not self._grow(flags):
+                break
+        if flags:
+            raise RuntimeError("graph constructor capacity exceeded: " +
+                               "; ".join(msg for bit, msg in nv.GC_FLAGS.items() if flags & bit))
+        p, ws, sm = d["p"], d["ws"], d["sm"]
         B, J, H, W = sm.shape
-        mask = self.masks.detach().float().contiguous() if self.mask_crowds else None
-        dev = sm.device
         with torch.cuda.device(dev):
             stream = nv.current_stream()
-            for attempt in range(6):
-                p = nv.GcParams(
-                    batch=B, num_joints=J, height=H, width=W, pool_kernel=self.pool_kernel_size, top_k=self._top_k,
-                    use_threshold=int(self.detect_threshold is not None),
-                    threshold=float(self.detect_threshold if self.detect_threshold is not None else 0.0),
-                    graph_type=nv.GRAPH_FULLY if self.mpn_graph_type == "fully" else nv.GRAPH_KNN, knn_k=KNN_K,
-                    edge_features=self._edge_feat_bits,
-                    norm_factor=float(max(W, H) if self.normalize_node_distance else 1),     # CG.py:311-314
-                    cand_capacity=self.cand_capacity, max_det_per_type=self.max_det_per_type, max_nodes=self.max_nodes,
-                    scoremaps=sm.data_ptr(), mask=mask.data_ptr() if mask is not None else None)
-                ws_bytes = int(lib.pgmp_gc_workspace_bytes(p))
-                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-                p.workspace, p.workspace_bytes = ws.data_ptr(), ws_bytes
-                counts = torch.empty(2 + 2 * B + 1, dtype=torch.int64, device=dev)
-                nv.check(lib.pgmp_gc_detect(p, counts.data_ptr(), stream))
-                counts_h = counts.cpu()            # the one host read of the graph constructor
-                flags = int(counts_h[-1])
-                if not flags or not self._grow(flags):
-                    break
-            if flags:
-                raise RuntimeError("graph constructor capacity exceeded: " +
-                                   "; ".join(msg for bit, msg in nv.GC_FLAGS.items() if flags & bit))
+            cur = torch.cuda.current_stream(dev)
+            if d["stream"] != cur:                 # the emit kernels read the detection's workspace on this stream
+                cur.wait_event(d["event"])
+                for t_ in (ws, sm, d["counts"]) + ((d["mask"],) if d["mask"] is not None else ()):
+                    t_.record_stream(cur)
             N, E = int(counts_h[0]), int(counts_h[1])
             self.num_nodes_per_image = counts_h[2:2 + B].clone()
             self.num_edges_per_image = counts_h[2 + B:2 + 2 * B].clone()

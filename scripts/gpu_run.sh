@@ -1,3 +1,8 @@
 set -x
-timeout 600 python -m pytest tests -m gpu -x -q -k "nms or graph_constructor or no_threshold or capacities or full_size or pipeline" > gpurun_out/r2_pytest11.txt 2>&1; tail -3 gpurun_out/r2_pytest11.txt
-timeout 300 python scripts/bench_nms.py > gpurun_out/r2_nms_sweep13.txt 2>&1; tail -1 gpurun_out/r2_nms_sweep13.txt | cut -c1-900
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest17.txt 2>&1; tail -3 gpurun_out/r2_pytest17.txt
+python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench3.json 2> gpurun_out/r2_bench3.err; tail -c 400 gpurun_out/r2_bench3.err; python - <<'P'
+import json
+d=json.loads(open('gpurun_out/r2_bench3.json').read().strip().splitlines()[-1])
+for k in ('value','ms_per_step','serial_calls','e2e','roofline','roofline_nms','kernels','gpu_launches'):
+    print(k, json.dumps(d.get(k))[:900])
+P

@@ -284,6 +284,38 @@ def test_end_to_end_graph_constructor_into_mpn():
 # ------------------------------------------------------------------------------------------------
 # tensor-core mode (tcgen05 / TMEM, bf16x3 split with fp32 accumulation)
 # ------------------------------------------------------------------------------------------------
+def test_pipelined_api_equals_serial_calls():
+    """``GroupingPipeline`` (detection half of the next batch on a side stream, pinned host heatmaps copied there) returns
+    exactly what back-to-back ``construct_graph()`` + ``forward()`` calls return, batch after batch."""
+    from pgmp_b200.pipeline import GroupingPipeline
+    J, K = 17, 10
+    gcfg = pgmp_b200.config.bench_gc_config(k=K, graph_type="knn")
+    mcfg = pgmp_b200.config.flagship_mpn_config(J, STEPS=3, B200_PRECISION="tc")
+    model = synthetic.synth_mpn_state_dict(get_mpn_model(mcfg), 4).eval().to(DEV)
+    datas = [synthetic.synth_batch(2, J, 128, K, persons=3, first_index=2 * i) for i in range(4)]
+    serial = []
+    for d in datas:
+        t = {k: torch.from_numpy(v).to(DEV) for k, v in d.items()}
+        ret = get_graph_constructor(gcfg, scoremaps=t["scoremaps"], tagmaps=t["tagmaps"], features=t["features"], joints_gt=None,
+                                    factor_list=None, masks=None, device=DEV, testing=True, heatmaps=None, num_joints=J).construct_graph()
+        with torch.no_grad():
+            pe, pn, pc, _ = model(ret[0], ret[1], ret[2], node_types=ret[7][:, 2])
+        serial.append((ret, pe[-1], pn[-1], pc[-1]))
+    pipe = GroupingPipeline(gcfg, model, J, DEV)
+    for host in (False, True):
+        if host:      # pinned host inputs: heatmaps copied on the side stream, feature / tag maps gathered in place
+            batches = [{k: torch.from_numpy(d[k]).pin_memory() for k in ("scoremaps", "tagmaps", "features")} for d in datas]
+        else:
+            batches = [{k: torch.from_numpy(d[k]).to(DEV) for k in ("scoremaps", "tagmaps", "features")} for d in datas]
+        outs = list(pipe.run(batches))
+        torch.cuda.synchronize()
+        assert len(outs) == len(serial)
+        for (ret, (pe, pn, pc)), (sret, spe, spn, spc) in zip(outs, serial):
+            for i in (0, 1, 2, 7, 11, 12, 14):
+                assert torch.equal(ret[i], sret[i]), i
+            assert torch.equal(pe[-1], spe) and torch.equal(pn[-1], spn) and torch.equal(pc[-1], spc)
+
+
 def test_umma_selftest_gemm():
     """The tcgen05 building blocks in isolation: D = A . W^T for one 128x64x64 tile."""
     import pgmp_b200._native as nv
