@@ -377,18 +377,39 @@ def run_b200(args, rank, local_rank, world):
     # bytes that cross PCIe towards the device per step: the heatmap copy + the gathered feature / tag elements
     h2d = sm_h.numel() * 4 + n_nodes * feat_h.shape[1] * 4 + n_nodes * 4
 
-    # ---- the grouping tail (sigmoid / threshold / GAEC / persons) on the last logits, reported separately
-    ret, pe, pn, pc = step(sm, tags, feat)
-    group_persons(ret[7], pn[-1], ret[2], pe[-1], pc[-1], ret[12], J, node_threshold=0.1, detector_scores=ret[11])
+    # ---- the grouping tail (sigmoid / threshold / GAEC / persons): alone on the last logits, and inside the pipelined API
+    #      (batch i's grouping on a third stream while batch i + 1 goes through the network), resident and end to end
+    gcx = get_graph_constructor(gcfg, scoremaps=sm, tagmaps=tags, features=feat, joints_gt=None, factor_list=None, masks=None,
+                                device=dev, testing=True, heatmaps=None, num_joints=J)
+    ret = gcx.construct_graph()
+    with torch.no_grad():
+        pe, pn, pc, _ = model(ret[0], ret[1], ret[2], node_types=ret[7][:, 2])
+    gkw = dict(node_threshold=0.1, detector_scores=ret[11], nodes_per_image=gcx.num_nodes_per_image,
+               edges_per_image=gcx.num_edges_per_image)
+    group_persons(ret[7], pn[-1], ret[2], pe[-1], pc[-1], ret[12], J, **gkw)
     barrier()
     ev0.record()
     for _ in range(args.steps):
-        groups = group_persons(ret[7], pn[-1], ret[2], pe[-1], pc[-1], ret[12], J, node_threshold=0.1,
-                               detector_scores=ret[11])
+        groups = group_persons(ret[7], pn[-1], ret[2], pe[-1], pc[-1], ret[12], J, **gkw)
     ev1.record()
     barrier()
     t_group = reduce_max(ev0.elapsed_time(ev1) / 1e3)
     persons_per_image = sum(0 if g_ is None else len(g_[0]) for g_ in groups) / max(len(groups), 1)
+    pipe_g = GroupingPipeline(gcfg, model, J, dev, group=dict(node_threshold=0.1))
+
+    def run_grouped(batch, steps, after=None):
+        for out in pipe_g.run(batch for _ in range(steps)):
+            if after is not None:
+                after(out)
+
+    run_grouped(resident, 2)
+    barrier()
+    ev0.record()
+    run_grouped(resident, args.steps)
+    ev1.record()
+    barrier()
+    t_dev_g = reduce_max(ev0.elapsed_time(ev1) / 1e3)
+    t_e2e_g = time_e2e(lambda k: run_grouped(host, k, after=read_back))
 
     total_images = B * world * args.steps
     total_edges = reduce_sum(edges_per_step) * args.steps
@@ -489,8 +510,14 @@ def run_b200(args, rank, local_rank, world):
             "gpu_launches": int(launches), "roofline": roofline, "roofline_nms": roofline_nms, "cpu_baseline": cpu,
             "kernels": kernels,
             "grouping_tail": {"ms_per_step": 1e3 * t_group / args.steps, "persons_per_image": persons_per_image,
-                              "note": "sigmoid/threshold/GAEC/persons on the step's logits, timed separately "
-                                      "(not part of value: the metric is GC + MPN, SURVEY.md 8d)"},
+                              "note": "sigmoid / threshold / GAEC / persons on the step's logits, alone (not part of value: "
+                                      "the metric is GC + MPN, SURVEY.md 8d)",
+                              "with_grouping": {"value": B * world * args.steps / t_dev_g, "ms_per_step": 1e3 * t_dev_g / args.steps,
+                                                "e2e_value": B * world * args.steps / t_e2e_g,
+                                                "e2e_ms_per_step": 1e3 * t_e2e_g / args.steps,
+                                                "note": "GC + MPN + grouping per batch through GroupingPipeline(group=...): "
+                                                        "the grouping of batch i overlaps the network of batch i + 1; persons "
+                                                        "copied to the host every step"}},
             "graph": {"nodes_per_step_per_gpu": nodes_per_step, "edges_per_step_per_gpu": edges_per_step}}
     line["train_step"] = train
     print(json.dumps(line), flush=True)

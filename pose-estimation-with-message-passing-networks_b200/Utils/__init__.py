@@ -14,16 +14,41 @@ import torch
 from .. import _native as nv
 
 
-def group_persons(joint_det, node_logits, edge_index, edge_logits, class_logits, batch_index, num_joints,
-                  node_threshold=0.1, cc_method="GAEC", max_persons=None, detector_scores=None):
-    """Returns one entry per image of the batch: ``None`` where the reference's ``pred_to_ann`` returns
-    ``None`` before grouping (no detector score > 0.1, Utils.py:1448-1449; no edge between kept nodes,
-    :1452,1457) else ``(persons [P, J, 3] float64 ndarray, mutants bool, person_labels [N_b] int64 tensor)``
-    as ``pred_to_person`` does.
+class PendingGroups:
+    """Handle of a grouping launch (``group_persons_async``): ``result()`` waits for the device and splits the packed
+    outputs per image."""
 
-    ``node_logits`` / ``edge_logits`` / ``class_logits`` are the MPN's last predictions (logits: the sigmoid /
-    softmax of valid.py:109-111 are applied on the device); ``edge_index`` holds global node ids with the edges of
-    an image contiguous, as ``construct_graph`` returns them.
+    def __init__(self, B, max_persons, labels, node_off_h, small_h, persons_h, event):
+        self.B, self.max_persons, self.labels, self.node_off_h = B, max_persons, labels, node_off_h
+        self.small_h, self.persons_h, self.event = small_h, persons_h, event
+
+    def result(self):
+        self.event.synchronize()
+        small = self.small_h.numpy()                 # [5, B]: components, kept edges, persons, mutants, detector ok
+        persons = self.persons_h.numpy()
+        out = []
+        for b in range(self.B):
+            nk, npers, mut, ok = int(small[1, b]), int(small[2, b]), int(small[3, b]), int(small[4, b])
+            if npers > self.max_persons:
+                raise RuntimeError("more than max_persons=%d persons in image %d" % (self.max_persons, b))
+            if nk <= 0 or ok < 1:
+                out.append(None)
+                continue
+            out.append((persons[b, :npers].copy() if npers else np.array([]), bool(mut),
+                        self.labels[self.node_off_h[b]:self.node_off_h[b + 1]]))
+        return out
+
+
+def group_persons_async(joint_det, node_logits, edge_index, edge_logits, class_logits, batch_index, num_joints,
+                        node_threshold=0.1, cc_method="GAEC", max_persons=None, detector_scores=None,
+                        nodes_per_image=None, edges_per_image=None, stream=None):
+    """``group_persons`` without the wait: launches on ``stream`` (default: the current one), copies the packed results to
+    pinned host memory behind an event and returns a ``PendingGroups``.
+
+    ``nodes_per_image`` / ``edges_per_image``: the per-image counts the graph constructor already holds on the host
+    (``gc.num_nodes_per_image`` / ``gc.num_edges_per_image``).  They fix the batch size -- trailing images without
+    candidates stay in the result as ``None`` -- and spare the device-side counting and its host reads; without them the
+    batch size is ``batch_index[-1] + 1`` and the counts are read back once.
     """
     if cc_method not in nv.CC_METHODS:
         raise NotImplementedError("CC_METHOD=%r (GAEC, the reference default, and threshold are in scope)" % (cc_method,))
@@ -34,60 +59,85 @@ def group_persons(joint_det, node_logits, edge_index, edge_logits, class_logits,
     nv.require_cuda(batch_index, "batch_index", torch.int64)
     dev = joint_det.device
     N, E = joint_det.shape[0], edge_index.shape[1]
-    if N == 0:
-        return []
     lib = nv.lib()
-    B = int(batch_index[-1].item()) + 1
-    nodes_per = torch.bincount(batch_index, minlength=B)
-    edges_per = torch.bincount(batch_index[edge_index[0]], minlength=B) if E else torch.zeros(B, dtype=torch.int64, device=dev)
-    zero = torch.zeros(1, dtype=torch.int64, device=dev)
-    node_off = torch.cat([zero, nodes_per.cumsum(0)])
-    edge_off = torch.cat([zero, edges_per.cumsum(0)])
-    max_nodes = int(nodes_per.max().item())
+    if nodes_per_image is not None:
+        nodes_h = torch.as_tensor(nodes_per_image, dtype=torch.int64).cpu()
+        B = int(nodes_h.numel())
+        if edges_per_image is not None:
+            edges_h = torch.as_tensor(edges_per_image, dtype=torch.int64).cpu()
+        else:
+            edges_h = (torch.bincount(batch_index[edge_index[0]], minlength=B) if E else torch.zeros(B, dtype=torch.int64)).cpu()
+    else:
+        if N == 0:
+            return PendingGroups(0, 0, None, [0], torch.zeros((5, 0), dtype=torch.int32), torch.zeros(0), torch.cuda.Event())
+        B = int(batch_index[-1].item()) + 1
+        nodes_h = torch.bincount(batch_index, minlength=B).cpu()
+        edges_h = (torch.bincount(batch_index[edge_index[0]], minlength=B) if E else torch.zeros(B, dtype=torch.int64)).cpu()
+    if int(nodes_h.sum()) != N or int(edges_h.sum()) != E:
+        raise ValueError("nodes_per_image / edges_per_image do not add up to the graph's size")
+    off_h = torch.zeros((2, B + 1), dtype=torch.int64, pin_memory=True)
+    off_h[0, 1:] = nodes_h.cumsum(0)
+    off_h[1, 1:] = edges_h.cumsum(0)
+    max_nodes = max(int(nodes_h.max()) if B else 0, 1)
     J = int(num_joints)
     max_persons = int(max_persons or max(1, max_nodes // 2))
-    labels = torch.empty(N, dtype=torch.int64, device=dev)
-    ncomp = torch.empty(B, dtype=torch.int32, device=dev)
-    nkept = torch.empty(B, dtype=torch.int32, device=dev)
-    npers = torch.empty(B, dtype=torch.int32, device=dev)
-    mutants = torch.empty(B, dtype=torch.int32, device=dev)
-    persons = torch.zeros((B, max_persons, J, 3), dtype=torch.float64, device=dev)
-    jd = joint_det.contiguous()
-    nl = node_logits.detach().reshape(-1).contiguous()
-    el = edge_logits.detach().reshape(-1).contiguous()
-    ei = edge_index.contiguous()
-    cl = class_logits.detach().contiguous() if class_logits is not None else None
-    p = nv.GroupParams(batch=B, num_joints=J, num_nodes=N, num_edges=E, node_threshold=float(node_threshold),
-                       cc_method=nv.CC_METHODS[cc_method], edge_threshold=0.8,
-                       node_offsets=node_off.data_ptr(), edge_offsets=edge_off.data_ptr(), edge_index=ei.data_ptr(),
-                       joint_det=jd.data_ptr(), node_logits=nl.data_ptr(), edge_logits=el.data_ptr(),
-                       class_logits=cl.data_ptr() if cl is not None else None, person_labels=labels.data_ptr(),
-                       num_components=ncomp.data_ptr(), num_kept_edges=nkept.data_ptr(), max_persons=max_persons,
-                       max_nodes_per_image=max_nodes, persons=persons.data_ptr(), num_persons=npers.data_ptr(),
-                       mutants=mutants.data_ptr())
-    with torch.cuda.device(dev):
-        ws_bytes = int(lib.pgmp_group_workspace_bytes(p))
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        p.workspace, p.workspace_bytes = ws.data_ptr(), ws_bytes
-        nv.check(lib.pgmp_group_persons(p, nv.current_stream()))
-        ws.record_stream(torch.cuda.current_stream())
-    nkept_h, npers_h, mut_h = nkept.cpu().tolist(), npers.cpu().tolist(), mutants.cpu().tolist()
-    node_off_h = node_off.cpu().tolist()
-    persons_h = persons.cpu().numpy()
-    det_ok = None
-    if detector_scores is not None:                                # Utils.py:1448-1449
-        det_ok = torch.zeros(B, dtype=torch.int64, device=dev).index_add_(
-            0, batch_index, (detector_scores > 0.1).long()).cpu().tolist()
-    out = []
-    for b in range(B):
-        if npers_h[b] > max_persons:
-            raise RuntimeError("more than max_persons=%d persons in image %d" % (max_persons, b))
-        if nkept_h[b] <= 0 or (det_ok is not None and det_ok[b] < 1):
-            out.append(None)
-            continue
-        out.append((persons_h[b, :npers_h[b]].copy() if npers_h[b] else np.array([]), bool(mut_h[b]),
-                    labels[node_off_h[b]:node_off_h[b + 1]]))
-    return out
+    with torch.cuda.device(dev), torch.cuda.stream(stream if stream is not None else torch.cuda.current_stream(dev)):
+        off = off_h.to(dev, non_blocking=True)
+        labels = torch.empty(N, dtype=torch.int64, device=dev)
+        small = torch.zeros((5, B), dtype=torch.int32, device=dev)
+        persons = torch.zeros((B, max_persons, J, 3), dtype=torch.float64, device=dev)
+        jd = joint_det.contiguous()
+        nl = node_logits.detach().reshape(-1).contiguous()
+        el = edge_logits.detach().reshape(-1).contiguous()
+        ei = edge_index.contiguous()
+        cl = class_logits.detach().contiguous() if class_logits is not None else None
+        if detector_scores is not None:                            # Utils.py:1448-1449
+            small[4] = torch.zeros(B, dtype=torch.int64, device=dev).index_add_(
+                0, batch_index, (detector_scores > 0.1).long()).clamp_(max=1).int()
+        else:
+            small[4] = 1
+        if N > 0:
+            p = nv.GroupParams(batch=B, num_joints=J, num_nodes=N, num_edges=E, node_threshold=float(node_threshold),
+                               cc_method=nv.CC_METHODS[cc_method], edge_threshold=0.8,
+                               node_offsets=off[0].data_ptr(), edge_offsets=off[1].data_ptr(), edge_index=ei.data_ptr(),
+                               joint_det=jd.data_ptr(), node_logits=nl.data_ptr(), edge_logits=el.data_ptr(),
+                               class_logits=cl.data_ptr() if cl is not None else None, person_labels=labels.data_ptr(),
+                               num_components=small[0].data_ptr(), num_kept_edges=small[1].data_ptr(), max_persons=max_persons,
+                               max_nodes_per_image=max_nodes, persons=persons.data_ptr(), num_persons=small[2].data_ptr(),
+                               mutants=small[3].data_ptr())
+            ws_bytes = int(lib.pgmp_group_workspace_bytes(p))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            p.workspace, p.workspace_bytes = ws.data_ptr(), ws_bytes
+            nv.check(lib.pgmp_group_persons(p, nv.current_stream()))
+        small_h = torch.empty(small.shape, dtype=torch.int32, pin_memory=True)
+        persons_h = torch.empty(persons.shape, dtype=torch.float64, pin_memory=True)
+        small_h.copy_(small, non_blocking=True)
+        persons_h.copy_(persons, non_blocking=True)
+        event = torch.cuda.Event()
+        event.record()
+        if stream is not None:                                     # inputs produced on the caller's stream, read on this one
+            for t_ in (jd, nl, el, ei, batch_index) + ((cl,) if cl is not None else ()):
+                t_.record_stream(stream)
+    return PendingGroups(B, max_persons, labels, off_h[0].tolist(), small_h, persons_h, event)
+
+
+def group_persons(joint_det, node_logits, edge_index, edge_logits, class_logits, batch_index, num_joints,
+                  node_threshold=0.1, cc_method="GAEC", max_persons=None, detector_scores=None,
+                  nodes_per_image=None, edges_per_image=None):
+    """Returns one entry per image of the batch: ``None`` where the reference's ``pred_to_ann`` returns
+    ``None`` before grouping (no detector score > 0.1, Utils.py:1448-1449; no edge between kept nodes,
+    :1452,1457) else ``(persons [P, J, 3] float64 ndarray, mutants bool, person_labels [N_b] int64 tensor)``
+    as ``pred_to_person`` does.
+
+    ``node_logits`` / ``edge_logits`` / ``class_logits`` are the MPN's last predictions (logits: the sigmoid /
+    softmax of valid.py:109-111 are applied on the device); ``edge_index`` holds global node ids with the edges of
+    an image contiguous, as ``construct_graph`` returns them.  Pass ``nodes_per_image`` / ``edges_per_image`` (the graph
+    constructor's host-side counts) to keep trailing empty images in the result; one packed device-to-host copy.
+    """
+    return group_persons_async(joint_det, node_logits, edge_index, edge_logits, class_logits, batch_index, num_joints,
+                               node_threshold=node_threshold, cc_method=cc_method, max_persons=max_persons,
+                               detector_scores=detector_scores, nodes_per_image=nodes_per_image,
+                               edges_per_image=edges_per_image).result()
 
 
 def refine_persons(scoremaps, tags, persons, with_refine=True, adjustment=True):

@@ -19,7 +19,7 @@
 namespace pgmp {
 namespace {
 
-constexpr int kThreads = 1024;
+constexpr int kThreads = 512;    // an image has a few hundred nodes: more threads only make the ~5 barriers per contraction dearer
 constexpr uint32_t kFull = 0xffffffffu;
 
 struct GroupWs {
@@ -33,6 +33,9 @@ struct GroupWs {
   float* p_node;     // [B][M]
   int* type;         // [B][M] re-assigned joint type (argmax of the class head)
   int* comp;         // [B][M] component id per node
+  int* dirty;        // [B][M] rows to rescan after a contraction (used when the bookkeeping does not fit shared memory)
+  int* csize;        // [B][M] nodes per component root
+  unsigned long long* pkey;   // [B][M*J] per (component root, type): best (score bits << 32 | ~node) of its nodes
   uint64_t bytes;
 };
 
@@ -50,6 +53,9 @@ GroupWs carve(const pgmp_group_params& p, int M) {
   w.p_node = c.take<float>(B * M);
   w.type = c.take<int>(B * M);
   w.comp = c.take<int>(B * M);
+  w.dirty = c.take<int>(B * M);
+  w.csize = c.take<int>(B * M);
+  w.pkey = c.take<unsigned long long>(B * M * (uint64_t)p.num_joints);
   w.bytes = c.bytes();
   return w;
 }
@@ -65,16 +71,17 @@ __device__ void rescan_row(const double* __restrict__ W, const int* __restrict__
   const int lane = threadIdx.x & 31;
   double bv = -CUDART_INF;
   int bc = 0x7fffffff;
-  // four independent loads per lane in flight: the row sits in L2, a dependent loop would pay its latency per element
-  for (int c0 = r + 1 + lane; c0 < n; c0 += 128) {
-    double v[4];
+  // sixteen independent loads per lane in flight (a whole row of up to 512 entries in ONE L2 round trip): the rescan of
+  // the merged row sits on the critical path of every contraction (measured: the other warps wait for it at the barrier)
+  for (int c0 = r + 1 + lane; c0 < n; c0 += 512) {
+    double v[16];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 16; ++k) {
       const int c = c0 + 32 * k;
       v[k] = (c < n && (flags[c] & 1)) ? W[(size_t)r * n + c] : -CUDART_INF;
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < 16; ++k)
       if (v[k] != -CUDART_INF && better(v[k], c0 + 32 * k, bv, bc)) { bv = v[k]; bc = c0 + 32 * k; }
   }
 #pragma unroll
@@ -98,13 +105,15 @@ __global__ void __launch_bounds__(kThreads) group_kernel(const pgmp_group_params
   float* __restrict__ A = ws.adj32 + (size_t)b * M * M;
   double* __restrict__ W = ws.w + (size_t)b * M * M;
   int* __restrict__ mult = ws.mult + (size_t)b * M * M;
-  // the per-node bookkeeping of the greedy contraction lives in shared memory when it fits (20 bytes per node): every
+  // the per-node bookkeeping of the greedy contraction lives in shared memory when it fits (24 bytes per node): every
   // contraction step reads it in three dependent phases, an L2 round trip each when it sits in the workspace
   extern __shared__ __align__(16) unsigned char s_dyn[];
   double* __restrict__ best_val = use_smem ? reinterpret_cast<double*>(s_dyn) : ws.best_val + (size_t)b * M;
   int* __restrict__ best_col = use_smem ? reinterpret_cast<int*>(s_dyn + (size_t)8 * M) : ws.best_col + (size_t)b * M;
   int* __restrict__ rep = use_smem ? best_col + M : ws.rep + (size_t)b * M;
   int* __restrict__ flags = use_smem ? best_col + 2 * M : ws.flags + (size_t)b * M;
+  int* __restrict__ dirty = use_smem ? best_col + 3 * M : ws.dirty + (size_t)b * M;   // rows to rescan after a contraction
+  __shared__ int s_ndirty;
   float* __restrict__ pn = ws.p_node + (size_t)b * M;
   int* __restrict__ typ = ws.type + (size_t)b * M;
   int* __restrict__ comp = ws.comp + (size_t)b * M;
@@ -205,8 +214,8 @@ __global__ void __launch_bounds__(kThreads) group_kernel(const pgmp_group_params
     if (lane == 0) { s_val[warp] = bv; s_row[warp] = br; }
     __syncthreads();
     if (warp == 0) {
-      bv = s_val[lane];
-      br = s_row[lane];
+      bv = lane < kThreads / 32 ? s_val[lane] : -CUDART_INF;
+      br = lane < kThreads / 32 ? s_row[lane] : 0x7fffffff;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         const double ov = __shfl_xor_sync(kFull, bv, o);
@@ -218,31 +227,35 @@ __global__ void __launch_bounds__(kThreads) group_kernel(const pgmp_group_params
     __syncthreads();
     if (!(s_best >= 0.0)) break;                                    // "there must be negative weights", :213,222
     const int u = s_u, v = s_v;                                     // u < v: v is contracted into u
+    if (tid == 0) { flags[v] = 0; flags[u] |= 2; dirty[0] = u; s_ndirty = 1; }   // (the loop below skips q == u, q == v)
+    __syncthreads();
     for (int q = tid; q < n; q += kThreads) {
       if (rep[q] == v) rep[q] = u;
       if (q == u || q == v || !(flags[q] & 1)) continue;
       const double wv = W[(size_t)v * n + q];
       // entries (q, v) disappear: rows q < v whose best was column v must rescan
-      if (q < v && best_col[q] == v) flags[q] |= 2;
-      if (wv == -CUDART_INF) continue;
-      const double wu = W[(size_t)u * n + q];
-      const double nw = (wu == -CUDART_INF) ? wv : wu + wv;
-      W[(size_t)u * n + q] = nw;
-      W[(size_t)q * n + u] = nw;
-      if (q < u) {                                                  // entry (q, u) lives in row q
-        if (better(nw, u, best_val[q], best_col[q])) { best_val[q] = nw; best_col[q] = u; flags[q] &= ~2; }
-        else if (best_col[q] == u) flags[q] |= 2;
+      bool dq = (flags[q] & 2) != 0;
+      if (q < v && best_col[q] == v) dq = true;
+      if (wv != -CUDART_INF) {
+        const double wu = W[(size_t)u * n + q];
+        const double nw = (wu == -CUDART_INF) ? wv : wu + wv;
+        W[(size_t)u * n + q] = nw;
+        W[(size_t)q * n + u] = nw;
+        if (q < u) {                                                // entry (q, u) lives in row q
+          if (better(nw, u, best_val[q], best_col[q])) { best_val[q] = nw; best_col[q] = u; dq = false; }
+          else if (best_col[q] == u) dq = true;
+        }
       }
+      // only row q's own thread decides whether row q is dirty: the rows to rescan go to a list, so that the warps
+      // below do not each walk all n flags (measured: that walk and its barrier were 30 % of the kernel)
+      if (dq) { flags[q] |= 2; dirty[atomicAdd(&s_ndirty, 1)] = q; }
     }
     __syncthreads();
-    if (tid == 0) { flags[v] = 0; flags[u] |= 2; }
-    __syncthreads();
-    for (int r = warp; r < n; r += kThreads / 32) {
-      if ((flags[r] & 3) == 3) {
-        rescan_row(W, flags, n, r, best_val, best_col);
-        if (lane == 0) flags[r] &= ~2;
-      }
-      __syncwarp();
+    const int nd = s_ndirty;
+    for (int i = warp; i < nd; i += kThreads / 32) {
+      const int r = dirty[i];
+      rescan_row(W, flags, n, r, best_val, best_col);
+      if (lane == 0) flags[r] &= ~2;
     }
     __syncthreads();
   }
@@ -258,38 +271,52 @@ __global__ void __launch_bounds__(kThreads) group_kernel(const pgmp_group_params
   __syncthreads();
   for (int i = tid; i < n; i += kThreads) p.person_labels[n0 + i] = comp[rep[i]];
   __syncthreads();
-  // ---- persons (Utils.py:692-741): components with more than one node, per type the node with the best score
+  // ---- persons (Utils.py:692-741): components with more than one node, per type the node with the best score.  Every
+  //      node votes for its (component root, type) slot with score bits << 32 | ~node: the largest key is the first
+  //      maximum of :718; then one warp walks the roots in order (persons are numbered by their smallest node).
+  int* __restrict__ csize = ws.csize + (size_t)b * M;
+  unsigned long long* __restrict__ pkey = ws.pkey + (size_t)b * M * J;
+  for (int i = tid; i < n; i += kThreads) csize[i] = 0;
+  for (int i = tid; i < n * J; i += kThreads) pkey[i] = 0ull;
+  __syncthreads();
+  for (int i = tid; i < n; i += kThreads) {
+    atomicAdd(&csize[rep[i]], 1);
+    const float sc = pn[i] > 0.f ? pn[i] : 0.f;
+    atomicMax(&pkey[(size_t)rep[i] * J + typ[i]], ((unsigned long long)__float_as_uint(sc) << 32) | (unsigned long long)(0xffffffffu - (unsigned)i));
+  }
+  __syncthreads();
   if (warp == 0) {
     int n_person = 0, mutant = 0;
     double* __restrict__ out = p.persons + (size_t)b * p.max_persons * J * 3;
-    for (int r = 0; r < n; ++r) {
-      if (rep[r] != r) continue;
-      int size = 0;
-      for (int i = r + lane; i < n; i += 32) size += rep[i] == r ? 1 : 0;
-      size = __reduce_add_sync(kFull, size);
-      if (size > J) mutant = 1;                                     // :703-706
-      if (size <= 1) continue;                                      // :708
-      int valid = 0;
-      for (int t = lane; t < J; t += 32) {
-        float best = -1.f;
-        int bi = -1;
-        for (int i = r; i < n; ++i)
-          if (rep[i] == r && typ[i] == t && pn[i] > best) { best = pn[i]; bi = i; }   // first maximum, :718
-        double x = 0, y = 0, sc = 0;
-        if (bi >= 0) {
-          x = (double)p.joint_det[(n0 + bi) * 3 + 0];
-          y = (double)p.joint_det[(n0 + bi) * 3 + 1];
-          sc = (double)best;
-          if (best > 0.f) valid = 1;
+    for (int r0 = 0; r0 < n; r0 += 32) {
+      const int rr = r0 + lane;
+      const int sz = rr < n && rep[rr] == rr ? csize[rr] : 0;
+      if (__any_sync(kFull, sz > J)) mutant = 1;                     // :703-706
+      uint32_t roots = __ballot_sync(kFull, sz > 1);                 // :708
+      while (roots) {
+        const int r = r0 + __ffs(roots) - 1;
+        roots &= roots - 1;
+        int valid = 0;
+        for (int t = lane; t < J; t += 32) {
+          const unsigned long long key = pkey[(size_t)r * J + t];
+          double x = 0, y = 0, sc = 0;
+          if (key != 0ull) {
+            const int bi = (int)(0xffffffffu - (unsigned)(key & 0xffffffffull));
+            const float best = __uint_as_float((unsigned)(key >> 32));
+            x = (double)p.joint_det[(n0 + bi) * 3 + 0];
+            y = (double)p.joint_det[(n0 + bi) * 3 + 1];
+            sc = (double)best;
+            if (best > 0.f) valid = 1;
+          }
+          if (n_person < p.max_persons) {
+            out[((size_t)n_person * J + t) * 3 + 0] = x;
+            out[((size_t)n_person * J + t) * 3 + 1] = y;
+            out[((size_t)n_person * J + t) * 3 + 2] = sc;
+          }
         }
-        if (n_person < p.max_persons) {
-          out[((size_t)n_person * J + t) * 3 + 0] = x;
-          out[((size_t)n_person * J + t) * 3 + 1] = y;
-          out[((size_t)n_person * J + t) * 3 + 2] = sc;
-        }
+        valid = __any_sync(kFull, valid);
+        if (valid) ++n_person;                                      // :725
       }
-      valid = __any_sync(kFull, valid);
-      if (valid) ++n_person;                                        // :725
     }
     if (lane == 0) { p.num_persons[b] = n_person; p.mutants[b] = mutant; }
   }
@@ -320,7 +347,7 @@ extern "C" int pgmp_group_persons(const pgmp_group_params* p, pgmp_stream_t stre
   const GroupWs w = carve(*p, p->max_nodes_per_image);
   if (w.bytes > p->workspace_bytes) return set_error(PGMP_ERR_INVALID, "workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t book = (size_t)20 * p->max_nodes_per_image;
+  const size_t book = (size_t)24 * p->max_nodes_per_image;
   const int use_smem = book <= 160 * 1024;
   if (use_smem && book > 48 * 1024)
     PGMP_CUDA(cudaFuncSetAttribute(group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)book));

@@ -12,6 +12,11 @@ full work; results are identical to the serial calls (same kernels, same order p
     pipe = GroupingPipeline(gc_config, mpn, num_joints, device)
     for graph, (preds_edge, preds_node, preds_class) in pipe.run(batches):   # batches: dicts of construct_graph kwargs
         ...
+
+With ``group=dict(node_threshold=..., cc_method=...)`` the grouping tail (sigmoid / threshold / GAEC / persons,
+``Utils.group_persons``) of batch ``i`` runs on a third stream while batch ``i + 1`` goes through the network -- the greedy
+contraction is a sequential algorithm that keeps one CTA per image busy for milliseconds on a fraction of the SMs -- and
+``run`` yields ``(graph, preds, groups)``.
 """
 
 import torch
@@ -20,11 +25,13 @@ from .graph_constructor import get_graph_constructor
 
 
 class GroupingPipeline:
-    def __init__(self, gc_config, model, num_joints, device, testing=True):
+    def __init__(self, gc_config, model, num_joints, device, testing=True, group=None):
         self.gc_config, self.model, self.num_joints = gc_config, model, num_joints
         self.device = torch.device(device)
         self.testing = testing
         self.side = torch.cuda.Stream(device=self.device)
+        self.group = dict(group) if group is not None else None
+        self.group_stream = torch.cuda.Stream(device=self.device) if group is not None else None
 
     def _submit(self, batch):
         """Start the detection half of ``batch`` on the side stream; returns the graph constructor holding it."""
@@ -45,15 +52,39 @@ class GroupingPipeline:
         with torch.no_grad():
             pe, pn, pc, _ = self.model(ret[0], ret[1], ret[2], node_labels=None, edge_labels=None, batch_index=ret[12],
                                        node_mask=None, node_types=ret[7][:, 2])
-        return ret, (pe, pn, pc)
+        if self.group is None:
+            return ret, (pe, pn, pc)
+        from .Utils import group_persons_async
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.group_stream.wait_event(ev)                   # the logits are ready on the main stream
+        pend = group_persons_async(ret[7], pn[-1], ret[2], pe[-1], pc[-1], ret[12], self.num_joints,
+                                   detector_scores=ret[11], nodes_per_image=gc.num_nodes_per_image,
+                                   edges_per_image=gc.num_edges_per_image, stream=self.group_stream, **self.group)
+        return ret, (pe, pn, pc), pend
 
     def run(self, batches):
-        """Generator over ``(graph 15-tuple, (preds_edge, preds_node, preds_class))``, one per batch, in order."""
-        prev = None
+        """Generator over ``(graph 15-tuple, (preds_edge, preds_node, preds_class))`` -- plus the groups of
+        ``Utils.group_persons`` when the pipeline was built with ``group=`` -- one per batch, in order."""
+        prev, waiting = None, None                         # constructor with its detection in flight; batch whose groups are in flight
         for batch in batches:
             cur = self._submit(batch)
             if prev is not None:
-                yield self._finish(prev)
+                out = self._finish(prev)
+                if self.group is None:
+                    yield out
+                else:
+                    if waiting is not None:
+                        yield waiting[0], waiting[1], waiting[2].result()
+                    waiting = out
             prev = cur
         if prev is not None:
-            yield self._finish(prev)
+            out = self._finish(prev)
+            if self.group is None:
+                yield out
+            else:
+                if waiting is not None:
+                    yield waiting[0], waiting[1], waiting[2].result()
+                yield out[0], out[1], out[2].result()
+        elif waiting is not None:
+            yield waiting[0], waiting[1], waiting[2].result()

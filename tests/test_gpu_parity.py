@@ -301,6 +301,20 @@ def test_pipelined_api_equals_serial_calls():
         with torch.no_grad():
             pe, pn, pc, _ = model(ret[0], ret[1], ret[2], node_types=ret[7][:, 2])
         serial.append((ret, pe[-1], pn[-1], pc[-1]))
+    from pgmp_b200.Utils import group_persons
+    serial_groups = []
+    for d, (sret, spe, spn, spc) in zip(datas, serial):
+        serial_groups.append(group_persons(sret[7], spn, sret[2], spe, spc, sret[12], J, node_threshold=0.5, detector_scores=sret[11]))
+    pipe_g = GroupingPipeline(gcfg, model, J, DEV, group=dict(node_threshold=0.5))
+    batches = [{k: torch.from_numpy(d[k]).to(DEV) for k in ("scoremaps", "tagmaps", "features")} for d in datas]
+    outs = list(pipe_g.run(batches))
+    assert len(outs) == len(datas)
+    for (ret, preds, groups), want in zip(outs, serial_groups):
+        assert len(groups) == len(want) == 2
+        for g_, w_ in zip(groups, want):
+            assert (g_ is None) == (w_ is None)
+            if g_ is not None:
+                assert np.array_equal(g_[0], w_[0]) and g_[1] == w_[1] and torch.equal(g_[2], w_[2])
     pipe = GroupingPipeline(gcfg, model, J, DEV)
     for host in (False, True):
         if host:      # pinned host inputs: heatmaps copied on the side stream, feature / tag maps gathered in place
