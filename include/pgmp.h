@@ -244,6 +244,11 @@ int pgmp_selftest_umma(const float* a, const float* w, float* d, pgmp_stream_t s
 /* the same product with the A operand in tensor memory (tcgen05.st + the TS form of tcgen05.mma) */
 int pgmp_selftest_umma_ts(const float* a, const float* w, float* d, pgmp_stream_t stream);
 
+/* The FIRST int32 of the workspace is a status word written by pgmp_mpn_forward (stream-ordered, no host sync inside):
+ * 0 = the input was well-formed; bit 0 = edge_index held a node id outside [0, num_nodes) -- the reference raises an
+ * IndexError there; here such an edge is dropped (its logit is left unwritten) and the caller reads the word when it next
+ * synchronises (the Python mirror raises at its next forward / check_status()). */
+#define PGMP_MPN_STATUS_BAD_EDGE 1
 uint64_t pgmp_mpn_workspace_bytes(const pgmp_mpn_params* p);
 int pgmp_mpn_forward(const pgmp_mpn_params* p, pgmp_stream_t stream);
 

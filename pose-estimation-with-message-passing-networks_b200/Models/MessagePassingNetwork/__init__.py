@@ -180,7 +180,17 @@ class _MpnTrainFunction(torch.autograd.Function):
             ctx.token = object()                                    # this forward owns the workspace until another forward takes it
             owners = model.__dict__.setdefault("_train_ws_owner", {})
             owners[ws.data_ptr()] = ctx.token
+            # the reference evaluates the node and class heads once more on the final features (:93-94): with BatchNorm in
+            # the heads (MPN.BN) that second call applies the momentum update of their running statistics a second time
+            twice = [m for head in (model.node_classification, model.classification) for m in head
+                     if isinstance(m, nn.BatchNorm1d)]
+            before = [(m.running_mean.clone(), m.running_var.clone()) for m in twice]
             nv.check(lib.pgmp_mpn_train_forward(p, nv.current_stream()))
+            for m, (mean0, var0) in zip(twice, before):      # r2 = (1 - mom) r1 + mom b  with  mom b = r1 - (1 - mom) r0
+                keep = 1.0 - m.momentum
+                m.running_mean.mul_(1.0 + keep).sub_(mean0, alpha=keep)
+                m.running_var.mul_(1.0 + keep).sub_(var0, alpha=keep)
+                m.num_batches_tracked += 1
         for mod in model.modules():            # the kernels updated the running statistics in place
             if isinstance(mod, nn.BatchNorm1d):
                 torch.autograd.graph.increment_version((mod.running_mean, mod.running_var))
@@ -259,10 +269,29 @@ class NodeClassificationMPNSimple(nn.Module):
         if self.precision not in nv.PRECISION:
             raise ValueError("B200_PRECISION must be one of %s" % (sorted(nv.PRECISION),))
         self._pack_cache = None
+        self._status = None          # (pinned status word of the previous forward, event)
 
     # ------------------------------------------------------------------ weight packing
+    def invalidate_packed_weights(self):
+        """Drop the packed (BatchNorm-folded, bf16-split) copy of the weights.  The cache notices ``load_state_dict``,
+        optimizer steps and every other in-place update that goes through autograd's version counter, and re-allocated
+        storage; updates through ``.data`` (``p.data.copy_()``, EMA swaps) bump no counter -- call this after them."""
+        self._pack_cache = None
+
+    def check_status(self):
+        """Raise if the previous ``forward`` met malformed input (an ``edge_index`` entry outside ``[0, N)``: the reference
+        raises an IndexError).  The forward itself never waits for the device; the status word is read here and at the
+        start of the next forward, once its copy has arrived."""
+        st = self._status
+        if st is not None and st[1].query():
+            self._status = None
+            if int(st[0][0]) & 1:
+                raise IndexError("edge_index of the previous forward held node ids outside [0, num_nodes): those edges were "
+                                 "dropped and their logits are undefined")
+
     def _pack(self, device):
-        key = (str(device),) + tuple(t._version for t in list(self.parameters()) + list(self.buffers()))
+        tensors = list(self.parameters()) + list(self.buffers())
+        key = (str(device),) + tuple((t._version, t.data_ptr()) for t in tensors)
         if self._pack_cache is not None and self._pack_cache[0] == key:
             return self._pack_cache[1]
         pk = _Packer()
@@ -356,6 +385,7 @@ class NodeClassificationMPNSimple(nn.Module):
     def forward(self, x, edge_attr, edge_index, **kwargs):
         if self.training:
             return self._forward_train(x, edge_attr, edge_index, **kwargs)
+        self.check_status()
         if self.node_steps != 0:
             raise NotImplementedError("NODE_STEPS != 0 (the reference's own loop omits node_types, App. A)")
         if self.edge_steps < 1:
@@ -407,6 +437,11 @@ class NodeClassificationMPNSimple(nn.Module):
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
                 p.workspace, p.workspace_bytes = ws.data_ptr(), ws_bytes
                 nv.check(lib.pgmp_mpn_forward(p, nv.current_stream()))
+                status_h = torch.empty(1, dtype=torch.int32, pin_memory=True)
+                status_h.copy_(ws[:4].view(torch.int32), non_blocking=True)     # first word of the workspace (pgmp.h)
+                ev = torch.cuda.Event()
+                ev.record()
+                self._status = (status_h, ev)
                 ws.record_stream(torch.cuda.current_stream())
         # lists of independent tensors: the caller mutates entries in place (PoseEstimation.py:95-101);
         # .squeeze() semantics of :82,:84,:93 (0-d when there is a single edge / node)

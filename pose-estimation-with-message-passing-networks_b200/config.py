@@ -40,7 +40,7 @@ def default_mpn_config(num_joints=17, **overrides):
     cfg = NS(
         NAME="NodeClassificationMPN", NODE_TYPE_SUMMARY="not", STEPS=10, NODE_STEPS=0, EDGE_MLP="agnostic",
         NODE_INPUT_DIM=128, AGGR_TYPE="agnostic", EDGE_INPUT_DIM=num_joints + 2, EDGE_FEATURE_DIM=64,
-        EDGE_FEATURE_HIDDEN=64, NODE_FEATURE_DIM=64, USE_NODE_UPDATE_MLP=False, BN=False, AGGR="max",
+        EDGE_FEATURE_HIDDEN=64, NODE_FEATURE_DIM=64, USE_NODE_UPDATE_MLP=False, BN=True, AGGR="max",
         AGGR_SUB="None", UPDATE_TYPE="mlp", SKIP=False, AUX_LOSS_STEPS=0, DROP_FEATURE="", EDGE_STEPS=0,
         LATE_FUSION_POS=False, NUM_JOINTS=num_joints, NODE_THRESHOLD=0.1,
         NODE_EMB=NS(BN=True, END_WITH_RELU=False, OUTPUT_SIZES=[128, 64, 64]),
@@ -57,13 +57,13 @@ def default_mpn_config(num_joints=17, **overrides):
 def flagship_mpn_config(num_joints=17, **overrides):
     """hybrid_class_agnostic_end2end/model_58_4.yaml:91-137: per-type messages,
     edge attention, skip connections, 10 steps."""
-    base = dict(AGGR_TYPE="per_type", AGGR="add", AGGR_SUB="node_edge_attn", SKIP=True, STEPS=10)
+    base = dict(AGGR_TYPE="per_type", AGGR="add", AGGR_SUB="node_edge_attn", SKIP=True, STEPS=10, BN=False)   # BN: False, model_58_4.yaml:135
     base.update(overrides)
     return default_mpn_config(num_joints, **base)
 
 
 def agnostic_mpn_config(num_joints=17, **overrides):
     """class_agnostic_end2end/model_57_1_0.yaml shape: agnostic MPLayer, max aggregation, skip."""
-    base = dict(AGGR_TYPE="agnostic", AGGR="max", SKIP=True, STEPS=10)
+    base = dict(AGGR_TYPE="agnostic", AGGR="max", SKIP=True, STEPS=10, BN=False)   # BN: False in the YAML (the code default is True, default_config.py:132)
     base.update(overrides)
     return default_mpn_config(num_joints, **base)

@@ -20,6 +20,7 @@ constexpr int kTile = 128;      // rows (slots / nodes) per CTA tile
 constexpr int kTileP = kTile + 1;  // padded row count of transposed shared-memory tiles
 
 struct MpnWorkspace {
+  int32_t* status;        // [1] FIRST word of the workspace: PGMP_MPN_STATUS_* bits set by the forward (0 = input was well-formed)
   // graph bookkeeping
   int32_t* node_type;     // [N] clamped to [0, T)
   int32_t* bin_count;     // [T*N] edges per (type, target)
@@ -69,6 +70,7 @@ inline MpnWorkspace carve_mpn(const pgmp_mpn_params& p) {
   w.max_slots = round_up<uint64_t>(E, kTile) + T * kTile;       // every group padded to 128
   const uint64_t bins = T * N;
   w.max_parts = (E < bins ? E : bins) + w.max_slots / kTile;      // non-empty bins + tile crossings
+  w.status = c.take<int32_t>(1);
   w.node_type = c.take<int32_t>(N);
   w.bin_count = c.take<int32_t>(bins);
   w.bin_cursor = c.take<int32_t>(bins);

@@ -22,10 +22,14 @@ __global__ void __launch_bounds__(256) node_types_kernel(const int64_t* __restri
 
 __global__ void __launch_bounds__(256) count_bins_kernel(const int64_t* __restrict__ edge_index, int64_t E, int64_t N,
                                                           const int32_t* __restrict__ node_type,
-                                                          int32_t* __restrict__ bin_count) {
+                                                          int32_t* __restrict__ bin_count, int32_t* __restrict__ status) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
   const int64_t src = edge_index[e], dst = edge_index[E + e];
+  if ((uint64_t)src >= (uint64_t)N || (uint64_t)dst >= (uint64_t)N) {   // the reference raises an IndexError here:
+    atomicOr(status, PGMP_MPN_STATUS_BAD_EDGE);                           // the edge is dropped and the status word says so
+    return;
+  }
   atomicAdd(&bin_count[(int64_t)node_type[src] * N + dst], 1);
 }
 
@@ -114,6 +118,7 @@ __global__ void __launch_bounds__(256) scatter_slots_kernel(const int64_t* __res
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
   const int64_t src = edge_index[e], dst = edge_index[E + e];
+  if ((uint64_t)src >= (uint64_t)N || (uint64_t)dst >= (uint64_t)N) return;   // dropped, flagged by count_bins_kernel
   const int t = node_type[src];
   const int64_t bin = (int64_t)t * N + dst;
   const int pos = atomicAdd(&bin_cursor[bin], 1);
@@ -154,6 +159,7 @@ int mpn_prepare_graph(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStrea
   const int64_t N = p.num_nodes, E = p.num_edges;
   const int T = p.num_types;
   const int64_t bins = (int64_t)T * N;
+  PGMP_CUDA(cudaMemsetAsync(w.status, 0, sizeof(int32_t), st));
   PGMP_CUDA(cudaMemsetAsync(w.bin_count, 0, sizeof(int32_t) * bins, st));
   PGMP_CUDA(cudaMemsetAsync(w.bin_cursor, 0, sizeof(int32_t) * bins, st));
   PGMP_CUDA(cudaMemsetAsync(w.slot_edge, 0xff, sizeof(int32_t) * w.max_slots, st));
@@ -163,7 +169,7 @@ int mpn_prepare_graph(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStrea
               w.node_type);
   if (E > 0)
     PGMP_LAUNCH(count_bins_kernel, (unsigned)ceil_div<int64_t>(E, 256), 256, 0, st, p.edge_index, E, N, w.node_type,
-                w.bin_count);
+                w.bin_count, w.status);
   PGMP_LAUNCH(scan_groups_kernel, T, 1024, 0, st, N, w.bin_count, w.bin_lstart, w.bin_lpart, w.group_total,
               w.group_parts);
   PGMP_LAUNCH(group_offsets_kernel, 1, 32, 0, st, T, w.group_total, w.group_parts, w.group_start, w.group_pstart);

@@ -330,6 +330,34 @@ def test_pipelined_api_equals_serial_calls():
             assert torch.equal(pe[-1], spe) and torch.equal(pn[-1], spn) and torch.equal(pc[-1], spc)
 
 
+def test_malformed_edge_index_is_reported_not_a_device_fault():
+    """A node id outside [0, N) in ``edge_index`` (the reference raises an IndexError): the edge is dropped, nothing is
+    written out of bounds, and the module raises once the status word of that forward has arrived; ``.data`` updates are
+    picked up after ``invalidate_packed_weights()``."""
+    cfg, g, model = mpn_case("flagship", "tc")
+    x, ea, ei, types = (torch.from_numpy(g[k]).to(DEV) for k in ("x", "edge_attr", "edge_index", "joint_det"))
+    types = types[:, 2].contiguous()
+    with torch.no_grad():
+        good = model(x, ea, ei, node_types=types)[0][-1].clone()
+    bad = ei.clone()
+    bad[0, 5] = x.shape[0] + 7
+    bad[1, 9] = -3
+    with torch.no_grad():
+        model(x, ea, bad, node_types=types)
+    torch.cuda.synchronize()
+    with pytest.raises(IndexError):
+        model.check_status()
+    with torch.no_grad():
+        again = model(x, ea, ei, node_types=types)[0][-1]
+    assert torch.equal(again, good)
+    p0 = next(model.parameters())
+    p0.data.mul_(1.5)
+    model.invalidate_packed_weights()
+    with torch.no_grad():
+        changed = model(x, ea, ei, node_types=types)[0][-1]
+    assert not torch.equal(changed, good)
+
+
 def test_umma_selftest_gemm():
     """The tcgen05 building blocks in isolation: D = A . W^T for one 128x64x64 tile."""
     import pgmp_b200._native as nv
