@@ -1,5 +1,6 @@
 """Drop-in for the reference's ``graph_constructor`` package
-(``src/graph_constructor/__init__.py:4-5``, ``ConstructGraph.py:9-249``), inference branch.
+(``src/graph_constructor/__init__.py:4-5``, ``ConstructGraph.py:9-249``): inference, and training with
+``joints_gt`` / ``factor_list`` (label slots of the 15-tuple, ``labels.py``).
 
 ``get_graph_constructor(config, **kwargs).construct_graph()`` keeps the reference's
 constructor keywords and its 15-tuple; the work runs in ``libpgmp.so``
@@ -120,9 +121,27 @@ class NaiveGraphConstructor:
         self.testing = testing
         self.config = config
 
-        if joints_gt is not None or config.USE_GT or config.CHEAT:
-            raise NotImplementedError("ground-truth label construction (ConstructGraph.py:104-143, 475-1158) is "
-                                      "training-only host code outside the inference hot path (SURVEY.md 8f)")
+        if config.USE_GT or config.CHEAT:
+            raise NotImplementedError("USE_GT / CHEAT (graphs built from the ground truth, ConstructGraph.py:70-99) are "
+                                      "debugging modes outside the hot path")
+        # training: labels from the ground truth (ConstructGraph.py:104-168), graph_constructor/labels.py
+        self.edge_label_method = config.EDGE_LABEL_METHOD
+        self.include_neighbouring_keypoints = config.USE_NEIGHBOURS
+        self.matching_radius = config.MATCHING_RADIUS
+        self.inclusion_radius = config.INCLUSION_RADIUS
+        self.with_background_class = config.WITH_BACKGROUND
+        self.node_dropout = config.NODE_DROPOUT if config.NODE_DROPOUT != 0.0 else None
+        self.use_weighted_class_loss = config.WEIGHT_CLASS_LOSS
+        self.heatmaps = heatmaps
+        if joints_gt is not None:
+            from .labels import SUPPORTED_METHODS
+            if self.edge_label_method not in SUPPORTED_METHODS:
+                raise NotImplementedError("EDGE_LABEL_METHOD=%r (4 and 6, 201 of the reference's 223 configs, are in scope)"
+                                          % (self.edge_label_method,))
+            if config.IMAGE_CENTRIC_SAMPLING:
+                raise NotImplementedError("IMAGE_CENTRIC_SAMPLING is out of scope")
+            if factor_list is None:
+                raise ValueError("joints_gt needs factor_list (PoseEstimation.py:82-87)")
         self.mask_crowds = config.MASK_CROWDS
         self.detect_threshold = config.DETECT_THRESHOLD if config.DETECT_THRESHOLD <= 1.5 else None   # CG.py:28
         self.hybrid_k = config.HYBRID_K
@@ -291,9 +310,25 @@ class NaiveGraphConstructor:
             ws.record_stream(torch.cuda.current_stream())
         if feat is not None and not fused and feat.requires_grad and torch.is_grad_enabled():
             x = _GatherNodeFeatures.apply(feat, x, batch_index, joint_det)
-        # the reference's 15-tuple (ConstructGraph.py:248-249); label slots are None at inference (:243-246)
-        return (x, edge_attr, edge_index, None, None, None, None, joint_det, None, None, None, joint_scores,
-                batch_index, None, joint_tags)
+        if self.joints_gt is None:
+            # the reference's 15-tuple (ConstructGraph.py:248-249); label slots are None at inference (:243-246)
+            return (x, edge_attr, edge_index, None, None, None, None, joint_det, None, None, None, joint_scores,
+                    batch_index, None, joint_tags)
+        from . import labels as L
+        lab = L.build_labels(self, joint_det, edge_index, batch_index, self.num_nodes_per_image.tolist())
+        if self.node_dropout is not None and not self.testing:
+            (x, edge_attr, edge_index, joint_det, joint_scores, batch_index, joint_tags, lab,
+             nodes_per_image) = L.node_dropout(self.node_dropout, x, edge_attr, edge_index, joint_det, joint_scores,
+                                               batch_index, joint_tags, lab, B)
+            self.num_nodes_per_image = nodes_per_image.cpu()
+            self.num_edges_per_image = torch.bincount(batch_index[edge_index[0]], minlength=B).cpu()
+        if self.use_weighted_class_loss and lab["class_mask"] is not None:      # ConstructGraph.py:170-176, indices as written there
+            hm = self.heatmaps.to(dev)
+            wts = hm[batch_index, lab["node_classes"], joint_det[:, 1], joint_det[:, 2]]
+            lab["class_mask"] = torch.where(wts < 0.1, torch.full_like(wts, 0.1), wts) * lab["class_mask"]
+        return (x, edge_attr, edge_index, lab["edge_labels"], lab["node_labels"], lab["node_classes"], None, joint_det,
+                lab["label_mask"], lab["label_mask_node"], lab["class_mask"], joint_scores, batch_index,
+                lab["node_persons"], joint_tags)
 
 
 def hr_process_output(output, mode, num_joints):

@@ -136,3 +136,38 @@ def image_subgraph(graph, logits, b):
     return dict(joint_det=graph["joint_det"][nsel], edge_index=graph["edge_index"][:, esel] - off,
                 node_logits=logits["node_logits"][nsel], edge_logits=logits["edge_logits"][esel],
                 class_logits=logits["class_logits"][nsel], num_joints=logits["num_joints"])
+
+
+def synth_joints_gt(image_index, num_joints=17, size=512, k=30, persons=8, width=None, max_persons=30, drop=0.2):
+    """Ground truth that goes with ``synth_scoremap(image_index, ...)``: the planted persons' joints.
+
+    Returns ``joints_gt [max_persons, J, 3]`` float32 (x, y, visibility; the layout ``PoseEstimation.forward`` hands to the
+    graph constructor, ``ConstructGraph.py:11``) and ``factors [max_persons, J]`` float32 (the OKS-style ``2 (k_j s)^2``
+    denominators of ``ConstructGraph.py:781-782``).  The positions are the persons' peak centres of the scoremap, moved by
+    up to one pixel; about ``drop`` of the joints are not annotated.  Same random stream as ``synth_scoremap``.
+    """
+    H = size
+    W = size if width is None else width
+    rng = np.random.default_rng(1000 + image_index)
+    centres = rng.uniform(0.15, 0.85, size=(persons, 2)) * np.array([W, H])
+    n_peaks = 2 * k + 8
+    body_pts = np.zeros((num_joints, persons, 2), dtype=np.int64)
+    for j in range(num_joints):                      # replay synth_scoremap's draws to recover the body peaks
+        jit = rng.normal(0.0, 0.1, size=(persons, 2)) * np.array([W, H])
+        body = centres + jit
+        rnd = rng.uniform(0, 1, size=(n_peaks, 2)) * np.array([W, H])
+        rnd[:min(persons, n_peaks)] = body[:min(persons, n_peaks)]
+        body_pts[j, :, 0] = np.clip(np.rint(rnd[:persons, 0]), _R, W - 1 - _R)
+        body_pts[j, :, 1] = np.clip(np.rint(rnd[:persons, 1]), _R, H - 1 - _R)
+        amps = np.linspace(0.2, 0.95, n_peaks, dtype=np.float32)
+        rng.shuffle(amps)
+    rng2 = np.random.default_rng(3000 + image_index)
+    gt = np.zeros((max_persons, num_joints, 3), dtype=np.float32)
+    factors = np.ones((max_persons, num_joints), dtype=np.float32)
+    for p in range(min(persons, max_persons)):
+        gt[p, :, 0] = body_pts[:, p, 0] + rng2.uniform(-1.0, 1.0, size=num_joints)
+        gt[p, :, 1] = body_pts[:, p, 1] + rng2.uniform(-1.0, 1.0, size=num_joints)
+        gt[p, :, 2] = (rng2.uniform(size=num_joints) >= drop).astype(np.float32)
+        factors[p] = rng2.uniform(20.0, 80.0, size=num_joints)
+    gt[:, :, :2] *= gt[:, :, 2:3]
+    return gt, factors

@@ -18,6 +18,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
+import numpy as np  # noqa: E402
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 import torch.nn.functional as F  # noqa: E402
@@ -46,7 +47,10 @@ def run_training(args, rank, world, dev):
     J, K = 17, 30
     data = synthetic.synth_batch(args.batch, J, args.size, K, persons=8, first_index=rank * args.batch)
     t = {k: torch.from_numpy(v).to(dev) for k, v in data.items()}
-    gcfg = pgmp_b200.config.bench_gc_config(k=K, graph_type="knn")
+    gts, facs = zip(*[synthetic.synth_joints_gt(rank * args.batch + b, J, args.size, K, persons=8) for b in range(args.batch)])
+    joints_gt, factors = torch.from_numpy(np.stack(gts)).to(dev), torch.from_numpy(np.stack(facs)).to(dev)
+    # labels from the ground truth as the reference's training loop gets them (EDGE_LABEL_METHOD 6, class_agnostic_end2end)
+    gcfg = pgmp_b200.config.bench_gc_config(k=K, graph_type="knn", EDGE_LABEL_METHOD=6, MATCHING_RADIUS=0.5)
     mcfg = pgmp_b200.config.agnostic_mpn_config(J, STEPS=args.mpn_steps)
     model = synthetic.synth_mpn_state_dict(get_mpn_model(mcfg), 0).to(dev).train()
     opt = torch.optim.Adam(model.parameters(), lr=1e-4)
@@ -58,19 +62,21 @@ def run_training(args, rank, world, dev):
     def step(timed):
         ev["step"][0].record()
         ev["gc"][0].record()
-        ret = get_graph_constructor(gcfg, scoremaps=t["scoremaps"], tagmaps=t["tagmaps"], features=t["features"], joints_gt=None,
-                                    factor_list=None, masks=None, device=dev, testing=False, heatmaps=None,
-                                    num_joints=J).construct_graph()
+        ret = get_graph_constructor(gcfg, scoremaps=t["scoremaps"], tagmaps=t["tagmaps"], features=t["features"],
+                                    joints_gt=joints_gt, factor_list=factors, masks=None, device=dev, testing=False,
+                                    heatmaps=None, num_joints=J).construct_graph()
         x, edge_attr, edge_index, joint_det = ret[0], ret[1], ret[2], ret[7]
+        edge_labels, node_labels, node_classes, label_mask, node_mask, class_mask = ret[3], ret[4], ret[5], ret[8], ret[9], ret[10]
         ev["gc"][1].record()
         N, E = x.shape[0], edge_index.shape[1]
         info.update(nodes=N, edges=E)
         ev["fwd"][0].record()
         pe, pn, pc, _ = model(x, edge_attr, edge_index, node_types=joint_det[:, 2])
         ev["fwd"][1].record()
-        loss = (F.binary_cross_entropy_with_logits(pe[-1], (torch.rand(E, device=dev, generator=gen) < 0.1).float())
-                + F.binary_cross_entropy_with_logits(pn[-1], (torch.rand(N, device=dev, generator=gen) < 0.5).float())
-                + F.cross_entropy(pc[-1], joint_det[:, 2]))
+        # masked losses on the constructor's labels (stock torch ops standing in for the reference's focal / CE losses)
+        loss = (F.binary_cross_entropy_with_logits(pe[-1], edge_labels, weight=label_mask, reduction="sum") / label_mask.sum().clamp(min=1)
+                + F.binary_cross_entropy_with_logits(pn[-1], node_labels, weight=node_mask, reduction="sum") / node_mask.sum().clamp(min=1)
+                + (F.cross_entropy(pc[-1], node_classes, reduction="none") * class_mask).sum() / class_mask.sum().clamp(min=1))
         opt.zero_grad(set_to_none=True)
         ev["bwd"][0].record()
         loss.backward()

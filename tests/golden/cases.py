@@ -149,3 +149,30 @@ def full_edge_sample(n, name):
         return np.arange(n)
     rng = np.random.default_rng(int.from_bytes(hashlib.sha256(("full_" + name).encode()).digest()[:4], "little"))
     return np.sort(rng.choice(n, FULL_EDGE_SAMPLE, replace=False))
+
+
+# ---- training branch of the graph constructor (labels): name -> (synthetic input kwargs, GC config overrides)
+LABEL_CASES = {
+    "m6": (dict(batch=2, num_joints=17, size=128, k=10, persons=3),
+           dict(k=10, graph_type="knn", EDGE_LABEL_METHOD=6, MATCHING_RADIUS=0.5, INCLUSION_RADIUS=0.75)),
+    "m6_neigh_bg": (dict(batch=2, num_joints=17, size=128, k=10, persons=3),
+                    dict(k=10, graph_type="knn", EDGE_LABEL_METHOD=6, MATCHING_RADIUS=0.3, INCLUSION_RADIUS=0.35,
+                         USE_NEIGHBOURS=True, WITH_BACKGROUND=True, POOL_KERNEL_SIZE=3)),
+    "m4_neigh": (dict(batch=2, num_joints=17, size=128, k=10, persons=3),
+                 dict(k=10, graph_type="fully", EDGE_LABEL_METHOD=4, MATCHING_RADIUS=0.1, INCLUSION_RADIUS=0.3,
+                      USE_NEIGHBOURS=True, POOL_KERNEL_SIZE=3)),
+    "m6_thr": (dict(batch=2, num_joints=17, size=128, k=10, persons=3),
+               dict(k=5, graph_type="knn", EDGE_LABEL_METHOD=6, MATCHING_RADIUS=0.5, DETECT_THRESHOLD=0.3)),
+}
+LABEL_SLOTS = dict(edge_labels=3, node_labels=4, node_classes=5, label_mask=8, label_mask_node=9, class_mask=10, node_persons=13)
+
+
+def label_inputs(name):
+    """Seeded inputs of a LABEL case: the synthetic batch, ``joints_gt [B, 30, J, 3]`` and ``factors [B, 30, J]``."""
+    import numpy as np
+    import pgmp_b200.synthetic as synthetic
+    inp_kw, _ = LABEL_CASES[name]
+    data = synthetic.synth_batch(**inp_kw)
+    gts, facs = zip(*[synthetic.synth_joints_gt(b, inp_kw["num_joints"], inp_kw["size"], inp_kw["k"], inp_kw["persons"])
+                      for b in range(inp_kw["batch"])])
+    return data, np.stack(gts), np.stack(facs)
