@@ -82,7 +82,9 @@ static_assert(kOffWg % 1024 == 0 && kWgBytes % 1024 == 0 && kWgAdd % 1024 == 0 &
 // Measured with in-kernel phase timers (17 000 cycles per tile, round 2): ~3 100 issuing the P / Q gathers (16-byte
 // chunks of 32 different rows per request: the L1 data pipe is the busiest unit, 55 %), ~1 100 per product between its
 // operands being ready and its result being visible (x 3), ~3 900 in the three epilogues, ~2 000 in the run scan,
-// ~2 400 in the run reduction.  Tried and rejected, with numbers, in DESIGN.md: cooperative (line-wide) table gathers
+// ~2 400 in the run reduction; with the three table gathers switched off (timing experiment) a launch takes 0.197 ms
+// instead of 0.227 ms, i.e. the chain of dependent phases with two tiles in flight per SM is the limit, not the gathers.
+// Tried and rejected, with numbers, in DESIGN.md: cooperative (line-wide) table gathers
 // through the staging tile, requesting the next tile's features a whole tile early, L2 prefetch of the next tile's rows.
 constexpr int kTgThreads = 256;                 // one tile group = one tile in flight
 constexpr int kEdge2Threads = 2 * kTgThreads;

@@ -1,3 +1,3 @@
 set -x
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest21.txt 2>&1; tail -3 gpurun_out/r2_pytest21.txt
-python scripts/bench_train.py --steps 5 --warmup 3 > gpurun_out/r2_train4.txt 2>&1; tail -1 gpurun_out/r2_train4.txt | cut -c1-700
+PGMP_EDGE_NOGATHER=1 timeout 300 python scripts/quick_profile.py 32 knn tc > gpurun_out/r2_qp_nogather.txt 2>&1; head -4 gpurun_out/r2_qp_nogather.txt
+timeout 300 python scripts/quick_profile.py 32 knn tc > gpurun_out/r2_qp_base.txt 2>&1; head -3 gpurun_out/r2_qp_base.txt
