@@ -449,12 +449,17 @@ def run_b200(args, rank, local_rank, world):
     bytes_per_launch = {
         "edge_step_kernel": 3 * 64 * elem * edges_per_step,       # read g, read C (skip constant), write g'
         "edge_step_tc_kernel": 3 * 64 * elem * edges_per_step,     # g and g' are bf16 hi+lo = 4 bytes per element
-        "nms_candidates_kernel<R, true>": J * SIZE * SIZE * 4 * B + nodes_per_step * 28,
     }.get(name)
+    if bytes_per_launch is None and name.startswith("nms_candidates"):
+        bytes_per_launch = J * SIZE * SIZE * 4 * B + nodes_per_step * 28
     roofline = None
     traffic = None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        tj = {}
+        for rnd in ("r1", "r2"):                      # the latest committed capture wins
+            fn = os.path.join(ROOT, "profiles", rnd + "_traffic.json")
+            if os.path.exists(fn):
+                tj.update(json.load(open(fn)))
         ent = tj.get(name)
         if ent and ent.get("edges_per_launch") == edges_per_step:
             traffic = ent["dram_bytes_per_launch"]

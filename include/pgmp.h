@@ -324,12 +324,13 @@ int pgmp_mpn_train_backward(const pgmp_mpn_train_params* p, pgmp_stream_t stream
  * ---------------------------------------------------------------------------------------------- */
 #define PGMP_CC_GAEC 0
 #define PGMP_CC_THRESHOLD 1
+#define PGMP_CC_GREEDY 2      /* greedy_person_construction, Utils.py:517-626: person_labels = core node of every node or -1 */
 
 typedef struct pgmp_group_params {
   int32_t batch, num_joints;
   int64_t num_nodes, num_edges;
   float node_threshold;                /* MPN.NODE_THRESHOLD */
-  int32_t cc_method;                   /* PGMP_CC_GAEC (greedy additive edge contraction) or PGMP_CC_THRESHOLD (Utils.py:508-509) */
+  int32_t cc_method;                   /* PGMP_CC_GAEC (greedy additive edge contraction), PGMP_CC_THRESHOLD (Utils.py:508-509) or PGMP_CC_GREEDY */
   float edge_threshold;                /* PGMP_CC_THRESHOLD: edges with probability > this join their ends (0.8 in the reference) */
   const int64_t* node_offsets;         /* device [B+1] prefix sums of nodes per image */
   const int64_t* edge_offsets;         /* device [B+1] prefix sums of edges per image (edges grouped by image) */

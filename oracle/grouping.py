@@ -157,9 +157,55 @@ def threshold_clusters(edge_index, edge_prob, n, edge_threshold=0.8):
     return np.array([find(i) for i in range(n)], dtype=np.int64)
 
 
+def greedy_person_construction(joint_det, node_prob, edge_index, edge_prob, class_prob, num_joints):
+    """``CC_METHOD == "greedy"`` (Utils.py:517-626).  Returns (persons [P,J,3] float64, taken [N] int64: the core node
+    that claimed each node, -1 for unclaimed nodes)."""
+    jd = np.array(joint_det, dtype=np.int64, copy=True)
+    n = len(jd)
+    if class_prob is not None:
+        jd[:, 2] = np.argmax(class_prob, axis=1)                  # :528-529
+    adj = np.zeros((n, n), dtype=np.float64)                      # :530
+    adj[edge_index[0], edge_index[1]] = edge_prob                 # :531
+    adj = (adj.T + adj) / 2.0                                     # :532
+    np.fill_diagonal(adj, 1.0)                                    # :533
+    taken = np.full(n, -1, dtype=np.int64)
+    by_type = [np.flatnonzero(jd[:, 2] == t) for t in range(num_joints)]
+    for t in range(num_joints):                                   # :549-583
+        for i in by_type[t].tolist():
+            if taken[i] != -1 or node_prob[i] < 0.5:
+                continue
+            taken[i] = i
+            for j in range(num_joints):
+                if j == t or len(by_type[j]) == 0:
+                    continue
+                row = adj[i, by_type[j]]
+                k = int(np.argmax(row))                           # first maximum; entries of other types count as 0
+                score, target = row[k], int(by_type[j][k])
+                if score == 0.0:
+                    continue
+                owner = taken[target]
+                if owner != -1 and adj[owner, target] > score:
+                    continue
+                taken[target] = i
+    persons = []
+    for c in range(int(taken.max()) + 1 if n else 0):             # :586-613
+        sel = taken == c
+        if sel.sum() > 1:
+            kp = np.zeros([num_joints, 3])
+            for t in range(num_joints):
+                s = sel & (jd[:, 2] == t)
+                if s.any():
+                    k = np.flatnonzero(s)[int(np.argmax(node_prob[s]))]
+                    kp[t] = jd[k]
+                    kp[t, 2] = node_prob[s].max()
+            if (kp[:, 2] > 0).sum() > 0:
+                persons.append(kp)
+    return np.array(persons), taken
+
+
 def pred_to_person(joint_det, node_logits, edge_index, edge_logits, class_logits, node_threshold, num_joints,
                    cc_method="GAEC"):
-    """valid.py:109-111 + Utils.py:1448-1457 + :499-514 for ``CC_METHOD in ("GAEC", "threshold")``.
+    """valid.py:109-111 + Utils.py:1448-1457 + :499-514 for ``CC_METHOD in ("GAEC", "threshold", "greedy")``.
 
     Returns (persons, mutants, person_labels) or None when the reference's
     ``pred_to_ann`` returns None before grouping (no edge survives)."""
@@ -170,6 +216,9 @@ def pred_to_person(joint_det, node_logits, edge_index, edge_logits, class_logits
     if ei.shape[1] == 0:
         return None                                               # Utils.py:1452,1457
     n = len(joint_det)
+    if cc_method == "greedy":
+        persons, taken = greedy_person_construction(np.asarray(joint_det), p_node, ei, pe, p_cls, num_joints)
+        return persons, False, taken                              # Utils.py:505-507
     if cc_method == "threshold":
         rep = threshold_clusters(ei, pe, n)
     else:

@@ -267,6 +267,9 @@ def load_reference_grouping(gaec_fn):
     ns = {"torch": torch, "np": np, "cluster_graph": ccu.cluster_graph, "Graph": _Data,
           "dense_to_sparse": _dense_to_sparse}
     exec(_lift(f"{REF_SRC}/Utils/Utils.py", 36, 40), ns)            # to_numpy
+    if not hasattr(np, "float"):
+        np.float = float                                           # alias used at Utils.py:530, dropped by numpy >= 1.24
+    exec(_lift(f"{REF_SRC}/Utils/Utils.py", 517, 626), ns)          # greedy_person_construction (CC_METHOD "greedy")
     exec(_lift(f"{REF_SRC}/Utils/Utils.py", 499, 514), ns)          # pred_to_person
     exec(_lift(f"{REF_SRC}/Utils/Utils.py", 672, 743), ns)          # graph_cluster_to_persons
     return ns["pred_to_person"], _subgraph

@@ -51,7 +51,8 @@ def group_persons_async(joint_det, node_logits, edge_index, edge_logits, class_l
     batch size is ``batch_index[-1] + 1`` and the counts are read back once.
     """
     if cc_method not in nv.CC_METHODS:
-        raise NotImplementedError("CC_METHOD=%r (GAEC, the reference default, and threshold are in scope)" % (cc_method,))
+        raise NotImplementedError("CC_METHOD=%r (GAEC, the reference default, threshold and greedy are in scope; KL / MUT need "
+                                  "the reference's missing native solver)" % (cc_method,))
     nv.require_cuda(joint_det, "joint_det", torch.int64)
     nv.require_cuda(node_logits, "node_logits", torch.float32)
     nv.require_cuda(edge_index, "edge_index", torch.int64)

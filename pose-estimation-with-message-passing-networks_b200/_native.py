@@ -106,7 +106,7 @@ class MpnTrainParams(C.Structure):
                 ("grad_x", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64)]
 
 
-CC_METHODS = {"GAEC": 0, "threshold": 1}
+CC_METHODS = {"GAEC": 0, "threshold": 1, "greedy": 2}
 
 
 class GroupParams(C.Structure):

@@ -150,9 +150,77 @@ __global__ void __launch_bounds__(kThreads) group_kernel(const pgmp_group_params
     if (s < d) atomicAdd(&mult[(size_t)s * n + d], 1); else s_any_lower = 1;
   }
   __syncthreads();
+  if (tid == 0) p.num_kept_edges[b] = s_kept;
+  if (p.cc_method == PGMP_CC_GREEDY) {
+    // ---- CC_METHOD "greedy" (greedy_person_construction, Utils.py:517-626).  Symmetric float64 adjacency
+    //      (p_ab + p_ba) / 2 with a unit diagonal (:531-534); types in order, within a type the nodes in order: an
+    //      unclaimed node with score >= 0.5 becomes the core of a person and claims, per other type, the node it is
+    //      connected to most strongly -- also one that is already claimed, unless its owner's edge is stronger (:556-583).
+    __shared__ int s_tstart[66];
+    __shared__ int s_ncand;
+    for (size_t i = tid; i < (size_t)n * n; i += kThreads) {
+      const int r = (int)(i / n), c = (int)(i - (size_t)r * n);
+      W[i] = r == c ? 1.0 : ((double)A[i] + (double)A[(size_t)c * n + r]) / 2.0;
+    }
+    for (int i = tid; i < n; i += kThreads) rep[i] = -1;                 // taken_joints
+    int* __restrict__ tlist = comp;                                       // nodes ordered by (type, index)
+    int* __restrict__ order = dirty;                                      // ... those with score >= 0.5: the core candidates
+    if (warp == 0) {
+      int nt = 0, nc = 0;
+      for (int t = 0; t < J; ++t) {
+        if (lane == 0) s_tstart[t] = nt;
+        for (int i0 = 0; i0 < n; i0 += 32) {
+          const int i = i0 + lane;
+          const bool is_t = i < n && typ[i] == t;
+          const bool is_c = is_t && !(pn[i] < 0.5f);
+          const uint32_t mt = __ballot_sync(kFull, is_t), mc = __ballot_sync(kFull, is_c);
+          if (is_t) tlist[nt + __popc(mt & ((1u << lane) - 1u))] = i;
+          if (is_c) order[nc + __popc(mc & ((1u << lane) - 1u))] = i;
+          nt += __popc(mt);
+          nc += __popc(mc);
+        }
+      }
+      if (lane == 0) { s_tstart[J] = nt; s_ncand = nc; }
+    }
+    __syncthreads();
+    const int ncand = s_ncand;
+    for (int k = 0; k < ncand; ++k) {
+      const int i = order[k];
+      // claimed by an earlier core -> not a core itself.  Every thread decides on its own: rep[i] changes in this
+      // iteration only by thread 0 marking i as its own core below (claims go to nodes of other types), which the
+      // test tolerates -- a thread that reads late must not skip the iteration and its barrier.
+      { const int r = rep[i]; if (r != -1 && r != i) continue; }
+      const int t = typ[i];
+      if (tid == 0) rep[i] = i;
+      for (int j = warp; j < J; j += kThreads / 32) {
+        if (j == t) continue;
+        double bv = 0.0;                                                   // masked row: entries of other types are 0 (:566-569)
+        int bi = 0x7fffffff;
+        for (int q = s_tstart[j] + lane; q < s_tstart[j + 1]; q += 32) {
+          const int c = tlist[q];
+          const double v = W[(size_t)i * n + c];
+          if (v > bv || (v == bv && v > 0.0 && c < bi)) { bv = v; bi = c; }   // first maximum
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double ov = __shfl_xor_sync(kFull, bv, o);
+          const int oi = __shfl_xor_sync(kFull, bi, o);
+          if (ov > bv || (ov == bv && ov > 0.0 && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0 && bv != 0.0) {                                      // :570-571 (the target is of another type: never i itself)
+          const int owner = rep[bi];
+          if (owner == -1 || !(W[(size_t)owner * n + bi] > bv)) rep[bi] = i;   // :573-583
+        }
+      }
+      __syncthreads();
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += kThreads) p.person_labels[n0 + i] = rep[i];
+    if (tid == 0) p.num_components[b] = 0;
+  }
   // ---- multicut weights on pairs a < b present in the kept edge list (:221-227)
   const int any_lower = s_any_lower;
-  if (tid == 0) p.num_kept_edges[b] = s_kept;
+  if (p.cc_method != PGMP_CC_GREEDY)
   for (size_t i = tid; i < (size_t)n * n; i += kThreads) {
     const int a = (int)(i / n), c = (int)(i - (size_t)a * n);
     if (a < c && mult[i] > 0) {
@@ -164,7 +232,8 @@ __global__ void __launch_bounds__(kThreads) group_kernel(const pgmp_group_params
     }
   }
   __syncthreads();
-  for (int r = warp; r < n; r += kThreads / 32) rescan_row(W, flags, n, r, best_val, best_col);
+  if (p.cc_method == PGMP_CC_GAEC)
+    for (int r = warp; r < n; r += kThreads / 32) rescan_row(W, flags, n, r, best_val, best_col);
   __syncthreads();
   // ---- CC_METHOD "threshold" (Utils.py:508-509): the kept edges with probability above the edge threshold are the
   //      solution; min-label propagation over the image's edge list + pointer jumping gives every node the smallest
@@ -261,15 +330,17 @@ __global__ void __launch_bounds__(kThreads) group_kernel(const pgmp_group_params
   }
   __syncthreads();
   // ---- component labels in order of the smallest member (scipy connected_components, Utils.py:688-691)
-  if (tid == 0) {
-    int c = 0;
-    for (int i = 0; i < n; ++i)
-      if (rep[i] == i) comp[i] = c++;
-    s_count = c;
-    p.num_components[b] = c;
+  if (p.cc_method != PGMP_CC_GREEDY) {
+    if (tid == 0) {
+      int c = 0;
+      for (int i = 0; i < n; ++i)
+        if (rep[i] == i) comp[i] = c++;
+      s_count = c;
+      p.num_components[b] = c;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += kThreads) p.person_labels[n0 + i] = comp[rep[i]];
   }
-  __syncthreads();
-  for (int i = tid; i < n; i += kThreads) p.person_labels[n0 + i] = comp[rep[i]];
   __syncthreads();
   // ---- persons (Utils.py:692-741): components with more than one node, per type the node with the best score.  Every
   //      node votes for its (component root, type) slot with score bits << 32 | ~node: the largest key is the first
@@ -280,6 +351,7 @@ __global__ void __launch_bounds__(kThreads) group_kernel(const pgmp_group_params
   for (int i = tid; i < n * J; i += kThreads) pkey[i] = 0ull;
   __syncthreads();
   for (int i = tid; i < n; i += kThreads) {
+    if (rep[i] < 0) continue;                                      // greedy: a node no person has claimed
     atomicAdd(&csize[rep[i]], 1);
     const float sc = pn[i] > 0.f ? pn[i] : 0.f;
     atomicMax(&pkey[(size_t)rep[i] * J + typ[i]], ((unsigned long long)__float_as_uint(sc) << 32) | (unsigned long long)(0xffffffffu - (unsigned)i));
@@ -290,7 +362,7 @@ __global__ void __launch_bounds__(kThreads) group_kernel(const pgmp_group_params
     double* __restrict__ out = p.persons + (size_t)b * p.max_persons * J * 3;
     for (int r0 = 0; r0 < n; r0 += 32) {
       const int rr = r0 + lane;
-      const int sz = rr < n && rep[rr] == rr ? csize[rr] : 0;
+      const int sz = rr < n ? csize[rr] : 0;                        // (only cluster ids -- roots / core nodes -- have members)
       if (__any_sync(kFull, sz > J)) mutant = 1;                     // :703-706
       uint32_t roots = __ballot_sync(kFull, sz > 1);                 // :708
       while (roots) {
@@ -318,7 +390,7 @@ __global__ void __launch_bounds__(kThreads) group_kernel(const pgmp_group_params
         if (valid) ++n_person;                                      // :725
       }
     }
-    if (lane == 0) { p.num_persons[b] = n_person; p.mutants[b] = mutant; }
+    if (lane == 0) { p.num_persons[b] = n_person; p.mutants[b] = p.cc_method == PGMP_CC_GREEDY ? 0 : mutant; }   // :506
   }
 }
 

@@ -7,7 +7,7 @@ import re
 import subprocess
 import sys
 
-R = sys.argv[1] if len(sys.argv) > 1 else "r1"
+R = sys.argv[1] if len(sys.argv) > 1 else "r2"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 
@@ -44,7 +44,9 @@ with open(os.path.join(P, f"{R}_launches_summary.txt"), "w") as f:
 
 traffic = {}
 for rep, note in ((f"{R}_edge_step_tc", "dominant kernel: one message-passing step over 929 518 edges (B=32)"),
-                  (f"{R}_nms", "heatmap NMS + candidate extraction over 32 x 17 x 512 x 512 fp32")):
+                  (f"{R}_nms", "heatmap NMS + candidate extraction over 32 x 17 x 512 x 512 fp32"),
+                  (f"{R}_group", "grouping tail (GAEC), one CTA per image, 32 images"),
+                  (f"{R}_gather_features", "node-feature gather from NCHW maps (one 32-byte sector per element)")):
     path = os.path.join(G, rep + ".ncu-rep")
     if not os.path.exists(path):
         continue
@@ -56,7 +58,8 @@ for rep, note in ((f"{R}_edge_step_tc", "dominant kernel: one message-passing st
     def val(k):
         x = float(r[h.index(k)])
         return x * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}[u[h.index(k)]]
-    kname = "edge_step_tc_kernel" if "edge" in rep else "nms_candidates_kernel<R, true>"
+    kname = {"edge_step_tc": "edge_step_tc_kernel", "nms": "nms_candidates_kernel", "group": "group_kernel",
+             "gather_features": "gather_features_kernel"}[rep[len(R) + 1:]]
     traffic[kname] = {"dram_bytes_per_launch": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
                       "edges_per_launch": 929518, "source": f"profiles/{rep}_ncu.txt (ncu --set full, one launch)"}
 json.dump(traffic, open(os.path.join(P, f"{R}_traffic.json"), "w"), indent=1)

@@ -1,3 +1,3 @@
 set -x
-PGMP_EDGE_NOGATHER=1 timeout 300 python scripts/quick_profile.py 32 knn tc > gpurun_out/r2_qp_nogather.txt 2>&1; head -4 gpurun_out/r2_qp_nogather.txt
-timeout 300 python scripts/quick_profile.py 32 knn tc > gpurun_out/r2_qp_base.txt 2>&1; head -3 gpurun_out/r2_qp_base.txt
+for i in 1 2 3; do timeout 900 python -m pytest tests -m gpu -x -q -k "group or pipeline or persons or refine" 2>&1 | tail -1; done
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest23.txt 2>&1; tail -2 gpurun_out/r2_pytest23.txt

@@ -2,7 +2,7 @@
 # Round profile pass (run under gpurun): tests, bench (both arms), ncu launch list, ncu --set full of the two
 # kernels the roofline is reported for.  Outputs go to gpurun_out/ and are summarised into profiles/ afterwards.
 set -u
-R=${1:-r1}
+R=${1:-r2}
 O=gpurun_out
 mkdir -p $O
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -3 > $O/${R}_pytest_gpu.txt
@@ -16,5 +16,9 @@ python scripts/quick_profile.py 32 knn tc > $O/plain_b.log 2>&1 && \
       python scripts/quick_profile.py 32 knn tc > $O/ncu_b.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:nms_candidates -s 2 -c 1 -o $O/${R}_nms \
       python scripts/quick_profile.py 32 knn tc > $O/ncu_c.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:group_kernel -s 1 -c 1 -o $O/${R}_group \
+      python scripts/dbg_group.py 32 > $O/ncu_d.log 2>&1
+ncu --set full --clock-control none -k regex:gather_features -c 1 -o $O/${R}_gather_features \
+      python scripts/quick_profile.py 32 knn tc > $O/ncu_e.log 2>&1
 cat $O/${R}_pytest_gpu.txt
 tail -c 300 $O/${R}_bench.err

@@ -477,6 +477,17 @@ def test_grouping_threshold_method_matches_reference(name, gc_name, seed):
     _check_grouping(g, nj, dict(logits, edge_logits=logits["edge_logits"] * 0.3), 0.1, cc_method="threshold")   # few joins
 
 
+@pytest.mark.parametrize("name,gc_name,seed", [("group_greedy_knn_small", "knn_small", 0), ("group_greedy_fully_small", "fully_small", 1),
+                                               ("group_greedy_crowdpose", "crowdpose", 2)])
+def test_grouping_greedy_method_matches_reference(name, gc_name, seed):
+    """CC_METHOD = "greedy" (greedy_person_construction, Utils.py:517-626): pure numpy in the reference, so the whole
+    grouping is pinned end to end -- fixtures from the reference's own code; labels = the core node that claimed each node."""
+    g, nj = _oracle_graph_for(gc_name)
+    logits = synthetic.synth_group_logits(g["joint_det"], g["batch_index"], g["edge_index"], num_joints=nj, seed=seed)
+    _check_grouping(g, nj, logits, 0.1, gold=golden(name), cc_method="greedy")
+    _check_grouping(g, nj, dict(logits, node_logits=logits["node_logits"] * 0.2), 0.3, cc_method="greedy")   # scores around 0.5
+
+
 @pytest.mark.parametrize("name,gc_name,seed", [("group_knn_small", "knn_small", 0), ("group_fully_small", "fully_small", 1),
                                                ("group_crowdpose", "crowdpose", 2)])
 def test_grouping_bit_exact_on_identical_logits(name, gc_name, seed):
