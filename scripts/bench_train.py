@@ -55,7 +55,7 @@ def run_training(args, rank, world, dev):
     model = synthetic.synth_mpn_state_dict(get_mpn_model(mcfg), 0).to(dev).train()
     opt = torch.optim.Adam(model.parameters(), lr=1e-4)
     gen = torch.Generator(device=dev).manual_seed(rank)
-    ev = {k: [torch.cuda.Event(enable_timing=True) for _ in range(2)] for k in ("gc", "fwd", "bwd", "ar", "step")}
+    ev = {k: [torch.cuda.Event(enable_timing=True) for _ in range(2)] for k in ("gc", "fwd", "loss", "bwd", "ar", "opt", "step")}
     acc = {k: 0.0 for k in ev}
     info = {}
 
@@ -73,18 +73,22 @@ def run_training(args, rank, world, dev):
         ev["fwd"][0].record()
         pe, pn, pc, _ = model(x, edge_attr, edge_index, node_types=joint_det[:, 2])
         ev["fwd"][1].record()
+        ev["loss"][0].record()
         # masked losses on the constructor's labels (stock torch ops standing in for the reference's focal / CE losses)
         loss = (F.binary_cross_entropy_with_logits(pe[-1], edge_labels, weight=label_mask, reduction="sum") / label_mask.sum().clamp(min=1)
                 + F.binary_cross_entropy_with_logits(pn[-1], node_labels, weight=node_mask, reduction="sum") / node_mask.sum().clamp(min=1)
                 + (F.cross_entropy(pc[-1], node_classes, reduction="none") * class_mask).sum() / class_mask.sum().clamp(min=1))
         opt.zero_grad(set_to_none=True)
+        ev["loss"][1].record()
         ev["bwd"][0].record()
         loss.backward()
         ev["bwd"][1].record()
         ev["ar"][0].record()
         info["allreduce_bytes"] = par.allreduce_gradients(model.parameters())
         ev["ar"][1].record()
+        ev["opt"][0].record()
         opt.step()
+        ev["opt"][1].record()
         ev["step"][1].record()
         torch.cuda.synchronize()
         if timed:
