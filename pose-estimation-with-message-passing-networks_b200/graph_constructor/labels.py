@@ -112,12 +112,21 @@ def build_labels(gc, joint_det, edge_index, batch_index, nodes_per_image):
     def one(b):
         return match_image(det_h[offs[b]:offs[b + 1]], gt_h[b], fac_h[b], method, max(H, W), gc.matching_radius,
                            gc.inclusion_radius, gc.include_neighbouring_keypoints)
-    if B > 1:                                               # the images are independent: torch and scipy release the GIL
-        from concurrent.futures import ThreadPoolExecutor
-        with ThreadPoolExecutor(max_workers=min(B, 8)) as pool:
-            matched = list(pool.map(one, range(B)))
-    else:
-        matched = [one(0)]
+    # the images are independent and torch / scipy release the GIL: a few worker threads, each running its tiny tensor
+    # operations single-threaded (intra-op threads on 50 k-element tensors only get in each other's way: measured 2x)
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    intra = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        workers = min(B, 8, max(2, (os.cpu_count() or 4) // 2))
+        if B > 1:
+            with ThreadPoolExecutor(max_workers=workers) as pool:
+                matched = list(pool.map(one, range(B)))
+        else:
+            matched = [one(0)]
+    finally:
+        torch.set_num_threads(intra)
     off = 0
     for b in range(B):
         n = int(nodes_per_image[b])
