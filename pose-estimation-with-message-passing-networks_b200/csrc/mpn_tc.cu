@@ -88,7 +88,7 @@ static_assert(kOffWg % 1024 == 0 && kWgBytes % 1024 == 0 && kWgAdd % 1024 == 0 &
 // through the staging tile, requesting the next tile's features a whole tile early, L2 prefetch of the next tile's rows.
 constexpr int kTgThreads = 256;                 // one tile group = one tile in flight
 constexpr int kEdge2Threads = 2 * kTgThreads;
-constexpr int kWg2Misc = kWgMisc;               // dst[128] prow[128] att[128] wa[64] bars[4] scan[12] seg[16] att1[128]
+constexpr int kWg2Misc = kWgMisc;               // dst[128] cw[128] (int2) wa[64] bars[4] scan[12] seg[16] att0[128] att1[128]
 constexpr int kWg2Bytes = kWgMisc + 3072;
 constexpr size_t kEdge2SmemBytes = kOffWg + 2 * kWg2Bytes + 64 + 1024;
 static_assert(kWg2Bytes % 1024 == 0, "operand tiles must be 1024-byte aligned");
@@ -117,9 +117,8 @@ __global__ void __launch_bounds__(kEdge2Threads, 1) edge_step_tc_kernel(const Ed
   const uint32_t add_a = smem_u32(wgb) + kWgAdd;
   const uint32_t wm_hi = smem_u32(wgb) + kWgWm, wm_lo = wm_hi + kWTile;
   int* s_dst = reinterpret_cast<int*>(wgb + kWg2Misc);
-  int* s_prow = s_dst + kTile;                                // part row stored by the last row of every run, else -1
-  float* s_att = reinterpret_cast<float*>(s_prow + kTile);    // first: half 0's share of the logit, then the softmax weight
-  float* s_wa = s_att + kTile;
+  int2* s_cw = reinterpret_cast<int2*>(s_dst + kTile);        // per row: .x = part row stored by the last row of a run, else -1;
+  float* s_wa = reinterpret_cast<float*>(s_cw + kTile);       //          .y = the row's softmax weight (float bits)
   uint64_t* bar = reinterpret_cast<uint64_t*>(s_wa + kD);   // MMA completions
   uint64_t* g_bar = bar + 1;                                  // bulk load of the edge-feature image
   uint64_t* c_bar = bar + 2;                                  // bulk load of the C image
@@ -127,7 +126,8 @@ __global__ void __launch_bounds__(kEdge2Threads, 1) edge_step_tc_kernel(const Ed
   float* s_wlast = s_wfirst + 4;                              // flags: bit 0 = lane 0 continues the previous warp's run,
   int* s_wflag = reinterpret_cast<int*>(s_wlast + 4);         //        bit 1 = the whole warp is one segment
   int* s_seg = s_wflag + 4;                                   // [16] first row of the k-th row segment of the run reduction
-  float* s_att1 = reinterpret_cast<float*>(s_seg + 16);       // half 1's share of the attention logit
+  float* s_att0 = reinterpret_cast<float*>(s_seg + 16);       // the two column halves' shares of the attention logit
+  float* s_att1 = s_att0 + kTile;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base + kOffWg + 2 * kWg2Bytes);
 
   if (warp == 0) tmem_alloc<kEdgeTmemCols>(tmem_slot);
@@ -216,29 +216,33 @@ __global__ void __launch_bounds__(kEdge2Threads, 1) edge_step_tc_kernel(const Ed
     }
     // ---- P[dst] and Q[src]: this thread's half of its two table rows (swizzled tile images: logical 16-byte chunk q
     //      of node n sits at position q ^ (n & 15)), requested before the first product is waited for, summed on arrival.
-    //      (Gathering the rows cooperatively -- 16 threads per 256-byte row through the staging tile -- was measured:
-    //      the L1 requests drop 8x but the gather latency lands on the tile's critical path, 3.28 ms instead of 2.26 ms
-    //      per 10 steps.)
-    float4 pq[8];
+    //      Pad rows (e < 0) read row 0: finite values that nothing consumes.
+    //      (Measured alternatives, per 10 steps: rows gathered cooperatively -- 16 threads per 256-byte row through the
+    //      staging tile -- 3.28 ms instead of 2.26 ms: the L1 requests drop 8x but the latency lands on the critical
+    //      path; the NEXT tile's rows requested before the run reduction: 2.44 ms (Q only) / 3.38 ms (P and Q, spills)
+    //      instead of 2.14 ms: the requests queue in front of the reduction's shared-memory reads.)
+    float4 pq[8], qv[8];
     {
       const float4* __restrict__ prow = reinterpret_cast<const float4*>(a.tab_p + (size_t)(e >= 0 ? dst : 0) * kD);
       const float4* __restrict__ qrow = reinterpret_cast<const float4*>(a.tab_q + (size_t)(e >= 0 ? src : 0) * kD);
-      const int xd = dst & 15, xs = src & 15;
-      float4 qv[8];
+      const int xd = e >= 0 ? dst & 15 : 0, xs = e >= 0 ? src & 15 : 0;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        pq[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        qv[q] = pq[q];
-        if (e >= 0) { pq[q] = __ldg(prow + ((8 * half + q) ^ xd)); qv[q] = __ldg(qrow + ((8 * half + q) ^ xs)); }
+        pq[q] = __ldg(prow + ((8 * half + q) ^ xd));
+        qv[q] = __ldg(qrow + ((8 * half + q) ^ xs));
       }
-      if (tt < 32 && elect_one()) {        // the edge features have landed: first product
-        mbar_wait(g_bar, ld_phase);
-        fence_after_sync();
-        issue_gemm_x3<kD>(tmem, a_hi, a_lo, 0, w1_hi, w1_lo, 0, 1, false);
-        mma_commit(bar);
-      }
+    }
+    if (tt < 32 && elect_one()) {        // the edge features have landed: first product
+      mbar_wait(g_bar, ld_phase);
+      fence_after_sync();
+      issue_gemm_x3<kD>(tmem, a_hi, a_lo, 0, w1_hi, w1_lo, 0, 1, false);
+      mma_commit(bar);
+    }
 #pragma unroll
-      for (int q = 0; q < 8; ++q) { pq[q].x += qv[q].x; pq[q].y += qv[q].y; pq[q].z += qv[q].z; pq[q].w += qv[q].w; }
+    for (int q = 0; q < 8; ++q) {
+      const float2 lo2 = add2(make_float2(pq[q].x, pq[q].y), make_float2(qv[q].x, qv[q].y));
+      const float2 hi2 = add2(make_float2(pq[q].z, pq[q].w), make_float2(qv[q].z, qv[q].w));
+      pq[q] = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
     }
     if (a.c0) mbar_wait(c_bar, ld_phase);          // the C image sits in the staging tile
     ld_phase ^= 1;
@@ -247,23 +251,21 @@ __global__ void __launch_bounds__(kEdge2Threads, 1) edge_step_tc_kernel(const Ed
     fence_after_sync();
     float d[32];
     tmem_ld32(tmem_row + (uint32_t)c0col, d);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      float4 v = pq[q];
-      if (a.c0) {
-        const float4 c = lds128f(add_a + 4 * stage_index(row, c0col + 4 * q));
-        v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
-      }
-      d[4 * q + 0] = fmaxf(d[4 * q + 0] + v.x, 0.f);
-      d[4 * q + 1] = fmaxf(d[4 * q + 1] + v.y, 0.f);
-      d[4 * q + 2] = fmaxf(d[4 * q + 2] + v.z, 0.f);
-      d[4 * q + 3] = fmaxf(d[4 * q + 3] + v.w, 0.f);
-    }
-    {   // hidden -> tensor memory (TS-form A operand: element k of a row in half k & 1 of column k / 2): this thread's
-        // 32 elements are 16 columns of the hi block (64 ..) and 16 of the lo block (96 ..)
+    {   // hidden = ReLU(acc + C + P + Q) -> tensor memory (TS-form A operand: element k of a row in half k & 1 of column
+        // k / 2): this thread's 32 elements are 16 columns of the hi block (64 ..) and 16 of the lo block (96 ..).
+        // Packed adds; the ReLU is part of the bf16 split.
       uint32_t h[16], l[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) split2(d[2 * i], d[2 * i + 1], h[i], l[i]);
+      for (int q = 0; q < 8; ++q) {
+        float2 v0 = make_float2(pq[q].x, pq[q].y), v1 = make_float2(pq[q].z, pq[q].w);
+        if (a.c0) {
+          const float4 c = lds128f(add_a + 4 * stage_index(row, c0col + 4 * q));
+          v0 = add2(v0, make_float2(c.x, c.y));
+          v1 = add2(v1, make_float2(c.z, c.w));
+        }
+        split2_relu(add2(make_float2(d[4 * q + 0], d[4 * q + 1]), v0), h[2 * q], l[2 * q]);
+        split2_relu(add2(make_float2(d[4 * q + 2], d[4 * q + 3]), v1), h[2 * q + 1], l[2 * q + 1]);
+      }
       tmem_st16(tmem_row + 64 + 16 * half, h);
       tmem_st16(tmem_row + 96 + 16 * half, l);
       tmem_st_wait();
@@ -279,44 +281,39 @@ __global__ void __launch_bounds__(kEdge2Threads, 1) edge_step_tc_kernel(const Ed
     float4 rv[8];
     {
       const float4* __restrict__ rrow = reinterpret_cast<const float4*>(a.tab_r + ((size_t)t * a.N + (e >= 0 ? dst : 0)) * kD);
-      const int xd = dst & 15;
+      const int xd = e >= 0 ? dst & 15 : 0;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        rv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e >= 0) rv[q] = __ldg(rrow + ((8 * half + q) ^ xd));
-      }
+      for (int q = 0; q < 8; ++q) rv[q] = __ldg(rrow + ((8 * half + q) ^ xd));
     }
     mbar_wait(bar, phase);
     phase ^= 1;
     fence_after_sync();
     tmem_ld32(tmem_row + (uint32_t)c0col, d);
-    {
-      float at0 = 0.f, at1 = 0.f, at2 = 0.f, at3 = 0.f;   // four independent chains
-#pragma unroll
-      for (int o = 0; o < 32; o += 4) {
-        d[o + 0] = fmaxf(d[o + 0] + s_b2[c0col + o + 0], 0.f);
-        d[o + 1] = fmaxf(d[o + 1] + s_b2[c0col + o + 1], 0.f);
-        d[o + 2] = fmaxf(d[o + 2] + s_b2[c0col + o + 2], 0.f);
-        d[o + 3] = fmaxf(d[o + 3] + s_b2[c0col + o + 3], 0.f);
-        at0 = fmaf(d[o + 0], s_wa[c0col + o + 0], at0);
-        at1 = fmaf(d[o + 1], s_wa[c0col + o + 1], at1);
-        at2 = fmaf(d[o + 2], s_wa[c0col + o + 2], at2);
-        at3 = fmaf(d[o + 3], s_wa[c0col + o + 3], at3);
-      }
-      (half ? s_att1 : s_att)[row] = (at0 + at1) + (at2 + at3);
-    }
-    {   // g' -> the operand tile (4 of the row's 8 sixteen-byte chunks per thread)
+    {   // g' = ReLU(acc + b2): attention logit share (two packed chains) and the operand tile (4 of the row's 8
+        // sixteen-byte chunks per thread)
+      float2 at0 = make_float2(0.f, 0.f), at1 = at0;
+      const uint32_t b2_a = smem_u32(s_b2) + 4u * (uint32_t)c0col, wa_a = smem_u32(s_wa) + 4u * (uint32_t)c0col;
       const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
       const uint32_t x = (uint32_t)(row & 7);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t h[4], l[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) split2(d[8 * c + 2 * i], d[8 * c + 2 * i + 1], h[i], l[i]);
+        for (int i = 0; i < 2; ++i) {
+          const float4 b = lds128f(b2_a + 32 * c + 16 * i), wv = lds128f(wa_a + 32 * c + 16 * i);
+          float2 v0 = add2(make_float2(d[8 * c + 4 * i + 0], d[8 * c + 4 * i + 1]), make_float2(b.x, b.y));
+          float2 v1 = add2(make_float2(d[8 * c + 4 * i + 2], d[8 * c + 4 * i + 3]), make_float2(b.z, b.w));
+          v0.x = fmaxf(v0.x, 0.f); v0.y = fmaxf(v0.y, 0.f); v1.x = fmaxf(v1.x, 0.f); v1.y = fmaxf(v1.y, 0.f);
+          at0 = fma2(v0, make_float2(wv.x, wv.y), at0);
+          at1 = fma2(v1, make_float2(wv.z, wv.w), at1);
+          split2_pos(v0, h[2 * i], l[2 * i]);
+          split2_pos(v1, h[2 * i + 1], l[2 * i + 1]);
+        }
         const uint32_t off = row_off + (((uint32_t)(4 * half + c) ^ x) << 4);
         sts128(a_hi + off, h[0], h[1], h[2], h[3]);
         sts128(a_lo + off, l[0], l[1], l[2], l[3]);
       }
+      (half ? s_att1 : s_att0)[row] = (at0.x + at0.y) + (at1.x + at1.y);
     }
     fence_before_sync();
     fence_async_smem();
@@ -333,10 +330,10 @@ __global__ void __launch_bounds__(kEdge2Threads, 1) edge_step_tc_kernel(const Ed
     //      maximum logit of every run -- first within the warp (segmented shuffle scan), then across the four warps
     //      through shared memory -- the softmax weight of every row, and for the last row of a run its part row
     if (half == 0) {
-      const float att = att_bias + (s_att[row] + s_att1[row]);
+      const float att = att_bias + (s_att0[row] + s_att1[row]);
       const bool is_start = e < 0 || row == 0 || s_dst[row - 1] != dst;   // invalid rows are runs of their own
       const int lane = row & 31, wq = row >> 5;
-      float run_max = att;
+      float run_max = att, wgt;
       int seg_first = 0, seg_last = 31;
       if (a.attn) {
         const unsigned starts = __ballot_sync(0xffffffffu, is_start);
@@ -363,9 +360,9 @@ __global__ void __launch_bounds__(kEdge2Threads, 1) edge_step_tc_kernel(const Ed
             run_max = fmaxf(run_max, s_wlast[k2]);
             if ((s_wflag[k2] & 3) != 3) break;
           }
-        s_att[row] = e >= 0 ? __expf(att - run_max) : 0.f;
+        wgt = e >= 0 ? __expf(att - run_max) : 0.f;
       } else {
-        s_att[row] = e >= 0 ? 1.f : 0.f;
+        wgt = e >= 0 ? 1.f : 0.f;
       }
       int ctl = -1;
       if (e >= 0 && (row == kTile - 1 || s_dst[row + 1] != dst)) {
@@ -373,7 +370,7 @@ __global__ void __launch_bounds__(kEdge2Threads, 1) edge_step_tc_kernel(const Ed
         ctl = s_gpstart[t] + bin_lp + (tile - (first_slot >> 7));
         if (a.attn) a.part_mx[ctl] = run_max;
       }
-      s_prow[row] = ctl;
+      s_cw[row] = make_int2(ctl, __float_as_int(wgt));
       if (e >= 0 && is_start)      // segment k of the reduction starts at the first run start >= 8 k
         for (int k = row >> 3; k >= 1; --k)
           if (atomicMin(&s_seg[k], row) < row) break;
@@ -384,10 +381,12 @@ __global__ void __launch_bounds__(kEdge2Threads, 1) edge_step_tc_kernel(const Ed
     tmem_ld32(tmem_row + (uint32_t)c0col, d);
     // ---- message m = ReLU(d + R) goes to this thread's half of its staging row (the C row was consumed by the first epilogue)
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
+    for (int q = 0; q < 8; ++q) {
+      const float2 m0 = add2(make_float2(d[4 * q + 0], d[4 * q + 1]), make_float2(rv[q].x, rv[q].y));
+      const float2 m1 = add2(make_float2(d[4 * q + 2], d[4 * q + 3]), make_float2(rv[q].z, rv[q].w));
       sts128f(add_a + 4 * stage_index(row, c0col + 4 * q),
-              make_float4(fmaxf(d[4 * q + 0] + rv[q].x, 0.f), fmaxf(d[4 * q + 1] + rv[q].y, 0.f),
-                          fmaxf(d[4 * q + 2] + rv[q].z, 0.f), fmaxf(d[4 * q + 3] + rv[q].w, 0.f)));
+              make_float4(fmaxf(m0.x, 0.f), fmaxf(m0.y, 0.f), fmaxf(m1.x, 0.f), fmaxf(m1.y, 0.f)));
+    }
     if (a.with_head) {   // head layer 1 epilogue -> A, layer 2 on the tensor cores
       tmem_ld32(tmem_row + 64 + (uint32_t)c0col, d);
 #pragma unroll
@@ -433,39 +432,39 @@ __global__ void __launch_bounds__(kEdge2Threads, 1) edge_step_tc_kernel(const Ed
     //      256-byte rows.  Four rows per batch: the shared-memory reads of a batch precede its dependent arithmetic.
     {
       const int seg = tt >> 4;
-      const uint32_t c4 = (uint32_t)(tt & 15);
+      const uint32_t c4 = (uint32_t)(tt & 15), c4x = c4 << 4;
       const int r_begin = s_seg[seg], r_end = seg == 15 ? kTile : s_seg[seg + 1];
-      const bool use_max = a.aggr == PGMP_AGGR_MAX && !a.attn;
-      const float u0 = use_max ? -INFINITY : 0.f;
-      float se = 0.f;
-      float4 u = make_float4(u0, u0, u0, u0);
-      for (int rb = r_begin; rb < r_end; rb += 4) {
-        int ctl[4];
-        float wv[4];
-        float4 mv[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int r = min(rb + j, kTile - 1);
-          const bool in = rb + j < r_end;
-          ctl[j] = in ? s_prow[r] : -1;
-          wv[j] = in ? s_att[r] : 0.f;
-          mv[j] = lds128f(add_a + (uint32_t)r * 256u + ((c4 ^ (uint32_t)(r & 15)) << 4));
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (use_max) {
-            if (wv[j] > 0.f) {
-              u.x = fmaxf(u.x, mv[j].x); u.y = fmaxf(u.y, mv[j].y); u.z = fmaxf(u.z, mv[j].z); u.w = fmaxf(u.w, mv[j].w);
-            }
-          } else {
-            se += wv[j];
-            u.x = fmaf(wv[j], mv[j].x, u.x); u.y = fmaf(wv[j], mv[j].y, u.y);
-            u.z = fmaf(wv[j], mv[j].z, u.z); u.w = fmaf(wv[j], mv[j].w, u.w);
+      const uint32_t cw_a = smem_u32(s_cw);
+      float* const out = a.part_val + 4 * c4;
+      if (a.aggr == PGMP_AGGR_MAX && !a.attn) {
+        float4 u = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll 2
+        for (int r = r_begin; r < r_end; ++r) {
+          const uint2 cw = lds64(cw_a + 8u * (uint32_t)r);
+          const float4 mv = lds128f(add_a + (uint32_t)r * 256u + ((c4x ^ ((uint32_t)r << 4)) & 0xf0u));
+          if (cw.y != 0u) {     // weight 1 (valid row) or 0 (pad row)
+            u.x = fmaxf(u.x, mv.x); u.y = fmaxf(u.y, mv.y); u.z = fmaxf(u.z, mv.z); u.w = fmaxf(u.w, mv.w);
           }
-          if (ctl[j] >= 0) {
-            *reinterpret_cast<float4*>(a.part_val + (size_t)ctl[j] * kD + 4 * c4) = u;
-            if (a.attn && c4 == 0) a.part_se[ctl[j]] = se;
-            u = make_float4(u0, u0, u0, u0);
+          if ((int)cw.x >= 0) {
+            *reinterpret_cast<float4*>(out + (size_t)cw.x * kD) = u;
+            u = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+          }
+        }
+      } else {
+        float se = 0.f;
+        float2 u0 = make_float2(0.f, 0.f), u1 = u0;
+#pragma unroll 2
+        for (int r = r_begin; r < r_end; ++r) {
+          const uint2 cw = lds64(cw_a + 8u * (uint32_t)r);
+          const float4 mv = lds128f(add_a + (uint32_t)r * 256u + ((c4x ^ ((uint32_t)r << 4)) & 0xf0u));
+          const float wv = __uint_as_float(cw.y);
+          se += wv;
+          u0 = fma2(make_float2(wv, wv), make_float2(mv.x, mv.y), u0);
+          u1 = fma2(make_float2(wv, wv), make_float2(mv.z, mv.w), u1);
+          if ((int)cw.x >= 0) {
+            *reinterpret_cast<float4*>(out + (size_t)cw.x * kD) = make_float4(u0.x, u0.y, u1.x, u1.y);
+            if (a.attn && c4 == 0) a.part_se[cw.x] = se;
+            u0 = make_float2(0.f, 0.f); u1 = u0;
             se = 0.f;
           }
         }

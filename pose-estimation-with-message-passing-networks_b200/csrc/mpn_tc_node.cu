@@ -25,39 +25,6 @@ using namespace umma;
 constexpr int kImage = kTile * kD * 4;   // bytes of one node-tile image: hi tile (16 KB) then lo tile (16 KB)
 constexpr int kHalf = kTile * 128;       // bytes of one [128][64] bf16 tile
 constexpr int kWBlock = kD * 128;        // bytes of one [64][64] bf16 tile
-constexpr int kTmemCols = 64;
-constexpr int kGroups = 4;               // type groups of the node update for large graphs (small graphs: one per type)
-
-struct Setup {
-  uint32_t base;      // shared address of the 1024-aligned payload
-  uint8_t* base_ptr;
-  uint64_t* bar;
-  uint32_t* tmem_slot;
-  uint32_t tmem;
-};
-
-__device__ __forceinline__ Setup setup_cta(uint8_t* raw, size_t payload_bytes) {
-  Setup s;
-  s.base_ptr = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
-  s.base = smem_u32(s.base_ptr);
-  s.bar = reinterpret_cast<uint64_t*>(s.base_ptr + payload_bytes);
-  s.tmem_slot = reinterpret_cast<uint32_t*>(s.bar + 1);
-  if ((threadIdx.x >> 5) == 0) tmem_alloc<kTmemCols>(s.tmem_slot);
-  if (threadIdx.x == 0) {
-    mbar_init(s.bar, 1);
-    fence_barrier_init();
-  }
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  s.tmem = *s.tmem_slot;
-  return s;
-}
-__device__ __forceinline__ void teardown_cta(const Setup& s) {
-  fence_before_sync();
-  __syncthreads();
-  if ((threadIdx.x >> 5) == 0) tmem_dealloc<kTmemCols>(s.tmem);
-}
 
 // asynchronous copy of a [rows][64] bf16 block (row stride src_ld elements) into a SWIZZLE_128B tile
 __device__ __forceinline__ void cp_async_weight_tile(uint32_t tile, const __nv_bfloat16* __restrict__ src, int rows, int src_ld) {
@@ -84,17 +51,19 @@ __global__ void __launch_bounds__(kTile) node_to_image_kernel(const float* __res
 // ------------------------------------------------------------------------------------------------
 // Per-node tables.  Work item = (node tile, output chunk); chunk 0 / 1 are the target / source columns of
 // mlp_edge.0, chunk 2 + t the node columns of message MLP t.  Persistent CTAs (one per SM) walk a contiguous,
-// tile-major range of items.  Warp 4 is the producer: it fetches the A operand ([h0 ; h] tile images) once per tile
+// tile-major range of items.  Warp 8 is the producer: it fetches the A operand ([h0 ; h] tile images) once per tile
 // and the pre-swizzled weight images three items ahead (bulk copies), and issues the products into two alternating
-// TMEM accumulators.  Warps 0-3 are the epilogue: bias, fp32 rows staged as a swizzled tile image, one bulk copy per
-// item into the table (the step kernel gathers 16-byte chunks with the same swizzle).
+// TMEM accumulators.  Warps 0-3 and 4-7 are two epilogue groups, one per accumulator / staging buffer (even and odd
+// items): bias, fp32 rows staged as a swizzled tile image, one bulk copy per item into the table (the step kernel
+// gathers 16-byte chunks with the same swizzle).  One group alone left the tensor pipe 26 % busy: with a single warp per
+// scheduler every latency of the epilogue (bias loads, TMEM load, barrier) was exposed.
 constexpr int kTabA = 2 * kImage;                 // [h0 image][h image]
 constexpr int kTabW = 2 * 2 * kWBlock;            // one weight buffer: 2 K-blocks x (hi, lo)
 constexpr int kTabWBufs = 3;
 constexpr int kTabStage = kTile * kD * 4;
 constexpr size_t kTabPayload = kTabA + kTabWBufs * kTabW + 2 * kTabStage;
 constexpr size_t kTabSmem = kTabPayload + 128 + 1024;
-constexpr int kTabThreads = kTile + 32;
+constexpr int kTabThreads = 2 * kTile + 32;
 
 __global__ void __launch_bounds__(kTabThreads, 1) node_tables_tc_kernel(
     const float* __restrict__ h0_img, const float* __restrict__ h_img, int64_t N, int skip, int per_type, int n_chunks,
@@ -129,8 +98,9 @@ __global__ void __launch_bounds__(kTabThreads, 1) node_tables_tc_kernel(
   const int per = (total_items + gridDim.x - 1) / gridDim.x;
   const int j0 = blockIdx.x * per, j1 = min(j0 + per, total_items);
 
-  if (tid >= kTile && elect_one()) {
-    // ---------------- producer (one elected lane of warp 4) ----------------
+  if (tid >= 2 * kTile) {
+   if (elect_one()) {
+    // ---------------- producer (one elected lane of warp 8) ----------------
     auto issue_w = [&](int j) {                         // weight image of item j -> buffer (j - j0) % 3
       const int i = j - j0, buf = i % kTabWBufs;
       if (i >= kTabWBufs) mbar_wait(w_free + buf, (uint32_t)(i / kTabWBufs - 1) & 1u);
@@ -144,7 +114,6 @@ __global__ void __launch_bounds__(kTabThreads, 1) node_tables_tc_kernel(
     for (int j = j0; j < j1 && j < j0 + kTabWBufs - 1; ++j) issue_w(j);
     for (int j = j0; j < j1; ++j) {
       const int i = j - j0, wb = i % kTabWBufs, db = i & 1;
-      if (j + kTabWBufs - 1 < j1) issue_w(j + kTabWBufs - 1);
       const int tile = j / n_chunks;
       if (tile != cur_tile) {                           // [h0 ; h] (NodeClassificationMPNSimple.py:77) or [h]
         if (i > 0) mbar_wait(d_full + ((i - 1) & 1), (uint32_t)((i - 1) >> 1) & 1u);   // every product on the old tile is done
@@ -162,38 +131,45 @@ __global__ void __launch_bounds__(kTabThreads, 1) node_tables_tc_kernel(
       issue_gemm_x3<kD>(tmem + db * 64, a0, a0 + kHalf, kImage, wbuf + wb * kTabW, wbuf + wb * kTabW + kWBlock, 2 * kWBlock, kb, false);
       mma_commit(d_full + db);
       mma_commit(w_free + wb);
+      // the weight image two items ahead reuses the buffer of item j - 1: requested AFTER this item's product is queued,
+      // so waiting for that buffer does not keep the tensor pipe idle
+      if (j + kTabWBufs - 1 < j1) issue_w(j + kTabWBufs - 1);
     }
-  } else if (tid < kTile) {
-    // ---------------- epilogue ----------------
-    for (int j = j0; j < j1; ++j) {
-      const int i = j - j0, db = i & 1;
+   }
+  } else {
+    // ---------------- epilogue: group eg takes the items with (j - j0) % 2 == eg ----------------
+    const int eg = tid >> 7, row = tid & (kTile - 1);
+    const bool store_lane = (row < 32) && elect_one();  // issues this group's bulk stores (always the same lane)
+    const uint32_t st = stage + eg * kTabStage;
+    for (int j = j0 + eg; j < j1; j += 2) {
+      const int i = j - j0;
       const int c = j % n_chunks, tile = j / n_chunks;
       const float* __restrict__ bias = c == 0 ? (skip ? nullptr : b1) : (c == 1 ? nullptr : bm + (size_t)(per_type ? c - 2 : 0) * kD);
       float* __restrict__ dst = c == 0 ? tab_p : (c == 1 ? tab_q : tab_r + (size_t)(c - 2) * N * kD);
       float4 bv[kD / 4];
 #pragma unroll
       for (int q = 0; q < kD / 4; ++q) bv[q] = bias ? __ldg(reinterpret_cast<const float4*>(bias) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-      mbar_wait(d_full + db, (uint32_t)(i >> 1) & 1u);
+      if (store_lane) bulk_wait_read();                 // this group's previous store has finished reading the staging buffer
+      mbar_wait(d_full + eg, (uint32_t)(i >> 1) & 1u);
       fence_after_sync();
       float d[kD];
-      tmem_ld64(tmem + db * 64, 0, d);
+      tmem_ld64(tmem + eg * 64, 0, d);
       fence_before_sync();
-      mbar_arrive(d_free + db);                         // the accumulator may be overwritten
-      const uint32_t st = stage + db * kTabStage;
+      mbar_arrive(d_free + eg);                         // the accumulator may be overwritten
+      named_bar_sync(1 + eg, kTile);                    // ... and the staging buffer is free
 #pragma unroll
       for (int q = 0; q < kD / 4; ++q)
-        sts128f(st + 4 * stage_index(tid, 4 * q),
+        sts128f(st + 4 * stage_index(row, 4 * q),
                 make_float4(d[4 * q] + bv[q].x, d[4 * q + 1] + bv[q].y, d[4 * q + 2] + bv[q].z, d[4 * q + 3] + bv[q].w));
       fence_async_smem();
-      if (tid < 32 && elect_one()) bulk_wait_read();    // the other staging buffer is free for the next item
-      named_bar_sync(1, kTile);
-      if (tid < 32 && elect_one()) {
+      named_bar_sync(1 + eg, kTile);
+      if (store_lane) {
         const int64_t row0 = (int64_t)tile * kTile;
         const int64_t rows = N - row0 < kTile ? N - row0 : kTile;
         bulk_store(dst + row0 * kD, st, (uint32_t)rows * kD * 4);
       }
     }
-    if (tid < 32 && elect_one()) bulk_wait_all();
+    if (store_lane) bulk_wait_all();
   }
   fence_before_sync();
   __syncthreads();
@@ -207,8 +183,12 @@ __global__ void __launch_bounds__(kTabThreads, 1) node_tables_tc_kernel(
 // shared-memory tile, one type ahead of the merge; the bin bookkeeping is requested two types ahead.  A bin that
 // straddles two tiles of the step kernel (about 3 %) has a second part: its owner thread requests that row and the
 // two (max, sum) pairs into registers together with the prefetch, so no lane pays a dependent chain of loads.
+// The A operand goes to TENSOR memory (TS form, `tcgen05.st` of the bf16 hi / lo pairs) and both it and the weight tile
+// are double-buffered: the product of type t is only waited for when type t + 2 needs its buffers, so the ~1 100-cycle
+// issue-to-completion latency of a product is off the per-type chain (it used to end every iteration).
 constexpr int kUpdRows = kTile * kD * 4;                      // one row buffer: [128][64] fp32, swizzled rows
-constexpr size_t kUpdPayload = 2 * kHalf + 2 * kWBlock + 2 * kUpdRows + kTile * 4;   // A, W, 2 row buffers, part ids
+constexpr size_t kUpdPayload = 2 * 2 * kWBlock + 2 * kUpdRows + kTile * 4;   // 2 x W (hi, lo), 2 row buffers, part ids
+constexpr int kUpdTmemCols = 256;                             // accumulator [0, 64), A operands (hi 32 + lo 32) at 64 and 128
 // Two CTAs per SM need 2 x (this + 1 KB system reservation) <= 228 KB, which leaves no room for alignment slack: the
 // kernel relies on the 1024-byte alignment of the dynamic shared-memory window (declared, and checked with a trap).
 constexpr size_t kUpdSmem = kUpdPayload + 64;
@@ -219,18 +199,29 @@ __global__ void __launch_bounds__(kTile) node_update_tc_kernel(AggrView av, int6
                                                                float* __restrict__ partial) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   if (smem_u32(smem_raw) & 1023u) __trap();                   // no slack is allocated for re-aligning (see kUpdSmem)
-  Setup s = setup_cta(smem_raw, kUpdPayload);
-  const uint32_t a_hi = s.base, a_lo = a_hi + kHalf, w_hi = a_lo + kHalf, w_lo = w_hi + kWBlock;
-  const uint32_t rows = w_lo + kWBlock;                       // buffer i at + i * kUpdRows
-  int* s_part = reinterpret_cast<int*>(s.base_ptr + 2 * kHalf + 2 * kWBlock + 2 * kUpdRows);   // [128] part row or -1
+  const uint32_t wbuf = smem_u32(smem_raw);                   // weight buffer i: hi at + i * 2 * kWBlock, lo + kWBlock
+  const uint32_t rows = wbuf + 2 * 2 * kWBlock;               // row buffer i at + i * kUpdRows
+  int* s_part = reinterpret_cast<int*>(smem_raw + 2 * 2 * kWBlock + 2 * kUpdRows);   // [128] part row or -1
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kUpdPayload);   // [2] product on buffer i complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
   const int tid = threadIdx.x, grp = blockIdx.y;
+  if ((tid >> 5) == 0) tmem_alloc<kUpdTmemCols>(tmem_slot);
+  if (tid == 0) {
+    mbar_init(bars, 1);
+    mbar_init(bars + 1, 1);
+    fence_barrier_init();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_lane = tmem + ((uint32_t)((tid >> 5) * 32) << 16);
   const int per = (T + groups - 1) / groups;
   const int t0 = grp * per, t1 = min(t0 + per, T);
   const int64_t row0 = (int64_t)blockIdx.x * kTile;
   const int64_t row = row0 + tid;
   const int64_t srow = row < N ? row : N - 1;
   const uint32_t r0 = (uint32_t)(tid >> 4), c4 = (uint32_t)(tid & 15);
-  uint32_t phase = 0;
   float u[kD];
 
   struct Bin { int cnt, ls, lp; };
@@ -282,6 +273,12 @@ __global__ void __launch_bounds__(kTile) node_update_tc_kernel(AggrView av, int6
   __syncthreads();
   fetch(t0);
   for (int t = t0; t < t1; ++t) {
+    const int i = t - t0, buf = i & 1;
+    const uint32_t w_hi = wbuf + (uint32_t)buf * 2 * kWBlock, w_lo = w_hi + kWBlock;
+    if (i >= 2) {                                 // the product of type t - 2 has released this weight / operand buffer
+      mbar_wait(bars + buf, (uint32_t)((i >> 1) - 1) & 1u);
+      fence_after_sync();
+    }
     cp_async_weight_tile(w_hi, wu + (size_t)t * 2 * kD * kD, kD, kD);
     cp_async_weight_tile(w_lo, wu + (size_t)t * 2 * kD * kD + kD * kD, kD, kD);
     cp_async_commit();
@@ -327,23 +324,23 @@ __global__ void __launch_bounds__(kTile) node_update_tc_kernel(AggrView av, int6
     } else {
       merge_parts(av, t, srow, N, u);             // a bin of more than 128 edges spread over three or more tiles
     }
-    store_split_row_a(a_hi, a_lo, tid, u);
+    store_split_row_tmem(tmem_lane + 64 + 64 * buf, tmem_lane + 96 + 64 * buf, u);
     fence_before_sync();
     fence_async_smem();
     __syncthreads();
     if (tid < 32 && elect_one()) {
       fence_after_sync();
-      issue_gemm_x3<kD>(s.tmem, a_hi, a_lo, 0, w_hi, w_lo, 0, 1, t > t0);
-      mma_commit(s.bar);
+      issue_gemm_x3_ts<kD>(tmem, tmem + 64 + 64 * buf, tmem + 96 + 64 * buf, w_hi, w_lo, t > t0);
+      mma_commit(bars + buf);
     }
     cur = nxt; nxt = after; x_cur = x_nxt;
-    mbar_wait(s.bar, phase);                      // operand tiles are reused by the next type
-    phase ^= 1;
   }
   cp_async_wait_all();
   if (t1 > t0) {
+    const int last = t1 - t0 - 1;                 // the last commit covers every product issued before it
+    mbar_wait(bars + (last & 1), (uint32_t)(last >> 1) & 1u);
     fence_after_sync();
-    tmem_ld64(s.tmem, 0, u);
+    tmem_ld64(tmem, 0, u);
   } else {
 #pragma unroll
     for (int o = 0; o < kD; ++o) u[o] = 0.f;
@@ -351,7 +348,9 @@ __global__ void __launch_bounds__(kTile) node_update_tc_kernel(AggrView av, int6
   float4* __restrict__ o4 = reinterpret_cast<float4*>(partial + ((size_t)grp * Np + row) * kD);
 #pragma unroll
   for (int q = 0; q < kD / 4; ++q) o4[q] = make_float4(u[4 * q], u[4 * q + 1], u[4 * q + 2], u[4 * q + 3]);
-  teardown_cta(s);
+  fence_before_sync();
+  __syncthreads();
+  if ((tid >> 5) == 0) tmem_dealloc<kUpdTmemCols>(tmem);
 }
 
 // h' = ReLU(sum of the group partials + bias) -> fp32 rows + operand image; node / class heads when reported

@@ -283,6 +283,33 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
   const __nv_bfloat162 l = __floats2bfloat162_rn(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+// packed fp32 pairs (FADD2 / FFMA2 of sm_100: one issue slot for two lanes of arithmetic)
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; add.rn.f32x2 rd, ra, rb; mov.b64 {%0, %1}, rd;}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7};"
+      " fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0, %1}, rd;}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+// ReLU folded into the split: hi = bf16_rz(max(v, 0)) (toward zero, so v - hi >= 0 for v >= 0 and hi = 0 for v < 0),
+// lo = bf16_rn(max(v - hi, 0)).  hi + lo = max(v, 0) to 2^-17 relative (round-to-nearest hi: 2^-18); no FMNMX.
+__device__ __forceinline__ void split2_relu(float2 v, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v.y), "f"(v.x));
+  const float2 r = add2(v, make_float2(-__uint_as_float(hi << 16), -__uint_as_float(hi & 0xffff0000u)));
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r.y), "f"(r.x));
+}
+// the same for values that are already non-negative
+__device__ __forceinline__ void split2_pos(float2 v, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rz.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v.y), "f"(v.x));
+  const float2 r = add2(v, make_float2(-__uint_as_float(hi << 16), -__uint_as_float(hi & 0xffff0000u)));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r.y), "f"(r.x));
+}
 // this thread's 64-wide row as a TS-form A operand: hi pairs -> 32 columns at t_hi, lo pairs -> 32 columns at t_lo
 // (t_* already carry the lane base of the warp)
 __device__ __forceinline__ void store_split_row_tmem(uint32_t t_hi, uint32_t t_lo, const float (&v)[64]) {
