@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libpgmp.so")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("PGMP_NVCC_EXTRA", "").split()
 
 MAX_LAYERS = 6
 GRAPH_KNN, GRAPH_FULLY = 0, 1

@@ -34,6 +34,10 @@ struct MpnWorkspace {
   int32_t* slot_edge;     // [S] caller's edge id or -1
   int32_t* slot_src;      // [S]
   int32_t* slot_dst;      // [S]
+  int2* slot_run;         // [S] tensor-core mode, step-invariant run bookkeeping of the step kernel: .x = part row stored by the
+                          //     last row of a run (else -1), .y = first lane | last lane << 5 of the row's run inside its warp
+                          //     | run start << 10 | valid << 11
+  int32_t* tile_seg;      // [S / 128][32] first row of the k-th row segment of the tile's run reduction
   // features
   float* h0;              // [N][64] node embedding
   float* h;               // [N][64] current node feature
@@ -83,6 +87,8 @@ inline MpnWorkspace carve_mpn(const pgmp_mpn_params& p) {
   w.slot_edge = c.take<int32_t>(w.max_slots);
   w.slot_src = c.take<int32_t>(w.max_slots);
   w.slot_dst = c.take<int32_t>(w.max_slots);
+  w.slot_run = c.take<int2>(p.precision == PGMP_PRECISION_TC ? w.max_slots : 0);
+  w.tile_seg = c.take<int32_t>(p.precision == PGMP_PRECISION_TC ? w.max_slots / kTile * 32 : 0);
   w.h0 = c.take<float>(N * kD);
   w.h = c.take<float>(N * kD);
   const uint64_t Np = round_up<uint64_t>(N, kTile);

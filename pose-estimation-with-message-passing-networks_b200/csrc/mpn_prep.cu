@@ -153,6 +153,57 @@ __global__ void __launch_bounds__(256) finish_bins_kernel(const int64_t* __restr
   }
 }
 
+// Step-invariant run bookkeeping of the tensor-core step kernel, one CTA per 128-slot tile: a run = the consecutive rows
+// of one (type, target) bin inside the tile (pad rows are runs of their own).  Per row: the part row its run is stored to
+// (last row of the run only), the run's extent inside the row's warp (for the segmented maximum of the attention
+// logits); per tile: the rows at which the 32 segments of the run reduction begin (segment k starts at the first run
+// start at or after row 4 k, so that every run is reduced by one thread per column group, rows in order).
+__global__ void __launch_bounds__(kTile) slot_runs_kernel(int64_t N, int T, const int32_t* __restrict__ slot_dst,
+                                                           const int32_t* __restrict__ bin_lstart,
+                                                           const int32_t* __restrict__ bin_lpart,
+                                                           const int32_t* __restrict__ group_start,
+                                                           const int32_t* __restrict__ group_pstart,
+                                                           int2* __restrict__ slot_run, int32_t* __restrict__ tile_seg) {
+  __shared__ unsigned s_mask[4];
+  const int tile = blockIdx.x, row = threadIdx.x, lane = row & 31;
+  const int slot0 = tile * kTile;
+  if (slot0 >= group_start[T]) return;
+  int t = 0;
+  while (t + 1 < T && slot0 >= group_start[t + 1]) ++t;
+  const int64_t sl = (int64_t)slot0 + row;
+  const int dst = slot_dst[sl];
+  const bool valid = dst >= 0;
+  const bool is_start = !valid || row == 0 || slot_dst[sl - 1] != dst;
+  const bool is_last = valid && (row == kTile - 1 || slot_dst[sl + 1] != dst);
+  int ctl = -1;
+  if (is_last) {
+    const int64_t bin = (int64_t)t * N + dst;
+    const int first_slot = group_start[t] + bin_lstart[bin];
+    ctl = group_pstart[t] + bin_lpart[bin] + (tile - (first_slot >> 7));
+  }
+  const unsigned starts = __ballot_sync(kFull, is_start);
+  const unsigned upto = kFull >> (31 - lane);
+  const int seg_first = 31 - __clz((starts | 1u) & upto);
+  const unsigned above = starts & ~upto;
+  const int seg_last = above ? __ffs(above) - 2 : 31;
+  slot_run[sl] = make_int2(ctl, seg_first | seg_last << 5 | (is_start ? 1 << 10 : 0) | (valid ? 1 << 11 : 0));
+  const unsigned vstarts = __ballot_sync(kFull, valid && is_start);
+  if (lane == 0) s_mask[row >> 5] = vstarts;
+  __syncthreads();
+  if (row < 32) {
+    int first = row == 0 ? 0 : kTile;
+    if (row > 0) {
+      const int from = 4 * row;
+      for (int w = from >> 5; w < 4; ++w) {
+        unsigned m = s_mask[w];
+        if (w == (from >> 5)) m &= kFull << (from & 31);
+        if (m) { first = 32 * w + __ffs(m) - 1; break; }
+      }
+    }
+    tile_seg[tile * 32 + row] = first;
+  }
+}
+
 }  // namespace
 
 int mpn_prepare_graph(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t st) {
@@ -178,6 +229,9 @@ int mpn_prepare_graph(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStrea
                 w.node_type, w.bin_lstart, w.group_start, w.bin_cursor, w.slot_edge);
     PGMP_LAUNCH(finish_bins_kernel, (unsigned)ceil_div<int64_t>(bins, 256), 256, 0, st, p.edge_index, E, N, T,
                 w.bin_count, w.bin_lstart, w.group_start, w.slot_edge, w.slot_src, w.slot_dst);
+    if (p.precision == PGMP_PRECISION_TC)
+      PGMP_LAUNCH(slot_runs_kernel, (unsigned)(w.max_slots / kTile), kTile, 0, st, N, T, w.slot_dst, w.bin_lstart,
+                  w.bin_lpart, w.group_start, w.group_pstart, w.slot_run, w.tile_seg);
   }
   return PGMP_OK;
 }

@@ -44,7 +44,8 @@ constexpr int kEdgeTmemCols = 256;         // 2 warpgroups x (message / hidden a
 
 struct EdgeTcArgs {
   const int32_t* slot_edge; const int32_t* slot_src; const int32_t* slot_dst;
-  const int32_t* group_start; const int32_t* group_pstart; const int32_t* bin_lstart; const int32_t* bin_lpart;
+  const int2* slot_run; const int32_t* tile_seg;      // step-invariant run bookkeeping (mpn_prep.cu: slot_runs_kernel)
+  const int32_t* group_start; const int32_t* group_pstart;
   float* g; const float* c0; const float* tab_p; const float* tab_q; const float* tab_r;
   const __nv_bfloat16* w1; const __nv_bfloat16* w2; const __nv_bfloat16* wm;   // [2][64][64], [2][64][64], [Tm][2][64][64]
   const float* b2; const float* wa; const float* ba;
@@ -56,6 +57,7 @@ struct EdgeTcArgs {
   const __nv_bfloat16* wh1; const __nv_bfloat16* wh2;   // [2][64][64], [2][32][64]
   const float* bh1; const float* bh2; const float* wh3; const float* bh3;
   float* edge_logits;
+  int one_group;
 };
 
 // ---- shared-memory map of the edge kernel (offsets from the 1024-aligned base) ----------------------
@@ -88,11 +90,18 @@ static_assert(kOffWg % 1024 == 0 && kWgBytes % 1024 == 0 && kWgAdd % 1024 == 0 &
 // through the staging tile, requesting the next tile's features a whole tile early, L2 prefetch of the next tile's rows.
 constexpr int kTgThreads = 256;                 // one tile group = one tile in flight
 constexpr int kEdge2Threads = 2 * kTgThreads;
-constexpr int kWg2Misc = kWgMisc;               // dst[128] cw[128] (int2) wa[64] bars[4] scan[12] seg[16] att0[128] att1[128]
+constexpr int kWg2Misc = kWgMisc;               // cw[128] (int2) wa[64] bars[4] scan[12] seg[32] att0[128] att1[128]
 constexpr int kWg2Bytes = kWgMisc + 3072;
 constexpr size_t kEdge2SmemBytes = kOffWg + 2 * kWg2Bytes + 64 + 1024;
 static_assert(kWg2Bytes % 1024 == 0, "operand tiles must be 1024-byte aligned");
 static_assert(kEdge2SmemBytes <= 227 * 1024, "edge step: shared memory");
+
+#ifdef PGMP_TIMELINE
+__device__ long long g_step_tl[4][32][32];      // development aid: clock64 at 16 points of a tile, 2 CTAs x 2 tile groups
+#define TL(k) do { if (tl_on && tl_i < 32) g_step_tl[tl_slot][tl_i][k] = clock64(); } while (0)
+#else
+#define TL(k) do { } while (0)
+#endif
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   tmem_ld16(taddr, v);
@@ -116,8 +125,7 @@ __global__ void __launch_bounds__(kEdge2Threads, 1) edge_step_tc_kernel(const Ed
   const uint32_t a_hi = smem_u32(wgb) + kWgA, a_lo = a_hi + kATile;
   const uint32_t add_a = smem_u32(wgb) + kWgAdd;
   const uint32_t wm_hi = smem_u32(wgb) + kWgWm, wm_lo = wm_hi + kWTile;
-  int* s_dst = reinterpret_cast<int*>(wgb + kWg2Misc);
-  int2* s_cw = reinterpret_cast<int2*>(s_dst + kTile);        // per row: .x = part row stored by the last row of a run, else -1;
+  int2* s_cw = reinterpret_cast<int2*>(wgb + kWg2Misc);       // per row: .x = part row stored by the last row of a run, else -1;
   float* s_wa = reinterpret_cast<float*>(s_cw + kTile);       //          .y = the row's softmax weight (float bits)
   uint64_t* bar = reinterpret_cast<uint64_t*>(s_wa + kD);   // MMA completions
   uint64_t* g_bar = bar + 1;                                  // bulk load of the edge-feature image
@@ -125,8 +133,8 @@ __global__ void __launch_bounds__(kEdge2Threads, 1) edge_step_tc_kernel(const Ed
   float* s_wfirst = reinterpret_cast<float*>(bar + 4);        // per warp: max logit of its first / last run segment,
   float* s_wlast = s_wfirst + 4;                              // flags: bit 0 = lane 0 continues the previous warp's run,
   int* s_wflag = reinterpret_cast<int*>(s_wlast + 4);         //        bit 1 = the whole warp is one segment
-  int* s_seg = s_wflag + 4;                                   // [16] first row of the k-th row segment of the run reduction
-  float* s_att0 = reinterpret_cast<float*>(s_seg + 16);       // the two column halves' shares of the attention logit
+  int* s_seg = s_wflag + 4;                                   // [32] first row of the k-th row segment of the run reduction
+  float* s_att0 = reinterpret_cast<float*>(s_seg + 32);       // the two column halves' shares of the attention logit
   float* s_att1 = s_att0 + kTile;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base + kOffWg + 2 * kWg2Bytes);
 
@@ -163,19 +171,35 @@ __global__ void __launch_bounds__(kEdge2Threads, 1) edge_step_tc_kernel(const Ed
   uint8_t* __restrict__ g_img = reinterpret_cast<uint8_t*>(a.g);
 
   const int total_tiles = a.group_start[a.T] >> 7;
+#ifdef PGMP_TIMELINE
+  const int units = a.one_group ? gridDim.x : 2 * gridDim.x;      // development aid: one tile group per SM idle
+  const int per_unit = (total_tiles + units - 1) / units;
+  const int tile_begin = a.one_group ? (tg ? total_tiles : blockIdx.x * per_unit) : (blockIdx.x * 2 + tg) * per_unit;
+#else
   const int units = 2 * gridDim.x;
   const int per_unit = (total_tiles + units - 1) / units;
   const int tile_begin = (blockIdx.x * 2 + tg) * per_unit;
+#endif
   const int tile_end = min(tile_begin + per_unit, total_tiles);
 
-  int n_e = -1, n_src = -1, n_dst = -1;      // per-row indices, prefetched one tile ahead (both halves of a row hold them)
+  int n_src = -1, n_dst = -1, n_seg = 0;     // per-row indices, prefetched one tile ahead (both halves of a row hold them)
+  int2 n_run = make_int2(-1, 0);
   if (tile_begin < tile_end) {
     const int64_t sl = (int64_t)tile_begin * kTile + row;
-    n_e = a.slot_edge[sl]; n_src = a.slot_src[sl]; n_dst = a.slot_dst[sl];
+    n_src = a.slot_src[sl]; n_dst = a.slot_dst[sl]; n_run = a.slot_run[sl];
+    if (tt < 32) n_seg = a.tile_seg[tile_begin * 32 + tt];
   }
   int t = 0;                    // source type of the tile: monotone over the tiles of a tile group
+#ifdef PGMP_TIMELINE
+  const bool tl_on = tt == 0 && !a.with_head && (blockIdx.x == 3 || blockIdx.x == 100);
+  const int tl_slot = (blockIdx.x == 100 ? 2 : 0) + tg;
+#endif
   for (int tile = tile_begin; tile < tile_end; ++tile) {
     const int slot0 = tile * kTile;
+#ifdef PGMP_TIMELINE
+    const int tl_i = tile - tile_begin;
+#endif
+    TL(0);
     while (t + 1 < a.T && slot0 >= s_gstart[t + 1]) ++t;
     const int tm = a.per_type ? t : 0;
     const int col = a.attn == PGMP_ATTN_PER_TYPE ? t : 0;
@@ -189,19 +213,15 @@ __global__ void __launch_bounds__(kEdge2Threads, 1) edge_step_tc_kernel(const Ed
         bulk_load(add_a, a.c0 + (size_t)slot0 * kD, kAddTile, c_bar);
         if (tile + 1 < tile_end) bulk_prefetch_l2(a.c0 + (size_t)(slot0 + kTile) * kD, kAddTile);
       }
+      if (tile + 1 < tile_end) bulk_prefetch_l2(g_img + (size_t)(tile + 1) * (2 * kATile), 2 * kATile);
     }
-    const int e = n_e, src = n_src, dst = n_dst;
-    if (half == 0) s_dst[row] = e >= 0 ? dst : -1;
-    if (tt < 16) s_seg[tt] = tt == 0 ? 0 : kTile;
+    const int src = n_src, dst = n_dst, e = dst;       // pad rows have src = dst = -1
+    const int2 run = n_run;
+    if (tt < 32) s_seg[tt] = n_seg;
     if (tile + 1 < tile_end) {   // next tile's indices
       const int64_t sl = (int64_t)slot0 + kTile + row;
-      n_e = a.slot_edge[sl]; n_src = a.slot_src[sl]; n_dst = a.slot_dst[sl];
-    }
-    int bin_ls = 0, bin_lp = 0;   // where this row's bin starts (slots / parts), used by the last row of a run
-    if (half == 0 && e >= 0) {
-      const int64_t bin = (int64_t)t * a.N + dst;
-      bin_ls = a.bin_lstart[bin];
-      bin_lp = a.bin_lpart[bin];
+      n_src = a.slot_src[sl]; n_dst = a.slot_dst[sl]; n_run = a.slot_run[sl];
+      if (tt < 32) n_seg = a.tile_seg[(tile + 1) * 32 + tt];
     }
     if (tm != cur_tm) {     // all MMAs of the previous tile have completed
       load_weight_tile_a(wm_hi, a.wm + (size_t)tm * 2 * kD * kD, kD, kD, tt, kTgThreads);
@@ -232,6 +252,7 @@ __global__ void __launch_bounds__(kEdge2Threads, 1) edge_step_tc_kernel(const Ed
         qv[q] = __ldg(qrow + ((8 * half + q) ^ xs));
       }
     }
+    TL(1);
     if (tt < 32 && elect_one()) {        // the edge features have landed: first product
       mbar_wait(g_bar, ld_phase);
       fence_after_sync();
@@ -244,11 +265,14 @@ __global__ void __launch_bounds__(kEdge2Threads, 1) edge_step_tc_kernel(const Ed
       const float2 hi2 = add2(make_float2(pq[q].z, pq[q].w), make_float2(qv[q].z, qv[q].w));
       pq[q] = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
     }
+    TL(2);
     if (a.c0) mbar_wait(c_bar, ld_phase);          // the C image sits in the staging tile
     ld_phase ^= 1;
+    TL(3);
     mbar_wait(bar, phase);
     phase ^= 1;
     fence_after_sync();
+    TL(4);
     float d[32];
     tmem_ld32(tmem_row + (uint32_t)c0col, d);
     {   // hidden = ReLU(acc + C + P + Q) -> tensor memory (TS-form A operand: element k of a row in half k & 1 of column
@@ -270,9 +294,11 @@ __global__ void __launch_bounds__(kEdge2Threads, 1) edge_step_tc_kernel(const Ed
       tmem_st16(tmem_row + 96 + 16 * half, l);
       tmem_st_wait();
     }
+    TL(5);
     fence_before_sync();
     named_bar_sync(bar_id, kTgThreads);
-    if (tt < 32 && elect_one()) {
+    TL(6);
+    if (tt >= kTgThreads - 32 && elect_one()) {      // issued by the group's last warp: the others go on to their R rows
       fence_after_sync();
       issue_gemm_x3_ts<kD>(tmem, tmem + 64, tmem + 96, w2_hi, w2_lo, false);
       mma_commit(bar);
@@ -285,9 +311,11 @@ __global__ void __launch_bounds__(kEdge2Threads, 1) edge_step_tc_kernel(const Ed
 #pragma unroll
       for (int q = 0; q < 8; ++q) rv[q] = __ldg(rrow + ((8 * half + q) ^ xd));
     }
+    TL(7);
     mbar_wait(bar, phase);
     phase ^= 1;
     fence_after_sync();
+    TL(8);
     tmem_ld32(tmem_row + (uint32_t)c0col, d);
     {   // g' = ReLU(acc + b2): attention logit share (two packed chains) and the operand tile (4 of the row's 8
         // sixteen-byte chunks per thread)
@@ -315,41 +343,40 @@ __global__ void __launch_bounds__(kEdge2Threads, 1) edge_step_tc_kernel(const Ed
       }
       (half ? s_att1 : s_att0)[row] = (at0.x + at0.y) + (at1.x + at1.y);
     }
+    TL(9);
     fence_before_sync();
     fence_async_smem();
     named_bar_sync(bar_id, kTgThreads);
-    if (tt < 32 && elect_one()) {
+    TL(10);
+    if (tt >= kTile && tt < kTile + 32 && elect_one()) {   // issued by a warp of column half 1: half 0 runs the scan meanwhile
       fence_after_sync();
       issue_gemm_x3<kD>(tmem, a_hi, a_lo, 0, wm_hi, wm_lo, 0, 1, false);
       if (a.with_head) issue_gemm_x3<kD>(tmem + 64, a_hi, a_lo, 0, wh1_hi, wh1_lo, 0, 1, false);
       mma_commit(bar);
     }
     // ---- write back g' as the bf16 hi/lo tile image (what the next step's MMA consumes): one bulk copy
+    TL(16);
     if (copier_warp && elect_one()) bulk_store(g_img + (size_t)tile * (2 * kATile), a_hi, 2 * kATile);
     // ---- runs of equal targets (a bin, or the part of it inside this tile), handled by the half-0 thread of every row:
     //      maximum logit of every run -- first within the warp (segmented shuffle scan), then across the four warps
     //      through shared memory -- the softmax weight of every row, and for the last row of a run its part row
     if (half == 0) {
       const float att = att_bias + (s_att0[row] + s_att1[row]);
-      const bool is_start = e < 0 || row == 0 || s_dst[row - 1] != dst;   // invalid rows are runs of their own
       const int lane = row & 31, wq = row >> 5;
       float run_max = att, wgt;
-      int seg_first = 0, seg_last = 31;
       if (a.attn) {
-        const unsigned starts = __ballot_sync(0xffffffffu, is_start);
-        const unsigned upto = 0xffffffffu >> (31 - lane);
-        seg_first = 31 - __clz((starts | 1u) & upto);
-        const unsigned above = starts & ~upto;
-        seg_last = above ? __ffs(above) - 2 : 31;
+        const int seg_first = run.y & 31, seg_last = (run.y >> 5) & 31;
 #pragma unroll
         for (int dd = 1; dd < 32; dd <<= 1) {
           const float o = __shfl_down_sync(0xffffffffu, run_max, dd);
           if (lane + dd <= seg_last) run_max = fmaxf(run_max, o);
         }
         run_max = __shfl_sync(0xffffffffu, run_max, seg_first);
-        if (lane == 0) { s_wfirst[wq] = run_max; s_wflag[wq] = (is_start ? 0 : 1) | (seg_last == 31 ? 2 : 0); }
+        if (lane == 0) { s_wfirst[wq] = run_max; s_wflag[wq] = ((run.y >> 10) & 1 ? 0 : 1) | (seg_last == 31 ? 2 : 0); }
         if (lane == 31) s_wlast[wq] = run_max;
+        TL(17);
         named_bar_sync(scan_bar_id, kTile);
+        TL(18);
         if (seg_last == 31)        // the run may continue in the following warps
           for (int k2 = wq + 1; k2 < 4 && (s_wflag[k2] & 1); ++k2) {
             run_max = fmaxf(run_max, s_wfirst[k2]);
@@ -361,23 +388,29 @@ __global__ void __launch_bounds__(kEdge2Threads, 1) edge_step_tc_kernel(const Ed
             if ((s_wflag[k2] & 3) != 3) break;
           }
         wgt = e >= 0 ? __expf(att - run_max) : 0.f;
+        if (run.x >= 0) a.part_mx[run.x] = run_max;
       } else {
         wgt = e >= 0 ? 1.f : 0.f;
       }
-      int ctl = -1;
-      if (e >= 0 && (row == kTile - 1 || s_dst[row + 1] != dst)) {
-        const int first_slot = s_gstart[t] + bin_ls;
-        ctl = s_gpstart[t] + bin_lp + (tile - (first_slot >> 7));
-        if (a.attn) a.part_mx[ctl] = run_max;
-      }
-      s_cw[row] = make_int2(ctl, __float_as_int(wgt));
-      if (e >= 0 && is_start)      // segment k of the reduction starts at the first run start >= 8 k
-        for (int k = row >> 3; k >= 1; --k)
-          if (atomicMin(&s_seg[k], row) < row) break;
+      TL(19);
+      s_cw[row] = make_int2(run.x, __float_as_int(wgt));
+      TL(20);
     }
+    TL(11);
     mbar_wait(bar, phase);
     phase ^= 1;
     fence_after_sync();
+    TL(12);
+    // the operand tiles are free (no head): fetch the next tile's edge features behind the third epilogue and the reduction
+    g_issued = false;
+    if (!a.with_head && tile + 1 < tile_end) {
+      if (copier_warp && elect_one()) {
+        bulk_wait_read();
+        mbar_expect_tx(g_bar, 2 * kATile);
+        bulk_load(a_hi, g_img + (size_t)(tile + 1) * (2 * kATile), 2 * kATile, g_bar);
+      }
+      g_issued = true;
+    }
     tmem_ld32(tmem_row + (uint32_t)c0col, d);
     // ---- message m = ReLU(d + R) goes to this thread's half of its staging row (the C row was consumed by the first epilogue)
 #pragma unroll
@@ -415,56 +448,59 @@ __global__ void __launch_bounds__(kEdge2Threads, 1) edge_step_tc_kernel(const Ed
         mma_commit(bar);
       }
     } else {
+      TL(13);
       named_bar_sync(bar_id, kTgThreads);
+      TL(14);
     }
-    // the operand tiles are free (no head): fetch the next tile's edge features behind the reduction
-    g_issued = false;
-    if (!a.with_head && tile + 1 < tile_end) {
-      if (copier_warp && elect_one()) {
-        bulk_wait_read();
-        mbar_expect_tx(g_bar, 2 * kATile);
-        bulk_load(a_hi, g_img + (size_t)(tile + 1) * (2 * kATile), 2 * kATile, g_bar);
-      }
-      g_issued = true;
-    }
-    // ---- reduce every run: thread = (4 columns, one of 16 row segments); the segments meet at run boundaries, so
-    //      every run is reduced by one thread per column quad, rows in order (deterministic), results stored as
-    //      256-byte rows.  Four rows per batch: the shared-memory reads of a batch precede its dependent arithmetic.
+    TL(21);
+    // ---- reduce every run: thread = (two column quads c8 and c8 + 8, one of 32 row segments); the segments meet at run
+    //      boundaries (tile_seg), so every run is reduced by one thread per column group, rows in order (deterministic),
+    //      results stored as 256-byte part rows.
     {
-      const int seg = tt >> 4;
-      const uint32_t c4 = (uint32_t)(tt & 15), c4x = c4 << 4;
-      const int r_begin = s_seg[seg], r_end = seg == 15 ? kTile : s_seg[seg + 1];
+      const int seg = tt >> 3;
+      const uint32_t c8x = (uint32_t)(tt & 7) << 4;
+      const int r_begin = s_seg[seg], r_end = seg == 31 ? kTile : s_seg[seg + 1];
       const uint32_t cw_a = smem_u32(s_cw);
-      float* const out = a.part_val + 4 * c4;
+      float* const out = a.part_val + 4 * (tt & 7);
       if (a.aggr == PGMP_AGGR_MAX && !a.attn) {
-        float4 u = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        float4 u = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), v = u;
 #pragma unroll 2
         for (int r = r_begin; r < r_end; ++r) {
           const uint2 cw = lds64(cw_a + 8u * (uint32_t)r);
-          const float4 mv = lds128f(add_a + (uint32_t)r * 256u + ((c4x ^ ((uint32_t)r << 4)) & 0xf0u));
+          const uint32_t ra = add_a + (uint32_t)r * 256u, x = ((uint32_t)r << 4) & 0xf0u;
+          const float4 m0 = lds128f(ra + (c8x ^ x)), m1 = lds128f(ra + ((c8x | 0x80u) ^ x));
           if (cw.y != 0u) {     // weight 1 (valid row) or 0 (pad row)
-            u.x = fmaxf(u.x, mv.x); u.y = fmaxf(u.y, mv.y); u.z = fmaxf(u.z, mv.z); u.w = fmaxf(u.w, mv.w);
+            u.x = fmaxf(u.x, m0.x); u.y = fmaxf(u.y, m0.y); u.z = fmaxf(u.z, m0.z); u.w = fmaxf(u.w, m0.w);
+            v.x = fmaxf(v.x, m1.x); v.y = fmaxf(v.y, m1.y); v.z = fmaxf(v.z, m1.z); v.w = fmaxf(v.w, m1.w);
           }
           if ((int)cw.x >= 0) {
-            *reinterpret_cast<float4*>(out + (size_t)cw.x * kD) = u;
-            u = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            float* o = out + (size_t)cw.x * kD;
+            *reinterpret_cast<float4*>(o) = u;
+            *reinterpret_cast<float4*>(o + 32) = v;
+            u = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY); v = u;
           }
         }
       } else {
         float se = 0.f;
-        float2 u0 = make_float2(0.f, 0.f), u1 = u0;
+        float2 u0 = make_float2(0.f, 0.f), u1 = u0, v0 = u0, v1 = u0;
 #pragma unroll 2
         for (int r = r_begin; r < r_end; ++r) {
           const uint2 cw = lds64(cw_a + 8u * (uint32_t)r);
-          const float4 mv = lds128f(add_a + (uint32_t)r * 256u + ((c4x ^ ((uint32_t)r << 4)) & 0xf0u));
+          const uint32_t ra = add_a + (uint32_t)r * 256u, x = ((uint32_t)r << 4) & 0xf0u;
+          const float4 m0 = lds128f(ra + (c8x ^ x)), m1 = lds128f(ra + ((c8x | 0x80u) ^ x));
           const float wv = __uint_as_float(cw.y);
+          const float2 w2 = make_float2(wv, wv);
           se += wv;
-          u0 = fma2(make_float2(wv, wv), make_float2(mv.x, mv.y), u0);
-          u1 = fma2(make_float2(wv, wv), make_float2(mv.z, mv.w), u1);
+          u0 = fma2(w2, make_float2(m0.x, m0.y), u0);
+          u1 = fma2(w2, make_float2(m0.z, m0.w), u1);
+          v0 = fma2(w2, make_float2(m1.x, m1.y), v0);
+          v1 = fma2(w2, make_float2(m1.z, m1.w), v1);
           if ((int)cw.x >= 0) {
-            *reinterpret_cast<float4*>(out + (size_t)cw.x * kD) = make_float4(u0.x, u0.y, u1.x, u1.y);
-            if (a.attn && c4 == 0) a.part_se[cw.x] = se;
-            u0 = make_float2(0.f, 0.f); u1 = u0;
+            float* o = out + (size_t)cw.x * kD;
+            *reinterpret_cast<float4*>(o) = make_float4(u0.x, u0.y, u1.x, u1.y);
+            *reinterpret_cast<float4*>(o + 32) = make_float4(v0.x, v0.y, v1.x, v1.y);
+            if (a.attn && (tt & 7) == 0) a.part_se[cw.x] = se;
+            u0 = make_float2(0.f, 0.f); u1 = u0; v0 = u0; v1 = u0;
             se = 0.f;
           }
         }
@@ -480,9 +516,10 @@ __global__ void __launch_bounds__(kEdge2Threads, 1) edge_step_tc_kernel(const Ed
         float logit = __ldg(a.bh3);
 #pragma unroll
         for (int o = 0; o < 32; ++o) logit = fmaf(fmaxf(hv[o] + s_bh2[o], 0.f), s_wh3[o], logit);
-        if (e >= 0) a.edge_logits[e] = logit;
+        if (e >= 0) a.edge_logits[a.slot_edge[slot0 + row]] = logit;
       }
     }
+    TL(15);
     fence_before_sync();
     named_bar_sync(bar_id, kTgThreads);   // the next tile overwrites the staging / operand tiles
   }
@@ -679,7 +716,8 @@ int mpn_forward_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   EdgeTcArgs a;
   a.slot_edge = w.slot_edge; a.slot_src = w.slot_src; a.slot_dst = w.slot_dst;
-  a.group_start = w.group_start; a.group_pstart = w.group_pstart; a.bin_lstart = w.bin_lstart; a.bin_lpart = w.bin_lpart;
+  a.slot_run = w.slot_run; a.tile_seg = w.tile_seg;
+  a.group_start = w.group_start; a.group_pstart = w.group_pstart;
   a.g = w.g; a.c0 = p.skip ? w.c0 : nullptr; a.tab_p = w.tab_p; a.tab_q = w.tab_q; a.tab_r = w.tab_r;
   a.w1 = static_cast<const __nv_bfloat16*>(p.tc_w1_e); a.w2 = static_cast<const __nv_bfloat16*>(p.tc_w2);
   a.wm = static_cast<const __nv_bfloat16*>(p.tc_wm_e);
@@ -695,7 +733,13 @@ int mpn_forward_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t
   a.wh1 = static_cast<const __nv_bfloat16*>(p.tc_wh1); a.wh2 = static_cast<const __nv_bfloat16*>(p.tc_wh2);
   a.bh1 = eh.bias[0]; a.bh2 = eh.bias[1]; a.wh3 = eh.wt[2]; a.bh3 = eh.bias[2];
   const unsigned max_units = (unsigned)ceil_div<uint64_t>(w.max_slots / kTile, 2);
-  const unsigned grid = max_units < (unsigned)sms ? max_units : (unsigned)sms;
+  unsigned grid = max_units < (unsigned)sms ? max_units : (unsigned)sms;
+#ifdef PGMP_TIMELINE
+  if (const char* gs = getenv("PGMP_STEP_GRID")) grid = (unsigned)atoi(gs);      // development aid: scaling experiments
+  a.one_group = getenv("PGMP_STEP_ONE_GROUP") != nullptr;
+#else
+  a.one_group = 0;
+#endif
   const int first_out = p.steps - p.aux_loss_steps - 1 > 0 ? p.steps - p.aux_loss_steps - 1 : 0;
   for (int s = 0; s < p.steps; ++s) {
     if (s > 0) {
@@ -715,6 +759,12 @@ int mpn_forward_tc(const pgmp_mpn_params& p, const MpnWorkspace& w, cudaStream_t
 }
 
 }  // namespace pgmp
+
+#ifdef PGMP_TIMELINE
+extern "C" int pgmp_debug_step_timeline(long long* out) {
+  return cudaMemcpyFromSymbol(out, pgmp::g_step_tl, sizeof(long long) * 4 * 32 * 32) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 extern "C" int pgmp_selftest_umma(const float* a, const float* w, float* d, pgmp_stream_t stream) {
   using namespace pgmp;

@@ -1,2 +1,6 @@
-timeout 900 python -m pytest tests -m gpu -x -q -k "mpn or tensor or full or smoke or pipelined" 2>&1 | tail -8
-timeout 300 python scripts/quick_profile.py 32 knn tc > gpurun_out/r2_qp_v3b.txt 2>&1; head -8 gpurun_out/r2_qp_v3b.txt
+export PGMP_NVCC_EXTRA=-DPGMP_TIMELINE
+timeout 900 python -m pytest tests -m gpu -x -q -k "mpn or tensor or full or smoke or pipelined" 2>&1 | tail -3
+timeout 300 python scripts/quick_profile.py 32 knn tc 2>&1 | sed -n 1,4p
+timeout 300 python scripts/step_timeline.py 2>&1 | grep -A8 "CTA 3 tile group 0"
+PGMP_STEP_ONE_GROUP=1 timeout 300 python scripts/quick_profile.py 32 knn tc 2>&1 | sed -n 2,2p
+PGMP_STEP_ONE_GROUP=1 timeout 300 python scripts/step_timeline.py 2>&1 | grep -A8 "CTA 3 tile group 0"
