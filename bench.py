@@ -428,10 +428,15 @@ def run_b200(args, rank, local_rank, world):
         del feat, tags, sm
         torch.cuda.empty_cache()
         r = bt.run_training(bt.parse(["--steps", "5", "--warmup", "3"]), rank, world, dev)
+        keys = ("value", "unit", "ms_per_step", "ms", "edges_per_s", "config", "allreduce_bytes", "gpu_launches")
         if rank == 0:
-            train = {k: r[k] for k in ("value", "unit", "ms_per_step", "ms", "edges_per_s", "config", "allreduce_bytes", "gpu_launches")}
+            train = {k: r[k] for k in keys}
+        # the same step with the flagship per-type / attention layer (TypeAwareMPNLayer, the hybrid_* configs)
+        r = bt.run_training(bt.parse(["--steps", "5", "--warmup", "3", "--model", "flagship"]), rank, world, dev)
+        if rank == 0:
+            train["flagship"] = {k: r[k] for k in keys}
     except Exception as exc:      # the headline line must not depend on the training row
-        train = {"error": "%s: %s" % (type(exc).__name__, exc)}
+        train = dict(train or {}, error="%s: %s" % (type(exc).__name__, exc))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

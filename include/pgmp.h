@@ -308,6 +308,14 @@ typedef struct pgmp_mpn_train_params {
   float* grad_x;                           /* out [N, node_emb.dims[0]] or NULL */
   void* workspace;                         /* device, pgmp_mpn_train_workspace_bytes() bytes, 256-B aligned; must survive from forward to backward */
   uint64_t workspace_bytes;
+  /* TypeAwareMPNLayer (layers.py:157-274), per_type != 0: wm / bm are mlp_node.mlp.0.0 [64][nd + 64] and matrix t sits
+   * wm_type_stride elements further (17 matrices); wu is update_mlp.0 [64][num_types * 64]; attn = PGMP_ATTN_* with
+   * attn_net.0 = wa [1 or 17][64], ba.  Both calls wait for the stream once (the sizes of the 17 source-type groups
+   * are read back: the per-type products are launched per group). */
+  int32_t per_type, num_types, attn, reserved_;
+  const int64_t* node_types;               /* device [N], values in [0, num_types) (after NODE_TYPE_SUMMARY) */
+  int64_t wm_type_stride;
+  int64_t wa, ba;
 } pgmp_mpn_train_params;
 
 uint64_t pgmp_mpn_train_workspace_bytes(const pgmp_mpn_train_params* p);

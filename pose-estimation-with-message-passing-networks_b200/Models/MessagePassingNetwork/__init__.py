@@ -124,7 +124,7 @@ class _MpnTrainFunction(torch.autograd.Function):
     stand where torch autograd runs the reference's Python forward (train.py:232-236)."""
 
     @staticmethod
-    def forward(ctx, model, x, edge_attr, edge_index, *params):
+    def forward(ctx, model, x, edge_attr, edge_index, node_types, *params):
         names = [n for n, _ in model.named_parameters()]
         dev = x.device
         lib = nv.lib()
@@ -160,7 +160,17 @@ class _MpnTrainFunction(torch.autograd.Function):
             setattr(p, field, _mlp_train_struct(getattr(model, name), name, offsets))
         p.w1, p.b1 = offsets["mpn_node_cls.mlp_edge.0.weight"], offsets["mpn_node_cls.mlp_edge.0.bias"]
         p.w2, p.b2 = offsets["mpn_node_cls.mlp_edge.2.weight"], offsets["mpn_node_cls.mlp_edge.2.bias"]
-        p.wm, p.bm = offsets["mpn_node_cls.mlp_node.0.weight"], offsets["mpn_node_cls.mlp_node.0.bias"]
+        nt = None
+        if model.aggr_type == "per_type":          # TypeAwareMPNLayer: 17 message matrices, attention, update over all types
+            nt = node_types.detach().contiguous()
+            p.per_type, p.num_types, p.attn = 1, layer.num_types, nv.ATTN[layer.aggr_sub]
+            p.node_types = nt.data_ptr()
+            p.wm, p.bm = offsets["mpn_node_cls.mlp_node.mlp.0.0.weight"], offsets["mpn_node_cls.mlp_node.mlp.0.0.bias"]
+            p.wm_type_stride = offsets["mpn_node_cls.mlp_node.mlp.1.0.weight"] - p.wm
+            if layer.attn_net is not None:
+                p.wa, p.ba = offsets["mpn_node_cls.attn_net.0.weight"], offsets["mpn_node_cls.attn_net.0.bias"]
+        else:
+            p.wm, p.bm = offsets["mpn_node_cls.mlp_node.0.weight"], offsets["mpn_node_cls.mlp_node.0.bias"]
         if layer.update_mlp is not None:
             p.wu, p.bu = offsets["mpn_node_cls.update_mlp.0.weight"], offsets["mpn_node_cls.update_mlp.0.bias"]
         with torch.cuda.device(dev):
@@ -197,7 +207,7 @@ class _MpnTrainFunction(torch.autograd.Function):
                 mod.num_batches_tracked += 1
         ctx.p, ctx.sizes, ctx.shapes = p, sizes, [tuple(q.shape) for q in params]
         ctx.offsets = [offsets[n] for n in names]
-        ctx.keep = (flat, x_, ea, ei, ws, edge_logits, node_logits, class_logits)   # the forward's activations live in ws
+        ctx.keep = (flat, x_, ea, ei, ws, edge_logits, node_logits, class_logits) + ((nt,) if nt is not None else ())   # the forward's activations live in ws
         ctx.pool, ctx.owners = pool, owners
         ctx.need_x = x.requires_grad
         return edge_logits, node_logits, class_logits
@@ -223,7 +233,7 @@ class _MpnTrainFunction(torch.autograd.Function):
         out = [grads[off:off + k].view(shape) for off, k, shape in zip(ctx.offsets, ctx.sizes, ctx.shapes)]
         if len(ctx.pool) < 2 and not any(e[1] is ctx.keep[4] for e in ctx.pool):
             ctx.pool.append((torch.cuda.current_stream().cuda_stream, ctx.keep[4]))   # stream-ordered reuse
-        return (None, grad_x, None, None) + tuple(out)
+        return (None, grad_x, None, None, None) + tuple(out)
 
 
 class NodeClassificationMPNSimple(nn.Module):
@@ -455,9 +465,15 @@ class NodeClassificationMPNSimple(nn.Module):
 
 def _forward_train(self, x, edge_attr, edge_index, **kwargs):
     """``train()`` mode: BatchNorm batch statistics, activations kept for the reverse pass."""
-    if self.aggr_type != "agnostic":
-        raise NotImplementedError("training kernels cover the type-agnostic MPLayer (class_agnostic_end2end configs); "
-                                  "AGGR_TYPE=%r trains with the reference for now" % (self.aggr_type,))
+    node_types = None
+    if self.aggr_type == "per_type":
+        if self.mpn_node_cls.update_type != "mlp":
+            raise NotImplementedError("training kernels cover UPDATE_TYPE mlp; %r trains with the reference for now"
+                                      % (self.mpn_node_cls.update_type,))
+        node_types = sum_node_types(self.node_summary, kwargs["node_types"])          # :64
+        nv.require_cuda(node_types, "node_types", torch.int64)
+        if node_types.shape[0] != x.shape[0]:
+            raise ValueError("node_types must be [N]")
     if self.node_steps != 0 or self.edge_steps < 1:
         raise NotImplementedError("NODE_STEPS != 0 / STEPS < 1")
     nv.require_cuda(x, "x", torch.float32)
@@ -473,7 +489,7 @@ def _forward_train(self, x, edge_attr, edge_index, **kwargs):
     params = [p for _, p in self.named_parameters()]
     for p in params:
         nv.require_cuda(p, "parameter", torch.float32)
-    edge_logits, node_logits, class_logits = _MpnTrainFunction.apply(self, x, edge_attr, edge_index, *params)
+    edge_logits, node_logits, class_logits = _MpnTrainFunction.apply(self, x, edge_attr, edge_index, node_types, *params)
     n_out = self.num_outputs()
     preds_edge = [edge_logits[i].squeeze() for i in range(n_out)]
     preds_node = [node_logits[i].squeeze() for i in range(n_out)]

@@ -103,7 +103,9 @@ class MpnTrainParams(C.Structure):
                 ("bm", C.c_int64), ("wu", C.c_int64), ("bu", C.c_int64),
                 ("edge_logits", C.c_void_p), ("node_logits", C.c_void_p), ("class_logits", C.c_void_p),
                 ("d_edge_logits", C.c_void_p), ("d_node_logits", C.c_void_p), ("d_class_logits", C.c_void_p),
-                ("grad_x", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64)]
+                ("grad_x", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64),
+                ("per_type", C.c_int32), ("num_types", C.c_int32), ("attn", C.c_int32), ("reserved_", C.c_int32),
+                ("node_types", C.c_void_p), ("wm_type_stride", C.c_int64), ("wa", C.c_int64), ("ba", C.c_int64)]
 
 
 CC_METHODS = {"GAEC": 0, "threshold": 1, "greedy": 2}

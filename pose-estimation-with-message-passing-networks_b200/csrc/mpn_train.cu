@@ -173,6 +173,7 @@ struct FwdArgs {
   int relu;
   float* Y;
   int ldy;
+  int add1_ld;      // row stride of add1 (64, or num_types * 64 for the per-type tables)
 };
 
 template <bool VEC>
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(256) lin_fwd_kernel(const FwdArgs q) {
   for (int h = 0; h < 2; ++h) {
     const int64_t gr = r0 + wr + g + 8 * h;
     if (gr >= q.M) continue;
-    const float* e1 = q.add1 ? q.add1 + q.idx1[gr] * kD : nullptr;
+    const float* e1 = q.add1 ? q.add1 + q.idx1[gr] * q.add1_ld : nullptr;
     const float* e2 = q.add2 ? q.add2 + q.idx2[gr] * kD : nullptr;
 #pragma unroll
     for (int nb = 0; nb < 4; ++nb)
@@ -539,6 +540,174 @@ __global__ void __launch_bounds__(256) aggregate_bwd_kernel(const float* __restr
   }
 }
 
+
+// ------------------------------------------------------------------ per-type layer (TypeAwareMPNLayer, layers.py:157-274)
+// Everything per edge is order-agnostic, so the per-type step runs in a TYPE-SORTED edge order (stable counting sort of
+// the edges by the type of their source node): rows [type_ptr[t], type_ptr[t + 1]) use the message matrix of type t, only
+// the edge logits and their gradients are (un)permuted.  Per-(target, type) bins (key = target * T + type, so that the bin
+// index is the row of the [N][T * 64] update input) carry the attention softmax and the aggregation.
+constexpr int kSortBlock = 1024;
+constexpr int kMaxTypes = 17;
+
+__global__ void __launch_bounds__(256) edge_type_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ node_types,
+                                                         int64_t E, int64_t N, int T, int32_t* __restrict__ etype,
+                                                         int32_t* __restrict__ bad) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int64_t j = src[e];
+  int t = 0;
+  if (j < 0 || j >= N) { *bad = 1; } else {
+    const int64_t v = node_types[j];
+    if (v < 0 || v >= T) *bad = 1; else t = (int)v;
+  }
+  etype[e] = t;
+}
+
+// hist[t][block] = edges of type t in the block's 1024 edges
+__global__ void __launch_bounds__(kSortBlock) type_hist_kernel(const int32_t* __restrict__ etype, int64_t E, int nblocks,
+                                                                int32_t* __restrict__ hist) {
+  __shared__ int s_cnt[kMaxTypes];
+  if (threadIdx.x < kMaxTypes) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t e = (int64_t)blockIdx.x * kSortBlock + threadIdx.x;
+  if (e < E) atomicAdd(&s_cnt[etype[e]], 1);
+  __syncthreads();
+  if (threadIdx.x < kMaxTypes) hist[threadIdx.x * nblocks + blockIdx.x] = s_cnt[threadIdx.x];
+}
+
+// stable scatter: position = (edges of smaller type) + (edges of the same type in earlier blocks: `base`, the exclusive scan
+// of hist) + (edges of the same type earlier in this block)
+__global__ void __launch_bounds__(kSortBlock) type_scatter_kernel(const int32_t* __restrict__ etype, int64_t E, int nblocks,
+                                                                   const int32_t* __restrict__ base, int32_t* __restrict__ perm) {
+  __shared__ int s_warp[32][kMaxTypes];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t e = (int64_t)blockIdx.x * kSortBlock + threadIdx.x;
+  const int t = e < E ? etype[e] : -1;
+  const unsigned same = __match_any_sync(kFull, t);
+  const int rank = __popc(same & ((1u << lane) - 1u));
+  for (int k = lane; k < kMaxTypes; k += 32) s_warp[warp][k] = 0;
+  __syncwarp();
+  if (t >= 0 && rank == 0) s_warp[warp][t] = __popc(same);
+  __syncthreads();
+  if (t < 0) return;
+  int before = 0;
+  for (int w2 = 0; w2 < warp; ++w2) before += s_warp[w2][t];
+  perm[base[t * nblocks + blockIdx.x] + before + rank] = (int32_t)e;
+}
+
+__global__ void type_ptr_kernel(const int32_t* __restrict__ base, int nblocks, int32_t* __restrict__ type_ptr) {
+  const int t = threadIdx.x;
+  if (t <= kMaxTypes) type_ptr[t] = base[t * nblocks];      // base[kMaxTypes * nblocks] = E
+}
+
+// the graph in sorted order: endpoints, bin keys, edge attributes
+__global__ void __launch_bounds__(256) sorted_graph_kernel(const int64_t* __restrict__ edge_index, const int32_t* __restrict__ etype,
+                                                            const int32_t* __restrict__ perm, int64_t E, int T,
+                                                            int64_t* __restrict__ s_src, int64_t* __restrict__ s_dst,
+                                                            int64_t* __restrict__ s_key) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= E) return;
+  const int64_t e = perm[i];
+  const int64_t d = edge_index[E + e];
+  s_src[i] = edge_index[e];
+  s_dst[i] = d;
+  s_key[i] = d * T + etype[e];
+}
+
+// out[i][:] = in[perm[i]][:] (gather = 1) or out[perm[i]][:] = in[i][:] (gather = 0), rows of `width` floats
+__global__ void __launch_bounds__(256) permute_rows_kernel(const float* __restrict__ in, const int32_t* __restrict__ perm,
+                                                            int64_t E, int width, int gather, float* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= E * width) return;
+  const int64_t i = idx / width;
+  const int c = (int)(idx - i * width);
+  const int64_t e = perm[i];
+  if (gather) out[idx] = in[e * width + c]; else out[e * width + c] = in[idx];
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+// one warp per (target, type) bin: attention logit a = <g', wa[col]> + ba[col] (col = type or 0), softmax over the bin
+// exp(a - max) / (sum + 1e-12) (torch_scatter's scatter_softmax, layers.py:242-249), U[bin] = sum alpha m.  The logits
+// pass through `alpha` (written by lane 0, read by the warp after __syncwarp).
+__global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__ g, const float* __restrict__ m,
+                                                        const float* __restrict__ wa, const float* __restrict__ ba, int per_type_col,
+                                                        int T, const int32_t* __restrict__ ptr, const int32_t* __restrict__ perm,
+                                                        int64_t nbins, float* __restrict__ alpha, float* __restrict__ U) {
+  const int64_t bin = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (bin >= nbins) return;
+  const int b = ptr[bin], e = ptr[bin + 1];
+  float u0 = 0.f, u1 = 0.f;
+  if (e > b) {
+    const int col = per_type_col ? (int)(bin % T) : 0;
+    const float w0 = wa[col * kD + lane], w1 = wa[col * kD + lane + 32], bias = ba[col];
+    float mx = -INFINITY;
+    for (int i = b; i < e; ++i) {
+      const int64_t r = perm[i];
+      const float a = warp_sum(fmaf(g[r * kD + lane], w0, g[r * kD + lane + 32] * w1)) + bias;
+      if (lane == 0) alpha[r] = a;
+      mx = fmaxf(mx, a);
+    }
+    __syncwarp();
+    float se = 0.f;
+    for (int i = b; i < e; ++i) se += expf(alpha[perm[i]] - mx);
+    const float inv = 1.f / (se + 1e-12f);
+    __syncwarp();
+    for (int i = b; i < e; ++i) {
+      const int64_t r = perm[i];
+      const float al = expf(alpha[r] - mx) * inv;
+      u0 = fmaf(al, m[r * kD + lane], u0);
+      u1 = fmaf(al, m[r * kD + lane + 32], u1);
+      __syncwarp();
+      if (lane == 0) alpha[r] = al;
+    }
+  }
+  U[bin * kD + lane] = u0;
+  U[bin * kD + lane + 32] = u1;
+}
+
+// reverse: dm = alpha dU (through the ReLU of the message), d alpha = <m, dU>, da = alpha (d alpha - sum alpha d alpha);
+// the logit's gradient goes on into g' (dg += da wa[col]) and is kept in `da` for the attn_net weight gradient
+__global__ void __launch_bounds__(256) attn_bwd_kernel(const float* __restrict__ dU, const float* __restrict__ m,
+                                                        const float* __restrict__ alpha, const float* __restrict__ wa,
+                                                        int per_type_col, int T, const int32_t* __restrict__ ptr,
+                                                        const int32_t* __restrict__ perm, int64_t nbins,
+                                                        float* __restrict__ dm, float* __restrict__ da, float* __restrict__ dg) {
+  const int64_t bin = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (bin >= nbins) return;
+  const int b = ptr[bin], e = ptr[bin + 1];
+  if (e <= b) return;
+  const int col = per_type_col ? (int)(bin % T) : 0;
+  const float w0 = wa[col * kD + lane], w1 = wa[col * kD + lane + 32];
+  const float d0 = dU[bin * kD + lane], d1 = dU[bin * kD + lane + 32];
+  float s = 0.f;
+  for (int i = b; i < e; ++i) {
+    const int64_t r = perm[i];
+    const float dal = warp_sum(fmaf(m[r * kD + lane], d0, m[r * kD + lane + 32] * d1));
+    if (lane == 0) da[r] = dal;
+    s = fmaf(alpha[r], dal, s);
+  }
+  __syncwarp();
+  for (int i = b; i < e; ++i) {
+    const int64_t r = perm[i];
+    const float al = alpha[r];
+    const float v = al * (da[r] - s);
+    __syncwarp();
+    if (lane == 0) da[r] = v;
+    const float m0 = m[r * kD + lane], m1 = m[r * kD + lane + 32];
+    dm[r * kD + lane] = m0 > 0.f ? al * d0 : 0.f;
+    dm[r * kD + lane + 32] = m1 > 0.f ? al * d1 : 0.f;
+    dg[r * kD + lane] += v * w0;
+    dg[r * kD + lane + 32] += v * w1;
+  }
+}
+
 // ------------------------------------------------------------------ BatchNorm1d, training mode
 // column sums in fp64 over a row range: mode 0 (sum y, sum y^2); mode 1 (sum g, sum g * xhat)
 __global__ void __launch_bounds__(256) bn_partial_kernel(const float* __restrict__ Y, const float* __restrict__ G,
@@ -655,6 +824,10 @@ struct TrainWs {
   float *dh, *dhp, *dh0, *tn1, *tn2, *tn3, *dg, *dg0, *be1, *be2, *ga, *gb;
   double* bn_part;
   float *bn_m1, *bn_m2, *part, *partb;
+  // per-type layer
+  int32_t *etype, *type_hist, *type_base, *type_perm, *type_ptr, *bin_ptr, *bin_perm;
+  int64_t *s_src, *s_dst, *s_key;
+  float *s_attr, *alpha[kMaxSteps], *U[kMaxSteps], *tab_rt, *dU, *dR, *da, *d_edge;
   uint64_t bytes;
 };
 
@@ -686,7 +859,8 @@ TrainWs carve_train(const pgmp_mpn_train_params& p) {
   w.src_ptr = c.take<int32_t>(N + 1);
   w.dst_perm = c.take<int32_t>(E);
   w.src_perm = c.take<int32_t>(E);
-  w.cnt = c.take<int32_t>(N);
+  const uint64_t T = p.per_type ? (uint64_t)p.num_types : 1;
+  w.cnt = c.take<int32_t>(N * T + 1);
   w.bad = c.take<int32_t>(1);
   w.node_emb = carve_mlp(c, p.node_emb, N, nullptr);
   w.edge_emb = carve_mlp(c, p.edge_emb, E, nullptr);
@@ -699,7 +873,8 @@ TrainWs carve_train(const pgmp_mpn_train_params& p) {
     w.h[s] = p.has_update_mlp ? c.take<float>(N * kD) : w.agg[s];
   }
   for (int k = 0; k < n_out && k < kMaxOut; ++k) {
-    w.edge_head[k] = carve_mlp(c, p.edge_head, E, p.edge_logits ? p.edge_logits + (uint64_t)k * E : nullptr);
+    // per-type: the edge head runs in the sorted edge order, its output is un-permuted into edge_logits afterwards
+    w.edge_head[k] = carve_mlp(c, p.edge_head, E, p.edge_logits && !p.per_type ? p.edge_logits + (uint64_t)k * E : nullptr);
     w.node_head[k] = carve_mlp(c, p.node_head, N, p.node_logits ? p.node_logits + (uint64_t)k * N : nullptr);
     w.class_head[k] = carve_mlp(c, p.class_head, N, p.class_logits ? p.class_logits + (uint64_t)k * N * p.num_classes : nullptr);
   }
@@ -724,6 +899,29 @@ TrainWs carve_train(const pgmp_mpn_train_params& p) {
   w.bn_m2 = c.take<float>(kMaxWidth);
   w.part = c.take<float>((uint64_t)kMaxSplits * kMaxWidth * kMaxWidth);
   w.partb = c.take<float>((uint64_t)kMaxSplits * kMaxWidth);
+  if (p.per_type) {
+    const uint64_t nb = ceil_div<uint64_t>(E > 0 ? E : 1, kSortBlock);
+    w.etype = c.take<int32_t>(E);
+    w.type_hist = c.take<int32_t>(kMaxTypes * nb + 1);
+    w.type_base = c.take<int32_t>(kMaxTypes * nb + 1);
+    w.type_perm = c.take<int32_t>(E);
+    w.type_ptr = c.take<int32_t>(kMaxTypes + 1);
+    w.bin_ptr = c.take<int32_t>(N * T + 1);
+    w.bin_perm = c.take<int32_t>(E);
+    w.s_src = c.take<int64_t>(E);
+    w.s_dst = c.take<int64_t>(E);
+    w.s_key = c.take<int64_t>(E);
+    w.s_attr = c.take<float>(E * (uint64_t)p.edge_emb.dims[0]);
+    for (int s = 0; s < p.steps && s < kMaxSteps; ++s) {
+      w.alpha[s] = c.take<float>(p.attn ? E : 0);
+      w.U[s] = c.take<float>(N * T * kD);
+    }
+    w.tab_rt = c.take<float>(N * T * kD);
+    w.dU = c.take<float>(N * T * kD);
+    w.dR = c.take<float>(N * T * kD);
+    w.da = c.take<float>(E);
+    w.d_edge = c.take<float>(E);
+  }
   w.bytes = c.bytes();
   return w;
 }
@@ -741,9 +939,9 @@ inline bool vec_w(const float* W, int ldw, int coloff, int K) { return al16(W) &
 
 int launch_fwd(cudaStream_t st, const ASrc& a, int64_t M, const float* W, int ldw, int coloff, const float* bias, int O,
                int relu, float* Y, const float* add1 = nullptr, const int64_t* idx1 = nullptr, const float* add2 = nullptr,
-               const int64_t* idx2 = nullptr) {
+               const int64_t* idx2 = nullptr, int ldy = 0, int add1_ld = kD) {
   if (M <= 0) return PGMP_OK;
-  FwdArgs g{a, M, src_width(a), O, W, ldw, coloff, bias, add1, idx1, add2, idx2, relu, Y, O};
+  FwdArgs g{a, M, src_width(a), O, W, ldw, coloff, bias, add1, idx1, add2, idx2, relu, Y, ldy ? ldy : O, add1_ld};
   const dim3 grid(blocks_for(M, BM), (unsigned)ceil_div(O, BN));
   if (vec_src(a) && vec_w(W, ldw, coloff, g.K))
     PGMP_LAUNCH(lin_fwd_kernel<true>, grid, 256, 0, st, g);
@@ -753,11 +951,12 @@ int launch_fwd(cudaStream_t st, const ASrc& a, int64_t M, const float* W, int ld
 }
 
 int launch_bwd_in(cudaStream_t st, const float* dY, int O, int64_t M, const float* W, int ldw, int coloff, int K, Target t0,
-                  const Target* t1 = nullptr) {
+                  const Target* t1 = nullptr, int ldd = 0) {
   if (M <= 0) return PGMP_OK;
-  BwdInArgs g{dY, O, M, O, K, W, ldw, coloff, t1 ? 2 : 1, {t0, t1 ? *t1 : Target{nullptr, 0, 0, 0, 0, nullptr}}};
+  if (!ldd) ldd = O;
+  BwdInArgs g{dY, ldd, M, O, K, W, ldw, coloff, t1 ? 2 : 1, {t0, t1 ? *t1 : Target{nullptr, 0, 0, 0, 0, nullptr}}};
   const dim3 grid(blocks_for(M, BM), (unsigned)ceil_div(K, BN));
-  if (al16(dY) && !(O & 3) && vec_w(W, ldw, coloff, K))
+  if (al16(dY) && !(ldd & 3) && !(O & 3) && vec_w(W, ldw, coloff, K))
     PGMP_LAUNCH(lin_bwd_in_kernel<true>, grid, 256, 0, st, g);
   else
     PGMP_LAUNCH(lin_bwd_in_kernel<false>, grid, 256, 0, st, g);
@@ -766,16 +965,19 @@ int launch_bwd_in(cudaStream_t st, const float* dY, int O, int64_t M, const floa
 
 // dW[:, coloff : coloff + K] += dY^T A (and db += column sums of dY when db != null)
 int launch_bwd_w(cudaStream_t st, const TrainWs& w, const float* dY, int O, const ASrc& a, int64_t M, float* dW, int ldw,
-                 int coloff, float* db) {
+                 int coloff, float* db, int ldd = 0) {
   if (M <= 0) return PGMP_OK;
+  if (!ldd) ldd = O;
   const int K = src_width(a);
   int splits = (int)ceil_div<int64_t>(M, 256);
   if (splits > kMaxSplits) splits = kMaxSplits;
+  const int64_t cap = (int64_t)kMaxSplits * kMaxWidth * kMaxWidth / ((int64_t)O * K);    // partial tiles that fit w.part
+  if (splits > cap) splits = (int)(cap > 1 ? cap : 1);
   const int64_t rows = round_up<int64_t>(ceil_div<int64_t>(M, splits), BK);
   splits = (int)ceil_div<int64_t>(M, rows);
-  BwdWArgs g{dY, O, O, a, K, M, rows, w.part, db ? w.partb : nullptr};
+  BwdWArgs g{dY, ldd, O, a, K, M, rows, w.part, db ? w.partb : nullptr};
   const dim3 grid((unsigned)ceil_div(K, BN), (unsigned)ceil_div(O, BN), (unsigned)splits);
-  if (al16(dY) && !(O & 3) && vec_src(a) && !(K & 3))
+  if (al16(dY) && !(ldd & 3) && !(O & 3) && vec_src(a) && !(K & 3))
     PGMP_LAUNCH(lin_bwd_w_kernel<true>, grid, 256, 0, st, g);
   else
     PGMP_LAUNCH(lin_bwd_w_kernel<false>, grid, 256, 0, st, g);
@@ -897,10 +1099,212 @@ int validate_train(const pgmp_mpn_train_params* p, bool backward) {
   PGMP_TRY(validate_mlp(p->class_head, "classification", kD, p->num_classes));
   if (!p->x || !p->params || !p->node_logits || !p->class_logits || !p->workspace) return set_error(PGMP_ERR_INVALID, "null device pointer");
   if (p->num_edges > 0 && (!p->edge_attr || !p->edge_index || !p->edge_logits)) return set_error(PGMP_ERR_INVALID, "null edge pointer");
+  if (p->per_type) {
+    if (p->num_types < 1 || p->num_types > kMaxTypes) return set_error(PGMP_ERR_INVALID, "per_type: num_types %d", p->num_types);
+    if (!p->has_update_mlp) return set_error(PGMP_ERR_INVALID, "per_type needs update_mlp (layers.py:253-258)");
+    if (p->attn < 0 || p->attn > 2) return set_error(PGMP_ERR_INVALID, "attn %d", p->attn);
+    if (!p->node_types) return set_error(PGMP_ERR_INVALID, "per_type without node_types");
+    if ((int64_t)p->num_nodes * p->num_types > (1ll << 30)) return set_error(PGMP_ERR_INVALID, "too many (node, type) bins");
+  } else if (p->attn) {
+    return set_error(PGMP_ERR_INVALID, "attention aggregation needs per_type");
+  }
   if (backward) {
     if (!p->grads || !p->d_node_logits || !p->d_class_logits || (p->num_edges > 0 && !p->d_edge_logits))
       return set_error(PGMP_ERR_INVALID, "backward: null gradient pointer");
   }
+  return PGMP_OK;
+}
+
+
+// ================================================================== per-type layer: forward / backward
+// sizes of the 17 source-type groups on the host (one stream wait): the per-type products are launched per group
+int read_type_ptr(const TrainWs& w, cudaStream_t st, int32_t (&tp)[kMaxTypes + 1]) {
+  PGMP_CUDA(cudaMemcpyAsync(tp, w.type_ptr, sizeof(tp), cudaMemcpyDeviceToHost, st));
+  PGMP_CUDA(cudaStreamSynchronize(st));
+  return PGMP_OK;
+}
+
+int mpn_train_forward_pt(const pgmp_mpn_train_params& p, const TrainWs& w, cudaStream_t st) {
+  const int64_t N = p.num_nodes, E = p.num_edges;
+  const float* P = p.params;
+  const int T = p.num_types;
+  const int nd = p.skip ? 2 * kD : kD, ed = nd;
+  const int ld1 = 2 * nd + ed, ldm = nd + kD, ldu = T * kD;
+  const int64_t bins = N * T;
+  const int ain = p.edge_emb.dims[0];
+
+  PGMP_CUDA(cudaMemsetAsync(w.bad, 0, sizeof(int32_t), st));
+  int32_t tp[kMaxTypes + 1] = {};
+  if (E > 0) {
+    const int nb = (int)ceil_div<int64_t>(E, kSortBlock);
+    PGMP_LAUNCH(edge_type_kernel, blocks_for(E), 256, 0, st, p.edge_index, p.node_types, E, N, T, w.etype, w.bad);
+    PGMP_LAUNCH(type_hist_kernel, (unsigned)nb, kSortBlock, 0, st, w.etype, E, nb, w.type_hist);
+    PGMP_LAUNCH(csr_scan_kernel, 1, 1024, 0, st, w.type_hist, (int64_t)kMaxTypes * nb, w.type_base);
+    PGMP_LAUNCH(type_scatter_kernel, (unsigned)nb, kSortBlock, 0, st, w.etype, E, nb, w.type_base, w.type_perm);
+    PGMP_LAUNCH(type_ptr_kernel, 1, 32, 0, st, w.type_base, nb, w.type_ptr);
+    PGMP_LAUNCH(sorted_graph_kernel, blocks_for(E), 256, 0, st, p.edge_index, w.etype, w.type_perm, E, T, w.s_src, w.s_dst, w.s_key);
+    PGMP_LAUNCH(permute_rows_kernel, blocks_for(E * ain), 256, 0, st, p.edge_attr, w.type_perm, E, ain, 1, w.s_attr);
+    PGMP_TRY(read_type_ptr(w, st, tp));
+  }
+  const int64_t* src = w.s_src;
+  const int64_t* dst = w.s_dst;
+  PGMP_TRY(build_csr(st, w, dst, E, N, w.dst_ptr, w.dst_perm));
+  PGMP_TRY(build_csr(st, w, src, E, N, w.src_ptr, w.src_perm));
+  PGMP_TRY(build_csr(st, w, w.s_key, E, bins, w.bin_ptr, w.bin_perm));
+
+  PGMP_TRY(mlp_forward(st, w, p.node_emb, w.node_emb, src1(p.x, p.node_emb.dims[0]), N, P));
+  PGMP_TRY(mlp_forward(st, w, p.edge_emb, w.edge_emb, src1(w.s_attr, ain), E, P));
+  const float* h0 = w.node_emb.out(p.node_emb);
+  const float* g0 = w.edge_emb.out(p.edge_emb);
+  const int first = p.steps - n_out_of(p);
+  for (int s = 0; s < p.steps; ++s) {
+    const float* hp = s ? w.h[s - 1] : h0;
+    const float* gp = s ? w.g[s - 1] : g0;
+    const ASrc xs = p.skip ? src2(h0, hp, kD) : src1(hp, kD);
+    const ASrc es = p.skip ? src2(g0, gp, kD) : src1(gp, kD);
+    // mlp_edge (layers.py:171-175, 214)
+    PGMP_TRY(launch_fwd(st, xs, N, P + p.w1, ld1, 0, nullptr, kD, 0, w.tab_p));
+    PGMP_TRY(launch_fwd(st, xs, N, P + p.w1, ld1, nd, nullptr, kD, 0, w.tab_q));
+    PGMP_TRY(launch_fwd(st, es, E, P + p.w1, ld1, 2 * nd, P + p.b1, kD, 1, w.hid[s], w.tab_p, dst, w.tab_q, src));
+    PGMP_TRY(launch_fwd(st, src1(w.hid[s], kD), E, P + p.w2, kD, 0, P + p.b2, kD, 1, w.g[s]));
+    // per-type message (layers.py:222-224, 264-274): m = ReLU(Wm[t] [x_i ; g'] + bm[t]), t = type of the source
+    for (int t = 0; t < kMaxTypes; ++t) {
+      const int64_t a = tp[t], cnt = tp[t + 1] - tp[t];
+      if (cnt <= 0) continue;
+      const float* Wt = P + p.wm + (int64_t)t * p.wm_type_stride;
+      const float* bt = P + p.bm + (int64_t)t * p.wm_type_stride;
+      PGMP_TRY(launch_fwd(st, xs, N, Wt, ldm, 0, bt, kD, 0, w.tab_rt + t * kD, nullptr, nullptr, nullptr, nullptr, ldu));
+      PGMP_TRY(launch_fwd(st, src1(w.g[s] + a * kD, kD), cnt, Wt, ldm, nd, nullptr, kD, 1, w.m[s] + a * kD, w.tab_rt + t * kD,
+                          dst + a, nullptr, nullptr, 0, ldu));
+    }
+    // aggregation per (target, type) (layers.py:234-251) and the update MLP over the concatenated types (:253-258)
+    if (p.attn)
+      PGMP_LAUNCH(attn_fwd_kernel, blocks_for(bins, 8), 256, 0, st, w.g[s], w.m[s], P + p.wa, P + p.ba,
+                  p.attn == PGMP_ATTN_PER_TYPE ? 1 : 0, T, w.bin_ptr, w.bin_perm, bins, w.alpha[s], w.U[s]);
+    else
+      PGMP_LAUNCH(aggregate_fwd_kernel, blocks_for(bins, 4), 256, 0, st, w.m[s], w.bin_ptr, w.bin_perm, bins, p.aggr, w.U[s]);
+    PGMP_TRY(launch_fwd(st, src1(w.U[s], ldu), N, P + p.wu, ldu, 0, P + p.bu, kD, 1, w.h[s]));
+    if (s >= first) {
+      const int k = s - first;
+      PGMP_TRY(mlp_forward(st, w, p.node_head, w.node_head[k], src1(w.h[s], kD), N, P));
+      PGMP_TRY(mlp_forward(st, w, p.class_head, w.class_head[k], src1(w.h[s], kD), N, P));
+      PGMP_TRY(mlp_forward(st, w, p.edge_head, w.edge_head[k], src1(w.g[s], kD), E, P));
+      if (E > 0)
+        PGMP_LAUNCH(permute_rows_kernel, blocks_for(E), 256, 0, st, w.edge_head[k].out(p.edge_head), w.type_perm, E, 1, 0,
+                    p.edge_logits + (int64_t)k * E);
+    }
+  }
+  return PGMP_OK;
+}
+
+int mpn_train_backward_pt(const pgmp_mpn_train_params& p, const TrainWs& w, cudaStream_t st) {
+  const int64_t N = p.num_nodes, E = p.num_edges;
+  const float* P = p.params;
+  float* G = p.grads;
+  const int T = p.num_types;
+  const int nd = p.skip ? 2 * kD : kD, ed = nd;
+  const int ld1 = 2 * nd + ed, ldm = nd + kD, ldu = T * kD;
+  const int64_t bins = N * T;
+  const int J = p.num_classes;
+  const float* h0 = w.node_emb.out(p.node_emb);
+  const float* g0 = w.edge_emb.out(p.edge_emb);
+  const int first = p.steps - n_out_of(p);
+  const int64_t nN = N * kD, nE = E * kD;
+  const int64_t* src = w.s_src;
+  const int64_t* dst = w.s_dst;
+  int32_t tp[kMaxTypes + 1] = {};
+  if (E > 0) PGMP_TRY(read_type_ptr(w, st, tp));
+
+  float* dh = w.dh;
+  float* dhp = w.dhp;
+  PGMP_CUDA(cudaMemsetAsync(dh, 0, sizeof(float) * nN, st));
+  PGMP_CUDA(cudaMemsetAsync(w.dh0, 0, sizeof(float) * nN, st));
+  if (E > 0) {
+    PGMP_CUDA(cudaMemsetAsync(w.dg, 0, sizeof(float) * nE, st));
+    PGMP_CUDA(cudaMemsetAsync(w.dg0, 0, sizeof(float) * nE, st));
+  }
+  const Target none{nullptr, 0, 0, 0, 0, nullptr};
+  for (int s = p.steps - 1; s >= 0; --s) {
+    const float* hp = s ? w.h[s - 1] : h0;
+    const float* gp = s ? w.g[s - 1] : g0;
+    const ASrc xs = p.skip ? src2(h0, hp, kD) : src1(hp, kD);
+    const ASrc es = p.skip ? src2(g0, gp, kD) : src1(gp, kD);
+    if (s >= first) {
+      const int k = s - first;
+      if (E > 0)
+        PGMP_LAUNCH(permute_rows_kernel, blocks_for(E), 256, 0, st, p.d_edge_logits + (int64_t)k * E, w.type_perm, E, 1, 1, w.d_edge);
+      PGMP_TRY(mlp_backward(st, w, p.edge_head, w.edge_head[k], src1(w.g[s], kD), E, P, G, w.d_edge, 1,
+                            Target{w.dg, kD, 0, kD, 1}, none));
+      PGMP_TRY(mlp_backward(st, w, p.node_head, w.node_head[k], src1(w.h[s], kD), N, P, G, p.d_node_logits + (int64_t)k * N, 1,
+                            Target{dh, kD, 0, kD, 1}, none));
+      PGMP_TRY(mlp_backward(st, w, p.class_head, w.class_head[k], src1(w.h[s], kD), N, P, G,
+                            p.d_class_logits + (int64_t)k * N * J, 1, Target{dh, kD, 0, kD, 1}, none));
+    }
+    // update_mlp over [N][T * 64]
+    PGMP_LAUNCH(relu_mask_kernel, blocks_for(nN), 256, 0, st, dh, w.h[s], w.tn1, nN);
+    PGMP_TRY(launch_bwd_w(st, w, w.tn1, kD, src1(w.U[s], ldu), N, G + p.wu, ldu, 0, G + p.bu));
+    PGMP_TRY(launch_bwd_in(st, w.tn1, kD, N, P + p.wu, ldu, 0, ldu, Target{w.dU, ldu, 0, ldu, 0}));
+    PGMP_CUDA(cudaMemsetAsync(dhp, 0, sizeof(float) * nN, st));
+    const Target tx0{p.skip ? w.dh0 : dhp, kD, 0, kD, 1};
+    const Target tx1{dhp, kD, kD, kD, 1};
+    if (E > 0) {
+      float* dm = w.be1;
+      if (p.attn) {
+        // softmax-weighted sum: dm, the logit gradients da (and their share of dg), then the attn_net weights
+        PGMP_LAUNCH(attn_bwd_kernel, blocks_for(bins, 8), 256, 0, st, w.dU, w.m[s], w.alpha[s], P + p.wa,
+                    p.attn == PGMP_ATTN_PER_TYPE ? 1 : 0, T, w.bin_ptr, w.bin_perm, bins, dm, w.da, w.dg);
+        if (p.attn == PGMP_ATTN_PER_TYPE) {
+          for (int t = 0; t < T; ++t) {
+            const int64_t a = tp[t], cnt = tp[t + 1] - tp[t];
+            if (cnt > 0)
+              PGMP_TRY(launch_bwd_w(st, w, w.da + a, 1, src1(w.g[s] + a * kD, kD), cnt, G + p.wa + (int64_t)t * kD, kD, 0, G + p.ba + t));
+          }
+        } else {
+          PGMP_TRY(launch_bwd_w(st, w, w.da, 1, src1(w.g[s], kD), E, G + p.wa, kD, 0, G + p.ba));
+        }
+      } else {
+        PGMP_LAUNCH(aggregate_bwd_kernel, blocks_for(bins, 4), 256, 0, st, w.dU, w.m[s], w.U[s], w.bin_ptr, w.bin_perm, bins, p.aggr, dm);
+      }
+      // per-type message MLP: edge columns per edge, node columns through the per-(target, type) sums dR
+      PGMP_LAUNCH(seg_sum_kernel, blocks_for(bins, 4), 256, 0, st, dm, w.bin_ptr, w.bin_perm, bins, w.dR);
+      for (int t = 0; t < kMaxTypes; ++t) {
+        const int64_t a = tp[t], cnt = tp[t + 1] - tp[t];
+        if (cnt <= 0) continue;
+        const float* Wt = P + p.wm + (int64_t)t * p.wm_type_stride;
+        float* dWt = G + p.wm + (int64_t)t * p.wm_type_stride;
+        float* dbt = G + p.bm + (int64_t)t * p.wm_type_stride;
+        PGMP_TRY(launch_bwd_w(st, w, dm + a * kD, kD, src1(w.g[s] + a * kD, kD), cnt, dWt, ldm, nd, nullptr));
+        PGMP_TRY(launch_bwd_w(st, w, w.dR + t * kD, kD, xs, N, dWt, ldm, 0, dbt, ldu));
+        PGMP_TRY(launch_bwd_in(st, w.dR + t * kD, kD, N, Wt, ldm, 0, nd, tx0, p.skip ? &tx1 : nullptr, ldu));
+        // the gradient of g_s is complete with this term: the epilogue also applies the ReLU of mlp_edge.2
+        PGMP_TRY(launch_bwd_in(st, dm + a * kD, kD, cnt, Wt, ldm, nd, kD, Target{w.dg + a * kD, kD, 0, kD, 1, w.g[s] + a * kD}));
+      }
+      // mlp_edge.2
+      PGMP_TRY(launch_bwd_w(st, w, w.dg, kD, src1(w.hid[s], kD), E, G + p.w2, kD, 0, G + p.b2));
+      float* dhid = w.be2;
+      PGMP_TRY(launch_bwd_in(st, w.dg, kD, E, P + p.w2, kD, 0, kD, Target{dhid, kD, 0, kD, 0, w.hid[s]}));
+      // mlp_edge.0
+      PGMP_LAUNCH(seg_sum_kernel, blocks_for(N, 4), 256, 0, st, dhid, w.dst_ptr, w.dst_perm, N, w.tn1);
+      PGMP_LAUNCH(seg_sum_kernel, blocks_for(N, 4), 256, 0, st, dhid, w.src_ptr, w.src_perm, N, w.tn2);
+      PGMP_TRY(launch_bwd_w(st, w, dhid, kD, es, E, G + p.w1, ld1, 2 * nd, nullptr));
+      PGMP_TRY(launch_bwd_w(st, w, w.tn1, kD, xs, N, G + p.w1, ld1, 0, G + p.b1));
+      PGMP_TRY(launch_bwd_w(st, w, w.tn2, kD, xs, N, G + p.w1, ld1, nd, nullptr));
+      PGMP_TRY(launch_bwd_in(st, w.tn1, kD, N, P + p.w1, ld1, 0, nd, tx0, p.skip ? &tx1 : nullptr));
+      PGMP_TRY(launch_bwd_in(st, w.tn2, kD, N, P + p.w1, ld1, nd, nd, tx0, p.skip ? &tx1 : nullptr));
+      const Target te0{p.skip ? w.dg0 : w.dg, kD, 0, kD, p.skip ? 1 : 0};
+      const Target te1{w.dg, kD, kD, kD, 0};
+      PGMP_TRY(launch_bwd_in(st, dhid, kD, E, P + p.w1, ld1, 2 * nd, ed, te0, p.skip ? &te1 : nullptr));
+    }
+    float* tmp = dh;
+    dh = dhp;
+    dhp = tmp;
+  }
+  PGMP_LAUNCH(add_into_kernel, blocks_for(nN), 256, 0, st, w.dh0, dh, nN);
+  if (E > 0) PGMP_LAUNCH(add_into_kernel, blocks_for(nE), 256, 0, st, w.dg0, w.dg, nE);
+  const int xin = p.node_emb.dims[0];
+  PGMP_TRY(mlp_backward(st, w, p.node_emb, w.node_emb, src1(p.x, xin), N, P, G, w.dh0, p.grad_x ? 1 : 0,
+                        Target{p.grad_x, xin, 0, xin, 0}, none));
+  PGMP_TRY(mlp_backward(st, w, p.edge_emb, w.edge_emb, src1(w.s_attr, p.edge_emb.dims[0]), E, P, G, w.dg0, 0, none, none));
   return PGMP_OK;
 }
 
@@ -911,6 +1315,7 @@ int mpn_train_forward(const pgmp_mpn_train_params& p, cudaStream_t st) {
   const TrainWs w = carve_train(p);
   if (w.bytes > p.workspace_bytes)
     return set_error(PGMP_ERR_INVALID, "workspace too small: %llu < %llu", (unsigned long long)p.workspace_bytes, (unsigned long long)w.bytes);
+  if (p.per_type) return mpn_train_forward_pt(p, w, st);
   const int64_t N = p.num_nodes, E = p.num_edges;
   const float* P = p.params;
   const int64_t* src = p.edge_index;
@@ -958,6 +1363,7 @@ int mpn_train_backward(const pgmp_mpn_train_params& p, cudaStream_t st) {
   const TrainWs w = carve_train(p);
   if (w.bytes > p.workspace_bytes)
     return set_error(PGMP_ERR_INVALID, "workspace too small: %llu < %llu", (unsigned long long)p.workspace_bytes, (unsigned long long)w.bytes);
+  if (p.per_type) return mpn_train_backward_pt(p, w, st);
   const int64_t N = p.num_nodes, E = p.num_edges;
   const float* P = p.params;
   float* G = p.grads;

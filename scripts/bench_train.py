@@ -38,6 +38,8 @@ def parse(argv=None):
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--mpn-steps", type=int, default=10)
+    ap.add_argument("--model", choices=("agnostic", "flagship"), default="agnostic",
+                    help="agnostic = class_agnostic_end2end (BASELINE configs[4]); flagship = the per-type / attention layer (hybrid_*)")
     ap.add_argument("--profile", action="store_true", help="after the timed steps: one more step with per-kernel CUDA events")
     return ap.parse_args(argv)
 
@@ -51,7 +53,7 @@ def run_training(args, rank, world, dev):
     joints_gt, factors = torch.from_numpy(np.stack(gts)).to(dev), torch.from_numpy(np.stack(facs)).to(dev)
     # labels from the ground truth as the reference's training loop gets them (EDGE_LABEL_METHOD 6, class_agnostic_end2end)
     gcfg = pgmp_b200.config.bench_gc_config(k=K, graph_type="knn", EDGE_LABEL_METHOD=6, MATCHING_RADIUS=0.5)
-    mcfg = pgmp_b200.config.agnostic_mpn_config(J, STEPS=args.mpn_steps)
+    mcfg = (pgmp_b200.config.flagship_mpn_config if args.model == "flagship" else pgmp_b200.config.agnostic_mpn_config)(J, STEPS=args.mpn_steps)
     model = synthetic.synth_mpn_state_dict(get_mpn_model(mcfg), 0).to(dev).train()
     opt = torch.optim.Adam(model.parameters(), lr=1e-4)
     gen = torch.Generator(device=dev).manual_seed(rank)
@@ -112,8 +114,10 @@ def run_training(args, rank, world, dev):
             "metric": "training step: images/sec (GC + MPN forward + backward + gradient all-reduce + Adam)",
             "value": imgs / (ms["step"] * 1e-3), "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms["step"], "ms": ms, "edges_per_s": info["edges"] * world / (ms["step"] * 1e-3),
-            "config": {"workload": "configs[4]: %d synthetic %dx%d images per GPU, agnostic MPLayer (max, skip, %d steps), "
-                                   "kNN-50 graph" % (args.batch, args.size, args.size, args.mpn_steps),
+            "config": {"workload": "configs[4]: %d synthetic %dx%d images per GPU, %s (skip, %d steps), kNN-50 graph"
+                                   % (args.batch, args.size, args.size,
+                                      "per-type TypeAwareMPNLayer with attention" if args.model == "flagship" else "agnostic MPLayer (max)",
+                                      args.mpn_steps),
                        "nodes_per_gpu": info["nodes"], "edges_per_gpu": info["edges"]},
             "dtype": "f32", "data": "synthetic", "scaling": "weak", "allreduce_bytes": info["allreduce_bytes"],
             "gpu_launches": launches, "loss_first_last": [losses[0], losses[-1]]})

@@ -85,8 +85,8 @@ def test_factories_follow_the_reference_contract():
     assert names["edge_embedding.9.weight"].shape == (64, 64) and "edge_embedding.8.weight" in names
     a = get_mpn_model(pgmp_b200.config.agnostic_mpn_config())
     assert sum(p.numel() for p in a.parameters()) == 101203
-    with pytest.raises(NotImplementedError):
-        m.train()(torch.zeros(1), torch.zeros(1), torch.zeros(1), node_types=None)
+    with pytest.raises(RuntimeError, match="no CPU path"):      # per-type training runs in libpgmp.so as well
+        m.train()(torch.zeros(1), torch.zeros(1), torch.zeros(1), node_types=torch.zeros(1, dtype=torch.int64))
 
 
 def test_training_mlp_descriptor_follows_make_mlp():
@@ -128,5 +128,8 @@ def test_training_mode_rejects_cpu_tensors():
     with pytest.raises(RuntimeError, match="no CPU path"):
         model(torch.zeros(4, 128), torch.zeros(2, 19), torch.zeros(2, 2, dtype=torch.int64), node_types=torch.zeros(4, dtype=torch.int64))
     flagship = get_mpn_model(pgmp_b200.config.flagship_mpn_config(17, STEPS=2)).train()
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="no CPU path"):
         flagship(torch.zeros(4, 128), torch.zeros(2, 19), torch.zeros(2, 2, dtype=torch.int64), node_types=torch.zeros(4, dtype=torch.int64))
+    hier = get_mpn_model(pgmp_b200.config.flagship_mpn_config(17, STEPS=2, UPDATE_TYPE="hierarch_mlp")).train()
+    with pytest.raises(NotImplementedError):     # the training kernels cover UPDATE_TYPE mlp
+        hier(torch.zeros(4, 128), torch.zeros(2, 19), torch.zeros(2, 2, dtype=torch.int64), node_types=torch.zeros(4, dtype=torch.int64))
