@@ -323,6 +323,65 @@ int pgmp_mpn_train_forward(const pgmp_mpn_train_params* p, pgmp_stream_t stream)
 int pgmp_mpn_train_backward(const pgmp_mpn_train_params* p, pgmp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Training-time label construction, host part (no device work): the detection-to-ground-truth matching of every image
+ * of a batch -- src/graph_constructor/ConstructGraph.py:626-686 (EDGE_LABEL_METHOD 4), :769-942 (method 6),
+ * USE_NEIGHBOURS :704-727 / :890-911 -- on the float32 similarity matrices exp(-d^2 / factor) (:773-785) the caller
+ * computed.  Replaces the per-image torch / scipy.optimize.linear_sum_assignment calls of the reference's Python loop;
+ * the assignment is SciPy's algorithm restated (csrc/match.cu).  All pointers are HOST memory.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pgmp_match_params {
+  int32_t batch;
+  int32_t method;                      /* EDGE_LABEL_METHOD: 4 or 6 */
+  int32_t use_neighbours;              /* USE_NEIGHBOURS */
+  int32_t num_threads;                 /* images are matched in parallel */
+  float matching_radius, inclusion_radius;
+  const float* sim;                    /* [batch][rows][cols]: similarity of annotated joint r to candidate c */
+  int64_t sim_stride_b, sim_stride_g;  /* element strides of the image and the row */
+  int32_t max_gt, max_det;             /* row strides of gt_type / det_type / ambiguous */
+  const int32_t* num_gt;               /* [batch] annotated joints of the image (rows in use) */
+  const int32_t* num_det;              /* [batch] candidates of the image (columns in use) */
+  const int32_t* gt_type;              /* [batch][max_gt] joint type of every annotated joint */
+  const int32_t* det_type;             /* [batch][max_det] joint type of every candidate */
+  int32_t cap;                         /* capacity of match_row / match_col per image */
+  int32_t* match_row;                  /* out [batch][cap]: annotated joint of every matched candidate (matches first, then neighbours) */
+  int32_t* match_col;                  /* out [batch][cap]: the candidate */
+  int32_t* num_match;                  /* out [batch] */
+  uint8_t* ambiguous;                  /* out [batch][max_det] (use_neighbours): candidates claimed by more than one joint */
+  /* optional per-node outputs over the whole batch (node = node_offsets[image] + candidate); NULL node_person skips them */
+  const int64_t* node_offsets;         /* [batch + 1] */
+  const int32_t* gt_person;            /* [batch][max_gt] person of every annotated joint */
+  int64_t* node_person;                /* out [N]: person the node is matched to, else -1 */
+  int64_t* node_class;                 /* out [N]: joint type of the matched annotation, else 0 */
+  float* node_label;                   /* out [N]: 1 for matched nodes */
+  uint8_t* node_ambiguous;             /* out [N] (use_neighbours) */
+} pgmp_match_params;
+
+int pgmp_match_labels(const pgmp_match_params* p);
+
+/* The exponent -d^2 / factor of the similarity (:773-785) of every annotated joint (rows, in the order of the image's
+ * gt[:, :, 2].nonzero()) to every candidate of its image, float32, operation for operation what the reference computes;
+ * the caller applies exp() with the reference's own routine (torch.exp) and hands the result to pgmp_match_labels. */
+typedef struct pgmp_label_args_params {
+  int32_t batch, max_persons, num_joints, num_threads;
+  float clamp_max;                     /* annotated positions are rounded and clamped to [0, clamp_max] */
+  float min_arg;                       /* exponents below this are raised to it (-80: the caller thresholds the matrix anyway); -INF: none */
+  const int64_t* det;                  /* host [N][3] (x, y, type) */
+  const int64_t* node_offsets;         /* host [batch + 1] */
+  const float* gt;                     /* host [batch][max_persons][num_joints][3] (x, y, visible) */
+  const float* factors;                /* host [batch][max_persons][num_joints] */
+  int32_t max_gt, max_det;             /* row counts of the padded outputs */
+  float* arg;                          /* out [batch][max_gt][max_det] */
+  int32_t* num_gt;                     /* out [batch] */
+  int32_t* gt_type;                    /* out [batch][max_gt] */
+  int32_t* gt_person;                  /* out [batch][max_gt] */
+  int32_t* det_type;                   /* out [batch][max_det] */
+} pgmp_label_args_params;
+
+int pgmp_label_similarity_args(const pgmp_label_args_params* p);
+/* scipy.optimize.linear_sum_assignment(cost [nr][nc], maximize): rows / cols hold min(nr, nc) entries */
+int pgmp_linear_sum_assignment(const double* cost, int64_t nr, int64_t nc, int maximize, int64_t* rows, int64_t* cols);
+
+/* ------------------------------------------------------------------------------------------------
  * Grouping tail -- replaces sigmoid/softmax (src/valid.py:109-111), the node threshold + subgraph
  * of pred_to_ann (src/Utils/Utils.py:1448-1451), pred_to_person with CC_METHOD GAEC (:499-514),
  * cluster_graph / extract_edge_matrix / cluster_andres_graph

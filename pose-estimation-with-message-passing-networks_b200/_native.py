@@ -108,6 +108,25 @@ class MpnTrainParams(C.Structure):
                 ("node_types", C.c_void_p), ("wm_type_stride", C.c_int64), ("wa", C.c_int64), ("ba", C.c_int64)]
 
 
+class MatchParams(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("method", C.c_int32), ("use_neighbours", C.c_int32), ("num_threads", C.c_int32),
+                ("matching_radius", C.c_float), ("inclusion_radius", C.c_float), ("sim", C.c_void_p),
+                ("sim_stride_b", C.c_int64), ("sim_stride_g", C.c_int64), ("max_gt", C.c_int32), ("max_det", C.c_int32),
+                ("num_gt", C.c_void_p), ("num_det", C.c_void_p), ("gt_type", C.c_void_p), ("det_type", C.c_void_p),
+                ("cap", C.c_int32), ("match_row", C.c_void_p), ("match_col", C.c_void_p), ("num_match", C.c_void_p),
+                ("ambiguous", C.c_void_p), ("node_offsets", C.c_void_p), ("gt_person", C.c_void_p),
+                ("node_person", C.c_void_p), ("node_class", C.c_void_p), ("node_label", C.c_void_p),
+                ("node_ambiguous", C.c_void_p)]
+
+
+class LabelArgsParams(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("max_persons", C.c_int32), ("num_joints", C.c_int32), ("num_threads", C.c_int32),
+                ("clamp_max", C.c_float), ("min_arg", C.c_float), ("det", C.c_void_p), ("node_offsets", C.c_void_p),
+                ("gt", C.c_void_p), ("factors", C.c_void_p), ("max_gt", C.c_int32), ("max_det", C.c_int32),
+                ("arg", C.c_void_p), ("num_gt", C.c_void_p), ("gt_type", C.c_void_p), ("gt_person", C.c_void_p),
+                ("det_type", C.c_void_p)]
+
+
 CC_METHODS = {"GAEC": 0, "threshold": 1, "greedy": 2}
 
 
@@ -156,6 +175,9 @@ SYMBOLS = {
     "pgmp_group_persons": (C.c_int, [C.POINTER(GroupParams), C.c_void_p]),
     "pgmp_refine_workspace_bytes": (C.c_uint64, [C.POINTER(RefineParams)]),
     "pgmp_refine_persons": (C.c_int, [C.POINTER(RefineParams), C.c_void_p]),
+    "pgmp_match_labels": (C.c_int, [C.POINTER(MatchParams)]),
+    "pgmp_label_similarity_args": (C.c_int, [C.POINTER(LabelArgsParams)]),
+    "pgmp_linear_sum_assignment": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

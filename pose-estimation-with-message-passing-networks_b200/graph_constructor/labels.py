@@ -5,9 +5,13 @@ matchings ``_construct_edge_labels_4`` (:626-686) and ``_construct_edge_labels_6
 (:1096-1134), ``create_loss_mask`` (:1137-1158) and the node dropout (:152-168).
 
 Split of the work: the detection-to-ground-truth MATCHING of an image is a similarity matrix of a few hundred ground
-truth joints x candidates and one or two linear sum assignments.  It runs on the host with the very operations the
-reference uses (float32 torch arithmetic, ``scipy.optimize.linear_sum_assignment``) so that the assignment is the
-reference's bit for bit; it needs ONE device-to-host copy of the candidates per batch.  Everything per EDGE
+truth joints x candidates and one or two linear sum assignments.  It runs on the host, natively and for all images of
+the batch in parallel (``csrc/match.cu``: ``pgmp_label_similarity_args`` computes the exponents with the reference's
+float32 arithmetic, ``torch.exp`` -- the reference's own routine -- turns them into similarities, ``pgmp_match_labels``
+does the masks, thresholds, assignments -- SciPy's ``linear_sum_assignment`` algorithm restated, checked against SciPy --
+fill-in and neighbour rules), so that the assignment is the reference's bit for bit; it needs ONE device-to-host copy
+of the candidates per batch.  The per-image torch / scipy form of the same matching is kept as test infrastructure in
+``oracle/labels.py``.  Everything per EDGE
 (``match_cc``, ``create_loss_mask``, the empty-image rule, node dropout and the re-indexing it entails) runs on the
 device over the whole batch at once -- integer compares and gathers, exact by construction.
 """
@@ -18,125 +22,83 @@ import torch
 SUPPORTED_METHODS = (4, 6)
 
 
-def _similarity(det, gt, factors, clamp_max, floor):
-    """OKS-like similarity of every annotated joint to every candidate (:773-785): ``exp(-d^2 / factor)``, float32.
-    ``floor``: the smallest radius the caller thresholds the matrix with.  Far-apart pairs give subnormal results, which
-    cost the CPU microcode traps (measured: 2 ms of a 5.6 ms image); when every value below ``floor`` is zeroed anyway the
-    exponent is clamped at -80 first -- the values that survive the threshold keep their exact bits."""
-    person_idx, joint_idx = gt[:, :, 2].nonzero(as_tuple=True)
-    pos = gt[person_idx, joint_idx, :2].unsqueeze(1).round().float().clamp(0, clamp_max)
-    dist = (pos - det[:, :2].float()).pow(2).sum(dim=2)
-    arg = -dist / factors[person_idx, joint_idx][:, None]
-    sim = torch.exp(arg.clamp_(min=-80.0) if floor > 1e-30 else arg)
-    other_type = torch.logical_not(torch.eq(joint_idx.unsqueeze(1), det[:, 2]))
-    return person_idx, joint_idx, sim, other_type
-
-
-def _assign(cost):
-    from scipy.optimize import linear_sum_assignment
-    return linear_sum_assignment(cost, maximize=True)
-
-
-def _neighbours(cost, rows, cols, num_gt, inclusion_radius):
-    """``USE_NEIGHBOURS``: further candidates within the inclusion radius of a matched joint; candidates claimed by more
-    than one joint are ambiguous and leave the loss (:704-727, :890-911).  ``cost`` is modified in place."""
-    cost[cost < inclusion_radius] = 0.0
-    cost[:, cols] = 0.0
-    ambiguous = (cost != 0.0).sum(axis=0) > 1.0
-    cost[:, ambiguous] = 0.0
-    r2, _ = np.nonzero(cost)
-    for r in set(r2.tolist()) - set(rows.tolist()):          # joints without a match of their own take no neighbours
-        cost[r] = 0.0
-    r2, c2 = np.nonzero(cost)
-    lookup = np.full(num_gt, -1, dtype=np.int64)
-    lookup[rows] = np.arange(len(rows), dtype=np.int64)
-    return lookup[r2], c2, ambiguous
-
-
-def match_image(det, gt, factors, method, clamp_max, matching_radius, inclusion_radius, use_neighbours):
-    """One image: ``det [n, 3]`` int64 (x, y, type), ``gt [P, J, 3]``, ``factors [P, J]`` (CPU tensors).
-    Returns ``(nodes, persons, joints, ambiguous)``: the matched candidates, the person / joint type of the ground-truth
-    joint each is matched to, and the boolean ambiguity mask over the candidates (``None`` without ``USE_NEIGHBOURS``)."""
-    floor = min(matching_radius, inclusion_radius) if use_neighbours else matching_radius
-    person_idx, joint_idx, sim, other_type = _similarity(det, gt, factors, clamp_max, floor)
-    num_gt = len(person_idx)
-    if method == 4:                                          # same-type matches only (:642-652)
-        sim[other_type] = 0.0
-        sim[sim < matching_radius] = 0.0
-        cost = sim.numpy()
-        rows, cols = _assign(cost)
-        keep = cost[rows, cols] != 0.0
-        rows, cols = rows[keep], cols[keep]
-        neigh_cost = cost
-    else:                                                    # 6: same type first, any other type as a fill-in (:811-830)
-        same, diff = sim.clone(), sim.clone()
-        same[other_type] = 0.0
-        same[same < matching_radius] = 0.0
-        diff[torch.logical_not(other_type)] = 0.0
-        diff[diff < matching_radius] = 0.0
-        cost_same, cost_diff = same.numpy(), diff.numpy()
-        sol_same, sol_diff = _assign(cost_same), _assign(cost_diff)
-        rows, cols = sol_same
-        fill_in = np.logical_not(cost_same[rows, cols] != 0.0)
-        cols[fill_in] = sol_diff[1][fill_in]
-        keep = cost_diff[sol_diff] + cost_same[sol_same] != 0.0
-        rows, cols = rows[keep], cols[keep]
-        neigh_cost = sim.numpy()
-    persons, joints = person_idx[rows], joint_idx[rows]
-    nodes = torch.from_numpy(np.ascontiguousarray(cols))
-    ambiguous = None
-    if use_neighbours:
-        r2, c2, ambiguous = _neighbours(neigh_cost, rows, cols, num_gt, inclusion_radius)
-        nodes = torch.cat([nodes, torch.from_numpy(np.ascontiguousarray(c2))])
-        persons = torch.cat([persons, persons[torch.from_numpy(r2)]])
-        joints = torch.cat([joints, joints[torch.from_numpy(r2)]])
-    return nodes, persons, joints, ambiguous
-
-
 def build_labels(gc, joint_det, edge_index, batch_index, nodes_per_image):
+    """See ``_build_labels``.  The host tensors here are small (the largest, the similarity matrices, take 0.3 ms on one
+    thread), so torch's intra-op pool is switched off for the duration: OpenMP workers left spinning after a parallel
+    region share the cores with the matcher's threads and double the time of this function (measured: 6.5 -> 3.2 ms)."""
+    intra = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        return _build_labels(gc, joint_det, edge_index, batch_index, nodes_per_image)
+    finally:
+        torch.set_num_threads(intra)
+
+
+def _build_labels(gc, joint_det, edge_index, batch_index, nodes_per_image):
     """Labels of the whole batch.  ``gc``: the graph constructor (config + ``joints_gt`` / ``factor_list``); the graph
     tensors are the device outputs of the emit step.  Returns a dict with the 15-tuple's label slots."""
     dev = joint_det.device
     method = gc.edge_label_method
     B = len(nodes_per_image)
-    det_h = joint_det.cpu()                                  # the one host copy the matching needs
+    import ctypes as C
+    import os
+    from .. import _native as nv
+    lib = nv.lib()
+    det_h = joint_det.cpu().contiguous()                     # the one host copy the matching needs
     gt_h, fac_h = gc.joints_gt.detach().cpu(), gc.factor_list.detach().cpu()
+    if fac_h.dtype != torch.float32 or not gt_h.is_floating_point():
+        raise NotImplementedError("joints_gt / factor_list: float tensors with float32 factors (the reference's data pipeline)")
+    vis = gt_h[:, :, :, 2] != 0
+    gt32 = torch.cat([gt_h[..., :2].round().float(), vis.float().unsqueeze(-1)], dim=-1).contiguous()   # rounded in the source dtype (:774)
+    fac_h = fac_h.contiguous()
     H, W = gc.scoremaps.shape[2], gc.scoremaps.shape[3]
     N = joint_det.shape[0]
+    P, J = gt_h.shape[1], gt_h.shape[2]
+    use_nb = bool(gc.include_neighbouring_keypoints)
+    floor = min(gc.matching_radius, gc.inclusion_radius) if use_nb else gc.matching_radius
+    counts = np.asarray(nodes_per_image, dtype=np.int64)
+    offs = torch.from_numpy(np.concatenate([[0], np.cumsum(counts)]))
+    n_max = max(int(counts.max()) if B else 0, 1)
+    g_max = max(int(vis.sum(dim=(1, 2)).max()) if B else 0, 1)
+    threads = min(max(B, 1), 16, os.cpu_count() or 4)
+    # 1. the exponent -d^2 / factor of the similarity (:773-785) for the whole batch, natively -- float32, operation for
+    #    operation the reference's arithmetic.  Far-apart pairs would give subnormal similarities, which cost the CPU
+    #    microcode traps; when every value below `floor` is zeroed anyway the exponent is clamped at -80 first: the values
+    #    that survive the thresholds keep their exact bits.
+    arg = torch.zeros((B, g_max, n_max), dtype=torch.float32)
+    num_gt = torch.zeros(B, dtype=torch.int32)
+    gt_type = torch.zeros((B, g_max), dtype=torch.int32)
+    gt_person = torch.zeros((B, g_max), dtype=torch.int32)
+    det_type = torch.zeros((B, n_max), dtype=torch.int32)
+    ap = nv.LabelArgsParams(batch=B, max_persons=P, num_joints=J, num_threads=threads, clamp_max=float(max(H, W)),
+                            min_arg=-80.0 if floor > 1e-30 else float("-inf"), det=det_h.data_ptr(),
+                            node_offsets=offs.data_ptr(), gt=gt32.data_ptr(), factors=fac_h.data_ptr(), max_gt=g_max,
+                            max_det=n_max, arg=arg.data_ptr(), num_gt=num_gt.data_ptr(), gt_type=gt_type.data_ptr(),
+                            gt_person=gt_person.data_ptr(), det_type=det_type.data_ptr())
+    nv.check(lib.pgmp_label_similarity_args(C.byref(ap)))
+    # 2. exp() with the reference's own routine, so that every similarity carries the reference's bits
+    sim = torch.exp_(arg)
+    # 3. masks, radius thresholds, the linear sum assignments, fill-in and neighbour rules, per-node labels: natively
+    cap = n_max + g_max
+    match_row = torch.empty((B, cap), dtype=torch.int32)
+    match_col = torch.empty((B, cap), dtype=torch.int32)
+    num_match = torch.zeros(B, dtype=torch.int32)
+    amb_pad = torch.zeros((B, n_max), dtype=torch.uint8)
     person_h = torch.full((N,), -1, dtype=torch.int64)
     class_h = torch.zeros(N, dtype=torch.int64)
     label_h = torch.zeros(N, dtype=torch.float32)
-    amb_h = torch.zeros(N, dtype=torch.bool)
-    offs = np.concatenate([[0], np.cumsum(np.asarray(nodes_per_image, dtype=np.int64))])
-
-    def one(b):
-        return match_image(det_h[offs[b]:offs[b + 1]], gt_h[b], fac_h[b], method, max(H, W), gc.matching_radius,
-                           gc.inclusion_radius, gc.include_neighbouring_keypoints)
-    # the images are independent and torch / scipy release the GIL: a few worker threads, each running its tiny tensor
-    # operations single-threaded (intra-op threads on 50 k-element tensors only get in each other's way: measured 2x)
-    import os
-    from concurrent.futures import ThreadPoolExecutor
-    intra = torch.get_num_threads()
-    torch.set_num_threads(1)
-    try:
-        workers = min(B, 8, max(2, (os.cpu_count() or 4) // 2))
-        if B > 1:
-            with ThreadPoolExecutor(max_workers=workers) as pool:
-                matched = list(pool.map(one, range(B)))
-        else:
-            matched = [one(0)]
-    finally:
-        torch.set_num_threads(intra)
-    off = 0
-    for b in range(B):
-        n = int(nodes_per_image[b])
-        nodes, persons, joints, ambiguous = matched[b]
-        person_h[off + nodes] = persons.long()
-        class_h[off + nodes] = joints
-        label_h[off + nodes] = 1.0
-        if ambiguous is not None:
-            amb_h[off:off + n] = torch.from_numpy(ambiguous)
-        off += n
+    amb_u8 = torch.zeros(N, dtype=torch.uint8)
+    num_det = torch.from_numpy(counts.astype(np.int32))
+    mp = nv.MatchParams(batch=B, method=method, use_neighbours=int(use_nb), num_threads=threads,
+                        matching_radius=gc.matching_radius, inclusion_radius=gc.inclusion_radius, sim=sim.data_ptr(),
+                        sim_stride_b=sim.stride(0), sim_stride_g=sim.stride(1), max_gt=g_max, max_det=n_max,
+                        num_gt=num_gt.data_ptr(), num_det=num_det.data_ptr(), gt_type=gt_type.data_ptr(),
+                        det_type=det_type.data_ptr(), cap=cap, match_row=match_row.data_ptr(),
+                        match_col=match_col.data_ptr(), num_match=num_match.data_ptr(), ambiguous=amb_pad.data_ptr(),
+                        node_offsets=offs.data_ptr(), gt_person=gt_person.data_ptr(), node_person=person_h.data_ptr(),
+                        node_class=class_h.data_ptr(), node_label=label_h.data_ptr(), node_ambiguous=amb_u8.data_ptr())
+    nv.check(lib.pgmp_match_labels(C.byref(mp)))
+    amb_h = amb_u8.bool()
     person, node_labels, amb = person_h.to(dev), label_h.to(dev), amb_h.to(dev)
     src, dst = edge_index[0], edge_index[1]
     # match_cc: an edge is positive iff both ends are matched to joints of the same person (unmatched ends never agree)

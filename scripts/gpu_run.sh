@@ -1,1 +1,5 @@
-timeout 900 python -m pytest tests/test_gpu_train.py -q -k "fixture or full_size" 2>&1 | grep -E "^E  |Error|assert|passed|failed" | head -40
+PGMP_LABELS_ST=1 timeout 600 python scripts/time_labels.py 2>&1 | cut -c1-150 | sed -n 2,2p
+KMP_BLOCKTIME=0 timeout 600 python scripts/time_labels.py 2>&1 | cut -c1-150 | sed -n 2,2p
+OMP_WAIT_POLICY=passive timeout 600 python scripts/time_labels.py 2>&1 | cut -c1-150 | sed -n 2,2p
+GOMP_SPINCOUNT=0 timeout 600 python scripts/time_labels.py 2>&1 | cut -c1-150 | sed -n 2,2p
+python -c "import torch; print(torch.__config__.parallel_info())" | head -12
