@@ -234,8 +234,9 @@ __global__ void __launch_bounds__(kEdge2Threads, 1) edge_step_tc_kernel(const Ed
       att_bias = __ldg(a.ba + col);
       cur_col = col;
     }
-    // ---- P[dst] and Q[src]: this thread's half of its two table rows (swizzled tile images: logical 16-byte chunk q
-    //      of node n sits at position q ^ (n & 15)), requested before the first product is waited for, summed on arrival.
+    // ---- P[dst] and Q[src]: this thread's half of its two table rows (swizzled tile images: the logical 32-byte pair m
+    //      of node n sits at pair position m ^ (n & 7), umma::table_index), four 256-bit loads per half row, requested
+    //      before the first product is waited for, summed on arrival.
     //      Pad rows (e < 0) read row 0: finite values that nothing consumes.
     //      (Measured alternatives, per 10 steps: rows gathered cooperatively -- 16 threads per 256-byte row through the
     //      staging tile -- 3.28 ms instead of 2.26 ms: the L1 requests drop 8x but the latency lands on the critical
@@ -243,13 +244,15 @@ __global__ void __launch_bounds__(kEdge2Threads, 1) edge_step_tc_kernel(const Ed
     //      instead of 2.14 ms: the requests queue in front of the reduction's shared-memory reads.)
     float4 pq[8], qv[8];
     {
-      const float4* __restrict__ prow = reinterpret_cast<const float4*>(a.tab_p + (size_t)(e >= 0 ? dst : 0) * kD);
-      const float4* __restrict__ qrow = reinterpret_cast<const float4*>(a.tab_q + (size_t)(e >= 0 ? src : 0) * kD);
-      const int xd = e >= 0 ? dst & 15 : 0, xs = e >= 0 ? src & 15 : 0;
+      const float* __restrict__ prow = a.tab_p + (size_t)(e >= 0 ? dst : 0) * kD;
+      const float* __restrict__ qrow = a.tab_q + (size_t)(e >= 0 ? src : 0) * kD;
+      const int xd = e >= 0 ? dst & 7 : 0, xs = e >= 0 ? src & 7 : 0;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        pq[q] = __ldg(prow + ((8 * half + q) ^ xd));
-        qv[q] = __ldg(qrow + ((8 * half + q) ^ xs));
+      for (int q = 0; q < 4; ++q) {
+        const float8 pv = ldg256(prow + 8 * ((4 * half + q) ^ xd));
+        const float8 qq = ldg256(qrow + 8 * ((4 * half + q) ^ xs));
+        pq[2 * q] = pv.a; pq[2 * q + 1] = pv.b;
+        qv[2 * q] = qq.a; qv[2 * q + 1] = qq.b;
       }
     }
     TL(1);
@@ -306,10 +309,13 @@ __global__ void __launch_bounds__(kEdge2Threads, 1) edge_step_tc_kernel(const Ed
     // ---- R[type][dst]: this thread's half row, requested now, consumed by the third epilogue
     float4 rv[8];
     {
-      const float4* __restrict__ rrow = reinterpret_cast<const float4*>(a.tab_r + ((size_t)t * a.N + (e >= 0 ? dst : 0)) * kD);
-      const int xd = e >= 0 ? dst & 15 : 0;
+      const float* __restrict__ rrow = a.tab_r + ((size_t)t * a.N + (e >= 0 ? dst : 0)) * kD;
+      const int xd = e >= 0 ? dst & 7 : 0;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) rv[q] = __ldg(rrow + ((8 * half + q) ^ xd));
+      for (int q = 0; q < 4; ++q) {
+        const float8 r8 = ldg256(rrow + 8 * ((4 * half + q) ^ xd));
+        rv[2 * q] = r8.a; rv[2 * q + 1] = r8.b;
+      }
     }
     TL(7);
     mbar_wait(bar, phase);

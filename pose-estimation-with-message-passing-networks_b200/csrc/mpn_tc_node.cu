@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(kTabThreads, 1) node_tables_tc_kernel(
       named_bar_sync(1 + eg, kTile);                    // ... and the staging buffer is free
 #pragma unroll
       for (int q = 0; q < kD / 4; ++q)
-        sts128f(st + 4 * stage_index(row, 4 * q),
+        sts128f(st + 4 * table_index(row, 4 * q),
                 make_float4(d[4 * q] + bv[q].x, d[4 * q + 1] + bv[q].y, d[4 * q + 2] + bv[q].z, d[4 * q + 3] + bv[q].w));
       fence_async_smem();
       named_bar_sync(1 + eg, kTile);

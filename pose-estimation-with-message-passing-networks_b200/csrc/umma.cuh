@@ -229,6 +229,22 @@ __device__ __forceinline__ int stage_index(int row, int col) {
   return row * 64 + ((((col >> 2) ^ (row & 15)) << 2) | (col & 3));
 }
 
+// The per-node tables (P, Q, R) use a 32-byte-granular variant: the 32-byte pair m of row r sits at pair position
+// m ^ (r & 7).  Row-per-thread 16-byte shared-memory stores stay bank-conflict free (the 8 lanes of a phase hit 8
+// different pairs), and the step kernel fetches a row with 256-bit loads -- half the requests of 16-byte chunks
+// for gathers whose every lane touches a different row (the L1 request rate is what bounds them).
+__device__ __forceinline__ int table_index(int row, int col) {
+  return row * 64 + ((((col >> 3) ^ (row & 7)) << 3) | (col & 7));
+}
+struct float8 { float4 a, b; };
+__device__ __forceinline__ float8 ldg256(const float* p) {       // 32-byte aligned, read-only path
+  float8 v;
+  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v.a.x), "=f"(v.a.y), "=f"(v.a.z), "=f"(v.a.w), "=f"(v.b.x), "=f"(v.b.y), "=f"(v.b.z), "=f"(v.b.w)
+               : "l"(p));
+  return v;
+}
+
 // ---- operand tile writers ------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t sw128_offset(int row, int chunk16) {
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk16 ^ (row & 7)) << 4));

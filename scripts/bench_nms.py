@@ -18,11 +18,13 @@ sm = torch.from_numpy(np.stack([synthetic.synth_scoremap(b, J, S, K) for b in ra
 feat = torch.zeros(B, 4, S, S, device=dev)
 gcfg = pgmp_b200.config.bench_gc_config(k=K, graph_type="knn")
 out = {}
-for rows in [0, 32, 64, 128, 256, 512]:
-    if rows:
+for rows in [0, "notail", 128, 256, 512]:
+    os.environ.pop("PGMP_NMS_STRIP_ROWS", None)
+    os.environ.pop("PGMP_NMS_TAIL", None)
+    if rows == "notail":          # whole maps only: 544 CTAs on 444 slots, the last wave is partial
+        os.environ["PGMP_NMS_TAIL"] = "0"
+    elif rows:
         os.environ["PGMP_NMS_STRIP_ROWS"] = str(rows)
-    else:
-        os.environ.pop("PGMP_NMS_STRIP_ROWS", None)
 
     def step():
         return get_graph_constructor(gcfg, scoremaps=sm, tagmaps=sm, features=feat, joints_gt=None, factor_list=None, masks=None,
