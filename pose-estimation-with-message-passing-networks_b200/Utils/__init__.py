@@ -12,6 +12,8 @@ import numpy as np
 import torch
 
 from .. import _native as nv
+from .transformations import (gen_ann_format, gen_ann_format_correct, gen_ann_format_mean, persons_to_ann,  # noqa: F401
+                              reverse_affine_map, reverse_affine_map_points)
 
 
 class PendingGroups:
