@@ -158,6 +158,26 @@ int pgmp_gc_assemble_scoremaps(const float* stage1, const float* stage2, int32_t
                                int32_t h, int32_t w, int32_t H, int32_t W, int32_t mode, float* scoremaps, float* tags,
                                pgmp_stream_t stream);
 
+/* The same assembly fused into the detection: pgmp_gc_detect_fused() is pgmp_gc_detect() on the scoremaps
+ *   A_t = (stage2[t] + up(stage1[t])[:, :J]) / 2      (mode AVG; SMALL: up(stage1[t])[:, :J])
+ *   scoremaps = A_0                                                    (n_terms 1: hr_process_output, hrnet.py:587-611)
+ *   scoremaps[b, j, y, x] = (A_0[b, j, y, x] + A_1[b, flip_index[j], y, W - 1 - x]) / 2
+ *                                                                      (n_terms 2: the FLIP_TEST average of one scale,
+ *                                                                       PoseEstimation.py:343-364, 377-402, multi_scales_testing.py:162)
+ * evaluated by the NMS kernel's loader warps straight into its shared-memory row ring: the assembled map is never
+ * written to or re-read from HBM unless scoremaps_out asks for it (the pose-assembly tail reads it).  The scores of the
+ * detections are re-evaluated at their pixels with the same arithmetic.  p->scoremaps is ignored; width % 4 == 0,
+ * width <= 1024 and the threshold path (use_threshold 1) or a non-NULL scoremaps_out are required (PGMP_ERR_INVALID
+ * otherwise: run pgmp_gc_assemble_scoremaps + pgmp_gc_detect).  Bit-identical to those two calls. */
+typedef struct pgmp_gc_assembly {
+  const float* stage1[2];                    /* device [B, channels1, h, w]; [1] = outputs for the flipped image or NULL */
+  const float* stage2[2];                    /* device [B, num_joints, H, W] (mode AVG) */
+  int32_t channels1, h, w, mode, n_terms;
+  int32_t flip_index[32];                    /* n_terms 2: joint permutation (FLIP_CONFIG), num_joints entries */
+  float* scoremaps_out;                      /* optional device [B, J, H, W] */
+} pgmp_gc_assembly;
+int pgmp_gc_detect_fused(const pgmp_gc_params* p, const pgmp_gc_assembly* a, int64_t* counts, pgmp_stream_t stream);
+
 /* Reverse of the node-feature gather of pgmp_gc_emit (x[n, :] = features[b, :, y, x], ConstructGraph.py:265, 269) under
  * autograd -- end-to-end training, train.py:232: d_features[b, :, y, x] = sum of grad_x[n, :] over the nodes at that pixel
  * (candidates of different joint types can share one), summed in node order without atomics.  d_features ([B, C, H, W],

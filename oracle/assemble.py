@@ -44,3 +44,11 @@ def hr_process_output(s1, s2, num_joints, mode="avg"):
     if mode == "small":
         return up[:, :num_joints], tags
     raise NotImplementedError(mode)
+
+
+def flip_average(score, score_flipped, flip_index):
+    """Flip-test average of one scale (PoseEstimation.py:377-402 + multi_scales_testing.py:162): the flipped image's
+    assembled heatmaps are mirrored back along x (``torch.flip(output, [3])``), their joint channels permuted
+    (``[:, flip_index]``) and averaged with the plain ones, ``(heatmaps[0] + heatmaps[1]) / 2.0``."""
+    back = np.asarray(score_flipped, f32)[:, :, :, ::-1][:, list(flip_index)]
+    return ((np.asarray(score, f32) + back).astype(f32) * f32(0.5)).astype(f32)

@@ -42,6 +42,12 @@ class GcParams(C.Structure):
                 ("mask", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64)]
 
 
+class GcAssembly(C.Structure):
+    _fields_ = [("stage1", C.c_void_p * 2), ("stage2", C.c_void_p * 2), ("channels1", C.c_int32), ("h", C.c_int32),
+                ("w", C.c_int32), ("mode", C.c_int32), ("n_terms", C.c_int32), ("flip_index", C.c_int32 * 32),
+                ("scoremaps_out", C.c_void_p)]
+
+
 class GcOutputs(C.Structure):
     _fields_ = [("total_nodes", C.c_int64), ("total_edges", C.c_int64), ("features", C.c_void_p),
                 ("feat_stride_b", C.c_int64), ("feat_stride_c", C.c_int64), ("feat_stride_y", C.c_int64),
@@ -158,6 +164,7 @@ SYMBOLS = {
     "pgmp_profile_collect": (C.c_int, [C.c_char_p, C.c_int]),
     "pgmp_gc_workspace_bytes": (C.c_uint64, [C.POINTER(GcParams)]),
     "pgmp_gc_detect": (C.c_int, [C.POINTER(GcParams), C.c_void_p, C.c_void_p]),
+    "pgmp_gc_detect_fused": (C.c_int, [C.POINTER(GcParams), C.POINTER(GcAssembly), C.c_void_p, C.c_void_p]),
     "pgmp_gc_emit": (C.c_int, [C.POINTER(GcParams), C.POINTER(GcOutputs), C.c_void_p]),
     "pgmp_gc_gather_conv": (C.c_int, [C.POINTER(GatherConvParams), C.c_void_p]),
     "pgmp_gc_assemble_scoremaps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

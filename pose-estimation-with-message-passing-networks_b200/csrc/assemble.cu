@@ -25,13 +25,7 @@ struct AssembleArgs {
 };
 
 __device__ __forceinline__ void source_index(float scale, int dst, int in, int& i0, int& i1, float& l0, float& l1) {
-  float src = __fadd_rn(__fmul_rn(scale, __fadd_rn((float)dst, 0.5f)), -0.5f);
-  if (src < 0.f) src = 0.f;
-  i0 = (int)src;
-  if (i0 > in - 1) i0 = in - 1;
-  i1 = i0 + (i0 < in - 1 ? 1 : 0);
-  l1 = __fadd_rn(src, -(float)i0);
-  l0 = __fadd_rn(1.f, -l1);
+  bilinear_source_index(scale, dst, in, i0, i1, l0, l1);
 }
 
 constexpr int kAsmRows = 4;   // consecutive output rows per thread: the column indices / weights are computed once
@@ -62,9 +56,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(const AssembleArgs a) {
     float out[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float top = __fadd_rn(__fmul_rn(wx0[q], __ldg(r0 + i0[q])), __fmul_rn(wx1[q], __ldg(r0 + i1[q])));
-      const float bot = __fadd_rn(__fmul_rn(wx0[q], __ldg(r1 + i0[q])), __fmul_rn(wx1[q], __ldg(r1 + i1[q])));
-      out[q] = __fadd_rn(__fmul_rn(wy0, top), __fmul_rn(wy1, bot));
+      out[q] = bilinear_combine(wx0[q], wx1[q], wy0, wy1, __ldg(r0 + i0[q]), __ldg(r0 + i1[q]), __ldg(r1 + i0[q]), __ldg(r1 + i1[q]));
     }
     float* __restrict__ dst;
     if (heat) {

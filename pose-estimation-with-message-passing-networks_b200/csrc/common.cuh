@@ -54,6 +54,25 @@ __host__ __device__ constexpr T round_up(T a, T b) {
   return ceil_div(a, b) * b;
 }
 
+// ATen's bilinear source index / weights, align_corners = False (area_pixel_compute_source_index + the linear
+// weights of upsample_bilinear2d): src = scale * (dst + 0.5) - 0.5 clamped at 0, i1 = i0 + (i0 < in - 1), weights
+// (1 - l, l), every operation rounded separately.  Shared by assemble.cu and the fused NMS loader (gc.cu).
+__device__ __forceinline__ void bilinear_source_index(float scale, int dst, int in, int& i0, int& i1, float& l0, float& l1) {
+  float src = __fadd_rn(__fmul_rn(scale, __fadd_rn((float)dst, 0.5f)), -0.5f);
+  if (src < 0.f) src = 0.f;
+  i0 = (int)src;
+  if (i0 > in - 1) i0 = in - 1;
+  i1 = i0 + (i0 < in - 1 ? 1 : 0);
+  l1 = __fadd_rn(src, -(float)i0);
+  l0 = __fadd_rn(1.f, -l1);
+}
+// out = wy0 * (wx0 p00 + wx1 p01) + wy1 * (wx0 p10 + wx1 p11), products and sums rounded separately
+__device__ __forceinline__ float bilinear_combine(float wx0, float wx1, float wy0, float wy1, float p00, float p01, float p10, float p11) {
+  const float top = __fadd_rn(__fmul_rn(wx0, p00), __fmul_rn(wx1, p01));
+  const float bot = __fadd_rn(__fmul_rn(wx0, p10), __fmul_rn(wx1, p11));
+  return __fadd_rn(__fmul_rn(wy0, top), __fmul_rn(wy1, bot));
+}
+
 // bump allocator over the caller's workspace; with base == nullptr it only measures
 struct Carver {
   char* base;

@@ -85,9 +85,44 @@ constexpr int kNmsListCap = 512;     // per-CTA shared-memory candidate queue (c
 constexpr int kNmsKeepCap = 256;     // the producer warp's list of survivors (>= the running cut)
 constexpr int kNmsClaimMargin = 256; // a consumer thread claims a queue slot only while this many are free (<= 256 consumer threads race)
 
+// Scoremap assembly fused into the loader (pgmp_gc_detect_fused): the map the NMS runs on is
+//   A_t = (stage2_t + up(stage1_t)) / 2 (avg) or up(stage1_t) (small);  map = A_0, or with the flipped image's outputs
+//   map[j][y][x] = (A_0[j][y][x] + A_1[flip[j]][y][W - 1 - x]) / 2
+// with ATen's bilinear arithmetic (common.cuh) -- the same operations in the same order as assemble.cu, so the values
+// are bit-identical to the materialised map.
+constexpr int kNmsFuseLoaders = 4;   // loader warps of the fused kernel (each evaluates S / 4 rows of a stage)
+struct AsmDev {
+  const float* s1[2]; const float* s2[2];
+  int C1, h, w, mode, terms;
+  float scale_y, scale_x;
+  int flip[32];
+  float* out;
+};
+
+__device__ __forceinline__ float asm_term(const AsmDev& A, int t, int b, int j, int J, int H, int W, int y, int x) {
+  int y0, y1, x0, x1;
+  float wy0, wy1, wx0, wx1;
+  bilinear_source_index(A.scale_y, y, A.h, y0, y1, wy0, wy1);
+  bilinear_source_index(A.scale_x, x, A.w, x0, x1, wx0, wx1);
+  const float* __restrict__ plane = A.s1[t] + ((size_t)b * A.C1 + j) * A.h * A.w;
+  const float* __restrict__ r0 = plane + (size_t)y0 * A.w;
+  const float* __restrict__ r1 = plane + (size_t)y1 * A.w;
+  float v = bilinear_combine(wx0, wx1, wy0, wy1, __ldg(r0 + x0), __ldg(r0 + x1), __ldg(r1 + x0), __ldg(r1 + x1));
+  if (A.mode == PGMP_ASSEMBLE_AVG) v = __fmul_rn(__fadd_rn(__ldg(A.s2[t] + (((size_t)b * J + j) * H + y) * W + x), v), 0.5f);
+  return v;
+}
+// one pixel of the assembled map (the detections' scores when the map is not materialised)
+__device__ __forceinline__ float asm_value(const AsmDev& A, int b, int j, int J, int H, int W, int y, int x) {
+  float v = asm_term(A, 0, b, j, J, H, W, y, x);
+  if (A.terms == 2) v = __fmul_rn(__fadd_rn(v, asm_term(A, 1, b, A.flip[j], J, H, W, y, W - 1 - x)), 0.5f);
+  return v;
+}
+
 struct NmsArgs {
+  AsmDev asmb;
   const float* scoremaps; const float* mask;
   int J, H, W, xtiles, rows_per_cta, pitch, top_k, use_thr;
+  int src_rows, exact2x;                          // FUSE: half-resolution rows a ring stage can depend on; H = 2 h and W = 2 w
   float thr;
   uint64_t* cand_keys; uint32_t* cand_count; int cand_cap; uint32_t* flags;
 };
@@ -253,23 +288,27 @@ __device__ __forceinline__ bool nms_any_ge(float4 a, float4 b) {
 //   SELECTOR  drains the candidate queue, keeps the survivors and re-selects the running cut.
 // Consumer warps never meet at a CTA-wide barrier until the strip ends: a warp that runs into a blob does not hold
 // up the others, and neither the copies nor the cut wait for each other.
-template <int R, int RPW, bool VEC, bool MASK>
-__global__ void __launch_bounds__(320, 3) nms_candidates_kernel(const NmsArgs a) {
+// FUSE: the loader is kNmsFuseLoaders warps that EVALUATE the rows of the map (AsmDev) instead of copying them.
+template <int R, int RPW, bool VEC, bool MASK, bool FUSE>
+__global__ void __launch_bounds__(FUSE ? 288 + 32 * kNmsFuseLoaders : 320, FUSE ? 2 : 3) nms_candidates_kernel(const NmsArgs a) {
   constexpr int S = kNmsStageRows, RW = S / RPW, HALO = R > 0 ? 1 : 0;
   extern __shared__ __align__(128) uint8_t nms_smem[];
   const int P = a.pitch, H = a.H, W = a.W;
   uint64_t* s_keys = reinterpret_cast<uint64_t*>(nms_smem + (size_t)kNmsRingRows * P * 4);   // the queue (ring)
   uint64_t* s_keep = s_keys + kNmsListCap;                               // the selector's survivors
   uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_keep + kNmsKeepCap);
-  uint64_t* s_bars = reinterpret_cast<uint64_t*>(s_hist + 256);          // full[4], empty[4]
+  uint64_t* s_bars = reinterpret_cast<uint64_t*>(s_hist + 256);          // full[4], empty[4], raw[4] (FUSE: the stage's bulk copies)
   // [0] queue entries claimed [1] effective cut (score bits) [4] queue entries consumed [5] survivors [6] consumer warps done
   // [7] next work item
-  uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_bars + 2 * kNmsStages);
+  uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_bars + 3 * kNmsStages);
+  int2* s_ci = reinterpret_cast<int2*>(s_misc + 16);                     // FUSE: per map column the two source columns ...
+  float2* s_cw = reinterpret_cast<float2*>(s_ci + P);                    // ... and their weights
   const uint32_t ring_a = nms_smem_u32(nms_smem), keys_a = nms_smem_u32(s_keys), cnt_a = nms_smem_u32(s_misc);
   const uint32_t full_a = nms_smem_u32(s_bars), empty_a = full_a + 8u * kNmsStages;
 
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int n_cons = (int)(blockDim.x >> 5) - 2;                         // consumer warps
+  constexpr int NL = FUSE ? kNmsFuseLoaders : 1;                         // loader warps
+  const int n_cons = (int)(blockDim.x >> 5) - 1 - NL;                    // consumer warps
   const int bands = n_cons / RW;
   const int b = blockIdx.z, j = blockIdx.y;
   const int strip = blockIdx.x / a.xtiles, xt = blockIdx.x - strip * a.xtiles;
@@ -292,14 +331,155 @@ __global__ void __launch_bounds__(320, 3) nms_candidates_kernel(const NmsArgs a)
 
   for (int i = t; i < kNmsListCap; i += blockDim.x) s_keys[i] = 0ull;     // 0 = "empty slot"
   if (t == 0) {
-    for (int i = 0; i < kNmsStages; ++i) { nms_mbar_init(full_a + 8u * i, 1); nms_mbar_init(empty_a + 8u * i, (uint32_t)n_cons); }
+    for (int i = 0; i < kNmsStages; ++i) {
+      nms_mbar_init(full_a + 8u * i, (uint32_t)NL); nms_mbar_init(empty_a + 8u * i, (uint32_t)n_cons);
+      nms_mbar_init(empty_a + 8u * (kNmsStages + i), 1);
+    }
     s_misc[0] = 0; s_misc[4] = 0; s_misc[5] = 0; s_misc[6] = 0; s_misc[7] = 0;
     s_misc[1] = 1u;      // smallest positive float: "x >= cut" == "x > 0" until a real cut exists
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (FUSE) {
+    for (int x = t; x < W; x += blockDim.x) {
+      int i0, i1;
+      float l0, l1;
+      bilinear_source_index(a.asmb.scale_x, x, a.asmb.w, i0, i1, l0, l1);
+      s_ci[x] = make_int2(i0, i1);
+      s_cw[x] = make_float2(l0, l1);
+    }
+  }
   __syncthreads();
 
-  if (warp == n_cons) {
+  if (FUSE && warp >= n_cons && warp < n_cons + NL) {
+    // ---- ASSEMBLING LOADERS.  Global memory is only touched by the bulk-copy engine: per ring stage one copy brings the
+    //      full-resolution rows (stage 2) straight into the ring slot and one the few half-resolution rows they depend
+    //      on (stage 1) into a double-buffered source tile, two stages ahead; the loader warps (warp lw: rows lw, lw + NL,
+    //      ... of the stage) then turn the slot into the assembled rows IN PLACE -- source values, column indices /
+    //      weights and the stage-2 value all come from shared memory -- and hand it to the consumers.  One tile spans
+    //      the map's width (launch_nms), ring column = map column.  Only the flipped image's stage-2 values (mirrored
+    //      columns) are read with ordinary loads.
+    const AsmDev& A = a.asmb;
+    const int lw = warp - n_cons;
+    const int sw = A.w, src_cap = a.src_rows * sw;               // floats per source tile
+    float* s_src = reinterpret_cast<float*>(s_cw + P);           // [2 buffers][terms][src_rows][w]
+    const uint32_t src_a = nms_smem_u32(s_src), raw_a = empty_a + 8u * kNmsStages;
+    const bool avg = A.mode == PGMP_ASSEMBLE_AVG, two = A.terms == 2;
+    const int jf = two ? A.flip[j] : j;
+    const float* __restrict__ plane0 = A.s1[0] + ((size_t)b * A.C1 + j) * A.h * sw;
+    const float* __restrict__ plane1 = A.s1[two ? 1 : 0] + ((size_t)b * A.C1 + jf) * A.h * sw;
+    const float* __restrict__ full0 = avg ? A.s2[0] + (size_t)bj * H * W : nullptr;
+    const float* __restrict__ full1 = avg && two ? A.s2[1] + ((size_t)b * a.J + jf) * H * W : nullptr;
+    auto src_first = [&](int y) { int i0, i1; float l0, l1; bilinear_source_index(A.scale_y, y, A.h, i0, i1, l0, l1); return i0; };
+    auto src_last = [&](int y) { int i0, i1; float l0, l1; bilinear_source_index(A.scale_y, y, A.h, i0, i1, l0, l1); return i1; };
+    auto issue = [&](int L) {                                    // one thread: the copies of stage L
+      const unsigned stg = (unsigned)L % kNmsStages;
+      if (L >= kNmsStages) {
+        nms_mbar_wait(empty_a + 8u * stg, (uint32_t)(L / kNmsStages + 1) & 1u);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the slot was last written by ordinary stores
+      }
+      const int ys = ybase + L * S, r_lo = max(ys, 0), nrows = min(ys + S, y_need) - r_lo;
+      const uint32_t bar = raw_a + 8u * stg;
+      if (nrows <= 0) { nms_mbar_arrive(bar); return; }
+      const int sy = src_first(r_lo), ns = src_last(r_lo + nrows - 1) - sy + 1;
+      const uint32_t sbytes = (uint32_t)(ns * sw) * 4u, fbytes = avg ? (uint32_t)nrows * rowb : 0u;
+      nms_mbar_expect_tx(bar, fbytes + sbytes * (two ? 2u : 1u));
+      if (avg) nms_bulk_load(ring_a + (uint32_t)((unsigned)(r_lo - ybase) % kNmsRingRows) * rowb, full0 + (size_t)r_lo * W, fbytes, bar);
+      const uint32_t sdst = src_a + (uint32_t)((L & 1) * 2 * src_cap) * 4u;
+      nms_bulk_load(sdst, plane0 + (size_t)sy * sw, sbytes, bar);
+      if (two) nms_bulk_load(sdst + (uint32_t)src_cap * 4u, plane1 + (size_t)sy * sw, sbytes, bar);
+    };
+    if (lw == 0 && lane == 0) {
+      issue(0);
+      if (n_stage > 1) issue(1);
+    }
+    for (int L = 0; L < n_stage; ++L) {
+      const unsigned stg = (unsigned)L % kNmsStages;
+      const int ys = ybase + L * S, r_lo = max(ys, 0), nrows = min(ys + S, y_need) - r_lo;
+      nms_mbar_wait(raw_a + 8u * stg, (uint32_t)(L / kNmsStages) & 1u);
+      const int sy = nrows > 0 ? src_first(r_lo) : 0;
+      float* slot = reinterpret_cast<float*>(nms_smem) + (size_t)(stg * S) * P;
+      const float* __restrict__ src0 = s_src + (size_t)(L & 1) * 2 * src_cap;
+      const float* __restrict__ src1 = src0 + src_cap;
+      for (int r = lw; r < S; r += NL) {
+        const int y = ys + r;
+        float4* dst = reinterpret_cast<float4*>(slot + (size_t)r * P);
+        if ((unsigned)y >= (unsigned)H) {             // rows above / below the image read as zeros
+          for (int i = lane; i < P / 4; i += 32) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          continue;
+        }
+        if (y >= y_need) continue;
+        int y0s, y1s;
+        float wy0, wy1;
+        bilinear_source_index(A.scale_y, y, A.h, y0s, y1s, wy0, wy1);
+        const int o0 = (y0s - sy) * sw, o1 = (y1s - sy) * sw;
+        float4* __restrict__ gout = A.out ? reinterpret_cast<float4*>(A.out + ((size_t)bj * H + y) * W) : nullptr;
+        const float* __restrict__ f1row = full1 ? full1 + (size_t)y * W : nullptr;
+        // up-sampled stage 1 at map columns x .. x + 3.  Exactly doubled maps (H = 2 h, W = 2 w: HigherHRNet) need the four
+        // source columns x / 2 - 1 .. x / 2 + 2 only, with weights 1/4, 3/4 (what bilinear_source_index yields there:
+        // scale 1/2 makes every step exact; column 0 has weights 1, 0) -- 6 shared loads; other sizes go through the
+        // per-column index / weight tables.
+        auto up4 = [&](const float* __restrict__ sp, int x, float (&o)[4]) {
+          const float* __restrict__ p0 = sp + o0; const float* __restrict__ p1 = sp + o1;
+          if (a.exact2x) {
+            const int m2 = x >> 1, ia = max(m2 - 1, 0), id = min(m2 + 2, sw - 1);
+            const float2 t = *reinterpret_cast<const float2*>(p0 + m2), u = *reinterpret_cast<const float2*>(p1 + m2);
+            const float ta = p0[ia], td = p0[id], ua = p1[ia], ud = p1[id];
+            if (x == 0) o[0] = bilinear_combine(1.f, 0.f, wy0, wy1, t.x, t.y, u.x, u.y);
+            else o[0] = bilinear_combine(0.25f, 0.75f, wy0, wy1, ta, t.x, ua, u.x);
+            o[1] = bilinear_combine(0.75f, 0.25f, wy0, wy1, t.x, t.y, u.x, u.y);
+            o[2] = bilinear_combine(0.25f, 0.75f, wy0, wy1, t.x, t.y, u.x, u.y);
+            o[3] = bilinear_combine(0.75f, 0.25f, wy0, wy1, t.y, td, u.y, ud);
+            return;
+          }
+          const int4 ca = *reinterpret_cast<const int4*>(s_ci + x), cb = *reinterpret_cast<const int4*>(s_ci + x + 2);
+          const float4 wa = *reinterpret_cast<const float4*>(s_cw + x), wb = *reinterpret_cast<const float4*>(s_cw + x + 2);
+          o[0] = bilinear_combine(wa.x, wa.y, wy0, wy1, p0[ca.x], p0[ca.y], p1[ca.x], p1[ca.y]);
+          o[1] = bilinear_combine(wa.z, wa.w, wy0, wy1, p0[ca.z], p0[ca.w], p1[ca.z], p1[ca.w]);
+          o[2] = bilinear_combine(wb.x, wb.y, wy0, wy1, p0[cb.x], p0[cb.y], p1[cb.x], p1[cb.y]);
+          o[3] = bilinear_combine(wb.z, wb.w, wy0, wy1, p0[cb.z], p0[cb.w], p1[cb.z], p1[cb.w]);
+        };
+        auto group = [&](int c4) -> float4 {          // the assembled map at columns 4 c4 .. 4 c4 + 3 of row y
+          const int x = 4 * c4;
+          float4 fv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (f1row) fv = __ldg(reinterpret_cast<const float4*>(f1row + (W - 4 - x)));   // requested first: the one global load
+          float o[4];
+          up4(src0, x, o);
+          if (avg) {
+            const float4 v = dst[c4];                                         // the stage-2 values the bulk copy put there
+            o[0] = __fmul_rn(__fadd_rn(v.x, o[0]), 0.5f); o[1] = __fmul_rn(__fadd_rn(v.y, o[1]), 0.5f);
+            o[2] = __fmul_rn(__fadd_rn(v.z, o[2]), 0.5f); o[3] = __fmul_rn(__fadd_rn(v.w, o[3]), 0.5f);
+          }
+          if (two) {                                  // the flipped image's map, mirrored: columns W - 1 - (x + q)
+            float f[4];
+            up4(src1, W - 4 - x, f);
+            if (avg) {
+              f[0] = __fmul_rn(__fadd_rn(fv.x, f[0]), 0.5f); f[1] = __fmul_rn(__fadd_rn(fv.y, f[1]), 0.5f);
+              f[2] = __fmul_rn(__fadd_rn(fv.z, f[2]), 0.5f); f[3] = __fmul_rn(__fadd_rn(fv.w, f[3]), 0.5f);
+            }
+            o[0] = __fmul_rn(__fadd_rn(o[0], f[3]), 0.5f); o[1] = __fmul_rn(__fadd_rn(o[1], f[2]), 0.5f);
+            o[2] = __fmul_rn(__fadd_rn(o[2], f[1]), 0.5f); o[3] = __fmul_rn(__fadd_rn(o[3], f[0]), 0.5f);
+          }
+          return make_float4(o[0], o[1], o[2], o[3]);
+        };
+        int c4 = lane;
+        if (!two)                                     // two groups per pass: the second group's loads are not held up by the first's store
+          for (; c4 + 32 < W / 4; c4 += 64) {
+            const float4 va = group(c4), vb = group(c4 + 32);
+            dst[c4] = va; dst[c4 + 32] = vb;
+            if (gout) { gout[c4] = va; gout[c4 + 32] = vb; }
+          }
+        for (; c4 < W / 4; c4 += 32) {
+          const float4 v = group(c4);
+          dst[c4] = v;
+          if (gout) gout[c4] = v;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) nms_mbar_arrive(full_a + 8u * stg);
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * NL) : "memory");   // every loader is done with this stage's source tile
+      if (lw == 0 && lane == 0 && L + 2 < n_stage) issue(L + 2);
+    }
+  } else if (!FUSE && warp == n_cons) {
     // ---- LOADER: stage L = map rows [ybase + L S, ybase + (L + 1) S) -> ring rows (L mod 4) S ...
     for (int L = 0; L < n_stage; ++L) {
       if (L >= kNmsStages) nms_mbar_wait(empty_a + 8u * ((unsigned)L % kNmsStages), (uint32_t)(L / kNmsStages + 1) & 1u);
@@ -340,7 +520,7 @@ __global__ void __launch_bounds__(320, 3) nms_candidates_kernel(const NmsArgs a)
       }
       __syncwarp();
     }
-  } else if (warp == n_cons + 1) {
+  } else if (warp == n_cons + NL) {
     // ---- SELECTOR: drain the candidate queue.  Entries are taken in claim order up to the first one whose 8-byte store
     //      has not landed yet; survivors (>= cut) join the keep list, the slots are zeroed and released.
     const uint32_t trigger = (uint32_t)min(kNmsKeepCap - 64, max(3 * a.top_k, 96));   // survivors that start a re-selection
@@ -639,7 +819,7 @@ __global__ void __launch_bounds__(256) layout_nodes_kernel(
     const float* __restrict__ scoremaps, const float* __restrict__ mask, int J, int H, int W, int use_thr,
     int max_det, int max_nodes, const int32_t* __restrict__ det_idx, const int32_t* __restrict__ det_n1,
     const int32_t* __restrict__ det_n2, int32_t* __restrict__ node_xyt, float* __restrict__ node_score,
-    int32_t* __restrict__ node_count, uint32_t* __restrict__ flags) {
+    int32_t* __restrict__ node_count, uint32_t* __restrict__ flags, const AsmDev A, const int fused) {
   extern __shared__ int32_t s_start[];   // [2][J]
   __shared__ int s_total;
   const int b = blockIdx.x;
@@ -662,7 +842,7 @@ __global__ void __launch_bounds__(256) layout_nodes_kernel(
       const int flat = packed & 0x7fffffff;                 // bit 31: a zero-score pixel that pads the top-k block
       const int y = flat / W, x = flat - y * W;
       const int node = i < n1 ? s_start[j] + i : s_start[J + j] + (i - n1);
-      float s = packed < 0 ? 0.f : map[flat];
+      float s = packed < 0 ? 0.f : (fused ? asm_value(A, b, j, J, H, W, y, x) : map[flat]);
       if (mask && packed >= 0) s = s * mask[(size_t)b * H * W + flat];
       if (!use_thr) s = __fadd_rn(s, 1e-10f);   // CG.py:1189
       node_xyt[(size_t)b * max_nodes + node] = pack_xyt(x, y, j);
@@ -958,7 +1138,7 @@ int validate(const pgmp_gc_params* p) {
   if (p->graph_type != PGMP_GRAPH_KNN && p->graph_type != PGMP_GRAPH_FULLY)
     return set_error(PGMP_ERR_INVALID, "graph_type %d", p->graph_type);
   if (p->edge_features == 0 || (p->edge_features & ~3)) return set_error(PGMP_ERR_INVALID, "edge_features %d", p->edge_features);
-  if (!p->scoremaps || !p->workspace) return set_error(PGMP_ERR_INVALID, "null device pointer");
+  if (!p->workspace) return set_error(PGMP_ERR_INVALID, "null device pointer");
   return PGMP_OK;
 }
 
@@ -985,8 +1165,8 @@ int nms_strip_rows(const pgmp_gc_params& p, int xtiles) {
 }
 
 template <int R>
-int launch_nms(const pgmp_gc_params& p, const GcWorkspace& w, cudaStream_t st) {
-  const bool vec = (p.width % 4 == 0) && (reinterpret_cast<uintptr_t>(p.scoremaps) % 16 == 0) &&
+int launch_nms(const pgmp_gc_params& p, const GcWorkspace& w, cudaStream_t st, const AsmDev* fuse) {
+  const bool vec = (p.width % 4 == 0) && (fuse || reinterpret_cast<uintptr_t>(p.scoremaps) % 16 == 0) &&
                    (reinterpret_cast<uintptr_t>(p.mask) % 16 == 0);
   const int chunks = ceil_div(p.width, 4);
   const int xtiles = ceil_div(chunks, 256);
@@ -994,7 +1174,13 @@ int launch_nms(const pgmp_gc_params& p, const GcWorkspace& w, cudaStream_t st) {
   const int bands = threads / 32;
   const int rw = bands <= 4 ? 2 : 1;                              // row groups: consumer warps = bands x rw <= 8 (+ loader and selector warps)
   NmsArgs a;
-  a.scoremaps = p.scoremaps; a.mask = p.mask; a.J = p.num_joints; a.H = p.height; a.W = p.width; a.xtiles = xtiles;
+  if (fuse) {
+    if (!vec || xtiles != 1) return set_error(PGMP_ERR_INVALID, "fused assembly needs width %% 4 == 0, width <= 1024 and a 16-byte aligned mask");
+    a.asmb = *fuse;
+  } else {
+    a.asmb = AsmDev{};
+  }
+  a.scoremaps = fuse ? nullptr : p.scoremaps; a.mask = p.mask; a.J = p.num_joints; a.H = p.height; a.W = p.width; a.xtiles = xtiles;
   a.rows_per_cta = nms_strip_rows(p, xtiles);
   // ring row pitch (floats): the map's width when one tile spans it (a stage is one contiguous bulk copy), else the
   // tile's columns + 4 either side; unaligned maps: rounded up and zero-filled by the copying warp
@@ -1002,14 +1188,28 @@ int launch_nms(const pgmp_gc_params& p, const GcWorkspace& w, cudaStream_t st) {
   a.pitch = vec ? cols : round_up(cols, 4) + 4;
   a.top_k = p.top_k; a.use_thr = p.use_threshold; a.thr = p.threshold;
   a.cand_keys = w.cand_keys; a.cand_count = w.cand_count; a.cand_cap = p.cand_capacity; a.flags = w.flags;
-  const size_t smem = (size_t)kNmsRingRows * a.pitch * 4 + (size_t)(kNmsListCap + kNmsKeepCap) * 8 + 256 * 4 + 2 * kNmsStages * 8 + 64;
+  a.src_rows = 0; a.exact2x = 0;
+  if (fuse) {
+    if (fuse->w % 4) return set_error(PGMP_ERR_INVALID, "fused assembly needs a stage-1 width that is a multiple of 4 (bulk copies of whole rows)");
+    a.src_rows = (int)((double)fuse->h / p.height * kNmsStageRows) + 3;
+    if (a.src_rows > fuse->h) a.src_rows = fuse->h;
+    a.exact2x = (p.height == 2 * fuse->h && p.width == 2 * fuse->w && fuse->w >= 2) ? 1 : 0;
+  }
+  const size_t smem = (size_t)kNmsRingRows * a.pitch * 4 + (size_t)(kNmsListCap + kNmsKeepCap) * 8 + 256 * 4 + 3 * kNmsStages * 8 + 64 +
+                      (fuse ? (size_t)a.pitch * 16 + (size_t)2 * 2 * a.src_rows * fuse->w * 4 : 0);
   const dim3 grid(ceil_div(p.height, a.rows_per_cta) * xtiles, p.num_joints, p.batch);
-  const int block = 32 * (bands * rw + 2);
-#define PGMP_NMS_LAUNCH2(RPW, V, M)                                                                                             \
-  do {                                                                                                                          \
-    PGMP_CUDA(cudaFuncSetAttribute(nms_candidates_kernel<R, RPW, V, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    PGMP_LAUNCH((nms_candidates_kernel<R, RPW, V, M>), grid, block, smem, st, a);                                               \
+  const int block = 32 * (bands * rw + 1 + (fuse ? kNmsFuseLoaders : 1));
+#define PGMP_NMS_LAUNCH3(RPW, V, M, F)                                                                                             \
+  do {                                                                                                                             \
+    PGMP_CUDA(cudaFuncSetAttribute(nms_candidates_kernel<R, RPW, V, M, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    PGMP_LAUNCH((nms_candidates_kernel<R, RPW, V, M, F>), grid, block, smem, st, a);                                               \
   } while (0)
+#define PGMP_NMS_LAUNCH2(RPW, V, M) PGMP_NMS_LAUNCH3(RPW, V, M, false)
+  if (fuse) {
+    if (rw == 2) { if (p.mask) PGMP_NMS_LAUNCH3(4, true, true, true); else PGMP_NMS_LAUNCH3(4, true, false, true); }
+    else { if (p.mask) PGMP_NMS_LAUNCH3(8, true, true, true); else PGMP_NMS_LAUNCH3(8, true, false, true); }
+    return PGMP_OK;
+  }
 #define PGMP_NMS_LAUNCH(V, M)                                             \
   do {                                                                    \
     if (rw == 2) PGMP_NMS_LAUNCH2(4, V, M); else PGMP_NMS_LAUNCH2(8, V, M); \
@@ -1018,6 +1218,7 @@ int launch_nms(const pgmp_gc_params& p, const GcWorkspace& w, cudaStream_t st) {
   else { if (p.mask) PGMP_NMS_LAUNCH(false, true); else PGMP_NMS_LAUNCH(false, false); }
 #undef PGMP_NMS_LAUNCH
 #undef PGMP_NMS_LAUNCH2
+#undef PGMP_NMS_LAUNCH3
   return PGMP_OK;
 }
 
@@ -1033,10 +1234,21 @@ extern "C" uint64_t pgmp_gc_workspace_bytes(const pgmp_gc_params* p) {
   return carve(q).bytes;
 }
 
-extern "C" int pgmp_gc_detect(const pgmp_gc_params* p, int64_t* counts, pgmp_stream_t stream) {
+static int gc_detect(const pgmp_gc_params* p_in, const AsmDev* fuse, int64_t* counts, pgmp_stream_t stream) {
+  pgmp_gc_params q;
+  if (p_in && fuse) {           // the map the later kernels may read: the materialised one, if any
+    q = *p_in;
+    q.scoremaps = fuse->out;
+    p_in = &q;
+  }
+  const pgmp_gc_params* p = p_in;
   int rc = validate(p);
   if (rc != PGMP_OK) return rc;
   if (!counts) return set_error(PGMP_ERR_INVALID, "null counts");
+  if (!fuse && !p->scoremaps) return set_error(PGMP_ERR_INVALID, "null device pointer");
+  const bool lazy = fuse && !fuse->out;                   // scores re-evaluated at the detections
+  if (lazy && !p->use_threshold)
+    return set_error(PGMP_ERR_INVALID, "the no-threshold path pads with zero-score pixels of the map: pass scoremaps_out");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const GcWorkspace w = carve(*p);
   if (w.bytes > p->workspace_bytes)
@@ -1046,11 +1258,11 @@ extern "C" int pgmp_gc_detect(const pgmp_gc_params* p, int64_t* counts, pgmp_str
   PGMP_CUDA(cudaMemsetAsync(w.cand_count, 0, sizeof(uint32_t) * B * J, st));
   PGMP_CUDA(cudaMemsetAsync(w.flags, 0, sizeof(uint32_t), st));
   switch (p->pool_kernel / 2) {
-    case 0: rc = launch_nms<0>(*p, w, st); break;
-    case 1: rc = launch_nms<1>(*p, w, st); break;
-    case 2: rc = launch_nms<2>(*p, w, st); break;
-    case 3: rc = launch_nms<3>(*p, w, st); break;
-    default: rc = launch_nms<4>(*p, w, st); break;
+    case 0: rc = launch_nms<0>(*p, w, st, fuse); break;
+    case 1: rc = launch_nms<1>(*p, w, st, fuse); break;
+    case 2: rc = launch_nms<2>(*p, w, st, fuse); break;
+    case 3: rc = launch_nms<3>(*p, w, st, fuse); break;
+    default: rc = launch_nms<4>(*p, w, st, fuse); break;
   }
   if (rc != PGMP_OK) return rc;
   int P = 1;
@@ -1063,7 +1275,7 @@ extern "C" int pgmp_gc_detect(const pgmp_gc_params* p, int64_t* counts, pgmp_str
               p->pool_kernel / 2, w.det_idx, w.det_n1, w.det_n2, w.flags);
   PGMP_LAUNCH(layout_nodes_kernel, B, 256, sizeof(int32_t) * 2 * J, st, p->scoremaps, p->mask, J, p->height, p->width,
               p->use_threshold, p->max_det_per_type, p->max_nodes, w.det_idx, w.det_n1, w.det_n2, w.node_xyt,
-              w.node_score, w.node_count, w.flags);
+              w.node_score, w.node_count, w.flags, lazy ? *fuse : AsmDev{}, lazy ? 1 : 0);
   const int fully = p->graph_type == PGMP_GRAPH_FULLY;
   if (!fully) {
     PGMP_CUDA(cudaMemsetAsync(w.adj, 0, sizeof(uint32_t) * (size_t)B * p->max_nodes * (p->max_nodes / 32), st));
@@ -1077,6 +1289,36 @@ extern "C" int pgmp_gc_detect(const pgmp_gc_params* p, int64_t* counts, pgmp_str
   PGMP_LAUNCH(totals_kernel, 1, 32, 0, st, w.node_count, w.rowptr, B, p->max_nodes, w.node_base, w.edge_base, w.flags,
               counts);
   return PGMP_OK;
+}
+
+extern "C" int pgmp_gc_detect(const pgmp_gc_params* p, int64_t* counts, pgmp_stream_t stream) {
+  return gc_detect(p, nullptr, counts, stream);
+}
+
+extern "C" int pgmp_gc_detect_fused(const pgmp_gc_params* p, const pgmp_gc_assembly* a, int64_t* counts, pgmp_stream_t stream) {
+  if (!p || !a) return set_error(PGMP_ERR_INVALID, "null params");
+  if (a->mode != PGMP_ASSEMBLE_AVG && a->mode != PGMP_ASSEMBLE_SMALL) return set_error(PGMP_ERR_INVALID, "mode %d", a->mode);
+  if (a->n_terms != 1 && a->n_terms != 2) return set_error(PGMP_ERR_INVALID, "n_terms %d", a->n_terms);
+  if (a->h <= 0 || a->w <= 0 || a->channels1 < p->num_joints || p->num_joints > 32)
+    return set_error(PGMP_ERR_INVALID, "bad stage sizes (channels1 %d, %d x %d, %d joints)", a->channels1, a->h, a->w, p->num_joints);
+  AsmDev d{};
+  for (int t = 0; t < a->n_terms; ++t) {
+    if (!a->stage1[t] || (a->mode == PGMP_ASSEMBLE_AVG && !a->stage2[t])) return set_error(PGMP_ERR_INVALID, "null stage pointer (term %d)", t);
+    if (reinterpret_cast<uintptr_t>(a->stage2[t]) % 16) return set_error(PGMP_ERR_INVALID, "stage2 must be 16-byte aligned");
+    d.s1[t] = a->stage1[t]; d.s2[t] = a->stage2[t];
+  }
+  if (reinterpret_cast<uintptr_t>(a->scoremaps_out) % 16) return set_error(PGMP_ERR_INVALID, "scoremaps_out must be 16-byte aligned");
+  d.C1 = a->channels1; d.h = a->h; d.w = a->w; d.mode = a->mode; d.terms = a->n_terms;
+  d.scale_y = (float)a->h / (float)p->height; d.scale_x = (float)a->w / (float)p->width;
+  for (int j = 0; j < 32; ++j) {
+    d.flip[j] = j;
+    if (a->n_terms == 2 && j < p->num_joints) {
+      if (a->flip_index[j] < 0 || a->flip_index[j] >= p->num_joints) return set_error(PGMP_ERR_INVALID, "flip_index[%d] = %d", j, a->flip_index[j]);
+      d.flip[j] = a->flip_index[j];
+    }
+  }
+  d.out = a->scoremaps_out;
+  return gc_detect(p, &d, counts, stream);
 }
 
 extern "C" int pgmp_gc_emit(const pgmp_gc_params* p, const pgmp_gc_outputs* o, pgmp_stream_t stream) {

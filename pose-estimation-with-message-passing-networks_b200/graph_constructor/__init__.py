@@ -86,6 +86,60 @@ class ConvUpsampleFeatures:
         return self._wt, self._b
 
 
+class HeadStages:
+    """Lazy stand-in for the ``scoremaps`` argument: the two output stages of the HigherHRNet head, assembled INSIDE the
+    NMS kernel's load stage (``pgmp_gc_detect_fused``) instead of by ``hr_process_output`` in front of it
+    (src/Models/HigherHRNet/hrnet.py:587-611: interpolate the half-resolution stage, average with the full-resolution
+    one).  The assembled ``[B, J, H, W]`` map -- 570 MB at 32 x 17 x 512 x 512 -- is then neither written nor re-read;
+    ``keep_scoremaps=True`` still writes it (``.scoremaps`` after the detection) for the pose-assembly tail
+    (``refine`` / ``adjust``).  ``flipped`` / ``flip_index`` add the flip-test average of one scale
+    (PoseEstimation.py:343-402, multi_scales_testing.py:162): ``(A + A_flipped[:, flip_index, :, ::-1]) / 2``.
+    Results are bit-identical to ``hr_process_output`` + the plain constructor."""
+
+    def __init__(self, outputs, num_joints, mode="avg", flipped=None, flip_index=None, keep_scoremaps=False):
+        s1, s2 = outputs
+        if mode not in ("avg", "small"):
+            raise NotImplementedError("mode %r ('large' needs no assembly: pass scoremap_2)" % (mode,))
+        if flipped is not None and flip_index is None:
+            raise ValueError("flipped outputs need flip_index (FLIP_CONFIG)")
+        self.terms = [(s1, s2)] + ([tuple(flipped)] if flipped is not None else [])
+        for a, b in self.terms:
+            nv.require_cuda(a, "scoremap_1", torch.float32)
+            nv.require_cuda(b, "scoremap_2", torch.float32)
+            if a.shape != s1.shape or b.shape != s2.shape:
+                raise ValueError("flipped outputs must have the shapes of the plain ones")
+        B, C1 = s1.shape[0], s1.shape[1]
+        if C1 < num_joints or s2.shape[0] != B or (mode == "avg" and s2.shape[1] != num_joints):
+            raise ValueError("scoremap_1 must be [B, >= J, h, w] and scoremap_2 [B, J, H, W]")
+        if num_joints > 32:
+            raise NotImplementedError("more than 32 joint types")
+        self.mode, self.num_joints = mode, num_joints
+        self.flip_index = [int(i) for i in flip_index] if flip_index is not None else None
+        if self.flip_index is not None and sorted(self.flip_index) != list(range(num_joints)):
+            raise ValueError("flip_index must be a permutation of the joint types")
+        self.keep_scoremaps = keep_scoremaps
+        self.scoremaps = None
+        self.shape = (B, num_joints, s2.shape[2], s2.shape[3])
+        self.device = s1.device
+        self.dtype = torch.float32
+
+    def dim(self):
+        return 4
+
+    def assembly(self, out):
+        """The C-ABI description of the terms (tensors made contiguous are kept alive on ``self``)."""
+        self._keep = [(a.detach().contiguous(), b.detach().contiguous()) for a, b in self.terms]
+        a = nv.GcAssembly()
+        for t, (x1, x2) in enumerate(self._keep):
+            a.stage1[t], a.stage2[t] = x1.data_ptr(), x2.data_ptr()
+        a.channels1, a.h, a.w = self._keep[0][0].shape[1:4]
+        a.mode, a.n_terms = (0 if self.mode == "avg" else 1), len(self._keep)
+        for j, i in enumerate(self.flip_index or []):
+            a.flip_index[j] = i
+        a.scoremaps_out = out.data_ptr() if out is not None else None
+        return a
+
+
 class NaiveGraphConstructor:
     """Same constructor signature as the reference class (ConstructGraph.py:11)."""
 
@@ -96,7 +150,10 @@ class NaiveGraphConstructor:
             raise RuntimeError("pgmp_b200 graph constructor needs a CUDA device (no CPU fallback)")
         # pinned host heatmaps are copied by the detection launch itself (on its stream, non-blocking): with
         # detect_async() the copy of the next batch overlaps the current batch's kernels
-        self.scoremaps = scoremaps if _host_resident(scoremaps, need_contiguous=True) else scoremaps.to(self.device)
+        if isinstance(scoremaps, HeadStages):
+            self.scoremaps = scoremaps                       # assembled inside the NMS kernel (pgmp_gc_detect_fused)
+        else:
+            self.scoremaps = scoremaps if _host_resident(scoremaps, need_contiguous=True) else scoremaps.to(self.device)
         self._pending = None
         # The reference moves every input to the device (ConstructGraph.py:12-18).  Only N pixels of the feature and
         # tag maps are ever read (N x C x 4 bytes of a 134 MB map per image), so pinned host tensors are left where
@@ -197,8 +254,19 @@ class NaiveGraphConstructor:
         if sm_in.dim() != 4 or sm_in.shape[1] != self.num_joints:
             raise ValueError("scoremaps must be [B, num_joints, H, W], got %s" % (tuple(sm_in.shape),))
         B, J, H, W = sm_in.shape
+        fused = isinstance(sm_in, HeadStages)
         with torch.cuda.device(dev), torch.cuda.stream(stream if stream is not None else torch.cuda.current_stream(dev)):
-            if sm_in.device.type == "cpu":
+            if fused:
+                # the no-threshold path pads with zero-score pixels of the map (CG.py:1187): it needs the map in memory
+                keep = sm_in.keep_scoremaps or self.detect_threshold is None
+                sm = torch.empty(sm_in.shape, dtype=torch.float32, device=dev) if keep else None
+                asm = sm_in.assembly(sm)
+                sm_in.scoremaps = sm
+                if stream is not None:
+                    for pair in sm_in._keep:            # allocated on the caller's stream, read on this one
+                        for t_ in pair:
+                            t_.record_stream(stream)
+            elif sm_in.device.type == "cpu":
                 sm = torch.empty(sm_in.shape, dtype=torch.float32, device=dev)
                 sm.copy_(sm_in, non_blocking=True)
             else:
@@ -214,12 +282,17 @@ class NaiveGraphConstructor:
                 edge_features=self._edge_feat_bits,
                 norm_factor=float(max(W, H) if self.normalize_node_distance else 1),     # CG.py:311-314
                 cand_capacity=self.cand_capacity, max_det_per_type=self.max_det_per_type, max_nodes=self.max_nodes,
-                scoremaps=sm.data_ptr(), mask=mask.data_ptr() if mask is not None else None)
+                scoremaps=sm.data_ptr() if sm is not None else None, mask=mask.data_ptr() if mask is not None else None)
             ws_bytes = int(lib.pgmp_gc_workspace_bytes(p))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             p.workspace, p.workspace_bytes = ws.data_ptr(), ws_bytes
             counts = torch.empty(2 + 2 * B + 1, dtype=torch.int64, device=dev)
-            nv.check(lib.pgmp_gc_detect(p, counts.data_ptr(), nv.current_stream()))
+            if fused:
+                nv.check(lib.pgmp_gc_detect_fused(p, asm, counts.data_ptr(), nv.current_stream()))
+                if sm is None:
+                    sm = torch.empty((B, J, H, W), dtype=torch.float32, device="meta")   # shape only
+            else:
+                nv.check(lib.pgmp_gc_detect(p, counts.data_ptr(), nv.current_stream()))
             counts_h = torch.empty(counts.shape, dtype=torch.int64, pin_memory=True)
             counts_h.copy_(counts, non_blocking=True)
             event = torch.cuda.Event()
@@ -257,7 +330,8 @@ class NaiveGraphConstructor:
             if d["stream"] != cur:                 # the emit kernels read the detection's workspace on this stream
                 cur.wait_event(d["event"])
                 for t_ in (ws, sm, d["counts"]) + ((d["mask"],) if d["mask"] is not None else ()):
-                    t_.record_stream(cur)
+                    if t_.device.type == "cuda":
+                        t_.record_stream(cur)
             N, E = int(counts_h[0]), int(counts_h[1])
             self.num_nodes_per_image = counts_h[2:2 + B].clone()
             self.num_edges_per_image = counts_h[2 + B:2 + 2 * B].clone()

@@ -35,15 +35,16 @@ def test_struct_sizes_match_header():
     """sizeof() of every ctypes mirror equals the C compiler's (catches field drift)."""
     import subprocess
     import tempfile
-    src = '#include <stdio.h>\n#include "pgmp.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(pgmp_gc_params),' \
-          ' sizeof(pgmp_gc_outputs), sizeof(pgmp_mlp), sizeof(pgmp_mpn_params), sizeof(pgmp_group_params));return 0;}\n'
+    src = '#include <stdio.h>\n#include "pgmp.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(pgmp_gc_params),' \
+          ' sizeof(pgmp_gc_outputs), sizeof(pgmp_mlp), sizeof(pgmp_mpn_params), sizeof(pgmp_group_params),' \
+          ' sizeof(pgmp_gc_assembly));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "s.c")
         open(c, "w").write(src)
         exe = os.path.join(d, "s")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         sizes = [int(v) for v in subprocess.check_output([exe]).split()]
-    mirrors = [nv.GcParams, nv.GcOutputs, nv.Mlp, nv.MpnParams, nv.GroupParams]
+    mirrors = [nv.GcParams, nv.GcOutputs, nv.Mlp, nv.MpnParams, nv.GroupParams, nv.GcAssembly]
     assert sizes == [ctypes.sizeof(m) for m in mirrors]
 
 

@@ -78,3 +78,122 @@ def test_assembled_scoremaps_feed_the_graph_constructor():
     want = oracle.gc.construct_graph(o_score, o_tags, data["features"], cfg, J)
     for key, slot in (("x", 0), ("edge_attr", 1), ("edge_index", 2), ("joint_det", 7), ("joint_scores", 11), ("joint_tags", 14)):
         assert np.array_equal(ret[slot].cpu().numpy(), want[key]), key
+
+
+COCO_FLIP = [0, 2, 1, 4, 3, 6, 5, 8, 7, 10, 9, 12, 11, 14, 13, 16, 15]      # FLIP_CONFIG['COCO'] (hr_utils)
+
+
+def _stages(B, J, S, K, seed, persons=3):
+    """Full-resolution stage = synthetic heatmaps, half-resolution stage = 2 x 2 block means + noise, random tag maps."""
+    import pgmp_b200.synthetic as synthetic
+    data = synthetic.synth_batch(B, J, S, K, persons=persons)
+    rng = np.random.default_rng(seed)
+    s2 = data["scoremaps"]
+    heat = s2.reshape(B, J, S // 2, 2, S // 2, 2).mean((3, 5)).astype(np.float32) + rng.uniform(0, 0.01, (B, J, S // 2, S // 2)).astype(np.float32)
+    s1 = np.concatenate([heat, rng.standard_normal((B, J, S // 2, S // 2)).astype(np.float32)], 1)
+    return data, s1, s2
+
+
+def test_oracle_flip_average_matches_the_reference_operations():
+    """oracle.assemble.flip_average against the reference's own torch operations (PoseEstimation.py:377-402,
+    multi_scales_testing.py:162) on random maps."""
+    rng = np.random.default_rng(5)
+    a, af = rng.standard_normal((2, 17, 12, 20)).astype(np.float32), rng.standard_normal((2, 17, 12, 20)).astype(np.float32)
+    heat_flip = torch.flip(torch.from_numpy(af), [3])[:, COCO_FLIP, :, :]
+    want = ((torch.from_numpy(a) + heat_flip) / 2.0).numpy()
+    assert np.array_equal(A.flip_average(a, af, COCO_FLIP), want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["avg", "small", "avg_keep", "avg_flip", "avg_flip_keep", "avg_mask", "no_threshold", "pool3_rect",
+                                  "generic_scale", "generic_scale_flip"])
+def test_fused_assembly_in_the_nms_loader_is_bit_exact(case):
+    """HeadStages as the ``scoremaps`` argument: the NMS loader warps evaluate the assembled map row by row into the
+    shared-memory ring (pgmp_gc_detect_fused); every output of construct_graph() must equal the oracle chain
+    (assembly -> graph constructor) bit for bit, with and without the materialised map."""
+    import oracle
+    import pgmp_b200
+    from pgmp_b200.graph_constructor import HeadStages, get_graph_constructor
+    J, K = 17, 10
+    B, S = (2, 128)
+    data, s1, s2 = _stages(B, J, S, K, seed=3)
+    mode = "small" if case == "small" else "avg"
+    if case == "pool3_rect":          # non-square maps, another pool kernel
+        s1, s2 = np.ascontiguousarray(s1[:, :, :40, :]), np.ascontiguousarray(s2[:, :, :80, :])
+        data = {k: (np.ascontiguousarray(v[:, :, :80, :]) if v.ndim == 4 and v.shape[2] == S else v) for k, v in data.items()}
+    if case.startswith("generic_scale"):   # not an exact doubling: the per-column index / weight tables
+        rng = np.random.default_rng(8)
+        s1 = np.concatenate([rng.uniform(0, 0.02, (B, J, 48, 44)), rng.standard_normal((B, J, 48, 44))], 1).astype(np.float32)
+    kw = {}
+    if case == "no_threshold":
+        kw["DETECT_THRESHOLD"] = 2.0
+    if case == "pool3_rect":
+        kw["POOL_KERNEL_SIZE"] = 3
+    masks = None
+    if case == "avg_mask":
+        kw["MASK_CROWDS"] = True
+        masks = (np.random.default_rng(1).uniform(0, 1, (B, S, S)) > 0.2).astype(np.float32)
+    cfg = pgmp_b200.config.bench_gc_config(k=K, graph_type="knn", **kw)
+    t = lambda a: torch.from_numpy(a).cuda()
+    o_score, o_tags = oracle.assemble.hr_process_output(s1, s2, J, mode)
+    flipped = flip_index = None
+    if "flip" in case:
+        _, s1f, s2f = _stages(B, J, S, K, seed=11)
+        if case.startswith("generic_scale"):
+            s1f = np.random.default_rng(9).uniform(0, 0.02, s1.shape).astype(np.float32)
+        s1f, s2f = np.ascontiguousarray(s1f[..., ::-1]), np.ascontiguousarray(s2f[..., ::-1])
+        flipped, flip_index = (t(s1f), t(s2f)), COCO_FLIP
+        o_flip, _ = oracle.assemble.hr_process_output(s1f, s2f, J, mode)
+        o_score = oracle.assemble.flip_average(o_score, o_flip, COCO_FLIP)
+    stages = HeadStages((t(s1), t(s2)), J, mode=mode, flipped=flipped, flip_index=flip_index, keep_scoremaps="keep" in case)
+    ret = get_graph_constructor(cfg, scoremaps=stages, tagmaps=t(o_tags), features=t(data["features"]), joints_gt=None,
+                                factor_list=None, masks=t(masks) if masks is not None else None, device="cuda:0", testing=True,
+                                heatmaps=None, num_joints=J).construct_graph()
+    want = oracle.gc.construct_graph(o_score, o_tags, data["features"], cfg, J, masks=masks)
+    assert want["joint_det"].shape[0] > 50
+    for key, slot in (("x", 0), ("edge_attr", 1), ("edge_index", 2), ("joint_det", 7), ("joint_scores", 11), ("joint_tags", 14)):
+        assert np.array_equal(ret[slot].cpu().numpy(), want[key]), key
+    if "keep" in case or case == "no_threshold":
+        assert np.array_equal(stages.scoremaps.cpu().numpy(), o_score)         # the materialised map, bit for bit
+    else:
+        assert stages.scoremaps is None
+
+
+@pytest.mark.gpu
+def test_fused_assembly_rejects_what_it_does_not_cover():
+    import pgmp_b200
+    from pgmp_b200.graph_constructor import HeadStages, get_graph_constructor
+    J = 4
+    s1, s2 = torch.rand(1, 2 * J, 16, 15, device="cuda"), torch.rand(1, J, 32, 30, device="cuda")       # width % 4 != 0
+    cfg = pgmp_b200.config.bench_gc_config(k=5, graph_type="knn")
+    with pytest.raises(RuntimeError, match="width"):
+        get_graph_constructor(cfg, scoremaps=HeadStages((s1, s2), J), tagmaps=None, features=None, joints_gt=None, factor_list=None,
+                              masks=None, device="cuda:0", testing=True, heatmaps=None, num_joints=J).construct_graph()
+    with pytest.raises(NotImplementedError):
+        HeadStages((s1, s2), J, mode="large")
+    with pytest.raises(ValueError):
+        HeadStages((s1, s2), J, flipped=(s1, s2))
+
+
+@pytest.mark.gpu
+def test_fused_assembly_full_size_equals_the_two_kernel_path():
+    """BASELINE size (32 x 17 x 512 x 512, flip-test average on): fused detection = assembly kernels + plain detection."""
+    import pgmp_b200
+    from pgmp_b200.graph_constructor import HeadStages, get_graph_constructor, hr_process_output
+    J, K, B, S = 17, 30, 32, 512
+    data, s1, s2 = _stages(B, J, S, K, seed=2, persons=6)
+    t = lambda a: torch.from_numpy(a).cuda()
+    s1d, s2d = t(s1), t(s2)
+    s1f, s2f = torch.flip(s1d, [3]).contiguous(), torch.flip(s2d, [3]).contiguous()
+    cfg = pgmp_b200.config.bench_gc_config(k=K, graph_type="knn")
+    feat = torch.zeros(B, 4, S, S, device="cuda")
+    a0, _, tags = hr_process_output(((s1d, s2d), None), "avg", J)
+    a1, _, _ = hr_process_output(((s1f, s2f), None), "avg", J)
+    score = (a0 + torch.flip(a1, [3])[:, COCO_FLIP]) / 2.0
+    run = lambda sm: get_graph_constructor(cfg, scoremaps=sm, tagmaps=tags, features=feat, joints_gt=None, factor_list=None, masks=None,
+                                           device="cuda:0", testing=True, heatmaps=None, num_joints=J).construct_graph()
+    want = run(score)
+    got = run(HeadStages((s1d, s2d), J, flipped=(s1f, s2f), flip_index=COCO_FLIP))
+    assert want[7].shape[0] > 10000
+    for slot in (0, 1, 2, 7, 11, 12, 14):
+        assert torch.equal(got[slot], want[slot]), slot
