@@ -417,6 +417,50 @@ def run_b200(args, rank, local_rank, world):
     total_images = B * world * args.steps
     total_edges = reduce_sum(edges_per_step) * args.steps
     value = total_images / t_dev
+    # ---- SURVEY.md 8f rank 2, beside the headline (N = 1): the head's two output stages assembled inside the NMS load
+    #      stage (HeadStages -> pgmp_gc_detect_fused) against assemble_kernel + plain detection, same maps
+    assembly = None
+    if world == 1:
+        try:
+            from pgmp_b200.graph_constructor import HeadStages, hr_process_output
+            gen2 = torch.Generator(device=dev).manual_seed(5)
+            s1 = torch.cat([torch.nn.functional.avg_pool2d(sm, 2) + 0.01 * torch.rand(B, J, SIZE // 2, SIZE // 2, device=dev, generator=gen2),
+                            torch.randn(B, J, SIZE // 2, SIZE // 2, device=dev, generator=gen2)], 1).contiguous()
+            small = torch.zeros(B, 4, SIZE, SIZE, device=dev)
+
+            def gc_of(scoremaps, tagmaps):
+                return get_graph_constructor(gcfg, scoremaps=scoremaps, tagmaps=tagmaps, features=small, joints_gt=None,
+                                             factor_list=None, masks=None, device=dev, testing=True, heatmaps=None,
+                                             num_joints=J).construct_graph()
+
+            def two_kernels():
+                score, _, tg = hr_process_output(((s1, sm), None), "avg", J)
+                return gc_of(score, tg)
+
+            def fused():
+                st = HeadStages((s1, sm), J)
+                return gc_of(st, st)
+
+            assembly = {}
+            for nm, fn in (("assemble_then_detect", two_kernels), ("fused", fused)):
+                for _ in range(3):
+                    fn()
+                nv.profile(True)
+                for _ in range(args.steps):
+                    fn()
+                pa = nv.profile_collect()
+                nv.profile(False)
+                assembly[nm] = {k: v[1] / args.steps for k, v in pa.items()
+                                if k.startswith("nms_candidates") or k.startswith("assemble") or k.startswith("stage_tags")}
+                assembly[nm]["ms"] = sum(assembly[nm].values())
+            rd = B * J * (SIZE * SIZE + (SIZE // 2) ** 2) * 4
+            assembly["fused_bytes_read"] = rd
+            assembly["fused_gbs"] = rd / assembly["fused"]["ms"] / 1e6
+            assembly["note"] = ("hr_process_output (hrnet.py:587-611) + NMS: the fused kernel reads both stages once and writes "
+                                "no map; the two-kernel path writes and re-reads the 570 MB map and the up-sampled tag maps")
+            del s1, small
+        except Exception as exc:
+            assembly = {"error": "%s: %s" % (type(exc).__name__, exc)}
     # BASELINE.json configs[4] beside the headline: one training step of the agnostic MPN
     # (GC + forward + reverse pass + gradient all-reduce + Adam), same ranks; scripts/bench_train.py is the stand-alone form
     train = None
@@ -534,6 +578,7 @@ def run_b200(args, rank, local_rank, world):
                                                         "copied to the host every step"}},
             "graph": {"nodes_per_step_per_gpu": nodes_per_step, "edges_per_step_per_gpu": edges_per_step}}
     line["train_step"] = train
+    line["scoremap_assembly"] = assembly
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -177,6 +177,12 @@ typedef struct pgmp_gc_assembly {
   float* scoremaps_out;                      /* optional device [B, J, H, W] */
 } pgmp_gc_assembly;
 int pgmp_gc_detect_fused(const pgmp_gc_params* p, const pgmp_gc_assembly* a, int64_t* counts, pgmp_stream_t stream);
+/* ... and the tags of the detections (ConstructGraph.py:103) without the up-sampled tag maps: joint_tags[n] =
+ * up(stage1)[batch_index[n], num_joints + type, y, x] for the (x, y, type) rows pgmp_gc_emit wrote (tag dimension 1:
+ * stage 1 = num_joints heatmaps + num_joints tag maps); bit-identical to indexing the up-sampled maps. */
+int pgmp_gc_gather_stage_tags(const float* stage1, int32_t channels1, int32_t num_joints, int32_t h, int32_t w, int32_t H,
+                              int32_t W, const int64_t* joint_det, const int64_t* batch_index, int64_t num_nodes,
+                              float* joint_tags, pgmp_stream_t stream);
 
 /* Reverse of the node-feature gather of pgmp_gc_emit (x[n, :] = features[b, :, y, x], ConstructGraph.py:265, 269) under
  * autograd -- end-to-end training, train.py:232: d_features[b, :, y, x] = sum of grad_x[n, :] over the nodes at that pixel

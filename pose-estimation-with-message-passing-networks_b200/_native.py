@@ -165,6 +165,8 @@ SYMBOLS = {
     "pgmp_gc_workspace_bytes": (C.c_uint64, [C.POINTER(GcParams)]),
     "pgmp_gc_detect": (C.c_int, [C.POINTER(GcParams), C.c_void_p, C.c_void_p]),
     "pgmp_gc_detect_fused": (C.c_int, [C.POINTER(GcParams), C.POINTER(GcAssembly), C.c_void_p, C.c_void_p]),
+    "pgmp_gc_gather_stage_tags": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                            C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "pgmp_gc_emit": (C.c_int, [C.POINTER(GcParams), C.POINTER(GcOutputs), C.c_void_p]),
     "pgmp_gc_gather_conv": (C.c_int, [C.POINTER(GatherConvParams), C.c_void_p]),
     "pgmp_gc_assemble_scoremaps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

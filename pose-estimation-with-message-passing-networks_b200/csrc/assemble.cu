@@ -89,8 +89,40 @@ __global__ void __launch_bounds__(256) assemble_kernel(const AssembleArgs a) {
   }
 }
 
+// joint_tags[n] = up(stage1)[b, J + type, y, x] at the detections only (the tag half of hr_process_output evaluated
+// where ConstructGraph.py:103 reads it): the same arithmetic as assemble_kernel, 4 source values per node.
+__global__ void __launch_bounds__(256) stage_tags_kernel(const float* __restrict__ s1, int C1, int J, int h, int w, float scale_y,
+                                                         float scale_x, const int64_t* __restrict__ joint_det,
+                                                         const int64_t* __restrict__ batch_index, int64_t N,
+                                                         float* __restrict__ joint_tags) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int x = (int)joint_det[n * 3], y = (int)joint_det[n * 3 + 1], t = (int)joint_det[n * 3 + 2];
+  int y0, y1, x0, x1;
+  float wy0, wy1, wx0, wx1;
+  source_index(scale_y, y, h, y0, y1, wy0, wy1);
+  source_index(scale_x, x, w, x0, x1, wx0, wx1);
+  const float* __restrict__ plane = s1 + ((size_t)batch_index[n] * C1 + J + t) * h * w;
+  const float* __restrict__ r0 = plane + (size_t)y0 * w;
+  const float* __restrict__ r1 = plane + (size_t)y1 * w;
+  joint_tags[n] = bilinear_combine(wx0, wx1, wy0, wy1, __ldg(r0 + x0), __ldg(r0 + x1), __ldg(r1 + x0), __ldg(r1 + x1));
+}
+
 }  // namespace
 }  // namespace pgmp
+
+extern "C" int pgmp_gc_gather_stage_tags(const float* stage1, int32_t channels1, int32_t num_joints, int32_t h, int32_t w,
+                                         int32_t H, int32_t W, const int64_t* joint_det, const int64_t* batch_index,
+                                         int64_t num_nodes, float* joint_tags, pgmp_stream_t stream) {
+  using namespace pgmp;
+  if (num_nodes == 0) return PGMP_OK;
+  if (!stage1 || !joint_det || !batch_index || !joint_tags || num_nodes < 0) return set_error(PGMP_ERR_INVALID, "null pointer");
+  if (channels1 < 2 * num_joints || h <= 0 || w <= 0 || H <= 0 || W <= 0)
+    return set_error(PGMP_ERR_INVALID, "stage 1 must hold num_joints heatmaps and num_joints tag maps");
+  PGMP_LAUNCH(stage_tags_kernel, (unsigned)ceil_div<int64_t>(num_nodes, 256), 256, 0, static_cast<cudaStream_t>(stream), stage1,
+              channels1, num_joints, h, w, (float)h / (float)H, (float)w / (float)W, joint_det, batch_index, num_nodes, joint_tags);
+  return PGMP_OK;
+}
 
 extern "C" int pgmp_gc_assemble_scoremaps(const float* stage1, const float* stage2, int32_t batch, int32_t channels1,
                                           int32_t num_joints, int32_t h, int32_t w, int32_t H, int32_t W, int32_t mode,

@@ -94,7 +94,9 @@ class HeadStages:
     ``keep_scoremaps=True`` still writes it (``.scoremaps`` after the detection) for the pose-assembly tail
     (``refine`` / ``adjust``).  ``flipped`` / ``flip_index`` add the flip-test average of one scale
     (PoseEstimation.py:343-402, multi_scales_testing.py:162): ``(A + A_flipped[:, flip_index, :, ::-1]) / 2``.
-    Results are bit-identical to ``hr_process_output`` + the plain constructor."""
+    Results are bit-identical to ``hr_process_output`` + the plain constructor.  The same object can be passed as
+    ``tagmaps``: the detections' tags are then interpolated from the half-resolution stage at their pixels only
+    (``pgmp_gc_gather_stage_tags``) and the up-sampled tag maps are not built either."""
 
     def __init__(self, outputs, num_joints, mode="avg", flipped=None, flip_index=None, keep_scoremaps=False):
         s1, s2 = outputs
@@ -159,8 +161,11 @@ class NaiveGraphConstructor:
         # tag maps are ever read (N x C x 4 bytes of a 134 MB map per image), so pinned host tensors are left where
         # they are and the gather kernels read those pixels in place over PCIe (unified addressing); like a
         # non_blocking copy from pinned memory, the caller must not overwrite them before the stream has caught up.
-        self.tagmaps = tagmaps if _host_resident(tagmaps, need_contiguous=True) else (
-            tagmaps.to(self.device) if tagmaps is not None else None)
+        if isinstance(tagmaps, HeadStages):
+            self.tagmaps = tagmaps                           # tags evaluated at the detections (pgmp_gc_gather_stage_tags)
+        else:
+            self.tagmaps = tagmaps if _host_resident(tagmaps, need_contiguous=True) else (
+                tagmaps.to(self.device) if tagmaps is not None else None)
         if isinstance(features, ConvUpsampleFeatures):
             # every candidate reads a 4 x 4 x Cin neighbourhood of the (small) backbone map: a host-resident map is
             # copied, reading it in place would cost more PCIe transactions than the copy
@@ -348,7 +353,13 @@ class NaiveGraphConstructor:
             batch_index = torch.empty((N,), dtype=torch.int64, device=dev)
             tags = self.tagmaps
             tag_dim, joint_tags, tags_c = 1, None, None
-            if tags is not None:
+            stage_tags = isinstance(tags, HeadStages)
+            if stage_tags:
+                s1t = tags.terms[0][0].detach().contiguous()
+                if s1t.shape[1] != 2 * J or tuple(tags.shape[2:]) != (H, W):
+                    raise ValueError("HeadStages as tagmaps: scoremap_1 must hold J heatmaps + J tag maps for %d x %d maps" % (H, W))
+                joint_tags = torch.empty((N,), dtype=torch.float32, device=dev)
+            elif tags is not None:
                 if tags.dim() not in (4, 5):
                     raise ValueError("tagmaps must be [B,J,H,W] or [B,J,H,W,T]")
                 tag_dim = tags.shape[4] if tags.dim() == 5 else 1
@@ -372,6 +383,10 @@ class NaiveGraphConstructor:
             o.edge_attr, o.edge_index = edge_attr.data_ptr(), edge_index.data_ptr()
             o.joint_det, o.joint_scores, o.batch_index = joint_det.data_ptr(), joint_scores.data_ptr(), batch_index.data_ptr()
             nv.check(lib.pgmp_gc_emit(p, o, stream))
+            if stage_tags:        # up(scoremap_1)[:, J:] at the detections only: the tag maps are never up-sampled
+                nv.check(lib.pgmp_gc_gather_stage_tags(s1t.data_ptr(), s1t.shape[1], J, s1t.shape[2], s1t.shape[3], H, W,
+                                                       joint_det.data_ptr(), batch_index.data_ptr(), N, joint_tags.data_ptr(),
+                                                       stream))
             if fused and N > 0:
                 wt, bias = feat.pack(dev)
                 fm = feat.feat.detach()

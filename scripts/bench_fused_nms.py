@@ -36,7 +36,7 @@ def two_kernels():
 
 def fused(keep=False, flip=False):
     st = HeadStages((s1, s2), J, flipped=(s1f, s2f) if flip else None, flip_index=FLIP if flip else None, keep_scoremaps=keep)
-    return gc(st, None)
+    return gc(st, st)
 
 
 out = {}
