@@ -90,7 +90,7 @@ constexpr int kNmsClaimMargin = 256; // a consumer thread claims a queue slot on
 //   map[j][y][x] = (A_0[j][y][x] + A_1[flip[j]][y][W - 1 - x]) / 2
 // with ATen's bilinear arithmetic (common.cuh) -- the same operations in the same order as assemble.cu, so the values
 // are bit-identical to the materialised map.
-constexpr int kNmsFuseLoaders = 4;   // loader warps of the fused kernel (each evaluates S / 4 rows of a stage)
+constexpr int kNmsFuseLoaders = 8;   // loader warps of the fused kernel (each evaluates S / 4 rows of a stage)
 struct AsmDev {
   const float* s1[2]; const float* s2[2];
   int C1, h, w, mode, terms;
