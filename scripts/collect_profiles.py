@@ -11,7 +11,7 @@ R = sys.argv[1] if len(sys.argv) > 1 else "r2"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 
-for name in ("bench.json", "bench_ref.json", "pytest_gpu.txt"):
+for name in ("bench.json", "bench_ref.json", "pytest_gpu.txt", "fused_nms_bench.txt"):
     src = os.path.join(G, f"{R}_{name}")
     if os.path.exists(src):
         open(os.path.join(P, f"{R}_{name}"), "w").write(open(src).read())
@@ -46,7 +46,8 @@ traffic = {}
 for rep, note in ((f"{R}_edge_step_tc", "dominant kernel: one message-passing step over 929 518 edges (B=32)"),
                   (f"{R}_nms", "heatmap NMS + candidate extraction over 32 x 17 x 512 x 512 fp32"),
                   (f"{R}_group", "grouping tail (GAEC), one CTA per image, 32 images"),
-                  (f"{R}_gather_features", "node-feature gather from NCHW maps (one 32-byte sector per element)")):
+                  (f"{R}_gather_features", "node-feature gather from NCHW maps (one 32-byte sector per element)"),
+                  (f"{R}_nms_fused", "NMS with the scoremap assembly fused into its load stage (pgmp_gc_detect_fused), 32 x 17 x 512 x 512")):
     path = os.path.join(G, rep + ".ncu-rep")
     if not os.path.exists(path):
         continue
@@ -59,7 +60,7 @@ for rep, note in ((f"{R}_edge_step_tc", "dominant kernel: one message-passing st
         x = float(r[h.index(k)])
         return x * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}[u[h.index(k)]]
     kname = {"edge_step_tc": "edge_step_tc_kernel", "nms": "nms_candidates_kernel", "group": "group_kernel",
-             "gather_features": "gather_features_kernel"}[rep[len(R) + 1:]]
+             "gather_features": "gather_features_kernel", "nms_fused": "nms_candidates_kernel (fused assembly)"}[rep[len(R) + 1:]]
     traffic[kname] = {"dram_bytes_per_launch": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
                       "edges_per_launch": 929518, "source": f"profiles/{rep}_ncu.txt (ncu --set full, one launch)"}
 json.dump(traffic, open(os.path.join(P, f"{R}_traffic.json"), "w"), indent=1)

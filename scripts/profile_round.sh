@@ -20,5 +20,9 @@ ncu --set full --clock-control none --import-source on -k regex:group_kernel -s 
       python scripts/dbg_group.py 32 > $O/ncu_d.log 2>&1
 ncu --set full --clock-control none -k regex:gather_features -c 1 -o $O/${R}_gather_features \
       python scripts/quick_profile.py 32 knn tc > $O/ncu_e.log 2>&1
+# scoremap assembly fused into the NMS loader: launches 0-12 of nms_candidates are the two-kernel path, 13.. the fused one
+python scripts/bench_fused_nms.py > $O/${R}_fused_nms_bench.txt 2>&1 && \
+  ncu --set full --clock-control none --import-source on -k regex:nms_candidates -s 15 -c 1 -o $O/${R}_nms_fused \
+      python scripts/bench_fused_nms.py > $O/ncu_f.log 2>&1
 cat $O/${R}_pytest_gpu.txt
 tail -c 300 $O/${R}_bench.err
