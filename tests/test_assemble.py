@@ -199,3 +199,49 @@ def test_fused_assembly_full_size_equals_the_two_kernel_path():
     assert want[7].shape[0] > 10000
     for slot in (0, 1, 2, 7, 11, 12, 14):
         assert torch.equal(got[slot], want[slot]), slot
+
+
+@pytest.mark.gpu
+def test_fused_assembly_through_the_pipelined_api():
+    """GroupingPipeline with HeadStages batches (the detection half, assembly included, runs one batch ahead on the side
+    stream) = the serial two-kernel calls, bit for bit."""
+    import pgmp_b200
+    import pgmp_b200.synthetic as synthetic
+    from pgmp_b200.graph_constructor import HeadStages, get_graph_constructor, hr_process_output
+    from pgmp_b200.Models.MessagePassingNetwork import get_mpn_model
+    from pgmp_b200.pipeline import GroupingPipeline
+    J, K, B, S = 17, 10, 2, 128
+    cfg = pgmp_b200.config.bench_gc_config(k=K, graph_type="knn")
+    mcfg = pgmp_b200.config.flagship_mpn_config(J, STEPS=2, B200_PRECISION="tc")
+    model = synthetic.synth_mpn_state_dict(get_mpn_model(mcfg), 1).eval().cuda()
+    t = lambda a: torch.from_numpy(a).cuda()
+    batches, want = [], []
+    for seed in (3, 4, 5):
+        data, s1, s2 = _stages(B, J, S, K, seed=seed)
+        s1d, s2d, feat = t(s1), t(s2), t(data["features"])
+        st = HeadStages((s1d, s2d), J)
+        batches.append({"scoremaps": st, "tagmaps": st, "features": feat})
+        score, _, tags = hr_process_output(((s1d, s2d), None), "avg", J)
+        ret = get_graph_constructor(cfg, scoremaps=score, tagmaps=tags, features=feat, joints_gt=None, factor_list=None, masks=None,
+                                    device="cuda:0", testing=True, heatmaps=None, num_joints=J).construct_graph()
+        with torch.no_grad():
+            pe, pn, pc, _ = model(ret[0], ret[1], ret[2], node_types=ret[7][:, 2])
+        want.append((ret, pe[-1].clone(), pn[-1].clone(), pc[-1].clone()))
+    outs = list(GroupingPipeline(cfg, model, J, "cuda:0").run(batches))
+    assert len(outs) == 3
+    for (ret, (pe, pn, pc)), (wret, wpe, wpn, wpc) in zip(outs, want):
+        for slot in (0, 1, 2, 7, 11, 12, 14):
+            assert torch.equal(ret[slot], wret[slot]), slot
+        assert torch.equal(pe[-1], wpe) and torch.equal(pn[-1], wpn) and torch.equal(pc[-1], wpc)
+
+
+def test_head_stages_host_logic_without_a_gpu():
+    """No CPU fallback: CPU stages are rejected when the stand-in is built; argument checks do not need a device."""
+    from pgmp_b200.graph_constructor import HeadStages
+    s1, s2 = torch.zeros(1, 8, 8, 8), torch.zeros(1, 4, 16, 16)
+    with pytest.raises(Exception, match="(?i)cuda"):
+        HeadStages((s1, s2), 4)
+    with pytest.raises(NotImplementedError):
+        HeadStages((s1, s2), 4, mode="large")
+    with pytest.raises(ValueError):
+        HeadStages((s1, s2), 4, flipped=(s1, s2))
