@@ -59,6 +59,7 @@ def run_training(args, rank, world, dev):
     gen = torch.Generator(device=dev).manual_seed(rank)
     ev = {k: [torch.cuda.Event(enable_timing=True) for _ in range(2)] for k in ("gc", "fwd", "loss", "bwd", "ar", "opt", "step")}
     acc = {k: 0.0 for k in ev}
+    per_step = {k: [] for k in ev}
     info = {}
 
     def step(timed):
@@ -96,6 +97,7 @@ def run_training(args, rank, world, dev):
         if timed:
             for k in ev:
                 acc[k] += ev[k][0].elapsed_time(ev[k][1])
+                per_step[k].append(ev[k][0].elapsed_time(ev[k][1]))
         return float(loss.detach())
 
     for _ in range(args.warmup):
@@ -107,13 +109,16 @@ def run_training(args, rank, world, dev):
     losses = [step(True) for _ in range(args.steps)]
     launches = nv.kernel_launches() - launches0
     ms = {k: par.max_over_ranks(v / args.steps, dev) for k, v in acc.items()}
+    # the phases are driven by the host (stock torch losses, Python between the calls): one host hiccup in a 5-step run moves
+    # the mean by milliseconds, so the per-phase medians are reported next to the means
+    med = {k: par.max_over_ranks(sorted(v)[len(v) // 2], dev) for k, v in per_step.items()}
     result = None
     if rank == 0:
         imgs = args.batch * world
         result = ({
             "metric": "training step: images/sec (GC + MPN forward + backward + gradient all-reduce + Adam)",
             "value": imgs / (ms["step"] * 1e-3), "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms["step"], "ms": ms, "edges_per_s": info["edges"] * world / (ms["step"] * 1e-3),
+            "ms_per_step": ms["step"], "ms": ms, "ms_median": med, "value_median": imgs / (med["step"] * 1e-3), "edges_per_s": info["edges"] * world / (ms["step"] * 1e-3),
             "config": {"workload": "configs[4]: %d synthetic %dx%d images per GPU, %s (skip, %d steps), kNN-50 graph"
                                    % (args.batch, args.size, args.size,
                                       "per-type TypeAwareMPNLayer with attention" if args.model == "flagship" else "agnostic MPLayer (max)",
