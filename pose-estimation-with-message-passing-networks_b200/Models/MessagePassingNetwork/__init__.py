@@ -300,8 +300,14 @@ class NodeClassificationMPNSimple(nn.Module):
                                  "dropped and their logits are undefined")
 
     def _pack(self, device):
-        tensors = list(self.parameters()) + list(self.buffers())
-        key = (str(device),) + tuple((t._version, t.data_ptr()) for t in tensors)
+        # the (container, name) slots of every parameter / buffer are collected once: walking the module tree through
+        # parameters() + buffers() on every forward cost 0.6 ms of host time per batch (a sixth of the GPU time of a
+        # 32-image batch); a re-assigned Parameter is still seen, the slots are looked up each time
+        slots = self.__dict__.get("_pack_slots")
+        if slots is None:
+            slots = [(d, n) for m in self.modules() for d in (m._parameters, m._buffers) for n in d]
+            self.__dict__["_pack_slots"] = slots
+        key = (str(device),) + tuple((t._version, t.data_ptr()) for t in (d[n] for d, n in slots) if t is not None)
         if self._pack_cache is not None and self._pack_cache[0] == key:
             return self._pack_cache[1]
         pk = _Packer()

@@ -29,3 +29,28 @@ for _ in range(20):
 torch.cuda.synchronize()
 tot=(time.perf_counter()-t0)/20
 print(f"wall/step {tot*1e3:.3f} ms; host in construct_graph (incl. its sync) {np.mean(a)*1e3:.3f} ms; host in mpn forward {np.mean(b)*1e3:.3f} ms")
+
+# where the host time goes (cProfile over 20 pipelined batches, cumulative top entries)
+import cProfile, pstats, io
+from pgmp_b200.pipeline import GroupingPipeline
+pipe = GroupingPipeline(gcfg, model, J, dev)
+batch = {"scoremaps": sm, "tagmaps": tags, "features": feat}
+for _ in pipe.run(batch for _ in range(5)):
+    pass
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in pipe.run(batch for _ in range(40)):
+    pass
+t_host = (time.perf_counter() - t0) / 40
+torch.cuda.synchronize()
+t_all = (time.perf_counter() - t0) / 40
+print(f"pipelined: host loop {t_host*1e3:.3f} ms per batch (without the final drain), wall {t_all*1e3:.3f} ms per batch")
+pr = cProfile.Profile()
+pr.enable()
+for _ in pipe.run(batch for _ in range(20)):
+    pass
+pr.disable()
+torch.cuda.synchronize()
+s_ = io.StringIO()
+pstats.Stats(pr, stream=s_).sort_stats("tottime").print_stats(22)
+print("\n".join(l[:150] for l in s_.getvalue().splitlines()[:45]))
