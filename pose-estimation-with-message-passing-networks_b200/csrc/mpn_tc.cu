@@ -244,13 +244,14 @@ __global__ void __launch_bounds__(kEdge2Threads, 1) edge_step_tc_kernel(const Ed
     //      instead of 2.14 ms: the requests queue in front of the reduction's shared-memory reads.)
     float4 pq[8], qv[8];
     {
-      const float* __restrict__ prow = a.tab_p + (size_t)(e >= 0 ? dst : 0) * kD;
-      const float* __restrict__ qrow = a.tab_q + (size_t)(e >= 0 ? src : 0) * kD;
+      // (rows are 256-byte aligned: the swizzled pair position (4 half + q) ^ x is one XOR on the low address bits)
       const int xd = e >= 0 ? dst & 7 : 0, xs = e >= 0 ? src & 7 : 0;
+      const uintptr_t p0 = reinterpret_cast<uintptr_t>(a.tab_p + (size_t)(e >= 0 ? dst : 0) * kD) + (uintptr_t)(((4 * half) ^ xd) << 5);
+      const uintptr_t q0 = reinterpret_cast<uintptr_t>(a.tab_q + (size_t)(e >= 0 ? src : 0) * kD) + (uintptr_t)(((4 * half) ^ xs) << 5);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float8 pv = ldg256(prow + 8 * ((4 * half + q) ^ xd));
-        const float8 qq = ldg256(qrow + 8 * ((4 * half + q) ^ xs));
+        const float8 pv = ldg256(reinterpret_cast<const float*>(p0 ^ (uintptr_t)(q << 5)));
+        const float8 qq = ldg256(reinterpret_cast<const float*>(q0 ^ (uintptr_t)(q << 5)));
         pq[2 * q] = pv.a; pq[2 * q + 1] = pv.b;
         qv[2 * q] = qq.a; qv[2 * q + 1] = qq.b;
       }
@@ -309,11 +310,11 @@ __global__ void __launch_bounds__(kEdge2Threads, 1) edge_step_tc_kernel(const Ed
     // ---- R[type][dst]: this thread's half row, requested now, consumed by the third epilogue
     float4 rv[8];
     {
-      const float* __restrict__ rrow = a.tab_r + ((size_t)t * a.N + (e >= 0 ? dst : 0)) * kD;
       const int xd = e >= 0 ? dst & 7 : 0;
+      const uintptr_t r0 = reinterpret_cast<uintptr_t>(a.tab_r + ((size_t)t * a.N + (e >= 0 ? dst : 0)) * kD) + (uintptr_t)(((4 * half) ^ xd) << 5);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float8 r8 = ldg256(rrow + 8 * ((4 * half + q) ^ xd));
+        const float8 r8 = ldg256(reinterpret_cast<const float*>(r0 ^ (uintptr_t)(q << 5)));
         rv[2 * q] = r8.a; rv[2 * q + 1] = r8.b;
       }
     }
@@ -327,8 +328,7 @@ __global__ void __launch_bounds__(kEdge2Threads, 1) edge_step_tc_kernel(const Ed
         // sixteen-byte chunks per thread)
       float2 at0 = make_float2(0.f, 0.f), at1 = at0;
       const uint32_t b2_a = smem_u32(s_b2) + 4u * (uint32_t)c0col, wa_a = smem_u32(s_wa) + 4u * (uint32_t)c0col;
-      const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
-      const uint32_t x = (uint32_t)(row & 7);
+      const uint32_t off0 = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128) + (((uint32_t)(4 * half) ^ (uint32_t)(row & 7)) << 4);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t h[4], l[4];
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(kEdge2Threads, 1) edge_step_tc_kernel(const Ed
           split2_pos(v0, h[2 * i], l[2 * i]);
           split2_pos(v1, h[2 * i + 1], l[2 * i + 1]);
         }
-        const uint32_t off = row_off + (((uint32_t)(4 * half + c) ^ x) << 4);
+        const uint32_t off = off0 ^ (uint32_t)(c << 4);
         sts128(a_hi + off, h[0], h[1], h[2], h[3]);
         sts128(a_lo + off, l[0], l[1], l[2], l[3]);
       }
@@ -419,11 +419,12 @@ __global__ void __launch_bounds__(kEdge2Threads, 1) edge_step_tc_kernel(const Ed
     }
     tmem_ld32(tmem_row + (uint32_t)c0col, d);
     // ---- message m = ReLU(d + R) goes to this thread's half of its staging row (the C row was consumed by the first epilogue)
+    const uint32_t m_a0 = add_a + 4 * stage_index(row, c0col);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const float2 m0 = add2(make_float2(d[4 * q + 0], d[4 * q + 1]), make_float2(rv[q].x, rv[q].y));
       const float2 m1 = add2(make_float2(d[4 * q + 2], d[4 * q + 3]), make_float2(rv[q].z, rv[q].w));
-      sts128f(add_a + 4 * stage_index(row, c0col + 4 * q),
+      sts128f(m_a0 ^ (uint32_t)(q << 4),
               make_float4(fmaxf(m0.x, 0.f), fmaxf(m0.y, 0.f), fmaxf(m1.x, 0.f), fmaxf(m1.y, 0.f)));
     }
     if (a.with_head) {   // head layer 1 epilogue -> A, layer 2 on the tensor cores
