@@ -147,6 +147,19 @@ typedef struct pgmp_gather_conv_params {
 /* x = interpolate(feature_gather(feat))[:, y, x] at the candidates only; stream-ordered after pgmp_gc_emit */
 int pgmp_gc_gather_conv(const pgmp_gather_conv_params* p, pgmp_stream_t stream);
 
+/* Reverse pass of pgmp_gc_gather_conv (training end to end through ConvUpsampleFeatures: gradients of the feature_gather
+ * convolution and of the backbone map, PoseEstimation.py:64-66, train.py:232).  With P[n][(ky 3 + kx) Cin + ci] the
+ * interpolated 3 x 3 x Cin input patch of node n (x = bias + P weight_t):
+ *   pgmp_gc_gather_conv_patches   writes P [N][9 Cin] (the forward's arithmetic); the caller forms d weight_t = P^T d x,
+ *                                 d bias = sum d x and d P = d x weight_t^T with its library GEMM;
+ *   pgmp_gc_gather_conv_backward  adds d P into d_features ([B, Cin, h, w], the strides of p->features, zero-filled by the
+ *                                 caller) through the transposed interpolation; no atomics: one CTA per image walks its
+ *                                 nodes in node order, so overlapping neighbourhoods are summed in a fixed order.
+ * p->x / weight_t / bias are not read by either call. */
+int pgmp_gc_gather_conv_patches(const pgmp_gather_conv_params* p, float* patches, pgmp_stream_t stream);
+int pgmp_gc_gather_conv_backward(const pgmp_gather_conv_params* p, const float* d_patches, int32_t batch, float* d_features,
+                                 pgmp_stream_t stream);
+
 /* Scoremap assembly in front of the NMS -- hr_process_output (src/Models/HigherHRNet/hrnet.py:587-611):
  *   up = interpolate(stage1 [B, C1, h, w], size = (H, W), bilinear, align_corners = False)
  *   scoremaps [B, J, H, W] = (stage2 + up[:, :J]) / 2 (PGMP_ASSEMBLE_AVG) or up[:, :J] (PGMP_ASSEMBLE_SMALL)

@@ -169,6 +169,8 @@ SYMBOLS = {
                                             C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "pgmp_gc_emit": (C.c_int, [C.POINTER(GcParams), C.POINTER(GcOutputs), C.c_void_p]),
     "pgmp_gc_gather_conv": (C.c_int, [C.POINTER(GatherConvParams), C.c_void_p]),
+    "pgmp_gc_gather_conv_patches": (C.c_int, [C.POINTER(GatherConvParams), C.c_void_p, C.c_void_p]),
+    "pgmp_gc_gather_conv_backward": (C.c_int, [C.POINTER(GatherConvParams), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "pgmp_gc_assemble_scoremaps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                              C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pgmp_gc_gather_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64,

@@ -255,3 +255,123 @@ extern "C" int pgmp_gc_gather_backward(const float* grad_x, const int64_t* joint
               batch_index, num_nodes, (int)channels, d_features, stride_b, stride_c, stride_y, stride_x);
   return PGMP_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Reverse pass of pgmp_gc_gather_conv (end-to-end training with ConvUpsampleFeatures: the gradients of the
+// feature_gather convolution and of the backbone map, PoseEstimation.py:64-66, train.py:232).
+//   x = bias + P Wmat,  P[n][k] = the interpolated input patch of node n  (k = (ky 3 + kx) Cin + ci)
+//   d Wmat = P^T d x,  d bias = sum_n d x,  d P = d x Wmat^T                (plain products: the caller's library GEMM)
+//   d feat[b, ci, y_t + ky - 1, x_t + kx - 1] += ly[t] lx[t] d P[n][k]     (this file)
+// pgmp_gc_gather_conv_patches writes P with the forward's arithmetic; pgmp_gc_gather_conv_backward scatters d P into
+// the (zero-filled) map WITHOUT atomics: one CTA per image walks its nodes in node order, the threads of the CTA own
+// the 16 x Cin (neighbourhood position, channel) pairs of the current node -- different addresses within a node,
+// nodes strictly one after the other -- so colliding neighbourhoods are summed in a fixed order.
+// ------------------------------------------------------------------------------------------------
+namespace pgmp {
+namespace {
+
+__global__ void __launch_bounds__(256) gather_conv_patches_kernel(const GatherConvArgs a, float* __restrict__ patches) {
+  const int K = 9 * a.cin;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n * K) return;
+  const int64_t n = i / K;
+  const int k = (int)(i - n * K), ci = k % a.cin, kk = k / a.cin, ky = kk / 3, kx = kk - 3 * ky;
+  int y0, y1, x0, x1;
+  float ly[2], lx[2];
+  bilinear_tap((int)a.joint_det[n * 3 + 1], a.h, a.out_h, y0, y1, ly[0], ly[1]);
+  bilinear_tap((int)a.joint_det[n * 3 + 0], a.w, a.out_w, x0, x1, lx[0], lx[1]);
+  const float* __restrict__ f = a.feat + a.batch_index[n] * a.sb + ci * a.sc;
+  float p = 0.f;
+#pragma unroll
+  for (int ty = 0; ty < 2; ++ty)
+#pragma unroll
+    for (int tx = 0; tx < 2; ++tx) {
+      const int yy = (ty ? y1 : y0) + ky - 1, xx = (tx ? x1 : x0) + kx - 1;
+      const float v = ((unsigned)yy < (unsigned)a.h && (unsigned)xx < (unsigned)a.w) ? __ldg(f + yy * a.sy + xx * a.sx) : 0.f;
+      p = __fadd_rn(p, __fmul_rn(__fmul_rn(ly[ty], lx[tx]), v));
+    }
+  patches[i] = p;
+}
+
+__global__ void __launch_bounds__(512) gather_conv_scatter_kernel(const GatherConvArgs a, const float* __restrict__ d_patches,
+                                                                   float* __restrict__ df) {
+  const int b = blockIdx.x;
+  // this image's nodes [first, last): batch_index ascends
+  int64_t lo = 0, hi = a.n;
+  while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (a.batch_index[mid] < b) lo = mid + 1; else hi = mid; }
+  const int64_t first = lo;
+  hi = a.n;
+  while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (a.batch_index[mid] <= b) lo = mid + 1; else hi = mid; }
+  const int64_t last = lo;
+  const int K = 9 * a.cin, pairs = 16 * a.cin;
+  float* __restrict__ plane = df + (int64_t)b * a.sb;
+  for (int64_t n = first; n < last; ++n) {
+    int y0, y1, x0, x1;
+    float ly[2], lx[2];
+    bilinear_tap((int)a.joint_det[n * 3 + 1], a.h, a.out_h, y0, y1, ly[0], ly[1]);
+    bilinear_tap((int)a.joint_det[n * 3 + 0], a.w, a.out_w, x0, x1, lx[0], lx[1]);
+    const int dy = y1 - y0, dx = x1 - x0;
+    const float* __restrict__ dp = d_patches + n * K;
+    for (int i = threadIdx.x; i < pairs; i += blockDim.x) {
+      const int ci = i % a.cin, pos = i / a.cin, py = pos >> 2, px = pos & 3;
+      const int yy = y0 - 1 + py, xx = x0 - 1 + px;
+      if ((unsigned)yy >= (unsigned)a.h || (unsigned)xx >= (unsigned)a.w) continue;   // the convolution's zero padding
+      float c = 0.f;
+      bool any = false;
+#pragma unroll
+      for (int ty = 0; ty < 2; ++ty)
+#pragma unroll
+        for (int tx = 0; tx < 2; ++tx) {
+          const int ky = py - (ty ? dy : 0), kx = px - (tx ? dx : 0);
+          if ((unsigned)ky < 3u && (unsigned)kx < 3u) {
+            c = __fadd_rn(c, __fmul_rn(__fmul_rn(ly[ty], lx[tx]), dp[(ky * 3 + kx) * a.cin + ci]));
+            any = true;
+          }
+        }
+      if (any) {
+        float* __restrict__ q = plane + ci * a.sc + yy * a.sy + xx * a.sx;
+        *q = __fadd_rn(*q, c);
+      }
+    }
+    __syncthreads();        // the next node may touch the same pixels
+  }
+}
+
+int fill_gather_conv_args(const pgmp_gather_conv_params* p, GatherConvArgs& a) {
+  if (!p) return set_error(PGMP_ERR_INVALID, "null params");
+  if (p->num_nodes < 0 || p->cin <= 0 || p->height <= 0 || p->width <= 0 || p->out_height <= 0 || p->out_width <= 0)
+    return set_error(PGMP_ERR_INVALID, "bad sizes");
+  if (p->num_nodes > 0 && (!p->features || !p->joint_det || !p->batch_index)) return set_error(PGMP_ERR_INVALID, "null pointer");
+  a.feat = p->features; a.sb = p->feat_stride_b; a.sc = p->feat_stride_c; a.sy = p->feat_stride_y; a.sx = p->feat_stride_x;
+  a.cin = p->cin; a.h = p->height; a.w = p->width; a.cout = p->cout; a.out_h = p->out_height; a.out_w = p->out_width;
+  a.wmat = p->weight_t; a.bias = p->bias; a.joint_det = p->joint_det; a.batch_index = p->batch_index; a.n = p->num_nodes;
+  a.x = p->x; a.w_in_smem = 0;
+  return PGMP_OK;
+}
+
+}  // namespace
+}  // namespace pgmp
+
+extern "C" int pgmp_gc_gather_conv_patches(const pgmp_gather_conv_params* p, float* patches, pgmp_stream_t stream) {
+  using namespace pgmp;
+  GatherConvArgs a;
+  const int rc = fill_gather_conv_args(p, a);
+  if (rc != PGMP_OK) return rc;
+  if (a.n == 0) return PGMP_OK;
+  if (!patches) return set_error(PGMP_ERR_INVALID, "null pointer");
+  const int64_t total = a.n * 9 * a.cin;
+  PGMP_LAUNCH(gather_conv_patches_kernel, (unsigned)ceil_div<int64_t>(total, 256), 256, 0, static_cast<cudaStream_t>(stream), a, patches);
+  return PGMP_OK;
+}
+
+extern "C" int pgmp_gc_gather_conv_backward(const pgmp_gather_conv_params* p, const float* d_patches, int32_t batch,
+                                            float* d_features, pgmp_stream_t stream) {
+  using namespace pgmp;
+  GatherConvArgs a;
+  const int rc = fill_gather_conv_args(p, a);
+  if (rc != PGMP_OK) return rc;
+  if (a.n == 0 || batch <= 0) return PGMP_OK;
+  if (!d_patches || !d_features) return set_error(PGMP_ERR_INVALID, "null pointer");
+  PGMP_LAUNCH(gather_conv_scatter_kernel, (unsigned)batch, 512, 0, static_cast<cudaStream_t>(stream), a, d_patches, d_features);
+  return PGMP_OK;
+}

@@ -38,6 +38,50 @@ class _GatherNodeFeatures(torch.autograd.Function):
         return g, None, None, None
 
 
+class _GatherConvFeatures(torch.autograd.Function):
+    """``ConvUpsampleFeatures`` under autograd (end-to-end training, train.py:232): the forward is the fused CUDA kernel
+    inside ``construct_graph``; the reverse pass returns the gradients of the backbone map, of the ``feature_gather``
+    weight and of its bias.  ``x = bias + P W`` with the interpolated input patches ``P [N, 9 Cin]``: ``d W = P^T d x`` and
+    ``d P = d x W^T`` are plain fp32 library products, the patches and the transposed interpolation back into the map are
+    ``pgmp_gc_gather_conv_patches`` / ``pgmp_gc_gather_conv_backward`` (no atomics, fixed summation order)."""
+
+    @staticmethod
+    def forward(ctx, feat, weight, bias, x_out, batch_index, joint_det, size):
+        ctx.save_for_backward(feat, weight, batch_index, joint_det)
+        ctx.size = size
+        return x_out.view_as(x_out)
+
+    @staticmethod
+    def backward(ctx, grad):
+        feat, weight, batch_index, joint_det = ctx.saved_tensors
+        lib = nv.lib()
+        gx = grad.contiguous().float()
+        N, (cout, cin) = gx.shape[0], weight.shape[:2]
+        fm = feat.detach()
+
+        def params(t):
+            return nv.GatherConvParams(
+                features=t.data_ptr(), feat_stride_b=t.stride(0), feat_stride_c=t.stride(1), feat_stride_y=t.stride(2),
+                feat_stride_x=t.stride(3), cin=cin, height=fm.shape[2], width=fm.shape[3], cout=cout, out_height=ctx.size[0],
+                out_width=ctx.size[1], joint_det=joint_det.data_ptr(), batch_index=batch_index.data_ptr(), num_nodes=N)
+
+        d_feat = d_weight = d_bias = None
+        with torch.cuda.device(gx.device):
+            if ctx.needs_input_grad[1]:
+                patches = torch.empty((N, 9 * cin), dtype=torch.float32, device=gx.device)
+                nv.check(lib.pgmp_gc_gather_conv_patches(params(fm), patches.data_ptr(), nv.current_stream()))
+                d_weight = (patches.t() @ gx).view(3, 3, cin, cout).permute(3, 2, 0, 1).contiguous()
+            if ctx.needs_input_grad[2]:
+                d_bias = gx.sum(0)
+            if ctx.needs_input_grad[0]:
+                wt = weight.detach().float().permute(2, 3, 1, 0).reshape(9 * cin, cout)      # [(ky, kx, ci), co]
+                d_patches = (gx @ wt.t()).contiguous()
+                d_feat = torch.zeros(fm.shape, dtype=torch.float32, device=gx.device)
+                nv.check(lib.pgmp_gc_gather_conv_backward(params(d_feat), d_patches.data_ptr(), fm.shape[0], d_feat.data_ptr(),
+                                                          nv.current_stream()))
+        return d_feat, d_weight, d_bias, None, None, None, None
+
+
 def _host_resident(t, need_contiguous=False):
     """A pinned fp32 host tensor the gather kernels can read in place (no gradient flows into it)."""
     return (t is not None and t.device.type == "cpu" and t.is_pinned() and t.dtype == torch.float32
@@ -54,7 +98,9 @@ class ConvUpsampleFeatures:
     ``feat``: ``[B, Cin, h, w]`` float32, CUDA or pinned host.  ``conv``: the model's ``feature_gather``
     (``nn.Conv2d(Cin, Cout <= 128, 3, 1, 1)``) or a ``(weight [Cout,Cin,3,3], bias [Cout])`` pair.  ``size``: the
     ``(H, W)`` the reference interpolates to (the heatmap size; equal to ``(h, w)`` in the training ``forward``).
-    Inference only: no gradient flows to ``feat`` or the convolution.
+    Under autograd (``feat`` or the convolution's parameters require a gradient) the reverse pass is native too
+    (``_GatherConvFeatures``): the ``[B, Cout, H, W]`` maps are not materialised in training either, and the
+    ``feature_gather`` gradients join the MPN's in ``parallel.allreduce_gradients``.
     """
 
     def __init__(self, feat, conv, size):
@@ -399,6 +445,9 @@ class NaiveGraphConstructor:
             ws.record_stream(torch.cuda.current_stream())
         if feat is not None and not fused and feat.requires_grad and torch.is_grad_enabled():
             x = _GatherNodeFeatures.apply(feat, x, batch_index, joint_det)
+        if fused and N > 0 and torch.is_grad_enabled() and (
+                feat.feat.requires_grad or feat.weight.requires_grad or (feat.bias is not None and feat.bias.requires_grad)):
+            x = _GatherConvFeatures.apply(feat.feat, feat.weight, feat.bias, x, batch_index, joint_det, (H, W))
         if self.joints_gt is None:
             # the reference's 15-tuple (ConstructGraph.py:248-249); label slots are None at inference (:243-246)
             return (x, edge_attr, edge_index, None, None, None, None, joint_det, None, None, None, joint_scores,

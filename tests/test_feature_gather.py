@@ -102,4 +102,74 @@ def test_graph_constructor_with_lazy_features_equals_materialised_features():
         for i in (1, 2, 7, 11, 12, 14):
             assert torch.equal(got[i], want[i]), i
         assert got[0].shape == want[0].shape
-        assert_close(got[0].cpu().numpy(), want[0].cpu().numpy(), FP32_TOL, "x: lazy vs materialised features")
+        assert got[0].requires_grad                       # the convolution's parameters require gradients: x carries them on
+        assert_close(got[0].detach().cpu().numpy(), want[0].cpu().numpy(), FP32_TOL, "x: lazy vs materialised features")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 8, 16, 16, 16, 32, 32), (2, 32, 20, 28, 64, 20, 28), (1, 5, 7, 9, 16, 21, 18)],
+                         ids=["x2", "same_size", "x3_odd"])
+def test_lazy_features_reverse_pass_matches_torch_autograd(shape):
+    """Training end to end through ConvUpsampleFeatures: gradients of the backbone map, the feature_gather weight and bias
+    from the native reverse pass (_GatherConvFeatures) against torch autograd through the reference's own operations
+    (conv2d + interpolate + gather, fp32, TF32 off); overlapping neighbourhoods, image corners, duplicate pixels; the
+    reverse pass is bit-reproducible (no atomics)."""
+    from pgmp_b200.graph_constructor import _GatherConvFeatures
+    import pgmp_b200._native as nv
+    B, cin, h, w, cout, H, W = shape
+    feat, wt, bias, jd, bi = _case(5, B, cin, h, w, cout, H, W, 77)
+    jd[5:9] = jd[4]                                           # several candidates at one pixel
+    coeff = np.random.default_rng(3).standard_normal((jd.shape[0], cout)).astype(np.float32)
+    t = lambda a: torch.from_numpy(a).to(DEV)
+    jd_t, bi_t, c_t = t(jd), t(bi), t(coeff)
+
+    tf32c, tf32m = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        f0, w0, b0 = t(feat).requires_grad_(True), t(wt).requires_grad_(True), t(bias).requires_grad_(True)
+        full = torch.nn.functional.conv2d(f0, w0, b0, 1, 1)
+        if (H, W) != (h, w):
+            full = torch.nn.functional.interpolate(full, size=(H, W), mode="bilinear", align_corners=False)
+        (full[bi_t, :, jd_t[:, 1], jd_t[:, 0]] * c_t).sum().backward()
+
+        grads = []
+        for _ in range(2):
+            f1, w1, b1 = t(feat).requires_grad_(True), t(wt).requires_grad_(True), t(bias).requires_grad_(True)
+            x = torch.empty((jd.shape[0], cout), device=DEV)
+            wt_t = w1.detach().permute(2, 3, 1, 0).reshape(-1, cout).contiguous()
+            p = nv.GatherConvParams(features=f1.data_ptr(), feat_stride_b=f1.stride(0), feat_stride_c=f1.stride(1),
+                                    feat_stride_y=f1.stride(2), feat_stride_x=f1.stride(3), cin=cin, height=h, width=w, cout=cout,
+                                    out_height=H, out_width=W, weight_t=wt_t.data_ptr(), bias=b1.data_ptr(),
+                                    joint_det=jd_t.data_ptr(), batch_index=bi_t.data_ptr(), num_nodes=jd.shape[0], x=x.data_ptr())
+            nv.check(nv.lib().pgmp_gc_gather_conv(p, nv.current_stream()))
+            (_GatherConvFeatures.apply(f1, w1, b1, x, bi_t, jd_t, (H, W)) * c_t).sum().backward()
+            grads.append((f1.grad.clone(), w1.grad.clone(), b1.grad.clone()))
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32c, tf32m
+    for got, want, name in zip(grads[0], (f0.grad, w0.grad, b0.grad), ("d feat", "d weight", "d bias")):
+        assert got.shape == want.shape
+        assert_close(got.cpu().numpy(), want.cpu().numpy(), 2e-5, name + ": native reverse pass vs torch autograd")
+    for a, b in zip(grads[0], grads[1]):
+        assert torch.equal(a, b)                             # fixed summation order
+
+
+@pytest.mark.gpu
+def test_graph_constructor_trains_through_lazy_features():
+    """construct_graph() with ConvUpsampleFeatures whose parameters require gradients returns an x that back-propagates
+    into the backbone map and the convolution (PoseEstimation.py:64-66 under train.py:232)."""
+    from pgmp_b200.graph_constructor import ConvUpsampleFeatures, get_graph_constructor
+    B, J, S, K = 2, 17, 128, 10
+    sm = torch.from_numpy(np.stack([synthetic.synth_scoremap(b, J, S, K) for b in range(B)])).to(DEV)
+    backbone = torch.randn(B, 32, S, S, device=DEV).requires_grad_(True)
+    conv = torch.nn.Conv2d(32, 128, 3, 1, 1).to(DEV)
+    gcfg = pgmp_b200.config.bench_gc_config(k=K, graph_type="knn")
+    ret = get_graph_constructor(gcfg, scoremaps=sm, tagmaps=None, features=ConvUpsampleFeatures(backbone, conv, (S, S)),
+                                joints_gt=None, factor_list=None, masks=None, device=DEV, testing=True, heatmaps=None,
+                                num_joints=J).construct_graph()
+    x = ret[0]
+    assert x.requires_grad
+    x.square().sum().backward()
+    assert backbone.grad is not None and conv.weight.grad is not None and conv.bias.grad is not None
+    assert float(backbone.grad.abs().sum()) > 0 and float(conv.weight.grad.abs().sum()) > 0
+    touched = (backbone.grad.abs().sum(1) > 0).sum().item()
+    assert touched <= 9 * x.shape[0]                         # only the 3 x 3 neighbourhoods of the candidates (same size: one tap)
