@@ -173,11 +173,42 @@ def run_reference(args, rank, world):
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler(threading.Thread):
-    def __init__(self, index):
+    """SM clock and throttle reasons of this rank's GPU, sampled DURING the timed region.  In-process NVML calls
+    (nvidia_ml_py, ~50 us each, every 20 ms): spawning `nvidia-smi` instead forks this process -- gigabytes of pinned
+    mappings -- inside the timed region and holds the interpreter lock while it does (measured at 2 GPUs: the pipelined
+    loop, whose host thread must keep launching, ran 4.7 ms per step with the fork in it against 4.0 ms for the serial
+    loop without).  `nvidia-smi` remains the fallback when NVML cannot be loaded."""
+
+    def __init__(self, index, pci_bus_id=None):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], threading.Event()
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = (pynvml.nvmlDeviceGetHandleByPciBusId(pci_bus_id.encode()) if pci_bus_id
+                           else pynvml.nvmlDeviceGetHandleByIndex(index))
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
     def run(self):
+        if self.nvml is not None:
+            nv_ = self.nvml
+            bits = (0x8, 0x40, 0x20, 0x4)        # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
+            while not self.stop_flag.is_set():
+                try:
+                    sm = nv_.nvmlDeviceGetClockInfo(self.handle, nv_.NVML_CLOCK_SM)
+                    try:
+                        why = nv_.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                    except Exception:
+                        why = nv_.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                    self.rows.append([str(sm), str(self.max_sm)] + ["Active" if why & b else "Not Active" for b in bits])
+                except Exception:
+                    pass
+                self.stop_flag.wait(0.02)
+            return
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self.stop_flag.is_set():
@@ -200,7 +231,7 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+                "samples": len(self.rows), "source": "nvml (in process)" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -307,7 +338,8 @@ def run_b200(args, rank, local_rank, world):
     nodes_per_step = int(ret[0].shape[0])
 
     # ---- timed region 1: inputs resident in HBM, K batches through the pipelined API
-    sampler = ClockSampler(local_rank)
+    pr_ = torch.cuda.get_device_properties(local_rank)
+    sampler = ClockSampler(local_rank, "%08X:%02X:%02X.0" % (pr_.pci_domain_id, pr_.pci_bus_id, pr_.pci_device_id))
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
