@@ -529,7 +529,8 @@ def run_b200(args, rank, local_rank, world):
         del feat, tags, sm
         torch.cuda.empty_cache()
         r = bt.run_training(bt.parse(["--steps", "5", "--warmup", "3"]), rank, world, dev)
-        keys = ("value", "unit", "ms_per_step", "ms", "ms_median", "value_median", "edges_per_s", "config", "allreduce_bytes", "gpu_launches")
+        keys = ("value", "unit", "ms_per_step", "ms", "ms_median", "value_median", "edges_per_s", "config", "allreduce_bytes",
+                "trained_parameters", "node_features", "gpu_launches")
         if rank == 0:
             train = {k: r[k] for k in keys}
         # the same step with the flagship per-type / attention layer (TypeAwareMPNLayer, the hybrid_* configs)

@@ -40,6 +40,9 @@ def parse(argv=None):
     ap.add_argument("--mpn-steps", type=int, default=10)
     ap.add_argument("--model", choices=("agnostic", "flagship"), default="agnostic",
                     help="agnostic = class_agnostic_end2end (BASELINE configs[4]); flagship = the per-type / attention layer (hybrid_*)")
+    ap.add_argument("--materialised-features", action="store_true",
+                    help="node features gathered from a given [B,128,H,W] map (no feature_gather parameters in the step); default: "
+                         "ConvUpsampleFeatures over a 32-channel backbone map, the feature_gather gradients join the all-reduce")
     ap.add_argument("--profile", action="store_true", help="after the timed steps: one more step with per-kernel CUDA events")
     return ap.parse_args(argv)
 
@@ -55,7 +58,18 @@ def run_training(args, rank, world, dev):
     gcfg = pgmp_b200.config.bench_gc_config(k=K, graph_type="knn", EDGE_LABEL_METHOD=6, MATCHING_RADIUS=0.5)
     mcfg = (pgmp_b200.config.flagship_mpn_config if args.model == "flagship" else pgmp_b200.config.agnostic_mpn_config)(J, STEPS=args.mpn_steps)
     model = synthetic.synth_mpn_state_dict(get_mpn_model(mcfg), 0).to(dev).train()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    # the MPN's 101 203 (agnostic) parameters + the 36 992 of feature_gather (Conv2d(32, 128, 3, 1, 1),
+    # PoseEstimation.py:64-66) are trained and all-reduced; the HRNet backbone stays out (its 32-channel map is an input)
+    params = list(model.parameters())
+    features = t["features"]
+    if not args.materialised_features:
+        from pgmp_b200.graph_constructor import ConvUpsampleFeatures
+        torch.manual_seed(7)
+        feature_gather = torch.nn.Conv2d(32, features.shape[1], 3, 1, 1).to(dev)
+        backbone_map = torch.randn(args.batch, 32, args.size, args.size, device=dev,
+                                   generator=torch.Generator(device=dev).manual_seed(100 + rank))
+        params += list(feature_gather.parameters())
+    opt = torch.optim.Adam(params, lr=1e-4)
     gen = torch.Generator(device=dev).manual_seed(rank)
     ev = {k: [torch.cuda.Event(enable_timing=True) for _ in range(2)] for k in ("gc", "fwd", "loss", "bwd", "ar", "opt", "step")}
     acc = {k: 0.0 for k in ev}
@@ -65,7 +79,8 @@ def run_training(args, rank, world, dev):
     def step(timed):
         ev["step"][0].record()
         ev["gc"][0].record()
-        ret = get_graph_constructor(gcfg, scoremaps=t["scoremaps"], tagmaps=t["tagmaps"], features=t["features"],
+        feats = features if args.materialised_features else ConvUpsampleFeatures(backbone_map, feature_gather, (args.size, args.size))
+        ret = get_graph_constructor(gcfg, scoremaps=t["scoremaps"], tagmaps=t["tagmaps"], features=feats,
                                     joints_gt=joints_gt, factor_list=factors, masks=None, device=dev, testing=False,
                                     heatmaps=None, num_joints=J).construct_graph()
         x, edge_attr, edge_index, joint_det = ret[0], ret[1], ret[2], ret[7]
@@ -87,7 +102,8 @@ def run_training(args, rank, world, dev):
         loss.backward()
         ev["bwd"][1].record()
         ev["ar"][0].record()
-        info["allreduce_bytes"] = par.allreduce_gradients(model.parameters())
+        info["allreduce_bytes"] = par.allreduce_gradients(params)
+        info["trained_parameters"] = sum(p.numel() for p in params)
         ev["ar"][1].record()
         ev["opt"][0].record()
         opt.step()
@@ -125,6 +141,9 @@ def run_training(args, rank, world, dev):
                                       args.mpn_steps),
                        "nodes_per_gpu": info["nodes"], "edges_per_gpu": info["edges"]},
             "dtype": "f32", "data": "synthetic", "scaling": "weak", "allreduce_bytes": info["allreduce_bytes"],
+            "trained_parameters": info["trained_parameters"],
+            "node_features": "gathered from a given map" if args.materialised_features else
+                             "ConvUpsampleFeatures (feature_gather conv + interpolation at the candidates, trained)",
             "gpu_launches": launches, "loss_first_last": [losses[0], losses[-1]]})
     if args.profile and rank == 0:
         import time
