@@ -1197,6 +1197,9 @@ int launch_nms(const pgmp_gc_params& p, const GcWorkspace& w, cudaStream_t st, c
   }
   const size_t smem = (size_t)kNmsRingRows * a.pitch * 4 + (size_t)(kNmsListCap + kNmsKeepCap) * 8 + 256 * 4 + 3 * kNmsStages * 8 + 64 +
                       (fuse ? (size_t)a.pitch * 16 + (size_t)2 * 2 * a.src_rows * fuse->w * 4 : 0);
+  if (smem > 227 * 1024)
+    return set_error(PGMP_ERR_INVALID, "NMS row ring of %zu bytes does not fit in shared memory (fused assembly of %d x %d maps from %d x %d: "
+                     "run pgmp_gc_assemble_scoremaps + pgmp_gc_detect)", smem, p.height, p.width, fuse ? fuse->h : 0, fuse ? fuse->w : 0);
   const dim3 grid(ceil_div(p.height, a.rows_per_cta) * xtiles, p.num_joints, p.batch);
   const int block = 32 * (bands * rw + 1 + (fuse ? kNmsFuseLoaders : 1));
 #define PGMP_NMS_LAUNCH3(RPW, V, M, F)                                                                                             \
