@@ -537,6 +537,15 @@ def run_b200(args, rank, local_rank, world):
         r = bt.run_training(bt.parse(["--steps", "5", "--warmup", "3", "--model", "flagship"]), rank, world, dev)
         if rank == 0:
             train["flagship"] = {k: r[k] for k in keys}
+        # ... and the agnostic step with its E-level forward products on tcgen05 (PGMP_TRAIN_TC=1, csrc/mpn_train_tc.cu:
+        # bf16 hi / lo operand pairs, 1e-5-level forward; the rows above use the 3xTF32 kernels the parity tests pin)
+        os.environ["PGMP_TRAIN_TC"] = "1"
+        try:
+            r = bt.run_training(bt.parse(["--steps", "5", "--warmup", "3"]), rank, world, dev)
+        finally:
+            os.environ.pop("PGMP_TRAIN_TC", None)
+        if rank == 0:
+            train["tc_forward"] = {k: r[k] for k in keys}
     except Exception as exc:      # the headline line must not depend on the training row
         train = dict(train or {}, error="%s: %s" % (type(exc).__name__, exc))
     if rank != 0:

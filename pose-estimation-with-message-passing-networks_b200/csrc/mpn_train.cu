@@ -18,6 +18,7 @@
 // fp32 SIMT; BatchNorm statistics accumulate in fp64.  Moving the E-level products to tcgen05 (bf16x3 operand images as in
 // mpn_tc.cu) is the next step.
 #include "common.cuh"
+#include "mpn_train_tc.cuh"
 
 namespace pgmp {
 namespace {
@@ -942,6 +943,18 @@ int launch_fwd(cudaStream_t st, const ASrc& a, int64_t M, const float* W, int ld
                const int64_t* idx2 = nullptr, int ldy = 0, int add1_ld = kD) {
   if (M <= 0) return PGMP_OK;
   FwdArgs g{a, M, src_width(a), O, W, ldw, coloff, bias, add1, idx1, add2, idx2, relu, Y, ldy ? ldy : O, add1_ld};
+  // PGMP_TRAIN_TC=1: the large 64-output products (the E-level ones) on the 5th-generation tensor cores, bf16x3 operand
+  // split (mpn_train_tc.cu); default: the 3xTF32 mma.sync kernels below, which the fp32-level parity tests pin
+  {
+    const char* env = getenv("PGMP_TRAIN_TC");
+    const bool blocks64 = a.s[0].w == kD && (a.n == 1 || a.s[1].w == kD);
+    if (env && atoi(env) != 0 && O == kD && M >= 4096 && blocks64 && vec_src(a) && vec_w(W, ldw, coloff, g.K) && al16(Y) &&
+        !(g.ldy & 3) && (!bias || al16(bias)) && (!add1 || (al16(add1) && !(add1_ld & 3))) && (!add2 || al16(add2))) {
+      LinFwdTc t{a.s[0].p, a.s[0].ld, a.n > 1 ? a.s[1].p : nullptr, a.n > 1 ? a.s[1].ld : 0, M, W, ldw, coloff, bias,
+                 add1, idx1, add1_ld, add2, idx2, relu, Y, g.ldy};
+      return launch_lin_fwd_tc(st, t);
+    }
+  }
   const dim3 grid(blocks_for(M, BM), (unsigned)ceil_div(O, BN));
   if (vec_src(a) && vec_w(W, ldw, coloff, g.K))
     PGMP_LAUNCH(lin_fwd_kernel<true>, grid, 256, 0, st, g);

@@ -266,3 +266,31 @@ def test_gather_gradient_reaches_the_feature_maps():
                                  masks=None, device=DEV, testing=False, heatmaps=None, num_joints=J).construct_graph()
     (ret2[0] * torch.from_numpy(coeff).to(DEV)).sum().backward()
     assert np.array_equal(feat2.grad.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("name", ["agnostic_max", "max_fully_update_mlp", "pt_flagship"])
+def test_training_forward_products_on_tcgen05(name, monkeypatch):
+    """PGMP_TRAIN_TC=1: the E-level forward products run on the 5th-generation tensor cores (mpn_train_tc.cu, bf16 hi / lo
+    operand pairs, fp32 accumulation in tensor memory).  Logits within 1e-4 of the float64 oracle (the 3xTF32 default:
+    2e-5), gradients within the same bound as the default mode; the kernel must actually have run."""
+    import pgmp_b200._native as nv
+    monkeypatch.setenv("PGMP_TRAIN_TC", "1")
+    gc_name, over, seed, gtol = VARIANTS[name][:4]
+    g = graph_for(gc_name)
+    cfg = mpn_config_for(pgmp_b200.config, VARIANTS[name][4] if len(VARIANTS[name]) > 4 else "agnostic_mpn_config", over)
+    nv.profile(True)
+    model, sd0, x, pe, pn, pc, coeffs, loss = run_cuda(cfg, seed, g)
+    prof = nv.profile_collect()
+    nv.profile(False)
+    assert any(k.startswith("lin_fwd_tc_kernel") for k in prof), sorted(prof)
+    ope, opn, opc, oloss, ogx, ograds, ostats = T.loss_and_gradients(sd0, cfg, g["x"], g["edge_attr"], g["edge_index"],
+                                                                      g["joint_det"][:, 2], coeffs)
+    for i in range(len(ope)):
+        check(f"edge_{i}", pe[i], ope[i], 1e-4)
+        check(f"node_{i}", pn[i], opn[i], 1e-4)
+        check(f"class_{i}", pc[i], opc[i], 1e-4)
+    check_grad("grad_x", x.grad, ogx, gtol)
+    params = dict(model.named_parameters())
+    for pname, want in ograds.items():
+        if np.abs(want).max() >= 1e-9:
+            check_grad("grad " + pname, params[pname].grad, want, gtol)
