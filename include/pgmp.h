@@ -298,6 +298,8 @@ int pgmp_mpn_forward(const pgmp_mpn_params* p, pgmp_stream_t stream);
  * type-agnostic MPLayer (layers.py:32-86; AGGR max / add / mean, SKIP, USE_NODE_UPDATE_MLP), and the
  * reverse pass torch autograd runs for the reference (train.py:232-236): gradients of every
  * parameter and of the node input x.  fp32-accurate throughout (products: tensor cores with the 3xTF32 operand split; statistics in fp64).
+ * PGMP_TRAIN_TC=1 in the environment moves the E-level forward products to tcgen05 (bf16 hi / lo operand pairs, fp32
+ * accumulation in tensor memory: ~1e-5 relative instead of ~1e-6; csrc/mpn_train_tc.cu).
  *
  * Parameters and their gradients are two flat fp32 device buffers with the same element offsets;
  * every matrix keeps the layout of its nn.Linear.weight, [out][in].
