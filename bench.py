@@ -528,7 +528,7 @@ def run_b200(args, rank, local_rank, world):
         spec.loader.exec_module(bt)
         del feat, tags, sm
         torch.cuda.empty_cache()
-        r = bt.run_training(bt.parse(["--steps", "5", "--warmup", "3"]), rank, world, dev)
+        r = bt.run_training(bt.parse(["--steps", "10", "--warmup", "3"]), rank, world, dev)
         keys = ("value", "unit", "ms_per_step", "ms", "ms_median", "value_median", "edges_per_s", "config", "allreduce_bytes",
                 "trained_parameters", "node_features", "gpu_launches")
         if rank == 0:
