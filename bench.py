@@ -510,6 +510,29 @@ def run_b200(args, rank, local_rank, world):
                 assembly[nm] = {k: v[1] / args.steps for k, v in pa.items()
                                 if k.startswith("nms_candidates") or k.startswith("assemble") or k.startswith("stage_tags")}
                 assembly[nm]["ms"] = sum(assembly[nm].values())
+            # the whole path from the head's two stages (assembly + GC + MPN per batch through GroupingPipeline): the stages
+            # assembled by hr_process_output in front of the constructor, against HeadStages passed straight in
+            def whole_path(make_batch):
+                def run(k):
+                    for _ in pipe.run(make_batch() for _ in range(k)):
+                        pass
+                run(max(args.warmup, 3))
+                barrier()
+                ev0.record()
+                run(args.steps)
+                ev1.record()
+                barrier()
+                return ev0.elapsed_time(ev1) / args.steps
+
+            def batch_two():
+                score, _, tg = hr_process_output(((s1, sm), None), "avg", J)
+                return dict(scoremaps=score, tagmaps=tg, features=feat)
+
+            def batch_fused():
+                st = HeadStages((s1, sm), J)
+                return dict(scoremaps=st, tagmaps=st, features=feat)
+
+            assembly["whole_path_ms_per_step"] = {"assemble_then_pipeline": whole_path(batch_two), "head_stages_fused": whole_path(batch_fused)}
             rd = B * J * (SIZE * SIZE + (SIZE // 2) ** 2) * 4
             assembly["fused_bytes_read"] = rd
             assembly["fused_gbs"] = rd / assembly["fused"]["ms"] / 1e6
