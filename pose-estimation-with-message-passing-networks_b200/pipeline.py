@@ -5,9 +5,13 @@ output sizes of the graph constructor are data dependent, so one host read (the 
 detection half and everything after it; issued back to back, that read drains the stream once per batch and the ~60
 short launches that follow it start on an idle GPU.  ``GroupingPipeline`` keeps the drop-in API and hides the wait:
 the detection half of batch ``i + 1`` (NMS, candidates, kNN adjacency, counts) -- and, for pinned HOST heatmaps, its
-host-to-device copy -- is launched on a side stream before batch ``i`` is finished on the main stream, so by the time
-``construct_graph()`` needs the counts they have long arrived and the GPU never runs dry.  Every batch still does the
-full work; results are identical to the serial calls (same kernels, same order per batch).
+host-to-device copy -- is launched on a side stream before batch ``i`` is finished, so by the time
+``construct_graph()`` needs the counts they have long arrived and the GPU never runs dry.  Consecutive batches run
+their emit half and the network on two alternating compute streams (``interleave=True``): a batch is a dependent chain
+of ~45 kernels with a drain / fill bubble at every boundary, and the neighbouring batch's kernels fill those bubbles
+(measured: 3.50 -> 3.19 ms per 32-image batch); the caller's stream waits for a batch before it is handed out, so the
+results are used exactly as after the serial calls.  Every batch still does the full work; results are identical to the
+serial calls (same kernels, same order per batch).
 
     pipe = GroupingPipeline(gc_config, mpn, num_joints, device)
     for graph, (preds_edge, preds_node, preds_class) in pipe.run(batches):   # batches: dicts of construct_graph kwargs
@@ -25,11 +29,16 @@ from .graph_constructor import get_graph_constructor
 
 
 class GroupingPipeline:
-    def __init__(self, gc_config, model, num_joints, device, testing=True, group=None):
+    def __init__(self, gc_config, model, num_joints, device, testing=True, group=None, interleave=True):
         self.gc_config, self.model, self.num_joints = gc_config, model, num_joints
         self.device = torch.device(device)
         self.testing = testing
         self.side = torch.cuda.Stream(device=self.device)
+        # consecutive batches go through emit + network on two alternating streams: the ~45 kernels of a batch are a
+        # dependent chain with a drain / fill bubble at every boundary, and the neighbouring batch's kernels fill them
+        self.compute = [torch.cuda.Stream(device=self.device) for _ in range(2)] if (interleave and group is None) else None
+        self._count = 0
+        self._repacked = None                               # event after a batch that (re)built the model's packed weights
         self.group = dict(group) if group is not None else None
         self.group_stream = torch.cuda.Stream(device=self.device) if group is not None else None
 
@@ -40,12 +49,35 @@ class GroupingPipeline:
                                    features=batch.get("features"), joints_gt=None, factor_list=None,
                                    masks=batch.get("masks"), device=self.device, testing=self.testing, heatmaps=None,
                                    num_joints=self.num_joints)
-        if batch["scoremaps"].device.type == "cuda":        # produced on the main stream (the backbone): order after it
-            ev = torch.cuda.Event()
-            ev.record(main)
+        ev = torch.cuda.Event()                              # the inputs were produced on the main stream (the backbone)
+        ev.record(main)
+        gc._inputs_ready = ev
+        if batch["scoremaps"].device.type == "cuda":
             self.side.wait_event(ev)
         gc.detect_async(self.side)
         return gc
+
+    def _finish_interleaved(self, gc):
+        """``_finish`` on one of the two compute streams; the caller's stream waits for the batch before it is handed out."""
+        main = torch.cuda.current_stream(self.device)
+        cs = self.compute[self._count & 1]
+        self._count += 1
+        cs.wait_event(gc._inputs_ready)
+        if self._repacked is not None:                       # the other stream built the packed weights this batch reads
+            cs.wait_event(self._repacked)
+            self._repacked = None
+        cache = getattr(self.model, "_pack_cache", None)
+        with torch.cuda.stream(cs):
+            out = self._finish(gc)
+            done = torch.cuda.Event()
+            done.record(cs)
+        if getattr(self.model, "_pack_cache", None) is not cache:
+            self._repacked = done
+        main.wait_event(done)
+        for t in list(out[0]) + [x for lst in out[1] for x in lst]:
+            if torch.is_tensor(t) and t.device.type == "cuda":
+                t.record_stream(main)                        # allocated on the compute stream, consumed on the caller's
+        return out
 
     def _finish(self, gc):
         ret = gc.construct_graph()
@@ -70,7 +102,7 @@ class GroupingPipeline:
         for batch in batches:
             cur = self._submit(batch)
             if prev is not None:
-                out = self._finish(prev)
+                out = self._finish_interleaved(prev) if self.compute is not None else self._finish(prev)
                 if self.group is None:
                     yield out
                 else:
@@ -79,7 +111,7 @@ class GroupingPipeline:
                     waiting = out
             prev = cur
         if prev is not None:
-            out = self._finish(prev)
+            out = self._finish_interleaved(prev) if self.compute is not None else self._finish(prev)
             if self.group is None:
                 yield out
             else:
