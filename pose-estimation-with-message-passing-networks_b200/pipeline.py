@@ -36,7 +36,7 @@ class GroupingPipeline:
         self.side = torch.cuda.Stream(device=self.device)
         # consecutive batches go through emit + network on two alternating streams: the ~45 kernels of a batch are a
         # dependent chain with a drain / fill bubble at every boundary, and the neighbouring batch's kernels fill them
-        self.compute = [torch.cuda.Stream(device=self.device) for _ in range(2)] if (interleave and group is None) else None
+        self.compute = [torch.cuda.Stream(device=self.device) for _ in range(2)] if interleave else None
         self._count = 0
         self._repacked = None                               # event after a batch that (re)built the model's packed weights
         self.group = dict(group) if group is not None else None
